@@ -1,0 +1,261 @@
+/*
+ * islands_b200.h — C ABI of the B200-native LEANN / HNSW search hot path.
+ *
+ * This is the drop-in boundary for the `src/core` vector-index API of panbanda/islands
+ * (reference paths below are relative to the reference repository root).  Every entry
+ * point is `extern "C"`, takes plain pointers and sizes, and returns an `isl_status`
+ * that mirrors the reference's `CoreError` (src/core/error.rs:9-62).  No torch types,
+ * no C++ types, no exceptions cross this boundary.
+ *
+ * Conventions kept from the reference:
+ *   - empty index  -> search returns ISL_OK with zero results (leann.rs:875-877, hnsw.rs:459-461)
+ *   - ef := max(ef, k)                                       (leann.rs:890, hnsw.rs:500)
+ *   - results ascending by distance, at most k per query     (leann.rs:984-987, :895)
+ *   - ties are broken by (distance, id) — the order of the reference's own heaps
+ *     (leann.rs:701-702, :907-908) applied to the final sort as well
+ *   - search takes a const handle (reference: &self) and is re-entrant
+ *   - ids are u64 at the ABI (reference type); on the device they are u32 (n < 2^31)
+ *
+ * Host pointers are copied to / from the device inside the call.  Entry points with a
+ * `_dev` suffix take device pointers on the current CUDA device and do no host copies.
+ * All work is enqueued on an internal per-handle stream and the call returns after the
+ * stream has been synchronised (the `_async_dev` forms return right after the launch).
+ *
+ * There is NO CPU fallback: if no CUDA device is usable every compute entry point
+ * returns ISL_CUDA_ERROR and isl_last_error() says why.
+ */
+#ifndef ISLANDS_B200_H
+#define ISLANDS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ISL_ABI_VERSION 1
+#define ISL_NO_ENTRY (-1)
+#define ISL_INVALID_ID UINT64_MAX
+
+/* Mirrors CoreError (src/core/error.rs:9-62). */
+typedef enum isl_status {
+  ISL_OK = 0,
+  ISL_DIM_MISMATCH = 1,     /* CoreError::DimensionMismatch{expected,actual} */
+  ISL_EMPTY_COLLECTION = 2, /* CoreError::EmptyCollection */
+  ISL_INVALID_CONFIG = 3,   /* CoreError::InvalidConfig(String) */
+  ISL_INDEX_NOT_BUILT = 4,  /* CoreError::IndexNotBuilt */
+  ISL_NODE_NOT_FOUND = 5,   /* CoreError::NodeNotFound(u64) */
+  ISL_PQ_ERROR = 6,         /* CoreError::PQError(String) */
+  ISL_SERIALIZATION = 7,    /* CoreError::Serialization / Deserialization */
+  ISL_CUDA_ERROR = 8,       /* no reference analogue: device failure, never a fallback */
+  ISL_INVALID_ARGUMENT = 9  /* null pointer / out-of-range argument at the ABI */
+} isl_status;
+
+/* DistanceMetric (src/core/distance.rs:9-19); values = serde variant index. */
+typedef enum isl_metric {
+  ISL_METRIC_COSINE = 0,
+  ISL_METRIC_EUCLIDEAN = 1,
+  ISL_METRIC_DOT = 2,
+  ISL_METRIC_MANHATTAN = 3
+} isl_metric;
+
+/* PruningStrategy (src/core/leann.rs:168-178). */
+typedef enum isl_pruning_strategy {
+  ISL_PRUNE_GLOBAL = 0,
+  ISL_PRUNE_LOCAL = 1,
+  ISL_PRUNE_PROPORTIONAL = 2 /* thread_rng in the reference (leann.rs:1043): rejected here */
+} isl_pruning_strategy;
+
+/* LeannConfig (src/core/leann.rs:322-371), same field order. */
+typedef struct isl_leann_config {
+  uint64_t m;
+  uint64_t m0;
+  uint64_t ef_construction;
+  double ml;
+  uint64_t max_layers;
+  int32_t metric; /* isl_metric */
+  uint64_t ef_search;
+  uint64_t beam_width;
+  float prune_ratio;
+  int32_t pruning_strategy; /* isl_pruning_strategy */
+  int32_t high_degree_pruning;
+  float hub_percentile;
+  int32_t is_compact;
+  int32_t is_recompute;
+} isl_leann_config;
+
+/* HnswConfig (src/core/hnsw.rs:15-28). */
+typedef struct isl_hnsw_config {
+  uint64_t m;
+  uint64_t m0;
+  uint64_t ef_construction;
+  double ml;
+  int32_t metric;
+  uint64_t max_layers;
+} isl_hnsw_config;
+
+/* PQConfig (src/core/pq.rs:13-22); seed < 0 means None. */
+typedef struct isl_pq_config {
+  uint64_t num_subquantizers;
+  uint64_t num_centroids;
+  uint64_t training_iterations;
+  int64_t seed;
+} isl_pq_config;
+
+/* Per-query traversal counters (the reference counts `embeddings_computed`, leann.rs:920,950).
+ * n_hop   = expanded candidates (loop iterations that reached the neighbour fetch)
+ * n_edge  = neighbour ids read
+ * n_dist  = exact distances evaluated (entry included)
+ * n_adc   = PQ table distances evaluated (two-level search only)
+ * n_rerank= exact distances evaluated for promoted nodes (two-level search only; subset of n_dist) */
+typedef struct isl_search_stats {
+  uint64_t n_hop;
+  uint64_t n_edge;
+  uint64_t n_dist;
+  uint64_t n_adc;
+  uint64_t n_rerank;
+} isl_search_stats;
+
+typedef struct isl_index isl_index; /* LeannIndex + CsrGraph + resident vectors (leann.rs:193-208, :493-500) */
+typedef struct isl_pq isl_pq;       /* ProductQuantizer (pq.rs:116-129) */
+typedef struct isl_hnsw isl_hnsw;   /* HnswGraph (hnsw.rs:151-164) */
+
+/* ---- library ---------------------------------------------------------------------- */
+int isl_abi_version(void);
+/* Thread-local message of the last failing call on this thread (String payloads of CoreError). */
+const char* isl_last_error(void);
+/* Number of usable CUDA devices (0 => every compute call fails with ISL_CUDA_ERROR). */
+int isl_device_count(void);
+/* Launch bookkeeping for benchmarks: kernels launched by this library since the last reset. */
+uint64_t isl_kernel_launch_count(void);
+void isl_kernel_launch_count_reset(void);
+
+/* ---- configs (leann.rs:373-461, hnsw.rs:37-85, pq.rs:24-65) ---------------------- */
+isl_status isl_leann_config_default(isl_leann_config* out);  /* paper_default(): m=30,m0=60,efC=128 */
+isl_status isl_leann_config_fast(isl_leann_config* out);     /* leann.rs:406-416 */
+isl_status isl_leann_config_accurate(isl_leann_config* out); /* leann.rs:419-429 */
+isl_status isl_leann_config_validate(const isl_leann_config* cfg);
+isl_status isl_hnsw_config_default(isl_hnsw_config* out);
+isl_status isl_hnsw_config_validate(const isl_hnsw_config* cfg);
+isl_status isl_pq_config_default(isl_pq_config* out);
+isl_status isl_pq_config_validate(const isl_pq_config* cfg, uint64_t dimension);
+uint64_t isl_pq_config_bytes_per_vector(const isl_pq_config* cfg); /* pq.rs:58-64 */
+
+/* ---- distances (src/core/distance.rs) --------------------------------------------- */
+/* Distance::calculate (distance.rs:37-52): one pair; len_a != len_b -> ISL_DIM_MISMATCH. */
+isl_status isl_distance_calculate(int32_t metric, const float* a, uint64_t len_a, const float* b,
+                                  uint64_t len_b, float* out);
+/* Distance::calculate_squared (distance.rs:54-66). */
+isl_status isl_distance_calculate_squared(int32_t metric, const float* a, uint64_t len_a,
+                                          const float* b, uint64_t len_b, float* out);
+/* Distance::batch_calculate (distance.rs:32-34): rows is [n_rows][dim] row-major. */
+isl_status isl_distance_batch(int32_t metric, const float* query, const float* rows,
+                              uint64_t n_rows, uint32_t dim, float* out);
+isl_status isl_distance_batch_dev(int32_t metric, const float* d_query, const float* d_rows,
+                                  uint64_t n_rows, uint32_t dim, float* d_out);
+/* normalize_vector (distance.rs:125-132) applied to each of n_rows rows in place. */
+isl_status isl_normalize_rows(float* rows, uint64_t n_rows, uint32_t dim);
+
+/* ---- LEANN index (src/core/leann.rs) ----------------------------------------------- */
+/* Adopt an existing CSR graph ("identical graphs" entry): CsrGraph fields (leann.rs:193-208)
+ * node_offsets [n+1], neighbors [node_offsets[n]], levels [n] (may be NULL -> zeros),
+ * entry_point (ISL_NO_ENTRY = None).  `vectors` [n][dim] are the embeddings the
+ * InMemoryEmbeddingProvider (leann.rs:104-159) would return; they are made resident in HBM. */
+isl_status isl_index_from_csr(const isl_leann_config* cfg, uint32_t dim, uint64_t n,
+                              const uint64_t* node_offsets, const uint64_t* neighbors,
+                              const uint64_t* levels, int64_t entry_point, const float* vectors,
+                              isl_index** out);
+/* LeannIndex::build (leann.rs:560-631).  levels_or_null: explicit per-node levels (the reference
+ * draws them from thread_rng, leann.rs:549-554); NULL -> drawn from `seed` with the same formula.
+ * batch = 1 reproduces the reference's sequential insertion order exactly; batch > 1 inserts
+ * `batch` nodes against one graph snapshot (GPU-parallel construction). */
+isl_status isl_index_build(const isl_leann_config* cfg, uint32_t dim, uint64_t n,
+                           const float* vectors, const uint64_t* levels_or_null, uint64_t seed,
+                           uint32_t batch, isl_index** out);
+isl_status isl_index_build_dev(const isl_leann_config* cfg, uint32_t dim, uint64_t n,
+                               const float* d_vectors, const uint64_t* levels_or_null,
+                               uint64_t seed, uint32_t batch, isl_index** out);
+void isl_index_free(isl_index* idx);
+uint64_t isl_index_len(const isl_index* idx);            /* LeannIndex::len */
+uint32_t isl_index_dimension(const isl_index* idx);      /* LeannIndex::dimension (0 = None) */
+uint64_t isl_index_num_edges(const isl_index* idx);      /* graph.neighbors.len() */
+int64_t isl_index_entry_point(const isl_index* idx);     /* graph.entry_point */
+uint64_t isl_index_max_level(const isl_index* idx);      /* graph.max_level */
+uint64_t isl_index_storage_bytes(const isl_index* idx);  /* CsrGraph::storage_bytes (leann.rs:296-301) */
+/* Copy the CSR arrays out; any pointer may be NULL.  node_offsets [n+1], neighbors [num_edges],
+ * levels [n], degree_counts [n]. */
+isl_status isl_index_export_csr(const isl_index* idx, uint64_t* node_offsets, uint64_t* neighbors,
+                                uint64_t* levels, uint64_t* degree_counts);
+/* CsrGraph::get_neighbors (leann.rs:225-233): returns count, writes up to cap ids;
+ * node_id >= n -> ISL_NODE_NOT_FOUND (reference: None). */
+isl_status isl_index_get_neighbors(const isl_index* idx, uint64_t node_id, uint64_t* out,
+                                   uint64_t cap, uint64_t* out_count);
+
+/* Batched LeannIndex::search_with_params (leann.rs:868-896) over nq queries [nq][dim].
+ * out_ids/out_dist are [nq][k], padded with ISL_INVALID_ID / +inf; out_count [nq];
+ * stats_or_null [nq].  query_dim != index dimension -> ISL_DIM_MISMATCH. */
+isl_status isl_index_search(const isl_index* idx, const float* queries, uint64_t nq,
+                            uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* out_ids,
+                            float* out_dist, uint32_t* out_count, isl_search_stats* stats_or_null);
+isl_status isl_index_search_dev(const isl_index* idx, const float* d_queries, uint64_t nq,
+                                uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
+                                float* d_out_dist, uint32_t* d_out_count,
+                                isl_search_stats* d_stats_or_null);
+/* LeannIndex::search (leann.rs:858-865): ef = config.ef_search. */
+isl_status isl_index_search_default(const isl_index* idx, const float* queries, uint64_t nq,
+                                    uint32_t query_dim, uint32_t k, uint64_t* out_ids,
+                                    float* out_dist, uint32_t* out_count);
+/* Duration in milliseconds (CUDA events on the handle's stream) of the search kernel of the
+ * last isl_index_search* call on this handle, and the algorithmic HBM bytes it moved. */
+isl_status isl_index_last_search_timing(const isl_index* idx, float* kernel_ms,
+                                        uint64_t* kernel_launches);
+
+/* ---- Product quantizer (src/core/pq.rs) -------------------------------------------- */
+isl_status isl_pq_new(uint32_t dimension, const isl_pq_config* cfg, isl_pq** out); /* pq.rs:133-149 */
+void isl_pq_free(isl_pq* pq);
+isl_status isl_pq_set_metric(isl_pq* pq, int32_t metric);                          /* with_metric, pq.rs:152-155 */
+int32_t isl_pq_is_trained(const isl_pq* pq);
+uint64_t isl_pq_num_subquantizers(const isl_pq* pq);
+float isl_pq_compression_ratio(const isl_pq* pq);                                   /* pq.rs:168-172 */
+/* ProductQuantizer::train (pq.rs:175-218): vectors [n][dimension]. */
+isl_status isl_pq_train(isl_pq* pq, const float* vectors, uint64_t n, uint32_t dim);
+/* Install codebooks trained elsewhere: [m][ksub][dsub]; marks the quantizer trained. */
+isl_status isl_pq_set_codebooks(isl_pq* pq, const float* codebooks, uint64_t num_centroids);
+isl_status isl_pq_get_codebooks(const isl_pq* pq, float* out, uint64_t* out_num_centroids);
+/* Batched ProductQuantizer::encode (pq.rs:221-244): codes [n][m] u16. */
+isl_status isl_pq_encode(const isl_pq* pq, const float* vectors, uint64_t n, uint32_t dim,
+                         uint16_t* out_codes);
+/* Batched decode (pq.rs:247-271): codes [n][codes_per_vector]; out [n][dimension]. */
+isl_status isl_pq_decode(const isl_pq* pq, const uint16_t* codes, uint64_t n,
+                         uint64_t codes_per_vector, float* out);
+/* build_distance_tables (pq.rs:307-338): tables [m][ksub]. */
+isl_status isl_pq_build_tables(const isl_pq* pq, const float* query, uint32_t dim, float* out_tables);
+/* table_distance (pq.rs:341-348) for n code rows against one table set. */
+isl_status isl_pq_table_distance(const isl_pq* pq, const float* tables, const uint16_t* codes,
+                                 uint64_t n, float* out);
+/* asymmetric_distance (pq.rs:275-304) for n code rows against one query. */
+isl_status isl_pq_asymmetric_distance(const isl_pq* pq, const float* query, uint32_t dim,
+                                      const uint16_t* codes, uint64_t n, float* out);
+
+/* ---- two-level search (docs/leann-specification.md:223-269; no reference code) ------ */
+/* Attach PQ codes [n][m] (u16 at the ABI) for ADC-carried traversal; rerank_ratio = `a`. */
+isl_status isl_index_attach_pq(isl_index* idx, const isl_pq* pq, const uint16_t* codes);
+isl_status isl_index_search_two_level(const isl_index* idx, const float* queries, uint64_t nq,
+                                      uint32_t query_dim, uint32_t k, uint32_t ef,
+                                      float rerank_ratio, uint64_t* out_ids, float* out_dist,
+                                      uint32_t* out_count, isl_search_stats* stats_or_null);
+
+/* ---- island / shard merge (search.rs:211-237, indexer/service.rs:775-801) ---------- */
+/* Per query, merge `parts` lists of k (dist,id) pairs laid out [parts][nq][k] into the k best
+ * by (dist, id); ISL_INVALID_ID entries are ignored. */
+isl_status isl_merge_topk(const uint64_t* ids, const float* dist, uint32_t parts, uint64_t nq,
+                          uint32_t k, uint64_t* out_ids, float* out_dist, uint32_t* out_count);
+isl_status isl_merge_topk_dev(const uint64_t* d_ids, const float* d_dist, uint32_t parts,
+                              uint64_t nq, uint32_t k, uint64_t* d_out_ids, float* d_out_dist,
+                              uint32_t* d_out_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISLANDS_B200_H */

@@ -1,0 +1,10 @@
+"""islands_b200 — B200-native (sm_100a) LEANN / HNSW search hot path behind the reference's
+`src/core` API.  Compute lives in lib/libislands_b200.so (C ABI: include/islands_b200.h);
+this package is the host-side mirror of the reference interface.  No CPU fallback."""
+from .core import (CoreError, CsrGraph, CudaError, DimensionMismatch, DistanceMetric, EmptyCollection,
+                   HnswConfig, IndexNotBuilt, InMemoryEmbeddingProvider, InvalidArgument, InvalidConfig,
+                   LeannConfig, LeannIndex, NodeNotFound, PQConfig, PQError, ProductQuantizer,
+                   PruningStrategy, SerializationError, merge_topk, normalize_vector, normalized,
+                   random_level, to_similarity)
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,575 @@
+"""Host-side mirror of the reference's `src/core` API for the search hot path.
+
+Same names, argument meaning and error behaviour as the Rust (paths relative to the reference):
+  DistanceMetric / Distance           src/core/distance.rs:7-67
+  CoreError variants                  src/core/error.rs:9-62
+  LeannConfig, LeannIndex, CsrGraph   src/core/leann.rs:193-302, 322-461, 493-1067
+  InMemoryEmbeddingProvider           src/core/leann.rs:104-159
+  PQConfig, ProductQuantizer          src/core/pq.rs:13-65, 116-359
+  MultiIndexSearcher-style merge      src/core/search.rs:211-237
+
+Everything here is argument marshalling over the C ABI (include/islands_b200.h); all compute
+runs in libislands_b200.so on the GPU.  numpy arrays in, numpy arrays out.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import (HnswConfigStruct, LeannConfigStruct, PQConfigStruct, SearchStatsStruct,
+                   f32p, u16p, u32p, u64p)
+
+
+# ---- errors (src/core/error.rs:9-62) ---------------------------------------------------------
+class CoreError(Exception):
+    status = -1
+
+
+class DimensionMismatch(CoreError):
+    status = 1
+
+
+class EmptyCollection(CoreError):
+    status = 2
+
+
+class InvalidConfig(CoreError):
+    status = 3
+
+
+class IndexNotBuilt(CoreError):
+    status = 4
+
+
+class NodeNotFound(CoreError):
+    status = 5
+
+
+class PQError(CoreError):
+    status = 6
+
+
+class SerializationError(CoreError):
+    status = 7
+
+
+class CudaError(CoreError):
+    status = 8
+
+
+class InvalidArgument(CoreError):
+    status = 9
+
+
+_ERRORS = {c.status: c for c in (DimensionMismatch, EmptyCollection, InvalidConfig, IndexNotBuilt,
+                                 NodeNotFound, PQError, SerializationError, CudaError, InvalidArgument)}
+
+
+def _check(status):
+    if status != _ffi.ISL_OK:
+        raise _ERRORS.get(status, CoreError)(_ffi.last_error())
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+# ---- distance.rs ------------------------------------------------------------------------------
+class DistanceMetric:
+    """DistanceMetric (distance.rs:9-19) + the Distance trait methods (distance.rs:22-67)."""
+
+    Cosine = 0
+    Euclidean = 1
+    DotProduct = 2
+    Manhattan = 3
+    _names = {0: "cosine", 1: "euclidean", 2: "dotproduct", 3: "manhattan"}
+
+    def __init__(self, value=0):
+        self.value = int(value)
+
+    def __eq__(self, other):
+        return int(getattr(other, "value", other)) == self.value
+
+    def __hash__(self):
+        return hash(self.value)
+
+    def __repr__(self):
+        return f"DistanceMetric.{self._names[self.value]}"
+
+    def calculate(self, a, b):
+        a, b = _f32(a), _f32(b)
+        out = C.c_float()
+        _check(_ffi.load().isl_distance_calculate(self.value, _ptr(a, f32p), a.size, _ptr(b, f32p), b.size,
+                                                  C.byref(out)))
+        return out.value
+
+    def calculate_squared(self, a, b):
+        a, b = _f32(a), _f32(b)
+        out = C.c_float()
+        _check(_ffi.load().isl_distance_calculate_squared(self.value, _ptr(a, f32p), a.size, _ptr(b, f32p),
+                                                          b.size, C.byref(out)))
+        return out.value
+
+    def batch_calculate(self, query, vectors):
+        query = _f32(query)
+        vectors = _f32(vectors)
+        if vectors.size == 0:
+            return np.zeros(0, np.float32)
+        vectors = vectors.reshape(-1, vectors.shape[-1])
+        if vectors.shape[1] != query.size:
+            raise DimensionMismatch(f"dimension mismatch: expected {query.size}, got {vectors.shape[1]}")
+        out = np.empty(vectors.shape[0], np.float32)
+        _check(_ffi.load().isl_distance_batch(self.value, _ptr(query, f32p), _ptr(vectors, f32p),
+                                              vectors.shape[0], query.size, _ptr(out, f32p)))
+        return out
+
+
+def normalize_vector(v):
+    """normalize_vector / normalized (distance.rs:125-139); returns a new array."""
+    a = _f32(v).copy()
+    rows = a.reshape(1, -1) if a.ndim == 1 else a
+    _check(_ffi.load().isl_normalize_rows(_ptr(rows, f32p), rows.shape[0], rows.shape[1]))
+    return a
+
+
+normalized = normalize_vector
+
+
+# ---- leann.rs ---------------------------------------------------------------------------------
+class PruningStrategy:
+    Global = 0
+    Local = 1
+    Proportional = 2
+
+
+class LeannConfig:
+    """LeannConfig (leann.rs:322-461)."""
+
+    _fields = [f[0] for f in LeannConfigStruct._fields_]
+
+    def __init__(self, **kw):
+        s = LeannConfigStruct()
+        _check(_ffi.load().isl_leann_config_default(C.byref(s)))
+        self._s = s
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    def __getattr__(self, name):
+        if name in LeannConfig._fields:
+            return getattr(self._s, name)
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        if name in LeannConfig._fields:
+            setattr(self._s, name, getattr(value, "value", value))
+        else:
+            object.__setattr__(self, name, value)
+
+    @classmethod
+    def paper_default(cls):
+        return cls()
+
+    @classmethod
+    def default(cls):
+        return cls()
+
+    @classmethod
+    def fast(cls):
+        c = cls()
+        _check(_ffi.load().isl_leann_config_fast(C.byref(c._s)))
+        return c
+
+    @classmethod
+    def accurate(cls):
+        c = cls()
+        _check(_ffi.load().isl_leann_config_accurate(C.byref(c._s)))
+        return c
+
+    def validate(self):
+        _check(_ffi.load().isl_leann_config_validate(C.byref(self._s)))
+
+
+class HnswConfig:
+    """HnswConfig (hnsw.rs:15-86)."""
+
+    _fields = [f[0] for f in HnswConfigStruct._fields_]
+
+    def __init__(self, **kw):
+        s = HnswConfigStruct()
+        _check(_ffi.load().isl_hnsw_config_default(C.byref(s)))
+        self._s = s
+        for k, v in kw.items():
+            setattr(self._s, k, getattr(v, "value", v))
+
+    def __getattr__(self, name):
+        if name in HnswConfig._fields:
+            return getattr(self._s, name)
+        raise AttributeError(name)
+
+    def validate(self):
+        _check(_ffi.load().isl_hnsw_config_validate(C.byref(self._s)))
+
+
+class InMemoryEmbeddingProvider:
+    """InMemoryEmbeddingProvider (leann.rs:104-159): id -> stored embedding."""
+
+    def __init__(self, embeddings):
+        e = _f32(embeddings)
+        if e.size == 0:
+            raise EmptyCollection("empty collection")
+        self.embeddings = e.reshape(-1, e.shape[-1])
+
+    def dimension(self):
+        return self.embeddings.shape[1]
+
+    def compute_embedding(self, id):
+        if id >= self.embeddings.shape[0]:
+            raise NodeNotFound(f"node {id} not found")
+        return self.embeddings[id].copy()
+
+    def compute_embeddings_batch(self, ids):
+        return np.stack([self.compute_embedding(i) for i in ids])
+
+
+class CsrGraph:
+    """CsrGraph (leann.rs:193-302): plain arrays in the reference's layout."""
+
+    def __init__(self):
+        self.node_offsets = np.zeros(1, np.uint64)
+        self.neighbors = np.zeros(0, np.uint64)
+        self.levels = np.zeros(0, np.uint64)
+        self.entry_point = None
+        self.max_level = 0
+        self.num_nodes = 0
+        self.degree_counts = np.zeros(0, np.uint64)
+
+    def get_neighbors(self, node_id):
+        if node_id >= self.num_nodes:
+            return None
+        s, e = int(self.node_offsets[node_id]), int(self.node_offsets[node_id + 1])
+        return self.neighbors[s:e]
+
+    def add_node(self, neighbors, level):
+        nid = self.num_nodes
+        self.num_nodes += 1
+        self.levels = np.append(self.levels, np.uint64(level))
+        self.degree_counts = np.append(self.degree_counts, np.uint64(len(neighbors)))
+        self.neighbors = np.concatenate([self.neighbors, np.asarray(neighbors, np.uint64)])
+        self.node_offsets = np.append(self.node_offsets, np.uint64(self.neighbors.size))
+        if self.entry_point is None or level > self.max_level:
+            self.entry_point = nid
+            self.max_level = level
+        return nid
+
+    def storage_bytes(self):
+        return 8 * (self.node_offsets.size + self.neighbors.size + self.levels.size + self.degree_counts.size)
+
+
+class SearchStats:
+    def __init__(self, arr):
+        self.n_hop = arr["n_hop"]
+        self.n_edge = arr["n_edge"]
+        self.n_dist = arr["n_dist"]
+        self.n_adc = arr["n_adc"]
+        self.n_rerank = arr["n_rerank"]
+
+
+_STATS_DTYPE = np.dtype([("n_hop", "<u8"), ("n_edge", "<u8"), ("n_dist", "<u8"), ("n_adc", "<u8"), ("n_rerank", "<u8")])
+
+
+class LeannIndex:
+    """LeannIndex (leann.rs:493-1067) with the graph and the provider's embeddings resident in HBM."""
+
+    def __init__(self, config=None):
+        self.config = config or LeannConfig()
+        self.config.validate()  # LeannIndex::new (leann.rs:504-511)
+        self._h = None
+        self._pq = None
+
+    # -- construction -------------------------------------------------------------------------
+    @classmethod
+    def from_csr(cls, config, vectors, node_offsets, neighbors, levels=None, entry_point=None):
+        self = cls(config)
+        v = _f32(vectors)
+        n = v.shape[0] if v.ndim == 2 else 0
+        dim = v.shape[1] if v.ndim == 2 else 0
+        off = np.ascontiguousarray(node_offsets, np.uint64)
+        nb = np.ascontiguousarray(neighbors, np.uint64)
+        lv = np.ascontiguousarray(levels, np.uint64) if levels is not None else None
+        h = C.c_void_p()
+        _check(_ffi.load().isl_index_from_csr(C.byref(self.config._s), dim, n, _ptr(off, u64p), _ptr(nb, u64p),
+                                              _ptr(lv, u64p), -1 if entry_point is None else int(entry_point),
+                                              _ptr(v, f32p), C.byref(h)))
+        self._h = h
+        return self
+
+    def build(self, provider, num_vectors, levels=None, seed=0, batch=1):
+        """LeannIndex::build (leann.rs:560-631).  `provider` is an InMemoryEmbeddingProvider (or an
+        [n, d] array); `levels` replaces the reference's thread_rng draw."""
+        self.free()
+        emb = provider.embeddings if hasattr(provider, "embeddings") else _f32(provider)
+        if num_vectors == 0:
+            h = C.c_void_p()
+            _check(_ffi.load().isl_index_from_csr(C.byref(self.config._s), 0, 0, None, None, None, -1, None,
+                                                  C.byref(h)))
+            self._h = h
+            return
+        if num_vectors > emb.shape[0]:
+            raise NodeNotFound(f"node {emb.shape[0]} not found")
+        v = _f32(emb[:num_vectors])
+        lv = np.ascontiguousarray(levels, np.uint64) if levels is not None else None
+        h = C.c_void_p()
+        _check(_ffi.load().isl_index_build(C.byref(self.config._s), v.shape[1], num_vectors, _ptr(v, f32p),
+                                           _ptr(lv, u64p), seed, batch, C.byref(h)))
+        self._h = h
+
+    def free(self):
+        if self._h is not None:
+            _ffi.load().isl_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    # -- accessors ----------------------------------------------------------------------------
+    def __len__(self):
+        return int(_ffi.load().isl_index_len(self._h)) if self._h else 0
+
+    def is_empty(self):
+        return len(self) == 0
+
+    def dimension(self):
+        d = int(_ffi.load().isl_index_dimension(self._h)) if self._h else 0
+        return d or None
+
+    def storage_bytes(self):
+        return int(_ffi.load().isl_index_storage_bytes(self._h)) if self._h else 8
+
+    def is_recompute(self):
+        return bool(self.config.is_recompute)
+
+    def is_compact(self):
+        return bool(self.config.is_compact)
+
+    @property
+    def graph(self):
+        lib = _ffi.load()
+        g = CsrGraph()
+        if not self._h:
+            return g
+        n = len(self)
+        e = int(lib.isl_index_num_edges(self._h))
+        g.num_nodes = n
+        g.node_offsets = np.zeros(n + 1, np.uint64)
+        g.neighbors = np.zeros(e, np.uint64)
+        g.levels = np.zeros(n, np.uint64)
+        g.degree_counts = np.zeros(n, np.uint64)
+        _check(lib.isl_index_export_csr(self._h, _ptr(g.node_offsets, u64p), _ptr(g.neighbors, u64p) if e else None,
+                                        _ptr(g.levels, u64p) if n else None,
+                                        _ptr(g.degree_counts, u64p) if n else None))
+        ep = int(lib.isl_index_entry_point(self._h))
+        g.entry_point = None if ep < 0 else ep
+        g.max_level = int(lib.isl_index_max_level(self._h))
+        return g
+
+    # -- search -------------------------------------------------------------------------------
+    def search(self, query, k, provider=None):
+        """LeannIndex::search (leann.rs:858-865): one query -> [(id, dist)] sorted ascending."""
+        return self.search_with_params(query, k, int(self.config.ef_search), provider)
+
+    def search_with_params(self, query, k, ef, provider=None):
+        """LeannIndex::search_with_params (leann.rs:868-896)."""
+        ids, dist, cnt = self.search_batch(_f32(query).reshape(1, -1), k, ef)
+        return [(int(ids[0, i]), float(dist[0, i])) for i in range(int(cnt[0]))]
+
+    def search_batch(self, queries, k, ef=None, stats=False):
+        """Batched form: queries [nq, d] -> (ids [nq,k] u64, dist [nq,k] f32, count [nq] u32[, stats])."""
+        if self._h is None:
+            raise IndexNotBuilt("index not built")
+        q = _f32(queries)
+        q = q.reshape(1, -1) if q.ndim == 1 else q
+        nq, qd = q.shape
+        ef = int(self.config.ef_search) if ef is None else int(ef)
+        ids = np.empty((nq, k), np.uint64)
+        dist = np.empty((nq, k), np.float32)
+        cnt = np.empty(nq, np.uint32)
+        st = np.zeros(nq, _STATS_DTYPE) if stats else None
+        _check(_ffi.load().isl_index_search(self._h, _ptr(q, f32p), nq, qd, k, ef, _ptr(ids, u64p),
+                                            _ptr(dist, f32p), _ptr(cnt, u32p),
+                                            st.ctypes.data_as(C.POINTER(SearchStatsStruct)) if stats else None))
+        return (ids, dist, cnt, SearchStats(st)) if stats else (ids, dist, cnt)
+
+    def last_search_timing(self):
+        ms = C.c_float()
+        n = C.c_uint64()
+        _check(_ffi.load().isl_index_last_search_timing(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    # -- two-level search (docs/leann-specification.md:223-269) -----------------------------------
+    def attach_pq(self, pq, codes):
+        codes = np.ascontiguousarray(codes, np.uint16)
+        _check(_ffi.load().isl_index_attach_pq(self._h, pq._h, _ptr(codes, u16p)))
+        self._pq = pq  # keep the quantizer alive while attached
+
+    def search_two_level_batch(self, queries, k, ef, rerank_ratio, stats=False):
+        q = _f32(queries)
+        q = q.reshape(1, -1) if q.ndim == 1 else q
+        nq, qd = q.shape
+        ids = np.empty((nq, k), np.uint64)
+        dist = np.empty((nq, k), np.float32)
+        cnt = np.empty(nq, np.uint32)
+        st = np.zeros(nq, _STATS_DTYPE) if stats else None
+        _check(_ffi.load().isl_index_search_two_level(self._h, _ptr(q, f32p), nq, qd, k, int(ef),
+                                                      float(rerank_ratio), _ptr(ids, u64p), _ptr(dist, f32p),
+                                                      _ptr(cnt, u32p),
+                                                      st.ctypes.data_as(C.POINTER(SearchStatsStruct)) if stats else None))
+        return (ids, dist, cnt, SearchStats(st)) if stats else (ids, dist, cnt)
+
+
+def random_level(u, ml, max_layers):
+    """LeannIndex::random_level (leann.rs:549-554) for an explicit uniform draw u in (0,1)."""
+    lvl = math.floor(-math.log(u) * ml)
+    return min(max(lvl, 0), max_layers - 1)
+
+
+# ---- pq.rs --------------------------------------------------------------------------------------
+class PQConfig:
+    """PQConfig (pq.rs:13-65)."""
+
+    def __init__(self, num_subquantizers=8, num_centroids=256, training_iterations=25, seed=None):
+        self._s = PQConfigStruct(num_subquantizers, num_centroids, training_iterations, -1 if seed is None else seed)
+
+    num_subquantizers = property(lambda self: self._s.num_subquantizers)
+    num_centroids = property(lambda self: self._s.num_centroids)
+    training_iterations = property(lambda self: self._s.training_iterations)
+    seed = property(lambda self: None if self._s.seed < 0 else self._s.seed)
+
+    def validate(self, dimension):
+        _check(_ffi.load().isl_pq_config_validate(C.byref(self._s), dimension))
+
+    def bytes_per_vector(self):
+        return int(_ffi.load().isl_pq_config_bytes_per_vector(C.byref(self._s)))
+
+
+class ProductQuantizer:
+    """ProductQuantizer (pq.rs:116-359)."""
+
+    def __init__(self, dimension, config=None):
+        self.config = config or PQConfig()
+        self.dimension = dimension
+        h = C.c_void_p()
+        _check(_ffi.load().isl_pq_new(dimension, C.byref(self.config._s), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                _ffi.load().isl_pq_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def with_metric(self, metric):
+        _check(_ffi.load().isl_pq_set_metric(self._h, getattr(metric, "value", metric)))
+        return self
+
+    def is_trained(self):
+        return bool(_ffi.load().isl_pq_is_trained(self._h))
+
+    def num_subquantizers(self):
+        return int(_ffi.load().isl_pq_num_subquantizers(self._h))
+
+    def compression_ratio(self):
+        return float(_ffi.load().isl_pq_compression_ratio(self._h))
+
+    def train(self, vectors):
+        v = _f32(vectors)
+        if v.size == 0:
+            raise EmptyCollection("empty collection")  # pq.rs:176-178
+        v = v.reshape(-1, v.shape[-1])
+        _check(_ffi.load().isl_pq_train(self._h, _ptr(v, f32p), v.shape[0], v.shape[1]))
+
+    def set_codebooks(self, codebooks):
+        cb = _f32(codebooks)  # [m][ksub][dsub]
+        _check(_ffi.load().isl_pq_set_codebooks(self._h, _ptr(cb, f32p), cb.shape[1]))
+
+    def codebooks(self):
+        k = C.c_uint64()
+        _check(_ffi.load().isl_pq_get_codebooks(self._h, None, C.byref(k)))
+        m = self.num_subquantizers()
+        out = np.empty((m, k.value, self.dimension // m), np.float32)
+        _check(_ffi.load().isl_pq_get_codebooks(self._h, _ptr(out, f32p), C.byref(k)))
+        return out
+
+    def encode(self, vector):
+        v = _f32(vector)
+        single = v.ndim == 1
+        v2 = v.reshape(1, -1) if single else v
+        out = np.empty((v2.shape[0], self.num_subquantizers()), np.uint16)
+        _check(_ffi.load().isl_pq_encode(self._h, _ptr(v2, f32p), v2.shape[0], v2.shape[1], _ptr(out, u16p)))
+        return out[0] if single else out
+
+    def decode(self, codes):
+        c = np.ascontiguousarray(codes, np.uint16)
+        single = c.ndim == 1
+        c2 = c.reshape(1, -1) if single else c
+        out = np.empty((c2.shape[0], self.dimension), np.float32)
+        _check(_ffi.load().isl_pq_decode(self._h, _ptr(c2, u16p), c2.shape[0], c2.shape[1], _ptr(out, f32p)))
+        return out[0] if single else out
+
+    def build_distance_tables(self, query):
+        q = _f32(query)
+        k = C.c_uint64(0)
+        if self.is_trained():
+            _check(_ffi.load().isl_pq_get_codebooks(self._h, None, C.byref(k)))
+        out = np.empty((self.num_subquantizers(), k.value), np.float32)
+        _check(_ffi.load().isl_pq_build_tables(self._h, _ptr(q, f32p), q.size, _ptr(out, f32p)))
+        return out
+
+    def table_distance(self, tables, codes):
+        t = _f32(tables)
+        c = np.ascontiguousarray(codes, np.uint16)
+        single = c.ndim == 1
+        c2 = c.reshape(1, -1) if single else c
+        out = np.empty(c2.shape[0], np.float32)
+        _check(_ffi.load().isl_pq_table_distance(self._h, _ptr(t, f32p), _ptr(c2, u16p), c2.shape[0], _ptr(out, f32p)))
+        return float(out[0]) if single else out
+
+    def asymmetric_distance(self, query, codes):
+        q = _f32(query)
+        c = np.ascontiguousarray(codes, np.uint16)
+        single = c.ndim == 1
+        c2 = c.reshape(1, -1) if single else c
+        out = np.empty(c2.shape[0], np.float32)
+        _check(_ffi.load().isl_pq_asymmetric_distance(self._h, _ptr(q, f32p), q.size, _ptr(c2, u16p), c2.shape[0],
+                                                      _ptr(out, f32p)))
+        return float(out[0]) if single else out
+
+
+# ---- search.rs ----------------------------------------------------------------------------------
+def to_similarity(score):
+    """SearchResult::to_similarity (search.rs:99-102)."""
+    return np.float32(1.0) / (np.float32(1.0) + np.float32(score))
+
+
+def merge_topk(ids, dist, k):
+    """Island / shard merge (search.rs:211-237) under the (dist,id) rule.
+    ids, dist: [parts, nq, k] -> ([nq,k] ids, [nq,k] dist, [nq] count)."""
+    ids = np.ascontiguousarray(ids, np.uint64)
+    dist = _f32(dist)
+    parts, nq, kk = ids.shape
+    assert kk == k
+    out_ids = np.empty((nq, k), np.uint64)
+    out_dist = np.empty((nq, k), np.float32)
+    cnt = np.empty(nq, np.uint32)
+    _check(_ffi.load().isl_merge_topk(_ptr(ids, u64p), _ptr(dist, f32p), parts, nq, k, _ptr(out_ids, u64p),
+                                      _ptr(out_dist, f32p), _ptr(cnt, u32p)))
+    return out_ids, out_dist, cnt

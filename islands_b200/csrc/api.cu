@@ -1,0 +1,581 @@
+// api.cu — C ABI: library, configs, distance entry points, LEANN index (from_csr / search /
+// export), shard merge.  See include/islands_b200.h for the reference lines each one replaces.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <memory>
+
+#include "api_common.h"
+
+namespace isl {
+
+static thread_local std::string t_last_error;
+std::atomic<uint64_t> g_launch_count{0};
+
+void set_last_error(const std::string& msg) { t_last_error = msg; }
+isl_status fail(isl_status st, const std::string& msg) {
+  t_last_error = msg;
+  return st;
+}
+isl_status cuda_fail(cudaError_t e, const char* what) {
+  t_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  cudaGetLastError();  // clear the sticky-free error state
+  return ISL_CUDA_ERROR;
+}
+
+isl_status current_device(int* device, int* sms) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(ISL_CUDA_ERROR,
+                "no usable CUDA device: islands_b200 has no CPU fallback (cudaGetDeviceCount: " +
+                    std::string(e == cudaSuccess ? "0 devices" : cudaGetErrorString(e)) + ")");
+  }
+  ISL_CUDA_TRY(cudaGetDevice(device));
+  ISL_CUDA_TRY(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, *device));
+  return ISL_OK;
+}
+
+// leann.rs:432-460
+static isl_status validate_leann(const isl_leann_config* c) {
+  if (!c) return fail(ISL_INVALID_ARGUMENT, "config is null");
+  if (c->m == 0) return fail(ISL_INVALID_CONFIG, "M must be > 0");
+  if (c->m0 < c->m) return fail(ISL_INVALID_CONFIG, "M0 must be >= M");
+  if (c->ef_construction < c->m) return fail(ISL_INVALID_CONFIG, "ef_construction must be >= M");
+  if (!(c->prune_ratio >= 0.0f && c->prune_ratio <= 1.0f))
+    return fail(ISL_INVALID_CONFIG, "prune_ratio must be in [0.0, 1.0]");
+  if (c->beam_width == 0) return fail(ISL_INVALID_CONFIG, "beam_width must be > 0");
+  if (!(c->hub_percentile >= 0.0f && c->hub_percentile <= 1.0f))
+    return fail(ISL_INVALID_CONFIG, "hub_percentile must be in [0.0, 1.0]");
+  if (c->metric < 0 || c->metric > 3) return fail(ISL_INVALID_CONFIG, "unknown metric");
+  if (c->pruning_strategy < 0 || c->pruning_strategy > 2)
+    return fail(ISL_INVALID_CONFIG, "unknown pruning strategy");
+  return ISL_OK;
+}
+
+isl_status index_alloc_common(isl_index* idx) {
+  ISL_TRY(current_device(&idx->device, &idx->sms));
+  ISL_CUDA_TRY(cudaStreamCreateWithFlags(&idx->stream, cudaStreamNonBlocking));
+  ISL_CUDA_TRY(cudaEventCreate(&idx->ev0));
+  ISL_CUDA_TRY(cudaEventCreate(&idx->ev1));
+  ISL_TRY(ensure(idx->counters, 4));
+  return ISL_OK;
+}
+
+// Uploads h_offsets / h_nbrs to the device (u64 offsets, u32 ids) and derives max_degree.
+isl_status index_finish_graph(isl_index* idx) {
+  const uint64_t n = idx->n;
+  uint32_t maxdeg = 0;
+  for (uint64_t i = 0; i < n; ++i)
+    maxdeg = std::max<uint32_t>(maxdeg, (uint32_t)(idx->h_offsets[i + 1] - idx->h_offsets[i]));
+  idx->max_degree = maxdeg;
+  const uint64_t e = idx->h_nbrs.size();
+  ISL_CUDA_TRY(idx->offsets.alloc(n + 1));
+  ISL_CUDA_TRY(cudaMemcpyAsync(idx->offsets.p, idx->h_offsets.data(), (n + 1) * 8,
+                               cudaMemcpyHostToDevice, idx->stream));
+  std::vector<uint32_t> n32(e);
+  for (uint64_t i = 0; i < e; ++i) n32[i] = (uint32_t)idx->h_nbrs[i];
+  ISL_CUDA_TRY(idx->nbrs.alloc(std::max<uint64_t>(e, 1)));
+  if (e)
+    ISL_CUDA_TRY(cudaMemcpyAsync(idx->nbrs.p, n32.data(), e * 4, cudaMemcpyHostToDevice, idx->stream));
+  ISL_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+  return ISL_OK;
+}
+
+static void fill_empty(uint64_t nq, uint32_t k, uint64_t* ids, float* dist, uint32_t* count,
+                       isl_search_stats* stats) {
+  for (uint64_t i = 0; i < nq * (uint64_t)k; ++i) {
+    if (ids) ids[i] = ISL_INVALID_ID;
+    if (dist) dist[i] = std::numeric_limits<float>::infinity();
+  }
+  for (uint64_t q = 0; q < nq; ++q) {
+    if (count) count[q] = 0;
+    if (stats) stats[q] = isl_search_stats{0, 0, 0, 0, 0};
+  }
+}
+
+// Core of isl_index_search*: queries already on the device as [nq][q_ld] (q_ld % 4 == 0, zero
+// padded), outputs on the device.
+static isl_status search_device(const isl_index* idx, const float* d_queries, uint32_t q_ld,
+                                uint64_t nq, uint32_t k, uint32_t ef, uint64_t* d_ids, float* d_dist,
+                                uint32_t* d_count, isl_search_stats* d_stats) {
+  SearchPlan plan;
+  const uint32_t u_cap = std::max<uint32_t>(32, round_up(idx->max_degree, 32));
+  ISL_TRY(plan_search(idx->cfg.metric, idx->ld, ef, u_cap, idx->sms, &plan));
+  const uint32_t vis_words = round_up((uint32_t)((idx->n + 31) / 32), 4);
+  const uint32_t slots = (uint32_t)std::min<uint64_t>(plan.grid, nq);
+  ISL_TRY(ensure(idx->visited, (size_t)slots * vis_words));
+  if (!plan.r_in_smem) ISL_TRY(ensure(idx->r_global, (size_t)slots * ef));
+  ISL_CUDA_TRY(cudaMemsetAsync(idx->counters.p, 0, 4 * sizeof(unsigned int), idx->stream));
+
+  SearchArgs a{};
+  a.vectors = idx->vectors.p;
+  a.sqnorms = idx->sqnorms.p;
+  a.ld = idx->ld;
+  a.d = idx->dim;
+  a.n = (uint32_t)idx->n;
+  a.offsets = idx->offsets.p;
+  a.nbrs = idx->nbrs.p;
+  a.degrees = nullptr;
+  a.adj_stride = 0;
+  a.queries = d_queries;
+  a.q_ld = q_ld;
+  a.nq = (uint32_t)nq;
+  a.entry = (uint32_t)idx->entry;
+  a.k = k;
+  a.ef = ef;
+  a.metric = idx->cfg.metric;
+  a.prune_ratio = idx->cfg.prune_ratio;
+  a.strategy = idx->cfg.pruning_strategy;
+  a.visited = idx->visited.p;
+  a.vis_words = vis_words;
+  a.r_global = idx->r_global.p;
+  a.u_cap = u_cap;
+  a.out_ids = d_ids;
+  a.out_ids32 = nullptr;
+  a.out_dist = d_dist;
+  a.out_count = d_count;
+  a.stats = d_stats;
+  a.work_counter = idx->counters.p;
+  a.error_flag = idx->counters.p + 1;
+
+  ISL_CUDA_TRY(cudaEventRecord(idx->ev0, idx->stream));
+  ISL_TRY(launch_search(plan, a, idx->stream));
+  ISL_CUDA_TRY(cudaEventRecord(idx->ev1, idx->stream));
+  idx->last_launches = 1;
+  return ISL_OK;
+}
+
+static isl_status search_finish(const isl_index* idx) {
+  unsigned int h[4] = {0, 0, 0, 0};
+  ISL_CUDA_TRY(cudaMemcpyAsync(h, idx->counters.p, sizeof(h), cudaMemcpyDeviceToHost, idx->stream));
+  ISL_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+  float ms = 0.0f;
+  if (cudaEventElapsedTime(&ms, idx->ev0, idx->ev1) == cudaSuccess) idx->last_kernel_ms = ms;
+  if (h[1])
+    return fail(ISL_INVALID_ARGUMENT,
+                "search: more than 64 unexpanded candidates tie exactly with the worst result distance");
+  return ISL_OK;
+}
+
+static isl_status search_checks(const isl_index* idx, const void* queries, uint64_t nq,
+                                uint32_t query_dim, uint32_t k, uint32_t* ef, bool* trivial) {
+  *trivial = false;
+  if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
+  if (nq > 0 && !queries) return fail(ISL_INVALID_ARGUMENT, "queries is null");
+  if (nq > 0xffffffffull) return fail(ISL_INVALID_ARGUMENT, "too many queries in one batch");
+  if (idx->n == 0 || nq == 0 || k == 0) {  // leann.rs:875-877 / take(0)
+    *trivial = true;
+    return ISL_OK;
+  }
+  if (query_dim != idx->dim)  // leann.rs:880-887
+    return fail(ISL_DIM_MISMATCH, "dimension mismatch: expected " + std::to_string(idx->dim) +
+                                      ", got " + std::to_string(query_dim));
+  if (idx->entry < 0) return fail(ISL_INDEX_NOT_BUILT, "index not built");  // leann.rs:889
+  if (idx->cfg.prune_ratio != 0.0f && idx->cfg.pruning_strategy == ISL_PRUNE_PROPORTIONAL)
+    return fail(ISL_INVALID_CONFIG,
+                "PruningStrategy::Proportional draws from thread_rng in the reference and has no "
+                "deterministic definition; use Global or Local");
+  *ef = std::max(*ef, k);  // leann.rs:890
+  if (*ef > (1u << 24)) return fail(ISL_INVALID_ARGUMENT, "ef too large");
+  return ISL_OK;
+}
+
+}  // namespace isl
+
+using namespace isl;
+
+isl_index::~isl_index() {
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+extern "C" {
+
+int isl_abi_version(void) { return ISL_ABI_VERSION; }
+const char* isl_last_error(void) { return t_last_error.c_str(); }
+int isl_device_count(void) {
+  int c = 0;
+  if (cudaGetDeviceCount(&c) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return c;
+}
+uint64_t isl_kernel_launch_count(void) { return g_launch_count.load(); }
+void isl_kernel_launch_count_reset(void) { g_launch_count.store(0); }
+
+// ---- configs ------------------------------------------------------------------------------
+isl_status isl_leann_config_default(isl_leann_config* c) {
+  if (!c) return fail(ISL_INVALID_ARGUMENT, "out is null");
+  c->m = 30;  // leann.rs:386-403
+  c->m0 = 60;
+  c->ef_construction = 128;
+  c->ml = 1.0 / std::log(30.0);
+  c->max_layers = 16;
+  c->metric = ISL_METRIC_COSINE;
+  c->ef_search = 64;
+  c->beam_width = 1;
+  c->prune_ratio = 0.0f;
+  c->pruning_strategy = ISL_PRUNE_GLOBAL;
+  c->high_degree_pruning = 1;
+  c->hub_percentile = 0.02f;
+  c->is_compact = 1;
+  c->is_recompute = 1;
+  return ISL_OK;
+}
+isl_status isl_leann_config_fast(isl_leann_config* c) {
+  ISL_TRY(isl_leann_config_default(c));  // leann.rs:406-416
+  c->m = 16;
+  c->m0 = 32;
+  c->ef_construction = 100;
+  c->ef_search = 32;
+  c->beam_width = 1;
+  c->prune_ratio = 0.3f;
+  return ISL_OK;
+}
+isl_status isl_leann_config_accurate(isl_leann_config* c) {
+  ISL_TRY(isl_leann_config_default(c));  // leann.rs:419-429
+  c->m = 48;
+  c->m0 = 96;
+  c->ef_construction = 400;
+  c->ef_search = 128;
+  c->beam_width = 1;
+  c->prune_ratio = 0.0f;
+  return ISL_OK;
+}
+isl_status isl_leann_config_validate(const isl_leann_config* c) { return validate_leann(c); }
+
+isl_status isl_hnsw_config_default(isl_hnsw_config* c) {
+  if (!c) return fail(ISL_INVALID_ARGUMENT, "out is null");
+  c->m = 16;  // hnsw.rs:37-48
+  c->m0 = 32;
+  c->ef_construction = 200;
+  c->ml = 1.0 / std::log(16.0);
+  c->metric = ISL_METRIC_COSINE;
+  c->max_layers = 16;
+  return ISL_OK;
+}
+isl_status isl_hnsw_config_validate(const isl_hnsw_config* c) {
+  if (!c) return fail(ISL_INVALID_ARGUMENT, "config is null");
+  if (c->m == 0) return fail(ISL_INVALID_CONFIG, "M must be > 0");  // hnsw.rs:72-85
+  if (c->m0 < c->m) return fail(ISL_INVALID_CONFIG, "M0 must be >= M");
+  if (c->ef_construction < c->m) return fail(ISL_INVALID_CONFIG, "ef_construction must be >= M");
+  return ISL_OK;
+}
+isl_status isl_pq_config_default(isl_pq_config* c) {
+  if (!c) return fail(ISL_INVALID_ARGUMENT, "out is null");
+  c->num_subquantizers = 8;  // pq.rs:24-33
+  c->num_centroids = 256;
+  c->training_iterations = 25;
+  c->seed = -1;
+  return ISL_OK;
+}
+isl_status isl_pq_config_validate(const isl_pq_config* c, uint64_t dimension) {
+  if (!c) return fail(ISL_INVALID_ARGUMENT, "config is null");
+  if (c->num_subquantizers == 0)  // pq.rs:37-55
+    return fail(ISL_INVALID_CONFIG, "num_subquantizers must be > 0");
+  if (dimension % c->num_subquantizers != 0)
+    return fail(ISL_INVALID_CONFIG, "dimension " + std::to_string(dimension) +
+                                        " must be divisible by num_subquantizers " +
+                                        std::to_string(c->num_subquantizers));
+  if (c->num_centroids == 0 || c->num_centroids > 65536)
+    return fail(ISL_INVALID_CONFIG, "num_centroids must be in range [1, 65536]");
+  return ISL_OK;
+}
+uint64_t isl_pq_config_bytes_per_vector(const isl_pq_config* c) {
+  if (!c) return 0;
+  return c->num_centroids <= 256 ? c->num_subquantizers : c->num_subquantizers * 2;  // pq.rs:58-64
+}
+
+// ---- distances ------------------------------------------------------------------------------
+static isl_status distance_host(int32_t metric, const float* q, const float* rows, uint64_t n_rows,
+                                uint32_t dim, float* out, bool squared) {
+  if (metric < 0 || metric > 3) return fail(ISL_INVALID_CONFIG, "unknown metric");
+  if (n_rows == 0) return ISL_OK;
+  if (!q || !rows || !out) return fail(ISL_INVALID_ARGUMENT, "null pointer");
+  int device, sms;
+  ISL_TRY(current_device(&device, &sms));
+  const uint32_t ld = std::max<uint32_t>(4, round_up(dim, 4));
+  DevBuf<float> dq, dr, dout;
+  ISL_CUDA_TRY(dq.alloc(ld));
+  ISL_CUDA_TRY(dr.alloc(n_rows * ld));
+  ISL_CUDA_TRY(dout.alloc(n_rows));
+  ISL_CUDA_TRY(cudaMemset(dq.p, 0, dq.bytes()));
+  ISL_CUDA_TRY(cudaMemset(dr.p, 0, dr.bytes()));
+  if (dim) {
+    ISL_CUDA_TRY(cudaMemcpy(dq.p, q, (size_t)dim * 4, cudaMemcpyHostToDevice));
+    ISL_CUDA_TRY(cudaMemcpy2D(dr.p, (size_t)ld * 4, rows, (size_t)dim * 4, (size_t)dim * 4, n_rows,
+                              cudaMemcpyHostToDevice));
+  }
+  ISL_TRY(launch_distance_batch(metric, squared, dq.p, dr.p, n_rows, dim, ld, dout.p, sms, 0));
+  ISL_CUDA_TRY(cudaMemcpy(out, dout.p, n_rows * 4, cudaMemcpyDeviceToHost));
+  return ISL_OK;
+}
+
+isl_status isl_distance_calculate(int32_t metric, const float* a, uint64_t len_a, const float* b,
+                                  uint64_t len_b, float* out) {
+  if (len_a != len_b)  // distance.rs:39-44
+    return fail(ISL_DIM_MISMATCH, "dimension mismatch: expected " + std::to_string(len_a) + ", got " +
+                                      std::to_string(len_b));
+  if (!out) return fail(ISL_INVALID_ARGUMENT, "out is null");
+  return distance_host(metric, a, b, 1, (uint32_t)len_a, out, false);
+}
+
+isl_status isl_distance_calculate_squared(int32_t metric, const float* a, uint64_t len_a,
+                                          const float* b, uint64_t len_b, float* out) {
+  if (len_a != len_b)  // distance.rs:55-60
+    return fail(ISL_DIM_MISMATCH, "dimension mismatch: expected " + std::to_string(len_a) + ", got " +
+                                      std::to_string(len_b));
+  if (!out) return fail(ISL_INVALID_ARGUMENT, "out is null");
+  return distance_host(metric, a, b, 1, (uint32_t)len_a, out, true);
+}
+
+isl_status isl_distance_batch(int32_t metric, const float* query, const float* rows, uint64_t n_rows,
+                              uint32_t dim, float* out) {
+  return distance_host(metric, query, rows, n_rows, dim, out, false);
+}
+
+isl_status isl_distance_batch_dev(int32_t metric, const float* d_query, const float* d_rows,
+                                  uint64_t n_rows, uint32_t dim, float* d_out) {
+  if (metric < 0 || metric > 3) return fail(ISL_INVALID_CONFIG, "unknown metric");
+  if (n_rows == 0) return ISL_OK;
+  if (!d_query || !d_rows || !d_out) return fail(ISL_INVALID_ARGUMENT, "null pointer");
+  if (dim % 4 != 0 || (reinterpret_cast<uintptr_t>(d_rows) & 15) || (reinterpret_cast<uintptr_t>(d_query) & 15))
+    return fail(ISL_INVALID_ARGUMENT, "isl_distance_batch_dev needs dim % 4 == 0 and 16-byte aligned pointers");
+  int device, sms;
+  ISL_TRY(current_device(&device, &sms));
+  ISL_TRY(launch_distance_batch(metric, false, d_query, d_rows, n_rows, dim, dim, d_out, sms, 0));
+  ISL_CUDA_TRY(cudaStreamSynchronize(0));
+  return ISL_OK;
+}
+
+isl_status isl_normalize_rows(float* rows, uint64_t n_rows, uint32_t dim) {
+  if (n_rows == 0 || dim == 0) return ISL_OK;
+  if (!rows) return fail(ISL_INVALID_ARGUMENT, "rows is null");
+  int device, sms;
+  ISL_TRY(current_device(&device, &sms));
+  const uint32_t ld = round_up(dim, 4);
+  DevBuf<float> dr;
+  ISL_CUDA_TRY(dr.alloc(n_rows * ld));
+  ISL_CUDA_TRY(cudaMemset(dr.p, 0, dr.bytes()));
+  ISL_CUDA_TRY(cudaMemcpy2D(dr.p, (size_t)ld * 4, rows, (size_t)dim * 4, (size_t)dim * 4, n_rows,
+                            cudaMemcpyHostToDevice));
+  ISL_TRY(launch_normalize_rows(dr.p, n_rows, dim, ld, sms, 0));
+  ISL_CUDA_TRY(cudaMemcpy2D(rows, (size_t)dim * 4, dr.p, (size_t)ld * 4, (size_t)dim * 4, n_rows,
+                            cudaMemcpyDeviceToHost));
+  return ISL_OK;
+}
+
+// ---- LEANN index -----------------------------------------------------------------------------
+isl_status isl_index_from_csr(const isl_leann_config* cfg, uint32_t dim, uint64_t n,
+                              const uint64_t* node_offsets, const uint64_t* neighbors,
+                              const uint64_t* levels, int64_t entry_point, const float* vectors,
+                              isl_index** out) {
+  if (!out) return fail(ISL_INVALID_ARGUMENT, "out is null");
+  *out = nullptr;
+  ISL_TRY(validate_leann(cfg));  // LeannIndex::new (leann.rs:504-511)
+  if (n >= (1ull << 31)) return fail(ISL_INVALID_ARGUMENT, "n must be < 2^31 per index (shard larger sets)");
+  if (n > 0) {
+    if (!node_offsets || !vectors) return fail(ISL_INVALID_ARGUMENT, "null pointer");
+    if (dim == 0) return fail(ISL_INVALID_ARGUMENT, "dim must be > 0");
+    if (node_offsets[0] != 0) return fail(ISL_SERIALIZATION, "node_offsets[0] must be 0");
+    for (uint64_t i = 0; i < n; ++i)
+      if (node_offsets[i + 1] < node_offsets[i]) return fail(ISL_SERIALIZATION, "node_offsets must be non-decreasing");
+    if (node_offsets[n] > 0 && !neighbors) return fail(ISL_INVALID_ARGUMENT, "neighbors is null");
+    for (uint64_t i = 0; i < node_offsets[n]; ++i)
+      if (neighbors[i] >= n)  // the provider would fail with NodeNotFound (leann.rs:146-149)
+        return fail(ISL_NODE_NOT_FOUND, "neighbor id " + std::to_string(neighbors[i]) + " out of range");
+    if (entry_point >= (int64_t)n) return fail(ISL_NODE_NOT_FOUND, "entry point out of range");
+  }
+  std::unique_ptr<isl_index> idx(new isl_index());
+  idx->cfg = *cfg;
+  idx->n = n;
+  idx->dim = n ? dim : 0;
+  idx->ld = n ? std::max<uint32_t>(4, round_up(dim, 4)) : 0;
+  idx->entry = n ? entry_point : ISL_NO_ENTRY;
+  ISL_TRY(index_alloc_common(idx.get()));
+  if (n) {
+    idx->h_offsets.assign(node_offsets, node_offsets + n + 1);
+    idx->h_nbrs.assign(neighbors, neighbors + node_offsets[n]);
+    if (levels)
+      idx->h_levels.assign(levels, levels + n);
+    else
+      idx->h_levels.assign(n, 0);
+    idx->max_level = 0;
+    if (entry_point >= 0) idx->max_level = idx->h_levels[entry_point];
+    ISL_CUDA_TRY(idx->vectors.alloc(n * idx->ld));
+    if (idx->ld != dim) ISL_CUDA_TRY(cudaMemsetAsync(idx->vectors.p, 0, idx->vectors.bytes(), idx->stream));
+    ISL_CUDA_TRY(cudaMemcpy2DAsync(idx->vectors.p, (size_t)idx->ld * 4, vectors, (size_t)dim * 4,
+                                   (size_t)dim * 4, n, cudaMemcpyHostToDevice, idx->stream));
+    ISL_CUDA_TRY(idx->sqnorms.alloc(n));
+    ISL_TRY(launch_row_sqnorms(idx->vectors.p, n, dim, idx->ld, idx->sqnorms.p, idx->sms, idx->stream));
+    ISL_TRY(index_finish_graph(idx.get()));
+  } else {
+    idx->h_offsets.assign(1, 0);
+  }
+  *out = idx.release();
+  return ISL_OK;
+}
+
+void isl_index_free(isl_index* idx) {
+  if (!idx) return;
+  DeviceGuard g(idx->device);
+  delete idx;
+}
+uint64_t isl_index_len(const isl_index* idx) { return idx ? idx->n : 0; }
+uint32_t isl_index_dimension(const isl_index* idx) { return idx ? idx->dim : 0; }
+uint64_t isl_index_num_edges(const isl_index* idx) { return idx ? idx->h_nbrs.size() : 0; }
+int64_t isl_index_entry_point(const isl_index* idx) { return idx ? idx->entry : ISL_NO_ENTRY; }
+uint64_t isl_index_max_level(const isl_index* idx) { return idx ? idx->max_level : 0; }
+uint64_t isl_index_storage_bytes(const isl_index* idx) {
+  if (!idx) return 0;  // leann.rs:296-301: offsets + neighbors + levels + degree_counts, 8 B each
+  return (idx->h_offsets.size() + idx->h_nbrs.size() + idx->h_levels.size() + idx->n) * 8;
+}
+
+isl_status isl_index_export_csr(const isl_index* idx, uint64_t* node_offsets, uint64_t* neighbors,
+                                uint64_t* levels, uint64_t* degree_counts) {
+  if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
+  if (node_offsets) std::memcpy(node_offsets, idx->h_offsets.data(), idx->h_offsets.size() * 8);
+  if (neighbors && !idx->h_nbrs.empty()) std::memcpy(neighbors, idx->h_nbrs.data(), idx->h_nbrs.size() * 8);
+  if (levels && idx->n) std::memcpy(levels, idx->h_levels.data(), idx->n * 8);
+  if (degree_counts)
+    for (uint64_t i = 0; i < idx->n; ++i) degree_counts[i] = idx->h_offsets[i + 1] - idx->h_offsets[i];
+  return ISL_OK;
+}
+
+isl_status isl_index_get_neighbors(const isl_index* idx, uint64_t node_id, uint64_t* out, uint64_t cap,
+                                   uint64_t* out_count) {
+  if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
+  if (node_id >= idx->n) return fail(ISL_NODE_NOT_FOUND, "node " + std::to_string(node_id) + " not found");
+  const uint64_t s = idx->h_offsets[node_id], e = idx->h_offsets[node_id + 1];
+  if (out_count) *out_count = e - s;
+  for (uint64_t i = 0; i < e - s && i < cap; ++i) out[i] = idx->h_nbrs[s + i];
+  return ISL_OK;
+}
+
+isl_status isl_index_search(const isl_index* idx, const float* queries, uint64_t nq,
+                            uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* out_ids,
+                            float* out_dist, uint32_t* out_count, isl_search_stats* stats) {
+  bool trivial;
+  ISL_TRY(search_checks(idx, queries, nq, query_dim, k, &ef, &trivial));
+  if (trivial) {
+    fill_empty(nq, k, out_ids, out_dist, out_count, stats);
+    return ISL_OK;
+  }
+  if (!out_ids || !out_dist) return fail(ISL_INVALID_ARGUMENT, "output pointer is null");
+  DeviceGuard g(idx->device);
+  std::lock_guard<std::mutex> lock(idx->mu);
+  ISL_TRY(ensure(idx->q_stage, nq * idx->ld));
+  ISL_TRY(ensure(idx->out_ids, nq * k));
+  ISL_TRY(ensure(idx->out_dist, nq * k));
+  ISL_TRY(ensure(idx->out_count, nq));
+  if (stats) ISL_TRY(ensure(idx->out_stats, nq));
+  if (idx->ld != idx->dim)
+    ISL_CUDA_TRY(cudaMemsetAsync(idx->q_stage.p, 0, nq * idx->ld * 4, idx->stream));
+  ISL_CUDA_TRY(cudaMemcpy2DAsync(idx->q_stage.p, (size_t)idx->ld * 4, queries, (size_t)idx->dim * 4,
+                                 (size_t)idx->dim * 4, nq, cudaMemcpyHostToDevice, idx->stream));
+  ISL_TRY(search_device(idx, idx->q_stage.p, idx->ld, nq, k, ef, idx->out_ids.p, idx->out_dist.p,
+                        idx->out_count.p, stats ? idx->out_stats.p : nullptr));
+  ISL_CUDA_TRY(cudaMemcpyAsync(out_ids, idx->out_ids.p, nq * k * 8, cudaMemcpyDeviceToHost, idx->stream));
+  ISL_CUDA_TRY(cudaMemcpyAsync(out_dist, idx->out_dist.p, nq * k * 4, cudaMemcpyDeviceToHost, idx->stream));
+  if (out_count)
+    ISL_CUDA_TRY(cudaMemcpyAsync(out_count, idx->out_count.p, nq * 4, cudaMemcpyDeviceToHost, idx->stream));
+  if (stats)
+    ISL_CUDA_TRY(cudaMemcpyAsync(stats, idx->out_stats.p, nq * sizeof(isl_search_stats),
+                                 cudaMemcpyDeviceToHost, idx->stream));
+  return search_finish(idx);
+}
+
+isl_status isl_index_search_dev(const isl_index* idx, const float* d_queries, uint64_t nq,
+                                uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
+                                float* d_out_dist, uint32_t* d_out_count,
+                                isl_search_stats* d_stats) {
+  bool trivial;
+  ISL_TRY(search_checks(idx, d_queries, nq, query_dim, k, &ef, &trivial));
+  if (!d_out_ids || !d_out_dist) return fail(ISL_INVALID_ARGUMENT, "output pointer is null");
+  if (trivial) {
+    if (nq && k) {
+      // empty index: ids = INVALID (all ones), dist = +inf is written as NaN-free pattern
+      ISL_CUDA_TRY(cudaMemset(d_out_ids, 0xff, nq * k * 8));
+      std::vector<float> inf(nq * k, std::numeric_limits<float>::infinity());
+      ISL_CUDA_TRY(cudaMemcpy(d_out_dist, inf.data(), nq * k * 4, cudaMemcpyHostToDevice));
+    }
+    if (d_out_count && nq) ISL_CUDA_TRY(cudaMemset(d_out_count, 0, nq * 4));
+    if (d_stats && nq) ISL_CUDA_TRY(cudaMemset(d_stats, 0, nq * sizeof(isl_search_stats)));
+    return ISL_OK;
+  }
+  DeviceGuard g(idx->device);
+  std::lock_guard<std::mutex> lock(idx->mu);
+  const float* q = d_queries;
+  uint32_t q_ld = query_dim;
+  if (query_dim % 4 != 0 || (reinterpret_cast<uintptr_t>(d_queries) & 15)) {
+    ISL_TRY(ensure(idx->q_stage, nq * idx->ld));
+    ISL_TRY(launch_pad_rows(d_queries, query_dim, idx->q_stage.p, idx->ld, nq, idx->stream));
+    q = idx->q_stage.p;
+    q_ld = idx->ld;
+  }
+  // The caller's buffers may have been produced on another stream: order after everything
+  // already enqueued on the legacy default stream.
+  ISL_TRY(search_device(idx, q, q_ld, nq, k, ef, d_out_ids, d_out_dist, d_out_count, d_stats));
+  return search_finish(idx);
+}
+
+isl_status isl_index_search_default(const isl_index* idx, const float* queries, uint64_t nq,
+                                    uint32_t query_dim, uint32_t k, uint64_t* out_ids,
+                                    float* out_dist, uint32_t* out_count) {
+  if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
+  return isl_index_search(idx, queries, nq, query_dim, k, (uint32_t)idx->cfg.ef_search, out_ids,
+                          out_dist, out_count, nullptr);
+}
+
+isl_status isl_index_last_search_timing(const isl_index* idx, float* kernel_ms, uint64_t* kernel_launches) {
+  if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
+  if (kernel_ms) *kernel_ms = idx->last_kernel_ms;
+  if (kernel_launches) *kernel_launches = idx->last_launches;
+  return ISL_OK;
+}
+
+// ---- merge ----------------------------------------------------------------------------------
+isl_status isl_merge_topk_dev(const uint64_t* d_ids, const float* d_dist, uint32_t parts, uint64_t nq,
+                              uint32_t k, uint64_t* d_out_ids, float* d_out_dist,
+                              uint32_t* d_out_count) {
+  if (nq == 0 || k == 0) return ISL_OK;
+  if (!d_ids || !d_dist || !d_out_ids || !d_out_dist) return fail(ISL_INVALID_ARGUMENT, "null pointer");
+  if (parts == 0) return fail(ISL_INVALID_ARGUMENT, "parts must be > 0");
+  int device, sms;
+  ISL_TRY(current_device(&device, &sms));
+  ISL_TRY(launch_merge_topk(d_ids, d_dist, parts, nq, k, d_out_ids, d_out_dist, d_out_count, 0));
+  ISL_CUDA_TRY(cudaStreamSynchronize(0));
+  return ISL_OK;
+}
+
+isl_status isl_merge_topk(const uint64_t* ids, const float* dist, uint32_t parts, uint64_t nq,
+                          uint32_t k, uint64_t* out_ids, float* out_dist, uint32_t* out_count) {
+  if (nq == 0 || k == 0) return ISL_OK;
+  if (!ids || !dist || !out_ids || !out_dist) return fail(ISL_INVALID_ARGUMENT, "null pointer");
+  if (parts == 0) return fail(ISL_INVALID_ARGUMENT, "parts must be > 0");
+  const size_t total = (size_t)parts * nq * k;
+  DevBuf<uint64_t> di, doi;
+  DevBuf<float> dd, dod;
+  DevBuf<uint32_t> dc;
+  int device, sms;
+  ISL_TRY(current_device(&device, &sms));
+  ISL_CUDA_TRY(di.alloc(total));
+  ISL_CUDA_TRY(dd.alloc(total));
+  ISL_CUDA_TRY(doi.alloc(nq * k));
+  ISL_CUDA_TRY(dod.alloc(nq * k));
+  ISL_CUDA_TRY(dc.alloc(nq));
+  ISL_CUDA_TRY(cudaMemcpy(di.p, ids, total * 8, cudaMemcpyHostToDevice));
+  ISL_CUDA_TRY(cudaMemcpy(dd.p, dist, total * 4, cudaMemcpyHostToDevice));
+  ISL_TRY(launch_merge_topk(di.p, dd.p, parts, nq, k, doi.p, dod.p, dc.p, 0));
+  ISL_CUDA_TRY(cudaMemcpy(out_ids, doi.p, nq * k * 8, cudaMemcpyDeviceToHost));
+  ISL_CUDA_TRY(cudaMemcpy(out_dist, dod.p, nq * k * 4, cudaMemcpyDeviceToHost));
+  if (out_count) ISL_CUDA_TRY(cudaMemcpy(out_count, dc.p, nq * 4, cudaMemcpyDeviceToHost));
+  return ISL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// api_common.h — handle definitions shared by the C-ABI translation units.
+#pragma once
+
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "search.h"
+
+namespace isl {
+
+// Switches to `device` for the lifetime of the guard (handles are bound to their device).
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != device && cudaSetDevice(device) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+isl_status current_device(int* device, int* sms);
+inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
+
+}  // namespace isl
+
+struct isl_pq {
+  isl_pq_config cfg{};
+  uint32_t dim = 0, dsub = 0, ld_sub = 0;
+  uint32_t ksub = 0;  // centroids actually held per subspace (min(num_centroids, n_train))
+  int32_t metric = ISL_METRIC_EUCLIDEAN;  // pq.rs:146
+  bool trained = false;
+  int device = 0, sms = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<float> h_codebooks;      // [m][ksub][dsub]
+  isl::DevBuf<float> d_codebooks;      // [m][ksub][ld_sub]
+  mutable std::mutex mu;
+  isl::PqDev dev() const {
+    isl::PqDev p;
+    p.codebooks = d_codebooks.p;
+    p.m = (uint32_t)cfg.num_subquantizers;
+    p.ksub = ksub;
+    p.dsub = dsub;
+    p.ld_sub = ld_sub;
+    p.metric = metric;
+    return p;
+  }
+};
+
+struct isl_index {
+  isl_leann_config cfg{};
+  uint32_t dim = 0, ld = 0;
+  uint64_t n = 0;
+  int device = 0, sms = 0;
+  // CsrGraph (leann.rs:193-208), reference layout on the host for export
+  std::vector<uint64_t> h_offsets, h_nbrs, h_levels;
+  int64_t entry = ISL_NO_ENTRY;
+  uint64_t max_level = 0;
+  uint32_t max_degree = 0;
+  // resident in HBM
+  isl::DevBuf<float> vectors;    // [n][ld]
+  isl::DevBuf<float> sqnorms;    // [n]
+  isl::DevBuf<uint64_t> offsets; // [n+1]
+  isl::DevBuf<uint32_t> nbrs;    // [E]
+  // two-level search attachment
+  const isl_pq* pq = nullptr;
+  isl::DevBuf<uint8_t> codes8;    // [n][m] when ksub <= 256
+  isl::DevBuf<uint16_t> codes16;  // [n][m] otherwise
+  // per-handle stream, timing and scratch (guarded by mu: searches on one handle serialise)
+  mutable std::mutex mu;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  mutable float last_kernel_ms = 0.0f;
+  mutable uint64_t last_launches = 0;
+  mutable isl::DevBuf<uint32_t> visited;
+  mutable isl::DevBuf<uint2> r_global;
+  mutable isl::DevBuf<unsigned int> counters;  // [0] work counter, [1] error flag
+  mutable isl::DevBuf<float> q_stage;
+  mutable isl::DevBuf<uint64_t> out_ids;
+  mutable isl::DevBuf<float> out_dist;
+  mutable isl::DevBuf<uint32_t> out_count;
+  mutable isl::DevBuf<isl_search_stats> out_stats;
+  mutable isl::DevBuf<float> aux_f32;   // two-level: LUTs / approximate queues
+  mutable isl::DevBuf<uint2> aux_u2;
+  ~isl_index();
+};
+
+namespace isl {
+// Shared by api_index.cu and build.cu.
+isl_status index_alloc_common(isl_index* idx);
+isl_status index_finish_graph(isl_index* idx);  // uploads CSR, computes max degree
+template <class T>
+isl_status ensure(DevBuf<T>& b, size_t count) {
+  if (b.n >= count) return ISL_OK;
+  cudaError_t e = b.alloc(count);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
+  return ISL_OK;
+}
+}  // namespace isl

@@ -1,0 +1,58 @@
+// search.h — host-visible types of the batched best-first search (search_core.cuh / search.cu).
+#pragma once
+
+#include "common.cuh"
+
+namespace isl {
+
+struct SearchArgs {
+  // resident index
+  const float* vectors;     // [n][ld] f32, rows 16B aligned, zero padded to ld
+  const float* sqnorms;     // [n] Σ y² folded in reference order (cosine only)
+  uint32_t ld;
+  uint32_t d;
+  uint32_t n;
+  const uint64_t* offsets;  // CSR node_offsets [n+1]; nullptr => fixed-stride adjacency
+  const uint32_t* nbrs;     // CSR neighbours, or adjacency [n][adj_stride]
+  const uint32_t* degrees;  // fixed-stride mode: live degree per node
+  uint32_t adj_stride;
+  // queries
+  const float* queries;     // [nq][q_ld]
+  uint32_t q_ld;
+  uint32_t nq;
+  uint32_t entry;
+  uint32_t k;               // results written per query
+  uint32_t ef;              // already max(ef, k)
+  int32_t metric;
+  float prune_ratio;        // leann.rs:991-1056 (0 => identity)
+  int32_t strategy;
+  // scratch (per resident warp slot)
+  uint32_t* visited;        // [slots][vis_words]
+  uint32_t vis_words;
+  uint2* r_global;          // [slots][ef] when R does not fit shared memory
+  uint32_t u_cap;           // capacity of the unvisited list (>= max degree, multiple of 32)
+  // outputs
+  uint64_t* out_ids;        // [nq][k] (may be null)
+  uint32_t* out_ids32;      // [nq][k] (may be null; build path)
+  float* out_dist;          // [nq][k]
+  uint32_t* out_count;      // [nq]
+  isl_search_stats* stats;  // [nq] or null
+  unsigned int* work_counter;
+  unsigned int* error_flag; // set to 1 when the tie list overflows
+};
+
+struct SearchPlan {
+  size_t smem = 0;        // dynamic shared memory per one-warp CTA
+  int ctas_per_sm = 0;    // resident warps (= queries in flight) per SM
+  uint32_t grid = 0;      // resident warp slots on the device; scratch is sized for this many
+  bool r_in_smem = true;  // result array in shared memory (else L2-resident global memory)
+  int acc = 0;            // accumulation kind (dist_pass.cuh)
+};
+
+// Chooses the kernel variant, opts into the shared-memory size and reports the slot count.
+isl_status plan_search(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap, int sms, SearchPlan* plan);
+// Enqueues the search.  args.visited / args.r_global must cover plan.grid slots and
+// *args.work_counter / *args.error_flag must be zero.
+isl_status launch_search(const SearchPlan& plan, const SearchArgs& args, cudaStream_t st);
+
+}  // namespace isl

@@ -1,0 +1,311 @@
+// search_core.cuh — batched best-first graph search, one query per warp (one-warp CTAs).
+//
+// Restates the loop of LeannIndex::search_layer_recompute (src/core/leann.rs:899-988) and
+// search_layer_with_adjacency (leann.rs:692-749) with data structures chosen for a warp:
+//
+//   * results R: the reference's max-heap of (dist,id) bounded to ef is kept as an ASCENDING
+//     SORTED ARRAY of (dist,id|expanded-bit) — shared memory when it fits, L2-resident global
+//     memory otherwise.  The heap and the sorted array hold the same set because admission
+//     (`|R| < ef || d < worst.dist`, leann.rs:956-960) and eviction (pop max, :966-968) only
+//     depend on the order of the keys.
+//   * candidates C: the reference's unbounded min-heap is NOT materialised.  A candidate can
+//     still be expanded only while `!(|R| >= ef && d > worst.dist)` (leann.rs:924-928).  Every
+//     admitted, unexpanded node with d < worst.dist is in R; admitted nodes that were evicted
+//     from R stay expandable only while d == worst.dist — those rare entries are kept in a small
+//     `ties` list.  pop_min(C) is therefore "first unexpanded entry of R, else the smallest live
+//     tie"; the search ends when neither exists — exactly when the reference pops a stale
+//     candidate or drains C.
+//   * visited: exact bitset in global memory, one per resident warp; neighbours are marked
+//     visited BEFORE pruning (leann.rs:933-937), duplicates within a list keep the first.
+//   * exactly ONE candidate is expanded per iteration (multi-pop beams change ids).
+//   * distances: dist_pass.cuh (lane per candidate, reference-order fold); admission is then
+//     replayed sequentially in CSR order by the whole warp.
+#pragma once
+
+#include "dist_pass.cuh"
+#include "search.h"
+
+namespace isl {
+
+constexpr uint32_t kTieCap = 64;
+constexpr uint32_t kExpandedBit = 0x80000000u;
+
+template <int CH, int STAGES>
+__host__ __device__ constexpr size_t search_smem_bytes(uint32_t ld, uint32_t ef_smem, uint32_t u_cap) {
+  return (size_t)STAGES * StageGeom<CH>::STAGE_FLOATS * 4 + (size_t)ld * 4 + (size_t)ef_smem * 8 +
+         (size_t)u_cap * 4 + (size_t)kTieCap * 8;
+}
+
+template <bool R_SMEM>
+struct RView {
+  uint2* p;
+  __device__ __forceinline__ uint2 ld(uint32_t i) const {
+    if (R_SMEM) return p[i];
+    return __ldcg(p + i);
+  }
+  __device__ __forceinline__ void st(uint32_t i, uint2 v) const {
+    if (R_SMEM)
+      p[i] = v;
+    else
+      __stcg(p + i, v);
+  }
+};
+
+// leann.rs:991-1016 (Global / Local).  f32 arithmetic as in the reference.
+__device__ __forceinline__ uint32_t prune_keep(float prune_ratio, int strategy, uint32_t n_cands,
+                                               uint32_t r_len, uint32_t ef) {
+  if (prune_ratio == 0.0f || n_cands == 0) return n_cands;
+  const float fn = (float)n_cands;
+  uint32_t keep;
+  if (strategy == ISL_PRUNE_GLOBAL) {
+    const float ratio = __fdiv_rn((float)r_len, (float)ef);
+    keep = (uint32_t)ceilf(__fmul_rn(fn, __fsub_rn(1.0f, __fmul_rn(ratio, prune_ratio))));
+  } else {
+    keep = (uint32_t)ceilf(__fmul_rn(fn, __fsub_rn(1.0f, prune_ratio)));
+  }
+  if (keep < 1) keep = 1;
+  return keep < n_cands ? keep : n_cands;
+}
+
+template <int ACC, int CH, int STAGES, bool R_SMEM>
+__global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using G = StageGeom<CH>;
+  float* stage = reinterpret_cast<float*>(smem_raw);
+  float* q_smem = stage + STAGES * G::STAGE_FLOATS;
+  uint2* r_smem = reinterpret_cast<uint2*>(q_smem + a.ld);
+  uint32_t* u_list = reinterpret_cast<uint32_t*>(r_smem + (R_SMEM ? a.ef : 0));
+  uint2* ties = reinterpret_cast<uint2*>(u_list + a.u_cap);
+
+  const uint32_t lane = lane_id();
+  const uint32_t slot = blockIdx.x;
+  uint32_t* vis = a.visited + (size_t)slot * a.vis_words;
+  RView<R_SMEM> R{R_SMEM ? r_smem : a.r_global + (size_t)slot * a.ef};
+  const uint32_t ef = a.ef;
+
+  for (;;) {
+    uint32_t qi = 0;
+    if (lane == 0) qi = atomicAdd(a.work_counter, 1u);
+    qi = __shfl_sync(0xffffffffu, qi, 0);
+    if (qi >= a.nq) break;
+
+    // ---- per-query setup -------------------------------------------------------------
+    {
+      const float4* src = reinterpret_cast<const float4*>(a.queries + (size_t)qi * a.q_ld);
+      float4* dst = reinterpret_cast<float4*>(q_smem);
+      for (uint32_t i = lane; i < a.ld / 4; i += 32) dst[i] = src[i];
+      uint4* v4 = reinterpret_cast<uint4*>(vis);
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      for (uint32_t i = lane; i < a.vis_words / 4; i += 32) __stcg(v4 + i, z);
+    }
+    __threadfence();
+    __syncwarp();
+    const float na = (a.metric == ISL_METRIC_COSINE) ? smem_sqnorm_fold(q_smem, a.d) : 0.0f;
+
+    uint32_t r_len = 0, first_unexp = 0, n_ties = 0;
+    uint64_t n_hop = 0, n_edge = 0, n_dist = 0;
+
+    // ---- sorted insert into R (lowers to: binary search, warp shift, store) -------------
+    auto r_insert = [&](float dnew, uint32_t idnew) {
+      uint32_t lo = 0, hi = r_len;  // first position whose key is not < new key
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        const uint2 e = R.ld(mid);
+        if (key_lt(__uint_as_float(e.x), e.y & ~kExpandedBit, dnew, idnew))
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      const uint32_t pos = lo;
+      const bool full = (r_len == ef);
+      uint2 evicted = make_uint2(0, 0);
+      if (full) evicted = R.ld(ef - 1);
+      const int top = full ? (int)ef - 1 : (int)r_len;
+      for (int t = top; t > (int)pos; t -= 32) {
+        const int i = t - (int)lane;
+        const bool act = i > (int)pos;
+        uint2 e = make_uint2(0, 0);
+        if (act) e = R.ld(i - 1);
+        __syncwarp();
+        if (act) R.st(i, e);
+        __syncwarp();
+      }
+      if (lane == 0) R.st(pos, make_uint2(__float_as_uint(dnew), idnew));
+      __syncwarp();
+      if (!full) r_len++;
+      if (pos <= first_unexp) first_unexp = pos;
+      if (full && !(evicted.y & kExpandedBit)) {
+        // An evicted, unexpanded node stays expandable while its distance equals the worst
+        // distance in R (leann.rs:924-928 uses a strict `>`).
+        const uint2 w = R.ld(ef - 1);
+        const float wd = __uint_as_float(w.x), edist = __uint_as_float(evicted.x);
+        if (!of_lt(wd, edist)) {
+          if (n_ties == kTieCap) {  // drop stale ties first
+            uint32_t kept = 0;
+            for (uint32_t i = 0; i < n_ties; ++i) {
+              const uint2 t = ties[i];
+              if (!of_lt(wd, __uint_as_float(t.x))) {
+                __syncwarp();
+                if (lane == 0) ties[kept] = t;
+                kept++;
+              }
+            }
+            n_ties = kept;
+            __syncwarp();
+          }
+          if (n_ties == kTieCap) {
+            if (lane == 0) atomicExch(a.error_flag, 1u);
+          } else {
+            if (lane == 0) ties[n_ties] = evicted;
+            n_ties++;
+            __syncwarp();
+          }
+        }
+      }
+    };
+
+    // ---- distances of u_list[base .. base+cnt) and their sequential admission ------------
+    auto score_and_admit = [&](uint32_t base, uint32_t cnt) {
+      const float acc = warp_rows_fold<ACC, CH, STAGES>(a.vectors, a.ld, a.d, u_list + base, cnt,
+                                                        q_smem, stage);
+      float dn = 0.0f;
+      uint32_t cid = 0;
+      if (lane < cnt) {
+        cid = u_list[base + lane];
+        const float nb = (a.metric == ISL_METRIC_COSINE) ? __ldg(a.sqnorms + cid) : 0.0f;
+        dn = finalize_distance(a.metric, acc, na, nb);
+      }
+      float worst = 0.0f;
+      if (r_len > 0) worst = __uint_as_float(R.ld(r_len - 1).x);
+      uint32_t mask = __ballot_sync(0xffffffffu, lane < cnt && (r_len < ef || dn < worst));
+      while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float dj = __shfl_sync(0xffffffffu, dn, j);
+        const uint32_t idj = __shfl_sync(0xffffffffu, cid, j);
+        bool add = r_len < ef;
+        if (!add) add = dj < __uint_as_float(R.ld(ef - 1).x);  // raw f32 `<` (leann.rs:959)
+        if (add) r_insert(dj, idj);
+      }
+    };
+
+    // ---- entry point (leann.rs:911-916) ----------------------------------------------------
+    if (lane == 0) {
+      u_list[0] = a.entry;
+      atomicOr(vis + (a.entry >> 5), 1u << (a.entry & 31));
+    }
+    __syncwarp();
+    score_and_admit(0, 1);
+    n_dist = 1;
+
+    // ---- main loop (leann.rs:922-972) ------------------------------------------------------
+    for (;;) {
+      uint32_t cur;
+      if (first_unexp < r_len) {
+        uint2 e = R.ld(first_unexp);
+        cur = e.y;
+        __syncwarp();
+        if (lane == 0) R.st(first_unexp, make_uint2(e.x, e.y | kExpandedBit));
+        __syncwarp();
+        // advance to the next unexpanded entry
+        uint32_t nxt = r_len;
+        for (uint32_t b = first_unexp + 1; b < r_len; b += 32) {
+          const uint32_t i = b + lane;
+          const bool un = i < r_len && !(R.ld(i).y & kExpandedBit);
+          const uint32_t bal = __ballot_sync(0xffffffffu, un);
+          if (bal) {
+            nxt = b + __ffs(bal) - 1;
+            break;
+          }
+        }
+        first_unexp = nxt;
+      } else {
+        // smallest live tie, if any
+        const float wd = __uint_as_float(R.ld(r_len - 1).x);
+        int best = -1;
+        for (uint32_t i = 0; i < n_ties; ++i) {
+          const uint2 t = ties[i];
+          if (r_len >= ef && of_lt(wd, __uint_as_float(t.x))) continue;  // stale
+          if (best < 0 || key_lt(__uint_as_float(t.x), t.y, __uint_as_float(ties[best].x), ties[best].y))
+            best = (int)i;
+        }
+        if (best < 0) break;
+        cur = ties[best].y;
+        __syncwarp();
+        if (lane == 0) ties[best] = ties[n_ties - 1];
+        n_ties--;
+        __syncwarp();
+      }
+
+      // neighbour list of `cur`
+      uint64_t start;
+      uint32_t deg;
+      if (a.offsets) {
+        start = __ldg(a.offsets + cur);
+        deg = (uint32_t)(__ldg(a.offsets + cur + 1) - start);
+      } else {
+        start = (uint64_t)cur * a.adj_stride;
+        deg = __ldg(a.degrees + cur);
+      }
+      n_hop++;
+      n_edge += deg;
+
+      // unvisited neighbours, in list order (leann.rs:933-937)
+      uint32_t ucnt = 0;
+      for (uint32_t b = 0; b < deg; b += 32) {
+        const uint32_t i = b + lane;
+        const bool valid = i < deg;
+        uint32_t nid = 0xffffffffu;
+        if (valid) nid = __ldg(a.nbrs + start + i);
+        const uint32_t same = __match_any_sync(0xffffffffu, nid);
+        const bool first = lane == (uint32_t)(__ffs(same) - 1);
+        bool unv = false;
+        if (valid && first && nid < a.n) {
+          const uint32_t bit = 1u << (nid & 31);
+          const uint32_t old = atomicOr(vis + (nid >> 5), bit);
+          unv = !(old & bit);
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, unv);
+        if (unv) u_list[ucnt + __popc(bal & ((1u << lane) - 1))] = nid;
+        ucnt += __popc(bal);
+      }
+      __syncwarp();
+      if (ucnt == 0) continue;  // leann.rs:939-941
+
+      const uint32_t keep = prune_keep(a.prune_ratio, a.strategy, ucnt, r_len, ef);  // :944
+      n_dist += keep;
+      for (uint32_t b = 0; b < keep; b += 32) score_and_admit(b, min(32u, keep - b));
+    }
+
+    // ---- results: R is already sorted by (dist,id); take(k) (leann.rs:895) -----------------
+    const uint32_t cnt = r_len < a.k ? r_len : a.k;
+    for (uint32_t i = lane; i < a.k; i += 32) {
+      uint32_t id = 0xffffffffu;
+      float dist = __int_as_float(0x7f800000);
+      if (i < cnt) {
+        const uint2 e = R.ld(i);
+        id = e.y & ~kExpandedBit;
+        dist = __uint_as_float(e.x);
+      }
+      const size_t o = (size_t)qi * a.k + i;
+      if (a.out_ids) a.out_ids[o] = i < cnt ? (uint64_t)id : ISL_INVALID_ID;
+      if (a.out_ids32) a.out_ids32[o] = id;
+      a.out_dist[o] = dist;
+    }
+    if (lane == 0) {
+      if (a.out_count) a.out_count[qi] = cnt;
+      if (a.stats) {
+        isl_search_stats s;
+        s.n_hop = n_hop;
+        s.n_edge = n_edge;
+        s.n_dist = n_dist;
+        s.n_adc = 0;
+        s.n_rerank = 0;
+        a.stats[qi] = s;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace isl

@@ -1,0 +1,116 @@
+"""GPU best-first search vs the oracle (leann.rs:868-988) on identical graphs and inputs:
+ids bit-exact, distances bit-exact (bar: 1e-5 relative), counters equal."""
+import numpy as np
+import pytest
+
+from conftest import oracle_graph, uniform
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(orc, cfg, v, off, nbrs, entry, levels, queries, k, ef):
+    from islands_b200 import LeannIndex
+
+    idx = LeannIndex.from_csr(cfg, v, off, nbrs, levels, entry)
+    ids, dist, cnt, st = idx.search_batch(queries, k, ef, stats=True)
+    o_ids, o_dist, o_cnt, o_st = orc.leann_search(cfg._s, v, off, nbrs, entry, queries, k, ef, threads=8, stats=True)
+    assert np.array_equal(cnt, o_cnt)
+    assert np.array_equal(ids, o_ids)
+    # fp32 bar from north_star is 1e-5 relative; the kernels reproduce the fold order, so bits match
+    assert np.array_equal(dist.view(np.uint32), o_dist.view(np.uint32))
+    np.testing.assert_allclose(dist, o_dist, rtol=1e-5)
+    for f in ("n_hop", "n_edge", "n_dist"):
+        assert np.array_equal(getattr(st, f), o_st[f]), f
+    idx.free()
+
+
+@pytest.mark.parametrize("metric", [0, 1, 2, 3])
+@pytest.mark.parametrize("n,d", [(1000, 32), (4000, 96)])
+def test_search_matches_oracle(gpu_lib, orc, metric, n, d):
+    cfg, v, levels, off, nbrs, entry = oracle_graph(orc, n, d, seed=11, metric=metric)
+    q = uniform(np.random.RandomState(5), 200, d)
+    for k, ef in [(1, 10), (10, 64), (50, 50), (10, 512)]:
+        _compare(orc, cfg, v, off, nbrs, entry, levels, q, k, ef)
+
+
+def test_search_768d(gpu_lib, orc):
+    cfg, v, levels, off, nbrs, entry = oracle_graph(orc, 3000, 768, seed=3, batch=64)
+    q = uniform(np.random.RandomState(6), 128, 768)
+    _compare(orc, cfg, v, off, nbrs, entry, levels, q, 10, 64)
+    _compare(orc, cfg, v, off, nbrs, entry, levels, q, 10, 300)
+
+
+def test_search_odd_dimension(gpu_lib, orc):
+    # d not a multiple of 4 or of the staging slice: padded rows, guarded tail
+    cfg, v, levels, off, nbrs, entry = oracle_graph(orc, 1500, 70, seed=4)
+    q = uniform(np.random.RandomState(7), 100, 70)
+    _compare(orc, cfg, v, off, nbrs, entry, levels, q, 10, 64)
+
+
+def test_search_ties_duplicate_vectors(gpu_lib, orc):
+    # duplicate vectors force exact distance ties: (dist,id) order must decide identically
+    cfg, v, levels, off, nbrs, entry = oracle_graph(orc, 1200, 32, seed=9, dup=300)
+    q = np.concatenate([v[:64], uniform(np.random.RandomState(8), 64, 32)])
+    for k, ef in [(10, 16), (10, 64), (30, 30)]:
+        _compare(orc, cfg, v, off, nbrs, entry, levels, q, k, ef)
+
+
+def test_search_large_ef_global_results(gpu_lib, orc):
+    # ef above the shared-memory bound -> result array in global memory
+    cfg, v, levels, off, nbrs, entry = oracle_graph(orc, 4000, 32, seed=12)
+    q = uniform(np.random.RandomState(9), 64, 32)
+    _compare(orc, cfg, v, off, nbrs, entry, levels, q, 10, 3000)
+
+
+@pytest.mark.parametrize("strategy", [0, 1])
+@pytest.mark.parametrize("ratio", [0.3, 0.7])
+def test_search_with_pruning(gpu_lib, orc, strategy, ratio):
+    # leann.rs:991-1016 Global / Local frontier pruning
+    from islands_b200 import LeannConfig
+
+    cfg0, v, levels, off, nbrs, entry = oracle_graph(orc, 2000, 32, seed=13)
+    cfg = LeannConfig(prune_ratio=ratio, pruning_strategy=strategy)
+    q = uniform(np.random.RandomState(10), 100, 32)
+    _compare(orc, cfg, v, off, nbrs, entry, levels, q, 10, 64)
+
+
+def test_search_k_larger_than_n_and_ef_smaller_than_k(gpu_lib, orc):
+    cfg, v, levels, off, nbrs, entry = oracle_graph(orc, 40, 16, seed=14)
+    q = uniform(np.random.RandomState(11), 10, 16)
+    _compare(orc, cfg, v, off, nbrs, entry, levels, q, 64, 8)  # ef := max(ef,k); fewer than k results
+
+
+def test_search_reference_properties(gpu_lib, orc):
+    """Properties the reference's own tests pin (leann.rs:1289-1343, 1388-1433)."""
+    from islands_b200 import LeannIndex
+
+    cfg, v, levels, off, nbrs, entry = oracle_graph(orc, 200, 32, seed=15, m=48, m0=96, ef_construction=400)
+    idx = LeannIndex.from_csr(cfg, v, off, nbrs, levels, entry)
+    res = idx.search(v[0], 5)
+    assert res[0][0] == 0 and res[0][1] < 0.01  # self query (leann.rs:1289-1304)
+    res = idx.search_with_params(uniform(np.random.RandomState(1), 1, 32)[0], 20, 128)
+    d = [r[1] for r in res]
+    assert d == sorted(d) and len(res) == 20 and all(0 <= r[0] < 200 for r in res)
+    # recall@1 >= 0.35 floor (leann.rs:1388-1433)
+    q = uniform(np.random.RandomState(2), 20, 32)
+    ids, _, _ = idx.search_batch(q, 1, 128)
+    gt = np.array([np.argmin(orc.distance_batch(0, qq, v)) for qq in q])
+    assert (ids[:, 0] == gt).mean() >= 0.35
+
+
+def test_search_errors(gpu_lib, orc):
+    from islands_b200 import DimensionMismatch, IndexNotBuilt, InvalidConfig, LeannConfig, LeannIndex
+
+    cfg, v, levels, off, nbrs, entry = oracle_graph(orc, 200, 32, seed=15, m=48, m0=96, ef_construction=400)
+    idx = LeannIndex.from_csr(cfg, v, off, nbrs, levels, entry)
+    with pytest.raises(DimensionMismatch):  # leann.rs:880-887
+        idx.search(np.zeros(16, np.float32), 5)
+    noentry = LeannIndex.from_csr(cfg, v, off, nbrs, levels, None)
+    with pytest.raises(IndexNotBuilt):  # leann.rs:889
+        noentry.search(v[0], 5)
+    empty = LeannIndex.from_csr(cfg, np.zeros((0, 32), np.float32), [0], [], None, None)
+    assert empty.search(v[0], 5) == []  # leann.rs:875-877
+    assert len(empty) == 0 and empty.is_empty()
+    prop = LeannIndex.from_csr(LeannConfig(prune_ratio=0.5, pruning_strategy=2), v, off, nbrs, levels, entry)
+    with pytest.raises(InvalidConfig):
+        prop.search(v[0], 5)
