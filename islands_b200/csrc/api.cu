@@ -84,7 +84,7 @@ isl_status index_finish_graph(isl_index* idx) {
   return ISL_OK;
 }
 
-static void fill_empty(uint64_t nq, uint32_t k, uint64_t* ids, float* dist, uint32_t* count,
+void fill_empty(uint64_t nq, uint32_t k, uint64_t* ids, float* dist, uint32_t* count,
                        isl_search_stats* stats) {
   for (uint64_t i = 0; i < nq * (uint64_t)k; ++i) {
     if (ids) ids[i] = ISL_INVALID_ID;
@@ -148,7 +148,7 @@ static isl_status search_device(const isl_index* idx, const float* d_queries, ui
   return ISL_OK;
 }
 
-static isl_status search_finish(const isl_index* idx) {
+isl_status search_finish(const isl_index* idx) {
   unsigned int h[4] = {0, 0, 0, 0};
   ISL_CUDA_TRY(cudaMemcpyAsync(h, idx->counters.p, sizeof(h), cudaMemcpyDeviceToHost, idx->stream));
   ISL_CUDA_TRY(cudaStreamSynchronize(idx->stream));
@@ -160,7 +160,7 @@ static isl_status search_finish(const isl_index* idx) {
   return ISL_OK;
 }
 
-static isl_status search_checks(const isl_index* idx, const void* queries, uint64_t nq,
+isl_status search_checks(const isl_index* idx, const void* queries, uint64_t nq,
                                 uint32_t query_dim, uint32_t k, uint32_t* ef, bool* trivial) {
   *trivial = false;
   if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");

@@ -93,6 +93,11 @@ namespace isl {
 // Shared by api_index.cu and build.cu.
 isl_status index_alloc_common(isl_index* idx);
 isl_status index_finish_graph(isl_index* idx);  // uploads CSR, computes max degree
+void fill_empty(uint64_t nq, uint32_t k, uint64_t* ids, float* dist, uint32_t* count, isl_search_stats* stats);
+isl_status search_checks(const isl_index* idx, const void* queries, uint64_t nq, uint32_t query_dim, uint32_t k,
+                         uint32_t* ef, bool* trivial);
+isl_status search_finish(const isl_index* idx);
+isl_status pq_upload_codebooks(isl_pq* pq);
 template <class T>
 isl_status ensure(DevBuf<T>& b, size_t count) {
   if (b.n >= count) return ISL_OK;

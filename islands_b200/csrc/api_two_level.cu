@@ -1,0 +1,142 @@
+// api_two_level.cu — two-level search: PQ ADC traversal + exact rerank.
+// The reference has no code for this composition (src/core/leann.rs:54-56 says so); it is
+// defined from docs/leann-specification.md:223-269 and the PQ primitives pq.rs:307-348, and
+// restated on the CPU in oracle/orc_leann_search_two_level.  Parity is oracle<->GPU only.
+#include <algorithm>
+#include <cmath>
+
+#include "api_common.h"
+
+using namespace isl;
+
+extern "C" {
+
+isl_status isl_index_attach_pq(isl_index* idx, const isl_pq* pq, const uint16_t* codes) {
+  if (!idx || !pq) return fail(ISL_INVALID_ARGUMENT, "null handle");
+  if (!pq->trained) return fail(ISL_PQ_ERROR, "Quantizer not trained");
+  if (pq->dim != idx->dim && idx->n)
+    return fail(ISL_DIM_MISMATCH, "dimension mismatch: expected " + std::to_string(idx->dim) + ", got " +
+                                      std::to_string(pq->dim));
+  if (idx->n && !codes) return fail(ISL_INVALID_ARGUMENT, "codes is null");
+  DeviceGuard g(idx->device);
+  std::lock_guard<std::mutex> lock(idx->mu);
+  const uint32_t m = (uint32_t)pq->cfg.num_subquantizers;
+  const uint64_t total = idx->n * m;
+  for (uint64_t i = 0; i < total; ++i)
+    if (codes[i] >= pq->ksub) return fail(ISL_PQ_ERROR, "Invalid code " + std::to_string(codes[i]));
+  idx->codes8.release();
+  idx->codes16.release();
+  if (pq->ksub <= 256) {  // PQConfig::bytes_per_vector (pq.rs:58-64): one byte per code
+    std::vector<uint8_t> c8(total);
+    for (uint64_t i = 0; i < total; ++i) c8[i] = (uint8_t)codes[i];
+    ISL_CUDA_TRY(idx->codes8.alloc(std::max<uint64_t>(total, 1)));
+    if (total) ISL_CUDA_TRY(cudaMemcpy(idx->codes8.p, c8.data(), total, cudaMemcpyHostToDevice));
+  } else {
+    ISL_CUDA_TRY(idx->codes16.alloc(std::max<uint64_t>(total, 1)));
+    if (total) ISL_CUDA_TRY(cudaMemcpy(idx->codes16.p, codes, total * 2, cudaMemcpyHostToDevice));
+  }
+  idx->pq = pq;
+  return ISL_OK;
+}
+
+isl_status isl_index_search_two_level(const isl_index* idx, const float* queries, uint64_t nq,
+                                      uint32_t query_dim, uint32_t k, uint32_t ef, float rerank_ratio,
+                                      uint64_t* out_ids, float* out_dist, uint32_t* out_count,
+                                      isl_search_stats* stats) {
+  bool trivial;
+  ISL_TRY(search_checks(idx, queries, nq, query_dim, k, &ef, &trivial));
+  if (trivial) {
+    fill_empty(nq, k, out_ids, out_dist, out_count, stats);
+    return ISL_OK;
+  }
+  if (!idx->pq) return fail(ISL_PQ_ERROR, "no product quantizer attached (isl_index_attach_pq)");
+  if (!(rerank_ratio > 0.0f) || rerank_ratio > 1.0f)
+    return fail(ISL_INVALID_ARGUMENT, "rerank_ratio must be in (0, 1]");
+  if (!out_ids || !out_dist) return fail(ISL_INVALID_ARGUMENT, "output pointer is null");
+  const isl_pq* pq = idx->pq;
+  DeviceGuard g(idx->device);
+  std::lock_guard<std::mutex> lock(idx->mu);
+  const uint32_t m = (uint32_t)pq->cfg.num_subquantizers;
+  const uint32_t lut_floats = m * pq->ksub;
+
+  // |AQ| <= max_degree / a at all times (it gains at most max_degree entries per expansion and
+  // then loses ceil(a * |AQ|)); one spare entry per insertion batch keeps the bound simple.
+  const uint32_t maxdeg = std::max<uint32_t>(idx->max_degree, 1);
+  const uint64_t aq_cap64 = (uint64_t)std::ceil((double)maxdeg / (double)rerank_ratio) + maxdeg + 2;
+  if (aq_cap64 > (1u << 22)) return fail(ISL_INVALID_ARGUMENT, "rerank_ratio too small for this graph degree");
+  const uint32_t aq_cap = (uint32_t)aq_cap64;
+  const uint32_t u_cap = std::max<uint32_t>(32, round_up(maxdeg + 1, 32));
+
+  SearchPlan plan;
+  ISL_TRY(plan_search_two_level(idx->cfg.metric, idx->ld, ef, u_cap, m, pq->ksub, aq_cap, idx->sms, &plan));
+  const uint32_t vis_words = round_up((uint32_t)((idx->n + 31) / 32), 4);
+  const uint32_t slots = (uint32_t)std::min<uint64_t>(plan.grid, nq);
+  ISL_TRY(ensure(idx->visited, (size_t)slots * vis_words));
+  if (!plan.r_in_smem) ISL_TRY(ensure(idx->r_global, (size_t)slots * ef));
+  if (!plan.aq_smem_entries) ISL_TRY(ensure(idx->aux_u2, (size_t)slots * aq_cap));
+  ISL_TRY(ensure(idx->aux_f32, (size_t)nq * lut_floats + 2));
+  ISL_TRY(ensure(idx->q_stage, nq * idx->ld));
+  ISL_TRY(ensure(idx->out_ids, nq * k));
+  ISL_TRY(ensure(idx->out_dist, nq * k));
+  ISL_TRY(ensure(idx->out_count, nq));
+  if (stats) ISL_TRY(ensure(idx->out_stats, nq));
+  cudaStream_t st = idx->stream;
+  if (idx->ld != idx->dim) ISL_CUDA_TRY(cudaMemsetAsync(idx->q_stage.p, 0, nq * idx->ld * 4, st));
+  ISL_CUDA_TRY(cudaMemcpy2DAsync(idx->q_stage.p, (size_t)idx->ld * 4, queries, (size_t)idx->dim * 4,
+                                 (size_t)idx->dim * 4, nq, cudaMemcpyHostToDevice, st));
+  ISL_CUDA_TRY(cudaMemsetAsync(idx->counters.p, 0, 4 * sizeof(unsigned int), st));
+
+  ISL_CUDA_TRY(cudaEventRecord(idx->ev0, st));
+  // K3: per-query tables LUT[j][c] = Σ (q - c)^2 (pq.rs:307-338), then the traversal.
+  ISL_TRY(launch_pq_tables(pq->dev(), idx->q_stage.p, idx->ld, nq, idx->aux_f32.p, idx->sms, st));
+
+  SearchArgs a{};
+  a.vectors = idx->vectors.p;
+  a.sqnorms = idx->sqnorms.p;
+  a.ld = idx->ld;
+  a.d = idx->dim;
+  a.n = (uint32_t)idx->n;
+  a.offsets = idx->offsets.p;
+  a.nbrs = idx->nbrs.p;
+  a.queries = idx->q_stage.p;
+  a.q_ld = idx->ld;
+  a.nq = (uint32_t)nq;
+  a.entry = (uint32_t)idx->entry;
+  a.k = k;
+  a.ef = ef;
+  a.metric = idx->cfg.metric;
+  a.prune_ratio = 0.0f;  // the PQ queue replaces the frontier pruning strategies (leann.rs:351-353)
+  a.strategy = 0;
+  a.visited = idx->visited.p;
+  a.vis_words = vis_words;
+  a.r_global = idx->r_global.p;
+  a.u_cap = u_cap;
+  a.out_ids = idx->out_ids.p;
+  a.out_dist = idx->out_dist.p;
+  a.out_count = idx->out_count.p;
+  a.stats = stats ? idx->out_stats.p : nullptr;
+  a.work_counter = idx->counters.p;
+  a.error_flag = idx->counters.p + 1;
+  a.luts = idx->aux_f32.p;
+  a.codes8 = idx->codes8.p;
+  a.codes16 = idx->codes8.p ? nullptr : idx->codes16.p;
+  a.pq_m = m;
+  a.pq_ksub = pq->ksub;
+  a.rerank_ratio = rerank_ratio;
+  a.aq_cap = aq_cap;
+  a.aq_global = idx->aux_u2.p;
+  a.lut_smem_floats = plan.lut_smem_floats;
+  a.aq_smem_entries = plan.aq_smem_entries;
+  ISL_TRY(launch_search(plan, a, st));
+  ISL_CUDA_TRY(cudaEventRecord(idx->ev1, st));
+  idx->last_launches = 2;
+
+  ISL_CUDA_TRY(cudaMemcpyAsync(out_ids, idx->out_ids.p, nq * k * 8, cudaMemcpyDeviceToHost, st));
+  ISL_CUDA_TRY(cudaMemcpyAsync(out_dist, idx->out_dist.p, nq * k * 4, cudaMemcpyDeviceToHost, st));
+  if (out_count) ISL_CUDA_TRY(cudaMemcpyAsync(out_count, idx->out_count.p, nq * 4, cudaMemcpyDeviceToHost, st));
+  if (stats)
+    ISL_CUDA_TRY(cudaMemcpyAsync(stats, idx->out_stats.p, nq * sizeof(isl_search_stats), cudaMemcpyDeviceToHost, st));
+  return search_finish(idx);
+}
+
+}  // extern "C"

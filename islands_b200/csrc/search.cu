@@ -13,11 +13,14 @@ constexpr int kStages = 3;
 // R (8 B per entry) stays in shared memory up to this many entries; above, it lives in an
 // L2-resident global buffer so that enough warps stay resident per SM.
 constexpr uint32_t kEfSmemMax = 2048;
+constexpr uint32_t kLutSmemMaxFloats = 8192;  // 32 KB of PQ tables per query in shared memory
+constexpr uint32_t kAqSmemMaxEntries = 2048;  // 16 KB approximate queue in shared memory
 
-template <int ACC, bool R_SMEM>
+template <int ACC, bool R_SMEM, bool TWO>
 isl_status plan_one(uint32_t ld, uint32_t ef, uint32_t u_cap, int sms, SearchPlan* plan) {
-  auto kern = leann_search_kernel<ACC, kCH, kStages, R_SMEM>;
-  const size_t smem = search_smem_bytes<kCH, kStages>(ld, R_SMEM ? ef : 0, u_cap);
+  auto kern = leann_search_kernel<ACC, kCH, kStages, R_SMEM, TWO>;
+  const size_t smem = search_smem_bytes<kCH, kStages>(ld, R_SMEM ? ef : 0, u_cap, plan->lut_smem_floats,
+                                                      plan->aq_smem_entries);
   if (smem > 227 * 1024)
     return fail(ISL_INVALID_ARGUMENT, "search: dimension / ef need more than 227 KB of shared memory per warp");
   ISL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -31,23 +34,20 @@ isl_status plan_one(uint32_t ld, uint32_t ef, uint32_t u_cap, int sms, SearchPla
   return ISL_OK;
 }
 
-template <int ACC, bool R_SMEM>
+template <int ACC, bool R_SMEM, bool TWO>
 isl_status launch_one(const SearchPlan& plan, const SearchArgs& args, uint32_t grid, cudaStream_t st) {
-  leann_search_kernel<ACC, kCH, kStages, R_SMEM><<<grid, 32, plan.smem, st>>>(args);
+  leann_search_kernel<ACC, kCH, kStages, R_SMEM, TWO><<<grid, 32, plan.smem, st>>>(args);
   count_launch();
   ISL_CUDA_TRY(cudaGetLastError());
   return ISL_OK;
 }
-}  // namespace
 
-isl_status plan_search(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap, int sms, SearchPlan* plan) {
-  const bool r_smem = ef <= kEfSmemMax;
-  const int acc = acc_kind_of_metric(metric);
-  plan->acc = acc;
-#define ISL_PLAN(A)                                                          \
-  case A:                                                                    \
-    return r_smem ? plan_one<A, true>(ld, ef, u_cap, sms, plan)              \
-                  : plan_one<A, false>(ld, ef, u_cap, sms, plan);
+template <bool TWO>
+isl_status plan_dispatch(int acc, bool r_smem, uint32_t ld, uint32_t ef, uint32_t u_cap, int sms, SearchPlan* plan) {
+#define ISL_PLAN(A)                                                                \
+  case A:                                                                          \
+    return r_smem ? plan_one<A, true, TWO>(ld, ef, u_cap, sms, plan)               \
+                  : plan_one<A, false, TWO>(ld, ef, u_cap, sms, plan);
   switch (acc) {
     ISL_PLAN(ACC_DOT)
     ISL_PLAN(ACC_L2)
@@ -57,13 +57,12 @@ isl_status plan_search(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap,
   return fail(ISL_INVALID_CONFIG, "search: unknown metric");
 }
 
-isl_status launch_search(const SearchPlan& plan, const SearchArgs& args, cudaStream_t st) {
-  // Never launch more warps than queries: idle slots would only clear their bitsets.
-  const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(plan.grid, args.nq));
-#define ISL_LAUNCH(A)                                                        \
-  case A:                                                                    \
-    return plan.r_in_smem ? launch_one<A, true>(plan, args, grid, st)        \
-                          : launch_one<A, false>(plan, args, grid, st);
+template <bool TWO>
+isl_status launch_dispatch(const SearchPlan& plan, const SearchArgs& args, uint32_t grid, cudaStream_t st) {
+#define ISL_LAUNCH(A)                                                              \
+  case A:                                                                          \
+    return plan.r_in_smem ? launch_one<A, true, TWO>(plan, args, grid, st)         \
+                          : launch_one<A, false, TWO>(plan, args, grid, st);
   switch (plan.acc) {
     ISL_LAUNCH(ACC_DOT)
     ISL_LAUNCH(ACC_L2)
@@ -71,6 +70,34 @@ isl_status launch_search(const SearchPlan& plan, const SearchArgs& args, cudaStr
   }
 #undef ISL_LAUNCH
   return fail(ISL_INVALID_CONFIG, "search: unknown metric");
+}
+}  // namespace
+
+isl_status plan_search(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap, int sms, SearchPlan* plan) {
+  plan->acc = acc_kind_of_metric(metric);
+  plan->two_level = false;
+  plan->lut_smem_floats = 0;
+  plan->aq_smem_entries = 0;
+  plan->aq_cap = 0;
+  return plan_dispatch<false>(plan->acc, ef <= kEfSmemMax, ld, ef, u_cap, sms, plan);
+}
+
+isl_status plan_search_two_level(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap, uint32_t pq_m,
+                                 uint32_t pq_ksub, uint32_t aq_cap, int sms, SearchPlan* plan) {
+  plan->acc = acc_kind_of_metric(metric);
+  plan->two_level = true;
+  const uint32_t lut_floats = (pq_m * pq_ksub + 1u) & ~1u;  // even: keeps the queue 8-byte aligned
+  plan->lut_smem_floats = lut_floats <= kLutSmemMaxFloats ? lut_floats : 0;
+  plan->aq_cap = aq_cap;
+  plan->aq_smem_entries = aq_cap <= kAqSmemMaxEntries ? aq_cap : 0;
+  return plan_dispatch<true>(plan->acc, ef <= kEfSmemMax, ld, ef, u_cap, sms, plan);
+}
+
+isl_status launch_search(const SearchPlan& plan, const SearchArgs& args, cudaStream_t st) {
+  // Never launch more warps than queries: idle slots would only clear their bitsets.
+  const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(plan.grid, args.nq));
+  return plan.two_level ? launch_dispatch<true>(plan, args, grid, st)
+                        : launch_dispatch<false>(plan, args, grid, st);
 }
 
 }  // namespace isl

@@ -39,6 +39,16 @@ struct SearchArgs {
   isl_search_stats* stats;  // [nq] or null
   unsigned int* work_counter;
   unsigned int* error_flag; // set to 1 when the tie list overflows
+  // two-level search: PQ ADC traversal + exact rerank (docs/leann-specification.md:223-269)
+  const float* luts;        // [nq][pq_m*pq_ksub] squared-L2 tables (pq.rs:307-338)
+  const uint8_t* codes8;    // [n][pq_m] when pq_ksub <= 256
+  const uint16_t* codes16;  // [n][pq_m] otherwise
+  uint32_t pq_m, pq_ksub;
+  float rerank_ratio;
+  uint32_t aq_cap;          // capacity of the approximate queue (entries)
+  uint2* aq_global;         // [slots][aq_cap] when the queue does not fit shared memory
+  uint32_t lut_smem_floats; // pq_m*pq_ksub when the table is staged in shared memory, else 0
+  uint32_t aq_smem_entries; // aq_cap when the queue lives in shared memory, else 0
 };
 
 struct SearchPlan {
@@ -47,10 +57,16 @@ struct SearchPlan {
   uint32_t grid = 0;      // resident warp slots on the device; scratch is sized for this many
   bool r_in_smem = true;  // result array in shared memory (else L2-resident global memory)
   int acc = 0;            // accumulation kind (dist_pass.cuh)
+  bool two_level = false;
+  uint32_t lut_smem_floats = 0;  // PQ table staged in shared memory (0 => read from global/L2)
+  uint32_t aq_smem_entries = 0;  // approximate queue in shared memory (0 => global/L2)
+  uint32_t aq_cap = 0;
 };
 
 // Chooses the kernel variant, opts into the shared-memory size and reports the slot count.
 isl_status plan_search(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap, int sms, SearchPlan* plan);
+isl_status plan_search_two_level(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap, uint32_t pq_m,
+                                 uint32_t pq_ksub, uint32_t aq_cap, int sms, SearchPlan* plan);
 // Enqueues the search.  args.visited / args.r_global must cover plan.grid slots and
 // *args.work_counter / *args.error_flag must be zero.
 isl_status launch_search(const SearchPlan& plan, const SearchArgs& args, cudaStream_t st);

@@ -31,9 +31,10 @@ constexpr uint32_t kTieCap = 64;
 constexpr uint32_t kExpandedBit = 0x80000000u;
 
 template <int CH, int STAGES>
-__host__ __device__ constexpr size_t search_smem_bytes(uint32_t ld, uint32_t ef_smem, uint32_t u_cap) {
+__host__ __device__ constexpr size_t search_smem_bytes(uint32_t ld, uint32_t ef_smem, uint32_t u_cap,
+                                                       uint32_t lut_floats = 0, uint32_t aq_entries = 0) {
   return (size_t)STAGES * StageGeom<CH>::STAGE_FLOATS * 4 + (size_t)ld * 4 + (size_t)ef_smem * 8 +
-         (size_t)u_cap * 4 + (size_t)kTieCap * 8;
+         (size_t)u_cap * 4 + (size_t)kTieCap * 8 + (size_t)lut_floats * 4 + (size_t)aq_entries * 8;
 }
 
 template <bool R_SMEM>
@@ -67,7 +68,11 @@ __device__ __forceinline__ uint32_t prune_keep(float prune_ratio, int strategy, 
   return keep < n_cands ? keep : n_cands;
 }
 
-template <int ACC, int CH, int STAGES, bool R_SMEM>
+// TWO = two-level search: unvisited neighbours are scored with the PQ table distance
+// (pq.rs:341-348) into an approximate queue AQ ordered by (adc,id); after every expansion the
+// ceil(a*|AQ|) best entries (at least one) leave AQ, get their exact distance and go through the
+// same admission as the exact search.  Since |AQ| <= max_degree / a, AQ is a sorted array too.
+template <int ACC, int CH, int STAGES, bool R_SMEM, bool TWO>
 __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using G = StageGeom<CH>;
@@ -76,9 +81,21 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
   uint2* r_smem = reinterpret_cast<uint2*>(q_smem + a.ld);
   uint32_t* u_list = reinterpret_cast<uint32_t*>(r_smem + (R_SMEM ? a.ef : 0));
   uint2* ties = reinterpret_cast<uint2*>(u_list + a.u_cap);
+  float* lut_smem = reinterpret_cast<float*>(ties + kTieCap);
+  uint2* aq_smem = reinterpret_cast<uint2*>(lut_smem + (TWO ? a.lut_smem_floats : 0));
 
   const uint32_t lane = lane_id();
   const uint32_t slot = blockIdx.x;
+  uint2* AQ = nullptr;
+  if (TWO) AQ = a.aq_smem_entries ? aq_smem : a.aq_global + (size_t)slot * a.aq_cap;
+  const bool aq_in_smem = TWO && a.aq_smem_entries != 0;
+  auto aq_ld = [&](uint32_t i) -> uint2 { return aq_in_smem ? AQ[i] : __ldcg(AQ + i); };
+  auto aq_st = [&](uint32_t i, uint2 v) {
+    if (aq_in_smem)
+      AQ[i] = v;
+    else
+      __stcg(AQ + i, v);
+  };
   uint32_t* vis = a.visited + (size_t)slot * a.vis_words;
   RView<R_SMEM> R{R_SMEM ? r_smem : a.r_global + (size_t)slot * a.ef};
   const uint32_t ef = a.ef;
@@ -102,8 +119,19 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     __syncwarp();
     const float na = (a.metric == ISL_METRIC_COSINE) ? smem_sqnorm_fold(q_smem, a.d) : 0.0f;
 
-    uint32_t r_len = 0, first_unexp = 0, n_ties = 0;
-    uint64_t n_hop = 0, n_edge = 0, n_dist = 0;
+    uint32_t r_len = 0, first_unexp = 0, n_ties = 0, aq_len = 0;
+    uint64_t n_hop = 0, n_edge = 0, n_dist = 0, n_adc = 0, n_rerank = 0;
+    const float* lut = nullptr;
+    if (TWO) {
+      const float* g = a.luts + (size_t)qi * a.pq_m * a.pq_ksub;
+      if (a.lut_smem_floats) {
+        for (uint32_t i = lane; i < a.lut_smem_floats; i += 32) lut_smem[i] = __ldg(g + i);
+        __syncwarp();
+        lut = lut_smem;
+      } else {
+        lut = g;
+      }
+    }
 
     // ---- sorted insert into R (lowers to: binary search, warp shift, store) -------------
     auto r_insert = [&](float dnew, uint32_t idnew) {
@@ -270,11 +298,78 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         ucnt += __popc(bal);
       }
       __syncwarp();
-      if (ucnt == 0) continue;  // leann.rs:939-941
+      if (ucnt == 0 && (!TWO || aq_len == 0)) continue;  // leann.rs:939-941
 
-      const uint32_t keep = prune_keep(a.prune_ratio, a.strategy, ucnt, r_len, ef);  // :944
-      n_dist += keep;
-      for (uint32_t b = 0; b < keep; b += 32) score_and_admit(b, min(32u, keep - b));
+      if (!TWO) {
+        const uint32_t keep = prune_keep(a.prune_ratio, a.strategy, ucnt, r_len, ef);  // :944
+        n_dist += keep;
+        for (uint32_t b = 0; b < keep; b += 32) score_and_admit(b, min(32u, keep - b));
+        continue;
+      }
+
+      // ---- two-level: ADC for the frontier, then promote the best of AQ ---------------------
+      n_adc += ucnt;
+      for (uint32_t b = 0; b < ucnt; b += 32) {
+        const uint32_t i = b + lane;
+        float adc = 0.0f;
+        uint32_t nid = 0;
+        if (i < ucnt) {
+          nid = u_list[i];
+          float sacc = 0.0f;  // table_distance: left fold over subquantizers, then sqrt
+          if (a.codes8) {
+            const uint8_t* cd = a.codes8 + (size_t)nid * a.pq_m;
+            for (uint32_t j = 0; j < a.pq_m; ++j) sacc = __fadd_rn(sacc, lut[j * a.pq_ksub + cd[j]]);
+          } else {
+            const uint16_t* cd = a.codes16 + (size_t)nid * a.pq_m;
+            for (uint32_t j = 0; j < a.pq_m; ++j) sacc = __fadd_rn(sacc, lut[j * a.pq_ksub + cd[j]]);
+          }
+          adc = __fsqrt_rn(sacc);
+        }
+        const uint32_t cntb = min(32u, ucnt - b);
+        for (uint32_t t = 0; t < cntb; ++t) {  // sorted insert of each (adc,id) into AQ
+          const float dnew = __shfl_sync(0xffffffffu, adc, t);
+          const uint32_t idnew = __shfl_sync(0xffffffffu, nid, t);
+          uint32_t lo = 0, hi = aq_len;
+          while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const uint2 e = aq_ld(mid);
+            if (key_lt(__uint_as_float(e.x), e.y, dnew, idnew))
+              lo = mid + 1;
+            else
+              hi = mid;
+          }
+          for (int tt = (int)aq_len; tt > (int)lo; tt -= 32) {
+            const int ii = tt - (int)lane;
+            const bool act = ii > (int)lo;
+            uint2 e = make_uint2(0, 0);
+            if (act) e = aq_ld(ii - 1);
+            __syncwarp();
+            if (act) aq_st(ii, e);
+            __syncwarp();
+          }
+          if (lane == 0) aq_st(lo, make_uint2(__float_as_uint(dnew), idnew));
+          aq_len++;
+          __syncwarp();
+        }
+      }
+      uint32_t promote = (uint32_t)ceilf(__fmul_rn((float)aq_len, a.rerank_ratio));
+      if (promote < 1) promote = 1;
+      if (promote > aq_len) promote = aq_len;
+      for (uint32_t i = lane; i < promote; i += 32) u_list[i] = aq_ld(i).y;
+      __syncwarp();
+      for (uint32_t b = 0; b + promote < aq_len; b += 32) {  // close the gap left by the promoted prefix
+        const uint32_t i = b + lane;
+        uint2 e = make_uint2(0, 0);
+        const bool act = i + promote < aq_len;
+        if (act) e = aq_ld(i + promote);
+        __syncwarp();
+        if (act) aq_st(i, e);
+        __syncwarp();
+      }
+      aq_len -= promote;
+      n_dist += promote;
+      n_rerank += promote;
+      for (uint32_t b = 0; b < promote; b += 32) score_and_admit(b, min(32u, promote - b));
     }
 
     // ---- results: R is already sorted by (dist,id); take(k) (leann.rs:895) -----------------
@@ -299,8 +394,8 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         s.n_hop = n_hop;
         s.n_edge = n_edge;
         s.n_dist = n_dist;
-        s.n_adc = 0;
-        s.n_rerank = 0;
+        s.n_adc = n_adc;
+        s.n_rerank = n_rerank;
         a.stats[qi] = s;
       }
     }

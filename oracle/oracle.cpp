@@ -514,7 +514,7 @@ int32_t orc_leann_build_batched(const isl_leann_config* cfg, const float* vector
   AdjView g{&adj};
   uint64_t s = 0;
   while (s < n) {
-    uint64_t round = std::min<uint64_t>(batch, std::max<uint64_t>(1, s));  // ramp 1,1,2,4,...
+    uint64_t round = std::min<uint64_t>(batch, std::max<uint64_t>(1, s / 2));  // ramp 1,1,1,1,2,3,4,6,...
     uint64_t e = std::min<uint64_t>(n, s + round);
     std::vector<std::vector<uint64_t>> fwd(e - s);
     if (s > 0) {

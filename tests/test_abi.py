@@ -1,0 +1,127 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol that
+include/islands_b200.h declares, and fails loudly (no CPU fallback) without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "islands_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(isl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    from islands_b200 import _ffi
+
+    lib = _ffi.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 50
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in islands_b200.h but not exported"
+        assert name in _ffi.SIGNATURES, f"{name} has no ctypes signature"
+    assert set(_ffi.SIGNATURES) == set(declared)
+    assert lib.isl_abi_version() == 1
+
+
+def test_library_is_built_for_sm_100a_only():
+    import subprocess
+
+    from islands_b200 import _ffi
+
+    out = subprocess.run(["cuobjdump", "--list-elf", _ffi.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_config_defaults_and_validation():
+    """leann.rs:1091-1146, hnsw.rs:533-569, pq.rs:479-520 (host logic, no GPU needed)."""
+    from islands_b200 import HnswConfig, InvalidConfig, LeannConfig, PQConfig
+
+    c = LeannConfig()
+    assert (c.m, c.m0, c.ef_construction, c.ef_search, c.beam_width, c.max_layers) == (30, 60, 128, 64, 1, 16)
+    assert c.metric == 0 and c.prune_ratio == 0.0 and c.pruning_strategy == 0
+    assert c.high_degree_pruning == 1 and abs(c.hub_percentile - 0.02) < 1e-3
+    assert c.is_compact == 1 and c.is_recompute == 1
+    assert abs(c.ml - 1.0 / np.log(30.0)) < 1e-15
+    c.validate()
+    f = LeannConfig.fast()
+    assert (f.m, f.m0, f.ef_construction, f.ef_search) == (16, 32, 100, 32) and f.prune_ratio > 0
+    a = LeannConfig.accurate()
+    assert (a.m, a.m0, a.ef_construction, a.ef_search) == (48, 96, 400, 128) and a.prune_ratio == 0
+    for bad in (dict(m=0), dict(m=30, m0=10), dict(ef_construction=5), dict(prune_ratio=1.5),
+                dict(prune_ratio=-0.1), dict(beam_width=0), dict(hub_percentile=1.5)):
+        with pytest.raises(InvalidConfig):
+            LeannConfig(**bad).validate()
+    h = HnswConfig()
+    assert (h.m, h.m0, h.ef_construction, h.max_layers) == (16, 32, 200, 16)
+    h.validate()
+    with pytest.raises(InvalidConfig):
+        HnswConfig(m=0).validate()
+    with pytest.raises(InvalidConfig):
+        HnswConfig(m=16, m0=8).validate()
+    p = PQConfig()
+    assert (p.num_subquantizers, p.num_centroids, p.training_iterations, p.seed) == (8, 256, 25, None)
+    p.validate(128)
+    with pytest.raises(InvalidConfig):
+        p.validate(100)  # not divisible (pq.rs:493-494)
+    with pytest.raises(InvalidConfig):
+        PQConfig(num_subquantizers=0).validate(128)
+    with pytest.raises(InvalidConfig):
+        PQConfig(num_centroids=0).validate(128)
+    with pytest.raises(InvalidConfig):
+        PQConfig(num_centroids=70000).validate(128)
+    assert PQConfig(8, 256).bytes_per_vector() == 8      # pq.rs:505-520
+    assert PQConfig(8, 512).bytes_per_vector() == 16
+
+
+def test_host_side_argument_errors_need_no_gpu():
+    from islands_b200 import DimensionMismatch, DistanceMetric, to_similarity
+
+    with pytest.raises(DimensionMismatch):  # distance.rs:206-212 — checked before any device work
+        DistanceMetric(DistanceMetric.Cosine).calculate([1.0, 2.0], [1.0, 2.0, 3.0])
+    with pytest.raises(DimensionMismatch):
+        DistanceMetric(DistanceMetric.Euclidean).calculate_squared([1.0, 2.0], [1.0, 2.0, 3.0])
+    assert abs(to_similarity(0.0) - 1.0) < 1e-6 and abs(to_similarity(1.0) - 0.5) < 1e-6  # search.rs:311-324
+
+
+def test_csr_graph_mirror():
+    """CsrGraph accessors (leann.rs:1172-1220)."""
+    from islands_b200 import CsrGraph
+
+    g = CsrGraph()
+    assert g.num_nodes == 0 and g.entry_point is None
+    assert g.add_node([], 0) == 0 and g.entry_point == 0
+    assert g.add_node([0], 1) == 1 and g.entry_point == 1
+    g2 = CsrGraph()
+    g2.add_node([], 0)
+    g2.add_node([0], 0)
+    g2.add_node([0, 1], 0)
+    assert list(g2.get_neighbors(0)) == [] and list(g2.get_neighbors(1)) == [0]
+    assert list(g2.get_neighbors(2)) == [0, 1] and g2.get_neighbors(999) is None
+    assert g2.storage_bytes() == 8 * (4 + 3 + 3 + 3)
+
+
+def test_no_cpu_fallback_without_gpu():
+    from islands_b200 import CudaError, DistanceMetric, _ffi
+
+    if _ffi.load().isl_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(CudaError):
+        DistanceMetric(0).calculate([1.0, 0.0], [0.0, 1.0])
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under islands_b200/ may reference it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "islands_b200")):
+        if "lib" in dirpath.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                for needle in ("pyoracle", "libislands_oracle", "oracle.h", "import oracle", "from oracle", "dlopen"):
+                    assert needle not in text, (f, needle)

@@ -1,0 +1,47 @@
+"""Two-level search (PQ ADC traversal + exact rerank) vs the oracle's definition
+(docs/leann-specification.md:223-269; no reference code => parity is oracle<->GPU)."""
+import numpy as np
+import pytest
+
+from conftest import oracle_graph, uniform
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("m,ksub", [(8, 256), (4, 16), (16, 300), (48, 256)])
+@pytest.mark.parametrize("ratio", [0.1, 0.5, 1.0])
+def test_two_level_matches_oracle(gpu_lib, orc, m, ksub, ratio):
+    from islands_b200 import LeannIndex, PQConfig, ProductQuantizer
+
+    cfg, v, levels, off, nbrs, entry = oracle_graph(orc, 3000, 96, seed=61)
+    cb = orc.pq_train(1, v[:1000], m, ksub, 3, 7)
+    codes = orc.pq_encode(1, cb, v)
+    pq = ProductQuantizer(96, PQConfig(m, ksub, 3, 7))
+    pq.set_codebooks(cb)
+    idx = LeannIndex.from_csr(cfg, v, off, nbrs, levels, entry)
+    idx.attach_pq(pq, codes)
+    q = uniform(np.random.RandomState(62), 100, 96)
+    for k, ef in [(10, 32), (10, 128)]:
+        ids, dist, cnt, st = idx.search_two_level_batch(q, k, ef, ratio, stats=True)
+        o_ids, o_dist, o_cnt, o_st = orc.leann_search_two_level(cfg._s, v, off, nbrs, entry, cb, codes, q, k, ef,
+                                                                ratio, threads=8, stats=True)
+        assert np.array_equal(cnt, o_cnt)
+        assert np.array_equal(ids, o_ids)
+        assert np.array_equal(dist.view(np.uint32), o_dist.view(np.uint32))
+        for f in ("n_hop", "n_edge", "n_dist", "n_adc", "n_rerank"):
+            assert np.array_equal(getattr(st, f), o_st[f]), f
+    if ratio == 1.0:
+        # promoting everything evaluates every frontier node exactly: recall of the exact search
+        e_ids, _, _ = idx.search_batch(q, 10, 128)
+        t_ids, _, _ = idx.search_two_level_batch(q, 10, 128, 1.0)
+        overlap = np.mean([len(set(e_ids[i]) & set(t_ids[i])) / 10 for i in range(100)])
+        assert overlap > 0.9
+
+
+def test_two_level_needs_pq(gpu_lib, orc):
+    from islands_b200 import LeannIndex, PQError
+
+    cfg, v, levels, off, nbrs, entry = oracle_graph(orc, 3000, 96, seed=61)
+    idx = LeannIndex.from_csr(cfg, v, off, nbrs, levels, entry)
+    with pytest.raises(PQError):
+        idx.search_two_level_batch(v[:2], 5, 32, 0.1)
