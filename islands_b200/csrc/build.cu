@@ -194,11 +194,16 @@ apply_reverse_edges_kernel(const uint64_t* __restrict__ keys, const float* __res
         const uint32_t tot = d + 1;
         for (uint32_t i = lane; i < tot; i += 32) {
           const float x = s_d[i];
-          uint32_t rank = 0;
+          // rank = #{strictly closer} + #{equal (or unordered) and earlier}: a stable sort position.
+          // Kept as two separate counters: the fused boolean form was observed to drop the tie
+          // term under nvcc 12.9 -O3 (two equal distances then collided on one slot).
+          uint32_t closer = 0, tie_before = 0;
           for (uint32_t j = 0; j < tot; ++j) {
             const float y = s_d[j];
-            rank += (y < x) || (!(x < y) && !(y < x) && j < i);
+            closer += (y < x) ? 1u : 0u;
+            tie_before += (!(x < y) && !(y < x) && j < i) ? 1u : 0u;
           }
+          const uint32_t rank = closer + tie_before;
           t_id[rank] = s_id[i];
           t_d[rank] = x;
         }
