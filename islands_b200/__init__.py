@@ -4,7 +4,7 @@ this package is the host-side mirror of the reference interface.  No CPU fallbac
 from .core import (CoreError, CsrGraph, CudaError, DimensionMismatch, DistanceMetric, EmptyCollection,
                    HnswConfig, IndexNotBuilt, InMemoryEmbeddingProvider, InvalidArgument, InvalidConfig,
                    LeannConfig, LeannIndex, NodeNotFound, PQConfig, PQError, ProductQuantizer,
-                   PruningStrategy, SerializationError, merge_topk, normalize_vector, normalized,
+                   PruningStrategy, SerializationError, merge_topk, merge_topk_dev, normalize_vector, normalized,
                    random_level, to_similarity)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

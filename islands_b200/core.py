@@ -328,6 +328,24 @@ class LeannIndex:
                                            _ptr(lv, u64p), seed, batch, C.byref(h)))
         self._h = h
 
+    def build_dev(self, d_vectors_ptr, num_vectors, dim, levels=None, seed=0, batch=1):
+        """LeannIndex::build from embeddings already resident on the current CUDA device
+        (row-major [num_vectors, dim] f32 at the raw device address `d_vectors_ptr`)."""
+        self.free()
+        lv = np.ascontiguousarray(levels, np.uint64) if levels is not None else None
+        h = C.c_void_p()
+        _check(_ffi.load().isl_index_build_dev(C.byref(self.config._s), dim, num_vectors, C.c_void_p(d_vectors_ptr),
+                                               _ptr(lv, u64p), seed, batch, C.byref(h)))
+        self._h = h
+
+    def search_batch_dev(self, d_queries_ptr, nq, dim, k, ef, d_ids_ptr, d_dist_ptr, d_count_ptr=None,
+                         d_stats_ptr=None):
+        """Batched search with queries and outputs on the device (raw addresses): no host copies."""
+        _check(_ffi.load().isl_index_search_dev(self._h, C.c_void_p(d_queries_ptr), nq, dim, k, int(ef),
+                                                C.c_void_p(d_ids_ptr), C.c_void_p(d_dist_ptr),
+                                                C.c_void_p(d_count_ptr) if d_count_ptr else None,
+                                                C.c_void_p(d_stats_ptr) if d_stats_ptr else None))
+
     def free(self):
         if self._h is not None:
             _ffi.load().isl_index_free(self._h)
@@ -558,6 +576,13 @@ class ProductQuantizer:
 def to_similarity(score):
     """SearchResult::to_similarity (search.rs:99-102)."""
     return np.float32(1.0) / (np.float32(1.0) + np.float32(score))
+
+
+def merge_topk_dev(d_ids_ptr, d_dist_ptr, parts, nq, k, d_out_ids_ptr, d_out_dist_ptr, d_out_count_ptr=None):
+    """Device-pointer form of merge_topk: [parts, nq, k] lists already gathered on this GPU."""
+    _check(_ffi.load().isl_merge_topk_dev(C.c_void_p(d_ids_ptr), C.c_void_p(d_dist_ptr), parts, nq, k,
+                                          C.c_void_p(d_out_ids_ptr), C.c_void_p(d_out_dist_ptr),
+                                          C.c_void_p(d_out_count_ptr) if d_out_count_ptr else None))
 
 
 def merge_topk(ids, dist, k):
