@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libislands_b200.so")
+LIB_PATH = os.environ.get("ISL_DEV_LIB_PATH") or os.path.join(_HERE, "lib", "libislands_b200.so")
 
 ISL_OK = 0
 ISL_NO_ENTRY = -1

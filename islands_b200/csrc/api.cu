@@ -81,7 +81,34 @@ isl_status index_finish_graph(isl_index* idx) {
   if (e)
     ISL_CUDA_TRY(cudaMemcpyAsync(idx->nbrs.p, n32.data(), e * 4, cudaMemcpyHostToDevice, idx->stream));
   ISL_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+  return index_make_padded_adjacency(idx);
+}
+
+isl_status index_make_padded_adjacency(isl_index* idx) {
+  idx->adj_pad.release();
+  idx->adj_stride = 0;
+  const uint64_t n = idx->n, e = idx->h_nbrs.size();
+  if (n == 0) return ISL_OK;
+  const uint32_t stride = std::max<uint32_t>(32, round_up(idx->max_degree, 32));
+  if ((uint64_t)n * stride > 2 * e + 64 * n) return ISL_OK;  // very skewed degrees: keep CSR
+  ISL_CUDA_TRY(idx->adj_pad.alloc(n * stride));
+  ISL_TRY(launch_pad_adjacency(idx->offsets.p, idx->nbrs.p, n, stride, idx->adj_pad.p, idx->stream));
+  ISL_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+  idx->adj_stride = stride;
   return ISL_OK;
+}
+
+void search_args_set_graph(const isl_index* idx, SearchArgs* a) {
+  a->degrees = nullptr;
+  if (idx->adj_stride) {
+    a->offsets = nullptr;
+    a->nbrs = idx->adj_pad.p;
+    a->adj_stride = idx->adj_stride;
+  } else {
+    a->offsets = idx->offsets.p;
+    a->nbrs = idx->nbrs.p;
+    a->adj_stride = 0;
+  }
 }
 
 void fill_empty(uint64_t nq, uint32_t k, uint64_t* ids, float* dist, uint32_t* count,
@@ -116,10 +143,7 @@ static isl_status search_device(const isl_index* idx, const float* d_queries, ui
   a.ld = idx->ld;
   a.d = idx->dim;
   a.n = (uint32_t)idx->n;
-  a.offsets = idx->offsets.p;
-  a.nbrs = idx->nbrs.p;
-  a.degrees = nullptr;
-  a.adj_stride = 0;
+  search_args_set_graph(idx, &a);
   a.queries = d_queries;
   a.q_ld = q_ld;
   a.nq = (uint32_t)nq;

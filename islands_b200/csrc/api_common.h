@@ -66,6 +66,10 @@ struct isl_index {
   isl::DevBuf<float> sqnorms;    // [n]
   isl::DevBuf<uint64_t> offsets; // [n+1]
   isl::DevBuf<uint32_t> nbrs;    // [E]
+  // Search-time adjacency: fixed-stride rows padded with 0xffffffff (stride = max degree rounded
+  // up to 32).  Used instead of the CSR arrays when it costs at most ~2x their memory.
+  isl::DevBuf<uint32_t> adj_pad; // [n][adj_stride]
+  uint32_t adj_stride = 0;       // 0 => search walks the CSR arrays
   // two-level search attachment
   const isl_pq* pq = nullptr;
   isl::DevBuf<uint8_t> codes8;    // [n][m] when ksub <= 256
@@ -93,6 +97,8 @@ namespace isl {
 // Shared by api_index.cu and build.cu.
 isl_status index_alloc_common(isl_index* idx);
 isl_status index_finish_graph(isl_index* idx);  // uploads CSR, computes max degree
+isl_status index_make_padded_adjacency(isl_index* idx);  // device CSR -> adj_pad (or adj_stride = 0)
+void search_args_set_graph(const isl_index* idx, SearchArgs* a);
 void fill_empty(uint64_t nq, uint32_t k, uint64_t* ids, float* dist, uint32_t* count, isl_search_stats* stats);
 isl_status search_checks(const isl_index* idx, const void* queries, uint64_t nq, uint32_t query_dim, uint32_t k,
                          uint32_t* ef, bool* trivial);

@@ -96,8 +96,7 @@ isl_status isl_index_search_two_level(const isl_index* idx, const float* queries
   a.ld = idx->ld;
   a.d = idx->dim;
   a.n = (uint32_t)idx->n;
-  a.offsets = idx->offsets.p;
-  a.nbrs = idx->nbrs.p;
+  search_args_set_graph(idx, &a);
   a.queries = idx->q_stage.p;
   a.q_ld = idx->ld;
   a.nq = (uint32_t)nq;

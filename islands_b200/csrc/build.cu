@@ -451,6 +451,7 @@ isl_status build_graph(isl_index* idx, const uint64_t* levels_or_null, uint64_t 
   idx->max_degree = maxdeg;
   idx->entry = entry;
   idx->max_level = max_level;
+  ISL_TRY(index_make_padded_adjacency(idx));
   if (hflags[1]) return fail(ISL_INVALID_ARGUMENT, "build: too many exact distance ties during construction search");
   return ISL_OK;
 }

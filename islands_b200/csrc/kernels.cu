@@ -120,6 +120,18 @@ __global__ void narrow_ids_kernel(const uint64_t* __restrict__ src, uint32_t* __
   }
 }
 
+__global__ void pad_adjacency_kernel(const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ nbrs,
+                                     uint64_t n, uint32_t stride, uint32_t* __restrict__ out) {
+  const uint64_t total = n * stride;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t u = i / stride;
+    const uint32_t j = (uint32_t)(i % stride);
+    const uint64_t s = offsets[u], e = offsets[u + 1];
+    out[i] = j < e - s ? nbrs[s + j] : 0xffffffffu;
+  }
+}
+
 // One warp per query.  The parts*k candidates are staged in shared memory, then the k smallest
 // keys are extracted one at a time with a warp arg-min; positions (not keys) are retired, so
 // duplicate (dist,id) pairs coming from different parts are kept, as a concat+sort would.
@@ -232,6 +244,15 @@ isl_status launch_narrow_ids(const uint64_t* d_src, uint32_t* d_dst, uint64_t co
                              unsigned int* d_flag, cudaStream_t st) {
   if (count == 0) return ISL_OK;
   narrow_ids_kernel<<<grid_1d(count, 256), 256, 0, st>>>(d_src, d_dst, count, limit, d_flag);
+  count_launch();
+  ISL_CUDA_TRY(cudaGetLastError());
+  return ISL_OK;
+}
+
+isl_status launch_pad_adjacency(const uint64_t* d_offsets, const uint32_t* d_nbrs, uint64_t n, uint32_t stride,
+                                uint32_t* d_out, cudaStream_t st) {
+  if (n == 0) return ISL_OK;
+  pad_adjacency_kernel<<<grid_1d(n * stride, 256), 256, 0, st>>>(d_offsets, d_nbrs, n, stride, d_out);
   count_launch();
   ISL_CUDA_TRY(cudaGetLastError());
   return ISL_OK;

@@ -9,7 +9,10 @@ namespace isl {
 
 namespace {
 constexpr int kCH = 64;
-constexpr int kStages = 3;
+#ifndef ISL_STAGES
+#define ISL_STAGES 1
+#endif
+constexpr int kStages = ISL_STAGES;
 // R (8 B per entry) stays in shared memory up to this many entries; above, it lives in an
 // L2-resident global buffer so that enough warps stay resident per SM.
 constexpr uint32_t kEfSmemMax = 2048;

@@ -22,7 +22,7 @@
 //     replayed sequentially in CSR order by the whole warp.
 #pragma once
 
-#include "dist_pass.cuh"
+#include "row_stream.cuh"
 #include "search.h"
 
 namespace isl {
@@ -34,7 +34,8 @@ template <int CH, int STAGES>
 __host__ __device__ constexpr size_t search_smem_bytes(uint32_t ld, uint32_t ef_smem, uint32_t u_cap,
                                                        uint32_t lut_floats = 0, uint32_t aq_entries = 0) {
   return (size_t)STAGES * StageGeom<CH>::STAGE_FLOATS * 4 + (size_t)ld * 4 + (size_t)ef_smem * 8 +
-         (size_t)u_cap * 4 + (size_t)kTieCap * 8 + (size_t)lut_floats * 4 + (size_t)aq_entries * 8;
+         (size_t)u_cap * 8 + (size_t)kTieCap * 8 + (size_t)STAGES * 8 + (size_t)lut_floats * 4 +
+         (size_t)aq_entries * 8;
 }
 
 template <bool R_SMEM>
@@ -80,8 +81,10 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
   float* q_smem = stage + STAGES * G::STAGE_FLOATS;
   uint2* r_smem = reinterpret_cast<uint2*>(q_smem + a.ld);
   uint32_t* u_list = reinterpret_cast<uint32_t*>(r_smem + (R_SMEM ? a.ef : 0));
-  uint2* ties = reinterpret_cast<uint2*>(u_list + a.u_cap);
-  float* lut_smem = reinterpret_cast<float*>(ties + kTieCap);
+  float* u_nb = reinterpret_cast<float*>(u_list + a.u_cap);  // squared norms of the rows in u_list
+  uint2* ties = reinterpret_cast<uint2*>(u_nb + a.u_cap);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ties + kTieCap);
+  float* lut_smem = reinterpret_cast<float*>(bars + STAGES);
   uint2* aq_smem = reinterpret_cast<uint2*>(lut_smem + (TWO ? a.lut_smem_floats : 0));
 
   const uint32_t lane = lane_id();
@@ -99,6 +102,18 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
   uint32_t* vis = a.visited + (size_t)slot * a.vis_words;
   RView<R_SMEM> R{R_SMEM ? r_smem : a.r_global + (size_t)slot * a.ef};
   const uint32_t ef = a.ef;
+
+  RowRing<STAGES> ring;
+  ring.stage = stage;
+  ring.bars = bars;
+  ring.phase_bits = 0;
+  ring.islot = 0;
+  ring.cslot = 0;
+  if (lane == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(bars + s, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
 
   for (;;) {
     uint32_t qi = 0;
@@ -192,15 +207,17 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       }
     };
 
-    // ---- distances of u_list[base .. base+cnt) and their sequential admission ------------
-    auto score_and_admit = [&](uint32_t base, uint32_t cnt) {
-      const float acc = warp_rows_fold<ACC, CH, STAGES>(a.vectors, a.ld, a.d, u_list + base, cnt,
-                                                        q_smem, stage);
+    // ---- exact distances of u_list[0 .. total) and their sequential admission ----------------
+    // Streaming and fold: row_stream.cuh.  Admission replays the reference's per-neighbour loop
+    // (leann.rs:953-970) in list order over the lanes that can still be admitted.
+    auto admit_group = [&](uint32_t base, uint32_t cnt, float acc) {
       float dn = 0.0f;
       uint32_t cid = 0;
+      cp_async_wait<0>();  // the squared norms requested before the stream started
+      __syncwarp();
       if (lane < cnt) {
         cid = u_list[base + lane];
-        const float nb = (a.metric == ISL_METRIC_COSINE) ? __ldg(a.sqnorms + cid) : 0.0f;
+        const float nb = (a.metric == ISL_METRIC_COSINE) ? u_nb[base + lane] : 0.0f;
         dn = finalize_distance(a.metric, acc, na, nb);
       }
       float worst = 0.0f;
@@ -216,6 +233,15 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         if (add) r_insert(dj, idj);
       }
     };
+    auto score_and_admit = [&](uint32_t total) {
+      if (a.metric == ISL_METRIC_COSINE) {  // 4-byte async gathers: land long before the group is admitted
+        for (uint32_t i = lane; i < total; i += 32)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(u_nb + i)),
+                       "l"(a.sqnorms + u_list[i]));
+        cp_async_commit();
+      }
+      stream_rows_fold<ACC, STAGES>(ring, a.vectors, a.ld, a.d, u_list, total, q_smem, admit_group);
+    };
 
     // ---- entry point (leann.rs:911-916) ----------------------------------------------------
     if (lane == 0) {
@@ -223,7 +249,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       atomicOr(vis + (a.entry >> 5), 1u << (a.entry & 31));
     }
     __syncwarp();
-    score_and_admit(0, 1);
+    score_and_admit(1);
     n_dist = 1;
 
     // ---- main loop (leann.rs:922-972) ------------------------------------------------------
@@ -266,25 +292,44 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       }
 
       // neighbour list of `cur`
+      // Three layouts: CSR (offsets), fixed-stride rows with a live degree array (graph under
+      // construction), fixed-stride rows padded with 0xffffffff (finished index: one dependent
+      // load less per hop, and the row address of the NEXT candidate is known early enough to
+      // be prefetched into L2).
       uint64_t start;
       uint32_t deg;
+      bool sentinel = false;
       if (a.offsets) {
         start = __ldg(a.offsets + cur);
         deg = (uint32_t)(__ldg(a.offsets + cur + 1) - start);
       } else {
         start = (uint64_t)cur * a.adj_stride;
-        deg = __ldg(a.degrees + cur);
+        if (a.degrees) {
+          deg = __ldg(a.degrees + cur);
+        } else {
+          deg = a.adj_stride;
+          sentinel = true;
+          if (first_unexp < r_len && lane * 32 < a.adj_stride) {
+            const uint32_t nxt = R.ld(first_unexp).y & ~kExpandedBit;
+            const uint32_t* pf = a.nbrs + (size_t)nxt * a.adj_stride + lane * 32;
+            asm volatile("prefetch.global.L2 [%0];\n" ::"l"(pf));
+          }
+        }
       }
       n_hop++;
-      n_edge += deg;
+      if (!sentinel) n_edge += deg;
 
       // unvisited neighbours, in list order (leann.rs:933-937)
       uint32_t ucnt = 0;
       for (uint32_t b = 0; b < deg; b += 32) {
         const uint32_t i = b + lane;
-        const bool valid = i < deg;
+        bool valid = i < deg;
         uint32_t nid = 0xffffffffu;
         if (valid) nid = __ldg(a.nbrs + start + i);
+        if (sentinel) {
+          valid = valid && nid != 0xffffffffu;
+          n_edge += __popc(__ballot_sync(0xffffffffu, valid));
+        }
         const uint32_t same = __match_any_sync(0xffffffffu, nid);
         const bool first = lane == (uint32_t)(__ffs(same) - 1);
         bool unv = false;
@@ -303,7 +348,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       if (!TWO) {
         const uint32_t keep = prune_keep(a.prune_ratio, a.strategy, ucnt, r_len, ef);  // :944
         n_dist += keep;
-        for (uint32_t b = 0; b < keep; b += 32) score_and_admit(b, min(32u, keep - b));
+        score_and_admit(keep);
         continue;
       }
 
@@ -369,7 +414,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       aq_len -= promote;
       n_dist += promote;
       n_rerank += promote;
-      for (uint32_t b = 0; b < promote; b += 32) score_and_admit(b, min(32u, promote - b));
+      score_and_admit(promote);
     }
 
     // ---- results: R is already sorted by (dist,id); take(k) (leann.rs:895) -----------------
