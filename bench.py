@@ -167,13 +167,14 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    from islands_b200 import LeannConfig, LeannIndex, _ffi, merge_topk_dev
+    from islands_b200 import LeannConfig, LeannIndex, _ffi
+    from islands_b200.shard import ShardedLeannIndex, shard_range
 
     lib = _ffi.load()
     cfg = LeannConfig()  # paper_default: m=30, m0=60, efC=128, cosine, hub-preserving pruning 2%
     n, d, nq = a.n, a.d, a.nq
     parts = world if use_dist else 1
-    lo, hi = (rank * n) // parts, ((rank + 1) * n) // parts
+    lo, hi = shard_range(n, rank if use_dist else 0, parts)
 
     x, q = make_data(torch, a.dataset, n, nq, d, dev)
     n_gt = min(nq, 1000)
@@ -191,24 +192,15 @@ def main():
     dst = torch.empty((nq, K_TOP), dtype=torch.float32, device=dev)
     cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
     stats = torch.zeros((nq, 5), dtype=torch.int64, device=dev)
-    g_ids = torch.empty((parts, nq, K_TOP), dtype=torch.int64, device=dev) if use_dist else None
-    g_dst = torch.empty((parts, nq, K_TOP), dtype=torch.float32, device=dev) if use_dist else None
     m_ids = torch.empty((nq, K_TOP), dtype=torch.int64, device=dev)
     m_dst = torch.empty((nq, K_TOP), dtype=torch.float32, device=dev)
+    sharded = ShardedLeannIndex(index, lo, n)
 
     def step_device(nqq, ef, with_stats=False):
-        """One pass of the hot path with inputs resident in HBM; returns the final ids tensor."""
-        index.search_batch_dev(q.data_ptr(), nqq, d, K_TOP, ef, ids.data_ptr(), dst.data_ptr(), cnt.data_ptr(),
-                               stats.data_ptr() if with_stats else None)
-        if not use_dist:
-            return ids
-        # local -> global ids (padding stays all-ones), one all-gather of (dist,id) lists, per-query merge
-        gl = torch.where(ids[:nqq] >= 0, ids[:nqq] + lo, ids[:nqq])
-        dist.all_gather_into_tensor(g_ids[:, :nqq].contiguous() if nqq != nq else g_ids, gl.contiguous())
-        dist.all_gather_into_tensor(g_dst[:, :nqq].contiguous() if nqq != nq else g_dst, dst[:nqq].contiguous())
-        torch.cuda.synchronize()
-        merge_topk_dev(g_ids.data_ptr(), g_dst.data_ptr(), parts, nqq, K_TOP, m_ids.data_ptr(), m_dst.data_ptr())
-        return m_ids
+        """One pass of the hot path with inputs resident in HBM: per-shard search, then (N > 1) one
+        all-gather of the (dist, id) lists and the per-query merge.  Returns the final ids tensor."""
+        out_ids, _ = sharded.search_batch_dev(q[:nqq], K_TOP, ef, ids, dst, cnt, m_ids, m_dst, stats if with_stats else None)
+        return out_ids
 
     # ---- ef: smallest rung with recall@10 >= 0.95 (setup, untimed) ---------------------------------
     def recall_for(ef):

@@ -1,0 +1,204 @@
+// islands_b200.hpp — C++17 host-side mirror of the reference's `src/core` API over the C ABI.
+//
+// The reference is compiled Rust; its toolchain is not available in this image, so the host
+// side above the C ABI is C++ (header only) with the reference's names, argument meaning and
+// error behaviour:
+//   islands::DistanceMetric / calculate / batch_calculate   src/core/distance.rs:7-67
+//   islands::CoreError (+ kind)                             src/core/error.rs:9-62
+//   islands::LeannConfig / LeannIndex / CsrGraph            src/core/leann.rs:193-302, 322-461, 493-1067
+//   islands::PQConfig / ProductQuantizer                    src/core/pq.rs:13-65, 116-359
+//   islands::merge_results                                  src/core/search.rs:211-237
+// Link with -lislands_b200 (islands_b200/lib).  All compute runs on the GPU; nothing here has a
+// CPU fallback.
+#pragma once
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "islands_b200.h"
+
+namespace islands {
+
+enum class ErrorKind {
+  DimensionMismatch = ISL_DIM_MISMATCH,
+  EmptyCollection = ISL_EMPTY_COLLECTION,
+  InvalidConfig = ISL_INVALID_CONFIG,
+  IndexNotBuilt = ISL_INDEX_NOT_BUILT,
+  NodeNotFound = ISL_NODE_NOT_FOUND,
+  PQError = ISL_PQ_ERROR,
+  Serialization = ISL_SERIALIZATION,
+  Cuda = ISL_CUDA_ERROR,
+  InvalidArgument = ISL_INVALID_ARGUMENT,
+};
+
+// CoreError (error.rs:9-62): the variant is `kind`, the String payload is what().
+class CoreError : public std::runtime_error {
+ public:
+  CoreError(ErrorKind k, const std::string& msg) : std::runtime_error(msg), kind(k) {}
+  ErrorKind kind;
+};
+
+inline void check(isl_status st) {
+  if (st != ISL_OK) throw CoreError(static_cast<ErrorKind>(st), isl_last_error());
+}
+
+// ---- distance.rs ------------------------------------------------------------------------------
+enum class DistanceMetric : int32_t { Cosine = 0, Euclidean = 1, DotProduct = 2, Manhattan = 3 };
+
+inline float calculate(DistanceMetric m, const std::vector<float>& a, const std::vector<float>& b) {
+  float out = 0.0f;
+  check(isl_distance_calculate(static_cast<int32_t>(m), a.data(), a.size(), b.data(), b.size(), &out));
+  return out;
+}
+inline float calculate_squared(DistanceMetric m, const std::vector<float>& a, const std::vector<float>& b) {
+  float out = 0.0f;
+  check(isl_distance_calculate_squared(static_cast<int32_t>(m), a.data(), a.size(), b.data(), b.size(), &out));
+  return out;
+}
+// rows: [n][query.size()] row-major
+inline std::vector<float> batch_calculate(DistanceMetric m, const std::vector<float>& query,
+                                          const std::vector<float>& rows) {
+  const uint64_t n = query.empty() ? 0 : rows.size() / query.size();
+  std::vector<float> out(n);
+  check(isl_distance_batch(static_cast<int32_t>(m), query.data(), rows.data(), n, (uint32_t)query.size(), out.data()));
+  return out;
+}
+
+// ---- leann.rs -----------------------------------------------------------------------------------
+struct LeannConfig : isl_leann_config {
+  LeannConfig() { check(isl_leann_config_default(this)); }  // paper_default (leann.rs:386-403)
+  static LeannConfig paper_default() { return LeannConfig(); }
+  static LeannConfig fast() {
+    LeannConfig c;
+    check(isl_leann_config_fast(&c));
+    return c;
+  }
+  static LeannConfig accurate() {
+    LeannConfig c;
+    check(isl_leann_config_accurate(&c));
+    return c;
+  }
+  void validate() const { check(isl_leann_config_validate(this)); }
+};
+
+struct CsrGraph {  // leann.rs:193-208
+  std::vector<uint64_t> node_offsets{0}, neighbors, levels, degree_counts;
+  int64_t entry_point = ISL_NO_ENTRY;
+  uint64_t max_level = 0, num_nodes = 0;
+};
+
+using SearchResults = std::vector<std::pair<uint64_t, float>>;  // Vec<(u64, f32)>
+
+class LeannIndex {
+ public:
+  explicit LeannIndex(const LeannConfig& cfg = LeannConfig()) : cfg_(cfg) { cfg_.validate(); }
+  ~LeannIndex() { isl_index_free(h_); }
+  LeannIndex(const LeannIndex&) = delete;
+  LeannIndex& operator=(const LeannIndex&) = delete;
+
+  // LeannIndex::build (leann.rs:560-631).  `embeddings` plays the InMemoryEmbeddingProvider:
+  // row i is compute_embedding(i).  `levels` (optional) replaces the thread_rng draw.
+  void build(const std::vector<float>& embeddings, uint32_t dim, uint64_t num_vectors,
+             const std::vector<uint64_t>* levels = nullptr, uint64_t seed = 0, uint32_t batch = 1) {
+    reset();
+    check(isl_index_build(&cfg_, dim, num_vectors, embeddings.data(), levels ? levels->data() : nullptr, seed, batch,
+                          &h_));
+  }
+  void from_csr(const CsrGraph& g, const std::vector<float>& embeddings, uint32_t dim) {
+    reset();
+    check(isl_index_from_csr(&cfg_, dim, g.num_nodes, g.node_offsets.data(), g.neighbors.data(),
+                             g.levels.empty() ? nullptr : g.levels.data(), g.entry_point, embeddings.data(), &h_));
+  }
+  uint64_t len() const { return isl_index_len(h_); }
+  bool is_empty() const { return len() == 0; }
+  uint32_t dimension() const { return isl_index_dimension(h_); }
+  uint64_t storage_bytes() const { return isl_index_storage_bytes(h_); }
+
+  // LeannIndex::search / search_with_params (leann.rs:858-896)
+  SearchResults search(const std::vector<float>& query, uint32_t k) const {
+    return search_with_params(query, k, (uint32_t)cfg_.ef_search);
+  }
+  SearchResults search_with_params(const std::vector<float>& query, uint32_t k, uint32_t ef) const {
+    std::vector<uint64_t> ids(k);
+    std::vector<float> dist(k);
+    uint32_t count = 0;
+    check(isl_index_search(h_, query.data(), 1, (uint32_t)query.size(), k, ef, ids.data(), dist.data(), &count, nullptr));
+    SearchResults out;
+    for (uint32_t i = 0; i < count; ++i) out.emplace_back(ids[i], dist[i]);
+    return out;
+  }
+  CsrGraph graph() const {
+    CsrGraph g;
+    g.num_nodes = len();
+    g.node_offsets.assign(g.num_nodes + 1, 0);
+    g.neighbors.assign(isl_index_num_edges(h_), 0);
+    g.levels.assign(g.num_nodes, 0);
+    g.degree_counts.assign(g.num_nodes, 0);
+    check(isl_index_export_csr(h_, g.node_offsets.data(), g.neighbors.data(), g.levels.data(), g.degree_counts.data()));
+    g.entry_point = isl_index_entry_point(h_);
+    g.max_level = isl_index_max_level(h_);
+    return g;
+  }
+  isl_index* handle() const { return h_; }
+
+ private:
+  void reset() {
+    isl_index_free(h_);
+    h_ = nullptr;
+  }
+  LeannConfig cfg_;
+  isl_index* h_ = nullptr;
+};
+
+// ---- pq.rs ----------------------------------------------------------------------------------------
+struct PQConfig : isl_pq_config {
+  PQConfig() { check(isl_pq_config_default(this)); }
+  void validate(uint64_t dimension) const { check(isl_pq_config_validate(this, dimension)); }
+  uint64_t bytes_per_vector() const { return isl_pq_config_bytes_per_vector(this); }
+};
+
+class ProductQuantizer {
+ public:
+  ProductQuantizer(uint32_t dimension, const PQConfig& cfg = PQConfig()) : dim_(dimension) {
+    check(isl_pq_new(dimension, &cfg, &h_));
+  }
+  ~ProductQuantizer() { isl_pq_free(h_); }
+  ProductQuantizer(const ProductQuantizer&) = delete;
+  ProductQuantizer& operator=(const ProductQuantizer&) = delete;
+  ProductQuantizer& with_metric(DistanceMetric m) {
+    check(isl_pq_set_metric(h_, static_cast<int32_t>(m)));
+    return *this;
+  }
+  bool is_trained() const { return isl_pq_is_trained(h_) != 0; }
+  uint64_t num_subquantizers() const { return isl_pq_num_subquantizers(h_); }
+  float compression_ratio() const { return isl_pq_compression_ratio(h_); }
+  void train(const std::vector<float>& vectors) { check(isl_pq_train(h_, vectors.data(), vectors.size() / dim_, dim_)); }
+  std::vector<uint16_t> encode(const std::vector<float>& v) const {
+    std::vector<uint16_t> codes(num_subquantizers());
+    check(isl_pq_encode(h_, v.data(), 1, (uint32_t)v.size(), codes.data()));
+    return codes;
+  }
+  std::vector<float> decode(const std::vector<uint16_t>& codes) const {
+    std::vector<float> out(dim_);
+    check(isl_pq_decode(h_, codes.data(), 1, codes.size(), out.data()));
+    return out;
+  }
+  float asymmetric_distance(const std::vector<float>& q, const std::vector<uint16_t>& codes) const {
+    float out = 0.0f;
+    check(isl_pq_asymmetric_distance(h_, q.data(), (uint32_t)q.size(), codes.data(), 1, &out));
+    return out;
+  }
+  isl_pq* handle() const { return h_; }
+
+ private:
+  uint32_t dim_;
+  isl_pq* h_ = nullptr;
+};
+
+// ---- search.rs ----------------------------------------------------------------------------------
+inline float to_similarity(float score) { return 1.0f / (1.0f + score); }  // search.rs:99-102
+
+}  // namespace islands

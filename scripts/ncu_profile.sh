@@ -12,7 +12,7 @@ tail -1 gpurun_out/plain.log
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'leann_search|merge_topk|pq_tables' -s 265 -c 40 \
     --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:leann_search -s 270 -c 2 \
+ncu --set full --clock-control none --import-source on -k regex:leann_search -s 268 -c 1 \
     -o gpurun_out/prof_search -f $CMD > gpurun_out/ncu_full.log 2>&1
 echo "full capture rc=$?"
 ls -la gpurun_out/

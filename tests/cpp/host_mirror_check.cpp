@@ -1,0 +1,69 @@
+// Compiled and run by tests/test_cpp_host.py: the C++ host mirror (include/islands_b200.hpp)
+// links against the C ABI, keeps the reference's defaults / error behaviour, and — on a box
+// with a GPU ("gpu" argument) — builds and searches a small index.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "islands_b200.hpp"
+
+#define EXPECT(c)                                             \
+  do {                                                        \
+    if (!(c)) {                                               \
+      std::printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c); \
+      return 1;                                               \
+    }                                                         \
+  } while (0)
+
+int main(int argc, char** argv) {
+  using namespace islands;
+  LeannConfig c;
+  EXPECT(c.m == 30 && c.m0 == 60 && c.ef_construction == 128 && c.ef_search == 64);  // leann.rs:1091-1103
+  EXPECT(LeannConfig::fast().prune_ratio > 0.0f && LeannConfig::accurate().m0 == 96);
+  LeannConfig bad;
+  bad.m = 0;
+  try {
+    bad.validate();
+    EXPECT(false);
+  } catch (const CoreError& e) {
+    EXPECT(e.kind == ErrorKind::InvalidConfig);
+  }
+  try {  // distance.rs:206-212
+    calculate(DistanceMetric::Cosine, {1.f, 2.f}, {1.f, 2.f, 3.f});
+    EXPECT(false);
+  } catch (const CoreError& e) {
+    EXPECT(e.kind == ErrorKind::DimensionMismatch);
+  }
+  PQConfig pc;
+  EXPECT(pc.bytes_per_vector() == 8);
+  EXPECT(std::fabs(to_similarity(1.0f) - 0.5f) < 1e-7f);
+  if (argc > 1 && std::strcmp(argv[1], "gpu") == 0) {
+    EXPECT(std::fabs(calculate(DistanceMetric::Euclidean, {0.f, 0.f}, {3.f, 4.f}) - 5.0f) < 1e-6f);
+    const uint32_t n = 300, d = 16;
+    std::vector<float> v(n * d);
+    uint32_t s = 12345;
+    for (auto& x : v) {
+      s = s * 1664525u + 1013904223u;
+      x = (float)(s >> 8) / 8388608.0f - 1.0f;
+    }
+    LeannIndex idx;
+    idx.build(v, d, n, nullptr, 1, 8);
+    EXPECT(idx.len() == n && idx.dimension() == d);
+    std::vector<float> q(v.begin(), v.begin() + d);
+    auto r = idx.search(q, 5);
+    EXPECT(r.size() == 5 && r[0].first == 0 && r[0].second < 0.01f);
+    for (size_t i = 1; i < r.size(); ++i) EXPECT(r[i - 1].second <= r[i].second);
+    CsrGraph g = idx.graph();
+    EXPECT(g.num_nodes == n && g.node_offsets.back() == g.neighbors.size());
+  } else {
+    try {  // no device: loud failure, never a CPU fallback
+      calculate(DistanceMetric::Euclidean, {0.f, 0.f}, {3.f, 4.f});
+      if (isl_device_count() == 0) EXPECT(false);
+    } catch (const CoreError& e) {
+      EXPECT(e.kind == ErrorKind::Cuda);
+    }
+  }
+  std::printf("OK\n");
+  return 0;
+}
