@@ -29,7 +29,7 @@ EF_LADDER = [16, 24, 32, 48, 64, 96, 128, 192, 256, 384, 512, 768, 1024, 1536, 2
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="islands_b200", choices=["islands_b200", "reference"])
     ap.add_argument("--n", type=int, default=1_000_000)
@@ -371,7 +371,8 @@ def main():
             line["uniform_reference_distribution"] = {
                 "note": "U[-1,1)^768 (benches/hnsw_benchmarks.rs:9-14): distances concentrate, recall>=0.95 needs a near-exhaustive traversal for any graph index",
                 "by_ef": uni}
-    print(json.dumps(line))
+    if rank == 0:
+        print(json.dumps(line))
     if use_dist:
         dist.destroy_process_group()
 

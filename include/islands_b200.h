@@ -246,6 +246,15 @@ isl_status isl_index_search_two_level(const isl_index* idx, const float* queries
                                       float rerank_ratio, uint64_t* out_ids, float* out_dist,
                                       uint32_t* out_count, isl_search_stats* stats_or_null);
 
+/* "PQ ADC traversal + exact rerank": the best-first search of leann.rs:899-988 runs entirely on
+ * table distances (pq.rs:341-348; same admission / termination / tie rules with adc as the key),
+ * then the ef surviving candidates get their exact distance (distance.rs) and are returned sorted by
+ * (distance, id).  Traversal reads m code bytes per visited node instead of 4*dim. */
+isl_status isl_index_search_adc_rerank(const isl_index* idx, const float* queries, uint64_t nq,
+                                       uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* out_ids,
+                                       float* out_dist, uint32_t* out_count,
+                                       isl_search_stats* stats_or_null);
+
 /* ---- island / shard merge (search.rs:211-237, indexer/service.rs:775-801) ---------- */
 /* Per query, merge `parts` lists of k (dist,id) pairs laid out [parts][nq][k] into the k best
  * by (dist, id); ISL_INVALID_ID entries are ignored. */

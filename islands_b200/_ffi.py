@@ -136,6 +136,7 @@ SIGNATURES = {
     "isl_pq_asymmetric_distance": (C.c_int, [_VP, f32p, C.c_uint32, u16p, C.c_uint64, f32p]),
     "isl_index_attach_pq": (C.c_int, [_VP, _VP, u16p]),
     "isl_index_search_two_level": (C.c_int, [_VP, f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, u64p, f32p, u32p, _SSP]),
+    "isl_index_search_adc_rerank": (C.c_int, [_VP, f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u64p, f32p, u32p, _SSP]),
     "isl_merge_topk": (C.c_int, [u64p, f32p, C.c_uint32, C.c_uint64, C.c_uint32, u64p, f32p, u32p]),
     "isl_merge_topk_dev": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint64, C.c_uint32, _VP, _VP, _VP]),
 }

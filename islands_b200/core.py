@@ -452,6 +452,24 @@ class LeannIndex:
         return (ids, dist, cnt, SearchStats(st)) if stats else (ids, dist, cnt)
 
 
+def _adc_rerank(self, queries, k, ef, stats=False):
+    """PQ ADC traversal + exact rerank of the ef survivors (isl_index_search_adc_rerank)."""
+    q = _f32(queries)
+    q = q.reshape(1, -1) if q.ndim == 1 else q
+    nq, qd = q.shape
+    ids = np.empty((nq, k), np.uint64)
+    dist = np.empty((nq, k), np.float32)
+    cnt = np.empty(nq, np.uint32)
+    st = np.zeros(nq, _STATS_DTYPE) if stats else None
+    _check(_ffi.load().isl_index_search_adc_rerank(self._h, _ptr(q, f32p), nq, qd, k, int(ef), _ptr(ids, u64p),
+                                                   _ptr(dist, f32p), _ptr(cnt, u32p),
+                                                   st.ctypes.data_as(C.POINTER(SearchStatsStruct)) if stats else None))
+    return (ids, dist, cnt, SearchStats(st)) if stats else (ids, dist, cnt)
+
+
+LeannIndex.search_adc_rerank_batch = _adc_rerank
+
+
 def random_level(u, ml, max_layers):
     """LeannIndex::random_level (leann.rs:549-554) for an explicit uniform draw u in (0,1)."""
     lvl = math.floor(-math.log(u) * ml)

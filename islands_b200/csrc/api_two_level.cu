@@ -39,10 +39,10 @@ isl_status isl_index_attach_pq(isl_index* idx, const isl_pq* pq, const uint16_t*
   return ISL_OK;
 }
 
-isl_status isl_index_search_two_level(const isl_index* idx, const float* queries, uint64_t nq,
-                                      uint32_t query_dim, uint32_t k, uint32_t ef, float rerank_ratio,
-                                      uint64_t* out_ids, float* out_dist, uint32_t* out_count,
-                                      isl_search_stats* stats) {
+static isl_status pq_search_common(int mode, const isl_index* idx, const float* queries, uint64_t nq,
+                                   uint32_t query_dim, uint32_t k, uint32_t ef, float rerank_ratio,
+                                   uint64_t* out_ids, float* out_dist, uint32_t* out_count,
+                                   isl_search_stats* stats) {
   bool trivial;
   ISL_TRY(search_checks(idx, queries, nq, query_dim, k, &ef, &trivial));
   if (trivial) {
@@ -50,7 +50,7 @@ isl_status isl_index_search_two_level(const isl_index* idx, const float* queries
     return ISL_OK;
   }
   if (!idx->pq) return fail(ISL_PQ_ERROR, "no product quantizer attached (isl_index_attach_pq)");
-  if (!(rerank_ratio > 0.0f) || rerank_ratio > 1.0f)
+  if (mode == 1 && (!(rerank_ratio > 0.0f) || rerank_ratio > 1.0f))
     return fail(ISL_INVALID_ARGUMENT, "rerank_ratio must be in (0, 1]");
   if (!out_ids || !out_dist) return fail(ISL_INVALID_ARGUMENT, "output pointer is null");
   const isl_pq* pq = idx->pq;
@@ -62,18 +62,23 @@ isl_status isl_index_search_two_level(const isl_index* idx, const float* queries
   // |AQ| <= max_degree / a at all times (it gains at most max_degree entries per expansion and
   // then loses ceil(a * |AQ|)); one spare entry per insertion batch keeps the bound simple.
   const uint32_t maxdeg = std::max<uint32_t>(idx->max_degree, 1);
-  const uint64_t aq_cap64 = (uint64_t)std::ceil((double)maxdeg / (double)rerank_ratio) + maxdeg + 2;
-  if (aq_cap64 > (1u << 22)) return fail(ISL_INVALID_ARGUMENT, "rerank_ratio too small for this graph degree");
-  const uint32_t aq_cap = (uint32_t)aq_cap64;
-  const uint32_t u_cap = std::max<uint32_t>(32, round_up(maxdeg + 1, 32));
-
+  uint32_t aq_cap = 0;
+  uint32_t u_cap = std::max<uint32_t>(32, round_up(maxdeg + 1, 32));
   SearchPlan plan;
-  ISL_TRY(plan_search_two_level(idx->cfg.metric, idx->ld, ef, u_cap, m, pq->ksub, aq_cap, idx->sms, &plan));
+  if (mode == 1) {
+    const uint64_t aq_cap64 = (uint64_t)std::ceil((double)maxdeg / (double)rerank_ratio) + maxdeg + 2;
+    if (aq_cap64 > (1u << 22)) return fail(ISL_INVALID_ARGUMENT, "rerank_ratio too small for this graph degree");
+    aq_cap = (uint32_t)aq_cap64;
+    ISL_TRY(plan_search_two_level(idx->cfg.metric, idx->ld, ef, u_cap, m, pq->ksub, aq_cap, idx->sms, &plan));
+  } else {
+    u_cap = std::max<uint32_t>(u_cap, round_up(ef, 32));  // the rerank list holds the ef survivors
+    ISL_TRY(plan_search_adc(idx->cfg.metric, idx->ld, ef, u_cap, m, pq->ksub, idx->sms, &plan));
+  }
   const uint32_t vis_words = round_up((uint32_t)((idx->n + 31) / 32), 4);
   const uint32_t slots = (uint32_t)std::min<uint64_t>(plan.grid, nq);
   ISL_TRY(ensure(idx->visited, (size_t)slots * vis_words));
   if (!plan.r_in_smem) ISL_TRY(ensure(idx->r_global, (size_t)slots * ef));
-  if (!plan.aq_smem_entries) ISL_TRY(ensure(idx->aux_u2, (size_t)slots * aq_cap));
+  if (mode == 1 && !plan.aq_smem_entries) ISL_TRY(ensure(idx->aux_u2, (size_t)slots * aq_cap));
   ISL_TRY(ensure(idx->aux_f32, (size_t)nq * lut_floats + 2));
   ISL_TRY(ensure(idx->q_stage, nq * idx->ld));
   ISL_TRY(ensure(idx->out_ids, nq * k));
@@ -136,6 +141,19 @@ isl_status isl_index_search_two_level(const isl_index* idx, const float* queries
   if (stats)
     ISL_CUDA_TRY(cudaMemcpyAsync(stats, idx->out_stats.p, nq * sizeof(isl_search_stats), cudaMemcpyDeviceToHost, st));
   return search_finish(idx);
+}
+
+isl_status isl_index_search_two_level(const isl_index* idx, const float* queries, uint64_t nq,
+                                      uint32_t query_dim, uint32_t k, uint32_t ef, float rerank_ratio,
+                                      uint64_t* out_ids, float* out_dist, uint32_t* out_count,
+                                      isl_search_stats* stats) {
+  return pq_search_common(1, idx, queries, nq, query_dim, k, ef, rerank_ratio, out_ids, out_dist, out_count, stats);
+}
+
+isl_status isl_index_search_adc_rerank(const isl_index* idx, const float* queries, uint64_t nq,
+                                       uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* out_ids,
+                                       float* out_dist, uint32_t* out_count, isl_search_stats* stats) {
+  return pq_search_common(2, idx, queries, nq, query_dim, k, ef, 0.0f, out_ids, out_dist, out_count, stats);
 }
 
 }  // extern "C"

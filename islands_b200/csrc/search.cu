@@ -19,7 +19,7 @@ constexpr uint32_t kEfSmemMax = 2048;
 constexpr uint32_t kLutSmemMaxFloats = 8192;  // 32 KB of PQ tables per query in shared memory
 constexpr uint32_t kAqSmemMaxEntries = 2048;  // 16 KB approximate queue in shared memory
 
-template <int ACC, bool R_SMEM, bool TWO>
+template <int ACC, bool R_SMEM, int TWO>
 isl_status plan_one(uint32_t ld, uint32_t ef, uint32_t u_cap, int sms, SearchPlan* plan) {
   auto kern = leann_search_kernel<ACC, kCH, kStages, R_SMEM, TWO>;
   const size_t smem = search_smem_bytes<kCH, kStages>(ld, R_SMEM ? ef : 0, u_cap, plan->lut_smem_floats,
@@ -37,7 +37,7 @@ isl_status plan_one(uint32_t ld, uint32_t ef, uint32_t u_cap, int sms, SearchPla
   return ISL_OK;
 }
 
-template <int ACC, bool R_SMEM, bool TWO>
+template <int ACC, bool R_SMEM, int TWO>
 isl_status launch_one(const SearchPlan& plan, const SearchArgs& args, uint32_t grid, cudaStream_t st) {
   leann_search_kernel<ACC, kCH, kStages, R_SMEM, TWO><<<grid, 32, plan.smem, st>>>(args);
   count_launch();
@@ -45,7 +45,7 @@ isl_status launch_one(const SearchPlan& plan, const SearchArgs& args, uint32_t g
   return ISL_OK;
 }
 
-template <bool TWO>
+template <int TWO>
 isl_status plan_dispatch(int acc, bool r_smem, uint32_t ld, uint32_t ef, uint32_t u_cap, int sms, SearchPlan* plan) {
 #define ISL_PLAN(A)                                                                \
   case A:                                                                          \
@@ -60,7 +60,7 @@ isl_status plan_dispatch(int acc, bool r_smem, uint32_t ld, uint32_t ef, uint32_
   return fail(ISL_INVALID_CONFIG, "search: unknown metric");
 }
 
-template <bool TWO>
+template <int TWO>
 isl_status launch_dispatch(const SearchPlan& plan, const SearchArgs& args, uint32_t grid, cudaStream_t st) {
 #define ISL_LAUNCH(A)                                                              \
   case A:                                                                          \
@@ -82,7 +82,8 @@ isl_status plan_search(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap,
   plan->lut_smem_floats = 0;
   plan->aq_smem_entries = 0;
   plan->aq_cap = 0;
-  return plan_dispatch<false>(plan->acc, ef <= kEfSmemMax, ld, ef, u_cap, sms, plan);
+  plan->mode = 0;
+  return plan_dispatch<0>(plan->acc, ef <= kEfSmemMax, ld, ef, u_cap, sms, plan);
 }
 
 isl_status plan_search_two_level(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap, uint32_t pq_m,
@@ -93,14 +94,27 @@ isl_status plan_search_two_level(int32_t metric, uint32_t ld, uint32_t ef, uint3
   plan->lut_smem_floats = lut_floats <= kLutSmemMaxFloats ? lut_floats : 0;
   plan->aq_cap = aq_cap;
   plan->aq_smem_entries = aq_cap <= kAqSmemMaxEntries ? aq_cap : 0;
-  return plan_dispatch<true>(plan->acc, ef <= kEfSmemMax, ld, ef, u_cap, sms, plan);
+  plan->mode = 1;
+  return plan_dispatch<1>(plan->acc, ef <= kEfSmemMax, ld, ef, u_cap, sms, plan);
+}
+
+isl_status plan_search_adc(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap, uint32_t pq_m,
+                           uint32_t pq_ksub, int sms, SearchPlan* plan) {
+  plan->acc = acc_kind_of_metric(metric);
+  plan->two_level = true;
+  plan->mode = 2;
+  const uint32_t lut_floats = (pq_m * pq_ksub + 1u) & ~1u;
+  plan->lut_smem_floats = lut_floats <= kLutSmemMaxFloats ? lut_floats : 0;
+  plan->aq_cap = 0;
+  plan->aq_smem_entries = 0;
+  return plan_dispatch<2>(plan->acc, ef <= kEfSmemMax, ld, ef, u_cap, sms, plan);
 }
 
 isl_status launch_search(const SearchPlan& plan, const SearchArgs& args, cudaStream_t st) {
   // Never launch more warps than queries: idle slots would only clear their bitsets.
   const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(plan.grid, args.nq));
-  return plan.two_level ? launch_dispatch<true>(plan, args, grid, st)
-                        : launch_dispatch<false>(plan, args, grid, st);
+  if (plan.mode == 2) return launch_dispatch<2>(plan, args, grid, st);
+  return plan.mode == 1 ? launch_dispatch<1>(plan, args, grid, st) : launch_dispatch<0>(plan, args, grid, st);
 }
 
 }  // namespace isl

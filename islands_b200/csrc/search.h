@@ -58,6 +58,7 @@ struct SearchPlan {
   bool r_in_smem = true;  // result array in shared memory (else L2-resident global memory)
   int acc = 0;            // accumulation kind (dist_pass.cuh)
   bool two_level = false;
+  int mode = 0;           // 0 exact, 1 two-level (AQ promotion), 2 ADC traversal + exact rerank
   uint32_t lut_smem_floats = 0;  // PQ table staged in shared memory (0 => read from global/L2)
   uint32_t aq_smem_entries = 0;  // approximate queue in shared memory (0 => global/L2)
   uint32_t aq_cap = 0;
@@ -65,6 +66,8 @@ struct SearchPlan {
 
 // Chooses the kernel variant, opts into the shared-memory size and reports the slot count.
 isl_status plan_search(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap, int sms, SearchPlan* plan);
+isl_status plan_search_adc(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap, uint32_t pq_m,
+                           uint32_t pq_ksub, int sms, SearchPlan* plan);
 isl_status plan_search_two_level(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap, uint32_t pq_m,
                                  uint32_t pq_ksub, uint32_t aq_cap, int sms, SearchPlan* plan);
 // Enqueues the search.  args.visited / args.r_global must cover plan.grid slots and

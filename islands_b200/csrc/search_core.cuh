@@ -73,8 +73,15 @@ __device__ __forceinline__ uint32_t prune_keep(float prune_ratio, int strategy, 
 // (pq.rs:341-348) into an approximate queue AQ ordered by (adc,id); after every expansion the
 // ceil(a*|AQ|) best entries (at least one) leave AQ, get their exact distance and go through the
 // same admission as the exact search.  Since |AQ| <= max_degree / a, AQ is a sorted array too.
-template <int ACC, int CH, int STAGES, bool R_SMEM, bool TWO>
+//
+// MODE 2 (ADC) = "PQ ADC traversal + exact rerank": the whole best-first search runs on the
+// table distances (same admission / termination rules with adc in place of the exact distance),
+// then the ef surviving candidates get their exact distance and are re-sorted by (dist, id).
+// Traversal traffic drops from 4d bytes to m bytes per visited node.
+template <int ACC, int CH, int STAGES, bool R_SMEM, int MODE>
 __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
+  constexpr bool TWO = MODE == 1;
+  constexpr bool ADC = MODE == 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using G = StageGeom<CH>;
   float* stage = reinterpret_cast<float*>(smem_raw);
@@ -85,7 +92,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
   uint2* ties = reinterpret_cast<uint2*>(u_nb + a.u_cap);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ties + kTieCap);
   float* lut_smem = reinterpret_cast<float*>(bars + STAGES);
-  uint2* aq_smem = reinterpret_cast<uint2*>(lut_smem + (TWO ? a.lut_smem_floats : 0));
+  uint2* aq_smem = reinterpret_cast<uint2*>(lut_smem + (MODE != 0 ? a.lut_smem_floats : 0));
 
   const uint32_t lane = lane_id();
   const uint32_t slot = blockIdx.x;
@@ -137,7 +144,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     uint32_t r_len = 0, first_unexp = 0, n_ties = 0, aq_len = 0;
     uint64_t n_hop = 0, n_edge = 0, n_dist = 0, n_adc = 0, n_rerank = 0;
     const float* lut = nullptr;
-    if (TWO) {
+    if (MODE != 0) {
       const float* g = a.luts + (size_t)qi * a.pq_m * a.pq_ksub;
       if (a.lut_smem_floats) {
         for (uint32_t i = lane; i < a.lut_smem_floats; i += 32) lut_smem[i] = __ldg(g + i);
@@ -210,16 +217,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     // ---- exact distances of u_list[0 .. total) and their sequential admission ----------------
     // Streaming and fold: row_stream.cuh.  Admission replays the reference's per-neighbour loop
     // (leann.rs:953-970) in list order over the lanes that can still be admitted.
-    auto admit_group = [&](uint32_t base, uint32_t cnt, float acc) {
-      float dn = 0.0f;
-      uint32_t cid = 0;
-      cp_async_wait<0>();  // the squared norms requested before the stream started
-      __syncwarp();
-      if (lane < cnt) {
-        cid = u_list[base + lane];
-        const float nb = (a.metric == ISL_METRIC_COSINE) ? u_nb[base + lane] : 0.0f;
-        dn = finalize_distance(a.metric, acc, na, nb);
-      }
+    auto admit_values = [&](uint32_t cnt, float dn, uint32_t cid) {
       float worst = 0.0f;
       if (r_len > 0) worst = __uint_as_float(R.ld(r_len - 1).x);
       uint32_t mask = __ballot_sync(0xffffffffu, lane < cnt && (r_len < ef || dn < worst));
@@ -232,6 +230,30 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         if (!add) add = dj < __uint_as_float(R.ld(ef - 1).x);  // raw f32 `<` (leann.rs:959)
         if (add) r_insert(dj, idj);
       }
+    };
+    auto admit_group = [&](uint32_t base, uint32_t cnt, float acc) {
+      float dn = 0.0f;
+      uint32_t cid = 0;
+      cp_async_wait<0>();  // the squared norms requested before the stream started
+      __syncwarp();
+      if (lane < cnt) {
+        cid = u_list[base + lane];
+        const float nb = (a.metric == ISL_METRIC_COSINE) ? u_nb[base + lane] : 0.0f;
+        dn = finalize_distance(a.metric, acc, na, nb);
+      }
+      admit_values(cnt, dn, cid);
+    };
+    // table_distance (pq.rs:341-348) of node `nid`: left fold over the subquantizers, then sqrt
+    auto adc_of = [&](uint32_t nid) -> float {
+      float sacc = 0.0f;
+      if (a.codes8) {
+        const uint8_t* cd = a.codes8 + (size_t)nid * a.pq_m;
+        for (uint32_t j = 0; j < a.pq_m; ++j) sacc = __fadd_rn(sacc, lut[j * a.pq_ksub + cd[j]]);
+      } else {
+        const uint16_t* cd = a.codes16 + (size_t)nid * a.pq_m;
+        for (uint32_t j = 0; j < a.pq_m; ++j) sacc = __fadd_rn(sacc, lut[j * a.pq_ksub + cd[j]]);
+      }
+      return __fsqrt_rn(sacc);
     };
     auto score_and_admit = [&](uint32_t total) {
       if (a.metric == ISL_METRIC_COSINE) {  // 4-byte async gathers: land long before the group is admitted
@@ -249,8 +271,14 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       atomicOr(vis + (a.entry >> 5), 1u << (a.entry & 31));
     }
     __syncwarp();
-    score_and_admit(1);
-    n_dist = 1;
+    if (ADC) {
+      const float d0 = adc_of(a.entry);
+      admit_values(1, d0, a.entry);
+      n_adc = 1;
+    } else {
+      score_and_admit(1);
+      n_dist = 1;
+    }
 
     // ---- main loop (leann.rs:922-972) ------------------------------------------------------
     for (;;) {
@@ -345,6 +373,21 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       __syncwarp();
       if (ucnt == 0 && (!TWO || aq_len == 0)) continue;  // leann.rs:939-941
 
+      if (ADC) {
+        // traversal on table distances only: one lane per unvisited neighbour, list order
+        n_adc += ucnt;
+        for (uint32_t b = 0; b < ucnt; b += 32) {
+          const uint32_t i = b + lane;
+          float adc = 0.0f;
+          uint32_t nid = 0;
+          if (i < ucnt) {
+            nid = u_list[i];
+            adc = adc_of(nid);
+          }
+          admit_values(min(32u, ucnt - b), adc, nid);
+        }
+        continue;
+      }
       if (!TWO) {
         const uint32_t keep = prune_keep(a.prune_ratio, a.strategy, ucnt, r_len, ef);  // :944
         n_dist += keep;
@@ -360,15 +403,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         uint32_t nid = 0;
         if (i < ucnt) {
           nid = u_list[i];
-          float sacc = 0.0f;  // table_distance: left fold over subquantizers, then sqrt
-          if (a.codes8) {
-            const uint8_t* cd = a.codes8 + (size_t)nid * a.pq_m;
-            for (uint32_t j = 0; j < a.pq_m; ++j) sacc = __fadd_rn(sacc, lut[j * a.pq_ksub + cd[j]]);
-          } else {
-            const uint16_t* cd = a.codes16 + (size_t)nid * a.pq_m;
-            for (uint32_t j = 0; j < a.pq_m; ++j) sacc = __fadd_rn(sacc, lut[j * a.pq_ksub + cd[j]]);
-          }
-          adc = __fsqrt_rn(sacc);
+          adc = adc_of(nid);
         }
         const uint32_t cntb = min(32u, ucnt - b);
         for (uint32_t t = 0; t < cntb; ++t) {  // sorted insert of each (adc,id) into AQ
@@ -415,6 +450,21 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       n_dist += promote;
       n_rerank += promote;
       score_and_admit(promote);
+    }
+
+    if (ADC) {
+      // exact rerank of the ef survivors: their ids move to u_list, R is rebuilt from the exact
+      // distances (capacity ef >= their number, so every one is admitted) and ends up sorted by
+      // (dist, id).
+      const uint32_t total = r_len;
+      for (uint32_t i = lane; i < total; i += 32) u_list[i] = R.ld(i).y & ~kExpandedBit;
+      __syncwarp();
+      r_len = 0;
+      first_unexp = 0;
+      n_ties = 0;
+      n_dist = total;
+      n_rerank = total;
+      score_and_admit(total);
     }
 
     // ---- results: R is already sorted by (dist,id); take(k) (leann.rs:895) -----------------

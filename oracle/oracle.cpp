@@ -761,6 +761,83 @@ int32_t orc_leann_search_two_level(const isl_leann_config* cfg, const float* vec
   return ISL_OK;
 }
 
+// PQ ADC traversal + exact rerank: the loop of leann.rs:899-988 with table_distance (pq.rs:341-348)
+// as the distance, then exact distances for the ef survivors and a final (dist,id) sort.
+int32_t orc_leann_search_adc_rerank(const isl_leann_config* cfg, const float* vectors, uint64_t n, uint32_t d,
+                                    const uint64_t* offsets, const uint64_t* nbrs, int64_t entry,
+                                    const float* codebooks, uint32_t m, uint32_t ksub, const uint16_t* codes,
+                                    const float* queries, uint64_t nq, uint32_t k, uint32_t ef_in, uint64_t* out_ids,
+                                    float* out_dist, uint32_t* out_count, isl_search_stats* stats, int32_t threads) {
+  if (n == 0) {
+    for (uint64_t qi = 0; qi < nq; ++qi) {
+      std::vector<Key> none;
+      write_topk(none, k, out_ids + qi * k, out_dist + qi * k, out_count ? out_count + qi : nullptr);
+      if (stats) stats[qi] = isl_search_stats{0, 0, 0, 0, 0};
+    }
+    return ISL_OK;
+  }
+  if (entry < 0) return ISL_INDEX_NOT_BUILT;
+  const uint64_t ef = std::max<uint64_t>(ef_in, k);
+  const uint32_t dsub = d / m;
+  CsrView g{offsets, nbrs, n};
+  int nt = std::max(1, threads);
+  std::vector<Visited> vis(nt);
+  parallel_for(nq, threads, [&](uint64_t b, uint64_t e, int w) {
+    std::vector<float> lut((uint64_t)m * ksub);
+    std::vector<Key> res;
+    auto adc = [&](uint64_t id) {
+      float s = 0.0f;
+      const uint16_t* cd = codes + id * (uint64_t)m;
+      for (uint32_t j = 0; j < m; ++j) s = s + lut[(uint64_t)j * ksub + cd[j]];
+      return std::sqrt(s);
+    };
+    for (uint64_t qi = b; qi < e; ++qi) {
+      const float* q = queries + qi * (uint64_t)d;
+      orc_pq_build_tables(codebooks, m, ksub, dsub, q, lut.data());
+      Visited& visited = vis[w];
+      visited.reset(n);
+      MinHeap cand;
+      MaxHeap results;
+      float ed = adc((uint64_t)entry);
+      visited.insert((uint64_t)entry);
+      cand.push({ed, (uint64_t)entry});
+      results.push({ed, (uint64_t)entry});
+      uint64_t n_hop = 0, n_edge = 0, n_adc = 1;
+      while (!cand.empty()) {
+        Key c = cand.top();
+        cand.pop();
+        if (results.size() >= ef && of_gt(c.d, results.top().d)) break;
+        const uint64_t* nb;
+        uint64_t cnt;
+        g.get(c.id, nb, cnt);
+        n_hop++;
+        n_edge += cnt;
+        for (uint64_t i = 0; i < cnt; ++i) {
+          if (!visited.insert(nb[i])) continue;
+          float nd = adc(nb[i]);
+          n_adc++;
+          bool should_add = results.size() < ef || nd < results.top().d;
+          if (should_add) {
+            cand.push({nd, nb[i]});
+            results.push({nd, nb[i]});
+            if (results.size() > ef) results.pop();
+          }
+        }
+      }
+      res.clear();
+      while (!results.empty()) {
+        Key r = results.top();
+        results.pop();
+        res.push_back({calc(cfg->metric, q, vectors + r.id * (uint64_t)d, d), r.id});  // exact rerank
+      }
+      std::sort(res.begin(), res.end(), key_lt);
+      write_topk(res, k, out_ids + qi * k, out_dist + qi * k, out_count ? out_count + qi : nullptr);
+      if (stats) stats[qi] = isl_search_stats{n_hop, n_edge, res.size(), n_adc, res.size()};
+    }
+  });
+  return ISL_OK;
+}
+
 void orc_merge_topk(const uint64_t* ids, const float* dist, uint32_t parts, uint64_t nq, uint32_t k,
                     uint64_t* out_ids, float* out_dist, uint32_t* out_count) {
   std::vector<Key> all;

@@ -90,6 +90,14 @@ int32_t orc_leann_search_two_level(const isl_leann_config* cfg, const float* vec
                                    float* out_dist, uint32_t* out_count,
                                    isl_search_stats* stats_or_null, int32_t threads);
 
+/* "PQ ADC traversal + exact rerank" (definition: include/islands_b200.h isl_index_search_adc_rerank). */
+int32_t orc_leann_search_adc_rerank(const isl_leann_config* cfg, const float* vectors, uint64_t n, uint32_t d,
+                                    const uint64_t* offsets, const uint64_t* nbrs, int64_t entry,
+                                    const float* codebooks, uint32_t m, uint32_t ksub, const uint16_t* codes,
+                                    const float* queries, uint64_t nq, uint32_t k, uint32_t ef, uint64_t* out_ids,
+                                    float* out_dist, uint32_t* out_count, isl_search_stats* stats_or_null,
+                                    int32_t threads);
+
 /* search.rs:211-237 under the (dist,id) rule: lists [parts][nq][k]. */
 void orc_merge_topk(const uint64_t* ids, const float* dist, uint32_t parts, uint64_t nq, uint32_t k,
                     uint64_t* out_ids, float* out_dist, uint32_t* out_count);

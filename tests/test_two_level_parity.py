@@ -45,3 +45,28 @@ def test_two_level_needs_pq(gpu_lib, orc):
     idx = LeannIndex.from_csr(cfg, v, off, nbrs, levels, entry)
     with pytest.raises(PQError):
         idx.search_two_level_batch(v[:2], 5, 32, 0.1)
+
+
+@pytest.mark.parametrize("m,ksub", [(8, 256), (4, 16), (16, 300), (96, 256)])
+def test_adc_traversal_rerank_matches_oracle(gpu_lib, orc, m, ksub):
+    """PQ ADC traversal + exact rerank (include/islands_b200.h isl_index_search_adc_rerank)."""
+    from islands_b200 import LeannIndex, PQConfig, ProductQuantizer
+
+    cfg, v, levels, off, nbrs, entry = oracle_graph(orc, 3000, 96, seed=61)
+    cb = orc.pq_train(1, v[:1000], m, ksub, 3, 7)
+    codes = orc.pq_encode(1, cb, v)
+    pq = ProductQuantizer(96, PQConfig(m, ksub, 3, 7))
+    pq.set_codebooks(cb)
+    idx = LeannIndex.from_csr(cfg, v, off, nbrs, levels, entry)
+    idx.attach_pq(pq, codes)
+    q = np.concatenate([uniform(np.random.RandomState(63), 90, 96), v[:10]])
+    for k, ef in [(10, 16), (10, 100), (25, 200)]:
+        ids, dist, cnt, st = idx.search_adc_rerank_batch(q, k, ef, stats=True)
+        o_ids, o_dist, o_cnt, o_st = orc.leann_search_adc_rerank(cfg._s, v, off, nbrs, entry, cb, codes, q, k, ef,
+                                                                 threads=8, stats=True)
+        assert np.array_equal(cnt, o_cnt)
+        assert np.array_equal(ids, o_ids)
+        assert np.array_equal(dist.view(np.uint32), o_dist.view(np.uint32))
+        for f in ("n_hop", "n_edge", "n_dist", "n_adc", "n_rerank"):
+            assert np.array_equal(getattr(st, f), o_st[f]), f
+        assert (np.diff(dist, axis=1) >= 0).all()  # exact distances, ascending
