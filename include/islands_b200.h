@@ -255,6 +255,44 @@ isl_status isl_index_search_adc_rerank(const isl_index* idx, const float* querie
                                        float* out_dist, uint32_t* out_count,
                                        isl_search_stats* stats_or_null);
 
+/* ---- HNSW graph (src/core/hnsw.rs) -------------------------------------------------- */
+/* HnswGraph::new (hnsw.rs:167-178): empty graph; the dimension is fixed by the first insert. */
+isl_status isl_hnsw_new(const isl_hnsw_config* cfg, isl_hnsw** out);
+void isl_hnsw_free(isl_hnsw* g);
+uint64_t isl_hnsw_len(const isl_hnsw* g);           /* HnswGraph::len */
+uint32_t isl_hnsw_dimension(const isl_hnsw* g);     /* HnswGraph::dimension (0 = None) */
+int64_t isl_hnsw_entry_point(const isl_hnsw* g);    /* entry_point (ISL_NO_ENTRY = None) */
+uint64_t isl_hnsw_max_level(const isl_hnsw* g);
+/* `count` calls of HnswGraph::insert (hnsw.rs:214-329) for vectors [count][dim]; ids are
+ * len()..len()+count-1 and *out_first_id is the first.  levels_or_null: explicit level per vector
+ * (the reference draws them from thread_rng, hnsw.rs:206-211); NULL -> drawn from `seed` with the
+ * same formula.  batch = 1 is the reference's sequential insertion; batch > 1 inserts up to `batch`
+ * nodes against one graph snapshot (GPU-parallel construction).  dim != dimension() ->
+ * ISL_DIM_MISMATCH. */
+isl_status isl_hnsw_insert_batch(isl_hnsw* g, const float* vectors, uint64_t count, uint32_t dim,
+                                 const uint64_t* levels_or_null, uint64_t seed, uint32_t batch,
+                                 uint64_t* out_first_id);
+isl_status isl_hnsw_insert_batch_dev(isl_hnsw* g, const float* d_vectors, uint64_t count, uint32_t dim,
+                                     const uint64_t* levels_or_null, uint64_t seed, uint32_t batch,
+                                     uint64_t* out_first_id);
+/* HnswNode::level / neighbors_at (hnsw.rs:90-125) of get_node(node_id) (hnsw.rs:201-203). */
+isl_status isl_hnsw_node_level(const isl_hnsw* g, uint64_t node_id, uint64_t* out_level);
+isl_status isl_hnsw_get_neighbors(const isl_hnsw* g, uint64_t node_id, uint64_t layer, uint64_t* out,
+                                  uint64_t cap, uint64_t* out_count);
+/* All lists of one layer: out_degrees [len] (-1 = the node does not reach the layer),
+ * out_neighbors [len][m0 or m] padded with ISL_INVALID_ID; either pointer may be NULL. */
+isl_status isl_hnsw_export_layer(const isl_hnsw* g, uint64_t layer, int64_t* out_degrees,
+                                 uint64_t* out_neighbors);
+/* Batched HnswGraph::search (hnsw.rs:458-504): greedy descent from the entry point through the
+ * upper layers, then best-first search of layer 0 with ef := max(ef, k). */
+isl_status isl_hnsw_search(const isl_hnsw* g, const float* queries, uint64_t nq, uint32_t query_dim,
+                           uint32_t k, uint32_t ef, uint64_t* out_ids, float* out_dist,
+                           uint32_t* out_count);
+isl_status isl_hnsw_search_dev(const isl_hnsw* g, const float* d_queries, uint64_t nq,
+                               uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
+                               float* d_out_dist, uint32_t* d_out_count);
+isl_status isl_hnsw_last_search_timing(const isl_hnsw* g, float* kernel_ms);
+
 /* ---- island / shard merge (search.rs:211-237, indexer/service.rs:775-801) ---------- */
 /* Per query, merge `parts` lists of k (dist,id) pairs laid out [parts][nq][k] into the k best
  * by (dist, id); ISL_INVALID_ID entries are ignored. */

@@ -2,7 +2,7 @@
 `src/core` API.  Compute lives in lib/libislands_b200.so (C ABI: include/islands_b200.h);
 this package is the host-side mirror of the reference interface.  No CPU fallback."""
 from .core import (CoreError, CsrGraph, CudaError, DimensionMismatch, DistanceMetric, EmptyCollection,
-                   HnswConfig, IndexNotBuilt, InMemoryEmbeddingProvider, InvalidArgument, InvalidConfig,
+                   HnswConfig, HnswGraph, HnswNode, IndexNotBuilt, InMemoryEmbeddingProvider, InvalidArgument, InvalidConfig,
                    LeannConfig, LeannIndex, NodeNotFound, PQConfig, PQError, ProductQuantizer,
                    PruningStrategy, SerializationError, merge_topk, merge_topk_dev, normalize_vector, normalized,
                    random_level, to_similarity)

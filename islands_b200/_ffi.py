@@ -137,6 +137,20 @@ SIGNATURES = {
     "isl_index_attach_pq": (C.c_int, [_VP, _VP, u16p]),
     "isl_index_search_two_level": (C.c_int, [_VP, f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, u64p, f32p, u32p, _SSP]),
     "isl_index_search_adc_rerank": (C.c_int, [_VP, f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u64p, f32p, u32p, _SSP]),
+    "isl_hnsw_new": (C.c_int, [_HCP, _VPP]),
+    "isl_hnsw_free": (None, [_VP]),
+    "isl_hnsw_len": (C.c_uint64, [_VP]),
+    "isl_hnsw_dimension": (C.c_uint32, [_VP]),
+    "isl_hnsw_entry_point": (C.c_int64, [_VP]),
+    "isl_hnsw_max_level": (C.c_uint64, [_VP]),
+    "isl_hnsw_insert_batch": (C.c_int, [_VP, f32p, C.c_uint64, C.c_uint32, u64p, C.c_uint64, C.c_uint32, u64p]),
+    "isl_hnsw_insert_batch_dev": (C.c_int, [_VP, _VP, C.c_uint64, C.c_uint32, u64p, C.c_uint64, C.c_uint32, u64p]),
+    "isl_hnsw_node_level": (C.c_int, [_VP, C.c_uint64, u64p]),
+    "isl_hnsw_get_neighbors": (C.c_int, [_VP, C.c_uint64, C.c_uint64, u64p, C.c_uint64, u64p]),
+    "isl_hnsw_export_layer": (C.c_int, [_VP, C.c_uint64, C.POINTER(C.c_int64), u64p]),
+    "isl_hnsw_search": (C.c_int, [_VP, f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u64p, f32p, u32p]),
+    "isl_hnsw_search_dev": (C.c_int, [_VP, _VP, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _VP, _VP, _VP]),
+    "isl_hnsw_last_search_timing": (C.c_int, [_VP, f32p]),
     "isl_merge_topk": (C.c_int, [u64p, f32p, C.c_uint32, C.c_uint64, C.c_uint32, u64p, f32p, u32p]),
     "isl_merge_topk_dev": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint64, C.c_uint32, _VP, _VP, _VP]),
 }

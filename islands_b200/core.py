@@ -215,6 +215,130 @@ class HnswConfig:
         _check(_ffi.load().isl_hnsw_config_validate(C.byref(self._s)))
 
 
+class HnswNode:
+    """HnswNode (hnsw.rs:90-125): id, level, per-layer connections (vector stays on the device)."""
+
+    def __init__(self, id, level, connections):
+        self.id = id
+        self.level = level
+        self.connections = connections
+
+    def neighbors_at(self, layer):
+        return self.connections[layer] if layer < len(self.connections) else None
+
+
+class HnswGraph:
+    """HnswGraph (hnsw.rs:151-531) with vectors and all layers resident in HBM."""
+
+    def __init__(self, config=None):
+        self.config = config or HnswConfig()
+        self.config.validate()  # HnswGraph::new (hnsw.rs:167-178)
+        h = C.c_void_p()
+        _check(_ffi.load().isl_hnsw_new(C.byref(self.config._s), C.byref(h)))
+        self._h = h
+
+    def free(self):
+        if getattr(self, "_h", None) is not None:
+            _ffi.load().isl_hnsw_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(_ffi.load().isl_hnsw_len(self._h))
+
+    def is_empty(self):
+        return len(self) == 0
+
+    def dimension(self):
+        return int(_ffi.load().isl_hnsw_dimension(self._h)) or None
+
+    @property
+    def entry_point(self):
+        e = int(_ffi.load().isl_hnsw_entry_point(self._h))
+        return None if e < 0 else e
+
+    @property
+    def max_level(self):
+        return int(_ffi.load().isl_hnsw_max_level(self._h))
+
+    def insert(self, vector, level=None, seed=0):
+        """HnswGraph::insert (hnsw.rs:214-250) -> id.  `level` replaces the thread_rng draw."""
+        v = _f32(vector).reshape(1, -1)
+        return self.insert_batch(v, None if level is None else [level], seed=seed, batch=1)
+
+    def insert_batch(self, vectors, levels=None, seed=0, batch=1):
+        """len(vectors) inserts; batch > 1 inserts up to `batch` nodes per graph snapshot. -> first id"""
+        v = _f32(vectors)
+        v = v.reshape(1, -1) if v.ndim == 1 else v
+        lv = np.ascontiguousarray(levels, np.uint64) if levels is not None else None
+        first = C.c_uint64()
+        _check(_ffi.load().isl_hnsw_insert_batch(self._h, _ptr(v, f32p), v.shape[0], v.shape[1], _ptr(lv, u64p),
+                                                 seed, batch, C.byref(first)))
+        return first.value
+
+    def insert_batch_dev(self, d_vectors_ptr, count, dim, levels=None, seed=0, batch=1):
+        lv = np.ascontiguousarray(levels, np.uint64) if levels is not None else None
+        first = C.c_uint64()
+        _check(_ffi.load().isl_hnsw_insert_batch_dev(self._h, C.c_void_p(d_vectors_ptr), count, dim, _ptr(lv, u64p),
+                                                     seed, batch, C.byref(first)))
+        return first.value
+
+    def get_node(self, id):
+        """HnswGraph::get_node (hnsw.rs:201-203)."""
+        lib = _ffi.load()
+        lvl = C.c_uint64()
+        if lib.isl_hnsw_node_level(self._h, id, C.byref(lvl)) != 0:
+            return None
+        conns = []
+        cap = int(max(self.config.m0, self.config.m))
+        for layer in range(lvl.value + 1):
+            buf = np.empty(cap, np.uint64)
+            cnt = C.c_uint64()
+            _check(lib.isl_hnsw_get_neighbors(self._h, id, layer, _ptr(buf, u64p), cap, C.byref(cnt)))
+            conns.append(buf[:cnt.value].copy())
+        return HnswNode(id, lvl.value, conns)
+
+    def export_layer(self, layer):
+        """-> (degrees [n] int64, -1 where the node lacks the layer; neighbors [n, M] u64 padded)."""
+        n = len(self)
+        cc = int(self.config.m0 if layer == 0 else self.config.m)
+        deg = np.empty(n, np.int64)
+        nb = np.empty((n, cc), np.uint64)
+        _check(_ffi.load().isl_hnsw_export_layer(self._h, layer, deg.ctypes.data_as(C.POINTER(C.c_int64)), _ptr(nb, u64p)))
+        return deg, nb
+
+    def search(self, query, k, ef):
+        """HnswGraph::search (hnsw.rs:458-504): one query -> [(id, dist)] ascending."""
+        ids, dist, cnt = self.search_batch(_f32(query).reshape(1, -1), k, ef)
+        return [(int(ids[0, i]), float(dist[0, i])) for i in range(int(cnt[0]))]
+
+    def search_batch(self, queries, k, ef):
+        q = _f32(queries)
+        q = q.reshape(1, -1) if q.ndim == 1 else q
+        nq, qd = q.shape
+        ids = np.empty((nq, k), np.uint64)
+        dist = np.empty((nq, k), np.float32)
+        cnt = np.empty(nq, np.uint32)
+        _check(_ffi.load().isl_hnsw_search(self._h, _ptr(q, f32p), nq, qd, k, int(ef), _ptr(ids, u64p),
+                                           _ptr(dist, f32p), _ptr(cnt, u32p)))
+        return ids, dist, cnt
+
+    def search_batch_dev(self, d_queries_ptr, nq, dim, k, ef, d_ids_ptr, d_dist_ptr, d_count_ptr=None):
+        _check(_ffi.load().isl_hnsw_search_dev(self._h, C.c_void_p(d_queries_ptr), nq, dim, k, int(ef),
+                                               C.c_void_p(d_ids_ptr), C.c_void_p(d_dist_ptr),
+                                               C.c_void_p(d_count_ptr) if d_count_ptr else None))
+
+    def last_search_timing(self):
+        ms = C.c_float()
+        _check(_ffi.load().isl_hnsw_last_search_timing(self._h, C.byref(ms)))
+        return ms.value
+
+
 class InMemoryEmbeddingProvider:
     """InMemoryEmbeddingProvider (leann.rs:104-159): id -> stored embedding."""
 

@@ -49,6 +49,13 @@ struct SearchArgs {
   uint2* aq_global;         // [slots][aq_cap] when the queue does not fit shared memory
   uint32_t lut_smem_floats; // pq_m*pq_ksub when the table is staged in shared memory, else 0
   uint32_t aq_smem_entries; // aq_cap when the queue lives in shared memory, else 0
+  // HNSW (hnsw.rs): per-query entry points, queries taken from the vector table, layer row pools
+  const uint32_t* entries;   // entry node per query (null => `entry`): [nq], or indexed by node id when query_ids is set
+  const uint32_t* query_ids; // [nq] query i is vectors[query_ids[i]] (null => `queries`)
+  const uint32_t* row_map;   // node -> first adjacency row in a compact pool (null => row = node)
+  uint32_t row_add;          // added to row_map[node] (layer - 1)
+  const uint32_t* node_levels; // [n] top layer of every node; a node has no list above it (hnsw.rs:108-110)
+  uint32_t layer;            // layer being searched (only read when node_levels is set)
 };
 
 struct SearchPlan {

@@ -130,7 +130,9 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
 
     // ---- per-query setup -------------------------------------------------------------
     {
-      const float4* src = reinterpret_cast<const float4*>(a.queries + (size_t)qi * a.q_ld);
+      // a query is either row qi of the query matrix or (construction) a row of the vector table
+      const float4* src = reinterpret_cast<const float4*>(
+          a.query_ids ? a.vectors + (size_t)__ldg(a.query_ids + qi) * a.ld : a.queries + (size_t)qi * a.q_ld);
       float4* dst = reinterpret_cast<float4*>(q_smem);
       for (uint32_t i = lane; i < a.ld / 4; i += 32) dst[i] = src[i];
       uint4* v4 = reinterpret_cast<uint4*>(vis);
@@ -265,15 +267,16 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       stream_rows_fold<ACC, STAGES>(ring, a.vectors, a.ld, a.d, u_list, total, q_smem, admit_group);
     };
 
-    // ---- entry point (leann.rs:911-916) ----------------------------------------------------
+    // ---- entry point (leann.rs:911-916; per query for the HNSW layer searches, hnsw.rs:501) ----
+    const uint32_t entry = a.entries ? __ldg(a.entries + (a.query_ids ? __ldg(a.query_ids + qi) : qi)) : a.entry;
     if (lane == 0) {
-      u_list[0] = a.entry;
-      atomicOr(vis + (a.entry >> 5), 1u << (a.entry & 31));
+      u_list[0] = entry;
+      atomicOr(vis + (entry >> 5), 1u << (entry & 31));
     }
     __syncwarp();
     if (ADC) {
-      const float d0 = adc_of(a.entry);
-      admit_values(1, d0, a.entry);
+      const float d0 = adc_of(entry);
+      admit_values(1, d0, entry);
       n_adc = 1;
     } else {
       score_and_admit(1);
@@ -331,9 +334,14 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         start = __ldg(a.offsets + cur);
         deg = (uint32_t)(__ldg(a.offsets + cur + 1) - start);
       } else {
-        start = (uint64_t)cur * a.adj_stride;
-        if (a.degrees) {
-          deg = __ldg(a.degrees + cur);
+        // upper HNSW layers keep their rows in a compact pool: row = row_map[node] + row_add
+        const bool has_layer = !a.node_levels || __ldg(a.node_levels + cur) >= a.layer;
+        const uint32_t row = (a.row_map && has_layer) ? __ldg(a.row_map + cur) + a.row_add : cur;
+        start = (uint64_t)row * a.adj_stride;
+        if (!has_layer) {
+          deg = 0;  // neighbors_at(layer) is None above the node's own level (hnsw.rs:108-110, :362)
+        } else if (a.degrees) {
+          deg = __ldg(a.degrees + row);
         } else {
           deg = a.adj_stride;
           sentinel = true;

@@ -1030,6 +1030,102 @@ int32_t orc_hnsw_insert(orc_hnsw* g, const float* v, uint64_t level, uint64_t* o
   return ISL_OK;
 }
 
+// Round model of HnswGraph::insert for GPU-parallel construction (islands_b200/csrc/hnsw.cu).
+// `count` vectors are inserted in rounds of min(batch, max(1, len/2)) nodes.  Every node of a
+// round runs the read-only half of insert_node (greedy descent hnsw.rs:263-282, per-layer
+// search_layer + take(M) :285-300, entry for the next layer :316-318) against the graph as it stood
+// before the round; then the mutating half (own lists :298-300, reverse edges + prune_connections
+// :303-313, entry update :322-325, nodes.insert :327) is applied node by node in id order.
+// Within one insert the two halves commute (a layer's reverse edges only touch that layer's lists,
+// which no later search of the same insert reads), so batch = 1 is exactly orc_hnsw_insert.
+int32_t orc_hnsw_insert_batch(orc_hnsw* g, const float* vectors, uint64_t count, const uint64_t* levels,
+                              uint32_t batch, int32_t threads) {
+  if (batch == 0) batch = 1;
+  uint64_t done = 0;
+  while (done < count) {
+    const uint64_t have = g->nodes.size();
+    if (have == 0) {  // hnsw.rs:240-245
+      int32_t st = orc_hnsw_insert(g, vectors, levels[0], nullptr);
+      if (st != ISL_OK) return st;
+      done = 1;
+      continue;
+    }
+    const uint64_t round = std::min<uint64_t>(count - done, std::min<uint64_t>(batch, std::max<uint64_t>(1, have / 2)));
+    struct Plan {
+      std::vector<std::vector<Key>> sel;  // per layer 0..=level: the first M of search_layer's result
+    };
+    std::vector<Plan> plans(round);
+    std::vector<int32_t> status(round, ISL_OK);
+    parallel_for(round, threads, [&](uint64_t b, uint64_t e, int) {
+      std::vector<Key> found;
+      for (uint64_t i = b; i < e; ++i) {
+        const float* q = vectors + (done + i) * (uint64_t)g->d;
+        const uint64_t level = levels[done + i];
+        uint64_t current = (uint64_t)g->entry;
+        float current_dist = calc(g->cfg.metric, q, g->nodes.at(current).v.data(), g->d);
+        if (g->max_level >= level + 1) {
+          int32_t st = hnsw_greedy(g, q, current, current_dist, g->max_level, level + 1);
+          if (st != ISL_OK) { status[i] = st; continue; }
+        }
+        plans[i].sel.resize(level + 1);
+        for (uint64_t layer = level + 1; layer-- > 0;) {
+          int32_t st = hnsw_search_layer(g, q, current, g->cfg.ef_construction, layer, found);
+          if (st != ISL_OK) { status[i] = st; break; }
+          const uint64_t mm = layer == 0 ? g->cfg.m0 : g->cfg.m;
+          for (size_t t = 0; t < found.size() && t < mm; ++t) plans[i].sel[layer].push_back(found[t]);
+          if (!plans[i].sel[layer].empty()) current = plans[i].sel[layer][0].id;
+        }
+      }
+    });
+    for (int32_t st : status)
+      if (st != ISL_OK) return st;
+    for (uint64_t i = 0; i < round; ++i) {
+      const uint64_t id = g->next_id++;
+      const uint64_t level = levels[done + i];
+      orc_hnsw::Node node;
+      node.v.assign(vectors + (done + i) * (uint64_t)g->d, vectors + (done + i + 1) * (uint64_t)g->d);
+      node.level = level;
+      node.conn.resize(level + 1);
+      for (uint64_t layer = level + 1; layer-- > 0;) {
+        const uint64_t mm = layer == 0 ? g->cfg.m0 : g->cfg.m;
+        for (const Key& kx : plans[i].sel[layer]) node.conn[layer].push_back(kx.id);
+        for (const Key& kx : plans[i].sel[layer]) {
+          auto it = g->nodes.find(kx.id);
+          if (it == g->nodes.end() || layer >= it->second.conn.size()) continue;
+          auto& conns = it->second.conn[layer];
+          conns.push_back(id);
+          if (conns.size() > mm) {  // prune_connections: the id being inserted is not in `nodes` yet
+            struct S { uint64_t id; float dist; };
+            std::vector<S> scored;
+            const float* nv = it->second.v.data();
+            for (uint64_t x : conns) {
+              auto xit = g->nodes.find(x);
+              if (xit == g->nodes.end()) continue;
+              scored.push_back({x, calc(g->cfg.metric, nv, xit->second.v.data(), g->d)});
+            }
+            std::stable_sort(scored.begin(), scored.end(), [](const S& a, const S& b) { return a.dist < b.dist; });
+            std::vector<uint64_t> pruned;
+            for (size_t t = 0; t < scored.size() && t < mm; ++t) pruned.push_back(scored[t].id);
+            conns = pruned;
+          }
+        }
+      }
+      if (level > g->max_level) {
+        g->max_level = level;
+        g->entry = (int64_t)id;
+      }
+      g->nodes.emplace(id, std::move(node));
+    }
+    done += round;
+  }
+  return ISL_OK;
+}
+
+int64_t orc_hnsw_node_level(const orc_hnsw* g, uint64_t id) {
+  auto it = g->nodes.find(id);
+  return it == g->nodes.end() ? -1 : (int64_t)it->second.level;
+}
+
 int32_t orc_hnsw_search(const orc_hnsw* g, const float* queries, uint64_t nq, uint32_t k,
                         uint32_t ef_in, uint64_t* out_ids, float* out_dist, uint32_t* out_count,
                         int32_t threads) {

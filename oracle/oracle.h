@@ -107,6 +107,10 @@ typedef struct orc_hnsw orc_hnsw;
 orc_hnsw* orc_hnsw_new(const isl_hnsw_config* cfg, uint32_t d);
 void orc_hnsw_free(orc_hnsw* g);
 int32_t orc_hnsw_insert(orc_hnsw* g, const float* v, uint64_t level, uint64_t* out_id);
+/* Round model of insert for batched construction (see oracle.cpp); batch = 1 == orc_hnsw_insert. */
+int32_t orc_hnsw_insert_batch(orc_hnsw* g, const float* vectors, uint64_t count, const uint64_t* levels,
+                              uint32_t batch, int32_t threads);
+int64_t orc_hnsw_node_level(const orc_hnsw* g, uint64_t id);
 uint64_t orc_hnsw_len(const orc_hnsw* g);
 int64_t orc_hnsw_entry_point(const orc_hnsw* g);
 uint64_t orc_hnsw_max_level(const orc_hnsw* g);

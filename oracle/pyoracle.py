@@ -81,6 +81,10 @@ def lib():
         l.orc_hnsw_free.argtypes = [C.c_void_p]
         l.orc_hnsw_insert.restype = C.c_int32
         l.orc_hnsw_insert.argtypes = [C.c_void_p, f32p, C.c_uint64, u64p]
+        l.orc_hnsw_insert_batch.restype = C.c_int32
+        l.orc_hnsw_insert_batch.argtypes = [C.c_void_p, f32p, C.c_uint64, u64p, C.c_uint32, C.c_int32]
+        l.orc_hnsw_node_level.restype = C.c_int64
+        l.orc_hnsw_node_level.argtypes = [C.c_void_p, C.c_uint64]
         l.orc_hnsw_len.restype = C.c_uint64
         l.orc_hnsw_len.argtypes = [C.c_void_p]
         l.orc_hnsw_entry_point.restype = C.c_int64
@@ -302,6 +306,17 @@ class Hnsw:
         if rc != 0:
             raise RuntimeError(f"orc_hnsw_insert status {rc}")
         return out.value
+
+    def insert_batch(self, vectors, levels, batch=1, threads=1):
+        v = _f32(vectors)
+        lv = np.ascontiguousarray(levels, np.uint64)
+        rc = lib().orc_hnsw_insert_batch(self._h, _p(v, f32p), v.shape[0], _p(lv, u64p), batch, threads)
+        if rc != 0:
+            raise RuntimeError(f"orc_hnsw_insert_batch status {rc}")
+
+    def node_level(self, id):
+        lv = lib().orc_hnsw_node_level(self._h, id)
+        return None if lv < 0 else int(lv)
 
     def __len__(self):
         return int(lib().orc_hnsw_len(self._h))
