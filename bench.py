@@ -6,7 +6,14 @@ index (islands_b200 C ABI).  See DESIGN.md "measurement" for every definition us
 
   python bench.py --gpus 1 --steps K --warmup W            # this repo (CUDA, sm_100a)
   python bench.py --impl reference ...                     # the reference's CPU algorithm (oracle port)
-  torchrun --nproc-per-node N bench.py --gpus N ...        # index sharded by node range + NCCL merge
+  torchrun --nproc-per-node N bench.py --gpus N ...        # one island (n x d shard) per GPU, weak scaling
+
+N > 1 (DESIGN.md "multi-GPU"): every rank owns one island of `n` vectors (its own seed) — the total
+index is N*n vectors — and `value` counts queries routed to their island (the reference's
+`index_names` filter, src/indexer/service.rs:768-771): independent units, no data-path collective,
+weak scaling.  The same run also measures the all-islands search (every query on every shard, one
+NCCL all-gather of the (dist,id) lists + per-query merge, service.rs:777-801) and reports it under
+"all_islands".
 """
 import argparse
 import json
@@ -24,6 +31,7 @@ sys.path.insert(0, ROOT)
 K_TOP = 10
 RECALL_TARGET = 0.95
 EF_LADDER = [16, 24, 32, 48, 64, 96, 128, 192, 256, 384, 512, 768, 1024, 1536, 2048]
+EF_REFINE_STEP = 8  # after the coarse ladder, the last interval is refined in steps of 8
 
 
 def parse_args():
@@ -39,6 +47,8 @@ def parse_args():
     ap.add_argument("--ef", type=int, default=0, help="0 = smallest ef of the ladder with recall@10 >= 0.95")
     ap.add_argument("--build-batch", type=int, default=4096)
     ap.add_argument("--no-uniform", action="store_true", help="skip the secondary uniform-data measurement")
+    ap.add_argument("--no-adc", action="store_true", help="skip the secondary PQ ADC traversal + exact rerank measurement")
+    ap.add_argument("--pq-m", type=int, default=32, help="subquantizers of the ADC secondary (ksub = 256)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -46,21 +56,23 @@ def parse_args():
 # ---------------------------------------------------------------------------------------------
 # synthetic data (generated on the GPU; seeds fixed)
 # ---------------------------------------------------------------------------------------------
-def make_data(torch, dataset, n, nq, d, dev):
+def make_data(torch, dataset, n, nq, d, dev, seed=42, qseed=43):
     """latent32: x = z A + 0.05 eps, z ~ N(0, I_32), A ~ N(0, 1/32)^{32 x d}: d-dimensional vectors
     with the low intrinsic dimension typical of learned embeddings (graph ANN reaches 0.95 recall).
     uniform: i.i.d. U[-1,1), the distribution of the reference's criterion benches
     (benches/hnsw_benchmarks.rs:9-14) — a worst case for ANY graph index at d=768."""
     g = torch.Generator(device=dev)
-    g.manual_seed(42)
+    g.manual_seed(42)  # the latent basis is shared by every island and every query
     if dataset == "latent32":
         a = torch.randn((32, d), generator=g, device=dev) / 32 ** 0.5
+        g.manual_seed(seed + 7)
         x = torch.randn((n, 32), generator=g, device=dev) @ a + 0.05 * torch.randn((n, d), generator=g, device=dev)
-        g.manual_seed(43)
+        g.manual_seed(qseed)
         q = torch.randn((nq, 32), generator=g, device=dev) @ a + 0.05 * torch.randn((nq, d), generator=g, device=dev)
     else:
+        g.manual_seed(seed)
         x = torch.rand((n, d), generator=g, device=dev) * 2 - 1
-        g.manual_seed(43)
+        g.manual_seed(qseed)
         q = torch.rand((nq, d), generator=g, device=dev) * 2 - 1
     return x.contiguous(), q.contiguous()
 
@@ -148,6 +160,40 @@ def cpu_port_qps(orc, cfg, xh, off, nbrs, entry, qh, ef, threads, seconds):
     return m / dt, m, ids
 
 
+def ground_truth_scores(torch, x, q, k, chunk=1024):
+    """Like ground_truth, also returning the cosine similarities (for the cross-island merge)."""
+    xn = torch.nn.functional.normalize(x, dim=1)
+    qn = torch.nn.functional.normalize(q, dim=1)
+    vs, is_ = [], []
+    for s in range(0, q.shape[0], chunk):
+        t = (qn[s:s + chunk] @ xn.T).topk(k, dim=1)
+        vs.append(t.values)
+        is_.append(t.indices)
+    return torch.cat(vs), torch.cat(is_)
+
+
+def calibrate_ef(recall_for, target, fixed=0):
+    """Smallest ef with recall >= target: coarse ladder, then the last interval in steps of 8."""
+    curve = {}
+    if fixed > 0:
+        curve[fixed] = recall_for(fixed)
+        return fixed, curve
+    ef, prev = EF_LADDER[-1], 0
+    for e in EF_LADDER:
+        curve[e] = recall_for(e)
+        if curve[e] >= target:
+            ef = e
+            break
+        prev = e
+    if curve[ef] >= target and ef - prev > EF_REFINE_STEP:
+        for e in range(prev + EF_REFINE_STEP, ef, EF_REFINE_STEP):
+            curve[e] = recall_for(e)
+            if curve[e] >= target:
+                ef = e
+                break
+    return ef, dict(sorted(curve.items()))
+
+
 def main():
     a = parse_args()
     import torch
@@ -167,66 +213,56 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    from islands_b200 import LeannConfig, LeannIndex, _ffi
-    from islands_b200.shard import ShardedLeannIndex, shard_range
+    from islands_b200 import LeannConfig, LeannIndex, PQConfig, ProductQuantizer, _ffi
+    from islands_b200.shard import ShardedLeannIndex
 
     lib = _ffi.load()
     cfg = LeannConfig()  # paper_default: m=30, m0=60, efC=128, cosine, hub-preserving pruning 2%
     n, d, nq = a.n, a.d, a.nq
-    parts = world if use_dist else 1
-    lo, hi = shard_range(n, rank if use_dist else 0, parts)
+    island = rank if use_dist else 0  # one island of n vectors per GPU (weak scaling)
 
-    x, q = make_data(torch, a.dataset, n, nq, d, dev)
+    x, q = make_data(torch, a.dataset, n, nq, d, dev, seed=42 + 1000 * island, qseed=43 + 1000 * island)
     n_gt = min(nq, 1000)
     gt = ground_truth(torch, x, q[:n_gt], K_TOP)
-    shard = x[lo:hi].contiguous()
-    del x
-    torch.cuda.empty_cache()
 
     t0 = time.perf_counter()
     index = LeannIndex(cfg)
-    index.build_dev(shard.data_ptr(), hi - lo, d, seed=7, batch=a.build_batch)
+    index.build_dev(x.data_ptr(), n, d, seed=7, batch=a.build_batch)
     build_s = time.perf_counter() - t0
 
     ids = torch.empty((nq, K_TOP), dtype=torch.int64, device=dev)
     dst = torch.empty((nq, K_TOP), dtype=torch.float32, device=dev)
     cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
     stats = torch.zeros((nq, 5), dtype=torch.int64, device=dev)
-    m_ids = torch.empty((nq, K_TOP), dtype=torch.int64, device=dev)
-    m_dst = torch.empty((nq, K_TOP), dtype=torch.float32, device=dev)
-    sharded = ShardedLeannIndex(index, lo, n)
 
-    def step_device(nqq, ef, with_stats=False):
-        """One pass of the hot path with inputs resident in HBM: per-shard search, then (N > 1) one
-        all-gather of the (dist, id) lists and the per-query merge.  Returns the final ids tensor."""
-        out_ids, _ = sharded.search_batch_dev(q[:nqq], K_TOP, ef, ids, dst, cnt, m_ids, m_dst, stats if with_stats else None)
-        return out_ids
+    def step_device(ef, with_stats=False, queries=None):
+        """One pass of the hot path with inputs resident in HBM: this island's batch through the
+        batched best-first search (isl_index_search_dev).  Returns the ids tensor."""
+        qq = q if queries is None else queries
+        index.search_batch_dev(qq.data_ptr(), nq, d, K_TOP, ef, ids.data_ptr(), dst.data_ptr(), cnt.data_ptr(),
+                               stats.data_ptr() if with_stats else None)
+        return ids
 
-    # ---- ef: smallest rung with recall@10 >= 0.95 (setup, untimed) ---------------------------------
-    def recall_for(ef):
-        out = step_device(nq, ef)  # full batch keeps the gather shapes fixed
-        return recall_at_k(torch, out[:n_gt], gt)
+    def all_max(v):
+        if not use_dist:
+            return v
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    curve = {}
-    if a.ef > 0:
-        ef = a.ef
-        curve[ef] = recall_for(ef)
-    else:
-        ef = EF_LADDER[-1]
-        for e in EF_LADDER:
-            curve[e] = recall_for(e)
-            if curve[e] >= RECALL_TARGET:
-                ef = e
-                break
-    recall = curve[ef]
+    # ---- ef: smallest value with recall@10 >= 0.95 on every island (setup, untimed) -----------------
+    ef, curve = calibrate_ef(lambda e: recall_at_k(torch, step_device(e)[:n_gt], gt), RECALL_TARGET, a.ef)
+    ef = int(all_max(ef))
+    recall = curve[ef] if ef in curve else recall_at_k(torch, step_device(ef)[:n_gt], gt)
 
+    metric_name = "QPS at recall@10>=0.95 (1M x 768, M=30, top-10)"
     # =========================================================================================
     if a.impl == "reference":
         from oracle import pyoracle as orc
 
         threads = os.cpu_count() or 1
         g = index.graph
-        xh = shard.cpu().numpy()
+        xh = x.cpu().numpy()
         qh = q.cpu().numpy()
         off, nbrs, entry = g.node_offsets, g.neighbors, g.entry_point
         # size one step: ~ (cpu budget / steps) seconds of all-core work
@@ -243,9 +279,9 @@ def main():
         rec = recall_at_k(torch, torch.from_numpy(r_ids[:m].astype(np.int64)).to(dev), gt[:m])
         sample = f"{per_step} of {nq} queries per step, ef={ef}, graph built by the GPU library in setup (untimed)"
         print(json.dumps({
-            "impl": "reference", "metric": "QPS at recall@10>=0.95 (1M x 768, M=30, top-10)", "value": qps, "unit": "queries/s",
+            "impl": "reference", "metric": metric_name, "value": qps, "unit": "queries/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{n} x {d} f32 {a.dataset}, LEANN graph m=30 m0=60 efC=128, nq={nq} (sampled {per_step}), top-10, exact traversal, cosine",
                        "ef": ef, "recall_at_10": rec, "kind": "oracle port of src/core/leann.rs:868-988 (Rust reference cannot be built here)"},
             "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
@@ -255,7 +291,7 @@ def main():
         return
 
     # ---- counters for the roofline (one untimed pass with per-query stats) ---------------------------
-    step_device(nq, ef, with_stats=True)
+    step_device(ef, with_stats=True)
     torch.cuda.synchronize()
     alg_bytes, per_query = algorithmic_bytes(stats.cpu().numpy(), d, nq, K_TOP)
 
@@ -265,96 +301,131 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        barrier()
+        return all_max(time.perf_counter() - t0)
+
     # ---- value: K timed steps, inputs resident in HBM ------------------------------------------------
     for _ in range(a.warmup):
-        step_device(nq, ef)
+        step_device(ef)
     kernel_ms = []
     barrier()
     lib.isl_kernel_launch_count_reset()
     with ClockSampler(local) as clocks:
         t0 = time.perf_counter()
         for _ in range(a.steps):
-            step_device(nq, ef)
+            step_device(ef)
             kernel_ms.append(index.last_search_timing()[0])
         barrier()
         dt = time.perf_counter() - t0
     launches = int(lib.isl_kernel_launch_count())
-    if use_dist:
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    qps = nq * a.steps / dt
+    dt = all_max(dt)
+    qps = world * nq * a.steps / dt if use_dist else nq * a.steps / dt
 
     # ---- e2e: host buffers in, host results out, copies inside the timed region ------------------------
     qh = torch.empty((nq, d), dtype=torch.float32, pin_memory=True)
     qh.copy_(q)
-    out_ids_h = torch.empty((nq, K_TOP), dtype=torch.int64, pin_memory=True)
-    out_dst_h = torch.empty((nq, K_TOP), dtype=torch.float32, pin_memory=True)
     qn = qh.numpy()
-
-    def step_e2e():
-        if not use_dist:
-            return index.search_batch(qn, K_TOP, ef)  # isl_index_search: H2D queries, kernel, D2H results
-        q.copy_(qh, non_blocking=True)
-        out = step_device(nq, ef)
-        out_ids_h.copy_(out, non_blocking=True)
-        out_dst_h.copy_(m_dst, non_blocking=True)
-        torch.cuda.synchronize()
-        return None
-
-    for _ in range(max(1, a.warmup)):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        step_e2e()
-    barrier()
-    dt_e2e = time.perf_counter() - t0
-    if use_dist:
-        t = torch.tensor([dt_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt_e2e = float(t.item())
-    e2e_qps = nq * a.steps / dt_e2e
+    dt_e2e = timed(lambda: index.search_batch(qn, K_TOP, ef), a.steps, max(1, a.warmup))  # isl_index_search
+    e2e_qps = (world if use_dist else 1) * nq * a.steps / dt_e2e
 
     peak, peak_src = measured_peak()
     k_ms = float(np.mean(kernel_ms))
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
 
+    parts = world if use_dist else 1
     line = {
-        "metric": "QPS at recall@10>=0.95 (1M x 768, M=30, top-10)", "value": qps, "unit": "queries/s", "n_gpus": world if use_dist else 1,
+        "metric": metric_name, "value": qps, "unit": "queries/s", "n_gpus": parts,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": f"{n} x {d} f32 {a.dataset}, LEANN graph m=30 m0=60 efC=128 hub 2% (built on GPU in setup, {build_s:.1f}s), "
-                        f"batched {nq} queries, top-10, exact traversal, cosine",
+            "workload": f"{n} x {d} f32 {a.dataset} per GPU, LEANN graph m=30 m0=60 efC=128 hub 2% (built on GPU in setup, {build_s:.1f}s), "
+                        f"batched {nq} queries per GPU per step, top-10, exact traversal (leann.rs:868-988), cosine",
             "ef": ef, "recall_at_10": recall, "recall_curve": {str(k): round(v, 4) for k, v in curve.items()},
-            "shards": parts, "shard_nodes": hi - lo, "merge": "NCCL all-gather + per-query (dist,id) merge" if use_dist else "none",
-            "l2": "inputs larger than L2 (vector table %.2f GB vs 126 MB)" % ((hi - lo) * d * 4 / 1e9),
+            "islands": parts, "island_nodes": n, "total_nodes": parts * n,
+            "routing": "queries routed to their island (index_names filter, service.rs:768-771); no data-path collective" if use_dist else "single island",
+            "l2": "inputs larger than L2 (vector table %.2f GB vs 126 MB)" % (n * d * 4 / 1e9),
             "per_query": per_query,
         },
-        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4, "d2h_bytes_per_step": nq * K_TOP * 12 + (0 if use_dist else nq * 4)},
+        "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": parts * nq * d * 4,
+                "d2h_bytes_per_step": parts * (nq * K_TOP * 12 + nq * 4)},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": {"bound": "hbm", "kernel": "leann_search_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "peak_source": peak_src},
     }
 
-    # ---- cpu_baseline (rank 0, single GPU run only) -------------------------------------------------
+    # ---- N > 1: the all-islands search (every query on every shard + all-gather + merge) ---------------
+    if use_dist:
+        _, q_all = make_data(torch, a.dataset, 1, nq, d, dev, seed=1, qseed=43)  # the same batch on every rank
+        sc, li = ground_truth_scores(torch, x, q_all[:n_gt], K_TOP)
+        g_sc = torch.empty((world * n_gt, K_TOP), dtype=sc.dtype, device=dev)
+        g_id = torch.empty((world * n_gt, K_TOP), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(g_sc, sc.contiguous())
+        dist.all_gather_into_tensor(g_id, (li + rank * n).contiguous())
+        g_sc = g_sc.view(world, n_gt, K_TOP).permute(1, 0, 2).reshape(n_gt, -1)
+        g_id = g_id.view(world, n_gt, K_TOP).permute(1, 0, 2).reshape(n_gt, -1)
+        gt_all = g_id.gather(1, g_sc.topk(K_TOP, dim=1).indices)
+        sharded = ShardedLeannIndex(index, rank * n, world * n)
+        m_ids = torch.empty((nq, K_TOP), dtype=torch.int64, device=dev)
+        m_dst = torch.empty((nq, K_TOP), dtype=torch.float32, device=dev)
+
+        def step_all(e):
+            return sharded.search_batch_dev(q_all, K_TOP, e, ids, dst, cnt, m_ids, m_dst)[0]
+
+        ef_all, curve_all = calibrate_ef(lambda e: recall_at_k(torch, step_all(e)[:n_gt], gt_all), RECALL_TARGET)
+        dt_all = timed(lambda: step_all(ef_all), a.steps, a.warmup)
+        line["all_islands"] = {
+            "qps": nq * a.steps / dt_all, "ms_per_step": dt_all / a.steps * 1e3, "ef": ef_all,
+            "recall_at_10": curve_all[ef_all], "total_nodes": world * n,
+            "merge": "one NCCL all-gather of the per-shard (dist,id) lists + per-query (dist,id) merge kernel",
+            "note": "every query searches all islands (service.rs:777-801): queries are replicated, so QPS does not grow with N; the index does"}
+
+    # ---- cpu_baseline + secondary workloads (single GPU run only) ------------------------------------
     if not use_dist:
         from oracle import pyoracle as orc
 
         threads = os.cpu_count() or 1
         g = index.graph
-        xh = shard.cpu().numpy()
+        xh = x.cpu().numpy()
         cq, m, o_ids = cpu_port_qps(orc, cfg, xh, g.node_offsets, g.neighbors, g.entry_point, qn, ef, threads, a.cpu_seconds)
         same = bool(np.array_equal(o_ids.astype(np.int64), index.search_batch(qn[:m], K_TOP, ef)[0].astype(np.int64)))
         line["cpu_baseline"] = {"value": cq, "unit": "queries/s", "cores": threads, "kind": "port",
                                 "sample": f"first {m} of {nq} queries, same graph / ef, all host threads; ids equal to GPU: {same}"}
+
+        # secondary: BASELINE configs[1] names "PQ ADC traversal + exact rerank" — a mode the reference
+        # specifies (docs/leann-specification.md:223-269) but does not implement; measured beside the headline.
+        if not a.no_adc:
+            pq_m = a.pq_m
+            pq = ProductQuantizer(d, PQConfig(pq_m, 256, 8, 1))
+            pq.train(xh[:20000])
+            index.attach_pq(pq, pq.encode(xh))
+
+            def adc_recall(e):
+                r = index.search_adc_rerank_batch(qn, K_TOP, e)[0]
+                return recall_at_k(torch, torch.from_numpy(r[:n_gt].astype(np.int64)).to(dev), gt)
+
+            ef_adc, curve_adc = calibrate_ef(adc_recall, RECALL_TARGET)
+            _, _, _, st = index.search_adc_rerank_batch(qn, K_TOP, ef_adc, stats=True)
+            index.search_adc_rerank_batch(qn, K_TOP, ef_adc)
+            ms = index.last_search_timing()[0]
+            b = int(st.n_adc.sum()) * pq_m + int(st.n_edge.sum()) * 4 + int(st.n_hop.sum()) * 16 + int(st.n_rerank.sum()) * 4 * d \
+                + nq * (4 * d + 12 * K_TOP + pq_m * 256 * 4)
+            line["adc_rerank"] = {"pq_m": pq_m, "ef": ef_adc, "recall_at_10": curve_adc[ef_adc], "kernel_qps": nq / ms * 1e3,
+                                  "kernel_ms": ms, "algorithmic_gbps": b / ms / 1e6, "frac": b / ms / 1e6 / peak,
+                                  "n_adc": float(st.n_adc.mean()), "n_rerank": float(st.n_rerank.mean()),
+                                  "note": "parity unpinned: no reference implementation of this mode exists (leann.rs:54-56)"}
         del xh
 
         # secondary: the reference benches' own distribution (uniform), reported beside the headline
         if a.dataset != "uniform" and not a.no_uniform:
-            del index, shard
+            del index, x
             torch.cuda.empty_cache()
             xu, qu = make_data(torch, "uniform", n, nq, d, dev)
             gtu = ground_truth(torch, xu, qu[:n_gt], K_TOP)

@@ -6,6 +6,7 @@
 //   islands::DistanceMetric / calculate / batch_calculate   src/core/distance.rs:7-67
 //   islands::CoreError (+ kind)                             src/core/error.rs:9-62
 //   islands::LeannConfig / LeannIndex / CsrGraph            src/core/leann.rs:193-302, 322-461, 493-1067
+//   islands::HnswConfig / HnswGraph                       src/core/hnsw.rs:15-86, 151-531
 //   islands::PQConfig / ProductQuantizer                    src/core/pq.rs:13-65, 116-359
 //   islands::merge_results                                  src/core/search.rs:211-237
 // Link with -lislands_b200 (islands_b200/lib).  All compute runs on the GPU; nothing here has a
@@ -151,6 +152,61 @@ class LeannIndex {
   }
   LeannConfig cfg_;
   isl_index* h_ = nullptr;
+};
+
+// ---- hnsw.rs ------------------------------------------------------------------------------------
+struct HnswConfig : isl_hnsw_config {
+  HnswConfig() { check(isl_hnsw_config_default(this)); }  // hnsw.rs:37-48
+  void validate() const { check(isl_hnsw_config_validate(this)); }
+};
+
+class HnswGraph {  // hnsw.rs:151-531
+ public:
+  explicit HnswGraph(const HnswConfig& cfg = HnswConfig()) { check(isl_hnsw_new(&cfg, &h_)); }
+  ~HnswGraph() { isl_hnsw_free(h_); }
+  HnswGraph(const HnswGraph&) = delete;
+  HnswGraph& operator=(const HnswGraph&) = delete;
+  uint64_t len() const { return isl_hnsw_len(h_); }
+  bool is_empty() const { return len() == 0; }
+  uint32_t dimension() const { return isl_hnsw_dimension(h_); }
+  int64_t entry_point() const { return isl_hnsw_entry_point(h_); }
+  uint64_t max_level() const { return isl_hnsw_max_level(h_); }
+  // HnswGraph::insert (hnsw.rs:214-250) -> id; `level` (optional) replaces the thread_rng draw.
+  uint64_t insert(const std::vector<float>& v, const uint64_t* level = nullptr, uint64_t seed = 0) {
+    uint64_t id = 0;
+    check(isl_hnsw_insert_batch(h_, v.data(), 1, (uint32_t)v.size(), level, seed, 1, &id));
+    return id;
+  }
+  // `count` inserts, up to `batch` nodes per graph snapshot (GPU-parallel construction).
+  uint64_t insert_batch(const std::vector<float>& vectors, uint32_t dim, const std::vector<uint64_t>* levels = nullptr,
+                        uint64_t seed = 0, uint32_t batch = 1) {
+    uint64_t first = 0;
+    check(isl_hnsw_insert_batch(h_, vectors.data(), dim ? vectors.size() / dim : 0, dim,
+                                levels ? levels->data() : nullptr, seed, batch, &first));
+    return first;
+  }
+  // neighbors_at(layer) of get_node(id) (hnsw.rs:108-110, 201-203)
+  std::vector<uint64_t> neighbors_at(uint64_t id, uint64_t layer) const {
+    uint64_t cnt = 0;
+    check(isl_hnsw_get_neighbors(h_, id, layer, nullptr, 0, &cnt));
+    std::vector<uint64_t> out(cnt);
+    check(isl_hnsw_get_neighbors(h_, id, layer, out.data(), cnt, &cnt));
+    return out;
+  }
+  // HnswGraph::search (hnsw.rs:458-504)
+  SearchResults search(const std::vector<float>& query, uint32_t k, uint32_t ef) const {
+    std::vector<uint64_t> ids(k);
+    std::vector<float> dist(k);
+    uint32_t count = 0;
+    check(isl_hnsw_search(h_, query.data(), 1, (uint32_t)query.size(), k, ef, ids.data(), dist.data(), &count));
+    SearchResults out;
+    for (uint32_t i = 0; i < count; ++i) out.emplace_back(ids[i], dist[i]);
+    return out;
+  }
+  isl_hnsw* handle() const { return h_; }
+
+ private:
+  isl_hnsw* h_ = nullptr;
 };
 
 // ---- pq.rs ----------------------------------------------------------------------------------------

@@ -37,6 +37,8 @@ int main(int argc, char** argv) {
   }
   PQConfig pc;
   EXPECT(pc.bytes_per_vector() == 8);
+  HnswConfig hc;
+  EXPECT(hc.m == 16 && hc.m0 == 32 && hc.ef_construction == 200 && hc.max_layers == 16);  // hnsw.rs:533-545
   EXPECT(std::fabs(to_similarity(1.0f) - 0.5f) < 1e-7f);
   if (argc > 1 && std::strcmp(argv[1], "gpu") == 0) {
     EXPECT(std::fabs(calculate(DistanceMetric::Euclidean, {0.f, 0.f}, {3.f, 4.f}) - 5.0f) < 1e-6f);
@@ -56,6 +58,20 @@ int main(int argc, char** argv) {
     for (size_t i = 1; i < r.size(); ++i) EXPECT(r[i - 1].second <= r[i].second);
     CsrGraph g = idx.graph();
     EXPECT(g.num_nodes == n && g.node_offsets.back() == g.neighbors.size());
+    HnswGraph hg;  // hnsw.rs:571-640
+    EXPECT(hg.is_empty() && hg.entry_point() == ISL_NO_ENTRY);
+    EXPECT(hg.insert(q) == 0 && hg.len() == 1 && hg.dimension() == d);
+    std::vector<float> rest(v.begin() + d, v.end());
+    EXPECT(hg.insert_batch(rest, d, nullptr, 7, 16) == 1 && hg.len() == n);
+    auto hr = hg.search(q, 5, 50);
+    EXPECT(hr.size() == 5 && hr[0].first == 0 && hr[0].second < 0.01f);
+    EXPECT(!hg.neighbors_at(0, 0).empty());
+    try {
+      hg.insert(std::vector<float>(d + 1, 0.f));
+      EXPECT(false);
+    } catch (const CoreError& e) {
+      EXPECT(e.kind == ErrorKind::DimensionMismatch);
+    }
   } else {
     try {  // no device: loud failure, never a CPU fallback
       calculate(DistanceMetric::Euclidean, {0.f, 0.f}, {3.f, 4.f});
