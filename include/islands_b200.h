@@ -117,9 +117,24 @@ typedef struct isl_search_stats {
   uint64_t n_rerank;
 } isl_search_stats;
 
+/* Shape of the recompute encoder: BERT (the reference's CandleEmbedder loads a BERT-family model,
+ * src/core/embedding/candle_provider.rs:230-300).  head dimension is fixed at 64. */
+typedef struct isl_encoder_config {
+  uint32_t vocab_size;
+  uint32_t hidden_size;
+  uint32_t num_layers;
+  uint32_t num_heads;
+  uint32_t intermediate_size;
+  uint32_t max_position;
+  uint32_t type_vocab_size;
+  float layer_norm_eps;
+  int32_t normalize; /* EmbeddingConfig::normalize: L2-normalise the pooled vector */
+} isl_encoder_config;
+
 typedef struct isl_index isl_index; /* LeannIndex + CsrGraph + resident vectors (leann.rs:193-208, :493-500) */
 typedef struct isl_pq isl_pq;       /* ProductQuantizer (pq.rs:116-129) */
 typedef struct isl_hnsw isl_hnsw;   /* HnswGraph (hnsw.rs:151-164) */
+typedef struct isl_encoder isl_encoder; /* CandleEmbedder's model (candle_provider.rs) for on-demand recompute */
 
 /* ---- library ---------------------------------------------------------------------- */
 int isl_abi_version(void);
@@ -292,6 +307,36 @@ isl_status isl_hnsw_search_dev(const isl_hnsw* g, const float* d_queries, uint64
                                uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
                                float* d_out_dist, uint32_t* d_out_count);
 isl_status isl_hnsw_last_search_timing(const isl_hnsw* g, float* kernel_ms);
+
+/* ---- on-demand embedding recomputation (src/core/embedding/candle_provider.rs:353-507) ------- */
+/* BERT-base shape (110M parameters): vocab 30522, hidden 768, 12 layers, 12 heads, FFN 3072. */
+isl_status isl_encoder_config_default(isl_encoder_config* out);
+isl_status isl_encoder_new(const isl_encoder_config* cfg, isl_encoder** out);
+void isl_encoder_free(isl_encoder* enc);
+uint32_t isl_encoder_dimension(const isl_encoder* enc);          /* EmbeddingProvider::dimension */
+uint64_t isl_encoder_num_parameters(const isl_encoder* enc);
+/* Random-init weights of the configured shape: matrices and embeddings ~ N(0, stddev) from a
+ * counter-based generator keyed by `seed`, biases 0, LayerNorm weight 1 / bias 0. */
+isl_status isl_encoder_init_random(isl_encoder* enc, uint64_t seed, float stddev);
+/* Parameters by their Hugging Face BERT names ("embeddings.word_embeddings.weight",
+ * "encoder.layer.3.attention.self.query.weight", ...), f32 row-major [out][in]. */
+isl_status isl_encoder_set_parameter(isl_encoder* enc, const char* name, const float* data, uint64_t count);
+isl_status isl_encoder_get_parameter(const isl_encoder* enc, const char* name, float* out, uint64_t count);
+/* embed_texts_raw after tokenisation: token_ids [batch][seq_len] (padded with 0), lengths [batch] =
+ * number of attended tokens per row (attention_mask = 1 for the first lengths[b] positions);
+ * out [batch][hidden]: BERT forward (bf16 tensor-core GEMMs, f32 accumulate) -> masked mean pooling
+ * with clamp(sum_mask, 1e-9) -> L2 normalisation with clamp(norm, 1e-12) when cfg.normalize. */
+isl_status isl_encoder_embed(isl_encoder* enc, const int32_t* token_ids, const int32_t* lengths,
+                             uint64_t batch, uint32_t seq_len, float* out);
+isl_status isl_encoder_embed_dev(isl_encoder* enc, const int32_t* d_token_ids, const int32_t* d_lengths,
+                                 uint64_t batch, uint32_t seq_len, float* d_out);
+/* CUDA-event duration of the last embed call and the FLOPs it performed (GEMMs + attention). */
+isl_status isl_encoder_last_timing(const isl_encoder* enc, float* ms, double* flops);
+/* The encoder's dense contraction on its own (tcgen05): out = act(A[m][k] * W[n][k]^T + bias)
+ * (+ residual), A / W / residual / out_bf16 are bf16 on the device; k and n multiples of 64. */
+isl_status isl_gemm_bf16_dev(const void* d_a_bf16, const void* d_w_bf16, uint32_t m, uint32_t n, uint32_t k,
+                             const float* d_bias, const void* d_residual_bf16, int32_t gelu,
+                             void* d_out_bf16, float* d_out_f32);
 
 /* ---- island / shard merge (search.rs:211-237, indexer/service.rs:775-801) ---------- */
 /* Per query, merge `parts` lists of k (dist,id) pairs laid out [parts][nq][k] into the k best

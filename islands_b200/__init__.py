@@ -1,7 +1,7 @@
 """islands_b200 — B200-native (sm_100a) LEANN / HNSW search hot path behind the reference's
 `src/core` API.  Compute lives in lib/libislands_b200.so (C ABI: include/islands_b200.h);
 this package is the host-side mirror of the reference interface.  No CPU fallback."""
-from .core import (CoreError, CsrGraph, CudaError, DimensionMismatch, DistanceMetric, EmptyCollection,
+from .core import (Encoder, EncoderConfig, gemm_bf16_dev, CoreError, CsrGraph, CudaError, DimensionMismatch, DistanceMetric, EmptyCollection,
                    HnswConfig, HnswGraph, HnswNode, IndexNotBuilt, InMemoryEmbeddingProvider, InvalidArgument, InvalidConfig,
                    LeannConfig, LeannIndex, NodeNotFound, PQConfig, PQError, ProductQuantizer,
                    PruningStrategy, SerializationError, merge_topk, merge_topk_dev, normalize_vector, normalized,

@@ -65,6 +65,22 @@ class PQConfigStruct(C.Structure):
     ]
 
 
+class EncoderConfigStruct(C.Structure):
+    """isl_encoder_config: BERT shape of the recompute encoder."""
+
+    _fields_ = [
+        ("vocab_size", C.c_uint32),
+        ("hidden_size", C.c_uint32),
+        ("num_layers", C.c_uint32),
+        ("num_heads", C.c_uint32),
+        ("intermediate_size", C.c_uint32),
+        ("max_position", C.c_uint32),
+        ("type_vocab_size", C.c_uint32),
+        ("layer_norm_eps", C.c_float),
+        ("normalize", C.c_int32),
+    ]
+
+
 class SearchStatsStruct(C.Structure):
     _fields_ = [
         ("n_hop", C.c_uint64),
@@ -79,6 +95,8 @@ _LCP = C.POINTER(LeannConfigStruct)
 _HCP = C.POINTER(HnswConfigStruct)
 _PCP = C.POINTER(PQConfigStruct)
 _SSP = C.POINTER(SearchStatsStruct)
+_ECP = C.POINTER(EncoderConfigStruct)
+i32p = C.POINTER(C.c_int32)
 _VP = C.c_void_p
 _VPP = C.POINTER(C.c_void_p)
 
@@ -151,6 +169,18 @@ SIGNATURES = {
     "isl_hnsw_search": (C.c_int, [_VP, f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u64p, f32p, u32p]),
     "isl_hnsw_search_dev": (C.c_int, [_VP, _VP, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _VP, _VP, _VP]),
     "isl_hnsw_last_search_timing": (C.c_int, [_VP, f32p]),
+    "isl_encoder_config_default": (C.c_int, [_ECP]),
+    "isl_encoder_new": (C.c_int, [_ECP, _VPP]),
+    "isl_encoder_free": (None, [_VP]),
+    "isl_encoder_dimension": (C.c_uint32, [_VP]),
+    "isl_encoder_num_parameters": (C.c_uint64, [_VP]),
+    "isl_encoder_init_random": (C.c_int, [_VP, C.c_uint64, C.c_float]),
+    "isl_encoder_set_parameter": (C.c_int, [_VP, C.c_char_p, f32p, C.c_uint64]),
+    "isl_encoder_get_parameter": (C.c_int, [_VP, C.c_char_p, f32p, C.c_uint64]),
+    "isl_encoder_embed": (C.c_int, [_VP, i32p, i32p, C.c_uint64, C.c_uint32, f32p]),
+    "isl_encoder_embed_dev": (C.c_int, [_VP, _VP, _VP, C.c_uint64, C.c_uint32, _VP]),
+    "isl_encoder_last_timing": (C.c_int, [_VP, f32p, C.POINTER(C.c_double)]),
+    "isl_gemm_bf16_dev": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, C.c_uint32, _VP, _VP, C.c_int32, _VP, _VP]),
     "isl_merge_topk": (C.c_int, [u64p, f32p, C.c_uint32, C.c_uint64, C.c_uint32, u64p, f32p, u32p]),
     "isl_merge_topk_dev": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint64, C.c_uint32, _VP, _VP, _VP]),
 }

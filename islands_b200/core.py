@@ -17,7 +17,7 @@ import math
 import numpy as np
 
 from . import _ffi
-from ._ffi import (HnswConfigStruct, LeannConfigStruct, PQConfigStruct, SearchStatsStruct,
+from ._ffi import (EncoderConfigStruct, HnswConfigStruct, LeannConfigStruct, PQConfigStruct, SearchStatsStruct,
                    f32p, u16p, u32p, u64p)
 
 
@@ -712,6 +712,123 @@ class ProductQuantizer:
         _check(_ffi.load().isl_pq_asymmetric_distance(self._h, _ptr(q, f32p), q.size, _ptr(c2, u16p), c2.shape[0],
                                                       _ptr(out, f32p)))
         return float(out[0]) if single else out
+
+
+# ---- embedding/candle_provider.rs -----------------------------------------------------------------
+class EncoderConfig:
+    """Shape of the recompute encoder (BERT; default = BERT-base, 110M parameters)."""
+
+    _fields = [f[0] for f in EncoderConfigStruct._fields_]
+
+    def __init__(self, **kw):
+        s = EncoderConfigStruct()
+        _check(_ffi.load().isl_encoder_config_default(C.byref(s)))
+        self._s = s
+        for k, v in kw.items():
+            if k not in EncoderConfig._fields:
+                raise AttributeError(k)
+            setattr(self._s, k, v)
+
+    def __getattr__(self, name):
+        if name in EncoderConfig._fields:
+            return getattr(self._s, name)
+        raise AttributeError(name)
+
+
+class Encoder:
+    """The model behind CandleEmbedder::embed_texts_raw (candle_provider.rs:353-507) for token ids:
+    BERT forward on the tcgen05 tensor cores (bf16, f32 accumulate), masked mean pooling, L2 norm."""
+
+    def __init__(self, config=None):
+        self.config = config or EncoderConfig()
+        h = C.c_void_p()
+        _check(_ffi.load().isl_encoder_new(C.byref(self.config._s), C.byref(h)))
+        self._h = h
+
+    def free(self):
+        if getattr(self, "_h", None) is not None:
+            _ffi.load().isl_encoder_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def dimension(self):
+        return int(_ffi.load().isl_encoder_dimension(self._h))
+
+    def num_parameters(self):
+        return int(_ffi.load().isl_encoder_num_parameters(self._h))
+
+    def init_random(self, seed=46, stddev=0.02):
+        _check(_ffi.load().isl_encoder_init_random(self._h, seed, stddev))
+        return self
+
+    def parameter_shapes(self):
+        c = self.config
+        H, I = c.hidden_size, c.intermediate_size
+        shapes = {"embeddings.word_embeddings.weight": (c.vocab_size, H),
+                  "embeddings.position_embeddings.weight": (c.max_position, H),
+                  "embeddings.token_type_embeddings.weight": (c.type_vocab_size, H),
+                  "embeddings.LayerNorm.weight": (H,), "embeddings.LayerNorm.bias": (H,)}
+        for l in range(c.num_layers):
+            p = f"encoder.layer.{l}."
+            for n in ("query", "key", "value"):
+                shapes[p + f"attention.self.{n}.weight"] = (H, H)
+                shapes[p + f"attention.self.{n}.bias"] = (H,)
+            shapes[p + "attention.output.dense.weight"] = (H, H)
+            shapes[p + "attention.output.dense.bias"] = (H,)
+            shapes[p + "attention.output.LayerNorm.weight"] = (H,)
+            shapes[p + "attention.output.LayerNorm.bias"] = (H,)
+            shapes[p + "intermediate.dense.weight"] = (I, H)
+            shapes[p + "intermediate.dense.bias"] = (I,)
+            shapes[p + "output.dense.weight"] = (H, I)
+            shapes[p + "output.dense.bias"] = (H,)
+            shapes[p + "output.LayerNorm.weight"] = (H,)
+            shapes[p + "output.LayerNorm.bias"] = (H,)
+        return shapes
+
+    def get_parameter(self, name):
+        shape = self.parameter_shapes()[name]
+        out = np.empty(shape, np.float32)
+        _check(_ffi.load().isl_encoder_get_parameter(self._h, name.encode(), _ptr(out, f32p), out.size))
+        return out
+
+    def set_parameter(self, name, value):
+        v = _f32(value)
+        _check(_ffi.load().isl_encoder_set_parameter(self._h, name.encode(), _ptr(v, f32p), v.size))
+
+    def state_dict(self):
+        return {n: self.get_parameter(n) for n in self.parameter_shapes()}
+
+    def embed(self, token_ids, lengths):
+        """token_ids [B, S] int32 (0-padded), lengths [B] -> [B, hidden] f32."""
+        t = np.ascontiguousarray(token_ids, np.int32)
+        ln = np.ascontiguousarray(lengths, np.int32)
+        B, S = t.shape
+        out = np.empty((B, self.dimension()), np.float32)
+        _check(_ffi.load().isl_encoder_embed(self._h, t.ctypes.data_as(_ffi.i32p), ln.ctypes.data_as(_ffi.i32p), B, S,
+                                             _ptr(out, f32p)))
+        return out
+
+    def embed_dev(self, d_tokens_ptr, d_lengths_ptr, B, S, d_out_ptr):
+        _check(_ffi.load().isl_encoder_embed_dev(self._h, C.c_void_p(d_tokens_ptr), C.c_void_p(d_lengths_ptr), B, S,
+                                                 C.c_void_p(d_out_ptr)))
+
+    def last_timing(self):
+        ms = C.c_float()
+        fl = C.c_double()
+        _check(_ffi.load().isl_encoder_last_timing(self._h, C.byref(ms), C.byref(fl)))
+        return ms.value, fl.value
+
+
+def gemm_bf16_dev(d_a, d_w, m, n, k, d_bias=None, d_residual=None, gelu=False, d_out_bf16=None, d_out_f32=None):
+    """isl_gemm_bf16_dev: raw device addresses; out = act(A W^T + bias) (+ residual)."""
+    vp = lambda p: C.c_void_p(p) if p else None
+    _check(_ffi.load().isl_gemm_bf16_dev(vp(d_a), vp(d_w), m, n, k, vp(d_bias), vp(d_residual), int(gelu), vp(d_out_bf16),
+                                         vp(d_out_f32)))
 
 
 # ---- search.rs ----------------------------------------------------------------------------------

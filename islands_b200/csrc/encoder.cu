@@ -1,0 +1,699 @@
+// encoder.cu — on-demand embedding recomputation: the reference's
+// CandleEmbedder::embed_texts_raw (src/core/embedding/candle_provider.rs:353-507) restated for
+// token ids already on hand: BERT forward -> masked mean pooling (:438-474) -> optional L2
+// normalisation (:477-494).  The BERT forward itself is third-party in the reference
+// (candle-transformers 0.9.1 `bert`), so the architecture is the published one: word + position +
+// token-type embeddings, LayerNorm, L x { fused QKV projection, masked softmax attention, output
+// projection + residual + LayerNorm, GELU feed-forward + residual + LayerNorm }.
+//
+// Every dense contraction runs on the tcgen05 tensor cores (gemm_tcgen05.cuh) in bf16 with f32
+// accumulation; bias / GELU / residual are fused into the GEMM epilogue.  Attention (about 1 % of
+// the FLOPs at the sequence lengths of code chunks), LayerNorm, the embedding gather and the
+// pooling are CUDA-core kernels bound by HBM.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "api_common.h"
+#include "gemm_tcgen05.cuh"
+
+struct isl_encoder {
+  isl_encoder_config cfg{};
+  int device = 0, sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::mutex mu;
+  // f32 masters (one pool) + bf16 copies of the GEMM weights
+  isl::DevBuf<float> params;
+  isl::DevBuf<__nv_bfloat16> wbf16;
+  size_t n_params = 0, n_gemm = 0;
+  // workspace for `cap_tokens` tokens
+  size_t cap_tokens = 0, cap_seqs = 0;
+  isl::DevBuf<__nv_bfloat16> x, y, qkv, ctx, ffn;
+  isl::DevBuf<int32_t> tokens, lengths;
+  isl::DevBuf<float> pooled;
+  float last_ms = 0.0f;
+  double last_flops = 0.0;
+  ~isl_encoder() {
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace isl {
+namespace {
+
+// ---- parameter layout ------------------------------------------------------------------------
+struct Layout {
+  uint32_t H, L, I, V, P, TV;
+  size_t word, pos, type, emb_ln_w, emb_ln_b, layers, per_layer, total;
+  // offsets inside one layer block
+  size_t qkv_w, qkv_b, ao_w, ao_b, ln1_w, ln1_b, f1_w, f1_b, f2_w, f2_b, ln2_w, ln2_b;
+  // bf16 pool: per layer [qkv_w | ao_w | f1_w | f2_w]
+  size_t g_qkv, g_ao, g_f1, g_f2, g_per_layer, g_total;
+};
+
+Layout make_layout(const isl_encoder_config& c) {
+  Layout l{};
+  l.H = c.hidden_size;
+  l.L = c.num_layers;
+  l.I = c.intermediate_size;
+  l.V = c.vocab_size;
+  l.P = c.max_position;
+  l.TV = c.type_vocab_size;
+  const size_t H = l.H, I = l.I;
+  size_t o = 0;
+  l.word = o; o += (size_t)l.V * H;
+  l.pos = o; o += (size_t)l.P * H;
+  l.type = o; o += (size_t)l.TV * H;
+  l.emb_ln_w = o; o += H;
+  l.emb_ln_b = o; o += H;
+  l.layers = o;
+  size_t p = 0;
+  l.qkv_w = p; p += 3 * H * H;
+  l.qkv_b = p; p += 3 * H;
+  l.ao_w = p; p += H * H;
+  l.ao_b = p; p += H;
+  l.ln1_w = p; p += H;
+  l.ln1_b = p; p += H;
+  l.f1_w = p; p += I * H;
+  l.f1_b = p; p += I;
+  l.f2_w = p; p += H * I;
+  l.f2_b = p; p += H;
+  l.ln2_w = p; p += H;
+  l.ln2_b = p; p += H;
+  l.per_layer = p;
+  l.total = o + (size_t)l.L * p;
+  size_t g = 0;
+  l.g_qkv = g; g += 3 * H * H;
+  l.g_ao = g; g += H * H;
+  l.g_f1 = g; g += I * H;
+  l.g_f2 = g; g += H * I;
+  l.g_per_layer = g;
+  l.g_total = (size_t)l.L * g;
+  return l;
+}
+
+// Resolves a Hugging Face BERT parameter name to (offset, count) in the f32 pool; q/k/v live
+// inside the fused [3H][H] projection.
+bool resolve(const Layout& l, const std::string& name, size_t* off, size_t* count) {
+  const size_t H = l.H, I = l.I;
+  auto is = [&](const char* s) { return name == s; };
+  if (is("embeddings.word_embeddings.weight")) { *off = l.word; *count = (size_t)l.V * H; return true; }
+  if (is("embeddings.position_embeddings.weight")) { *off = l.pos; *count = (size_t)l.P * H; return true; }
+  if (is("embeddings.token_type_embeddings.weight")) { *off = l.type; *count = (size_t)l.TV * H; return true; }
+  if (is("embeddings.LayerNorm.weight")) { *off = l.emb_ln_w; *count = H; return true; }
+  if (is("embeddings.LayerNorm.bias")) { *off = l.emb_ln_b; *count = H; return true; }
+  const std::string pre = "encoder.layer.";
+  if (name.compare(0, pre.size(), pre) != 0) return false;
+  size_t dot = name.find('.', pre.size());
+  if (dot == std::string::npos) return false;
+  const int layer = std::atoi(name.substr(pre.size(), dot - pre.size()).c_str());
+  if (layer < 0 || (uint32_t)layer >= l.L) return false;
+  const std::string rest = name.substr(dot + 1);
+  const size_t base = l.layers + (size_t)layer * l.per_layer;
+  struct E { const char* n; size_t off, cnt; };
+  const E table[] = {
+      {"attention.self.query.weight", l.qkv_w, H * H},
+      {"attention.self.key.weight", l.qkv_w + H * H, H * H},
+      {"attention.self.value.weight", l.qkv_w + 2 * H * H, H * H},
+      {"attention.self.query.bias", l.qkv_b, H},
+      {"attention.self.key.bias", l.qkv_b + H, H},
+      {"attention.self.value.bias", l.qkv_b + 2 * H, H},
+      {"attention.output.dense.weight", l.ao_w, H * H},
+      {"attention.output.dense.bias", l.ao_b, H},
+      {"attention.output.LayerNorm.weight", l.ln1_w, H},
+      {"attention.output.LayerNorm.bias", l.ln1_b, H},
+      {"intermediate.dense.weight", l.f1_w, I * H},
+      {"intermediate.dense.bias", l.f1_b, I},
+      {"output.dense.weight", l.f2_w, H * I},
+      {"output.dense.bias", l.f2_b, H},
+      {"output.LayerNorm.weight", l.ln2_w, H},
+      {"output.LayerNorm.bias", l.ln2_b, H},
+  };
+  for (const E& e : table)
+    if (rest == e.n) {
+      *off = base + e.off;
+      *count = e.cnt;
+      return true;
+    }
+  return false;
+}
+
+// ---- small kernels ---------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+// N(0, std) from a counter-based hash (Box-Muller); the test oracle reads the values back.
+__global__ void init_normal_kernel(float* p, size_t count, uint64_t seed, float stddev) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    const uint64_t r = mix64(seed ^ (i * 0xD1342543DE82EF95ull));
+    const float u1 = ((float)((r >> 40) + 1)) * (1.0f / 16777217.0f);
+    const float u2 = ((float)((r >> 8) & 0xFFFFFF)) * (1.0f / 16777216.0f);
+    p[i] = stddev * sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+  }
+}
+__global__ void fill_kernel(float* p, size_t count, float v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t count) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+constexpr int kMaxPerLane = 32;  // H <= 1024 for the row kernels (H / 32 values per lane)
+
+// One warp per token: word + position + token-type(0) embeddings, then LayerNorm -> bf16.
+__global__ void __launch_bounds__(128)
+embed_ln_kernel(const int32_t* __restrict__ tokens, const float* __restrict__ word, const float* __restrict__ pos,
+                const float* __restrict__ type0, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                uint32_t T, uint32_t S, uint32_t H, uint32_t V, float eps, __nv_bfloat16* __restrict__ out) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= T) return;
+  int32_t tok = tokens[w];
+  if (tok < 0 || (uint32_t)tok >= V) tok = 0;
+  const float* we = word + (size_t)tok * H;
+  const float* pe = pos + (size_t)(w % S) * H;
+  float v[kMaxPerLane];
+  float sum = 0.0f;
+  const uint32_t per = H / 32;
+  for (uint32_t i = 0; i < per; ++i) {
+    const uint32_t c = i * 32 + lane;
+    v[i] = we[c] + pe[c] + type0[c];
+    sum += v[i];
+  }
+  const float mean = warp_sum(sum) / (float)H;
+  float var = 0.0f;
+  for (uint32_t i = 0; i < per; ++i) {
+    const float d = v[i] - mean;
+    var += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(var) / (float)H + eps);
+  for (uint32_t i = 0; i < per; ++i) {
+    const uint32_t c = i * 32 + lane;
+    out[(size_t)w * H + c] = __float2bfloat16_rn((v[i] - mean) * rstd * ln_w[c] + ln_b[c]);
+  }
+}
+
+// One warp per row: LayerNorm of a bf16 row (the residual sum written by the GEMM epilogue).
+__global__ void __launch_bounds__(128)
+layernorm_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                 uint32_t T, uint32_t H, float eps, __nv_bfloat16* __restrict__ out) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= T) return;
+  const __nv_bfloat162* r = reinterpret_cast<const __nv_bfloat162*>(in + (size_t)w * H);
+  float2 v[kMaxPerLane / 2];
+  float sum = 0.0f;
+  const uint32_t per = H / 64;
+  for (uint32_t i = 0; i < per; ++i) {
+    v[i] = __bfloat1622float2(r[i * 32 + lane]);
+    sum += v[i].x + v[i].y;
+  }
+  const float mean = warp_sum(sum) / (float)H;
+  float var = 0.0f;
+  for (uint32_t i = 0; i < per; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean;
+    var += a * a + b * b;
+  }
+  const float rstd = rsqrtf(warp_sum(var) / (float)H + eps);
+  __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(out + (size_t)w * H);
+  for (uint32_t i = 0; i < per; ++i) {
+    const uint32_t c = (i * 32 + lane) * 2;
+    o[i * 32 + lane] = __floats2bfloat162_rn((v[i].x - mean) * rstd * ln_w[c] + ln_b[c],
+                                             (v[i].y - mean) * rstd * ln_w[c + 1] + ln_b[c + 1]);
+  }
+}
+
+// Masked softmax attention, head_dim = 64.  One CTA per (sequence, head); keys/values of the
+// sequence staged in shared memory as f32; one warp per query row.  Padded key positions
+// (j >= len) are excluded — the additive -inf mask of BERT — and padded query rows are zeroed
+// (nothing downstream reads them: they are masked as keys and skipped by the pooling).
+__global__ void __launch_bounds__(128)
+attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ lengths, uint32_t S, uint32_t H,
+                 __nv_bfloat16* __restrict__ ctx) {
+  extern __shared__ float att_smem[];
+  const uint32_t b = blockIdx.x, h = blockIdx.y;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  const uint32_t len = min((uint32_t)max(lengths[b], 0), S);
+  float* Ks = att_smem;                 // [S][65]
+  float* Vs = Ks + (size_t)S * 65;      // [S][64]
+  float* qs = Vs + (size_t)S * 64;      // [warps][64]
+  float* ps = qs + warps * 64;          // [warps][S]
+  const size_t row_stride = 3 * (size_t)H;
+  const __nv_bfloat16* base = qkv + (size_t)b * S * row_stride + h * 64;
+  for (uint32_t i = threadIdx.x; i < len * 32; i += blockDim.x) {
+    const uint32_t j = i >> 5, c = (i & 31) * 2;
+    const float2 k2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + j * row_stride + H + c));
+    const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + j * row_stride + 2 * H + c));
+    Ks[j * 65 + c] = k2.x;
+    Ks[j * 65 + c + 1] = k2.y;
+    Vs[j * 64 + c] = v2.x;
+    Vs[j * 64 + c + 1] = v2.y;
+  }
+  __syncthreads();
+  float* q = qs + warp * 64;
+  float* p = ps + (size_t)warp * S;
+  for (uint32_t i = warp; i < S; i += warps) {
+    __nv_bfloat16* out = ctx + ((size_t)b * S + i) * H + h * 64;
+    if (i >= len) {
+      *reinterpret_cast<__nv_bfloat162*>(out + lane * 2) = __floats2bfloat162_rn(0.0f, 0.0f);
+      continue;
+    }
+    const float2 q2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + i * row_stride + lane * 2));
+    __syncwarp();
+    q[lane * 2] = q2.x * 0.125f;  // 1 / sqrt(64)
+    q[lane * 2 + 1] = q2.y * 0.125f;
+    __syncwarp();
+    float mx = -INFINITY;
+    for (uint32_t j = lane; j < len; j += 32) {
+      float s = 0.0f;
+#pragma unroll 16
+      for (uint32_t d = 0; d < 64; ++d) s = fmaf(q[d], Ks[j * 65 + d], s);
+      p[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float den = 0.0f;
+    for (uint32_t j = lane; j < len; j += 32) {
+      const float e = __expf(p[j] - mx);
+      p[j] = e;
+      den += e;
+    }
+    den = warp_sum(den);
+    __syncwarp();
+    float o0 = 0.0f, o1 = 0.0f;
+    for (uint32_t j = 0; j < len; ++j) {
+      const float pj = p[j];
+      o0 = fmaf(pj, Vs[j * 64 + lane], o0);
+      o1 = fmaf(pj, Vs[j * 64 + 32 + lane], o1);
+    }
+    const float inv = 1.0f / den;
+    out[lane] = __float2bfloat16_rn(o0 * inv);
+    out[32 + lane] = __float2bfloat16_rn(o1 * inv);
+  }
+}
+
+// Masked mean pooling (candle_provider.rs:438-474) and optional L2 normalisation (:477-494).
+__global__ void __launch_bounds__(256)
+pool_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ lengths, uint32_t S, uint32_t H,
+            int normalize, float* __restrict__ out) {
+  __shared__ float red[8];
+  const uint32_t b = blockIdx.x;
+  const uint32_t len = min((uint32_t)max(lengths[b], 0), S);
+  const float denom = fmaxf((float)len, 1e-9f);  // clamp(1e-9, MAX)
+  float sq = 0.0f;
+  for (uint32_t c = threadIdx.x; c < H; c += blockDim.x) {
+    float s = 0.0f;
+    for (uint32_t i = 0; i < len; ++i) s += __bfloat162float(x[((size_t)b * S + i) * H + c]);
+    s /= denom;
+    out[(size_t)b * H + c] = s;
+    sq += s * s;
+  }
+  if (!normalize) return;
+  sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  float tot = 0.0f;
+  for (uint32_t i = 0; i < (blockDim.x >> 5); ++i) tot += red[i];
+  const float nrm = fmaxf(sqrtf(tot), 1e-12f);  // clamp(1e-12, MAX)
+  for (uint32_t c = threadIdx.x; c < H; c += blockDim.x) out[(size_t)b * H + c] /= nrm;
+}
+
+// ---- TMA descriptors + GEMM launch ----------------------------------------------------------
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+isl_status get_encode_fn(EncodeFn* fn) {
+  static EncodeFn cached = nullptr;
+  if (!cached) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    ISL_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) return fail(ISL_CUDA_ERROR, "cuTensorMapEncodeTiled is not available");
+    cached = reinterpret_cast<EncodeFn>(p);
+  }
+  *fn = cached;
+  return ISL_OK;
+}
+
+// [rows][K] bf16 row-major, box = box_rows x 64 columns, 128-byte swizzle.
+isl_status make_map(const __nv_bfloat16* ptr, uint64_t rows, uint64_t K, uint32_t box_rows, CUtensorMap* map) {
+  EncodeFn fn;
+  ISL_TRY(get_encode_fn(&fn));
+  const cuuint64_t dims[2] = {K, rows};
+  const cuuint64_t strides[1] = {K * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)gemm::BK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ISL_CUDA_ERROR, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return ISL_OK;
+}
+
+template <int BN>
+isl_status launch_gemm_bn(const CUtensorMap& ma, const CUtensorMap& mb, const gemm::Params& p, int sms, cudaStream_t st) {
+  auto kern = gemm::gemm_bf16_tcgen05_kernel<BN>;
+  const size_t smem = gemm::smem_bytes<BN>();
+  ISL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles = ((p.M + gemm::BM - 1) / gemm::BM) * (p.N / BN);
+  kern<<<std::min(tiles, sms), gemm::THREADS, smem, st>>>(ma, mb, p);
+  count_launch();
+  ISL_CUDA_TRY(cudaGetLastError());
+  return ISL_OK;
+}
+
+}  // namespace
+
+// out = act(A[M][K] * W[N][K]^T + bias) (+ residual); A, W bf16 on the device (16-byte aligned rows).
+isl_status launch_gemm_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, int M, int N, int K, const float* bias,
+                            const __nv_bfloat16* residual, int epilogue, __nv_bfloat16* out_bf16, float* out_f32,
+                            int sms, cudaStream_t st) {
+  if (M <= 0) return ISL_OK;
+  if (K % gemm::BK != 0 || N % 64 != 0)
+    return fail(ISL_INVALID_ARGUMENT, "gemm: K and N must be multiples of 64");
+  const int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
+  CUtensorMap ma, mb;
+  ISL_TRY(make_map(A, (uint64_t)M, (uint64_t)K, gemm::BM, &ma));
+  ISL_TRY(make_map(W, (uint64_t)N, (uint64_t)K, (uint32_t)bn, &mb));
+  gemm::Params p{M, N, K, bias, residual, out_bf16, out_f32, epilogue};
+  if (bn == 256) return launch_gemm_bn<256>(ma, mb, p, sms, st);
+  if (bn == 128) return launch_gemm_bn<128>(ma, mb, p, sms, st);
+  return launch_gemm_bn<64>(ma, mb, p, sms, st);
+}
+
+namespace {
+
+isl_status validate_cfg(const isl_encoder_config* c) {
+  if (!c) return fail(ISL_INVALID_ARGUMENT, "config is null");
+  if (c->hidden_size == 0 || c->hidden_size % 64 != 0 || c->hidden_size > 1024)
+    return fail(ISL_INVALID_CONFIG, "hidden_size must be a multiple of 64 in [64, 1024]");
+  if (c->num_heads == 0 || c->hidden_size != c->num_heads * 64)
+    return fail(ISL_INVALID_CONFIG, "head dimension must be 64 (hidden_size == 64 * num_heads)");
+  if (c->intermediate_size == 0 || c->intermediate_size % 64 != 0)
+    return fail(ISL_INVALID_CONFIG, "intermediate_size must be a multiple of 64");
+  if (c->num_layers == 0 || c->vocab_size == 0 || c->max_position == 0 || c->type_vocab_size == 0)
+    return fail(ISL_INVALID_CONFIG, "num_layers, vocab_size, max_position and type_vocab_size must be > 0");
+  return ISL_OK;
+}
+
+isl_status ensure_workspace(isl_encoder* e, size_t seqs, size_t S) {
+  const size_t T = seqs * S, H = e->cfg.hidden_size, I = e->cfg.intermediate_size;
+  if (T > e->cap_tokens) {
+    ISL_CUDA_TRY(e->x.alloc(T * H));
+    ISL_CUDA_TRY(e->y.alloc(T * H));
+    ISL_CUDA_TRY(e->qkv.alloc(T * 3 * H));
+    ISL_CUDA_TRY(e->ctx.alloc(T * H));
+    ISL_CUDA_TRY(e->ffn.alloc(T * I));
+    ISL_CUDA_TRY(e->tokens.alloc(T));
+    e->cap_tokens = T;
+  }
+  if (seqs > e->cap_seqs) {
+    ISL_CUDA_TRY(e->lengths.alloc(seqs));
+    ISL_CUDA_TRY(e->pooled.alloc(seqs * H));
+    e->cap_seqs = seqs;
+  }
+  return ISL_OK;
+}
+
+// Forward of `seqs` sequences of S tokens resident on the device; d_out [seqs][H] f32.
+isl_status forward_device(isl_encoder* e, const int32_t* d_tokens, const int32_t* d_lengths, size_t seqs, size_t S,
+                          float* d_out) {
+  const Layout l = make_layout(e->cfg);
+  const uint32_t H = l.H, I = l.I;
+  const uint32_t T = (uint32_t)(seqs * S);
+  cudaStream_t st = e->stream;
+  const float* P = e->params.p;
+  const float eps = e->cfg.layer_norm_eps;
+  const uint32_t row_blocks = (T + 3) / 4;
+  embed_ln_kernel<<<row_blocks, 128, 0, st>>>(d_tokens, P + l.word, P + l.pos, P + l.type, P + l.emb_ln_w, P + l.emb_ln_b,
+                                             T, (uint32_t)S, H, l.V, eps, e->x.p);
+  count_launch();
+  const size_t att_smem = ((size_t)S * 65 + (size_t)S * 64 + 4 * 64 + 4 * S) * sizeof(float);
+  ISL_CUDA_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+  for (uint32_t layer = 0; layer < l.L; ++layer) {
+    const float* lp = P + l.layers + (size_t)layer * l.per_layer;
+    const __nv_bfloat16* gw = e->wbf16.p + (size_t)layer * l.g_per_layer;
+    ISL_TRY(launch_gemm_bf16(e->x.p, gw + l.g_qkv, (int)T, (int)(3 * H), (int)H, lp + l.qkv_b, nullptr, gemm::EPI_NONE,
+                             e->qkv.p, nullptr, e->sms, st));
+    attention_kernel<<<dim3((uint32_t)seqs, e->cfg.num_heads), 128, att_smem, st>>>(e->qkv.p, d_lengths, (uint32_t)S, H,
+                                                                                   e->ctx.p);
+    count_launch();
+    ISL_TRY(launch_gemm_bf16(e->ctx.p, gw + l.g_ao, (int)T, (int)H, (int)H, lp + l.ao_b, e->x.p, gemm::EPI_NONE, e->y.p,
+                             nullptr, e->sms, st));
+    layernorm_kernel<<<row_blocks, 128, 0, st>>>(e->y.p, lp + l.ln1_w, lp + l.ln1_b, T, H, eps, e->x.p);
+    count_launch();
+    ISL_TRY(launch_gemm_bf16(e->x.p, gw + l.g_f1, (int)T, (int)I, (int)H, lp + l.f1_b, nullptr, gemm::EPI_GELU, e->ffn.p,
+                             nullptr, e->sms, st));
+    ISL_TRY(launch_gemm_bf16(e->ffn.p, gw + l.g_f2, (int)T, (int)H, (int)I, lp + l.f2_b, e->x.p, gemm::EPI_NONE, e->y.p,
+                             nullptr, e->sms, st));
+    layernorm_kernel<<<row_blocks, 128, 0, st>>>(e->y.p, lp + l.ln2_w, lp + l.ln2_b, T, H, eps, e->x.p);
+    count_launch();
+  }
+  pool_kernel<<<(uint32_t)seqs, 256, 0, st>>>(e->x.p, d_lengths, (uint32_t)S, H, e->cfg.normalize, d_out);
+  count_launch();
+  ISL_CUDA_TRY(cudaGetLastError());
+  return ISL_OK;
+}
+
+double forward_flops(const isl_encoder_config& c, double seqs, double S) {
+  const double H = c.hidden_size, I = c.intermediate_size, T = seqs * S;
+  const double gemm = 2.0 * T * (3 * H * H + H * H + 2 * H * I);
+  const double att = 4.0 * T * S * H;  // QK^T and PV over the padded length
+  return c.num_layers * (gemm + att);
+}
+
+isl_status embed_impl(isl_encoder* e, const int32_t* tokens, const int32_t* lengths, bool on_device, uint64_t B,
+                      uint32_t S, float* out) {
+  if (!e) return fail(ISL_INVALID_ARGUMENT, "encoder is null");
+  if (B == 0) return ISL_OK;  // candle_provider.rs:354-356
+  if (!tokens || !lengths || !out) return fail(ISL_INVALID_ARGUMENT, "null pointer");
+  if (S == 0 || S > e->cfg.max_position) return fail(ISL_INVALID_ARGUMENT, "sequence length must be in [1, max_position]");
+  if (S > 256) return fail(ISL_INVALID_ARGUMENT, "sequence length > 256 is not supported by the attention kernel");
+  if (e->n_params == 0) return fail(ISL_INVALID_ARGUMENT, "encoder weights are not initialised");
+  DeviceGuard g(e->device);
+  std::lock_guard<std::mutex> lock(e->mu);
+  const uint32_t H = e->cfg.hidden_size;
+  const uint64_t chunk = std::max<uint64_t>(1, (1u << 17) / S);  // <= 128k tokens per pass
+  ISL_TRY(ensure_workspace(e, std::min<uint64_t>(B, chunk), S));
+  e->last_flops = forward_flops(e->cfg, (double)B, (double)S);
+  ISL_CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+  for (uint64_t s = 0; s < B; s += chunk) {
+    const uint64_t nb = std::min<uint64_t>(chunk, B - s);
+    const int32_t* dt = tokens + s * S;
+    const int32_t* dl = lengths + s;
+    float* dout = out + s * H;
+    if (!on_device) {
+      ISL_CUDA_TRY(cudaMemcpyAsync(e->tokens.p, tokens + s * S, nb * S * 4, cudaMemcpyHostToDevice, e->stream));
+      ISL_CUDA_TRY(cudaMemcpyAsync(e->lengths.p, lengths + s, nb * 4, cudaMemcpyHostToDevice, e->stream));
+      dt = e->tokens.p;
+      dl = e->lengths.p;
+      dout = e->pooled.p;
+    }
+    ISL_TRY(forward_device(e, dt, dl, nb, S, dout));
+    if (!on_device)
+      ISL_CUDA_TRY(cudaMemcpyAsync(out + s * H, e->pooled.p, nb * H * 4, cudaMemcpyDeviceToHost, e->stream));
+  }
+  ISL_CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+  ISL_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  float ms = 0.0f;
+  if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_ms = ms;
+  return ISL_OK;
+}
+
+isl_status refresh_bf16(isl_encoder* e) {
+  const Layout l = make_layout(e->cfg);
+  for (uint32_t layer = 0; layer < l.L; ++layer) {
+    const float* lp = e->params.p + l.layers + (size_t)layer * l.per_layer;
+    __nv_bfloat16* gw = e->wbf16.p + (size_t)layer * l.g_per_layer;
+    const size_t H = l.H, I = l.I;
+    const struct { size_t src, dst, cnt; } parts[4] = {
+        {l.qkv_w, l.g_qkv, 3 * H * H}, {l.ao_w, l.g_ao, H * H}, {l.f1_w, l.g_f1, I * H}, {l.f2_w, l.g_f2, H * I}};
+    for (const auto& pt : parts) {
+      to_bf16_kernel<<<1184, 256, 0, e->stream>>>(lp + pt.src, gw + pt.dst, pt.cnt);
+      count_launch();
+    }
+  }
+  ISL_CUDA_TRY(cudaGetLastError());
+  ISL_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return ISL_OK;
+}
+
+}  // namespace
+}  // namespace isl
+
+using namespace isl;
+
+extern "C" {
+
+isl_status isl_encoder_config_default(isl_encoder_config* c) {
+  if (!c) return fail(ISL_INVALID_ARGUMENT, "out is null");
+  c->vocab_size = 30522;  // BERT-base, the 110M-parameter shape of BASELINE.json configs[4]
+  c->hidden_size = 768;
+  c->num_layers = 12;
+  c->num_heads = 12;
+  c->intermediate_size = 3072;
+  c->max_position = 512;
+  c->type_vocab_size = 2;
+  c->layer_norm_eps = 1e-12f;
+  c->normalize = 1;  // EmbeddingConfig::normalize (candle_provider.rs:477)
+  return ISL_OK;
+}
+
+isl_status isl_encoder_new(const isl_encoder_config* cfg, isl_encoder** out) {
+  if (!out) return fail(ISL_INVALID_ARGUMENT, "out is null");
+  *out = nullptr;
+  ISL_TRY(validate_cfg(cfg));
+  std::unique_ptr<isl_encoder> e(new isl_encoder());
+  e->cfg = *cfg;
+  ISL_TRY(current_device(&e->device, &e->sms));
+  ISL_CUDA_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  ISL_CUDA_TRY(cudaEventCreate(&e->ev0));
+  ISL_CUDA_TRY(cudaEventCreate(&e->ev1));
+  const Layout l = make_layout(e->cfg);
+  ISL_CUDA_TRY(e->params.alloc(l.total));
+  ISL_CUDA_TRY(e->wbf16.alloc(l.g_total));
+  ISL_CUDA_TRY(cudaMemsetAsync(e->params.p, 0, e->params.bytes(), e->stream));
+  ISL_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  e->n_gemm = l.g_total;
+  *out = e.release();
+  return ISL_OK;
+}
+
+void isl_encoder_free(isl_encoder* e) {
+  if (!e) return;
+  DeviceGuard g(e->device);
+  delete e;
+}
+
+uint32_t isl_encoder_dimension(const isl_encoder* e) { return e ? e->cfg.hidden_size : 0; }
+
+uint64_t isl_encoder_num_parameters(const isl_encoder* e) { return e ? make_layout(e->cfg).total : 0; }
+
+isl_status isl_encoder_init_random(isl_encoder* e, uint64_t seed, float stddev) {
+  if (!e) return fail(ISL_INVALID_ARGUMENT, "encoder is null");
+  DeviceGuard g(e->device);
+  std::lock_guard<std::mutex> lock(e->mu);
+  const Layout l = make_layout(e->cfg);
+  float* P = e->params.p;
+  cudaStream_t st = e->stream;
+  const size_t H = l.H, I = l.I;
+  auto normal = [&](size_t off, size_t cnt, uint64_t tag) {
+    init_normal_kernel<<<1184, 256, 0, st>>>(P + off, cnt, seed * 0x100000001B3ull + tag, stddev);
+    count_launch();
+  };
+  auto fill = [&](size_t off, size_t cnt, float v) {
+    fill_kernel<<<64, 256, 0, st>>>(P + off, cnt, v);
+    count_launch();
+  };
+  normal(l.word, (size_t)l.V * H, 1);
+  normal(l.pos, (size_t)l.P * H, 2);
+  normal(l.type, (size_t)l.TV * H, 3);
+  fill(l.emb_ln_w, H, 1.0f);
+  fill(l.emb_ln_b, H, 0.0f);
+  for (uint32_t layer = 0; layer < l.L; ++layer) {
+    const size_t b = l.layers + (size_t)layer * l.per_layer;
+    const uint64_t t = 16 * (uint64_t)(layer + 1);
+    normal(b + l.qkv_w, 3 * H * H, t + 0);
+    fill(b + l.qkv_b, 3 * H, 0.0f);
+    normal(b + l.ao_w, H * H, t + 1);
+    fill(b + l.ao_b, H, 0.0f);
+    fill(b + l.ln1_w, H, 1.0f);
+    fill(b + l.ln1_b, H, 0.0f);
+    normal(b + l.f1_w, I * H, t + 2);
+    fill(b + l.f1_b, I, 0.0f);
+    normal(b + l.f2_w, H * I, t + 3);
+    fill(b + l.f2_b, H, 0.0f);
+    fill(b + l.ln2_w, H, 1.0f);
+    fill(b + l.ln2_b, H, 0.0f);
+  }
+  ISL_CUDA_TRY(cudaGetLastError());
+  ISL_TRY(refresh_bf16(e));
+  e->n_params = l.total;
+  return ISL_OK;
+}
+
+isl_status isl_encoder_set_parameter(isl_encoder* e, const char* name, const float* data, uint64_t count) {
+  if (!e || !name || !data) return fail(ISL_INVALID_ARGUMENT, "null pointer");
+  DeviceGuard g(e->device);
+  std::lock_guard<std::mutex> lock(e->mu);
+  const Layout l = make_layout(e->cfg);
+  size_t off, cnt;
+  if (!resolve(l, name, &off, &cnt)) return fail(ISL_INVALID_ARGUMENT, std::string("unknown parameter ") + name);
+  if (cnt != count)
+    return fail(ISL_DIM_MISMATCH, "dimension mismatch: expected " + std::to_string(cnt) + ", got " + std::to_string(count));
+  ISL_CUDA_TRY(cudaMemcpyAsync(e->params.p + off, data, cnt * 4, cudaMemcpyHostToDevice, e->stream));
+  ISL_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  ISL_TRY(refresh_bf16(e));
+  e->n_params = l.total;
+  return ISL_OK;
+}
+
+isl_status isl_encoder_get_parameter(const isl_encoder* e, const char* name, float* out, uint64_t count) {
+  if (!e || !name || !out) return fail(ISL_INVALID_ARGUMENT, "null pointer");
+  DeviceGuard g(e->device);
+  const Layout l = make_layout(e->cfg);
+  size_t off, cnt;
+  if (!resolve(l, name, &off, &cnt)) return fail(ISL_INVALID_ARGUMENT, std::string("unknown parameter ") + name);
+  if (cnt != count)
+    return fail(ISL_DIM_MISMATCH, "dimension mismatch: expected " + std::to_string(cnt) + ", got " + std::to_string(count));
+  ISL_CUDA_TRY(cudaMemcpy(out, e->params.p + off, cnt * 4, cudaMemcpyDeviceToHost));
+  return ISL_OK;
+}
+
+isl_status isl_encoder_embed(isl_encoder* e, const int32_t* token_ids, const int32_t* lengths, uint64_t batch,
+                             uint32_t seq_len, float* out) {
+  return embed_impl(e, token_ids, lengths, false, batch, seq_len, out);
+}
+
+isl_status isl_encoder_embed_dev(isl_encoder* e, const int32_t* d_token_ids, const int32_t* d_lengths, uint64_t batch,
+                                 uint32_t seq_len, float* d_out) {
+  if (e) {
+    DeviceGuard g(e->device);
+    cudaError_t err = cudaDeviceSynchronize();  // inputs may have been produced on another stream
+    if (err != cudaSuccess) return cuda_fail(err, "cudaDeviceSynchronize");
+  }
+  return embed_impl(e, d_token_ids, d_lengths, true, batch, seq_len, d_out);
+}
+
+isl_status isl_encoder_last_timing(const isl_encoder* e, float* ms, double* flops) {
+  if (!e) return fail(ISL_INVALID_ARGUMENT, "encoder is null");
+  if (ms) *ms = e->last_ms;
+  if (flops) *flops = e->last_flops;
+  return ISL_OK;
+}
+
+isl_status isl_gemm_bf16_dev(const void* d_a_bf16, const void* d_w_bf16, uint32_t m, uint32_t n, uint32_t k,
+                             const float* d_bias, const void* d_residual_bf16, int32_t gelu, void* d_out_bf16,
+                             float* d_out_f32) {
+  if (!d_a_bf16 || !d_w_bf16 || (!d_out_bf16 && !d_out_f32)) return fail(ISL_INVALID_ARGUMENT, "null pointer");
+  int device, sms;
+  ISL_TRY(current_device(&device, &sms));
+  ISL_TRY(launch_gemm_bf16(static_cast<const __nv_bfloat16*>(d_a_bf16), static_cast<const __nv_bfloat16*>(d_w_bf16), (int)m,
+                           (int)n, (int)k, d_bias, static_cast<const __nv_bfloat16*>(d_residual_bf16),
+                           gelu ? gemm::EPI_GELU : gemm::EPI_NONE, static_cast<__nv_bfloat16*>(d_out_bf16), d_out_f32, sms, 0));
+  ISL_CUDA_TRY(cudaStreamSynchronize(0));
+  return ISL_OK;
+}
+
+}  // extern "C"

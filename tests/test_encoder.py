@@ -1,0 +1,160 @@
+"""Recompute encoder: the tcgen05 GEMM against a torch fp32 reference of the same op,
+and the full bf16 encoder against the fp32 numpy oracle.  Tolerances (floating point, stated per
+north_star): GEMM f32-out 2e-3 relative to the row scale (bf16 operands, f32 accumulate); embeddings
+cosine >= 0.999 and max |diff| <= 2e-2 (x the output scale when not normalised); neighbour recall within 0.002 is checked in
+test_recompute_search.py."""
+import numpy as np
+import pytest
+
+
+def test_encoder_oracle_shapes_and_masking():
+    """CPU: the oracle ignores padded positions and returns unit vectors."""
+    from types import SimpleNamespace
+
+    from oracle.encoder_oracle import bert_embed
+
+    rng = np.random.RandomState(0)
+    cfg = SimpleNamespace(hidden_size=64, num_layers=1, num_heads=1, layer_norm_eps=1e-12, normalize=1)
+    H, I, V, P = 64, 128, 50, 16
+    p = {"embeddings.word_embeddings.weight": rng.randn(V, H).astype(np.float32) * 0.02,
+         "embeddings.position_embeddings.weight": rng.randn(P, H).astype(np.float32) * 0.02,
+         "embeddings.token_type_embeddings.weight": rng.randn(2, H).astype(np.float32) * 0.02,
+         "embeddings.LayerNorm.weight": np.ones(H, np.float32), "embeddings.LayerNorm.bias": np.zeros(H, np.float32)}
+    pre = "encoder.layer.0."
+    for n, shp in [("attention.self.query", (H, H)), ("attention.self.key", (H, H)), ("attention.self.value", (H, H)),
+                   ("attention.output.dense", (H, H)), ("intermediate.dense", (I, H)), ("output.dense", (H, I))]:
+        p[pre + n + ".weight"] = rng.randn(*shp).astype(np.float32) * 0.02
+        p[pre + n + ".bias"] = np.zeros(shp[0], np.float32)
+    for n in ("attention.output.LayerNorm", "output.LayerNorm"):
+        p[pre + n + ".weight"] = np.ones(H, np.float32)
+        p[pre + n + ".bias"] = np.zeros(H, np.float32)
+    t = rng.randint(1, V, size=(3, 8))
+    a = bert_embed(p, cfg, t, [8, 5, 3])
+    t2 = t.copy()
+    t2[1, 5:] = 7  # padded positions must not matter
+    t2[2, 3:] = 9
+    b = bert_embed(p, cfg, t2, [8, 5, 3])
+    assert a.shape == (3, H)
+    np.testing.assert_allclose(a, b, atol=1e-6)
+    np.testing.assert_allclose(np.linalg.norm(a, axis=1), 1.0, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,n,k", [(300, 768, 768), (1024, 2304, 768), (257, 3072, 768), (640, 768, 3072),
+                                   (128, 128, 512), (70, 64, 64), (5000, 256, 128)])
+@pytest.mark.parametrize("mode", ["plain", "bias_gelu", "bias_residual"])
+def test_gemm_tcgen05_vs_torch_fp32(gpu_lib, m, n, k, mode):
+    import torch
+
+    from islands_b200 import gemm_bf16_dev
+
+    g = torch.Generator(device="cuda").manual_seed(m * 7 + n + k)
+    a = (torch.randn((m, k), generator=g, device="cuda") * 0.5).to(torch.bfloat16)
+    w = (torch.randn((n, k), generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+    bias = torch.randn((n,), generator=g, device="cuda") if mode != "plain" else None
+    res = torch.randn((m, n), generator=g, device="cuda").to(torch.bfloat16) if mode == "bias_residual" else None
+    out_bf = torch.full((m, n), 7.0, device="cuda", dtype=torch.bfloat16)
+    out_f = torch.full((m, n), 7.0, device="cuda", dtype=torch.float32)
+    torch.cuda.synchronize()
+    gemm_bf16_dev(a.data_ptr(), w.data_ptr(), m, n, k, bias.data_ptr() if bias is not None else None,
+                  res.data_ptr() if res is not None else None, mode == "bias_gelu", out_bf.data_ptr(), out_f.data_ptr())
+    ref = a.float() @ w.float().T  # plain PyTorch fp32 reference of the same op (same bf16-rounded operands)
+    if bias is not None:
+        ref = ref + bias
+    if mode == "bias_gelu":
+        ref = torch.nn.functional.gelu(ref)
+    if res is not None:
+        ref = ref + res.float()
+    scale = ref.abs().max().item() + 1e-6
+    err_f = (out_f - ref).abs().max().item() / scale
+    err_b = (out_bf.float() - ref).abs().max().item() / scale
+    assert err_f < 2e-3, err_f          # f32 accumulate of bf16 products vs fp32 matmul
+    assert err_b < 1e-2, err_b          # + one bf16 rounding of the output
+
+
+def _small_cfg(**kw):
+    from islands_b200 import EncoderConfig
+
+    base = dict(vocab_size=1000, hidden_size=128, num_layers=2, num_heads=2, intermediate_size=512, max_position=64)
+    base.update(kw)
+    return EncoderConfig(**base)
+
+
+def _check_embeddings(enc, cfg, tokens, lengths):
+    from oracle.encoder_oracle import bert_embed
+
+    out = enc.embed(tokens, lengths)
+    ref = bert_embed(enc.state_dict(), cfg, tokens, lengths)
+    cos = (out * ref).sum(1) / (np.linalg.norm(out, axis=1) * np.linalg.norm(ref, axis=1) + 1e-30)
+    live = np.asarray(lengths) > 0
+    assert cos[live].min() >= 0.999, cos[live].min()
+    tol = 2e-2 * max(1.0, float(np.abs(ref).max()))  # unit vectors: 2e-2 absolute; unnormalised: relative to the scale
+    assert np.abs(out - ref).max() <= tol, (np.abs(out - ref).max(), tol)
+    return out, ref
+
+
+@pytest.mark.gpu
+def test_encoder_small_vs_oracle(gpu_lib):
+    from islands_b200 import Encoder
+
+    cfg = _small_cfg()
+    enc = Encoder(cfg).init_random(seed=5, stddev=0.05)
+    rng = np.random.RandomState(1)
+    B, S = 37, 24
+    tokens = rng.randint(1, 1000, size=(B, S)).astype(np.int32)
+    lengths = rng.randint(1, S + 1, size=B).astype(np.int32)
+    lengths[0], lengths[1] = S, 1
+    for b in range(B):
+        tokens[b, lengths[b]:] = 0
+    out, _ = _check_embeddings(enc, cfg, tokens, lengths)
+    np.testing.assert_allclose(np.linalg.norm(out, axis=1), 1.0, atol=1e-4)
+    # padded positions do not influence the result
+    t2 = tokens.copy()
+    t2[5, lengths[5]:] = 77
+    assert np.array_equal(enc.embed(t2, lengths)[5], out[5]) or lengths[5] == S
+    # empty batch and unnormalised output
+    assert enc.embed(np.zeros((0, S), np.int32), np.zeros(0, np.int32)).shape == (0, 128)
+    cfg2 = _small_cfg(normalize=0)
+    enc2 = Encoder(cfg2).init_random(seed=5, stddev=0.05)
+    _check_embeddings(enc2, cfg2, tokens[:8], lengths[:8])
+
+
+@pytest.mark.gpu
+def test_encoder_bert_base_shape_vs_oracle(gpu_lib):
+    """The 110M-parameter shape of BASELINE configs[4] (random init N(0, 0.02)), small batch."""
+    from islands_b200 import Encoder, EncoderConfig
+
+    cfg = EncoderConfig()
+    enc = Encoder(cfg).init_random(seed=46, stddev=0.02)
+    assert 105e6 < enc.num_parameters() < 115e6
+    rng = np.random.RandomState(2)
+    B, S = 6, 32
+    tokens = rng.randint(1, cfg.vocab_size, size=(B, S)).astype(np.int32)
+    lengths = np.array([32, 31, 17, 8, 2, 1], np.int32)
+    for b in range(B):
+        tokens[b, lengths[b]:] = 0
+    _check_embeddings(enc, cfg, tokens, lengths)
+    ms, flops = enc.last_timing()
+    assert ms > 0 and flops > 0
+
+
+@pytest.mark.gpu
+def test_encoder_parameter_roundtrip_and_errors(gpu_lib):
+    from islands_b200 import DimensionMismatch, Encoder, InvalidArgument, InvalidConfig, EncoderConfig
+
+    with pytest.raises(InvalidConfig):
+        Encoder(EncoderConfig(hidden_size=100))
+    cfg = _small_cfg(num_layers=1)
+    enc = Encoder(cfg)
+    with pytest.raises(InvalidArgument):  # weights not initialised: loud failure, not zeros
+        enc.embed(np.ones((1, 4), np.int32), np.array([4], np.int32))
+    enc.init_random(seed=1)
+    w = np.random.RandomState(0).randn(128, 128).astype(np.float32) * 0.02
+    enc.set_parameter("encoder.layer.0.attention.self.key.weight", w)
+    assert np.array_equal(enc.get_parameter("encoder.layer.0.attention.self.key.weight"), w)
+    with pytest.raises(DimensionMismatch):
+        enc.set_parameter("encoder.layer.0.attention.self.key.weight", w[:64])
+    with pytest.raises(InvalidArgument):
+        enc.set_parameter("encoder.layer.9.attention.self.key.weight", w)
+    with pytest.raises(InvalidArgument):
+        enc.embed(np.ones((1, 100), np.int32), np.array([4], np.int32))  # S > max_position
