@@ -338,6 +338,24 @@ isl_status isl_gemm_bf16_dev(const void* d_a_bf16, const void* d_w_bf16, uint32_
                              const float* d_bias, const void* d_residual_bf16, int32_t gelu,
                              void* d_out_bf16, float* d_out_f32);
 
+/* ---- search with on-demand recompute (leann.rs:82-99 EmbeddingProvider seam, :947-950) ---------- */
+/* Attach the recompute provider: node i's embedding is encoder(token_ids[i][0..seq_len), lengths[i]).
+ * enc == NULL detaches.  The encoder must outlive the attachment; its dimension must equal the
+ * index dimension (else ISL_DIM_MISMATCH). */
+isl_status isl_index_set_recompute(isl_index* idx, isl_encoder* enc, const int32_t* token_ids,
+                                   const int32_t* lengths, uint32_t seq_len);
+/* Free the resident f32 embeddings (LEANN's storage saving): only the recompute search remains. */
+isl_status isl_index_drop_vectors(isl_index* idx);
+/* PQ ADC traversal -> recompute the distinct ef-survivors of the batch with the bf16 encoder ->
+ * exact rerank (reference-order f32 distances) against the recomputed embeddings. */
+isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* queries, uint64_t nq,
+                                          uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* out_ids,
+                                          float* out_dist, uint32_t* out_count,
+                                          isl_search_stats* stats_or_null);
+/* Nodes recomputed by the last recompute search and the CUDA-event time of its three stages. */
+isl_status isl_index_last_recompute(const isl_index* idx, uint64_t* unique_nodes, float* traverse_ms,
+                                    float* encoder_ms, float* rerank_ms);
+
 /* ---- island / shard merge (search.rs:211-237, indexer/service.rs:775-801) ---------- */
 /* Per query, merge `parts` lists of k (dist,id) pairs laid out [parts][nq][k] into the k best
  * by (dist, id); ISL_INVALID_ID entries are ignored. */

@@ -181,6 +181,10 @@ SIGNATURES = {
     "isl_encoder_embed_dev": (C.c_int, [_VP, _VP, _VP, C.c_uint64, C.c_uint32, _VP]),
     "isl_encoder_last_timing": (C.c_int, [_VP, f32p, C.POINTER(C.c_double)]),
     "isl_gemm_bf16_dev": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint32, C.c_uint32, _VP, _VP, C.c_int32, _VP, _VP]),
+    "isl_index_set_recompute": (C.c_int, [_VP, _VP, i32p, i32p, C.c_uint32]),
+    "isl_index_drop_vectors": (C.c_int, [_VP]),
+    "isl_index_search_adc_recompute": (C.c_int, [_VP, f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u64p, f32p, u32p, _SSP]),
+    "isl_index_last_recompute": (C.c_int, [_VP, u64p, f32p, f32p, f32p]),
     "isl_merge_topk": (C.c_int, [u64p, f32p, C.c_uint32, C.c_uint64, C.c_uint32, u64p, f32p, u32p]),
     "isl_merge_topk_dev": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint64, C.c_uint32, _VP, _VP, _VP]),
 }

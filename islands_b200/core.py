@@ -594,6 +594,51 @@ def _adc_rerank(self, queries, k, ef, stats=False):
 LeannIndex.search_adc_rerank_batch = _adc_rerank
 
 
+def _set_recompute(self, encoder, token_ids, lengths):
+    """EmbeddingProvider analogue (leann.rs:82-99): node i -> encoder(token_ids[i], lengths[i])."""
+    if encoder is None:
+        _check(_ffi.load().isl_index_set_recompute(self._h, None, None, None, 1))
+        self._enc = None
+        return
+    t = np.ascontiguousarray(token_ids, np.int32)
+    ln = np.ascontiguousarray(lengths, np.int32)
+    _check(_ffi.load().isl_index_set_recompute(self._h, encoder._h, t.ctypes.data_as(_ffi.i32p),
+                                               ln.ctypes.data_as(_ffi.i32p), t.shape[1]))
+    self._enc = encoder  # keep the encoder alive while attached
+
+
+def _drop_vectors(self):
+    _check(_ffi.load().isl_index_drop_vectors(self._h))
+
+
+def _adc_recompute(self, queries, k, ef, stats=False):
+    """ADC traversal + bf16 recompute of the survivors + exact rerank (isl_index_search_adc_recompute)."""
+    q = _f32(queries)
+    q = q.reshape(1, -1) if q.ndim == 1 else q
+    nq, qd = q.shape
+    ids = np.empty((nq, k), np.uint64)
+    dist = np.empty((nq, k), np.float32)
+    cnt = np.empty(nq, np.uint32)
+    st = np.zeros(nq, _STATS_DTYPE) if stats else None
+    _check(_ffi.load().isl_index_search_adc_recompute(self._h, _ptr(q, f32p), nq, qd, k, int(ef), _ptr(ids, u64p),
+                                                      _ptr(dist, f32p), _ptr(cnt, u32p),
+                                                      st.ctypes.data_as(C.POINTER(SearchStatsStruct)) if stats else None))
+    return (ids, dist, cnt, SearchStats(st)) if stats else (ids, dist, cnt)
+
+
+def _last_recompute(self):
+    u = C.c_uint64()
+    a, b, c = C.c_float(), C.c_float(), C.c_float()
+    _check(_ffi.load().isl_index_last_recompute(self._h, C.byref(u), C.byref(a), C.byref(b), C.byref(c)))
+    return dict(unique_nodes=u.value, traverse_ms=a.value, encoder_ms=b.value, rerank_ms=c.value)
+
+
+LeannIndex.set_recompute = _set_recompute
+LeannIndex.drop_vectors = _drop_vectors
+LeannIndex.search_adc_recompute_batch = _adc_recompute
+LeannIndex.last_recompute = _last_recompute
+
+
 def random_level(u, ml, max_layers):
     """LeannIndex::random_level (leann.rs:549-554) for an explicit uniform draw u in (0,1)."""
     lvl = math.floor(-math.log(u) * ml)

@@ -74,6 +74,17 @@ struct isl_index {
   const isl_pq* pq = nullptr;
   isl::DevBuf<uint8_t> codes8;    // [n][m] when ksub <= 256
   isl::DevBuf<uint16_t> codes16;  // [n][m] otherwise
+  // on-demand recompute attachment (EmbeddingProvider seam, leann.rs:82-99): token rows per node
+  isl_encoder* encoder = nullptr;
+  isl::DevBuf<int32_t> node_tokens;   // [n][tok_len]
+  isl::DevBuf<int32_t> node_lengths;  // [n]
+  uint32_t tok_len = 0;
+  mutable isl::DevBuf<uint32_t> rc_flags, rc_rows, rc_surv, rc_surv_cnt;
+  mutable isl::DevBuf<int32_t> rc_tok, rc_len;
+  mutable isl::DevBuf<float> rc_emb, rc_sq;
+  mutable isl::DevBuf<uint8_t> rc_tmp;
+  mutable uint64_t last_recomputed = 0;
+  mutable float last_encoder_ms = 0.0f, last_traverse_ms = 0.0f, last_rerank_ms = 0.0f;
   // per-handle stream, timing and scratch (guarded by mu: searches on one handle serialise)
   mutable std::mutex mu;
   cudaStream_t stream = nullptr;

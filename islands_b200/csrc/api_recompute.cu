@@ -1,0 +1,229 @@
+// api_recompute.cu — search with on-demand embedding recomputation (LEANN's storage-free mode):
+// the index keeps graph + PQ codes + token rows, NOT the f32 embeddings.  A query batch runs
+//   1. the ADC traversal (search_core.cuh MODE 2, phase 1): ef survivors per query, PQ bytes only;
+//   2. the recompute step: the distinct survivors of the whole batch are compacted (flag, scan,
+//      gather of their token rows) and pushed through the bf16 tcgen05 encoder once (encoder.cu);
+//   3. the exact rerank (MODE 2, phase 2): reference-order distances (distance.rs) of every
+//      survivor against the recomputed embeddings, sorted by (distance, id).
+// The reference's seam for this is EmbeddingProvider::compute_embeddings_batch (leann.rs:82-99)
+// called on the search frontier (leann.rs:947-950); batching the whole frontier of the batch into
+// one encoder pass is docs/leann-specification.md:364-394 ("dynamic batching").
+#include <cub/cub.cuh>
+
+#include <algorithm>
+
+#include "api_common.h"
+
+namespace isl {
+namespace {
+
+__global__ void mark_survivors_kernel(const uint32_t* __restrict__ surv, const uint32_t* __restrict__ cnt, uint32_t nq,
+                                      uint32_t ef, uint32_t* __restrict__ flags) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < (size_t)nq * ef; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t q = (uint32_t)(i / ef), j = (uint32_t)(i % ef);
+    if (j < cnt[q]) flags[surv[i]] = 1u;
+  }
+}
+
+// One warp per flagged node: its token row goes to row rows[id] of the compact batch.
+__global__ void gather_tokens_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ rows, uint32_t n,
+                                     const int32_t* __restrict__ tokens, const int32_t* __restrict__ lengths, uint32_t S,
+                                     int32_t* __restrict__ out_tok, int32_t* __restrict__ out_len) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5, lane = threadIdx.x & 31;
+  for (uint32_t id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; id < n; id += warps) {
+    if (!flags[id]) continue;
+    const uint32_t r = rows[id];
+    for (uint32_t i = lane; i < S; i += 32) out_tok[(size_t)r * S + i] = tokens[(size_t)id * S + i];
+    if (lane == 0) out_len[r] = lengths[id];
+  }
+}
+
+}  // namespace
+}  // namespace isl
+
+using namespace isl;
+
+extern "C" {
+
+isl_status isl_index_set_recompute(isl_index* idx, isl_encoder* enc, const int32_t* token_ids, const int32_t* lengths,
+                                   uint32_t seq_len) {
+  if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
+  DeviceGuard g(idx->device);
+  std::lock_guard<std::mutex> lock(idx->mu);
+  if (!enc) {  // detach
+    idx->encoder = nullptr;
+    idx->node_tokens.release();
+    idx->node_lengths.release();
+    idx->tok_len = 0;
+    return ISL_OK;
+  }
+  if (idx->n && (!token_ids || !lengths)) return fail(ISL_INVALID_ARGUMENT, "token_ids / lengths is null");
+  if (seq_len == 0) return fail(ISL_INVALID_ARGUMENT, "seq_len must be > 0");
+  if (idx->n && isl_encoder_dimension(enc) != idx->dim)  // EmbeddingProvider::dimension (leann.rs:97-98)
+    return fail(ISL_DIM_MISMATCH, "dimension mismatch: expected " + std::to_string(idx->dim) + ", got " +
+                                      std::to_string(isl_encoder_dimension(enc)));
+  if (idx->n && idx->ld != idx->dim) return fail(ISL_INVALID_ARGUMENT, "recompute needs dim % 4 == 0");
+  ISL_CUDA_TRY(idx->node_tokens.alloc(std::max<uint64_t>(idx->n * seq_len, 1)));
+  ISL_CUDA_TRY(idx->node_lengths.alloc(std::max<uint64_t>(idx->n, 1)));
+  if (idx->n) {
+    ISL_CUDA_TRY(cudaMemcpy(idx->node_tokens.p, token_ids, idx->n * seq_len * 4, cudaMemcpyHostToDevice));
+    ISL_CUDA_TRY(cudaMemcpy(idx->node_lengths.p, lengths, idx->n * 4, cudaMemcpyHostToDevice));
+  }
+  idx->encoder = enc;
+  idx->tok_len = seq_len;
+  return ISL_OK;
+}
+
+// Frees the resident f32 embeddings: afterwards only the recompute search works on this handle.
+isl_status isl_index_drop_vectors(isl_index* idx) {
+  if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
+  DeviceGuard g(idx->device);
+  std::lock_guard<std::mutex> lock(idx->mu);
+  if (!idx->encoder) return fail(ISL_INVALID_ARGUMENT, "attach a recompute encoder before dropping the stored vectors");
+  idx->vectors.release();
+  idx->sqnorms.release();
+  return ISL_OK;
+}
+
+isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* queries, uint64_t nq, uint32_t query_dim,
+                                          uint32_t k, uint32_t ef, uint64_t* out_ids, float* out_dist,
+                                          uint32_t* out_count, isl_search_stats* stats) {
+  bool trivial;
+  ISL_TRY(search_checks(idx, queries, nq, query_dim, k, &ef, &trivial));
+  if (trivial) {
+    fill_empty(nq, k, out_ids, out_dist, out_count, stats);
+    return ISL_OK;
+  }
+  if (!idx->pq) return fail(ISL_PQ_ERROR, "no product quantizer attached (isl_index_attach_pq)");
+  if (!idx->encoder) return fail(ISL_INVALID_ARGUMENT, "no recompute encoder attached (isl_index_set_recompute)");
+  if (!out_ids || !out_dist) return fail(ISL_INVALID_ARGUMENT, "output pointer is null");
+  const isl_pq* pq = idx->pq;
+  DeviceGuard g(idx->device);
+  std::lock_guard<std::mutex> lock(idx->mu);
+  const uint32_t m = (uint32_t)pq->cfg.num_subquantizers;
+  const uint32_t lut_floats = m * pq->ksub;
+  const uint32_t n = (uint32_t)idx->n;
+  const uint32_t maxdeg = std::max<uint32_t>(idx->max_degree, 1);
+  const uint32_t u_cap = std::max<uint32_t>(std::max<uint32_t>(32, round_up(maxdeg + 1, 32)), round_up(ef, 32));
+  SearchPlan plan;
+  ISL_TRY(plan_search_adc(idx->cfg.metric, idx->ld, ef, u_cap, m, pq->ksub, idx->sms, &plan));
+  const uint32_t vis_words = round_up((uint32_t)((idx->n + 31) / 32), 4);
+  const uint32_t slots = (uint32_t)std::min<uint64_t>(plan.grid, nq);
+  ISL_TRY(ensure(idx->visited, (size_t)slots * vis_words));
+  if (!plan.r_in_smem) ISL_TRY(ensure(idx->r_global, (size_t)slots * ef));
+  ISL_TRY(ensure(idx->aux_f32, (size_t)nq * lut_floats + 2));
+  ISL_TRY(ensure(idx->q_stage, nq * idx->ld));
+  ISL_TRY(ensure(idx->out_ids, nq * k));
+  ISL_TRY(ensure(idx->out_dist, nq * k));
+  ISL_TRY(ensure(idx->out_count, nq));
+  ISL_TRY(ensure(idx->out_stats, nq));
+  ISL_TRY(ensure(idx->rc_surv, nq * (size_t)ef));
+  ISL_TRY(ensure(idx->rc_surv_cnt, nq));
+  ISL_TRY(ensure(idx->rc_flags, (size_t)n + 1));
+  ISL_TRY(ensure(idx->rc_rows, (size_t)n + 1));
+  cudaStream_t st = idx->stream;
+  if (idx->ld != idx->dim) ISL_CUDA_TRY(cudaMemsetAsync(idx->q_stage.p, 0, nq * idx->ld * 4, st));
+  ISL_CUDA_TRY(cudaMemcpy2DAsync(idx->q_stage.p, (size_t)idx->ld * 4, queries, (size_t)idx->dim * 4, (size_t)idx->dim * 4,
+                                 nq, cudaMemcpyHostToDevice, st));
+  ISL_CUDA_TRY(cudaMemsetAsync(idx->counters.p, 0, 4 * sizeof(unsigned int), st));
+
+  // ---- 1. ADC traversal ------------------------------------------------------------------------
+  ISL_CUDA_TRY(cudaEventRecord(idx->ev0, st));
+  ISL_TRY(launch_pq_tables(pq->dev(), idx->q_stage.p, idx->ld, nq, idx->aux_f32.p, idx->sms, st));
+  SearchArgs a{};
+  a.vectors = nullptr;  // phase 1 never reads an embedding
+  a.sqnorms = nullptr;
+  a.ld = idx->ld;
+  a.d = idx->dim;
+  a.n = n;
+  search_args_set_graph(idx, &a);
+  a.queries = idx->q_stage.p;
+  a.q_ld = idx->ld;
+  a.nq = (uint32_t)nq;
+  a.entry = (uint32_t)idx->entry;
+  a.k = k;
+  a.ef = ef;
+  a.metric = idx->cfg.metric;
+  a.visited = idx->visited.p;
+  a.vis_words = vis_words;
+  a.r_global = idx->r_global.p;
+  a.u_cap = u_cap;
+  a.out_ids = idx->out_ids.p;
+  a.out_dist = idx->out_dist.p;
+  a.out_count = idx->out_count.p;
+  a.stats = idx->out_stats.p;
+  a.work_counter = idx->counters.p;
+  a.error_flag = idx->counters.p + 1;
+  a.luts = idx->aux_f32.p;
+  a.codes8 = idx->codes8.p;
+  a.codes16 = idx->codes8.p ? nullptr : idx->codes16.p;
+  a.pq_m = m;
+  a.pq_ksub = pq->ksub;
+  a.lut_smem_floats = plan.lut_smem_floats;
+  a.phase = 1;
+  a.surv_ids = idx->rc_surv.p;
+  a.surv_cnt = idx->rc_surv_cnt.p;
+  ISL_TRY(launch_search(plan, a, st));
+  ISL_CUDA_TRY(cudaEventRecord(idx->ev1, st));
+
+  // ---- 2. recompute the distinct survivors ----------------------------------------------------------
+  ISL_CUDA_TRY(cudaMemsetAsync(idx->rc_flags.p, 0, ((size_t)n + 1) * 4, st));
+  mark_survivors_kernel<<<1184, 256, 0, st>>>(idx->rc_surv.p, idx->rc_surv_cnt.p, (uint32_t)nq, ef, idx->rc_flags.p);
+  count_launch();
+  size_t scan_bytes = 0;
+  ISL_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, idx->rc_flags.p, idx->rc_rows.p, (int)(n + 1), st));
+  ISL_TRY(ensure(idx->rc_tmp, scan_bytes + 16));
+  ISL_CUDA_TRY(cub::DeviceScan::ExclusiveSum(idx->rc_tmp.p, scan_bytes, idx->rc_flags.p, idx->rc_rows.p, (int)(n + 1), st));
+  count_launch(2);
+  uint32_t unique = 0;
+  ISL_CUDA_TRY(cudaMemcpyAsync(&unique, idx->rc_rows.p + n, 4, cudaMemcpyDeviceToHost, st));
+  ISL_CUDA_TRY(cudaStreamSynchronize(st));
+  float ms = 0.0f;
+  if (cudaEventElapsedTime(&ms, idx->ev0, idx->ev1) == cudaSuccess) idx->last_traverse_ms = ms;
+  const uint32_t S = idx->tok_len;
+  ISL_TRY(ensure(idx->rc_tok, (size_t)unique * S + 1));
+  ISL_TRY(ensure(idx->rc_len, (size_t)unique + 1));
+  ISL_TRY(ensure(idx->rc_emb, (size_t)unique * idx->ld + 4));
+  ISL_TRY(ensure(idx->rc_sq, (size_t)unique + 1));
+  gather_tokens_kernel<<<1184, 256, 0, st>>>(idx->rc_flags.p, idx->rc_rows.p, n, idx->node_tokens.p, idx->node_lengths.p, S,
+                                            idx->rc_tok.p, idx->rc_len.p);
+  count_launch();
+  ISL_CUDA_TRY(cudaGetLastError());
+  ISL_CUDA_TRY(cudaStreamSynchronize(st));
+  ISL_TRY(isl_encoder_embed_dev(idx->encoder, idx->rc_tok.p, idx->rc_len.p, unique, S, idx->rc_emb.p));
+  isl_encoder_last_timing(idx->encoder, &idx->last_encoder_ms, nullptr);
+  idx->last_recomputed = unique;
+  ISL_TRY(launch_row_sqnorms(idx->rc_emb.p, unique, idx->dim, idx->ld, idx->rc_sq.p, idx->sms, st));
+
+  // ---- 3. exact rerank against the recomputed rows ---------------------------------------------------
+  ISL_CUDA_TRY(cudaMemsetAsync(idx->counters.p, 0, sizeof(unsigned int), st));
+  a.vectors = idx->rc_emb.p;
+  a.sqnorms = idx->rc_sq.p;
+  a.row_of_id = idx->rc_rows.p;
+  a.phase = 2;
+  ISL_CUDA_TRY(cudaEventRecord(idx->ev0, st));
+  ISL_TRY(launch_search(plan, a, st));
+  ISL_CUDA_TRY(cudaEventRecord(idx->ev1, st));
+  idx->last_launches = 3;
+
+  ISL_CUDA_TRY(cudaMemcpyAsync(out_ids, idx->out_ids.p, nq * k * 8, cudaMemcpyDeviceToHost, st));
+  ISL_CUDA_TRY(cudaMemcpyAsync(out_dist, idx->out_dist.p, nq * k * 4, cudaMemcpyDeviceToHost, st));
+  if (out_count) ISL_CUDA_TRY(cudaMemcpyAsync(out_count, idx->out_count.p, nq * 4, cudaMemcpyDeviceToHost, st));
+  if (stats)
+    ISL_CUDA_TRY(cudaMemcpyAsync(stats, idx->out_stats.p, nq * sizeof(isl_search_stats), cudaMemcpyDeviceToHost, st));
+  ISL_TRY(search_finish(idx));
+  idx->last_rerank_ms = idx->last_kernel_ms;
+  return ISL_OK;
+}
+
+isl_status isl_index_last_recompute(const isl_index* idx, uint64_t* unique_nodes, float* traverse_ms, float* encoder_ms,
+                                    float* rerank_ms) {
+  if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
+  if (unique_nodes) *unique_nodes = idx->last_recomputed;
+  if (traverse_ms) *traverse_ms = idx->last_traverse_ms;
+  if (encoder_ms) *encoder_ms = idx->last_encoder_ms;
+  if (rerank_ms) *rerank_ms = idx->last_rerank_ms;
+  return ISL_OK;
+}
+
+}  // extern "C"

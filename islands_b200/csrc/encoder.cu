@@ -244,71 +244,118 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__
 }
 
 // Masked softmax attention, head_dim = 64.  One CTA per (sequence, head); keys/values of the
-// sequence staged in shared memory as f32; one warp per query row.  Padded key positions
-// (j >= len) are excluded — the additive -inf mask of BERT — and padded query rows are zeroed
-// (nothing downstream reads them: they are masked as keys and skipped by the pooling).
+// sequence staged in shared memory as f32; each warp owns four query rows at a time so that every
+// K / V value read from shared memory feeds four FMAs (register blocking: 16 FMAs per 5 LDS.128 in
+// the score phase, 8 FMAs per 2 loads in the PV phase).  Padded key positions (j >= len) are
+// excluded — the additive -inf mask of BERT — and padded query rows are zeroed (nothing downstream
+// reads them: they are masked as keys and skipped by the pooling).
+constexpr uint32_t kAttRows = 4, kAttKStride = 68;
 __global__ void __launch_bounds__(128)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ lengths, uint32_t S, uint32_t H,
                  __nv_bfloat16* __restrict__ ctx) {
-  extern __shared__ float att_smem[];
+  extern __shared__ __align__(16) float att_smem[];
   const uint32_t b = blockIdx.x, h = blockIdx.y;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
   const uint32_t len = min((uint32_t)max(lengths[b], 0), S);
-  float* Ks = att_smem;                 // [S][65]
-  float* Vs = Ks + (size_t)S * 65;      // [S][64]
-  float* qs = Vs + (size_t)S * 64;      // [warps][64]
-  float* ps = qs + warps * 64;          // [warps][S]
+  float* Ks = att_smem;                           // [S][68]
+  float* Vs = Ks + (size_t)S * kAttKStride;       // [S][64]
+  float* qs = Vs + (size_t)S * 64;                // [warps][4][64]
+  float* ps = qs + warps * kAttRows * 64;         // [warps][S][4]
   const size_t row_stride = 3 * (size_t)H;
   const __nv_bfloat16* base = qkv + (size_t)b * S * row_stride + h * 64;
   for (uint32_t i = threadIdx.x; i < len * 32; i += blockDim.x) {
     const uint32_t j = i >> 5, c = (i & 31) * 2;
     const float2 k2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + j * row_stride + H + c));
     const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + j * row_stride + 2 * H + c));
-    Ks[j * 65 + c] = k2.x;
-    Ks[j * 65 + c + 1] = k2.y;
-    Vs[j * 64 + c] = v2.x;
-    Vs[j * 64 + c + 1] = v2.y;
+    *reinterpret_cast<float2*>(Ks + j * kAttKStride + c) = k2;
+    *reinterpret_cast<float2*>(Vs + j * 64 + c) = v2;
   }
   __syncthreads();
-  float* q = qs + warp * 64;
-  float* p = ps + (size_t)warp * S;
-  for (uint32_t i = warp; i < S; i += warps) {
-    __nv_bfloat16* out = ctx + ((size_t)b * S + i) * H + h * 64;
-    if (i >= len) {
-      *reinterpret_cast<__nv_bfloat162*>(out + lane * 2) = __floats2bfloat162_rn(0.0f, 0.0f);
+  float* q = qs + warp * kAttRows * 64;
+  float* p = ps + (size_t)warp * S * kAttRows;
+  for (uint32_t i0 = warp * kAttRows; i0 < S; i0 += warps * kAttRows) {
+    if (i0 >= len) {  // a whole group of padded rows
+      for (uint32_t r = 0; r < kAttRows && i0 + r < S; ++r)
+        *reinterpret_cast<__nv_bfloat162*>(ctx + ((size_t)b * S + i0 + r) * H + h * 64 + lane * 2) =
+            __floats2bfloat162_rn(0.0f, 0.0f);
       continue;
     }
-    const float2 q2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + i * row_stride + lane * 2));
     __syncwarp();
-    q[lane * 2] = q2.x * 0.125f;  // 1 / sqrt(64)
-    q[lane * 2 + 1] = q2.y * 0.125f;
-    __syncwarp();
-    float mx = -INFINITY;
-    for (uint32_t j = lane; j < len; j += 32) {
-      float s = 0.0f;
-#pragma unroll 16
-      for (uint32_t d = 0; d < 64; ++d) s = fmaf(q[d], Ks[j * 65 + d], s);
-      p[j] = s;
-      mx = fmaxf(mx, s);
+#pragma unroll
+    for (uint32_t r = 0; r < kAttRows; ++r) {
+      float2 q2 = make_float2(0.0f, 0.0f);
+      if (i0 + r < S)
+        q2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + (i0 + r) * row_stride + lane * 2));
+      *reinterpret_cast<float2*>(q + r * 64 + lane * 2) = make_float2(q2.x * 0.125f, q2.y * 0.125f);  // 1 / sqrt(64)
     }
-    mx = warp_max(mx);
-    float den = 0.0f;
-    for (uint32_t j = lane; j < len; j += 32) {
-      const float e = __expf(p[j] - mx);
-      p[j] = e;
-      den += e;
-    }
-    den = warp_sum(den);
     __syncwarp();
-    float o0 = 0.0f, o1 = 0.0f;
+    float mx[kAttRows];
+#pragma unroll
+    for (uint32_t r = 0; r < kAttRows; ++r) mx[r] = -INFINITY;
+    for (uint32_t j = lane; j < len; j += 32) {
+      float acc[kAttRows] = {0.0f, 0.0f, 0.0f, 0.0f};
+      const float4* k4 = reinterpret_cast<const float4*>(Ks + j * kAttKStride);
+#pragma unroll
+      for (uint32_t dg = 0; dg < 16; ++dg) {
+        const float4 kk = k4[dg];
+#pragma unroll
+        for (uint32_t r = 0; r < kAttRows; ++r) {
+          const float4 qq = *reinterpret_cast<const float4*>(q + r * 64 + dg * 4);
+          acc[r] = fmaf(qq.x, kk.x, acc[r]);
+          acc[r] = fmaf(qq.y, kk.y, acc[r]);
+          acc[r] = fmaf(qq.z, kk.z, acc[r]);
+          acc[r] = fmaf(qq.w, kk.w, acc[r]);
+        }
+      }
+      *reinterpret_cast<float4*>(p + j * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+#pragma unroll
+      for (uint32_t r = 0; r < kAttRows; ++r) mx[r] = fmaxf(mx[r], acc[r]);
+    }
+    float den[kAttRows];
+#pragma unroll
+    for (uint32_t r = 0; r < kAttRows; ++r) {
+      mx[r] = warp_max(mx[r]);
+      den[r] = 0.0f;
+    }
+    for (uint32_t j = lane; j < len; j += 32) {
+      float4 e = *reinterpret_cast<float4*>(p + j * 4);
+      e.x = __expf(e.x - mx[0]);
+      e.y = __expf(e.y - mx[1]);
+      e.z = __expf(e.z - mx[2]);
+      e.w = __expf(e.w - mx[3]);
+      *reinterpret_cast<float4*>(p + j * 4) = e;
+      den[0] += e.x;
+      den[1] += e.y;
+      den[2] += e.z;
+      den[3] += e.w;
+    }
+#pragma unroll
+    for (uint32_t r = 0; r < kAttRows; ++r) den[r] = warp_sum(den[r]);
+    __syncwarp();
+    float o[kAttRows][2];
+#pragma unroll
+    for (uint32_t r = 0; r < kAttRows; ++r) o[r][0] = o[r][1] = 0.0f;
+#pragma unroll 4
     for (uint32_t j = 0; j < len; ++j) {
-      const float pj = p[j];
-      o0 = fmaf(pj, Vs[j * 64 + lane], o0);
-      o1 = fmaf(pj, Vs[j * 64 + 32 + lane], o1);
+      const float4 pj = *reinterpret_cast<const float4*>(p + j * 4);
+      const float2 v2 = *reinterpret_cast<const float2*>(Vs + j * 64 + lane * 2);
+      o[0][0] = fmaf(pj.x, v2.x, o[0][0]);
+      o[0][1] = fmaf(pj.x, v2.y, o[0][1]);
+      o[1][0] = fmaf(pj.y, v2.x, o[1][0]);
+      o[1][1] = fmaf(pj.y, v2.y, o[1][1]);
+      o[2][0] = fmaf(pj.z, v2.x, o[2][0]);
+      o[2][1] = fmaf(pj.z, v2.y, o[2][1]);
+      o[3][0] = fmaf(pj.w, v2.x, o[3][0]);
+      o[3][1] = fmaf(pj.w, v2.y, o[3][1]);
     }
-    const float inv = 1.0f / den;
-    out[lane] = __float2bfloat16_rn(o0 * inv);
-    out[32 + lane] = __float2bfloat16_rn(o1 * inv);
+#pragma unroll
+    for (uint32_t r = 0; r < kAttRows; ++r) {
+      if (i0 + r >= S) continue;
+      const bool live = i0 + r < len;
+      const float inv = live ? 1.0f / den[r] : 0.0f;
+      *reinterpret_cast<__nv_bfloat162*>(ctx + ((size_t)b * S + i0 + r) * H + h * 64 + lane * 2) =
+          __floats2bfloat162_rn(o[r][0] * inv, o[r][1] * inv);
+    }
   }
 }
 
@@ -449,7 +496,7 @@ isl_status forward_device(isl_encoder* e, const int32_t* d_tokens, const int32_t
   embed_ln_kernel<<<row_blocks, 128, 0, st>>>(d_tokens, P + l.word, P + l.pos, P + l.type, P + l.emb_ln_w, P + l.emb_ln_b,
                                              T, (uint32_t)S, H, l.V, eps, e->x.p);
   count_launch();
-  const size_t att_smem = ((size_t)S * 65 + (size_t)S * 64 + 4 * 64 + 4 * S) * sizeof(float);
+  const size_t att_smem = ((size_t)S * kAttKStride + (size_t)S * 64 + 4 * kAttRows * 64 + 4 * (size_t)S * kAttRows) * sizeof(float);
   ISL_CUDA_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
   for (uint32_t layer = 0; layer < l.L; ++layer) {
     const float* lp = P + l.layers + (size_t)layer * l.per_layer;

@@ -64,7 +64,8 @@ struct RowRing {
 template <int ACC, int STAGES, class OnGroup>
 __device__ __forceinline__ void stream_rows_fold(RowRing<STAGES>& ring, const float* __restrict__ vectors, uint32_t ld,
                                                  uint32_t d, const uint32_t* row_ids, uint32_t total,
-                                                 const float* q_smem, OnGroup&& on_group) {
+                                                 const float* q_smem, OnGroup&& on_group,
+                                                 const uint32_t* __restrict__ row_of_id = nullptr) {
   using G = StageGeom<64>;
   const uint32_t lane = lane_id();
   const uint32_t ngroups = (total + 31) >> 5;
@@ -75,7 +76,11 @@ __device__ __forceinline__ void stream_rows_fold(RowRing<STAGES>& ring, const fl
     if (ig < ngroups) {
       icnt = min(32u, total - (ig << 5));
       ish = group_slice_shift(icnt);
-      my_row = lane < icnt ? vectors + (size_t)row_ids[(ig << 5) + lane] * ld : nullptr;
+      my_row = nullptr;
+      if (lane < icnt) {
+        const uint32_t id = row_ids[(ig << 5) + lane];
+        my_row = vectors + (size_t)(row_of_id ? __ldg(row_of_id + id) : id) * ld;
+      }
     }
   };
   load_issue_group();

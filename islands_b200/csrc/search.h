@@ -54,6 +54,13 @@ struct SearchArgs {
   const uint32_t* query_ids; // [nq] query i is vectors[query_ids[i]] (null => `queries`)
   const uint32_t* row_map;   // node -> first adjacency row in a compact pool (null => row = node)
   uint32_t row_add;          // added to row_map[node] (layer - 1)
+  // recompute (MODE 2 split in two launches around the encoder): phase 1 = ADC traversal only, the
+  // ef survivors are written to surv_ids / surv_cnt; phase 2 = exact rerank only of cand lists
+  // against rows addressed through row_of_id (recomputed embeddings live in a compact matrix)
+  uint32_t phase;              // 0 = both in one launch
+  uint32_t* surv_ids;          // [nq][ef]   (phase 1 out, phase 2 in)
+  uint32_t* surv_cnt;          // [nq]
+  const uint32_t* row_of_id;   // node id -> row of `vectors` / `sqnorms` (null => identity)
   const uint32_t* node_levels; // [n] top layer of every node; a node has no list above it (hnsw.rs:108-110)
   uint32_t layer;            // layer being searched (only read when node_levels is set)
 };

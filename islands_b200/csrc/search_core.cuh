@@ -135,9 +135,11 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
           a.query_ids ? a.vectors + (size_t)__ldg(a.query_ids + qi) * a.ld : a.queries + (size_t)qi * a.q_ld);
       float4* dst = reinterpret_cast<float4*>(q_smem);
       for (uint32_t i = lane; i < a.ld / 4; i += 32) dst[i] = src[i];
-      uint4* v4 = reinterpret_cast<uint4*>(vis);
-      const uint4 z = make_uint4(0, 0, 0, 0);
-      for (uint32_t i = lane; i < a.vis_words / 4; i += 32) __stcg(v4 + i, z);
+      if (!(ADC && a.phase == 2)) {  // the rerank-only launch never touches the visited set
+        uint4* v4 = reinterpret_cast<uint4*>(vis);
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = lane; i < a.vis_words / 4; i += 32) __stcg(v4 + i, z);
+      }
     }
     __threadfence();
     __syncwarp();
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     uint32_t r_len = 0, first_unexp = 0, n_ties = 0, aq_len = 0;
     uint64_t n_hop = 0, n_edge = 0, n_dist = 0, n_adc = 0, n_rerank = 0;
     const float* lut = nullptr;
-    if (MODE != 0) {
+    if (MODE != 0 && !(ADC && a.phase == 2)) {
       const float* g = a.luts + (size_t)qi * a.pq_m * a.pq_ksub;
       if (a.lut_smem_floats) {
         for (uint32_t i = lane; i < a.lut_smem_floats; i += 32) lut_smem[i] = __ldg(g + i);
@@ -261,30 +263,33 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       if (a.metric == ISL_METRIC_COSINE) {  // 4-byte async gathers: land long before the group is admitted
         for (uint32_t i = lane; i < total; i += 32)
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(u_nb + i)),
-                       "l"(a.sqnorms + u_list[i]));
+                       "l"(a.sqnorms + (a.row_of_id ? __ldg(a.row_of_id + u_list[i]) : u_list[i])));
         cp_async_commit();
       }
-      stream_rows_fold<ACC, STAGES>(ring, a.vectors, a.ld, a.d, u_list, total, q_smem, admit_group);
+      stream_rows_fold<ACC, STAGES>(ring, a.vectors, a.ld, a.d, u_list, total, q_smem, admit_group, a.row_of_id);
     };
 
+    const bool traverse = !(ADC && a.phase == 2);
     // ---- entry point (leann.rs:911-916; per query for the HNSW layer searches, hnsw.rs:501) ----
     const uint32_t entry = a.entries ? __ldg(a.entries + (a.query_ids ? __ldg(a.query_ids + qi) : qi)) : a.entry;
-    if (lane == 0) {
-      u_list[0] = entry;
-      atomicOr(vis + (entry >> 5), 1u << (entry & 31));
-    }
-    __syncwarp();
-    if (ADC) {
-      const float d0 = adc_of(entry);
-      admit_values(1, d0, entry);
-      n_adc = 1;
-    } else {
-      score_and_admit(1);
-      n_dist = 1;
+    if (traverse) {
+      if (lane == 0) {
+        u_list[0] = entry;
+        atomicOr(vis + (entry >> 5), 1u << (entry & 31));
+      }
+      __syncwarp();
+      if (ADC) {
+        const float d0 = adc_of(entry);
+        admit_values(1, d0, entry);
+        n_adc = 1;
+      } else {
+        score_and_admit(1);
+        n_dist = 1;
+      }
     }
 
     // ---- main loop (leann.rs:922-972) ------------------------------------------------------
-    for (;;) {
+    for (; traverse;) {
       uint32_t cur;
       if (first_unexp < r_len) {
         uint2 e = R.ld(first_unexp);
@@ -460,12 +465,35 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       score_and_admit(promote);
     }
 
+    if (ADC && a.phase == 1) {
+      // traversal-only launch: hand the ef survivors (ascending adc order) to the recompute step
+      for (uint32_t i = lane; i < r_len; i += 32) a.surv_ids[(size_t)qi * ef + i] = R.ld(i).y & ~kExpandedBit;
+      if (lane == 0) {
+        a.surv_cnt[qi] = r_len;
+        if (a.stats) {
+          isl_search_stats s;
+          s.n_hop = n_hop;
+          s.n_edge = n_edge;
+          s.n_dist = 0;
+          s.n_adc = n_adc;
+          s.n_rerank = 0;
+          a.stats[qi] = s;
+        }
+      }
+      __syncwarp();
+      continue;
+    }
     if (ADC) {
       // exact rerank of the ef survivors: their ids move to u_list, R is rebuilt from the exact
       // distances (capacity ef >= their number, so every one is admitted) and ends up sorted by
       // (dist, id).
-      const uint32_t total = r_len;
-      for (uint32_t i = lane; i < total; i += 32) u_list[i] = R.ld(i).y & ~kExpandedBit;
+      uint32_t total = r_len;
+      if (a.phase == 2) {
+        total = __ldg(a.surv_cnt + qi);
+        for (uint32_t i = lane; i < total; i += 32) u_list[i] = __ldg(a.surv_ids + (size_t)qi * ef + i);
+      } else {
+        for (uint32_t i = lane; i < total; i += 32) u_list[i] = R.ld(i).y & ~kExpandedBit;
+      }
       __syncwarp();
       r_len = 0;
       first_unexp = 0;
@@ -493,13 +521,18 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     if (lane == 0) {
       if (a.out_count) a.out_count[qi] = cnt;
       if (a.stats) {
-        isl_search_stats s;
-        s.n_hop = n_hop;
-        s.n_edge = n_edge;
-        s.n_dist = n_dist;
-        s.n_adc = n_adc;
-        s.n_rerank = n_rerank;
-        a.stats[qi] = s;
+        if (ADC && a.phase == 2) {  // the traversal launch wrote the other counters
+          a.stats[qi].n_dist = n_dist;
+          a.stats[qi].n_rerank = n_rerank;
+        } else {
+          isl_search_stats s;
+          s.n_hop = n_hop;
+          s.n_edge = n_edge;
+          s.n_dist = n_dist;
+          s.n_adc = n_adc;
+          s.n_rerank = n_rerank;
+          a.stats[qi] = s;
+        }
       }
     }
     __syncwarp();
