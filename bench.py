@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--ef", type=int, default=0, help="0 = smallest ef of the ladder with recall@10 >= 0.95")
     ap.add_argument("--build-batch", type=int, default=4096)
     ap.add_argument("--no-uniform", action="store_true", help="skip the secondary uniform-data measurement")
+    ap.add_argument("--no-encoder", action="store_true", help="skip the secondary recompute-encoder measurement")
     ap.add_argument("--no-adc", action="store_true", help="skip the secondary PQ ADC traversal + exact rerank measurement")
     ap.add_argument("--pq-m", type=int, default=32, help="subquantizers of the ADC secondary (ksub = 256)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline sample")
@@ -422,6 +423,38 @@ def main():
                                   "n_adc": float(st.n_adc.mean()), "n_rerank": float(st.n_rerank.mean()),
                                   "note": "parity unpinned: no reference implementation of this mode exists (leann.rs:54-56)"}
         del xh
+
+        # secondary: the recompute encoder (BASELINE configs[4]: random-init 110M bf16 encoder, the only
+        # tensor-core row) — one batch of frontier nodes through the tcgen05 encoder.
+        if not a.no_encoder:
+            from islands_b200 import Encoder, EncoderConfig
+
+            enc = Encoder(EncoderConfig()).init_random(seed=46, stddev=0.02)
+            eb, es = 2048, 64
+            gtok = torch.Generator(device=dev)
+            gtok.manual_seed(45)
+            tok = torch.randint(1, 30000, (eb, es), generator=gtok, device=dev, dtype=torch.int32)
+            eln = torch.full((eb,), es, device=dev, dtype=torch.int32)
+            eout = torch.empty((eb, 768), device=dev)
+            torch.cuda.synchronize()
+            ems = []
+            for it in range(5):
+                enc.embed_dev(tok.data_ptr(), eln.data_ptr(), eb, es, eout.data_ptr())
+                if it >= 2:
+                    ems.append(enc.last_timing())
+            ms_e = float(np.mean([m for m, _ in ems]))
+            fl = ems[0][1]
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    tpeak = float(json.load(f)["bf16_tflops_sustained"])
+            except Exception:
+                tpeak = 1400.0
+            line["recompute_encoder"] = {"shape": "BERT-base 110M random init, bf16 tcgen05 GEMMs, f32 accumulate", "batch": eb, "seq_len": es,
+                                         "ms": ms_e, "sequences_per_s": eb / ms_e * 1e3, "tflops": fl / ms_e / 1e9,
+                                         "roofline": {"bound": "tensor", "achieved": fl / ms_e / 1e9, "peak": tpeak, "unit": "TFLOP/s",
+                                                      "frac": fl / ms_e / 1e9 / tpeak, "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"}}
+            del enc, tok, eout
+            torch.cuda.empty_cache()
 
         # secondary: the reference benches' own distribution (uniform), reported beside the headline
         if a.dataset != "uniform" and not a.no_uniform:

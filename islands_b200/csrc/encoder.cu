@@ -12,6 +12,7 @@
 // pooling are CUDA-core kernels bound by HBM.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -46,6 +47,11 @@ struct isl_encoder {
 };
 
 namespace isl {
+// ISL_GEMM_SINGLE_CTA=1 keeps every GEMM on the single-CTA kernel (A/B comparison in profiles/).
+static const bool g_disable_pair = [] {
+  const char* e = std::getenv("ISL_GEMM_SINGLE_CTA");
+  return e && e[0] == '1';
+}();
 namespace {
 
 // ---- parameter layout ------------------------------------------------------------------------
@@ -430,6 +436,18 @@ isl_status launch_gemm_bn(const CUtensorMap& ma, const CUtensorMap& mb, const ge
   return ISL_OK;
 }
 
+isl_status launch_gemm_pair(const CUtensorMap& ma, const CUtensorMap& mb, const gemm::Params& p, int sms, cudaStream_t st) {
+  auto kern = gemm::gemm_bf16_tcgen05_pair_kernel;
+  const size_t smem = gemm::pair_smem_bytes();
+  ISL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles = ((p.M + 2 * gemm::BM - 1) / (2 * gemm::BM)) * (p.N / gemm::PAIR_BN);
+  const int clusters = std::max(1, std::min(tiles, sms / 2));
+  kern<<<2 * clusters, gemm::THREADS, smem, st>>>(ma, mb, p);  // __cluster_dims__(2,1,1)
+  count_launch();
+  ISL_CUDA_TRY(cudaGetLastError());
+  return ISL_OK;
+}
+
 }  // namespace
 
 // out = act(A[M][K] * W[N][K]^T + bias) (+ residual); A, W bf16 on the device (16-byte aligned rows).
@@ -442,6 +460,11 @@ isl_status launch_gemm_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, int 
   const int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
   CUtensorMap ma, mb;
   ISL_TRY(make_map(A, (uint64_t)M, (uint64_t)K, gemm::BM, &ma));
+  if (bn == 256 && M > gemm::BM && !g_disable_pair) {  // CTA pairs: 256 x 256 tiles, half of B per CTA
+    ISL_TRY(make_map(W, (uint64_t)N, (uint64_t)K, (uint32_t)gemm::PAIR_BN / 2, &mb));
+    gemm::Params pp{M, N, K, bias, residual, out_bf16, out_f32, epilogue};
+    return launch_gemm_pair(ma, mb, pp, sms, st);
+  }
   ISL_TRY(make_map(W, (uint64_t)N, (uint64_t)K, (uint32_t)bn, &mb));
   gemm::Params p{M, N, K, bias, residual, out_bf16, out_f32, epilogue};
   if (bn == 256) return launch_gemm_bn<256>(ma, mb, p, sms, st);
