@@ -52,6 +52,11 @@ static const bool g_disable_pair = [] {
   const char* e = std::getenv("ISL_GEMM_SINGLE_CTA");
   return e && e[0] == '1';
 }();
+// ISL_ATTENTION_CUDA_CORES=1 keeps attention on the register-blocked CUDA-core kernel (A/B comparison).
+static const bool g_attention_cuda_cores = [] {
+  const char* e = std::getenv("ISL_ATTENTION_CUDA_CORES");
+  return e && e[0] == '1';
+}();
 namespace {
 
 // ---- parameter layout ------------------------------------------------------------------------
@@ -365,6 +370,170 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restric
   }
 }
 
+// ---- attention on the (legacy) tensor path for S <= 128 ---------------------------------------------
+// QK^T and PV are 1 % of the encoder's FLOPs but cost a third of its time on the CUDA cores, so for
+// the sequence lengths of code chunks they run as mma.sync.m16n8k16 (bf16 in, f32 accumulate):
+// one CTA per (sequence, head), K / V / Q tiles in shared memory (row stride 72 bf16: conflict-free
+// ldmatrix), one warp per 16 query rows, scores and probabilities stay in registers (the m16n8
+// accumulator layout IS the A-fragment layout of the next MMA), V fragments via ldmatrix.trans.
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+constexpr uint32_t kAttLd = 72;  // bf16 elements per shared-memory row (144 bytes)
+
+template <int SMAX>
+__global__ void __launch_bounds__(128)
+attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ lengths, uint32_t S, uint32_t H,
+                     __nv_bfloat16* __restrict__ ctx) {
+  extern __shared__ __align__(16) unsigned char att_raw[];
+  const uint32_t b = blockIdx.x, h = blockIdx.y;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t len = min((uint32_t)max(lengths[b], 0), S);
+  const uint32_t S16 = (S + 15) & ~15u;
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(att_raw);  // [S16][72]
+  __nv_bfloat16* Vs = Ks + (size_t)S16 * kAttLd;                  // [S16][72]
+  __nv_bfloat16* Qw = Vs + (size_t)S16 * kAttLd + (size_t)warp * 16 * kAttLd;  // per warp [16][72]
+  const size_t row_stride = 3 * (size_t)H;
+  const __nv_bfloat16* base = qkv + (size_t)b * S * row_stride + h * 64;
+  __nv_bfloat16* out_base = ctx + (size_t)b * S * H + h * 64;
+  if (len == 0) {  // nothing attends: every row is padding
+    for (uint32_t i = threadIdx.x; i < S * 8; i += blockDim.x)
+      *reinterpret_cast<uint4*>(out_base + (size_t)(i >> 3) * H + (i & 7) * 8) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const uint32_t kend = (len + 15) & ~15u;  // keys beyond are never touched; [len, kend) are masked
+  for (uint32_t i = threadIdx.x; i < kend * 8; i += blockDim.x) {
+    const uint32_t j = i >> 3, pc = (i & 7) * 8;
+    uint4 k4 = make_uint4(0, 0, 0, 0), v4 = make_uint4(0, 0, 0, 0);
+    if (j < S) {
+      k4 = __ldg(reinterpret_cast<const uint4*>(base + j * row_stride + H + pc));
+      v4 = __ldg(reinterpret_cast<const uint4*>(base + j * row_stride + 2 * H + pc));
+    }
+    *reinterpret_cast<uint4*>(Ks + j * kAttLd + pc) = k4;
+    *reinterpret_cast<uint4*>(Vs + j * kAttLd + pc) = v4;
+  }
+  __syncthreads();
+  const uint32_t g = lane >> 2, t = lane & 3;
+  for (uint32_t i0 = warp * 16; i0 < S; i0 += 64) {
+    if (i0 >= len) {  // a tile of padded query rows
+      for (uint32_t i = lane; i < 16 * 8; i += 32)
+        if (i0 + (i >> 3) < S)
+          *reinterpret_cast<uint4*>(out_base + (size_t)(i0 + (i >> 3)) * H + (i & 7) * 8) = make_uint4(0, 0, 0, 0);
+      continue;
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < 16 * 8; i += 32) {
+      const uint32_t r = i >> 3, pc = (i & 7) * 8;
+      uint4 q4 = make_uint4(0, 0, 0, 0);
+      if (i0 + r < S) q4 = __ldg(reinterpret_cast<const uint4*>(base + (i0 + r) * row_stride + pc));
+      *reinterpret_cast<uint4*>(Qw + r * kAttLd + pc) = q4;
+    }
+    __syncwarp();
+    uint32_t qa[4][4];
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc)
+      ldsm_x4(smem_u32(Qw + (lane & 15) * kAttLd + kc * 16 + (lane >> 4) * 8), qa[kc][0], qa[kc][1], qa[kc][2], qa[kc][3]);
+    float sc[SMAX / 8][4];
+#pragma unroll
+    for (int nb = 0; nb < SMAX / 8; ++nb) {
+      sc[nb][0] = sc[nb][1] = sc[nb][2] = sc[nb][3] = 0.0f;
+      if ((uint32_t)nb * 8 < kend) {
+#pragma unroll
+        for (int kc2 = 0; kc2 < 2; ++kc2) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4(smem_u32(Ks + (nb * 8 + (lane & 7)) * kAttLd + kc2 * 32 + (lane >> 3) * 8), b0, b1, b2, b3);
+          mma_bf16_16816(sc[nb], qa[kc2 * 2][0], qa[kc2 * 2][1], qa[kc2 * 2][2], qa[kc2 * 2][3], b0, b1);
+          mma_bf16_16816(sc[nb], qa[kc2 * 2 + 1][0], qa[kc2 * 2 + 1][1], qa[kc2 * 2 + 1][2], qa[kc2 * 2 + 1][3], b2, b3);
+        }
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nb = 0; nb < SMAX / 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool live = (uint32_t)(nb * 8 + 2 * t + e) < len;
+        sc[nb][e] = live ? sc[nb][e] : -INFINITY;
+        sc[nb][2 + e] = live ? sc[nb][2 + e] : -INFINITY;
+        mx0 = fmaxf(mx0, sc[nb][e]);
+        mx1 = fmaxf(mx1, sc[nb][2 + e]);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float den0 = 0.0f, den1 = 0.0f;
+#pragma unroll
+    for (int nb = 0; nb < SMAX / 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        sc[nb][e] = __expf(0.125f * (sc[nb][e] - mx0));  // 1 / sqrt(64); exp(-inf) = 0 for masked keys
+        sc[nb][2 + e] = __expf(0.125f * (sc[nb][2 + e] - mx1));
+        den0 += sc[nb][e];
+        den1 += sc[nb][2 + e];
+      }
+    }
+    den0 += __shfl_xor_sync(0xffffffffu, den0, 1);
+    den0 += __shfl_xor_sync(0xffffffffu, den0, 2);
+    den1 += __shfl_xor_sync(0xffffffffu, den1, 1);
+    den1 += __shfl_xor_sync(0xffffffffu, den1, 2);
+    float o[8][4];
+#pragma unroll
+    for (int db = 0; db < 8; ++db) o[db][0] = o[db][1] = o[db][2] = o[db][3] = 0.0f;
+#pragma unroll
+    for (int kc = 0; kc < SMAX / 16; ++kc) {
+      if ((uint32_t)kc * 16 < kend) {
+        const uint32_t a0 = pack_bf16(sc[2 * kc][0], sc[2 * kc][1]);
+        const uint32_t a1 = pack_bf16(sc[2 * kc][2], sc[2 * kc][3]);
+        const uint32_t a2 = pack_bf16(sc[2 * kc + 1][0], sc[2 * kc + 1][1]);
+        const uint32_t a3 = pack_bf16(sc[2 * kc + 1][2], sc[2 * kc + 1][3]);
+#pragma unroll
+        for (int d2 = 0; d2 < 4; ++d2) {
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_trans(smem_u32(Vs + (kc * 16 + (lane & 15)) * kAttLd + d2 * 16 + (lane >> 4) * 8), b0, b1, b2, b3);
+          mma_bf16_16816(o[2 * d2], a0, a1, a2, a3, b0, b1);
+          mma_bf16_16816(o[2 * d2 + 1], a0, a1, a2, a3, b2, b3);
+        }
+      }
+    }
+    const float inv0 = 1.0f / den0, inv1 = 1.0f / den1;
+    __syncwarp();
+#pragma unroll
+    for (int db = 0; db < 8; ++db) {
+      *reinterpret_cast<uint32_t*>(Qw + g * kAttLd + db * 8 + 2 * t) = pack_bf16(o[db][0] * inv0, o[db][1] * inv0);
+      *reinterpret_cast<uint32_t*>(Qw + (g + 8) * kAttLd + db * 8 + 2 * t) = pack_bf16(o[db][2] * inv1, o[db][3] * inv1);
+    }
+    __syncwarp();
+    for (uint32_t i = lane; i < 16 * 8; i += 32) {
+      const uint32_t r = i >> 3, pc = (i & 7) * 8;
+      if (i0 + r >= S) continue;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (i0 + r < len) v = *reinterpret_cast<const uint4*>(Qw + r * kAttLd + pc);
+      *reinterpret_cast<uint4*>(out_base + (size_t)(i0 + r) * H + pc) = v;
+    }
+  }
+}
+
 // Masked mean pooling (candle_provider.rs:438-474) and optional L2 normalisation (:477-494).
 __global__ void __launch_bounds__(256)
 pool_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ lengths, uint32_t S, uint32_t H,
@@ -526,8 +695,19 @@ isl_status forward_device(isl_encoder* e, const int32_t* d_tokens, const int32_t
     const __nv_bfloat16* gw = e->wbf16.p + (size_t)layer * l.g_per_layer;
     ISL_TRY(launch_gemm_bf16(e->x.p, gw + l.g_qkv, (int)T, (int)(3 * H), (int)H, lp + l.qkv_b, nullptr, gemm::EPI_NONE,
                              e->qkv.p, nullptr, e->sms, st));
-    attention_kernel<<<dim3((uint32_t)seqs, e->cfg.num_heads), 128, att_smem, st>>>(e->qkv.p, d_lengths, (uint32_t)S, H,
-                                                                                   e->ctx.p);
+    if (S <= 128 && !g_attention_cuda_cores) {
+      const size_t S16 = (S + 15) & ~(size_t)15;
+      const size_t mma_smem = (2 * S16 + 4 * 16) * kAttLd * sizeof(__nv_bfloat16);
+      if (S <= 64)
+        attention_mma_kernel<64><<<dim3((uint32_t)seqs, e->cfg.num_heads), 128, mma_smem, st>>>(e->qkv.p, d_lengths, (uint32_t)S,
+                                                                                               H, e->ctx.p);
+      else
+        attention_mma_kernel<128><<<dim3((uint32_t)seqs, e->cfg.num_heads), 128, mma_smem, st>>>(e->qkv.p, d_lengths, (uint32_t)S,
+                                                                                                H, e->ctx.p);
+    } else {
+      attention_kernel<<<dim3((uint32_t)seqs, e->cfg.num_heads), 128, att_smem, st>>>(e->qkv.p, d_lengths, (uint32_t)S, H,
+                                                                                     e->ctx.p);
+    }
     count_launch();
     ISL_TRY(launch_gemm_bf16(e->ctx.p, gw + l.g_ao, (int)T, (int)H, (int)H, lp + l.ao_b, e->x.p, gemm::EPI_NONE, e->y.p,
                              nullptr, e->sms, st));
