@@ -46,8 +46,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                : "memory");
 }
 
+// log2(floats per slice): CH floats for a full group, doubling as the group thins out (at most 8x)
+template <int CH>
 __device__ __forceinline__ uint32_t group_slice_shift(uint32_t cnt) {
-  return cnt > 16 ? 6u : (cnt > 8 ? 7u : (cnt > 4 ? 8u : 9u));  // log2(floats per slice)
+  constexpr uint32_t B = CH == 64 ? 6u : (CH == 128 ? 7u : 8u);
+  return cnt > 16 ? B : (cnt > 8 ? B + 1 : (cnt > 4 ? B + 2 : B + 3));
 }
 
 template <int STAGES>
@@ -61,12 +64,12 @@ struct RowRing {
 
 // Folds rows row_ids[0 .. total) against the query in shared memory and calls
 // on_group(base, cnt, acc) after each group of <= 32 rows (acc = the lane's folded accumulator).
-template <int ACC, int STAGES, class OnGroup>
+template <int ACC, int STAGES, int CH = 64, class OnGroup>
 __device__ __forceinline__ void stream_rows_fold(RowRing<STAGES>& ring, const float* __restrict__ vectors, uint32_t ld,
                                                  uint32_t d, const uint32_t* row_ids, uint32_t total,
                                                  const float* q_smem, OnGroup&& on_group,
                                                  const uint32_t* __restrict__ row_of_id = nullptr) {
-  using G = StageGeom<64>;
+  using G = StageGeom<CH>;
   const uint32_t lane = lane_id();
   const uint32_t ngroups = (total + 31) >> 5;
   uint32_t ig = 0, ic = 0;                 // next slice to issue: group, chunk
@@ -75,7 +78,7 @@ __device__ __forceinline__ void stream_rows_fold(RowRing<STAGES>& ring, const fl
   auto load_issue_group = [&]() {
     if (ig < ngroups) {
       icnt = min(32u, total - (ig << 5));
-      ish = group_slice_shift(icnt);
+      ish = group_slice_shift<CH>(icnt);
       my_row = nullptr;
       if (lane < icnt) {
         const uint32_t id = row_ids[(ig << 5) + lane];
@@ -104,7 +107,7 @@ __device__ __forceinline__ void stream_rows_fold(RowRing<STAGES>& ring, const fl
   for (int s = 0; s < STAGES - 1; ++s) issue_next();
   for (uint32_t g = 0; g < ngroups; ++g) {
     const uint32_t cnt = min(32u, total - (g << 5));
-    const uint32_t sh = group_slice_shift(cnt);
+    const uint32_t sh = group_slice_shift<CH>(cnt);
     const uint32_t stride = (1u << sh) + 4;
     const uint32_t nch = (d + (1u << sh) - 1) >> sh;
     float acc = 0.0f;
@@ -117,9 +120,9 @@ __device__ __forceinline__ void stream_rows_fold(RowRing<STAGES>& ring, const fl
         const uint32_t len = min(1u << sh, d - col0);
         const float4* row = reinterpret_cast<const float4*>(ring.stage + ring.cslot * G::STAGE_FLOATS + lane * stride);
         const float4* qq = reinterpret_cast<const float4*>(q_smem + col0);
-        if (len == 64) {
+        if (len == CH) {
 #pragma unroll
-          for (int v = 0; v < 16; ++v) {
+          for (int v = 0; v < CH / 4; ++v) {
             const float4 y = row[v];
             const float4 x = qq[v];
             acc = acc_step<ACC>(acc, x.x, y.x);

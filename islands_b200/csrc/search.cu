@@ -8,7 +8,10 @@
 namespace isl {
 
 namespace {
-constexpr int kCH = 64;
+#ifndef ISL_CH
+#define ISL_CH 128
+#endif
+constexpr int kCH = ISL_CH;  // floats per row slice of a full group (row_stream.cuh)
 #ifndef ISL_STAGES
 #define ISL_STAGES 1
 #endif

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
                        "l"(a.sqnorms + (a.row_of_id ? __ldg(a.row_of_id + u_list[i]) : u_list[i])));
         cp_async_commit();
       }
-      stream_rows_fold<ACC, STAGES>(ring, a.vectors, a.ld, a.d, u_list, total, q_smem, admit_group, a.row_of_id);
+      stream_rows_fold<ACC, STAGES, CH>(ring, a.vectors, a.ld, a.d, u_list, total, q_smem, admit_group, a.row_of_id);
     };
 
     const bool traverse = !(ADC && a.phase == 2);
