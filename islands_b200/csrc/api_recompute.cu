@@ -104,13 +104,15 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
   const uint32_t lut_floats = m * pq->ksub;
   const uint32_t n = (uint32_t)idx->n;
   const uint32_t maxdeg = std::max<uint32_t>(idx->max_degree, 1);
-  const uint32_t u_cap = std::max<uint32_t>(std::max<uint32_t>(32, round_up(maxdeg + 1, 32)), round_up(ef, 32));
-  SearchPlan plan;
-  ISL_TRY(plan_search_adc(idx->cfg.metric, idx->ld, ef, u_cap, m, pq->ksub, idx->sms, &plan));
+  const uint32_t u_cap_t = std::max<uint32_t>(32, round_up(maxdeg + 1, 32));
+  const uint32_t u_cap_r = std::max<uint32_t>(32, round_up(ef, 32));
+  SearchPlan plan, plan_r;  // lean traversal (MODE 3) and rerank (MODE 2 / phase 2)
+  ISL_TRY(plan_search_adc_traverse(ef, u_cap_t, m, pq->ksub, idx->sms, &plan));
+  ISL_TRY(plan_search_rerank(idx->cfg.metric, idx->ld, ef, u_cap_r, idx->sms, &plan_r));
   const uint32_t vis_words = round_up((uint32_t)((idx->n + 31) / 32), 4);
-  const uint32_t slots = (uint32_t)std::min<uint64_t>(plan.grid, nq);
+  const uint32_t slots = (uint32_t)std::min<uint64_t>(std::max(plan.grid, plan_r.grid), nq);
   ISL_TRY(ensure(idx->visited, (size_t)slots * vis_words));
-  if (!plan.r_in_smem) ISL_TRY(ensure(idx->r_global, (size_t)slots * ef));
+  if (!plan.r_in_smem || !plan_r.r_in_smem) ISL_TRY(ensure(idx->r_global, (size_t)slots * ef));
   ISL_TRY(ensure(idx->aux_f32, (size_t)nq * lut_floats + 2));
   ISL_TRY(ensure(idx->q_stage, nq * idx->ld));
   ISL_TRY(ensure(idx->out_ids, nq * k));
@@ -147,7 +149,7 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
   a.visited = idx->visited.p;
   a.vis_words = vis_words;
   a.r_global = idx->r_global.p;
-  a.u_cap = u_cap;
+  a.u_cap = u_cap_t;
   a.out_ids = idx->out_ids.p;
   a.out_dist = idx->out_dist.p;
   a.out_count = idx->out_count.p;
@@ -201,8 +203,10 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
   a.sqnorms = idx->rc_sq.p;
   a.row_of_id = idx->rc_rows.p;
   a.phase = 2;
+  a.u_cap = u_cap_r;
+  a.lut_smem_floats = 0;
   ISL_CUDA_TRY(cudaEventRecord(idx->ev0, st));
-  ISL_TRY(launch_search(plan, a, st));
+  ISL_TRY(launch_search(plan_r, a, st));
   ISL_CUDA_TRY(cudaEventRecord(idx->ev1, st));
   idx->last_launches = 3;
 

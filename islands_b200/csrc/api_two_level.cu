@@ -59,6 +59,84 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
   const uint32_t m = (uint32_t)pq->cfg.num_subquantizers;
   const uint32_t lut_floats = m * pq->ksub;
 
+  if (mode == 2) {
+    // Two launches: the lean ADC traversal (MODE 3: no staging ring or query vector in shared memory,
+    // result array in registers up to ef = 256) hands its ef survivors to the exact rerank (MODE 2,
+    // phase 2).  Each half gets the occupancy its own shared-memory footprint allows.
+    const uint32_t maxdeg2 = std::max<uint32_t>(idx->max_degree, 1);
+    const uint32_t u_cap_t = std::max<uint32_t>(32, round_up(maxdeg2 + 1, 32));
+    const uint32_t u_cap_r = std::max<uint32_t>(32, round_up(ef, 32));
+    SearchPlan pt, pr;
+    ISL_TRY(plan_search_adc_traverse(ef, u_cap_t, m, pq->ksub, idx->sms, &pt));
+    ISL_TRY(plan_search_rerank(idx->cfg.metric, idx->ld, ef, u_cap_r, idx->sms, &pr));
+    const uint32_t vis_words2 = round_up((uint32_t)((idx->n + 31) / 32), 4);
+    const uint32_t slots_t = (uint32_t)std::min<uint64_t>(pt.grid, nq), slots_r = (uint32_t)std::min<uint64_t>(pr.grid, nq);
+    ISL_TRY(ensure(idx->visited, (size_t)slots_t * vis_words2));
+    if (!pt.r_in_smem || !pr.r_in_smem) ISL_TRY(ensure(idx->r_global, (size_t)std::max(slots_t, slots_r) * ef));
+    ISL_TRY(ensure(idx->aux_f32, (size_t)nq * lut_floats + 2));
+    ISL_TRY(ensure(idx->q_stage, nq * idx->ld));
+    ISL_TRY(ensure(idx->out_ids, nq * k));
+    ISL_TRY(ensure(idx->out_dist, nq * k));
+    ISL_TRY(ensure(idx->out_count, nq));
+    ISL_TRY(ensure(idx->out_stats, nq));
+    ISL_TRY(ensure(idx->rc_surv, nq * (size_t)ef));
+    ISL_TRY(ensure(idx->rc_surv_cnt, nq));
+    cudaStream_t st = idx->stream;
+    if (idx->ld != idx->dim) ISL_CUDA_TRY(cudaMemsetAsync(idx->q_stage.p, 0, nq * idx->ld * 4, st));
+    ISL_CUDA_TRY(cudaMemcpy2DAsync(idx->q_stage.p, (size_t)idx->ld * 4, queries, (size_t)idx->dim * 4,
+                                   (size_t)idx->dim * 4, nq, cudaMemcpyHostToDevice, st));
+    ISL_CUDA_TRY(cudaMemsetAsync(idx->counters.p, 0, 4 * sizeof(unsigned int), st));
+    ISL_CUDA_TRY(cudaEventRecord(idx->ev0, st));
+    ISL_TRY(launch_pq_tables(pq->dev(), idx->q_stage.p, idx->ld, nq, idx->aux_f32.p, idx->sms, st));
+    SearchArgs a{};
+    a.vectors = idx->vectors.p;
+    a.sqnorms = idx->sqnorms.p;
+    a.ld = idx->ld;
+    a.d = idx->dim;
+    a.n = (uint32_t)idx->n;
+    search_args_set_graph(idx, &a);
+    a.queries = idx->q_stage.p;
+    a.q_ld = idx->ld;
+    a.nq = (uint32_t)nq;
+    a.entry = (uint32_t)idx->entry;
+    a.k = k;
+    a.ef = ef;
+    a.metric = idx->cfg.metric;
+    a.visited = idx->visited.p;
+    a.vis_words = vis_words2;
+    a.r_global = idx->r_global.p;
+    a.u_cap = u_cap_t;
+    a.out_ids = idx->out_ids.p;
+    a.out_dist = idx->out_dist.p;
+    a.out_count = idx->out_count.p;
+    a.stats = idx->out_stats.p;
+    a.work_counter = idx->counters.p;
+    a.error_flag = idx->counters.p + 1;
+    a.luts = idx->aux_f32.p;
+    a.codes8 = idx->codes8.p;
+    a.codes16 = idx->codes8.p ? nullptr : idx->codes16.p;
+    a.pq_m = m;
+    a.pq_ksub = pq->ksub;
+    a.lut_smem_floats = pt.lut_smem_floats;
+    a.phase = 1;
+    a.surv_ids = idx->rc_surv.p;
+    a.surv_cnt = idx->rc_surv_cnt.p;
+    ISL_TRY(launch_search(pt, a, st));
+    ISL_CUDA_TRY(cudaMemsetAsync(idx->counters.p, 0, sizeof(unsigned int), st));  // work counter of the second launch
+    a.u_cap = u_cap_r;
+    a.lut_smem_floats = 0;
+    a.phase = 2;
+    ISL_TRY(launch_search(pr, a, st));
+    ISL_CUDA_TRY(cudaEventRecord(idx->ev1, st));
+    idx->last_launches = 3;
+    ISL_CUDA_TRY(cudaMemcpyAsync(out_ids, idx->out_ids.p, nq * k * 8, cudaMemcpyDeviceToHost, st));
+    ISL_CUDA_TRY(cudaMemcpyAsync(out_dist, idx->out_dist.p, nq * k * 4, cudaMemcpyDeviceToHost, st));
+    if (out_count) ISL_CUDA_TRY(cudaMemcpyAsync(out_count, idx->out_count.p, nq * 4, cudaMemcpyDeviceToHost, st));
+    if (stats)
+      ISL_CUDA_TRY(cudaMemcpyAsync(stats, idx->out_stats.p, nq * sizeof(isl_search_stats), cudaMemcpyDeviceToHost, st));
+    return search_finish(idx);
+  }
+
   // |AQ| <= max_degree / a at all times (it gains at most max_degree entries per expansion and
   // then loses ceil(a * |AQ|)); one spare entry per insertion batch keeps the bound simple.
   const uint32_t maxdeg = std::max<uint32_t>(idx->max_degree, 1);

@@ -48,6 +48,30 @@ isl_status launch_one(const SearchPlan& plan, const SearchArgs& args, uint32_t g
   return ISL_OK;
 }
 
+template <bool R_SMEM, int NR>
+isl_status plan_lean(uint32_t ef, uint32_t u_cap, int sms, SearchPlan* plan) {
+  auto kern = leann_search_kernel<ACC_DOT, kCH, kStages, R_SMEM, 3, NR>;
+  const size_t smem = search_smem_bytes<kCH, kStages>(0, (R_SMEM && NR == 0) ? ef : 0, u_cap, plan->lut_smem_floats, 0, true);
+  if (smem > 227 * 1024) return fail(ISL_INVALID_ARGUMENT, "search: ef needs more than 227 KB of shared memory per warp");
+  ISL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  ISL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+  if (per_sm < 1) return fail(ISL_CUDA_ERROR, "search: kernel does not fit on an SM");
+  plan->smem = smem;
+  plan->ctas_per_sm = per_sm;
+  plan->grid = (uint32_t)(per_sm * sms);
+  plan->r_in_smem = R_SMEM;
+  return ISL_OK;
+}
+
+template <bool R_SMEM, int NR>
+isl_status launch_lean(const SearchPlan& plan, const SearchArgs& args, uint32_t grid, cudaStream_t st) {
+  leann_search_kernel<ACC_DOT, kCH, kStages, R_SMEM, 3, NR><<<grid, 32, plan.smem, st>>>(args);
+  count_launch();
+  ISL_CUDA_TRY(cudaGetLastError());
+  return ISL_OK;
+}
+
 template <int TWO>
 isl_status plan_dispatch(int acc, bool r_smem, uint32_t ld, uint32_t ef, uint32_t u_cap, int sms, SearchPlan* plan) {
 #define ISL_PLAN(A)                                                                \
@@ -113,9 +137,46 @@ isl_status plan_search_adc(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_
   return plan_dispatch<2>(plan->acc, ef <= kEfSmemMax, ld, ef, u_cap, sms, plan);
 }
 
+isl_status plan_search_adc_traverse(uint32_t ef, uint32_t u_cap, uint32_t pq_m, uint32_t pq_ksub, int sms, SearchPlan* plan) {
+  plan->acc = ACC_DOT;
+  plan->two_level = true;
+  plan->mode = 3;
+  const uint32_t lut_floats = (pq_m * pq_ksub + 1u) & ~1u;
+  plan->lut_smem_floats = lut_floats <= kLutSmemMaxFloats ? lut_floats : 0;
+  plan->aq_cap = 0;
+  plan->aq_smem_entries = 0;
+  plan->nr = ef <= 64 ? 2 : (ef <= 128 ? 4 : (ef <= 192 ? 6 : (ef <= 256 ? 8 : 0)));
+  switch (plan->nr) {
+    case 2: return plan_lean<true, 2>(ef, u_cap, sms, plan);
+    case 4: return plan_lean<true, 4>(ef, u_cap, sms, plan);
+    case 6: return plan_lean<true, 6>(ef, u_cap, sms, plan);
+    case 8: return plan_lean<true, 8>(ef, u_cap, sms, plan);
+  }
+  return ef <= kEfSmemMax ? plan_lean<true, 0>(ef, u_cap, sms, plan) : plan_lean<false, 0>(ef, u_cap, sms, plan);
+}
+
+isl_status plan_search_rerank(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap, int sms, SearchPlan* plan) {
+  plan->acc = acc_kind_of_metric(metric);
+  plan->two_level = true;
+  plan->mode = 2;
+  plan->lut_smem_floats = 0;  // phase 2 never reads the PQ tables
+  plan->aq_cap = 0;
+  plan->aq_smem_entries = 0;
+  return plan_dispatch<2>(plan->acc, ef <= kEfSmemMax, ld, ef, u_cap, sms, plan);
+}
+
 isl_status launch_search(const SearchPlan& plan, const SearchArgs& args, cudaStream_t st) {
   // Never launch more warps than queries: idle slots would only clear their bitsets.
   const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(plan.grid, args.nq));
+  if (plan.mode == 3) {
+    switch (plan.nr) {
+      case 2: return launch_lean<true, 2>(plan, args, grid, st);
+      case 4: return launch_lean<true, 4>(plan, args, grid, st);
+      case 6: return launch_lean<true, 6>(plan, args, grid, st);
+      case 8: return launch_lean<true, 8>(plan, args, grid, st);
+    }
+    return plan.r_in_smem ? launch_lean<true, 0>(plan, args, grid, st) : launch_lean<false, 0>(plan, args, grid, st);
+  }
   if (plan.mode == 2) return launch_dispatch<2>(plan, args, grid, st);
   return plan.mode == 1 ? launch_dispatch<1>(plan, args, grid, st) : launch_dispatch<0>(plan, args, grid, st);
 }

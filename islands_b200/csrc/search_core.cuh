@@ -30,10 +30,11 @@ namespace isl {
 constexpr uint32_t kTieCap = 64;
 constexpr uint32_t kExpandedBit = 0x80000000u;
 
+// lean = the ADC-traversal-only kernel (MODE 3): no row staging ring, no query vector.
 template <int CH, int STAGES>
 __host__ __device__ constexpr size_t search_smem_bytes(uint32_t ld, uint32_t ef_smem, uint32_t u_cap,
-                                                       uint32_t lut_floats = 0, uint32_t aq_entries = 0) {
-  return (size_t)STAGES * StageGeom<CH>::STAGE_FLOATS * 4 + (size_t)ld * 4 + (size_t)ef_smem * 8 +
+                                                       uint32_t lut_floats = 0, uint32_t aq_entries = 0, bool lean = false) {
+  return (lean ? 0 : (size_t)STAGES * StageGeom<CH>::STAGE_FLOATS * 4 + (size_t)ld * 4) + (size_t)ef_smem * 8 +
          (size_t)u_cap * 8 + (size_t)kTieCap * 8 + (size_t)STAGES * 8 + (size_t)lut_floats * 4 +
          (size_t)aq_entries * 8;
 }
@@ -78,16 +79,25 @@ __device__ __forceinline__ uint32_t prune_keep(float prune_ratio, int strategy, 
 // table distances (same admission / termination rules with adc in place of the exact distance),
 // then the ef surviving candidates get their exact distance and are re-sorted by (dist, id).
 // Traversal traffic drops from 4d bytes to m bytes per visited node.
-template <int ACC, int CH, int STAGES, bool R_SMEM, int MODE>
+//
+// MODE 3 = the traversal half of MODE 2 as its own lean kernel (no staging ring, no query vector:
+// 2-3x the resident warps), survivors written out for a MODE 2 / phase 2 rerank launch.  With NR > 0
+// the result array R lives in REGISTERS, NR entries per lane (entry i = row i / 32 of lane i % 32):
+// insertion is a ballot-counted position plus one shuffle shift per row instead of a shared-memory
+// binary search and shift loop — the per-hop latency chain is what bounds the ADC traversal.
+template <int ACC, int CH, int STAGES, bool R_SMEM, int MODE, int NR = 0>
 __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
   constexpr bool TWO = MODE == 1;
-  constexpr bool ADC = MODE == 2;
+  constexpr bool ADC = MODE == 2 || MODE == 3;
+  constexpr bool LEAN = MODE == 3;
+  constexpr bool RREG = NR > 0;
+  constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using G = StageGeom<CH>;
   float* stage = reinterpret_cast<float*>(smem_raw);
-  float* q_smem = stage + STAGES * G::STAGE_FLOATS;
-  uint2* r_smem = reinterpret_cast<uint2*>(q_smem + a.ld);
-  uint32_t* u_list = reinterpret_cast<uint32_t*>(r_smem + (R_SMEM ? a.ef : 0));
+  float* q_smem = stage + (LEAN ? 0 : STAGES * G::STAGE_FLOATS);
+  uint2* r_smem = reinterpret_cast<uint2*>(q_smem + (LEAN ? 0 : a.ld));
+  uint32_t* u_list = reinterpret_cast<uint32_t*>(r_smem + ((R_SMEM && !RREG) ? a.ef : 0));
   float* u_nb = reinterpret_cast<float*>(u_list + a.u_cap);  // squared norms of the rows in u_list
   uint2* ties = reinterpret_cast<uint2*>(u_nb + a.u_cap);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ties + kTieCap);
@@ -109,6 +119,8 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
   uint32_t* vis = a.visited + (size_t)slot * a.vis_words;
   RView<R_SMEM> R{R_SMEM ? r_smem : a.r_global + (size_t)slot * a.ef};
   const uint32_t ef = a.ef;
+  float rk[RREG ? NR : 1];      // register-resident R: distances
+  uint32_t rid[RREG ? NR : 1];  //                      ids | expanded bit
 
   RowRing<STAGES> ring;
   ring.stage = stage;
@@ -131,10 +143,12 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     // ---- per-query setup -------------------------------------------------------------
     {
       // a query is either row qi of the query matrix or (construction) a row of the vector table
-      const float4* src = reinterpret_cast<const float4*>(
-          a.query_ids ? a.vectors + (size_t)__ldg(a.query_ids + qi) * a.ld : a.queries + (size_t)qi * a.q_ld);
-      float4* dst = reinterpret_cast<float4*>(q_smem);
-      for (uint32_t i = lane; i < a.ld / 4; i += 32) dst[i] = src[i];
+      if (!LEAN) {
+        const float4* src = reinterpret_cast<const float4*>(
+            a.query_ids ? a.vectors + (size_t)__ldg(a.query_ids + qi) * a.ld : a.queries + (size_t)qi * a.q_ld);
+        float4* dst = reinterpret_cast<float4*>(q_smem);
+        for (uint32_t i = lane; i < a.ld / 4; i += 32) dst[i] = src[i];
+      }
       if (!(ADC && a.phase == 2)) {  // the rerank-only launch never touches the visited set
         uint4* v4 = reinterpret_cast<uint4*>(vis);
         const uint4 z = make_uint4(0, 0, 0, 0);
@@ -143,9 +157,11 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     }
     __threadfence();
     __syncwarp();
-    const float na = (a.metric == ISL_METRIC_COSINE) ? smem_sqnorm_fold(q_smem, a.d) : 0.0f;
+    const float na = (!LEAN && a.metric == ISL_METRIC_COSINE) ? smem_sqnorm_fold(q_smem, a.d) : 0.0f;
 
     uint32_t r_len = 0, first_unexp = 0, n_ties = 0, aq_len = 0;
+    float wst_d = 0.0f;    // register R: the worst (last) entry, kept beside the rows
+    uint32_t wst_id = 0;
     uint64_t n_hop = 0, n_edge = 0, n_dist = 0, n_adc = 0, n_rerank = 0;
     const float* lut = nullptr;
     if (MODE != 0 && !(ADC && a.phase == 2)) {
@@ -159,40 +175,103 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       }
     }
 
-    // ---- sorted insert into R (lowers to: binary search, warp shift, store) -------------
-    auto r_insert = [&](float dnew, uint32_t idnew) {
-      uint32_t lo = 0, hi = r_len;  // first position whose key is not < new key
-      while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        const uint2 e = R.ld(mid);
-        if (key_lt(__uint_as_float(e.x), e.y & ~kExpandedBit, dnew, idnew))
-          lo = mid + 1;
-        else
-          hi = mid;
+    // ---- R access ---------------------------------------------------------------------------
+    auto r_get = [&](uint32_t i) __attribute__((always_inline)) -> uint2 {  // i is warp-uniform
+      if constexpr (!RREG) {
+        return R.ld(i);
+      } else {
+        // every row is shuffled and the wanted one selected afterwards: selecting the ROW first would be
+        // turned into dynamic indexing of rk[] / rid[] and push them out of the register file
+        float dd = 0.0f;
+        uint32_t ii = 0;
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+          const float sd = __shfl_sync(FULL, rk[j], i & 31);
+          const uint32_t si = __shfl_sync(FULL, rid[j], i & 31);
+          if ((i >> 5) == (uint32_t)j) {
+            dd = sd;
+            ii = si;
+          }
+        }
+        return make_uint2(__float_as_uint(dd), ii);
       }
-      const uint32_t pos = lo;
+    };
+    // ---- sorted insert into R ------------------------------------------------------------------
+    // shared/global R: binary search, warp shift, store.  register R: position = number of entries
+    // below the new key (one ballot per row), then every row shifts up by one lane (shfl_up, lane 0
+    // takes lane 31 of the row below) where index > position.
+    auto r_insert = [&](float dnew, uint32_t idnew) __attribute__((always_inline)) {
+      uint32_t pos;
       const bool full = (r_len == ef);
       uint2 evicted = make_uint2(0, 0);
-      if (full) evicted = R.ld(ef - 1);
-      const int top = full ? (int)ef - 1 : (int)r_len;
-      for (int t = top; t > (int)pos; t -= 32) {
-        const int i = t - (int)lane;
-        const bool act = i > (int)pos;
-        uint2 e = make_uint2(0, 0);
-        if (act) e = R.ld(i - 1);
-        __syncwarp();
-        if (act) R.st(i, e);
+      if constexpr (RREG) {
+        pos = 0;
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+          const uint32_t idx = j * 32 + lane;
+          const bool lt = idx < r_len && key_lt(rk[j], rid[j] & ~kExpandedBit, dnew, idnew);
+          pos += __popc(__ballot_sync(FULL, lt));
+        }
+        if (full) evicted = make_uint2(__float_as_uint(wst_d), wst_id);  // the current worst entry
+        const uint32_t top = full ? ef - 1 : r_len;
+#pragma unroll
+        for (int j = NR - 1; j >= 0; --j) {
+          float ud = __shfl_up_sync(FULL, rk[j], 1);
+          uint32_t ui = __shfl_up_sync(FULL, rid[j], 1);
+          if (j > 0) {
+            const float pd = __shfl_sync(FULL, rk[j > 0 ? j - 1 : 0], 31);
+            const uint32_t pi = __shfl_sync(FULL, rid[j > 0 ? j - 1 : 0], 31);
+            if (lane == 0) {
+              ud = pd;
+              ui = pi;
+            }
+          }
+          const uint32_t idx = j * 32 + lane;
+          if (idx > pos && idx <= top) {
+            rk[j] = ud;
+            rid[j] = ui;
+          }
+          if (idx == pos) {
+            rk[j] = dnew;
+            rid[j] = idnew;
+          }
+        }
+      } else {
+        uint32_t lo = 0, hi = r_len;  // first position whose key is not < new key
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          const uint2 e = R.ld(mid);
+          if (key_lt(__uint_as_float(e.x), e.y & ~kExpandedBit, dnew, idnew))
+            lo = mid + 1;
+          else
+            hi = mid;
+        }
+        pos = lo;
+        if (full) evicted = R.ld(ef - 1);
+        const int top = full ? (int)ef - 1 : (int)r_len;
+        for (int t = top; t > (int)pos; t -= 32) {
+          const int i = t - (int)lane;
+          const bool act = i > (int)pos;
+          uint2 e = make_uint2(0, 0);
+          if (act) e = R.ld(i - 1);
+          __syncwarp();
+          if (act) R.st(i, e);
+          __syncwarp();
+        }
+        if (lane == 0) R.st(pos, make_uint2(__float_as_uint(dnew), idnew));
         __syncwarp();
       }
-      if (lane == 0) R.st(pos, make_uint2(__float_as_uint(dnew), idnew));
-      __syncwarp();
       if (!full) r_len++;
       if (pos <= first_unexp) first_unexp = pos;
+      if constexpr (RREG) {
+        const uint2 w = r_get(r_len - 1);
+        wst_d = __uint_as_float(w.x);
+        wst_id = w.y;
+      }
       if (full && !(evicted.y & kExpandedBit)) {
         // An evicted, unexpanded node stays expandable while its distance equals the worst
         // distance in R (leann.rs:924-928 uses a strict `>`).
-        const uint2 w = R.ld(ef - 1);
-        const float wd = __uint_as_float(w.x), edist = __uint_as_float(evicted.x);
+        const float wd = RREG ? wst_d : __uint_as_float(R.ld(ef - 1).x), edist = __uint_as_float(evicted.x);
         if (!of_lt(wd, edist)) {
           if (n_ties == kTieCap) {  // drop stale ties first
             uint32_t kept = 0;
@@ -221,17 +300,17 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     // ---- exact distances of u_list[0 .. total) and their sequential admission ----------------
     // Streaming and fold: row_stream.cuh.  Admission replays the reference's per-neighbour loop
     // (leann.rs:953-970) in list order over the lanes that can still be admitted.
-    auto admit_values = [&](uint32_t cnt, float dn, uint32_t cid) {
+    auto admit_values = [&](bool ok, float dn, uint32_t cid) __attribute__((always_inline)) {
       float worst = 0.0f;
-      if (r_len > 0) worst = __uint_as_float(R.ld(r_len - 1).x);
-      uint32_t mask = __ballot_sync(0xffffffffu, lane < cnt && (r_len < ef || dn < worst));
+      if (r_len > 0) worst = RREG ? wst_d : __uint_as_float(R.ld(r_len - 1).x);
+      uint32_t mask = __ballot_sync(0xffffffffu, ok && (r_len < ef || dn < worst));
       while (mask) {
         const int j = __ffs(mask) - 1;
         mask &= mask - 1;
         const float dj = __shfl_sync(0xffffffffu, dn, j);
         const uint32_t idj = __shfl_sync(0xffffffffu, cid, j);
         bool add = r_len < ef;
-        if (!add) add = dj < __uint_as_float(R.ld(ef - 1).x);  // raw f32 `<` (leann.rs:959)
+        if (!add) add = dj < (RREG ? wst_d : __uint_as_float(R.ld(ef - 1).x));  // raw f32 `<` (leann.rs:959)
         if (add) r_insert(dj, idj);
       }
     };
@@ -245,7 +324,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         const float nb = (a.metric == ISL_METRIC_COSINE) ? u_nb[base + lane] : 0.0f;
         dn = finalize_distance(a.metric, acc, na, nb);
       }
-      admit_values(cnt, dn, cid);
+      admit_values(lane < cnt, dn, cid);
     };
     // table_distance (pq.rs:341-348) of node `nid`: left fold over the subquantizers, then sqrt
     auto adc_of = [&](uint32_t nid) -> float {
@@ -280,7 +359,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       __syncwarp();
       if (ADC) {
         const float d0 = adc_of(entry);
-        admit_values(1, d0, entry);
+        admit_values(lane == 0, d0, entry);
         n_adc = 1;
       } else {
         score_and_admit(1);
@@ -292,26 +371,37 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     for (; traverse;) {
       uint32_t cur;
       if (first_unexp < r_len) {
-        uint2 e = R.ld(first_unexp);
+        const uint2 e = r_get(first_unexp);
         cur = e.y;
-        __syncwarp();
-        if (lane == 0) R.st(first_unexp, make_uint2(e.x, e.y | kExpandedBit));
-        __syncwarp();
-        // advance to the next unexpanded entry
         uint32_t nxt = r_len;
-        for (uint32_t b = first_unexp + 1; b < r_len; b += 32) {
-          const uint32_t i = b + lane;
-          const bool un = i < r_len && !(R.ld(i).y & kExpandedBit);
-          const uint32_t bal = __ballot_sync(0xffffffffu, un);
-          if (bal) {
-            nxt = b + __ffs(bal) - 1;
-            break;
+        if constexpr (RREG) {
+#pragma unroll
+          for (int j = 0; j < NR; ++j) {
+            const uint32_t idx = j * 32 + lane;
+            if (idx == first_unexp) rid[j] |= kExpandedBit;
+            const bool un = idx > first_unexp && idx < r_len && !(rid[j] & kExpandedBit);
+            const uint32_t bal = __ballot_sync(FULL, un);
+            if (bal && nxt == r_len) nxt = j * 32 + __ffs(bal) - 1;
+          }
+        } else {
+          __syncwarp();
+          if (lane == 0) R.st(first_unexp, make_uint2(e.x, e.y | kExpandedBit));
+          __syncwarp();
+          // advance to the next unexpanded entry
+          for (uint32_t b = first_unexp + 1; b < r_len; b += 32) {
+            const uint32_t i = b + lane;
+            const bool un = i < r_len && !(R.ld(i).y & kExpandedBit);
+            const uint32_t bal = __ballot_sync(0xffffffffu, un);
+            if (bal) {
+              nxt = b + __ffs(bal) - 1;
+              break;
+            }
           }
         }
         first_unexp = nxt;
       } else {
         // smallest live tie, if any
-        const float wd = __uint_as_float(R.ld(r_len - 1).x);
+        const float wd = RREG ? wst_d : __uint_as_float(R.ld(r_len - 1).x);
         int best = -1;
         for (uint32_t i = 0; i < n_ties; ++i) {
           const uint2 t = ties[i];
@@ -350,15 +440,79 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         } else {
           deg = a.adj_stride;
           sentinel = true;
-          if (first_unexp < r_len && lane * 32 < a.adj_stride) {
-            const uint32_t nxt = R.ld(first_unexp).y & ~kExpandedBit;
-            const uint32_t* pf = a.nbrs + (size_t)nxt * a.adj_stride + lane * 32;
-            asm volatile("prefetch.global.L2 [%0];\n" ::"l"(pf));
+          if (first_unexp < r_len) {  // warp-uniform: r_get shuffles
+            const uint32_t nxt = r_get(first_unexp).y & ~kExpandedBit;
+            if (lane * 32 < a.adj_stride) {
+              const uint32_t* pf = a.nbrs + (size_t)nxt * a.adj_stride + lane * 32;
+              asm volatile("prefetch.global.L2 [%0];\n" ::"l"(pf));
+            }
           }
         }
       }
       n_hop++;
       if (!sentinel) n_edge += deg;
+
+      if (ADC && a.codes8 && (a.pq_m == 16 || a.pq_m == 32)) {
+        // ADC hop with every latency in flight at once: 64 list positions per pass (two per lane);
+        // their ids are loaded, then the visited-bit atomics AND the code rows of all positions are
+        // issued together (codes of already visited nodes are wasted bytes, ~15 %, but the test and
+        // the gather no longer wait for each other), then table distances, then admission in list
+        // order of the positions whose bit was clear.
+        const uint32_t nv = a.pq_m >> 4;  // 16-byte pieces per code row
+        for (uint32_t b = 0; b < deg; b += 64) {
+          uint32_t nid[2];
+          bool valid[2], chk[2];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const uint32_t i = b + r * 32 + lane;
+            nid[r] = i < deg ? __ldg(a.nbrs + start + i) : 0xffffffffu;
+          }
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            valid[r] = nid[r] != 0xffffffffu;
+            if (sentinel) n_edge += __popc(__ballot_sync(FULL, valid[r]));
+            const uint32_t same = __match_any_sync(FULL, nid[r]);
+            chk[r] = valid[r] && nid[r] < a.n && lane == (uint32_t)(__ffs(same) - 1);  // first of its value in this half
+          }
+          if (b + 32 < deg) {  // a value of the second half that already occurs in the first is not a first occurrence
+            for (uint32_t t = 0; t < 32; ++t) {
+              const uint32_t v0 = __shfl_sync(FULL, nid[0], t);
+              if (nid[1] == v0) chk[1] = false;
+            }
+          }
+          uint32_t old[2] = {0xffffffffu, 0xffffffffu};
+          uint4 cw[2][2];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            if (chk[r]) old[r] = atomicOr(vis + (nid[r] >> 5), 1u << (nid[r] & 31));
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              cw[r][v] = make_uint4(0, 0, 0, 0);
+              if (chk[r] && (uint32_t)v < nv) cw[r][v] = __ldg(reinterpret_cast<const uint4*>(a.codes8 + (size_t)nid[r] * a.pq_m) + v);
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            float sacc = 0.0f;  // table_distance (pq.rs:341-348): left fold over the subquantizers
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+              if ((uint32_t)v < nv) {
+                const uint32_t w[4] = {cw[r][v].x, cw[r][v].y, cw[r][v].z, cw[r][v].w};
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                  const uint32_t code = (w[k >> 2] >> ((k & 3) * 8)) & 0xffu;
+                  sacc = __fadd_rn(sacc, lut[(v * 16 + k) * a.pq_ksub + code]);
+                }
+              }
+            }
+            const float adc = __fsqrt_rn(sacc);
+            const bool unv = chk[r] && !(old[r] & (1u << (nid[r] & 31)));
+            n_adc += __popc(__ballot_sync(FULL, unv));
+            admit_values(unv, adc, nid[r]);
+          }
+        }
+        continue;
+      }
 
       // unvisited neighbours, in list order (leann.rs:933-937)
       uint32_t ucnt = 0;
@@ -397,7 +551,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
             nid = u_list[i];
             adc = adc_of(nid);
           }
-          admit_values(min(32u, ucnt - b), adc, nid);
+          admit_values(i < ucnt, adc, nid);
         }
         continue;
       }
@@ -465,9 +619,17 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       score_and_admit(promote);
     }
 
-    if (ADC && a.phase == 1) {
-      // traversal-only launch: hand the ef survivors (ascending adc order) to the recompute step
-      for (uint32_t i = lane; i < r_len; i += 32) a.surv_ids[(size_t)qi * ef + i] = R.ld(i).y & ~kExpandedBit;
+    if (ADC && (LEAN || a.phase == 1)) {
+      // traversal-only launch: hand the ef survivors (ascending adc order) to the rerank / recompute step
+      if constexpr (RREG) {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+          const uint32_t idx = j * 32 + lane;
+          if (idx < r_len) a.surv_ids[(size_t)qi * ef + idx] = rid[j] & ~kExpandedBit;
+        }
+      } else {
+        for (uint32_t i = lane; i < r_len; i += 32) a.surv_ids[(size_t)qi * ef + i] = R.ld(i).y & ~kExpandedBit;
+      }
       if (lane == 0) {
         a.surv_cnt[qi] = r_len;
         if (a.stats) {
