@@ -131,7 +131,8 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
 
   // ---- 1. ADC traversal ------------------------------------------------------------------------
   ISL_CUDA_TRY(cudaEventRecord(idx->ev0, st));
-  ISL_TRY(launch_pq_tables(pq->dev(), idx->q_stage.p, idx->ld, nq, idx->aux_f32.p, idx->sms, st));
+  const bool fused_lut = plan.lut_smem_floats != 0;  // tables built per query inside the traversal kernel
+  if (!fused_lut) ISL_TRY(launch_pq_tables(pq->dev(), idx->q_stage.p, idx->ld, nq, idx->aux_f32.p, idx->sms, st));
   SearchArgs a{};
   a.vectors = nullptr;  // phase 1 never reads an embedding
   a.sqnorms = nullptr;
@@ -156,7 +157,10 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
   a.stats = idx->out_stats.p;
   a.work_counter = idx->counters.p;
   a.error_flag = idx->counters.p + 1;
-  a.luts = idx->aux_f32.p;
+  a.luts = fused_lut ? nullptr : idx->aux_f32.p;
+  a.pq_codebooks = pq->d_codebooks.p;
+  a.pq_dsub = pq->dsub;
+  a.pq_ld_sub = pq->ld_sub;
   a.codes8 = idx->codes8.p;
   a.codes16 = idx->codes8.p ? nullptr : idx->codes16.p;
   a.pq_m = m;

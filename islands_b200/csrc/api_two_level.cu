@@ -87,7 +87,8 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
                                    (size_t)idx->dim * 4, nq, cudaMemcpyHostToDevice, st));
     ISL_CUDA_TRY(cudaMemsetAsync(idx->counters.p, 0, 4 * sizeof(unsigned int), st));
     ISL_CUDA_TRY(cudaEventRecord(idx->ev0, st));
-    ISL_TRY(launch_pq_tables(pq->dev(), idx->q_stage.p, idx->ld, nq, idx->aux_f32.p, idx->sms, st));
+    const bool fused_lut = pt.lut_smem_floats != 0;  // tables built per query inside the traversal kernel
+    if (!fused_lut) ISL_TRY(launch_pq_tables(pq->dev(), idx->q_stage.p, idx->ld, nq, idx->aux_f32.p, idx->sms, st));
     SearchArgs a{};
     a.vectors = idx->vectors.p;
     a.sqnorms = idx->sqnorms.p;
@@ -112,7 +113,10 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
     a.stats = idx->out_stats.p;
     a.work_counter = idx->counters.p;
     a.error_flag = idx->counters.p + 1;
-    a.luts = idx->aux_f32.p;
+    a.luts = fused_lut ? nullptr : idx->aux_f32.p;
+    a.pq_codebooks = pq->d_codebooks.p;
+    a.pq_dsub = pq->dsub;
+    a.pq_ld_sub = pq->ld_sub;
     a.codes8 = idx->codes8.p;
     a.codes16 = idx->codes8.p ? nullptr : idx->codes16.p;
     a.pq_m = m;

@@ -40,7 +40,9 @@ struct SearchArgs {
   unsigned int* work_counter;
   unsigned int* error_flag; // set to 1 when the tie list overflows
   // two-level search: PQ ADC traversal + exact rerank (docs/leann-specification.md:223-269)
-  const float* luts;        // [nq][pq_m*pq_ksub] squared-L2 tables (pq.rs:307-338)
+  const float* luts;        // [nq][pq_m*pq_ksub] squared-L2 tables (pq.rs:307-338); null => built per query in shared memory
+  const float* pq_codebooks; // [pq_m][pq_ksub][pq_ld_sub] (only read when luts is null)
+  uint32_t pq_dsub, pq_ld_sub;
   const uint8_t* codes8;    // [n][pq_m] when pq_ksub <= 256
   const uint16_t* codes16;  // [n][pq_m] otherwise
   uint32_t pq_m, pq_ksub;

@@ -165,13 +165,61 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     uint64_t n_hop = 0, n_edge = 0, n_dist = 0, n_adc = 0, n_rerank = 0;
     const float* lut = nullptr;
     if (MODE != 0 && !(ADC && a.phase == 2)) {
-      const float* g = a.luts + (size_t)qi * a.pq_m * a.pq_ksub;
-      if (a.lut_smem_floats) {
-        for (uint32_t i = lane; i < a.lut_smem_floats; i += 32) lut_smem[i] = __ldg(g + i);
+      if (a.luts == nullptr) {
+        // build_distance_tables (pq.rs:307-338) for this query straight into shared memory:
+        // LUT[j][c] = sum_t (q_jt - c_jct)^2, left fold, one centroid per lane.  ~200k fold steps per
+        // query against the L2-resident codebooks: a few percent of a traversal, and it saves the
+        // separate tables kernel plus 32 KB of table write + read per query.
+        const float* qv = a.queries + (size_t)qi * a.q_ld;
+        const uint32_t nvec = a.pq_ld_sub >> 2;
+        constexpr int CC = 4;  // centroids per lane in flight: independent fold chains hide the latency
+        for (uint32_t j = 0; j < a.pq_m; ++j) {
+          const float* qs = qv + (size_t)j * a.pq_dsub;
+          for (uint32_t c0 = 0; c0 < a.pq_ksub; c0 += 32 * CC) {
+            float acc[CC];
+            const float4* row[CC];
+#pragma unroll
+            for (int cc = 0; cc < CC; ++cc) {
+              acc[cc] = 0.0f;
+              const uint32_t c = min(c0 + cc * 32 + lane, a.pq_ksub - 1);
+              row[cc] = reinterpret_cast<const float4*>(a.pq_codebooks + ((size_t)j * a.pq_ksub + c) * a.pq_ld_sub);
+            }
+            for (uint32_t v = 0; v < nvec; ++v) {
+              float4 y[CC];
+#pragma unroll
+              for (int cc = 0; cc < CC; ++cc) y[cc] = __ldg(row[cc] + v);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t t = v * 4 + e;
+                if (t < a.pq_dsub) {
+                  const float qe = __ldg(qs + t);
+#pragma unroll
+                  for (int cc = 0; cc < CC; ++cc) {
+                    const float ye = e == 0 ? y[cc].x : (e == 1 ? y[cc].y : (e == 2 ? y[cc].z : y[cc].w));
+                    const float diff = __fsub_rn(qe, ye);
+                    acc[cc] = __fadd_rn(acc[cc], __fmul_rn(diff, diff));
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int cc = 0; cc < CC; ++cc) {
+              const uint32_t c = c0 + cc * 32 + lane;
+              if (c < a.pq_ksub) lut_smem[j * a.pq_ksub + c] = acc[cc];
+            }
+          }
+        }
         __syncwarp();
         lut = lut_smem;
       } else {
-        lut = g;
+        const float* g = a.luts + (size_t)qi * a.pq_m * a.pq_ksub;
+        if (a.lut_smem_floats) {
+          for (uint32_t i = lane; i < a.lut_smem_floats; i += 32) lut_smem[i] = __ldg(g + i);
+          __syncwarp();
+          lut = lut_smem;
+        } else {
+          lut = g;
+        }
       }
     }
 
