@@ -356,6 +356,24 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
 isl_status isl_index_last_recompute(const isl_index* idx, uint64_t* unique_nodes, float* traverse_ms,
                                     float* encoder_ms, float* rerank_ms);
 
+/* ---- to_bytes / from_bytes (leann.rs:1059-1066, pq.rs:351-358, hnsw.rs:507-514) -------------- */
+/* The reference's `bincode::serialize` layout (bincode 1.x defaults; islands_b200/csrc/bincode.h).
+ * out == NULL only reports the length in *out_len.  LeannIndex bytes hold the graph only
+ * (leann.rs:1058), so isl_index_from_bytes also takes the embeddings [n][dim] the provider returns.
+ * Malformed input -> ISL_SERIALIZATION (CoreError::Deserialization). */
+isl_status isl_index_to_bytes(const isl_index* idx, uint8_t* out, uint64_t cap, uint64_t* out_len);
+isl_status isl_index_from_bytes(const uint8_t* bytes, uint64_t len, const float* vectors, uint32_t dim,
+                                isl_index** out);
+isl_status isl_pq_to_bytes(const isl_pq* pq, uint8_t* out, uint64_t cap, uint64_t* out_len);
+isl_status isl_pq_from_bytes(const uint8_t* bytes, uint64_t len, isl_pq** out);
+isl_status isl_hnsw_to_bytes(const isl_hnsw* g, uint8_t* out, uint64_t cap, uint64_t* out_len);
+isl_status isl_hnsw_from_bytes(const uint8_t* bytes, uint64_t len, isl_hnsw** out);
+/* The configuration a handle carries (what from_bytes deserialised). */
+isl_status isl_index_get_config(const isl_index* idx, isl_leann_config* out);
+isl_status isl_pq_get_config(const isl_pq* pq, isl_pq_config* out);
+uint32_t isl_pq_dimension(const isl_pq* pq);
+isl_status isl_hnsw_get_config(const isl_hnsw* g, isl_hnsw_config* out);
+
 /* ---- island / shard merge (search.rs:211-237, indexer/service.rs:775-801) ---------- */
 /* Per query, merge `parts` lists of k (dist,id) pairs laid out [parts][nq][k] into the k best
  * by (dist, id); ISL_INVALID_ID entries are ignored. */

@@ -185,6 +185,16 @@ SIGNATURES = {
     "isl_index_drop_vectors": (C.c_int, [_VP]),
     "isl_index_search_adc_recompute": (C.c_int, [_VP, f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u64p, f32p, u32p, _SSP]),
     "isl_index_last_recompute": (C.c_int, [_VP, u64p, f32p, f32p, f32p]),
+    "isl_index_to_bytes": (C.c_int, [_VP, _VP, C.c_uint64, u64p]),
+    "isl_index_from_bytes": (C.c_int, [_VP, C.c_uint64, f32p, C.c_uint32, _VPP]),
+    "isl_pq_to_bytes": (C.c_int, [_VP, _VP, C.c_uint64, u64p]),
+    "isl_pq_from_bytes": (C.c_int, [_VP, C.c_uint64, _VPP]),
+    "isl_hnsw_to_bytes": (C.c_int, [_VP, _VP, C.c_uint64, u64p]),
+    "isl_hnsw_from_bytes": (C.c_int, [_VP, C.c_uint64, _VPP]),
+    "isl_index_get_config": (C.c_int, [_VP, _LCP]),
+    "isl_pq_get_config": (C.c_int, [_VP, _PCP]),
+    "isl_pq_dimension": (C.c_uint32, [_VP]),
+    "isl_hnsw_get_config": (C.c_int, [_VP, _HCP]),
     "isl_merge_topk": (C.c_int, [u64p, f32p, C.c_uint32, C.c_uint64, C.c_uint32, u64p, f32p, u32p]),
     "isl_merge_topk_dev": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint64, C.c_uint32, _VP, _VP, _VP]),
 }

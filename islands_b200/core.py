@@ -633,6 +633,77 @@ def _last_recompute(self):
     return dict(unique_nodes=u.value, traverse_ms=a.value, encoder_ms=b.value, rerank_ms=c.value)
 
 
+def _bytes_out(fn, handle):
+    n = C.c_uint64()
+    _check(fn(handle, None, 0, C.byref(n)))
+    buf = (C.c_uint8 * max(1, n.value))()
+    _check(fn(handle, C.cast(buf, C.c_void_p), n.value, C.byref(n)))
+    return bytes(bytearray(buf)[:n.value])
+
+
+def _index_to_bytes(self):
+    """LeannIndex::to_bytes (leann.rs:1059-1061): graph structure only, bincode layout."""
+    return _bytes_out(_ffi.load().isl_index_to_bytes, self._h)
+
+
+def _index_from_bytes(cls, data, vectors):
+    """LeannIndex::from_bytes (leann.rs:1064-1066) + the embeddings the provider would return."""
+    v = _f32(vectors)
+    buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data if len(data) else b"\0")
+    h = C.c_void_p()
+    cfg = LeannConfig()
+    _check(_ffi.load().isl_index_from_bytes(C.cast(buf, C.c_void_p), len(data), _ptr(v, f32p) if v.size else None,
+                                            v.shape[1] if v.ndim == 2 else 0, C.byref(h)))
+    _check(_ffi.load().isl_index_get_config(h, C.byref(cfg._s)))
+    self = cls.__new__(cls)
+    self.config = cfg
+    self._h = h
+    self._pq = None
+    return self
+
+
+LeannIndex.to_bytes = _index_to_bytes
+LeannIndex.from_bytes = classmethod(_index_from_bytes)
+
+
+def _pq_to_bytes(self):
+    """ProductQuantizer::to_bytes (pq.rs:351-353)."""
+    return _bytes_out(_ffi.load().isl_pq_to_bytes, self._h)
+
+
+def _pq_from_bytes(cls, data):
+    """ProductQuantizer::from_bytes (pq.rs:356-358)."""
+    buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data if len(data) else b"\0")
+    h = C.c_void_p()
+    _check(_ffi.load().isl_pq_from_bytes(C.cast(buf, C.c_void_p), len(data), C.byref(h)))
+    self = cls.__new__(cls)
+    self._h = h
+    self.config = PQConfig()
+    _check(_ffi.load().isl_pq_get_config(h, C.byref(self.config._s)))
+    self.dimension = int(_ffi.load().isl_pq_dimension(h))
+    return self
+
+
+def _hnsw_to_bytes(self):
+    """HnswGraph::to_bytes (hnsw.rs:507-509)."""
+    return _bytes_out(_ffi.load().isl_hnsw_to_bytes, self._h)
+
+
+def _hnsw_from_bytes(cls, data):
+    """HnswGraph::from_bytes (hnsw.rs:512-514)."""
+    buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data if len(data) else b"\0")
+    h = C.c_void_p()
+    _check(_ffi.load().isl_hnsw_from_bytes(C.cast(buf, C.c_void_p), len(data), C.byref(h)))
+    self = cls.__new__(cls)
+    self.config = HnswConfig()
+    _check(_ffi.load().isl_hnsw_get_config(h, C.byref(self.config._s)))
+    self._h = h
+    return self
+
+
+HnswGraph.to_bytes = _hnsw_to_bytes
+HnswGraph.from_bytes = classmethod(_hnsw_from_bytes)
+
 LeannIndex.set_recompute = _set_recompute
 LeannIndex.drop_vectors = _drop_vectors
 LeannIndex.search_adc_recompute_batch = _adc_recompute
@@ -902,3 +973,7 @@ def merge_topk(ids, dist, k):
     _check(_ffi.load().isl_merge_topk(_ptr(ids, u64p), _ptr(dist, f32p), parts, nq, k, _ptr(out_ids, u64p),
                                       _ptr(out_dist, f32p), _ptr(cnt, u32p)))
     return out_ids, out_dist, cnt
+
+
+ProductQuantizer.to_bytes = _pq_to_bytes
+ProductQuantizer.from_bytes = classmethod(_pq_from_bytes)

@@ -33,6 +33,7 @@
 #include <vector>
 
 #include "api_common.h"
+#include "bincode.h"
 #include "row_stream.cuh"
 
 struct isl_hnsw {
@@ -384,6 +385,95 @@ void fill_layer_args(const isl_hnsw* h, uint32_t layer, SearchArgs* a) {
     a->row_map = h->row_map.p;
     a->row_add = layer - 1;
   }
+}
+
+// dist[row][i] = metric(vec[node(row)], vec[adj[row][i]]) for every stored edge (one warp per row):
+// rebuilds the cached edge distances of a deserialised graph in reference order.
+template <int ACC>
+__global__ void __launch_bounds__(32)
+hnsw_edge_dist_kernel(const float* __restrict__ vectors, const float* __restrict__ sqnorms, uint32_t ld, uint32_t d,
+                      int32_t metric, const uint32_t* __restrict__ owner, uint32_t rows, const uint32_t* __restrict__ adj,
+                      const uint32_t* __restrict__ deg, uint32_t stride, float* __restrict__ out, uint32_t u_cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using G = StageGeom<64>;
+  float* stage = reinterpret_cast<float*>(smem_raw);
+  float* q_smem = stage + G::STAGE_FLOATS;
+  uint32_t* u_list = reinterpret_cast<uint32_t*>(q_smem + ld);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(u_list + u_cap);
+  const uint32_t lane = lane_id();
+  RowRing<1> ring;
+  ring.stage = stage;
+  ring.bars = bars;
+  ring.phase_bits = 0;
+  ring.islot = 0;
+  ring.cslot = 0;
+  if (lane == 0) {
+    mbar_init(bars, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  for (uint32_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const uint32_t node = owner ? owner[row] : row;
+    const uint32_t dg = deg[row];
+    __syncwarp();
+    const float4* src = reinterpret_cast<const float4*>(vectors + (size_t)node * ld);
+    for (uint32_t i = lane; i < ld / 4; i += 32) reinterpret_cast<float4*>(q_smem)[i] = src[i];
+    for (uint32_t i = lane; i < dg; i += 32) u_list[i] = adj[(size_t)row * stride + i];
+    __syncwarp();
+    const float na = (metric == ISL_METRIC_COSINE) ? smem_sqnorm_fold(q_smem, d) : 0.0f;
+    auto on_group = [&](uint32_t base, uint32_t cnt, float acc) {
+      if (lane < cnt) {
+        const float nb = (metric == ISL_METRIC_COSINE) ? __ldg(sqnorms + u_list[base + lane]) : 0.0f;
+        out[(size_t)row * stride + base + lane] = finalize_distance(metric, acc, na, nb);
+      }
+    };
+    stream_rows_fold<ACC, 1>(ring, vectors, ld, d, u_list, dg, q_smem, on_group);
+  }
+}
+
+template <int ACC>
+isl_status edge_dist_one(const isl_hnsw* h, const uint32_t* owner, uint32_t rows, const uint32_t* adj, const uint32_t* deg,
+                         uint32_t stride, float* out, cudaStream_t st) {
+  if (rows == 0) return ISL_OK;
+  const uint32_t u_cap = std::max<uint32_t>(32, round_up(stride, 32));
+  const size_t smem = ((size_t)StageGeom<64>::STAGE_FLOATS + h->ld + u_cap) * 4 + 16;
+  ISL_CUDA_TRY(cudaFuncSetAttribute(hnsw_edge_dist_kernel<ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  hnsw_edge_dist_kernel<ACC><<<std::min<uint32_t>(rows, (uint32_t)h->sms * 16), 32, smem, st>>>(
+      h->vectors.p, h->sqnorms.p, h->ld, h->dim, h->cfg.metric, owner, rows, adj, deg, stride, out, u_cap);
+  count_launch();
+  ISL_CUDA_TRY(cudaGetLastError());
+  return ISL_OK;
+}
+
+isl_status launch_edge_distances(isl_hnsw* h, cudaStream_t st) {
+  // upper-pool rows need their owning node: row_map[node] .. + level
+  std::vector<uint32_t> owner(h->n_upper);
+  for (uint64_t i = 0; i < h->n; ++i)
+    for (uint32_t L = 1; L <= h->h_levels[i]; ++L) owner[h->h_row_map[i] + L - 1] = (uint32_t)i;
+  DevBuf<uint32_t> d_owner;
+  if (h->n_upper) {
+    ISL_CUDA_TRY(d_owner.alloc(h->n_upper));
+    ISL_CUDA_TRY(cudaMemcpyAsync(d_owner.p, owner.data(), h->n_upper * 4, cudaMemcpyHostToDevice, st));
+  }
+  const uint32_t m0 = (uint32_t)h->cfg.m0, m = (uint32_t)h->cfg.m;
+  isl_status s1, s2;
+  switch (acc_kind_of_metric(h->cfg.metric)) {
+    case ACC_DOT:
+      s1 = edge_dist_one<ACC_DOT>(h, nullptr, (uint32_t)h->n, h->adj0.p, h->deg0.p, m0, h->dist0.p, st);
+      s2 = edge_dist_one<ACC_DOT>(h, d_owner.p, (uint32_t)h->n_upper, h->adjU.p, h->degU.p, m, h->distU.p, st);
+      break;
+    case ACC_L2:
+      s1 = edge_dist_one<ACC_L2>(h, nullptr, (uint32_t)h->n, h->adj0.p, h->deg0.p, m0, h->dist0.p, st);
+      s2 = edge_dist_one<ACC_L2>(h, d_owner.p, (uint32_t)h->n_upper, h->adjU.p, h->degU.p, m, h->distU.p, st);
+      break;
+    default:
+      s1 = edge_dist_one<ACC_L1>(h, nullptr, (uint32_t)h->n, h->adj0.p, h->deg0.p, m0, h->dist0.p, st);
+      s2 = edge_dist_one<ACC_L1>(h, d_owner.p, (uint32_t)h->n_upper, h->adjU.p, h->degU.p, m, h->distU.p, st);
+  }
+  ISL_TRY(s1);
+  ISL_TRY(s2);
+  ISL_CUDA_TRY(cudaStreamSynchronize(st));  // d_owner goes out of scope
+  return ISL_OK;
 }
 
 isl_status hnsw_insert_impl(isl_hnsw* h, const float* vectors, bool on_device, uint64_t count, uint32_t dim,
@@ -839,6 +929,182 @@ isl_status isl_hnsw_search_dev(const isl_hnsw* h, const float* d_queries, uint64
   }
   ISL_TRY(hnsw_search_device(h, q, q_ld, nq, k, ef, d_out_ids, d_out_dist, d_out_count));
   return hnsw_search_finish(h);
+}
+
+// HnswGraph { config, nodes: HashMap<u64, HnswNode{id, vector, connections, level}>, entry_point,
+// max_level, dimension, next_id } (hnsw.rs:151-164, :90-99) in the bincode layout of hnsw.rs:507-514.
+// The map is written in ascending id order (any order is a valid encoding of a HashMap).
+isl_status isl_hnsw_to_bytes(const isl_hnsw* h, uint8_t* out, uint64_t cap, uint64_t* out_len) {
+  if (!h) return fail(ISL_INVALID_ARGUMENT, "graph is null");
+  DeviceGuard g(h->device);
+  std::lock_guard<std::mutex> lock(h->mu);
+  const uint64_t n = h->n;
+  const uint32_t m0 = (uint32_t)h->cfg.m0, m = (uint32_t)h->cfg.m;
+  std::vector<float> vec(n * h->dim);
+  std::vector<uint32_t> deg0(n), adj0(n * m0), degU(h->n_upper), adjU(h->n_upper * m);
+  if (n) {
+    ISL_CUDA_TRY(cudaMemcpy2DAsync(vec.data(), (size_t)h->dim * 4, h->vectors.p, (size_t)h->ld * 4, (size_t)h->dim * 4, n,
+                                   cudaMemcpyDeviceToHost, h->stream));
+    ISL_CUDA_TRY(cudaMemcpyAsync(deg0.data(), h->deg0.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    ISL_CUDA_TRY(cudaMemcpyAsync(adj0.data(), h->adj0.p, n * m0 * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (h->n_upper) {
+      ISL_CUDA_TRY(cudaMemcpyAsync(degU.data(), h->degU.p, h->n_upper * 4, cudaMemcpyDeviceToHost, h->stream));
+      ISL_CUDA_TRY(cudaMemcpyAsync(adjU.data(), h->adjU.p, h->n_upper * m * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    ISL_CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  ByteWriter w;
+  w.u64(h->cfg.m);  // HnswConfig (hnsw.rs:15-28)
+  w.u64(h->cfg.m0);
+  w.u64(h->cfg.ef_construction);
+  w.f64(h->cfg.ml);
+  w.u32((uint32_t)h->cfg.metric);
+  w.u64(h->cfg.max_layers);
+  w.u64(n);
+  for (uint64_t i = 0; i < n; ++i) {
+    w.u64(i);  // key
+    w.u64(i);  // HnswNode::id
+    w.vec_f32(vec.data() + i * h->dim, h->dim);
+    const uint32_t lv = h->h_levels[i];
+    w.u64((uint64_t)lv + 1);  // connections: one list per layer 0..=level (hnsw.rs:104-106)
+    for (uint32_t L = 0; L <= lv; ++L) {
+      const uint64_t row = L == 0 ? i : h->h_row_map[i] + L - 1;
+      const uint32_t d = L == 0 ? deg0[row] : degU[row];
+      const uint32_t* a = L == 0 ? adj0.data() + row * m0 : adjU.data() + row * m;
+      w.u64(d);
+      for (uint32_t t = 0; t < d; ++t) w.u64(a[t]);
+    }
+    w.u64(lv);
+  }
+  w.opt_u64(h->entry >= 0, (uint64_t)h->entry);
+  w.u64(h->max_level);
+  w.opt_u64(h->dim != 0, h->dim);
+  w.u64(n);  // next_id
+  if (out_len) *out_len = w.buf.size();
+  if (!out) return ISL_OK;
+  if (cap < w.buf.size()) return fail(ISL_INVALID_ARGUMENT, "output buffer too small: need " + std::to_string(w.buf.size()) + " bytes");
+  std::memcpy(out, w.buf.data(), w.buf.size());
+  return ISL_OK;
+}
+
+isl_status isl_hnsw_from_bytes(const uint8_t* bytes, uint64_t len, isl_hnsw** out) {
+  if (!out) return fail(ISL_INVALID_ARGUMENT, "out is null");
+  *out = nullptr;
+  if (!bytes) return fail(ISL_INVALID_ARGUMENT, "bytes is null");
+  ByteReader r(bytes, len);
+  isl_hnsw_config c{};
+  c.m = r.u64();
+  c.m0 = r.u64();
+  c.ef_construction = r.u64();
+  c.ml = r.f64();
+  c.metric = (int32_t)r.u32();
+  c.max_layers = r.u64();
+  const uint64_t n = r.seq_len(40);
+  struct Node {
+    std::vector<float> v;
+    std::vector<std::vector<uint64_t>> conn;
+    uint64_t level = 0;
+    bool seen = false;
+  };
+  std::vector<Node> nodes(r.ok ? n : 0);
+  for (uint64_t i = 0; i < n && r.ok; ++i) {
+    const uint64_t key = r.u64(), id = r.u64();
+    if (!r.ok || key != id || id >= n || nodes[id].seen) {  // ids are 0..n-1 (hnsw.rs:227-228)
+      r.ok = false;
+      break;
+    }
+    Node& nd = nodes[id];
+    nd.seen = true;
+    r.vec_f32(&nd.v);
+    const uint64_t layers = r.seq_len(8);
+    nd.conn.resize(r.ok ? layers : 0);
+    for (uint64_t L = 0; L < layers && r.ok; ++L) r.vec_u64(&nd.conn[L]);
+    nd.level = r.u64();
+    if (nd.conn.size() != nd.level + 1 || nd.level > 255) r.ok = false;
+  }
+  uint64_t entry = 0, sdim = 0;
+  const bool has_entry = r.opt_u64(&entry);
+  const uint64_t max_level = r.u64();
+  const bool has_dim = r.opt_u64(&sdim);
+  const uint64_t next_id = r.u64();
+  if (!r.done() || c.metric < 0 || c.metric > 3 || next_id != n || (n > 0 && (!has_entry || !has_dim || entry >= n)))
+    return fail(ISL_SERIALIZATION, "deserialization failed: malformed HnswGraph bytes");
+  isl_hnsw* h = nullptr;
+  ISL_TRY(isl_hnsw_new(&c, &h));
+  std::unique_ptr<isl_hnsw, void (*)(isl_hnsw*)> guard(h, isl_hnsw_free);
+  if (n == 0) {
+    *out = guard.release();
+    return ISL_OK;
+  }
+  if (sdim == 0 || sdim > 0xffffffffull) return fail(ISL_SERIALIZATION, "deserialization failed: bad dimension");
+  const uint32_t dim = (uint32_t)sdim, m0 = (uint32_t)c.m0, m = (uint32_t)c.m;
+  DeviceGuard g(h->device);
+  h->dim = dim;
+  h->ld = std::max<uint32_t>(4, round_up(dim, 4));
+  h->n = n;
+  h->cap = n;
+  h->h_levels.resize(n);
+  h->h_row_map.resize(n);
+  uint64_t n_upper = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    if (nodes[i].v.size() != dim) return fail(ISL_SERIALIZATION, "deserialization failed: vector length differs from dimension");
+    h->h_levels[i] = (uint32_t)nodes[i].level;
+    h->h_row_map[i] = (uint32_t)n_upper;
+    n_upper += nodes[i].level;
+  }
+  h->n_upper = h->cap_upper = n_upper;
+  std::vector<float> vec((size_t)n * h->ld, 0.0f);
+  std::vector<uint32_t> deg0(n), adj0((size_t)n * m0, 0), degU(n_upper), adjU((size_t)n_upper * m, 0);
+  for (uint64_t i = 0; i < n; ++i) {
+    std::memcpy(vec.data() + i * h->ld, nodes[i].v.data(), (size_t)dim * 4);
+    for (uint64_t L = 0; L <= nodes[i].level; ++L) {
+      const auto& cl = nodes[i].conn[L];
+      const uint32_t cc = L == 0 ? m0 : m;
+      if (cl.size() > cc) return fail(ISL_SERIALIZATION, "deserialization failed: connection list longer than its capacity");
+      const uint64_t row = L == 0 ? i : h->h_row_map[i] + L - 1;
+      uint32_t* a = L == 0 ? adj0.data() + row * m0 : adjU.data() + row * m;
+      for (size_t t = 0; t < cl.size(); ++t) {
+        if (cl[t] >= n) return fail(ISL_NODE_NOT_FOUND, "node " + std::to_string(cl[t]) + " not found");
+        a[t] = (uint32_t)cl[t];
+      }
+      (L == 0 ? deg0[row] : degU[row]) = (uint32_t)cl.size();
+    }
+  }
+  cudaStream_t st = h->stream;
+  ISL_CUDA_TRY(h->vectors.alloc(n * h->ld));
+  ISL_CUDA_TRY(h->sqnorms.alloc(n));
+  ISL_CUDA_TRY(h->adj0.alloc(n * m0));
+  ISL_CUDA_TRY(h->dist0.alloc(n * m0));
+  ISL_CUDA_TRY(h->deg0.alloc(n));
+  ISL_CUDA_TRY(h->node_levels.alloc(n));
+  ISL_CUDA_TRY(h->row_map.alloc(n));
+  ISL_CUDA_TRY(h->cur_by_node.alloc(n));
+  ISL_CUDA_TRY(h->adjU.alloc(std::max<uint64_t>(n_upper * m, 1)));
+  ISL_CUDA_TRY(h->distU.alloc(std::max<uint64_t>(n_upper * m, 1)));
+  ISL_CUDA_TRY(h->degU.alloc(std::max<uint64_t>(n_upper, 1)));
+  ISL_CUDA_TRY(cudaMemcpyAsync(h->vectors.p, vec.data(), vec.size() * 4, cudaMemcpyHostToDevice, st));
+  ISL_CUDA_TRY(cudaMemcpyAsync(h->adj0.p, adj0.data(), adj0.size() * 4, cudaMemcpyHostToDevice, st));
+  ISL_CUDA_TRY(cudaMemcpyAsync(h->deg0.p, deg0.data(), n * 4, cudaMemcpyHostToDevice, st));
+  ISL_CUDA_TRY(cudaMemcpyAsync(h->node_levels.p, h->h_levels.data(), n * 4, cudaMemcpyHostToDevice, st));
+  ISL_CUDA_TRY(cudaMemcpyAsync(h->row_map.p, h->h_row_map.data(), n * 4, cudaMemcpyHostToDevice, st));
+  if (n_upper) {
+    ISL_CUDA_TRY(cudaMemcpyAsync(h->adjU.p, adjU.data(), adjU.size() * 4, cudaMemcpyHostToDevice, st));
+    ISL_CUDA_TRY(cudaMemcpyAsync(h->degU.p, degU.data(), n_upper * 4, cudaMemcpyHostToDevice, st));
+  }
+  ISL_TRY(launch_row_sqnorms(h->vectors.p, n, dim, h->ld, h->sqnorms.p, h->sms, st));
+  // cached edge distances (prune_connections needs them on the next insert): recomputed row by row
+  ISL_TRY(launch_edge_distances(h, st));
+  ISL_CUDA_TRY(cudaStreamSynchronize(st));
+  h->entry = (int64_t)entry;
+  h->max_level = max_level;
+  *out = guard.release();
+  return ISL_OK;
+}
+
+isl_status isl_hnsw_get_config(const isl_hnsw* h, isl_hnsw_config* out) {
+  if (!h || !out) return fail(ISL_INVALID_ARGUMENT, "null pointer");
+  *out = h->cfg;
+  return ISL_OK;
 }
 
 isl_status isl_hnsw_last_search_timing(const isl_hnsw* h, float* kernel_ms) {
