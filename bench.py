@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--ef", type=int, default=0, help="0 = smallest ef of the ladder with recall@10 >= 0.95")
     ap.add_argument("--build-batch", type=int, default=4096)
     ap.add_argument("--no-uniform", action="store_true", help="skip the secondary uniform-data measurement")
+    ap.add_argument("--no-hnsw", action="store_true", help="skip the secondary HnswGraph (configs[0]) measurement")
     ap.add_argument("--no-encoder", action="store_true", help="skip the secondary recompute-encoder measurement")
     ap.add_argument("--no-adc", action="store_true", help="skip the secondary PQ ADC traversal + exact rerank measurement")
     ap.add_argument("--pq-m", type=int, default=32, help="subquantizers of the ADC secondary (ksub = 256)")
@@ -454,6 +455,32 @@ def main():
                                          "roofline": {"bound": "tensor", "achieved": fl / ms_e / 1e9, "peak": tpeak, "unit": "TFLOP/s",
                                                       "frac": fl / ms_e / 1e9 / tpeak, "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"}}
             del enc, tok, eout
+            torch.cuda.empty_cache()
+
+        # secondary: BASELINE configs[0] — HnswGraph (hnsw.rs) on 100k random 768-d vectors, M=30, efSearch=64, top-10
+        if not a.no_hnsw:
+            from islands_b200 import HnswConfig, HnswGraph
+
+            hn = 100_000
+            xh_, qh_ = make_data(torch, "uniform", hn, nq, d, dev)
+            gth = ground_truth(torch, xh_, qh_[:n_gt], K_TOP)
+            hg = HnswGraph(HnswConfig(m=30, m0=60, ef_construction=128, ml=1.0 / np.log(30.0)))
+            t0 = time.perf_counter()
+            hg.insert_batch_dev(xh_.data_ptr(), hn, d, seed=7, batch=1024)
+            hbuild = time.perf_counter() - t0
+            hms = []
+            for it in range(4):
+                hg.search_batch_dev(qh_.data_ptr(), nq, d, K_TOP, 64, ids.data_ptr(), dst.data_ptr(), cnt.data_ptr())
+                if it:
+                    hms.append(hg.last_search_timing())
+            line["hnsw_config0"] = {"workload": "HnswGraph 100k x 768 uniform, m=30 m0=60 efC=128, 10000 queries, ef=64, top-10 (greedy descent + layer-0 search)",
+                                    "insert_s": hbuild, "inserts_per_s": hn / hbuild, "max_level": hg.max_level,
+                                    "search_ms": float(np.mean(hms)), "qps": nq / float(np.mean(hms)) * 1e3,
+                                    "recall_at_10": recall_at_k(torch, ids[:n_gt], gth),
+                                    "note": "bit-exact with the reference's HnswGraph, including its prune_connections quirk (hnsw.rs:419-420 with :327: "
+                                            "the id being inserted is filtered out of a full neighbour list), so only the first ~m0 nodes ever "
+                                            "receive incoming edges and the traversal stays among them: recall and speed are the reference's"}
+            del hg, xh_, qh_
             torch.cuda.empty_cache()
 
         # secondary: the reference benches' own distribution (uniform), reported beside the headline
