@@ -119,7 +119,7 @@ class ClockSampler:
                         self.reasons.add(nme)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._t.start()
@@ -338,6 +338,14 @@ def main():
     e2e_qps = (world if use_dist else 1) * nq * a.steps / dt_e2e
 
     peak, peak_src = measured_peak()
+    traffic = None  # DRAM bytes of this launch from the committed ncu --set full capture, when it is the same workload
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_search_traffic.json")) as f:
+            tj = json.load(f)
+        if tj["workload"] == {"n": n, "d": d, "nq": nq, "dataset": a.dataset, "ef": ef, "k": K_TOP}:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except Exception:
+        pass
     k_ms = float(np.mean(kernel_ms))
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
 
@@ -360,7 +368,7 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": {"bound": "hbm", "kernel": "leann_search_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "peak_source": peak_src},
+                     "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "peak_source": peak_src},
     }
 
     # ---- N > 1: the all-islands search (every query on every shard + all-gather + merge) ---------------

@@ -254,6 +254,62 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__
   }
 }
 
+// LayerNorm for H % 256 == 0: 16-byte loads and stores (8 bf16 per lane per pass, 512 contiguous bytes
+// per warp instruction).
+__global__ void __launch_bounds__(128)
+layernorm_vec_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                     uint32_t T, uint32_t H, float eps, __nv_bfloat16* __restrict__ out) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= T) return;
+  const uint4* r = reinterpret_cast<const uint4*>(in + (size_t)w * H);
+  const uint32_t per = H / 256;  // passes (<= 4 for H <= 1024)
+  float v[4][8];
+  float sum = 0.0f;
+#pragma unroll
+  for (uint32_t i = 0; i < 4; ++i) {
+    if (i < per) {
+      const uint4 x = __ldg(r + i * 32 + lane);
+      const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(&x);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(xb[j]);
+        v[i][2 * j] = f.x;
+        v[i][2 * j + 1] = f.y;
+        sum += f.x + f.y;
+      }
+    }
+  }
+  const float mean = warp_sum(sum) / (float)H;
+  float var = 0.0f;
+#pragma unroll
+  for (uint32_t i = 0; i < 4; ++i)
+    if (i < per) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dlt = v[i][j] - mean;
+        var += dlt * dlt;
+      }
+    }
+  const float rstd = rsqrtf(warp_sum(var) / (float)H + eps);
+  uint4* o = reinterpret_cast<uint4*>(out + (size_t)w * H);
+#pragma unroll
+  for (uint32_t i = 0; i < 4; ++i)
+    if (i < per) {
+      const uint32_t c = (i * 32 + lane) * 8;
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(ln_w + c)), w1 = __ldg(reinterpret_cast<const float4*>(ln_w + c + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(ln_b + c)), b1 = __ldg(reinterpret_cast<const float4*>(ln_b + c + 4));
+      const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint4 y;
+      __nv_bfloat162* yb = reinterpret_cast<__nv_bfloat162*>(&y);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        yb[j] = __floats2bfloat162_rn((v[i][2 * j] - mean) * rstd * ww[2 * j] + bb[2 * j],
+                                      (v[i][2 * j + 1] - mean) * rstd * ww[2 * j + 1] + bb[2 * j + 1]);
+      o[i * 32 + lane] = y;
+    }
+}
+
 // Masked softmax attention, head_dim = 64.  One CTA per (sequence, head); keys/values of the
 // sequence staged in shared memory as f32; each warp owns four query rows at a time so that every
 // K / V value read from shared memory feeds four FMAs (register blocking: 16 FMAs per 5 LDS.128 in
@@ -711,13 +767,19 @@ isl_status forward_device(isl_encoder* e, const int32_t* d_tokens, const int32_t
     count_launch();
     ISL_TRY(launch_gemm_bf16(e->ctx.p, gw + l.g_ao, (int)T, (int)H, (int)H, lp + l.ao_b, e->x.p, gemm::EPI_NONE, e->y.p,
                              nullptr, e->sms, st));
-    layernorm_kernel<<<row_blocks, 128, 0, st>>>(e->y.p, lp + l.ln1_w, lp + l.ln1_b, T, H, eps, e->x.p);
+    if (H % 256 == 0)
+      layernorm_vec_kernel<<<row_blocks, 128, 0, st>>>(e->y.p, lp + l.ln1_w, lp + l.ln1_b, T, H, eps, e->x.p);
+    else
+      layernorm_kernel<<<row_blocks, 128, 0, st>>>(e->y.p, lp + l.ln1_w, lp + l.ln1_b, T, H, eps, e->x.p);
     count_launch();
     ISL_TRY(launch_gemm_bf16(e->x.p, gw + l.g_f1, (int)T, (int)I, (int)H, lp + l.f1_b, nullptr, gemm::EPI_GELU, e->ffn.p,
                              nullptr, e->sms, st));
     ISL_TRY(launch_gemm_bf16(e->ffn.p, gw + l.g_f2, (int)T, (int)H, (int)I, lp + l.f2_b, e->x.p, gemm::EPI_NONE, e->y.p,
                              nullptr, e->sms, st));
-    layernorm_kernel<<<row_blocks, 128, 0, st>>>(e->y.p, lp + l.ln2_w, lp + l.ln2_b, T, H, eps, e->x.p);
+    if (H % 256 == 0)
+      layernorm_vec_kernel<<<row_blocks, 128, 0, st>>>(e->y.p, lp + l.ln2_w, lp + l.ln2_b, T, H, eps, e->x.p);
+    else
+      layernorm_kernel<<<row_blocks, 128, 0, st>>>(e->y.p, lp + l.ln2_w, lp + l.ln2_b, T, H, eps, e->x.p);
     count_launch();
   }
   pool_kernel<<<(uint32_t)seqs, 256, 0, st>>>(e->x.p, d_lengths, (uint32_t)S, H, e->cfg.normalize, d_out);
