@@ -373,6 +373,10 @@ isl_status isl_index_get_config(const isl_index* idx, isl_leann_config* out);
 isl_status isl_pq_get_config(const isl_pq* pq, isl_pq_config* out);
 uint32_t isl_pq_dimension(const isl_pq* pq);
 isl_status isl_hnsw_get_config(const isl_hnsw* g, isl_hnsw_config* out);
+/* One stored vector: HnswNode::vector (hnsw.rs:93-95) / InMemoryEmbeddingProvider::compute_embedding
+ * (leann.rs:141-150); out [dimension].  Used by SearchConfig::include_vectors (search.rs:160-164). */
+isl_status isl_hnsw_get_vector(const isl_hnsw* g, uint64_t node_id, float* out);
+isl_status isl_index_get_vector(const isl_index* idx, uint64_t node_id, float* out);
 
 /* ---- island / shard merge (search.rs:211-237, indexer/service.rs:775-801) ---------- */
 /* Per query, merge `parts` lists of k (dist,id) pairs laid out [parts][nq][k] into the k best

@@ -195,6 +195,8 @@ SIGNATURES = {
     "isl_pq_get_config": (C.c_int, [_VP, _PCP]),
     "isl_pq_dimension": (C.c_uint32, [_VP]),
     "isl_hnsw_get_config": (C.c_int, [_VP, _HCP]),
+    "isl_hnsw_get_vector": (C.c_int, [_VP, C.c_uint64, f32p]),
+    "isl_index_get_vector": (C.c_int, [_VP, C.c_uint64, f32p]),
     "isl_merge_topk": (C.c_int, [u64p, f32p, C.c_uint32, C.c_uint64, C.c_uint32, u64p, f32p, u32p]),
     "isl_merge_topk_dev": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint64, C.c_uint32, _VP, _VP, _VP]),
 }

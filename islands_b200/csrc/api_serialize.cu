@@ -186,4 +186,14 @@ isl_status isl_pq_get_config(const isl_pq* pq, isl_pq_config* out) {
 }
 uint32_t isl_pq_dimension(const isl_pq* pq) { return pq ? pq->dim : 0; }
 
+// InMemoryEmbeddingProvider::compute_embedding (leann.rs:141-150) for the resident embeddings.
+isl_status isl_index_get_vector(const isl_index* idx, uint64_t node_id, float* out) {
+  if (!idx || !out) return fail(ISL_INVALID_ARGUMENT, "null pointer");
+  if (node_id >= idx->n) return fail(ISL_NODE_NOT_FOUND, "node " + std::to_string(node_id) + " not found");
+  if (!idx->vectors.p) return fail(ISL_INVALID_ARGUMENT, "the stored vectors were dropped (recompute-only index)");
+  DeviceGuard g(idx->device);
+  ISL_CUDA_TRY(cudaMemcpy(out, idx->vectors.p + node_id * idx->ld, (size_t)idx->dim * 4, cudaMemcpyDeviceToHost));
+  return ISL_OK;
+}
+
 }  // extern "C"

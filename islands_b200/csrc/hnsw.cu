@@ -1101,6 +1101,15 @@ isl_status isl_hnsw_from_bytes(const uint8_t* bytes, uint64_t len, isl_hnsw** ou
   return ISL_OK;
 }
 
+// HnswNode::vector of get_node(node_id) (hnsw.rs:93-95, :201-203).
+isl_status isl_hnsw_get_vector(const isl_hnsw* h, uint64_t node_id, float* out) {
+  if (!h || !out) return fail(ISL_INVALID_ARGUMENT, "null pointer");
+  if (node_id >= h->n) return fail(ISL_NODE_NOT_FOUND, "node " + std::to_string(node_id) + " not found");
+  DeviceGuard g(h->device);
+  ISL_CUDA_TRY(cudaMemcpy(out, h->vectors.p + node_id * h->ld, (size_t)h->dim * 4, cudaMemcpyDeviceToHost));
+  return ISL_OK;
+}
+
 isl_status isl_hnsw_get_config(const isl_hnsw* h, isl_hnsw_config* out) {
   if (!h || !out) return fail(ISL_INVALID_ARGUMENT, "null pointer");
   *out = h->cfg;
