@@ -47,7 +47,7 @@ def test_two_level_needs_pq(gpu_lib, orc):
         idx.search_two_level_batch(v[:2], 5, 32, 0.1)
 
 
-@pytest.mark.parametrize("m,ksub", [(8, 256), (4, 16), (16, 300), (96, 256)])
+@pytest.mark.parametrize("m,ksub", [(8, 256), (4, 16), (16, 300), (96, 256), (32, 256), (16, 64)])
 def test_adc_traversal_rerank_matches_oracle(gpu_lib, orc, m, ksub):
     """PQ ADC traversal + exact rerank (include/islands_b200.h isl_index_search_adc_rerank)."""
     from islands_b200 import LeannIndex, PQConfig, ProductQuantizer
@@ -60,7 +60,10 @@ def test_adc_traversal_rerank_matches_oracle(gpu_lib, orc, m, ksub):
     idx = LeannIndex.from_csr(cfg, v, off, nbrs, levels, entry)
     idx.attach_pq(pq, codes)
     q = np.concatenate([uniform(np.random.RandomState(63), 90, 96), v[:10]])
-    for k, ef in [(10, 16), (10, 100), (25, 200)]:
+    # ef 16..200: result array in registers (2 / 4 / 8 entries per lane); 300: shared memory; 2500: global memory
+    for k, ef in [(10, 16), (10, 100), (25, 200), (10, 300), (10, 2500)]:
+        if ef == 2500 and m not in (32, 8):
+            continue
         ids, dist, cnt, st = idx.search_adc_rerank_batch(q, k, ef, stats=True)
         o_ids, o_dist, o_cnt, o_st = orc.leann_search_adc_rerank(cfg._s, v, off, nbrs, entry, cb, codes, q, k, ef,
                                                                  threads=8, stats=True)
@@ -70,3 +73,39 @@ def test_adc_traversal_rerank_matches_oracle(gpu_lib, orc, m, ksub):
         for f in ("n_hop", "n_edge", "n_dist", "n_adc", "n_rerank"):
             assert np.array_equal(getattr(st, f), o_st[f]), f
         assert (np.diff(dist, axis=1) >= 0).all()  # exact distances, ascending
+
+
+@pytest.mark.parametrize("m,ksub", [(32, 256), (8, 256)])
+def test_adc_traversal_with_duplicate_neighbours(gpu_lib, orc, m, ksub):
+    """Adjacency lists with repeated ids (from_csr accepts them): the first occurrence in LIST order
+    decides, within one half of a 64-position pass and across its two halves."""
+    from islands_b200 import LeannIndex, PQConfig, ProductQuantizer
+
+    cfg, v, levels, off, nbrs, entry = oracle_graph(orc, 3000, 96, seed=61)
+    nbrs = nbrs.copy()
+    rng = np.random.RandomState(5)
+    for node in rng.choice(3000, 600, replace=False):
+        s, e = int(off[node]), int(off[node + 1])
+        deg = e - s
+        if deg > 40:
+            nbrs[s + 33:s + 39] = nbrs[s + 2:s + 8]      # second half repeats ids of the first half
+            nbrs[s + 10] = nbrs[s + 9]                    # repeat inside the first half
+            nbrs[s + 39] = nbrs[s + 38 - 1 + 1]           # repeat inside the second half (39 == 38)
+            nbrs[s + 39] = nbrs[s + 38]
+    cb = orc.pq_train(1, v[:1000], m, ksub, 3, 7)
+    codes = orc.pq_encode(1, cb, v)
+    pq = ProductQuantizer(96, PQConfig(m, ksub, 3, 7))
+    pq.set_codebooks(cb)
+    idx = LeannIndex.from_csr(cfg, v, off, nbrs, levels, entry)
+    idx.attach_pq(pq, codes)
+    q = uniform(np.random.RandomState(64), 100, 96)
+    for k, ef in [(10, 64), (10, 150)]:
+        ids, dist, cnt, st = idx.search_adc_rerank_batch(q, k, ef, stats=True)
+        o_ids, o_dist, o_cnt, o_st = orc.leann_search_adc_rerank(cfg._s, v, off, nbrs, entry, cb, codes, q, k, ef,
+                                                                 threads=8, stats=True)
+        assert np.array_equal(ids, o_ids) and np.array_equal(dist.view(np.uint32), o_dist.view(np.uint32))
+        for f in ("n_hop", "n_edge", "n_adc", "n_rerank"):
+            assert np.array_equal(getattr(st, f), o_st[f]), f
+        e_ids, e_dist, _ = idx.search_batch(q, k, ef)
+        x_ids, x_dist, _ = orc.leann_search(cfg._s, v, off, nbrs, entry, q, k, ef, threads=8)
+        assert np.array_equal(e_ids, x_ids) and np.array_equal(e_dist.view(np.uint32), x_dist.view(np.uint32))
