@@ -7,6 +7,7 @@ from .core import (Encoder, EncoderConfig, gemm_bf16_dev, CoreError, CsrGraph, C
                    PruningStrategy, SerializationError, merge_topk, merge_topk_dev, normalize_vector, normalized,
                    random_level, to_similarity)
 
+from .registry import IslandRegistry, StoredIndex
 from .search import MultiIndexSearcher, SearchConfig, Searcher, SearchResult
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -919,6 +919,45 @@ class Encoder:
     def state_dict(self):
         return {n: self.get_parameter(n) for n in self.parameter_shapes()}
 
+    def load_safetensors(self, path, prefix=""):
+        """Load BERT weights from a .safetensors file (8-byte little-endian header length, JSON header
+        with dtype / shape / data_offsets, raw tensor bytes) — the format CandleEmbedder reads
+        (candle_provider.rs:230-300).  Tensor names are the Hugging Face ones, optionally under
+        `prefix` (e.g. "bert.").  F32 / F16 / BF16 are accepted.  Returns the names that were loaded."""
+        import json
+        import struct
+
+        with open(path, "rb") as f:
+            raw = f.read()
+        (hlen,) = struct.unpack("<Q", raw[:8])
+        header = json.loads(raw[8:8 + hlen].decode("utf-8"))
+        base = 8 + hlen
+        shapes = self.parameter_shapes()
+        loaded = []
+        for name, shape in shapes.items():
+            meta = header.get(prefix + name)
+            if meta is None:
+                continue
+            lo, hi = meta["data_offsets"]
+            buf = raw[base + lo:base + hi]
+            dt = meta["dtype"]
+            if dt == "F32":
+                arr = np.frombuffer(buf, "<f4")
+            elif dt == "F16":
+                arr = np.frombuffer(buf, "<f2").astype(np.float32)
+            elif dt == "BF16":
+                arr = (np.frombuffer(buf, "<u2").astype(np.uint32) << 16).view(np.float32)
+            else:
+                raise SerializationError(f"unsupported safetensors dtype {dt} for {name}")
+            if tuple(meta["shape"]) != tuple(shape):
+                raise DimensionMismatch(f"dimension mismatch: expected {tuple(shape)}, got {tuple(meta['shape'])} for {name}")
+            self.set_parameter(name, arr.reshape(shape))
+            loaded.append(name)
+        missing = [n for n in shapes if n not in loaded]
+        if missing:
+            raise SerializationError(f"safetensors file lacks {len(missing)} parameters, e.g. {missing[0]}")
+        return loaded
+
     def embed(self, token_ids, lengths):
         """token_ids [B, S] int32 (0-padded), lengths [B] -> [B, hidden] f32."""
         t = np.ascontiguousarray(token_ids, np.int32)
