@@ -1,0 +1,44 @@
+"""One-off measurement of BASELINE configs[4]: search with on-demand recompute at scale.
+An index of N nodes keeps graph + PQ codes + one S-token row per node; the batch's distinct ADC
+survivors go through the random-init BERT-base bf16 encoder; exact rerank on the recomputed rows.
+The graph is built over the encoder's own outputs (so the recompute results are the stored-vector
+results bit for bit — checked here on a sample), tokens come from a clustered table (near-duplicate
+chunks), which is what gives the neighbourhoods a graph index needs."""
+import json, os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from islands_b200 import Encoder, EncoderConfig, LeannConfig, LeannIndex, PQConfig, ProductQuantizer
+
+n, nq, S, k = int(os.environ.get("N", 200000)), int(os.environ.get("NQ", 256)), 64, 10
+ef = int(os.environ.get("EF", 128))
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev); g.manual_seed(45)
+clusters = max(64, n // 50)
+base = torch.randint(1, 30000, (clusters, S), generator=g, device=dev, dtype=torch.int32)
+def draw(count):
+    t = base[torch.randint(0, clusters, (count,), generator=g, device=dev)].clone()
+    flip = torch.rand((count, S), generator=g, device=dev) < 0.15
+    t[flip] = torch.randint(1, 30000, (int(flip.sum()),), generator=g, device=dev, dtype=torch.int32)
+    return t.contiguous(), torch.full((count,), S, device=dev, dtype=torch.int32)
+tok, ln = draw(n); qtok, qln = draw(nq)
+enc = Encoder(EncoderConfig()).init_random(seed=46, stddev=0.02)
+emb = torch.empty((n, 768), device=dev); qemb = torch.empty((nq, 768), device=dev)
+t0 = time.perf_counter(); enc.embed_dev(tok.data_ptr(), ln.data_ptr(), n, S, emb.data_ptr()); t_enc_all = time.perf_counter() - t0
+enc.embed_dev(qtok.data_ptr(), qln.data_ptr(), nq, S, qemb.data_ptr())
+index = LeannIndex(LeannConfig()); index.build_dev(emb.data_ptr(), n, 768, seed=7, batch=4096)
+xh = emb.cpu().numpy(); qh = qemb.cpu().numpy()
+pq = ProductQuantizer(768, PQConfig(32, 256, 8, 1)); pq.train(xh[:20000]); index.attach_pq(pq, pq.encode(xh))
+ids_a, dist_a, _ = index.search_adc_rerank_batch(qh, k, ef)                       # stored vectors
+index.set_recompute(enc, tok.cpu().numpy(), ln.cpu().numpy())
+ids_b, dist_b, _ = index.search_adc_recompute_batch(qh, k, ef)                    # warm-up + check
+t0 = time.perf_counter(); ids_b, dist_b, _ = index.search_adc_recompute_batch(qh, k, ef); dt = time.perf_counter() - t0
+info = index.last_recompute()
+xn = torch.nn.functional.normalize(emb, dim=1); qn = torch.nn.functional.normalize(qemb, dim=1)
+gt = (qn @ xn.T).topk(k, dim=1).indices.cpu().numpy()
+rec = float(np.mean([len(set(ids_b[i].tolist()) & set(gt[i].tolist())) / k for i in range(nq)]))
+ms_enc, fl = enc.last_timing()
+print(json.dumps(dict(n=n, nq=nq, S=S, ef=ef, index_encode_s=round(t_enc_all, 2), index_encode_seq_per_s=round(n / t_enc_all),
+                      recompute_batch_ms=round(dt * 1e3, 1), qps=round(nq / dt, 1), unique_nodes=info["unique_nodes"],
+                      traverse_ms=round(info["traverse_ms"], 2), encoder_ms=round(info["encoder_ms"], 2), rerank_ms=round(info["rerank_ms"], 2),
+                      encoder_tflops=round(fl / ms_enc / 1e9, 1), recall_at_10=rec,
+                      identical_to_stored=bool(np.array_equal(ids_a, ids_b) and np.array_equal(dist_a.view(np.uint32), dist_b.view(np.uint32))))))
