@@ -50,7 +50,9 @@ def parse_args():
     ap.add_argument("--no-hnsw", action="store_true", help="skip the secondary HnswGraph (configs[0]) measurement")
     ap.add_argument("--no-encoder", action="store_true", help="skip the secondary recompute-encoder measurement")
     ap.add_argument("--no-adc", action="store_true", help="skip the secondary PQ ADC traversal + exact rerank measurement")
-    ap.add_argument("--pq-m", type=int, default=32, help="subquantizers of the ADC secondary (ksub = 256)")
+    ap.add_argument("--pq-m", type=int, default=32, help="subquantizers of the ADC secondary")
+    ap.add_argument("--pq-ksub", type=int, default=128, help="centroids per subquantizer of the ADC secondary "
+                    "(128: a 16 KB table per query in shared memory keeps twice the warps resident of 256)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -413,7 +415,8 @@ def main():
         # specifies (docs/leann-specification.md:223-269) but does not implement; measured beside the headline.
         if not a.no_adc:
             pq_m = a.pq_m
-            pq = ProductQuantizer(d, PQConfig(pq_m, 256, 8, 1))
+            pq_ksub = a.pq_ksub
+            pq = ProductQuantizer(d, PQConfig(pq_m, pq_ksub, 8, 1))
             pq.train(xh[:20000])
             index.attach_pq(pq, pq.encode(xh))
 
@@ -426,8 +429,8 @@ def main():
             index.search_adc_rerank_batch(qn, K_TOP, ef_adc)
             ms = index.last_search_timing()[0]
             b = int(st.n_adc.sum()) * pq_m + int(st.n_edge.sum()) * 4 + int(st.n_hop.sum()) * 16 + int(st.n_rerank.sum()) * 4 * d \
-                + nq * (4 * d + 12 * K_TOP + pq_m * 256 * 4)
-            line["adc_rerank"] = {"pq_m": pq_m, "ef": ef_adc, "recall_at_10": curve_adc[ef_adc], "kernel_qps": nq / ms * 1e3,
+                + nq * (4 * d + 12 * K_TOP + pq_m * pq_ksub * 4)
+            line["adc_rerank"] = {"pq_m": pq_m, "pq_ksub": pq_ksub, "ef": ef_adc, "recall_at_10": curve_adc[ef_adc], "kernel_qps": nq / ms * 1e3,
                                   "kernel_ms": ms, "algorithmic_gbps": b / ms / 1e6, "frac": b / ms / 1e6 / peak,
                                   "n_adc": float(st.n_adc.mean()), "n_rerank": float(st.n_rerank.mean()),
                                   "note": "parity unpinned: no reference implementation of this mode exists (leann.rs:54-56)"}

@@ -7,6 +7,7 @@
 //   islands::CoreError (+ kind)                             src/core/error.rs:9-62
 //   islands::LeannConfig / LeannIndex / CsrGraph            src/core/leann.rs:193-302, 322-461, 493-1067
 //   islands::HnswConfig / HnswGraph                       src/core/hnsw.rs:15-86, 151-531
+//   islands::EncoderConfig / Encoder                     src/core/embedding/candle_provider.rs:353-507
 //   islands::PQConfig / ProductQuantizer                    src/core/pq.rs:13-65, 116-359
 //   islands::merge_results                                  src/core/search.rs:211-237
 // Link with -lislands_b200 (islands_b200/lib).  All compute runs on the GPU; nothing here has a
@@ -252,6 +253,35 @@ class ProductQuantizer {
  private:
   uint32_t dim_;
   isl_pq* h_ = nullptr;
+};
+
+// ---- embedding/candle_provider.rs ---------------------------------------------------------------
+struct EncoderConfig : isl_encoder_config {
+  EncoderConfig() { check(isl_encoder_config_default(this)); }  // BERT-base shape
+};
+
+// The model behind CandleEmbedder::embed_texts_raw (candle_provider.rs:353-507) for token ids.
+class Encoder {
+ public:
+  explicit Encoder(const EncoderConfig& cfg = EncoderConfig()) { check(isl_encoder_new(&cfg, &h_)); }
+  ~Encoder() { isl_encoder_free(h_); }
+  Encoder(const Encoder&) = delete;
+  Encoder& operator=(const Encoder&) = delete;
+  uint32_t dimension() const { return isl_encoder_dimension(h_); }  // EmbeddingProvider::dimension
+  void init_random(uint64_t seed = 46, float stddev = 0.02f) { check(isl_encoder_init_random(h_, seed, stddev)); }
+  void set_parameter(const std::string& name, const std::vector<float>& data) {
+    check(isl_encoder_set_parameter(h_, name.c_str(), data.data(), data.size()));
+  }
+  // token_ids [batch][seq_len] (0-padded), lengths [batch] -> [batch][dimension()] pooled, normalised
+  std::vector<float> embed(const std::vector<int32_t>& token_ids, const std::vector<int32_t>& lengths, uint32_t seq_len) {
+    std::vector<float> out(lengths.size() * (size_t)dimension());
+    check(isl_encoder_embed(h_, token_ids.data(), lengths.data(), lengths.size(), seq_len, out.data()));
+    return out;
+  }
+  isl_encoder* handle() const { return h_; }
+
+ private:
+  isl_encoder* h_ = nullptr;
 };
 
 // ---- search.rs ----------------------------------------------------------------------------------

@@ -11,7 +11,7 @@ gt = bench.ground_truth(torch, x, q[:1000], 10)
 idx = LeannIndex(LeannConfig()); idx.build_dev(x.data_ptr(), n, d, seed=7, batch=4096)
 xh = x.cpu().numpy(); qh = q.cpu().numpy()
 for m in [int(v) for v in os.environ.get("MS", "8,16,32").split(",")]:
-    pq = ProductQuantizer(d, PQConfig(m, 256, 8, 1))
+    pq = ProductQuantizer(d, PQConfig(m, int(os.environ.get("KSUB", 256)), 8, 1))
     t0 = time.time(); pq.train(xh[:20000]); t1 = time.time()
     codes = pq.encode(xh); t2 = time.time()
     idx.attach_pq(pq, codes)
@@ -21,6 +21,6 @@ for m in [int(v) for v in os.environ.get("MS", "8,16,32").split(",")]:
         ids, dist, cnt = idx.search_adc_rerank_batch(qh, 10, ef)
         ms, _ = idx.last_search_timing()
         rec = bench.recall_at_k(torch, torch.from_numpy(ids[:1000].astype(np.int64)).to(dev), gt)
-        b = st.n_adc.sum() * m + st.n_edge.sum() * 4 + st.n_hop.sum() * 16 + st.n_rerank.sum() * 4 * d + nq * (4 * d + 120 + m * 256 * 4)
+        b = st.n_adc.sum() * m + st.n_edge.sum() * 4 + st.n_hop.sum() * 16 + st.n_rerank.sum() * 4 * d + nq * (4 * d + 120 + m * int(os.environ.get("KSUB", 256)) * 4)
         print(json.dumps(dict(m=m, ef=ef, kernel_ms=round(ms, 2), qps=round(nq / ms * 1e3), recall=round(rec, 4), n_adc=float(st.n_adc.mean()),
                               n_rerank=float(st.n_rerank.mean()), n_hop=float(st.n_hop.mean()), gbps=round(b / ms / 1e6, 1))), flush=True)

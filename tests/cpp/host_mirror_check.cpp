@@ -37,6 +37,8 @@ int main(int argc, char** argv) {
   }
   PQConfig pc;
   EXPECT(pc.bytes_per_vector() == 8);
+  EncoderConfig ecd;
+  EXPECT(ecd.hidden_size == 768 && ecd.num_layers == 12 && ecd.intermediate_size == 3072);
   HnswConfig hc;
   EXPECT(hc.m == 16 && hc.m0 == 32 && hc.ef_construction == 200 && hc.max_layers == 16);  // hnsw.rs:533-545
   EXPECT(std::fabs(to_similarity(1.0f) - 0.5f) < 1e-7f);
@@ -66,6 +68,16 @@ int main(int argc, char** argv) {
     auto hr = hg.search(q, 5, 50);
     EXPECT(hr.size() == 5 && hr[0].first == 0 && hr[0].second < 0.01f);
     EXPECT(!hg.neighbors_at(0, 0).empty());
+    EncoderConfig ec;
+    ec.vocab_size = 200; ec.hidden_size = 64; ec.num_layers = 1; ec.num_heads = 1; ec.intermediate_size = 128; ec.max_position = 16;
+    Encoder enc(ec);
+    enc.init_random(3, 0.05f);
+    std::vector<int32_t> toks = {5, 6, 7, 0, 9, 10, 11, 12};
+    auto emb = enc.embed(toks, {3, 4}, 4);
+    EXPECT(emb.size() == 2 * 64);
+    float nrm = 0.f;
+    for (int i = 0; i < 64; ++i) nrm += emb[i] * emb[i];
+    EXPECT(std::fabs(nrm - 1.0f) < 1e-3f);  // L2-normalised (candle_provider.rs:477-494)
     try {
       hg.insert(std::vector<float>(d + 1, 0.f));
       EXPECT(false);
