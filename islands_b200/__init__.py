@@ -9,5 +9,6 @@ from .core import (Encoder, EncoderConfig, gemm_bf16_dev, CoreError, CsrGraph, C
 
 from .registry import IslandRegistry, StoredIndex
 from .search import MultiIndexSearcher, SearchConfig, Searcher, SearchResult
+from .storage import DeserializationError, FileSystemStorage, IndexMetadata, IndexReader, IndexWriter
 
 __all__ = [n for n in dir() if not n.startswith("_")]
