@@ -968,6 +968,19 @@ class Encoder:
                                              _ptr(out, f32p)))
         return out
 
+    def embed_texts_raw(self, tokenizer, texts):
+        """CandleEmbedder::embed_texts_raw (candle_provider.rs:353-507): tokenise the batch
+        (`tokenizer.encode_batch(texts, true)`), pad every row with zeros to the longest encoding,
+        BERT forward, mean pooling weighted by the attention mask, L2 normalisation.  `tokenizer` is an
+        islands_b200.tokenizer.BertWordPieceTokenizer.  Empty input -> empty output (:354-356)."""
+        if len(texts) == 0:
+            return np.zeros((0, self.dimension()), np.float32)
+        ids, types, mask = tokenizer.encode_batch_padded(list(texts))
+        lengths = mask.sum(axis=1).astype(np.int32)
+        if types.any() or not np.array_equal(mask, (np.arange(mask.shape[1])[None, :] < lengths[:, None]).astype(mask.dtype)):
+            raise InvalidArgument("embed_texts_raw: single sequences with right padding only")
+        return self.embed(ids, lengths)
+
     def embed_dev(self, d_tokens_ptr, d_lengths_ptr, B, S, d_out_ptr):
         _check(_ffi.load().isl_encoder_embed_dev(self._h, C.c_void_p(d_tokens_ptr), C.c_void_p(d_lengths_ptr), B, S,
                                                  C.c_void_p(d_out_ptr)))

@@ -158,3 +158,34 @@ def test_encoder_parameter_roundtrip_and_errors(gpu_lib):
         enc.set_parameter("encoder.layer.9.attention.self.key.weight", w)
     with pytest.raises(InvalidArgument):
         enc.embed(np.ones((1, 100), np.int32), np.array([4], np.int32))  # S > max_position
+
+
+@pytest.mark.gpu
+def test_embed_texts_raw_vs_oracle(gpu_lib):
+    """Text entry point (candle_provider.rs:353-507): WordPiece tokenisation (golden-pinned in
+    tests/test_tokenizer.py) -> zero padding to the batch maximum -> encoder; equal to the fp32 oracle on
+    the same token rows, and a text's embedding does not depend on what else is in the batch."""
+    import json
+    import os
+
+    from islands_b200 import Encoder
+    from islands_b200.tokenizer import BertWordPieceTokenizer
+    from oracle.encoder_oracle import bert_embed
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "tokenizer_golden.json"), encoding="utf-8") as f:
+        g = json.load(f)
+    spec = dict(g["cases"][0]["tokenizer_json"])
+    spec["model"] = dict(spec["model"], vocab=g["vocab"])
+    tok = BertWordPieceTokenizer.from_str(json.dumps(spec))
+    cfg = _small_cfg()
+    assert cfg.vocab_size >= len(g["vocab"])
+    enc = Encoder(cfg).init_random(seed=9, stddev=0.05)
+    texts = [t for t in g["texts"] if len(tok.encode(t).ids) <= cfg.max_position][:40]
+    out = enc.embed_texts_raw(tok, texts)
+    ids, _, mask = tok.encode_batch_padded(texts)
+    ref = bert_embed(enc.state_dict(), cfg, ids, mask.sum(1))
+    cos = (out * ref).sum(1) / (np.linalg.norm(out, axis=1) * np.linalg.norm(ref, axis=1))
+    assert cos.min() > 0.999, cos.min()
+    alone = enc.embed_texts_raw(tok, texts[3:4])
+    assert np.abs(alone[0] - out[3]).max() < 2e-2  # other padding length, same bf16 pipeline
+    assert enc.embed_texts_raw(tok, []).shape == (0, cfg.hidden_size)
