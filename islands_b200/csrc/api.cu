@@ -87,8 +87,19 @@ isl_status index_finish_graph(isl_index* idx) {
 isl_status index_make_padded_adjacency(isl_index* idx) {
   idx->adj_pad.release();
   idx->adj_stride = 0;
+  idx->lists_unique = false;
   const uint64_t n = idx->n, e = idx->h_nbrs.size();
   if (n == 0) return ISL_OK;
+  {
+    DevBuf<unsigned int> flag;
+    ISL_CUDA_TRY(flag.alloc(1));
+    ISL_CUDA_TRY(cudaMemsetAsync(flag.p, 0, sizeof(unsigned int), idx->stream));
+    ISL_TRY(launch_list_duplicates(idx->offsets.p, idx->nbrs.p, n, flag.p, idx->stream));
+    unsigned int h = 1;
+    ISL_CUDA_TRY(cudaMemcpyAsync(&h, flag.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, idx->stream));
+    ISL_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+    idx->lists_unique = (h == 0);
+  }
   const uint32_t stride = std::max<uint32_t>(32, round_up(idx->max_degree, 32));
   if ((uint64_t)n * stride > 2 * e + 64 * n) return ISL_OK;  // very skewed degrees: keep CSR
   ISL_CUDA_TRY(idx->adj_pad.alloc(n * stride));
@@ -100,6 +111,7 @@ isl_status index_make_padded_adjacency(isl_index* idx) {
 
 void search_args_set_graph(const isl_index* idx, SearchArgs* a) {
   a->degrees = nullptr;
+  a->lists_unique = idx->lists_unique ? 1u : 0u;
   if (idx->adj_stride) {
     a->offsets = nullptr;
     a->nbrs = idx->adj_pad.p;

@@ -70,6 +70,7 @@ struct isl_index {
   // up to 32).  Used instead of the CSR arrays when it costs at most ~2x their memory.
   isl::DevBuf<uint32_t> adj_pad; // [n][adj_stride]
   uint32_t adj_stride = 0;       // 0 => search walks the CSR arrays
+  bool lists_unique = false;     // no neighbour list names an id twice (scanned once per graph)
   // two-level search attachment
   const isl_pq* pq = nullptr;
   isl::DevBuf<uint8_t> codes8;    // [n][m] when ksub <= 256

@@ -132,6 +132,38 @@ __global__ void pad_adjacency_kernel(const uint64_t* __restrict__ offsets, const
   }
 }
 
+// One warp per node: sets *flag when a neighbour list names the same id twice.  A graph built by
+// LeannIndex::build never does (a node is linked to a neighbour once), a CSR handed to from_csr may;
+// the search keeps only the first occurrence (leann.rs:933-937), and can skip that test when no list
+// has one.
+__global__ void __launch_bounds__(256)
+list_duplicates_kernel(const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ nbrs, uint64_t n,
+                       unsigned int* __restrict__ flag) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t u = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < n; u += warps) {
+    const uint64_t s = offsets[u];
+    const uint32_t deg = (uint32_t)(offsets[u + 1] - s);
+    bool dup = false;
+    for (uint32_t b = 0; b < deg; b += 32) {
+      const bool valid = b + lane < deg;
+      const uint32_t v = valid ? nbrs[s + b + lane] : 0xffffffffu - lane;  // padding lanes never match a real id pair
+      // every warp-wide operation below is executed by all 32 lanes (b, c, t and deg are warp-uniform)
+      const uint32_t same = __match_any_sync(0xffffffffu, v);
+      const uint32_t live = __ballot_sync(0xffffffffu, valid);
+      if (valid && __popc(same & live) > 1) dup = true;
+      for (uint32_t c = 0; c < b; c += 32) {  // against the earlier chunks of the list (all full)
+        const uint32_t w = nbrs[s + c + lane];
+        for (uint32_t t = 0; t < 32; ++t) {
+          const uint32_t wt = __shfl_sync(0xffffffffu, w, t);
+          if (valid && wt == v) dup = true;
+        }
+      }
+    }
+    if (__any_sync(0xffffffffu, dup) && lane == 0) atomicExch(flag, 1u);
+  }
+}
+
 // One warp per query.  The parts*k candidates are staged in shared memory, then the k smallest
 // keys are extracted one at a time with a warp arg-min; positions (not keys) are retired, so
 // duplicate (dist,id) pairs coming from different parts are kept, as a concat+sort would.
@@ -253,6 +285,15 @@ isl_status launch_pad_adjacency(const uint64_t* d_offsets, const uint32_t* d_nbr
                                 uint32_t* d_out, cudaStream_t st) {
   if (n == 0) return ISL_OK;
   pad_adjacency_kernel<<<grid_1d(n * stride, 256), 256, 0, st>>>(d_offsets, d_nbrs, n, stride, d_out);
+  count_launch();
+  ISL_CUDA_TRY(cudaGetLastError());
+  return ISL_OK;
+}
+
+isl_status launch_list_duplicates(const uint64_t* d_offsets, const uint32_t* d_nbrs, uint64_t n, unsigned int* d_flag,
+                                  cudaStream_t st) {
+  if (n == 0) return ISL_OK;
+  list_duplicates_kernel<<<grid_1d(n * 32, 256), 256, 0, st>>>(d_offsets, d_nbrs, n, d_flag);
   count_launch();
   ISL_CUDA_TRY(cudaGetLastError());
   return ISL_OK;

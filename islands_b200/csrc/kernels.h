@@ -28,6 +28,10 @@ isl_status launch_narrow_ids(const uint64_t* d_src, uint32_t* d_dst, uint64_t co
 isl_status launch_pad_adjacency(const uint64_t* d_offsets, const uint32_t* d_nbrs, uint64_t n, uint32_t stride,
                                 uint32_t* d_out, cudaStream_t st);
 
+// Sets *d_flag (pre-zeroed) to 1 when some neighbour list holds an id twice.
+isl_status launch_list_duplicates(const uint64_t* d_offsets, const uint32_t* d_nbrs, uint64_t n, unsigned int* d_flag,
+                                  cudaStream_t st);
+
 // K8: per-query merge of [parts][nq][k] lists by (dist,id) (search.rs:211-237).
 isl_status launch_merge_topk(const uint64_t* d_ids, const float* d_dist, uint32_t parts, uint64_t nq,
                              uint32_t k, uint64_t* d_out_ids, float* d_out_dist,

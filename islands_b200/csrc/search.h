@@ -16,6 +16,7 @@ struct SearchArgs {
   const uint32_t* nbrs;     // CSR neighbours, or adjacency [n][adj_stride]
   const uint32_t* degrees;  // fixed-stride mode: live degree per node
   uint32_t adj_stride;
+  uint32_t lists_unique;    // 1 => no list holds an id twice: the first-occurrence test of a hop is skipped
   // queries
   const float* queries;     // [nq][q_ld]
   uint32_t q_ld;

@@ -119,8 +119,15 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
   uint32_t* vis = a.visited + (size_t)slot * a.vis_words;
   RView<R_SMEM> R{R_SMEM ? r_smem : a.r_global + (size_t)slot * a.ef};
   const uint32_t ef = a.ef;
-  float rk[RREG ? NR : 1];      // register-resident R: distances
-  uint32_t rid[RREG ? NR : 1];  //                      ids | expanded bit
+  // register-resident R: entry i = row i / 32 of lane i % 32, as a pair of unsigned words whose
+  // lexicographic order IS the (dist, id) order: kd = bits of the table distance (a square root: never
+  // negative, so the bit patterns order like the values; every NaN is folded onto 0x7fc00000 = greatest,
+  // OrderedFloat's rule), ki = id << 1 | expanded.  Ids are unique in R, so the flag bit never decides a
+  // comparison.  Slots past r_len hold the all-ones sentinel (greatest key, "expanded").
+  uint32_t kd[RREG ? NR : 1];
+  uint32_t ki[RREG ? NR : 1];
+  constexpr int WR0 = NR >= 2 ? NR - 2 : 0;  // the entry ef-1 sits in row NR-2 or NR-1 (NR = 2 * ceil(ef / 64))
+  const uint32_t wrow = (a.ef - 1) >> 5, wlane = (a.ef - 1) & 31;
 
   RowRing<STAGES> ring;
   ring.stage = stage;
@@ -160,8 +167,16 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     const float na = (!LEAN && a.metric == ISL_METRIC_COSINE) ? smem_sqnorm_fold(q_smem, a.d) : 0.0f;
 
     uint32_t r_len = 0, first_unexp = 0, n_ties = 0, aq_len = 0;
-    float wst_d = 0.0f;    // register R: the worst (last) entry, kept beside the rows
-    uint32_t wst_id = 0;
+    float wst_d = 0.0f;    // register R: the entry at index ef - 1 (the worst one once R is full), kept beside the rows
+    uint32_t wst_kd = 0xffffffffu, wst_ki = 0xffffffffu;
+    if constexpr (RREG) {
+#pragma unroll
+      for (int j = 0; j < NR; ++j) {
+        kd[j] = 0xffffffffu;
+        ki[j] = 0xffffffffu;
+      }
+      wst_d = __uint_as_float(wst_kd);
+    }
     uint64_t n_hop = 0, n_edge = 0, n_dist = 0, n_adc = 0, n_rerank = 0;
     const float* lut = nullptr;
     if (MODE != 0 && !(ADC && a.phase == 2)) {
@@ -228,20 +243,20 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       if constexpr (!RREG) {
         return R.ld(i);
       } else {
-        // every row is shuffled and the wanted one selected afterwards: selecting the ROW first would be
-        // turned into dynamic indexing of rk[] / rid[] and push them out of the register file
-        float dd = 0.0f;
-        uint32_t ii = 0;
+        // every row is shuffled and the wanted one selected afterwards: selecting the ROW first (by value
+        // or by a warp-uniform branch) is turned into dynamic indexing of kd[] / ki[] by the compiler and
+        // pushes them out of the register file (a stack frame in ptxas -v)
+        uint32_t sd = 0, si = 0;
 #pragma unroll
         for (int j = 0; j < NR; ++j) {
-          const float sd = __shfl_sync(FULL, rk[j], i & 31);
-          const uint32_t si = __shfl_sync(FULL, rid[j], i & 31);
+          const uint32_t td = __shfl_sync(FULL, kd[j], i & 31);
+          const uint32_t ti = __shfl_sync(FULL, ki[j], i & 31);
           if ((i >> 5) == (uint32_t)j) {
-            dd = sd;
-            ii = si;
+            sd = td;
+            si = ti;
           }
         }
-        return make_uint2(__float_as_uint(dd), ii);
+        return make_uint2(sd, ((si & 1u) ? kExpandedBit : 0u) | (si >> 1));
       }
     };
     // ---- sorted insert into R ------------------------------------------------------------------
@@ -253,35 +268,36 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       const bool full = (r_len == ef);
       uint2 evicted = make_uint2(0, 0);
       if constexpr (RREG) {
+        // position = number of keys below the new one: one 64-bit compare and one ballot per row.  Then
+        // every row at or above the position rotates up by one lane (lane 31 hands over the last entry
+        // of the row below); rows entirely below it are skipped with a warp-uniform branch.
+        const uint32_t nkd = (dnew != dnew) ? 0x7fc00000u : __float_as_uint(dnew);
+        const uint32_t nki = idnew << 1;
+        const uint64_t nkey = ((uint64_t)nkd << 32) | nki;
         pos = 0;
 #pragma unroll
         for (int j = 0; j < NR; ++j) {
-          const uint32_t idx = j * 32 + lane;
-          const bool lt = idx < r_len && key_lt(rk[j], rid[j] & ~kExpandedBit, dnew, idnew);
-          pos += __popc(__ballot_sync(FULL, lt));
+          const uint64_t key = ((uint64_t)kd[j] << 32) | ki[j];
+          pos += __popc(__ballot_sync(FULL, key < nkey));
         }
-        if (full) evicted = make_uint2(__float_as_uint(wst_d), wst_id);  // the current worst entry
+        if (full) evicted = make_uint2(wst_kd, wst_ki);  // the current worst entry (index ef - 1)
         const uint32_t top = full ? ef - 1 : r_len;
+        const uint32_t src = (lane + 31) & 31;
 #pragma unroll
         for (int j = NR - 1; j >= 0; --j) {
-          float ud = __shfl_up_sync(FULL, rk[j], 1);
-          uint32_t ui = __shfl_up_sync(FULL, rid[j], 1);
-          if (j > 0) {
-            const float pd = __shfl_sync(FULL, rk[j > 0 ? j - 1 : 0], 31);
-            const uint32_t pi = __shfl_sync(FULL, rid[j > 0 ? j - 1 : 0], 31);
-            if (lane == 0) {
-              ud = pd;
-              ui = pi;
+          if ((uint32_t)(j * 32 + 31) >= pos && (uint32_t)(j * 32) <= top) {
+            const bool hand = j > 0 && lane == 31;
+            const uint32_t ud = __shfl_sync(FULL, hand ? kd[j > 0 ? j - 1 : 0] : kd[j], src);
+            const uint32_t ui = __shfl_sync(FULL, hand ? ki[j > 0 ? j - 1 : 0] : ki[j], src);
+            const uint32_t idx = j * 32 + lane;
+            if (idx > pos && idx <= top) {
+              kd[j] = ud;
+              ki[j] = ui;
             }
-          }
-          const uint32_t idx = j * 32 + lane;
-          if (idx > pos && idx <= top) {
-            rk[j] = ud;
-            rid[j] = ui;
-          }
-          if (idx == pos) {
-            rk[j] = dnew;
-            rid[j] = idnew;
+            if (idx == pos) {
+              kd[j] = nkd;
+              ki[j] = nki;
+            }
           }
         }
       } else {
@@ -311,10 +327,11 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       }
       if (!full) r_len++;
       if (pos <= first_unexp) first_unexp = pos;
-      if constexpr (RREG) {
-        const uint2 w = r_get(r_len - 1);
-        wst_d = __uint_as_float(w.x);
-        wst_id = w.y;
+      if constexpr (RREG) {  // the entry at index ef - 1 (the sentinel until R is full)
+        wst_kd = __shfl_sync(FULL, wrow == (uint32_t)WR0 ? kd[WR0] : kd[NR - 1], wlane);
+        wst_ki = __shfl_sync(FULL, wrow == (uint32_t)WR0 ? ki[WR0] : ki[NR - 1], wlane);
+        wst_d = __uint_as_float(wst_kd);
+        if (full) evicted.y = ((evicted.y & 1u) ? kExpandedBit : 0u) | (evicted.y >> 1);
       }
       if (full && !(evicted.y & kExpandedBit)) {
         // An evicted, unexpanded node stays expandable while its distance equals the worst
@@ -423,13 +440,16 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         cur = e.y;
         uint32_t nxt = r_len;
         if constexpr (RREG) {
+          // mark it expanded and find the next unexpanded entry (sentinel slots read as expanded);
+          // rows below the popped one cannot hold it and are skipped
 #pragma unroll
           for (int j = 0; j < NR; ++j) {
-            const uint32_t idx = j * 32 + lane;
-            if (idx == first_unexp) rid[j] |= kExpandedBit;
-            const bool un = idx > first_unexp && idx < r_len && !(rid[j] & kExpandedBit);
-            const uint32_t bal = __ballot_sync(FULL, un);
-            if (bal && nxt == r_len) nxt = j * 32 + __ffs(bal) - 1;
+            if ((uint32_t)(j * 32 + 31) >= first_unexp && nxt == r_len) {
+              const uint32_t idx = j * 32 + lane;
+              if (idx == first_unexp) ki[j] |= 1u;
+              const uint32_t bal = __ballot_sync(FULL, idx > first_unexp && !(ki[j] & 1u));
+              if (bal) nxt = j * 32 + __ffs(bal) - 1;
+            }
           }
         } else {
           __syncwarp();
@@ -500,7 +520,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       n_hop++;
       if (!sentinel) n_edge += deg;
 
-      if (ADC && a.codes8 && (a.pq_m == 16 || a.pq_m == 32)) {
+      if (ADC && a.codes8 && (a.pq_m == 16 || a.pq_m == 32) && a.lut_smem_floats) {
         // ADC hop with every latency in flight at once: 64 list positions per pass (two per lane);
         // their ids are loaded, then the visited-bit atomics AND the code rows of all positions are
         // issued together (codes of already visited nodes are wasted bytes, ~15 %, but the test and
@@ -519,10 +539,13 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
           for (int r = 0; r < 2; ++r) {
             valid[r] = nid[r] != 0xffffffffu;
             if (sentinel) n_edge += __popc(__ballot_sync(FULL, valid[r]));
-            const uint32_t same = __match_any_sync(FULL, nid[r]);
-            chk[r] = valid[r] && nid[r] < a.n && lane == (uint32_t)(__ffs(same) - 1);  // first of its value in this half
+            chk[r] = valid[r] && nid[r] < a.n;
+            if (!a.lists_unique) {  // first of its value in this half
+              const uint32_t same = __match_any_sync(FULL, nid[r]);
+              chk[r] = chk[r] && lane == (uint32_t)(__ffs(same) - 1);
+            }
           }
-          if (b + 32 < deg) {  // a value of the second half that already occurs in the first is not a first occurrence
+          if (!a.lists_unique && b + 32 < deg) {  // a value of the second half that already occurs in the first is not a first occurrence
             for (uint32_t t = 0; t < 32; ++t) {
               const uint32_t v0 = __shfl_sync(FULL, nid[0], t);
               if (nid[1] == v0) chk[1] = false;
@@ -542,14 +565,16 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
             float sacc = 0.0f;  // table_distance (pq.rs:341-348): left fold over the subquantizers
+            const float* lj = lut_smem;  // the staged table: addressed as shared memory (LDS), one row per subquantizer
 #pragma unroll
             for (int v = 0; v < 2; ++v) {
               if ((uint32_t)v < nv) {
                 const uint32_t w[4] = {cw[r][v].x, cw[r][v].y, cw[r][v].z, cw[r][v].w};
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
-                  const uint32_t code = (w[k >> 2] >> ((k & 3) * 8)) & 0xffu;
-                  sacc = __fadd_rn(sacc, lut[(v * 16 + k) * a.pq_ksub + code]);
+                  const uint32_t code = __byte_perm(w[k >> 2], 0, 0x4440 + (k & 3));
+                  sacc = __fadd_rn(sacc, lj[code]);
+                  lj += a.pq_ksub;
                 }
               }
             }
@@ -673,7 +698,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
 #pragma unroll
         for (int j = 0; j < NR; ++j) {
           const uint32_t idx = j * 32 + lane;
-          if (idx < r_len) a.surv_ids[(size_t)qi * ef + idx] = rid[j] & ~kExpandedBit;
+          if (idx < r_len) a.surv_ids[(size_t)qi * ef + idx] = ki[j] >> 1;
         }
       } else {
         for (uint32_t i = lane; i < r_len; i += 32) a.surv_ids[(size_t)qi * ef + i] = R.ld(i).y & ~kExpandedBit;
