@@ -49,10 +49,12 @@ isl_status launch_one(const SearchPlan& plan, const SearchArgs& args, uint32_t g
 }
 
 template <bool R_SMEM, int NR>
-isl_status plan_lean(uint32_t ef, uint32_t u_cap, int sms, SearchPlan* plan) {
+isl_status plan_lean(uint32_t ef, uint32_t u_cap, uint32_t pq_m, int sms, SearchPlan* plan) {
   auto kern = leann_search_kernel<ACC_DOT, kCH, kStages, R_SMEM, 3, NR>;
-  const size_t smem = search_smem_bytes<kCH, kStages>(0, (R_SMEM && NR == 0) ? ef : 0, u_cap, plan->lut_smem_floats, 0, true);
+  const size_t smem = search_smem_bytes<kCH, kStages>(0, (R_SMEM && NR == 0) ? ef : 0, u_cap, plan->lut_smem_floats, 0, true) +
+                      (NR > 0 ? search_smem_bytes_idc() : 0);
   if (smem > 227 * 1024) return fail(ISL_INVALID_ARGUMENT, "search: ef needs more than 227 KB of shared memory per warp");
+  plan->novis_ok = NR > 0 && plan->lut_smem_floats != 0 && (pq_m == 16 || pq_m == 32);
   ISL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   ISL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
@@ -147,12 +149,12 @@ isl_status plan_search_adc_traverse(uint32_t ef, uint32_t u_cap, uint32_t pq_m, 
   plan->aq_smem_entries = 0;
   plan->nr = ef <= 64 ? 2 : (ef <= 128 ? 4 : (ef <= 192 ? 6 : (ef <= 256 ? 8 : 0)));
   switch (plan->nr) {
-    case 2: return plan_lean<true, 2>(ef, u_cap, sms, plan);
-    case 4: return plan_lean<true, 4>(ef, u_cap, sms, plan);
-    case 6: return plan_lean<true, 6>(ef, u_cap, sms, plan);
-    case 8: return plan_lean<true, 8>(ef, u_cap, sms, plan);
+    case 2: return plan_lean<true, 2>(ef, u_cap, pq_m, sms, plan);
+    case 4: return plan_lean<true, 4>(ef, u_cap, pq_m, sms, plan);
+    case 6: return plan_lean<true, 6>(ef, u_cap, pq_m, sms, plan);
+    case 8: return plan_lean<true, 8>(ef, u_cap, pq_m, sms, plan);
   }
-  return ef <= kEfSmemMax ? plan_lean<true, 0>(ef, u_cap, sms, plan) : plan_lean<false, 0>(ef, u_cap, sms, plan);
+  return ef <= kEfSmemMax ? plan_lean<true, 0>(ef, u_cap, pq_m, sms, plan) : plan_lean<false, 0>(ef, u_cap, pq_m, sms, plan);
 }
 
 isl_status plan_search_rerank(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap, int sms, SearchPlan* plan) {

@@ -17,6 +17,7 @@ struct SearchArgs {
   const uint32_t* degrees;  // fixed-stride mode: live degree per node
   uint32_t adj_stride;
   uint32_t lists_unique;    // 1 => no list holds an id twice: the first-occurrence test of a hop is skipped
+  uint32_t novis;           // lean ADC traversal with R in registers: no visited bitset (see search_core.cuh); needs stats == null
   // queries
   const float* queries;     // [nq][q_ld]
   uint32_t q_ld;
@@ -77,6 +78,7 @@ struct SearchPlan {
   bool two_level = false;
   int mode = 0;           // 0 exact, 1 two-level (AQ promotion), 2 ADC traversal + exact rerank, 3 ADC traversal only
   int nr = 0;             // MODE 3: result array in registers, nr entries per lane (0 = shared / global memory)
+  bool novis_ok = false;  // MODE 3: the launch may run without the visited bitset (SearchArgs::novis)
   uint32_t lut_smem_floats = 0;  // PQ table staged in shared memory (0 => read from global/L2)
   uint32_t aq_smem_entries = 0;  // approximate queue in shared memory (0 => global/L2)
   uint32_t aq_cap = 0;

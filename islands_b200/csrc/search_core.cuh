@@ -28,6 +28,7 @@
 namespace isl {
 
 constexpr uint32_t kTieCap = 64;
+constexpr uint32_t kIdcEntries = 1024;  // lean ADC traversal: direct-mapped cache of admitted ids (shared memory)
 constexpr uint32_t kExpandedBit = 0x80000000u;
 
 // lean = the ADC-traversal-only kernel (MODE 3): no row staging ring, no query vector.
@@ -38,6 +39,8 @@ __host__ __device__ constexpr size_t search_smem_bytes(uint32_t ld, uint32_t ef_
          (size_t)u_cap * 8 + (size_t)kTieCap * 8 + (size_t)STAGES * 8 + (size_t)lut_floats * 4 +
          (size_t)aq_entries * 8;
 }
+// the lean kernel with R in registers appends the admitted-id cache
+__host__ __device__ constexpr size_t search_smem_bytes_idc() { return (size_t)kIdcEntries * 4; }
 
 template <bool R_SMEM>
 struct RView {
@@ -103,6 +106,17 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(ties + kTieCap);
   float* lut_smem = reinterpret_cast<float*>(bars + STAGES);
   uint2* aq_smem = reinterpret_cast<uint2*>(lut_smem + (MODE != 0 ? a.lut_smem_floats : 0));
+  uint32_t* idc = reinterpret_cast<uint32_t*>(aq_smem + (TWO ? a.aq_smem_entries : 0));  // only laid out when NR > 0
+  // Lean ADC traversal without a visited set.  Scoring a node again can never change R: while R is not
+  // full every scored node is admitted, afterwards a node that was rejected (d >= worst) or evicted
+  // (key above the worst one) is rejected again because the worst distance only decreases, and a node
+  // that is still in R is found at its own insertion position (equal key) and dropped.  So the per-query
+  // bitset (n / 8 bytes zeroed per query, one DRAM read-modify-write per scored node: two thirds of the
+  // kernel's DRAM transactions at 1M nodes, profiles/) is replaced by that duplicate test plus a small
+  // direct-mapped cache of admitted ids that filters most repeats before they are replayed.  Ids,
+  // survivors, n_hop and n_edge are unchanged; n_adc (distinct nodes scored) is not defined in this
+  // mode, which is therefore only used when no statistics are requested.
+  const bool novis = RREG && LEAN && a.novis != 0;
 
   const uint32_t lane = lane_id();
   const uint32_t slot = blockIdx.x;
@@ -156,7 +170,9 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         float4* dst = reinterpret_cast<float4*>(q_smem);
         for (uint32_t i = lane; i < a.ld / 4; i += 32) dst[i] = src[i];
       }
-      if (!(ADC && a.phase == 2)) {  // the rerank-only launch never touches the visited set
+      if (novis) {
+        for (uint32_t i = lane; i < kIdcEntries; i += 32) idc[i] = 0xffffffffu;
+      } else if (!(ADC && a.phase == 2)) {  // the rerank-only launch never touches the visited set
         uint4* v4 = reinterpret_cast<uint4*>(vis);
         const uint4 z = make_uint4(0, 0, 0, 0);
         for (uint32_t i = lane; i < a.vis_words / 4; i += 32) __stcg(v4 + i, z);
@@ -275,10 +291,16 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         const uint32_t nki = idnew << 1;
         const uint64_t nkey = ((uint64_t)nkd << 32) | nki;
         pos = 0;
+        bool same = false;
 #pragma unroll
         for (int j = 0; j < NR; ++j) {
           const uint64_t key = ((uint64_t)kd[j] << 32) | ki[j];
           pos += __popc(__ballot_sync(FULL, key < nkey));
+          same = same || (kd[j] == nkd && (ki[j] >> 1) == idnew);
+        }
+        if (novis) {
+          if (__any_sync(FULL, same)) return;  // already in R (it sits at `pos`): scored twice, admitted once
+          if (lane == 0) idc[idnew & (kIdcEntries - 1)] = idnew;
         }
         if (full) evicted = make_uint2(wst_kd, wst_ki);  // the current worst entry (index ef - 1)
         const uint32_t top = full ? ef - 1 : r_len;
@@ -419,7 +441,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     if (traverse) {
       if (lane == 0) {
         u_list[0] = entry;
-        atomicOr(vis + (entry >> 5), 1u << (entry & 31));
+        if (!novis) atomicOr(vis + (entry >> 5), 1u << (entry & 31));
       }
       __syncwarp();
       if (ADC) {
@@ -527,6 +549,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         // the gather no longer wait for each other), then table distances, then admission in list
         // order of the positions whose bit was clear.
         const uint32_t nv = a.pq_m >> 4;  // 16-byte pieces per code row
+        if (novis) __syncwarp();          // lane 0's writes to the admitted-id cache are read by every lane below
         for (uint32_t b = 0; b < deg; b += 64) {
           uint32_t nid[2];
           bool valid[2], chk[2];
@@ -540,12 +563,12 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
             valid[r] = nid[r] != 0xffffffffu;
             if (sentinel) n_edge += __popc(__ballot_sync(FULL, valid[r]));
             chk[r] = valid[r] && nid[r] < a.n;
-            if (!a.lists_unique) {  // first of its value in this half
+            if (!a.lists_unique && !novis) {  // first of its value in this half
               const uint32_t same = __match_any_sync(FULL, nid[r]);
               chk[r] = chk[r] && lane == (uint32_t)(__ffs(same) - 1);
             }
           }
-          if (!a.lists_unique && b + 32 < deg) {  // a value of the second half that already occurs in the first is not a first occurrence
+          if (!a.lists_unique && !novis && b + 32 < deg) {  // a value of the second half that already occurs in the first is not a first occurrence
             for (uint32_t t = 0; t < 32; ++t) {
               const uint32_t v0 = __shfl_sync(FULL, nid[0], t);
               if (nid[1] == v0) chk[1] = false;
@@ -555,7 +578,12 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
           uint4 cw[2][2];
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
-            if (chk[r]) old[r] = atomicOr(vis + (nid[r] >> 5), 1u << (nid[r] & 31));
+            if (novis) {  // an id found in the admitted-id cache was admitted before: never again
+              if (chk[r] && idc[nid[r] & (kIdcEntries - 1)] == nid[r]) chk[r] = false;
+              old[r] = 0;
+            } else if (chk[r]) {
+              old[r] = atomicOr(vis + (nid[r] >> 5), 1u << (nid[r] & 31));
+            }
 #pragma unroll
             for (int v = 0; v < 2; ++v) {
               cw[r][v] = make_uint4(0, 0, 0, 0);

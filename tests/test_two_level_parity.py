@@ -73,6 +73,11 @@ def test_adc_traversal_rerank_matches_oracle(gpu_lib, orc, m, ksub):
         for f in ("n_hop", "n_edge", "n_dist", "n_adc", "n_rerank"):
             assert np.array_equal(getattr(st, f), o_st[f]), f
         assert (np.diff(dist, axis=1) >= 0).all()  # exact distances, ascending
+        # without statistics the traversal (ef <= 256, m = 16 / 32) runs without the visited bitset: nodes may be
+        # scored twice, the survivors and therefore the results must not change
+        ids2, dist2, cnt2 = idx.search_adc_rerank_batch(q, k, ef)
+        assert np.array_equal(cnt2, o_cnt) and np.array_equal(ids2, o_ids)
+        assert np.array_equal(dist2.view(np.uint32), o_dist.view(np.uint32))
 
 
 @pytest.mark.parametrize("m,ksub", [(32, 256), (8, 256)])
@@ -106,6 +111,38 @@ def test_adc_traversal_with_duplicate_neighbours(gpu_lib, orc, m, ksub):
         assert np.array_equal(ids, o_ids) and np.array_equal(dist.view(np.uint32), o_dist.view(np.uint32))
         for f in ("n_hop", "n_edge", "n_adc", "n_rerank"):
             assert np.array_equal(getattr(st, f), o_st[f]), f
+        ids2, dist2, _ = idx.search_adc_rerank_batch(q, k, ef)  # no statistics: traversal without the visited bitset
+        assert np.array_equal(ids2, o_ids) and np.array_equal(dist2.view(np.uint32), o_dist.view(np.uint32))
         e_ids, e_dist, _ = idx.search_batch(q, k, ef)
         x_ids, x_dist, _ = orc.leann_search(cfg._s, v, off, nbrs, entry, q, k, ef, threads=8)
         assert np.array_equal(e_ids, x_ids) and np.array_equal(e_dist.view(np.uint32), x_dist.view(np.uint32))
+
+
+@pytest.mark.parametrize("m,ksub", [(32, 64), (16, 128)])
+def test_adc_traversal_ties_with_and_without_visited_set(gpu_lib, orc, m, ksub):
+    """A third of the base vectors are exact copies of others (identical PQ codes => exact ties of
+    the table distance between different ids), small ef so that R evicts constantly.  The traversal with
+    statistics (visited bitset) and the one without (no visited set: duplicates are recognised in R, the
+    worst distance only decreases) must both return the oracle's ids and distances."""
+    from islands_b200 import LeannIndex, PQConfig, ProductQuantizer
+
+    cfg, v, levels, off, nbrs, entry = oracle_graph(orc, 3000, 96, seed=71, dup=1000)
+    cb = orc.pq_train(1, v[:1500], m, ksub, 3, 7)
+    codes = orc.pq_encode(1, cb, v)
+    assert np.array_equal(codes[:1000], codes[2000:])  # the copies carry the same codes
+    pq = ProductQuantizer(96, PQConfig(m, ksub, 3, 7))
+    pq.set_codebooks(cb)
+    idx = LeannIndex.from_csr(cfg, v, off, nbrs, levels, entry)
+    idx.attach_pq(pq, codes)
+    q = np.concatenate([uniform(np.random.RandomState(72), 150, 96), v[:50]])
+    for k, ef in [(5, 8), (10, 24), (10, 64), (20, 130), (10, 256)]:
+        ids, dist, cnt, st = idx.search_adc_rerank_batch(q, k, ef, stats=True)
+        o_ids, o_dist, o_cnt, o_st = orc.leann_search_adc_rerank(cfg._s, v, off, nbrs, entry, cb, codes, q, k, ef,
+                                                                 threads=8, stats=True)
+        assert np.array_equal(cnt, o_cnt) and np.array_equal(ids, o_ids)
+        assert np.array_equal(dist.view(np.uint32), o_dist.view(np.uint32))
+        for f in ("n_hop", "n_edge", "n_adc", "n_rerank"):
+            assert np.array_equal(getattr(st, f), o_st[f]), f
+        ids2, dist2, cnt2 = idx.search_adc_rerank_batch(q, k, ef)
+        assert np.array_equal(cnt2, o_cnt) and np.array_equal(ids2, o_ids), (k, ef)
+        assert np.array_equal(dist2.view(np.uint32), o_dist.view(np.uint32))
