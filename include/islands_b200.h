@@ -352,6 +352,13 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
                                           uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* out_ids,
                                           float* out_dist, uint32_t* out_count,
                                           isl_search_stats* stats_or_null);
+/* Hub-embedding cache (docs/leann-specification.md:661-690 `HubCache`): keep the embeddings of the `count`
+ * nodes with the highest in-degree (ties: smaller id) resident; the recompute search skips them.  They are
+ * computed with the attached encoder, so results are bit-identical with and without the cache.
+ * count == 0 drops the cache; attaching another provider drops it too. */
+isl_status isl_index_set_hub_cache(isl_index* idx, uint64_t count);
+/* Cached nodes, and how many distinct survivors of the last recompute search were served from the cache. */
+isl_status isl_index_hub_cache_info(const isl_index* idx, uint64_t* cached_nodes, uint64_t* last_hits);
 /* Nodes recomputed by the last recompute search and the CUDA-event time of its three stages. */
 isl_status isl_index_last_recompute(const isl_index* idx, uint64_t* unique_nodes, float* traverse_ms,
                                     float* encoder_ms, float* rerank_ms);

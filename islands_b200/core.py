@@ -630,7 +630,17 @@ def _last_recompute(self):
     u = C.c_uint64()
     a, b, c = C.c_float(), C.c_float(), C.c_float()
     _check(_ffi.load().isl_index_last_recompute(self._h, C.byref(u), C.byref(a), C.byref(b), C.byref(c)))
-    return dict(unique_nodes=u.value, traverse_ms=a.value, encoder_ms=b.value, rerank_ms=c.value)
+    h, hits = C.c_uint64(), C.c_uint64()
+    _check(_ffi.load().isl_index_hub_cache_info(self._h, C.byref(h), C.byref(hits)))
+    return dict(unique_nodes=u.value, traverse_ms=a.value, encoder_ms=b.value, rerank_ms=c.value,
+                hub_cache_nodes=h.value, hub_cache_hits=hits.value)
+
+
+def _set_hub_cache(self, count):
+    """`HubCache` of docs/leann-specification.md:661-690: keep the embeddings of the `count` highest
+    in-degree nodes resident so that the recompute search does not run them through the encoder
+    (isl_index_set_hub_cache).  0 drops the cache."""
+    _check(_ffi.load().isl_index_set_hub_cache(self._h, int(count)))
 
 
 def _bytes_out(fn, handle):
@@ -708,6 +718,7 @@ LeannIndex.set_recompute = _set_recompute
 LeannIndex.drop_vectors = _drop_vectors
 LeannIndex.search_adc_recompute_batch = _adc_recompute
 LeannIndex.last_recompute = _last_recompute
+LeannIndex.set_hub_cache = _set_hub_cache
 
 
 def random_level(u, ml, max_layers):

@@ -79,6 +79,12 @@ struct isl_index {
   isl_encoder* encoder = nullptr;
   isl::DevBuf<int32_t> node_tokens;   // [n][tok_len]
   isl::DevBuf<int32_t> node_lengths;  // [n]
+  // hub-embedding cache (docs/leann-specification.md:661-690): resident rows of the highest in-degree nodes
+  uint64_t hub_count = 0;
+  isl::DevBuf<float> hub_emb;         // [hub_count][ld]
+  isl::DevBuf<float> hub_sq;          // [hub_count]
+  isl::DevBuf<uint32_t> hub_row;      // [n] row in hub_emb or 0xffffffff
+  mutable uint64_t last_hub_hits = 0;
   uint32_t tok_len = 0;
   mutable isl::DevBuf<uint32_t> rc_flags, rc_rows, rc_surv, rc_surv_cnt;
   mutable isl::DevBuf<int32_t> rc_tok, rc_len;

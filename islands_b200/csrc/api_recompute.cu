@@ -38,6 +38,39 @@ __global__ void gather_tokens_kernel(const uint32_t* __restrict__ flags, const u
   }
 }
 
+// Hub cache: survivors whose embedding is resident are not recomputed.
+__global__ void clear_cached_flags_kernel(const uint32_t* __restrict__ hub_row, uint32_t n, uint32_t* __restrict__ flags,
+                                          unsigned int* __restrict__ hits) {
+  uint32_t local = 0;
+  for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
+    if (flags[id] && hub_row[id] != 0xffffffffu) {
+      flags[id] = 0u;
+      local++;
+    }
+  }
+  local = __reduce_add_sync(0xffffffffu, local);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(hits, local);
+}
+
+// row of the rerank matrix per node id: cached hubs first ([0, hubs)), recomputed rows after them
+__global__ void final_rows_kernel(const uint32_t* __restrict__ hub_row, uint32_t hubs, uint32_t n, uint32_t* __restrict__ rows) {
+  for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n; id += gridDim.x * blockDim.x) {
+    const uint32_t h = hub_row[id];
+    rows[id] = h != 0xffffffffu ? h : hubs + rows[id];
+  }
+}
+
+__global__ void gather_rows_by_id_kernel(const uint64_t* __restrict__ ids, uint32_t count, const int32_t* __restrict__ tokens,
+                                         const int32_t* __restrict__ lengths, uint32_t S, int32_t* __restrict__ out_tok,
+                                         int32_t* __restrict__ out_len) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5, lane = threadIdx.x & 31;
+  for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < count; r += warps) {
+    const uint64_t id = ids[r];
+    for (uint32_t i = lane; i < S; i += 32) out_tok[(size_t)r * S + i] = tokens[id * S + i];
+    if (lane == 0) out_len[r] = lengths[id];
+  }
+}
+
 }  // namespace
 }  // namespace isl
 
@@ -55,6 +88,10 @@ isl_status isl_index_set_recompute(isl_index* idx, isl_encoder* enc, const int32
     idx->node_tokens.release();
     idx->node_lengths.release();
     idx->tok_len = 0;
+    idx->hub_count = 0;
+    idx->hub_emb.release();
+    idx->hub_sq.release();
+    idx->hub_row.release();
     return ISL_OK;
   }
   if (idx->n && (!token_ids || !lengths)) return fail(ISL_INVALID_ARGUMENT, "token_ids / lengths is null");
@@ -71,6 +108,67 @@ isl_status isl_index_set_recompute(isl_index* idx, isl_encoder* enc, const int32
   }
   idx->encoder = enc;
   idx->tok_len = seq_len;
+  idx->hub_count = 0;  // a cache built with another provider is void
+  idx->hub_emb.release();
+  idx->hub_sq.release();
+  idx->hub_row.release();
+  return ISL_OK;
+}
+
+// Hub-embedding cache (docs/leann-specification.md:661-690): the `count` nodes with the highest in-degree
+// (ties: smaller id) keep their embedding resident — they are the rows a traversal reaches most often —
+// and the recompute search skips them.  Computed with the attached encoder, so cached and recomputed
+// rows are the same bits.  count == 0 drops the cache.
+isl_status isl_index_set_hub_cache(isl_index* idx, uint64_t count) {
+  if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
+  DeviceGuard g(idx->device);
+  std::lock_guard<std::mutex> lock(idx->mu);
+  if (!idx->encoder) return fail(ISL_INVALID_ARGUMENT, "no recompute encoder attached (isl_index_set_recompute)");
+  idx->hub_count = 0;
+  idx->hub_emb.release();
+  idx->hub_sq.release();
+  idx->hub_row.release();
+  const uint64_t n = idx->n;
+  count = std::min<uint64_t>(count, n);
+  if (count == 0) return ISL_OK;
+  std::vector<uint32_t> indeg(n, 0);
+  for (uint64_t v : idx->h_nbrs)
+    if (v < n) indeg[v]++;
+  std::vector<uint64_t> order(n);
+  for (uint64_t i = 0; i < n; ++i) order[i] = i;
+  auto hotter = [&](uint64_t a, uint64_t b) { return indeg[a] != indeg[b] ? indeg[a] > indeg[b] : a < b; };
+  std::nth_element(order.begin(), order.begin() + (count - 1), order.end(), hotter);
+  order.resize(count);
+  std::sort(order.begin(), order.end());  // cache rows in ascending id order
+  std::vector<uint32_t> h_row(n, 0xffffffffu);
+  for (uint64_t r = 0; r < count; ++r) h_row[order[r]] = (uint32_t)r;
+  const uint32_t S = idx->tok_len;
+  DevBuf<uint64_t> d_ids;
+  DevBuf<int32_t> tok, len;
+  ISL_CUDA_TRY(d_ids.alloc(count));
+  ISL_CUDA_TRY(tok.alloc(count * S));
+  ISL_CUDA_TRY(len.alloc(count));
+  ISL_CUDA_TRY(idx->hub_row.alloc(n));
+  ISL_CUDA_TRY(idx->hub_emb.alloc(count * idx->ld));
+  ISL_CUDA_TRY(idx->hub_sq.alloc(count));
+  cudaStream_t st = idx->stream;
+  ISL_CUDA_TRY(cudaMemcpyAsync(d_ids.p, order.data(), count * 8, cudaMemcpyHostToDevice, st));
+  ISL_CUDA_TRY(cudaMemcpyAsync(idx->hub_row.p, h_row.data(), n * 4, cudaMemcpyHostToDevice, st));
+  gather_rows_by_id_kernel<<<1184, 256, 0, st>>>(d_ids.p, (uint32_t)count, idx->node_tokens.p, idx->node_lengths.p, S, tok.p, len.p);
+  count_launch();
+  ISL_CUDA_TRY(cudaGetLastError());
+  ISL_CUDA_TRY(cudaStreamSynchronize(st));
+  ISL_TRY(isl_encoder_embed_dev(idx->encoder, tok.p, len.p, count, S, idx->hub_emb.p));
+  ISL_TRY(launch_row_sqnorms(idx->hub_emb.p, count, idx->dim, idx->ld, idx->hub_sq.p, idx->sms, st));
+  ISL_CUDA_TRY(cudaStreamSynchronize(st));
+  idx->hub_count = count;
+  return ISL_OK;
+}
+
+isl_status isl_index_hub_cache_info(const isl_index* idx, uint64_t* cached_nodes, uint64_t* last_hits) {
+  if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
+  if (cached_nodes) *cached_nodes = idx->hub_count;
+  if (last_hits) *last_hits = idx->last_hub_hits;
   return ISL_OK;
 }
 
@@ -176,30 +274,50 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
   ISL_CUDA_TRY(cudaMemsetAsync(idx->rc_flags.p, 0, ((size_t)n + 1) * 4, st));
   mark_survivors_kernel<<<1184, 256, 0, st>>>(idx->rc_surv.p, idx->rc_surv_cnt.p, (uint32_t)nq, ef, idx->rc_flags.p);
   count_launch();
+  const uint32_t hubs = (uint32_t)idx->hub_count;
+  if (hubs) {  // survivors with a resident embedding are not recomputed
+    ISL_CUDA_TRY(cudaMemsetAsync(idx->counters.p + 2, 0, sizeof(unsigned int), st));
+    clear_cached_flags_kernel<<<1184, 256, 0, st>>>(idx->hub_row.p, n, idx->rc_flags.p, idx->counters.p + 2);
+    count_launch();
+  }
   size_t scan_bytes = 0;
   ISL_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, idx->rc_flags.p, idx->rc_rows.p, (int)(n + 1), st));
   ISL_TRY(ensure(idx->rc_tmp, scan_bytes + 16));
   ISL_CUDA_TRY(cub::DeviceScan::ExclusiveSum(idx->rc_tmp.p, scan_bytes, idx->rc_flags.p, idx->rc_rows.p, (int)(n + 1), st));
   count_launch(2);
-  uint32_t unique = 0;
+  uint32_t unique = 0, hub_hits = 0;
   ISL_CUDA_TRY(cudaMemcpyAsync(&unique, idx->rc_rows.p + n, 4, cudaMemcpyDeviceToHost, st));
+  if (hubs) ISL_CUDA_TRY(cudaMemcpyAsync(&hub_hits, idx->counters.p + 2, 4, cudaMemcpyDeviceToHost, st));
   ISL_CUDA_TRY(cudaStreamSynchronize(st));
+  idx->last_hub_hits = hub_hits;
   float ms = 0.0f;
   if (cudaEventElapsedTime(&ms, idx->ev0, idx->ev1) == cudaSuccess) idx->last_traverse_ms = ms;
   const uint32_t S = idx->tok_len;
   ISL_TRY(ensure(idx->rc_tok, (size_t)unique * S + 1));
   ISL_TRY(ensure(idx->rc_len, (size_t)unique + 1));
-  ISL_TRY(ensure(idx->rc_emb, (size_t)unique * idx->ld + 4));
-  ISL_TRY(ensure(idx->rc_sq, (size_t)unique + 1));
+  // rerank matrix: [cached hub rows | rows recomputed for this batch]
+  ISL_TRY(ensure(idx->rc_emb, ((size_t)hubs + unique) * idx->ld + 4));
+  ISL_TRY(ensure(idx->rc_sq, (size_t)hubs + unique + 1));
+  if (hubs) {
+    ISL_CUDA_TRY(cudaMemcpyAsync(idx->rc_emb.p, idx->hub_emb.p, (size_t)hubs * idx->ld * 4, cudaMemcpyDeviceToDevice, st));
+    ISL_CUDA_TRY(cudaMemcpyAsync(idx->rc_sq.p, idx->hub_sq.p, (size_t)hubs * 4, cudaMemcpyDeviceToDevice, st));
+  }
   gather_tokens_kernel<<<1184, 256, 0, st>>>(idx->rc_flags.p, idx->rc_rows.p, n, idx->node_tokens.p, idx->node_lengths.p, S,
                                             idx->rc_tok.p, idx->rc_len.p);
   count_launch();
   ISL_CUDA_TRY(cudaGetLastError());
   ISL_CUDA_TRY(cudaStreamSynchronize(st));
-  ISL_TRY(isl_encoder_embed_dev(idx->encoder, idx->rc_tok.p, idx->rc_len.p, unique, S, idx->rc_emb.p));
-  isl_encoder_last_timing(idx->encoder, &idx->last_encoder_ms, nullptr);
+  idx->last_encoder_ms = 0.0f;
+  if (unique) {
+    ISL_TRY(isl_encoder_embed_dev(idx->encoder, idx->rc_tok.p, idx->rc_len.p, unique, S, idx->rc_emb.p + (size_t)hubs * idx->ld));
+    isl_encoder_last_timing(idx->encoder, &idx->last_encoder_ms, nullptr);
+    ISL_TRY(launch_row_sqnorms(idx->rc_emb.p + (size_t)hubs * idx->ld, unique, idx->dim, idx->ld, idx->rc_sq.p + hubs, idx->sms, st));
+  }
   idx->last_recomputed = unique;
-  ISL_TRY(launch_row_sqnorms(idx->rc_emb.p, unique, idx->dim, idx->ld, idx->rc_sq.p, idx->sms, st));
+  if (hubs) {
+    final_rows_kernel<<<1184, 256, 0, st>>>(idx->hub_row.p, hubs, n, idx->rc_rows.p);
+    count_launch();
+  }
 
   // ---- 3. exact rerank against the recomputed rows ---------------------------------------------------
   ISL_CUDA_TRY(cudaMemsetAsync(idx->counters.p, 0, sizeof(unsigned int), st));

@@ -121,3 +121,47 @@ def test_recompute_errors(gpu_lib):
         index.set_recompute(enc64, np.ones((300, 8), np.int32), np.full(300, 8, np.int32))
     with pytest.raises(InvalidArgument):
         index.drop_vectors()  # nothing attached: refusing beats silently losing the only copy
+
+
+def test_hub_cache_same_bits_fewer_recomputed_rows(gpu_lib):
+    """Hub-embedding cache (docs/leann-specification.md:661-690): the highest in-degree nodes keep their
+    embedding resident.  Results are the same bits with and without the cache (the cached rows were produced
+    by the same encoder), fewer rows go through the encoder, and the hits + recomputed rows add up to the
+    distinct survivors."""
+    n, nq, S, k, ef = 3000, 200, 16, 10, 64
+    enc, cfg_e, tok, ln, _, queries = _setup(n, nq, S)
+    stored = enc.embed(tok, ln)
+    index, pq = _index_over(stored, n)
+    index.set_recompute(enc, tok, ln)
+    ids_a, dist_a, cnt_a = index.search_adc_recompute_batch(queries, k, ef)
+    base = index.last_recompute()
+    assert base["hub_cache_nodes"] == 0 and base["hub_cache_hits"] == 0
+    index.set_hub_cache(300)
+    ids_b, dist_b, cnt_b = index.search_adc_recompute_batch(queries, k, ef)
+    info = index.last_recompute()
+    assert info["hub_cache_nodes"] == 300
+    assert info["hub_cache_hits"] > 0
+    assert info["unique_nodes"] + info["hub_cache_hits"] == base["unique_nodes"]
+    # hubs are over-represented among the survivors: 10 % of the nodes serve more than 10 % of them
+    assert info["hub_cache_hits"] / base["unique_nodes"] > 0.1
+    assert np.array_equal(cnt_a, cnt_b) and np.array_equal(ids_a, ids_b)
+    assert np.array_equal(dist_a.view(np.uint32), dist_b.view(np.uint32))
+    # the cached nodes are the highest in-degree ones (ties: smaller id)
+    g = index.graph
+    indeg = np.bincount(np.asarray(g.neighbors, np.int64), minlength=n)
+    order = np.lexsort((np.arange(n), -indeg))[:300]
+    # every node cached <=> every survivor among `order` is a hit: check through a cache of everything
+    index.set_hub_cache(n)
+    ids_c, dist_c, _ = index.search_adc_recompute_batch(queries, k, ef)
+    full = index.last_recompute()
+    assert full["unique_nodes"] == 0 and full["hub_cache_hits"] == base["unique_nodes"] and full["encoder_ms"] == 0
+    assert np.array_equal(ids_a, ids_c) and np.array_equal(dist_a.view(np.uint32), dist_c.view(np.uint32))
+    assert indeg[order].min() >= np.sort(indeg)[::-1][299]
+    index.set_hub_cache(0)
+    index.search_adc_recompute_batch(queries, k, ef)
+    assert index.last_recompute()["hub_cache_nodes"] == 0 and index.last_recompute()["unique_nodes"] == base["unique_nodes"]
+    # a cache needs a provider
+    index.set_recompute(None, None, None)
+    from islands_b200 import InvalidArgument
+    with pytest.raises(InvalidArgument):
+        index.set_hub_cache(10)
