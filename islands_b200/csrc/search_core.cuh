@@ -290,17 +290,20 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         const uint32_t nkd = (dnew != dnew) ? 0x7fc00000u : __float_as_uint(dnew);
         const uint32_t nki = idnew << 1;
         const uint64_t nkey = ((uint64_t)nkd << 32) | nki;
+        if (novis) {
+          // a node that is already in R (ids are unique there) was scored twice: admitted once.  Tested before
+          // the position is computed, so that a repeat costs one compare per row and a vote.
+          bool same = false;
+#pragma unroll
+          for (int j = 0; j < NR; ++j) same = same || ((ki[j] ^ nki) < 2u);
+          if (__any_sync(FULL, same)) return;
+          if (lane == 0) idc[idnew & (kIdcEntries - 1)] = idnew;
+        }
         pos = 0;
-        bool same = false;
 #pragma unroll
         for (int j = 0; j < NR; ++j) {
           const uint64_t key = ((uint64_t)kd[j] << 32) | ki[j];
           pos += __popc(__ballot_sync(FULL, key < nkey));
-          same = same || (kd[j] == nkd && (ki[j] >> 1) == idnew);
-        }
-        if (novis) {
-          if (__any_sync(FULL, same)) return;  // already in R (it sits at `pos`): scored twice, admitted once
-          if (lane == 0) idc[idnew & (kIdcEntries - 1)] = idnew;
         }
         if (full) evicted = make_uint2(wst_kd, wst_ki);  // the current worst entry (index ef - 1)
         const uint32_t top = full ? ef - 1 : r_len;
