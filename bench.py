@@ -40,8 +40,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="islands_b200", choices=["islands_b200", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000)
-    ap.add_argument("--d", type=int, default=768)
+    # (the long spellings exist because torchrun's own parser claims "--n" / "--d" prefixes when it launches this script)
+    ap.add_argument("--n", "--island-nodes", dest="n", type=int, default=1_000_000)
+    ap.add_argument("--d", "--dim", dest="d", type=int, default=768)
     ap.add_argument("--nq", type=int, default=10_000)
     ap.add_argument("--dataset", type=str, default="latent32", choices=["latent32", "uniform"])
     ap.add_argument("--ef", type=int, default=0, help="0 = smallest ef of the ladder with recall@10 >= 0.95")

@@ -352,6 +352,12 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
                                           uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* out_ids,
                                           float* out_dist, uint32_t* out_count,
                                           isl_search_stats* stats_or_null);
+/* "PQ ADC traversal + exact rerank" and its recompute form: give an exact distance (and, with recompute, an
+ * encoder pass) only to the `limit` survivors with the best table distance instead of all ef — the
+ * traversal stays wide, the expensive half shrinks (the role of the rerank ratio `a` of
+ * docs/leann-specification.md:223-269 for a traversal that runs entirely on table distances).
+ * The effective limit is max(limit, k); 0 (default) reranks every survivor. */
+isl_status isl_index_set_rerank_limit(isl_index* idx, uint32_t limit);
 /* Hub-embedding cache (docs/leann-specification.md:661-690 `HubCache`): keep the embeddings of the `count`
  * nodes with the highest in-degree (ties: smaller id) resident; the recompute search skips them.  They are
  * computed with the attached encoder, so results are bit-identical with and without the cache.

@@ -721,6 +721,15 @@ LeannIndex.last_recompute = _last_recompute
 LeannIndex.set_hub_cache = _set_hub_cache
 
 
+def _set_rerank_limit(self, limit):
+    """ADC traversal + exact rerank / recompute: only the `limit` survivors with the best table distance
+    get an exact distance (isl_index_set_rerank_limit); 0 = all ef survivors."""
+    _check(_ffi.load().isl_index_set_rerank_limit(self._h, int(limit)))
+
+
+LeannIndex.set_rerank_limit = _set_rerank_limit
+
+
 def random_level(u, ml, max_layers):
     """LeannIndex::random_level (leann.rs:549-554) for an explicit uniform draw u in (0,1)."""
     lvl = math.floor(-math.log(u) * ml)

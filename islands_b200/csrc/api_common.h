@@ -85,6 +85,7 @@ struct isl_index {
   isl::DevBuf<float> hub_sq;          // [hub_count]
   isl::DevBuf<uint32_t> hub_row;      // [n] row in hub_emb or 0xffffffff
   mutable uint64_t last_hub_hits = 0;
+  uint32_t rerank_limit = 0;  // ADC traversal + rerank / recompute: survivors that get an exact distance (0 = all ef)
   uint32_t tok_len = 0;
   mutable isl::DevBuf<uint32_t> rc_flags, rc_rows, rc_surv, rc_surv_cnt;
   mutable isl::DevBuf<int32_t> rc_tok, rc_len;

@@ -265,6 +265,7 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
   a.pq_ksub = pq->ksub;
   a.lut_smem_floats = plan.lut_smem_floats;
   a.phase = 1;
+  a.rerank_limit = idx->rerank_limit ? std::max(idx->rerank_limit, k) : 0u;
   a.surv_ids = idx->rc_surv.p;
   a.surv_cnt = idx->rc_surv_cnt.p;
   ISL_TRY(launch_search(plan, a, st));

@@ -125,6 +125,7 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
     a.pq_ksub = pq->ksub;
     a.lut_smem_floats = pt.lut_smem_floats;
     a.phase = 1;
+    a.rerank_limit = idx->rerank_limit ? std::max(idx->rerank_limit, k) : 0u;
     a.surv_ids = idx->rc_surv.p;
     a.surv_cnt = idx->rc_surv_cnt.p;
     ISL_TRY(launch_search(pt, a, st));
@@ -225,6 +226,13 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
   if (stats)
     ISL_CUDA_TRY(cudaMemcpyAsync(stats, idx->out_stats.p, nq * sizeof(isl_search_stats), cudaMemcpyDeviceToHost, st));
   return search_finish(idx);
+}
+
+isl_status isl_index_set_rerank_limit(isl_index* idx, uint32_t limit) {
+  if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
+  std::lock_guard<std::mutex> lock(idx->mu);
+  idx->rerank_limit = limit;
+  return ISL_OK;
 }
 
 isl_status isl_index_search_two_level(const isl_index* idx, const float* queries, uint64_t nq,

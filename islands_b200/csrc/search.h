@@ -62,6 +62,7 @@ struct SearchArgs {
   // ef survivors are written to surv_ids / surv_cnt; phase 2 = exact rerank only of cand lists
   // against rows addressed through row_of_id (recomputed embeddings live in a compact matrix)
   uint32_t phase;              // 0 = both in one launch
+  uint32_t rerank_limit;       // phase 1: hand over at most this many survivors, best table distance first (0 = all ef)
   uint32_t* surv_ids;          // [nq][ef]   (phase 1 out, phase 2 in)
   uint32_t* surv_cnt;          // [nq]
   const uint32_t* row_of_id;   // node id -> row of `vectors` / `sqnorms` (null => identity)

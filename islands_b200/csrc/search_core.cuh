@@ -724,18 +724,20 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     }
 
     if (ADC && (LEAN || a.phase == 1)) {
-      // traversal-only launch: hand the ef survivors (ascending adc order) to the rerank / recompute step
+      // traversal-only launch: hand the ef survivors (ascending adc order) to the rerank / recompute step;
+      // with a rerank limit only the best of them (isl_index_set_rerank_limit)
+      const uint32_t n_surv = a.rerank_limit ? min(r_len, a.rerank_limit) : r_len;
       if constexpr (RREG) {
 #pragma unroll
         for (int j = 0; j < NR; ++j) {
           const uint32_t idx = j * 32 + lane;
-          if (idx < r_len) a.surv_ids[(size_t)qi * ef + idx] = ki[j] >> 1;
+          if (idx < n_surv) a.surv_ids[(size_t)qi * ef + idx] = ki[j] >> 1;
         }
       } else {
-        for (uint32_t i = lane; i < r_len; i += 32) a.surv_ids[(size_t)qi * ef + i] = R.ld(i).y & ~kExpandedBit;
+        for (uint32_t i = lane; i < n_surv; i += 32) a.surv_ids[(size_t)qi * ef + i] = R.ld(i).y & ~kExpandedBit;
       }
       if (lane == 0) {
-        a.surv_cnt[qi] = r_len;
+        a.surv_cnt[qi] = n_surv;
         if (a.stats) {
           isl_search_stats s;
           s.n_hop = n_hop;

@@ -767,7 +767,8 @@ int32_t orc_leann_search_adc_rerank(const isl_leann_config* cfg, const float* ve
                                     const uint64_t* offsets, const uint64_t* nbrs, int64_t entry,
                                     const float* codebooks, uint32_t m, uint32_t ksub, const uint16_t* codes,
                                     const float* queries, uint64_t nq, uint32_t k, uint32_t ef_in, uint64_t* out_ids,
-                                    float* out_dist, uint32_t* out_count, isl_search_stats* stats, int32_t threads) {
+                                    float* out_dist, uint32_t* out_count, isl_search_stats* stats, int32_t threads,
+                                    uint32_t rerank_limit) {
   if (n == 0) {
     for (uint64_t qi = 0; qi < nq; ++qi) {
       std::vector<Key> none;
@@ -784,7 +785,7 @@ int32_t orc_leann_search_adc_rerank(const isl_leann_config* cfg, const float* ve
   std::vector<Visited> vis(nt);
   parallel_for(nq, threads, [&](uint64_t b, uint64_t e, int w) {
     std::vector<float> lut((uint64_t)m * ksub);
-    std::vector<Key> res;
+    std::vector<Key> res, surv;
     auto adc = [&](uint64_t id) {
       float s = 0.0f;
       const uint16_t* cd = codes + id * (uint64_t)m;
@@ -824,12 +825,19 @@ int32_t orc_leann_search_adc_rerank(const isl_leann_config* cfg, const float* ve
           }
         }
       }
-      res.clear();
+      // the survivors in ascending (adc, id) order; with a rerank limit only the first max(limit, k) of them
+      // get an exact distance (isl_index_set_rerank_limit)
+      surv.clear();
       while (!results.empty()) {
-        Key r = results.top();
+        surv.push_back(results.top());
         results.pop();
-        res.push_back({calc(cfg->metric, q, vectors + r.id * (uint64_t)d, d), r.id});  // exact rerank
       }
+      std::sort(surv.begin(), surv.end(), key_lt);
+      uint64_t keep = surv.size();
+      if (rerank_limit) keep = std::min<uint64_t>(keep, std::max<uint64_t>(rerank_limit, k));
+      res.clear();
+      for (uint64_t i = 0; i < keep; ++i)
+        res.push_back({calc(cfg->metric, q, vectors + surv[i].id * (uint64_t)d, d), surv[i].id});  // exact rerank
       std::sort(res.begin(), res.end(), key_lt);
       write_topk(res, k, out_ids + qi * k, out_dist + qi * k, out_count ? out_count + qi : nullptr);
       if (stats) stats[qi] = isl_search_stats{n_hop, n_edge, res.size(), n_adc, res.size()};

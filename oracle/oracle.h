@@ -96,7 +96,8 @@ int32_t orc_leann_search_adc_rerank(const isl_leann_config* cfg, const float* ve
                                     const float* codebooks, uint32_t m, uint32_t ksub, const uint16_t* codes,
                                     const float* queries, uint64_t nq, uint32_t k, uint32_t ef, uint64_t* out_ids,
                                     float* out_dist, uint32_t* out_count, isl_search_stats* stats_or_null,
-                                    int32_t threads);
+                                    int32_t threads,
+                                    uint32_t rerank_limit /* 0 = every survivor */);
 
 /* search.rs:211-237 under the (dist,id) rule: lists [parts][nq][k]. */
 void orc_merge_topk(const uint64_t* ids, const float* dist, uint32_t parts, uint64_t nq, uint32_t k,

@@ -70,7 +70,7 @@ def lib():
         l.orc_leann_search_adc_rerank.restype = C.c_int32
         l.orc_leann_search_adc_rerank.argtypes = [C.c_void_p, f32p, C.c_uint64, C.c_uint32, u64p, u64p, C.c_int64,
                                                   f32p, C.c_uint32, C.c_uint32, u16p, f32p, C.c_uint64, C.c_uint32,
-                                                  C.c_uint32, u64p, f32p, u32p, C.c_void_p, C.c_int32]
+                                                  C.c_uint32, u64p, f32p, u32p, C.c_void_p, C.c_int32, C.c_uint32]
         l.orc_merge_topk.restype = None
         l.orc_merge_topk.argtypes = [u64p, f32p, C.c_uint32, C.c_uint64, C.c_uint32, u64p, f32p, u32p]
         l.orc_to_similarity.restype = C.c_float
@@ -254,7 +254,8 @@ def leann_search_two_level(cfg, vectors, offsets, nbrs, entry, codebooks, codes,
     return (ids, dist, cnt, st) if stats else (ids, dist, cnt)
 
 
-def leann_search_adc_rerank(cfg, vectors, offsets, nbrs, entry, codebooks, codes, queries, k, ef, threads=1, stats=False):
+def leann_search_adc_rerank(cfg, vectors, offsets, nbrs, entry, codebooks, codes, queries, k, ef, threads=1, stats=False,
+                            rerank_limit=0):
     vectors, queries, cb = _f32(vectors), _f32(queries), _f32(codebooks)
     offsets = np.ascontiguousarray(offsets, np.uint64)
     nbrs = np.ascontiguousarray(nbrs, np.uint64)
@@ -269,7 +270,7 @@ def leann_search_adc_rerank(cfg, vectors, offsets, nbrs, entry, codebooks, codes
     rc = lib().orc_leann_search_adc_rerank(_cfgp(cfg), _p(vectors, f32p), n, d, _p(offsets, u64p), _p(nbrs, u64p),
                                            -1 if entry is None else int(entry), _p(cb, f32p), m, ksub, _p(codes, u16p),
                                            _p(queries, f32p), nq, k, ef, _p(ids, u64p), _p(dist, f32p), _p(cnt, u32p),
-                                           st.ctypes.data if stats else None, threads)
+                                           st.ctypes.data if stats else None, threads, int(rerank_limit))
     if rc != 0:
         raise RuntimeError(f"orc_leann_search_adc_rerank status {rc}")
     return (ids, dist, cnt, st) if stats else (ids, dist, cnt)

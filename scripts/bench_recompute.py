@@ -37,7 +37,29 @@ xn = torch.nn.functional.normalize(emb, dim=1); qn = torch.nn.functional.normali
 gt = (qn @ xn.T).topk(k, dim=1).indices.cpu().numpy()
 rec = float(np.mean([len(set(ids_b[i].tolist()) & set(gt[i].tolist())) / k for i in range(nq)]))
 ms_enc, fl = enc.last_timing()
-print(json.dumps(dict(n=n, nq=nq, S=S, ef=ef, index_encode_s=round(t_enc_all, 2), index_encode_seq_per_s=round(n / t_enc_all),
+# hub-embedding cache (docs/leann-specification.md:661-690): the top HUB_PCT % in-degree rows stay resident
+hub = {}
+for pct in [float(v) for v in os.environ.get("HUB_PCTS", "2,10").split(",") if v]:
+    t0 = time.perf_counter(); index.set_hub_cache(int(n * pct / 100)); t_set = time.perf_counter() - t0
+    index.search_adc_recompute_batch(qh, k, ef)
+    t0 = time.perf_counter(); ids_c, dist_c, _ = index.search_adc_recompute_batch(qh, k, ef); dtc = time.perf_counter() - t0
+    ic = index.last_recompute()
+    hub[str(pct)] = dict(cached_nodes=ic["hub_cache_nodes"], build_s=round(t_set, 2), hits=ic["hub_cache_hits"], recomputed=ic["unique_nodes"],
+                         batch_ms=round(dtc * 1e3, 1), encoder_ms=round(ic["encoder_ms"], 2),
+                         identical=bool(np.array_equal(ids_b, ids_c) and np.array_equal(dist_b.view(np.uint32), dist_c.view(np.uint32))))
+index.set_hub_cache(0)
+# rerank limit: the traversal keeps ef survivors, only the best LIMIT per query are recomputed
+lim = {}
+gtn = gt
+for limit in [int(v) for v in os.environ.get("LIMITS", "64,32,16").split(",") if v]:
+    index.set_rerank_limit(limit)
+    index.search_adc_recompute_batch(qh, k, ef)
+    t0 = time.perf_counter(); ids_l, _, _ = index.search_adc_recompute_batch(qh, k, ef); dtl = time.perf_counter() - t0
+    il = index.last_recompute()
+    lim[str(limit)] = dict(recomputed=il["unique_nodes"], batch_ms=round(dtl * 1e3, 1), qps=round(nq / dtl, 1), encoder_ms=round(il["encoder_ms"], 2),
+                           recall_at_10=float(np.mean([len(set(ids_l[i].tolist()) & set(gtn[i].tolist())) / k for i in range(nq)])))
+index.set_rerank_limit(0)
+print(json.dumps(dict(rerank_limit=lim, hub_cache=hub, n=n, nq=nq, S=S, ef=ef, index_encode_s=round(t_enc_all, 2), index_encode_seq_per_s=round(n / t_enc_all),
                       recompute_batch_ms=round(dt * 1e3, 1), qps=round(nq / dt, 1), unique_nodes=info["unique_nodes"],
                       traverse_ms=round(info["traverse_ms"], 2), encoder_ms=round(info["encoder_ms"], 2), rerank_ms=round(info["rerank_ms"], 2),
                       encoder_tflops=round(fl / ms_enc / 1e9, 1), recall_at_10=rec,

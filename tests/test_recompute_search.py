@@ -165,3 +165,24 @@ def test_hub_cache_same_bits_fewer_recomputed_rows(gpu_lib):
     from islands_b200 import InvalidArgument
     with pytest.raises(InvalidArgument):
         index.set_hub_cache(10)
+
+
+def test_recompute_with_rerank_limit(gpu_lib):
+    """With a rerank limit only the best `limit` survivors per query go through the encoder: fewer rows are
+    recomputed, and the result equals the stored-vector ADC + rerank search under the same limit bit for bit."""
+    n, nq, S, k, ef = 3000, 200, 16, 10, 64
+    enc, cfg_e, tok, ln, _, queries = _setup(n, nq, S)
+    stored = enc.embed(tok, ln)
+    index, pq = _index_over(stored, n)
+    index.set_recompute(enc, tok, ln)
+    index.search_adc_recompute_batch(queries, k, ef)
+    full_rows = index.last_recompute()["unique_nodes"]
+    index.set_rerank_limit(16)
+    ids_a, dist_a, cnt_a, st_a = index.search_adc_rerank_batch(queries, k, ef, stats=True)
+    ids_b, dist_b, cnt_b, st_b = index.search_adc_recompute_batch(queries, k, ef, stats=True)
+    assert index.last_recompute()["unique_nodes"] < full_rows
+    assert int(st_b.n_rerank.max()) <= 16
+    assert np.array_equal(cnt_a, cnt_b) and np.array_equal(ids_a, ids_b)
+    assert np.array_equal(dist_a.view(np.uint32), dist_b.view(np.uint32))
+    for f in ("n_hop", "n_edge", "n_adc", "n_rerank"):
+        assert np.array_equal(getattr(st_a, f), getattr(st_b, f)), f

@@ -146,3 +146,36 @@ def test_adc_traversal_ties_with_and_without_visited_set(gpu_lib, orc, m, ksub):
         ids2, dist2, cnt2 = idx.search_adc_rerank_batch(q, k, ef)
         assert np.array_equal(cnt2, o_cnt) and np.array_equal(ids2, o_ids), (k, ef)
         assert np.array_equal(dist2.view(np.uint32), o_dist.view(np.uint32))
+
+
+@pytest.mark.parametrize("m,ksub", [(32, 64), (8, 256)])
+def test_adc_rerank_limit_matches_oracle(gpu_lib, orc, m, ksub):
+    """isl_index_set_rerank_limit: the traversal keeps ef survivors, only the max(limit, k) with the best table
+    distance (ties by id) get an exact distance.  Same definition in the oracle; register / shared-memory R,
+    with and without statistics; limit 0 restores the full rerank."""
+    from islands_b200 import LeannIndex, PQConfig, ProductQuantizer
+
+    cfg, v, levels, off, nbrs, entry = oracle_graph(orc, 3000, 96, seed=61)
+    cb = orc.pq_train(1, v[:1000], m, ksub, 3, 7)
+    codes = orc.pq_encode(1, cb, v)
+    pq = ProductQuantizer(96, PQConfig(m, ksub, 3, 7))
+    pq.set_codebooks(cb)
+    idx = LeannIndex.from_csr(cfg, v, off, nbrs, levels, entry)
+    idx.attach_pq(pq, codes)
+    q = np.concatenate([uniform(np.random.RandomState(65), 90, 96), v[:10]])
+    for k, ef, limit in [(10, 100, 32), (10, 200, 10), (25, 200, 5), (10, 300, 40), (10, 64, 500)]:
+        idx.set_rerank_limit(limit)
+        o_ids, o_dist, o_cnt, o_st = orc.leann_search_adc_rerank(cfg._s, v, off, nbrs, entry, cb, codes, q, k, ef,
+                                                                 threads=8, stats=True, rerank_limit=limit)
+        ids, dist, cnt, st = idx.search_adc_rerank_batch(q, k, ef, stats=True)
+        ids2, dist2, cnt2 = idx.search_adc_rerank_batch(q, k, ef)
+        for a_ids, a_dist, a_cnt in ((ids, dist, cnt), (ids2, dist2, cnt2)):
+            assert np.array_equal(a_cnt, o_cnt) and np.array_equal(a_ids, o_ids), (k, ef, limit)
+            assert np.array_equal(a_dist.view(np.uint32), o_dist.view(np.uint32))
+        for f in ("n_hop", "n_edge", "n_dist", "n_adc", "n_rerank"):
+            assert np.array_equal(getattr(st, f), o_st[f]), f
+        assert int(st.n_rerank.max()) <= max(limit, k)
+    idx.set_rerank_limit(0)
+    ids, dist, cnt = idx.search_adc_rerank_batch(q, 10, 100)
+    o_ids, o_dist, _ = orc.leann_search_adc_rerank(cfg._s, v, off, nbrs, entry, cb, codes, q, 10, 100, threads=8)
+    assert np.array_equal(ids, o_ids) and np.array_equal(dist.view(np.uint32), o_dist.view(np.uint32))
