@@ -16,11 +16,12 @@ for m in [int(v) for v in os.environ.get("MS", "8,16,32").split(",")]:
     codes = pq.encode(xh); t2 = time.time()
     idx.attach_pq(pq, codes)
     print(json.dumps(dict(m=m, train_s=round(t1 - t0, 2), encode_s=round(t2 - t1, 2))), flush=True)
-    for ef in [int(v) for v in os.environ.get("EFS", "64,128,256,512").split(",")]:
+    for ef, lim in [(int(v), int(l)) for v in os.environ.get("EFS", "64,128,256,512").split(",") for l in os.environ.get("LIMITS", "0").split(",")]:
+        idx.set_rerank_limit(lim)
         ids, dist, cnt, st = idx.search_adc_rerank_batch(qh, 10, ef, stats=True)
         ids, dist, cnt = idx.search_adc_rerank_batch(qh, 10, ef)
         ms, _ = idx.last_search_timing()
         rec = bench.recall_at_k(torch, torch.from_numpy(ids[:1000].astype(np.int64)).to(dev), gt)
         b = st.n_adc.sum() * m + st.n_edge.sum() * 4 + st.n_hop.sum() * 16 + st.n_rerank.sum() * 4 * d + nq * (4 * d + 120 + m * int(os.environ.get("KSUB", 256)) * 4)
-        print(json.dumps(dict(m=m, ef=ef, kernel_ms=round(ms, 2), qps=round(nq / ms * 1e3), recall=round(rec, 4), n_adc=float(st.n_adc.mean()),
+        print(json.dumps(dict(m=m, ef=ef, limit=lim, kernel_ms=round(ms, 2), qps=round(nq / ms * 1e3), recall=round(rec, 4), n_adc=float(st.n_adc.mean()),
                               n_rerank=float(st.n_rerank.mean()), n_hop=float(st.n_hop.mean()), gbps=round(b / ms / 1e6, 1))), flush=True)
