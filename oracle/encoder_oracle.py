@@ -6,8 +6,11 @@ Restates the reference's CandleEmbedder::embed_texts_raw (src/core/embedding/can
 clamp(sum_mask, 1e-9) (:438-474) -> L2 normalisation with clamp(norm, 1e-12) (:477-494).  The BERT
 forward is third-party in the reference (candle-transformers 0.9.1 `bert`, Cargo.lock:1113; not
 vendored): this follows the published architecture (post-LayerNorm encoder, erf GELU, additive
-attention mask).  PARITY UNPINNED: the reference's own encoder tests check only config / preset
-strings (candle_provider.rs:514-592), so no golden embedding exists to pin this against.
+attention mask).  PINNING: the reference's own encoder tests check only config / preset strings
+(candle_provider.rs:514-592), so it holds no golden embedding; this restatement is pinned against
+Hugging Face transformers' BertModel — the implementation candle's bert.rs mirrors — plus the reference's
+pooling recipe, through tests/golden/encoder_golden.npz (tests/golden/make_encoder_golden.py; agreement
+2e-6 on unit vectors).  Not pinned against candle itself: no Rust toolchain here.
 """
 import numpy as np
 from scipy.special import erf

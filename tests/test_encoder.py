@@ -160,6 +160,56 @@ def test_encoder_parameter_roundtrip_and_errors(gpu_lib):
         enc.embed(np.ones((1, 100), np.int32), np.array([4], np.int32))  # S > max_position
 
 
+def _transformers_golden():
+    import os
+
+    import sys
+
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    if gdir not in sys.path:
+        sys.path.insert(0, gdir)
+    from encoder_params import SHAPE, make_params
+
+    return np.load(os.path.join(gdir, "encoder_golden.npz")), make_params(SHAPE, seed=0), SHAPE
+
+
+def test_encoder_oracle_vs_transformers_golden():
+    """Pins the fp32 oracle: Hugging Face transformers' BertModel (the implementation candle's bert.rs mirrors)
+    + the reference's pooling recipe (candle_provider.rs:438-494), run by tests/golden/make_encoder_golden.py.
+    Padded rows, a full-length row and a one-token row; unnormalised (pooled) and normalised outputs."""
+    from oracle.encoder_oracle import bert_embed
+
+    g, params, shape = _transformers_golden()
+
+    class Cfg:
+        hidden_size, num_layers, num_heads = shape["hidden_size"], shape["num_layers"], shape["num_heads"]
+        layer_norm_eps, normalize = 1e-12, 1
+
+    out = bert_embed(params, Cfg, g["token_ids"], g["lengths"])
+    assert np.abs(out - g["embeddings"]).max() < 2e-6
+    Cfg.normalize = 0
+    pooled = bert_embed(params, Cfg, g["token_ids"], g["lengths"])
+    assert np.abs(pooled - g["pooled"]).max() < 2e-5 * max(1.0, float(np.abs(g["pooled"]).max()))
+
+
+@pytest.mark.gpu
+def test_encoder_vs_transformers_golden(gpu_lib):
+    """The CUDA encoder loaded with the golden model's weights against transformers' own output (bf16 GEMM
+    operands, f32 accumulate: tolerance as in the oracle comparison)."""
+    from islands_b200 import Encoder, EncoderConfig
+
+    g, params, shape = _transformers_golden()
+    cfg = EncoderConfig(**shape)
+    enc = Encoder(cfg)
+    for name in enc.parameter_shapes():
+        enc.set_parameter(name, params[name])
+    out = enc.embed(g["token_ids"], g["lengths"])
+    ref = g["embeddings"]
+    cos = (out * ref).sum(1) / (np.linalg.norm(out, axis=1) * np.linalg.norm(ref, axis=1))
+    assert cos.min() > 0.999, cos.min()
+    assert np.abs(out - ref).max() < 2e-2
+
+
 @pytest.mark.gpu
 def test_embed_texts_raw_vs_oracle(gpu_lib):
     """Text entry point (candle_provider.rs:353-507): WordPiece tokenisation (golden-pinned in
