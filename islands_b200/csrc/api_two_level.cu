@@ -112,7 +112,7 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
     a.out_count = idx->out_count.p;
     a.stats = stats ? idx->out_stats.p : nullptr;
     // without statistics the traversal runs without the visited bitset (same survivors; search_core.cuh)
-    a.novis = (!stats && pt.novis_ok && idx->codes8.p) ? 1u : 0u;
+    a.novis = (!stats && pt.novis_ok && idx->codes8.p && idx->n < kIdcMaxNodes) ? 1u : 0u;
     a.work_counter = idx->counters.p;
     a.error_flag = idx->counters.p + 1;
     a.luts = fused_lut ? nullptr : idx->aux_f32.p;

@@ -54,7 +54,7 @@ isl_status plan_lean(uint32_t ef, uint32_t u_cap, uint32_t pq_m, int sms, Search
   const size_t smem = search_smem_bytes<kCH, kStages>(0, (R_SMEM && NR == 0) ? ef : 0, u_cap, plan->lut_smem_floats, 0, true) +
                       (NR > 0 ? search_smem_bytes_idc() : 0);
   if (smem > 227 * 1024) return fail(ISL_INVALID_ARGUMENT, "search: ef needs more than 227 KB of shared memory per warp");
-  plan->novis_ok = NR > 0 && plan->lut_smem_floats != 0 && (pq_m == 16 || pq_m == 32);
+  plan->novis_ok = NR > 0 && plan->lut_smem_floats != 0 && (pq_m == 16 || pq_m == 32);  // and n < kIdcMaxNodes (checked by the caller)
   ISL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   ISL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));

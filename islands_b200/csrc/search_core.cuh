@@ -28,7 +28,6 @@
 namespace isl {
 
 constexpr uint32_t kTieCap = 64;
-constexpr uint32_t kIdcEntries = 1024;  // lean ADC traversal: direct-mapped cache of admitted ids (shared memory)
 constexpr uint32_t kExpandedBit = 0x80000000u;
 
 // lean = the ADC-traversal-only kernel (MODE 3): no row staging ring, no query vector.
@@ -40,7 +39,7 @@ __host__ __device__ constexpr size_t search_smem_bytes(uint32_t ld, uint32_t ef_
          (size_t)aq_entries * 8;
 }
 // the lean kernel with R in registers appends the admitted-id cache
-__host__ __device__ constexpr size_t search_smem_bytes_idc() { return (size_t)kIdcEntries * 4; }
+__host__ __device__ constexpr size_t search_smem_bytes_idc() { return (size_t)kIdcEntries * 2; }
 
 template <bool R_SMEM>
 struct RView {
@@ -106,7 +105,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(ties + kTieCap);
   float* lut_smem = reinterpret_cast<float*>(bars + STAGES);
   uint2* aq_smem = reinterpret_cast<uint2*>(lut_smem + (MODE != 0 ? a.lut_smem_floats : 0));
-  uint32_t* idc = reinterpret_cast<uint32_t*>(aq_smem + (TWO ? a.aq_smem_entries : 0));  // only laid out when NR > 0
+  uint16_t* idc = reinterpret_cast<uint16_t*>(aq_smem + (TWO ? a.aq_smem_entries : 0));  // only laid out when NR > 0
   // Lean ADC traversal without a visited set.  Scoring a node again can never change R: while R is not
   // full every scored node is admitted, afterwards a node that was rejected (d >= worst) or evicted
   // (key above the worst one) is rejected again because the worst distance only decreases, and a node
@@ -171,7 +170,8 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         for (uint32_t i = lane; i < a.ld / 4; i += 32) dst[i] = src[i];
       }
       if (novis) {
-        for (uint32_t i = lane; i < kIdcEntries; i += 32) idc[i] = 0xffffffffu;
+        uint32_t* c2 = reinterpret_cast<uint32_t*>(idc);
+        for (uint32_t i = lane; i < kIdcEntries / 2; i += 32) c2[i] = 0xffffffffu;
       } else if (!(ADC && a.phase == 2)) {  // the rerank-only launch never touches the visited set
         uint4* v4 = reinterpret_cast<uint4*>(vis);
         const uint4 z = make_uint4(0, 0, 0, 0);
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
 #pragma unroll
           for (int j = 0; j < NR; ++j) same = same || ((ki[j] ^ nki) < 2u);
           if (__any_sync(FULL, same)) return;
-          if (lane == 0) idc[idnew & (kIdcEntries - 1)] = idnew;
+          if (lane == 0) idc[idnew & (kIdcEntries - 1)] = (uint16_t)(idnew >> kIdcBits);
         }
         pos = 0;
 #pragma unroll
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
             if (novis) {  // an id found in the admitted-id cache was admitted before: never again
-              if (chk[r] && idc[nid[r] & (kIdcEntries - 1)] == nid[r]) chk[r] = false;
+              if (chk[r] && idc[nid[r] & (kIdcEntries - 1)] == (uint16_t)(nid[r] >> kIdcBits)) chk[r] = false;
               old[r] = 0;
             } else if (chk[r]) {
               old[r] = atomicOr(vis + (nid[r] >> 5), 1u << (nid[r] & 31));
