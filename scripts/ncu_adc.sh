@@ -4,10 +4,12 @@
 set -u
 mkdir -p gpurun_out
 export MS=${MS:-32} KSUB=${KSUB:-128} EFS=${EFS:-192}
-NOSTATS_ONLY=1 python scripts/probe_adc.py > gpurun_out/adc_plain.log 2>&1 || { tail -5 gpurun_out/adc_plain.log; exit 1; }
+python scripts/probe_adc.py > gpurun_out/adc_plain.log 2>&1 || { tail -5 gpurun_out/adc_plain.log; exit 1; }
 tail -2 gpurun_out/adc_plain.log
 # the graph build launches the MODE 0 kernel; only the traversal kernel carries "3, 6>" / "3, 4>" ...
+# probe_adc.py calls the search twice per ef: with statistics (visited bitset) and without (bitset-free): SKIP=1 captures
+# the second, SKIP=0 the first
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
     -k regex:'leann_search_kernel.*3, *\(?i?n?t?\)?[2468]>' -s ${SKIP:-1} -c 1 -f -o gpurun_out/${OUT:-prof_adc} \
-    env NOSTATS_ONLY=1 python scripts/probe_adc.py > gpurun_out/adc_ncu.log 2>&1
+    env python scripts/probe_adc.py > gpurun_out/adc_ncu.log 2>&1
 echo "ncu rc=$?"; tail -3 gpurun_out/adc_ncu.log
