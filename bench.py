@@ -438,7 +438,7 @@ def main():
             line["adc_rerank"] = {"pq_m": pq_m, "pq_ksub": pq_ksub, "ef": ef_adc, "recall_at_10": curve_adc[ef_adc], "kernel_qps": nq / ms * 1e3,
                                   "kernel_ms": ms, "e2e_qps_host_buffers": nq / wall, "algorithmic_gbps": b / ms / 1e6, "frac": b / ms / 1e6 / peak,
                                   "n_adc": float(st.n_adc.mean()), "n_rerank": float(st.n_rerank.mean()),
-                                  "bound": "instruction latency of the per-hop chain at 11 resident warps per SM (16 KB table + 2 KB id cache per query); "
+                                  "bound": "instruction latency of the per-hop chain at 12 resident warps per SM (16 KB table + 1 KB id cache per query); "
                                            "the byte roofline is not the limiter: every access is one 32-byte sector, and with the per-query visited "
                                            "bitset the kernel sat at the measured random-sector ceiling of HBM (profiles/r01_sector_ceiling.txt)",
                                   "note": "parity unpinned: no reference implementation of this mode exists (leann.rs:54-56)"}

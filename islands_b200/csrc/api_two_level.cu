@@ -64,14 +64,18 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
     // result array in registers up to ef = 256) hands its ef survivors to the exact rerank (MODE 2,
     // phase 2).  Each half gets the occupancy its own shared-memory footprint allows.
     const uint32_t maxdeg2 = std::max<uint32_t>(idx->max_degree, 1);
-    const uint32_t u_cap_t = std::max<uint32_t>(32, round_up(maxdeg2 + 1, 32));
+    // the vectorised hop of the lean kernel (one-byte codes, m = 16 / 32, table in shared memory) keeps its list in
+    // registers: only the generic hop needs room for a whole neighbour list in shared memory
+    const bool vector_hop = idx->codes8.p && (m == 16 || m == 32) && lut_floats <= 8192;
+    const uint32_t u_cap_t = vector_hop ? 32u : std::max<uint32_t>(32, round_up(maxdeg2 + 1, 32));
     const uint32_t u_cap_r = std::max<uint32_t>(32, round_up(ef, 32));
     SearchPlan pt, pr;
     ISL_TRY(plan_search_adc_traverse(ef, u_cap_t, m, pq->ksub, idx->sms, &pt));
     ISL_TRY(plan_search_rerank(idx->cfg.metric, idx->ld, ef, u_cap_r, idx->sms, &pr));
     const uint32_t vis_words2 = round_up((uint32_t)((idx->n + 31) / 32), 4);
     const uint32_t slots_t = (uint32_t)std::min<uint64_t>(pt.grid, nq), slots_r = (uint32_t)std::min<uint64_t>(pr.grid, nq);
-    ISL_TRY(ensure(idx->visited, (size_t)slots_t * vis_words2));
+    const bool novis = !stats && pt.novis_ok && idx->codes8.p && idx->n < kIdcMaxNodes;
+    if (!novis) ISL_TRY(ensure(idx->visited, (size_t)slots_t * vis_words2));  // the bitset-free traversal needs no scratch
     if (!pt.r_in_smem || !pr.r_in_smem) ISL_TRY(ensure(idx->r_global, (size_t)std::max(slots_t, slots_r) * ef));
     ISL_TRY(ensure(idx->aux_f32, (size_t)nq * lut_floats + 2));
     ISL_TRY(ensure(idx->q_stage, nq * idx->ld));
@@ -112,7 +116,7 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
     a.out_count = idx->out_count.p;
     a.stats = stats ? idx->out_stats.p : nullptr;
     // without statistics the traversal runs without the visited bitset (same survivors; search_core.cuh)
-    a.novis = (!stats && pt.novis_ok && idx->codes8.p && idx->n < kIdcMaxNodes) ? 1u : 0u;
+    a.novis = novis ? 1u : 0u;
     a.work_counter = idx->counters.p;
     a.error_flag = idx->counters.p + 1;
     a.luts = fused_lut ? nullptr : idx->aux_f32.p;

@@ -8,7 +8,7 @@ namespace isl {
 // Lean ADC traversal: direct-mapped cache of admitted ids in shared memory.  An entry holds id >> kIdcBits as 16
 // bits (the slot supplies the low bits), which identifies the id exactly for n <= 2^(16 + kIdcBits) - the host
 // only enables the bitset-free traversal below that size.
-constexpr uint32_t kIdcBits = 10;
+constexpr uint32_t kIdcBits = 9;
 constexpr uint32_t kIdcEntries = 1u << kIdcBits;
 constexpr uint32_t kIdcMaxNodes = (0xffffu << kIdcBits);  // tag 0xffff is the empty marker
 
