@@ -277,8 +277,8 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     };
     // ---- sorted insert into R ------------------------------------------------------------------
     // shared/global R: binary search, warp shift, store.  register R: position = number of entries
-    // below the new key (one ballot per row), then every row shifts up by one lane (shfl_up, lane 0
-    // takes lane 31 of the row below) where index > position.
+    // below the new key (one 64-bit compare + ballot per row), then every row at or above it rotates up
+    // by one lane (lane 31 hands over the last entry of the row below).
     auto r_insert = [&](float dnew, uint32_t idnew) __attribute__((always_inline)) {
       uint32_t pos;
       const bool full = (r_len == ef);
