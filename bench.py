@@ -104,10 +104,32 @@ class ClockSampler:
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
+        self.source = "nvidia-smi"
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        # NVML in-process (a sample costs well under a millisecond, so even a sub-second timed region gets dozens);
+        # falls back to the nvidia-smi command line of the profiling recipe when the binding is missing.
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.source = "nvml (the counters nvidia-smi prints)"
+            while not self._stop.is_set():
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for nme, b in bits.items():
+                    if r & b:
+                        self.reasons.add(nme)
+                self._stop.wait(0.01)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -134,7 +156,7 @@ class ClockSampler:
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "source": self.source}
 
 
 def algorithmic_bytes(stats, d, nq, k):
