@@ -448,11 +448,12 @@ def main():
                 return recall_at_k(torch, torch.from_numpy(r[:n_gt].astype(np.int64)).to(dev), gt)
 
             ef_adc, curve_adc = calibrate_ef(adc_recall, RECALL_TARGET)
-            _, _, _, st = index.search_adc_rerank_batch(qn, K_TOP, ef_adc, stats=True)
+            ids_bitset, dist_bitset, _, st = index.search_adc_rerank_batch(qn, K_TOP, ef_adc, stats=True)
             ms_l, t0 = [], time.perf_counter()
             for _ in range(3):  # timed without statistics: the traversal then runs without the visited bitset
-                index.search_adc_rerank_batch(qn, K_TOP, ef_adc)
+                ids_free, dist_free, _ = index.search_adc_rerank_batch(qn, K_TOP, ef_adc)
                 ms_l.append(index.last_search_timing()[0])
+            same_adc = bool(np.array_equal(ids_bitset, ids_free) and np.array_equal(dist_bitset.view(np.uint32), dist_free.view(np.uint32)))
             wall = (time.perf_counter() - t0) / 3
             ms = float(np.mean(ms_l))
             b = int(st.n_adc.sum()) * pq_m + int(st.n_edge.sum()) * 4 + int(st.n_hop.sum()) * 16 + int(st.n_rerank.sum()) * 4 * d \
@@ -460,6 +461,7 @@ def main():
             line["adc_rerank"] = {"pq_m": pq_m, "pq_ksub": pq_ksub, "ef": ef_adc, "recall_at_10": curve_adc[ef_adc], "kernel_qps": nq / ms * 1e3,
                                   "kernel_ms": ms, "e2e_qps_host_buffers": nq / wall, "algorithmic_gbps": b / ms / 1e6, "frac": b / ms / 1e6 / peak,
                                   "n_adc": float(st.n_adc.mean()), "n_rerank": float(st.n_rerank.mean()),
+                                  "bitset_free_results_equal_bitset_results": same_adc,
                                   "bound": "instruction latency of the per-hop chain at 12 resident warps per SM (16 KB table + 1 KB id cache per query); "
                                            "the byte roofline is not the limiter: every access is one 32-byte sector, and with the per-query visited "
                                            "bitset the kernel sat at the measured random-sector ceiling of HBM (profiles/r01_sector_ceiling.txt)",

@@ -179,3 +179,33 @@ def test_adc_rerank_limit_matches_oracle(gpu_lib, orc, m, ksub):
     ids, dist, cnt = idx.search_adc_rerank_batch(q, 10, 100)
     o_ids, o_dist, _ = orc.leann_search_adc_rerank(cfg._s, v, off, nbrs, entry, cb, codes, q, 10, 100, threads=8)
     assert np.array_equal(ids, o_ids) and np.array_equal(dist.view(np.uint32), o_dist.view(np.uint32))
+
+
+@pytest.mark.parametrize("n,m0,ef_list", [(2000, 100, [1, 10, 70, 256]), (40, 24, [1, 5, 64]), (3, 24, [1, 4]), (1, 24, [1, 3])])
+def test_adc_traversal_edge_shapes(gpu_lib, orc, n, m0, ef_list):
+    """Shapes around the vectorised hop of the lean traversal: lists longer than one 64-position pass (m0 = 100),
+    graphs smaller than a pass / than k, a single node, ef = 1 and ef < k — with statistics (visited bitset) and
+    without (bitset-free), both against the oracle."""
+    from islands_b200 import LeannIndex, PQConfig, ProductQuantizer
+
+    cfg, v, levels, off, nbrs, entry = oracle_graph(orc, n, 64, seed=81, m=m0 // 2, m0=m0, ef_construction=max(m0 + 8, 64))
+    m, ksub = 16, min(32, n)
+    cb = orc.pq_train(1, v, m, ksub, 3, 7)
+    codes = orc.pq_encode(1, cb, v)
+    pq = ProductQuantizer(64, PQConfig(m, ksub, 3, 7))
+    pq.set_codebooks(cb)
+    idx = LeannIndex.from_csr(cfg, v, off, nbrs, levels, entry)
+    idx.attach_pq(pq, codes)
+    q = np.concatenate([uniform(np.random.RandomState(82), 40, 64), v[:min(n, 8)]])
+    for ef in ef_list:
+        for k in (1, 10):
+            o_ids, o_dist, o_cnt, o_st = orc.leann_search_adc_rerank(cfg._s, v, off, nbrs, entry, cb, codes, q, k, ef,
+                                                                     threads=4, stats=True)
+            ids, dist, cnt, st = idx.search_adc_rerank_batch(q, k, ef, stats=True)
+            ids2, dist2, cnt2 = idx.search_adc_rerank_batch(q, k, ef)
+            for a_ids, a_dist, a_cnt in ((ids, dist, cnt), (ids2, dist2, cnt2)):
+                assert np.array_equal(a_cnt, o_cnt), (n, ef, k)
+                assert np.array_equal(a_ids, o_ids), (n, ef, k)
+                assert np.array_equal(a_dist.view(np.uint32), o_dist.view(np.uint32))
+            for f in ("n_hop", "n_edge", "n_adc", "n_rerank"):
+                assert np.array_equal(getattr(st, f), o_st[f]), (f, n, ef, k)
