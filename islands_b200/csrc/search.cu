@@ -52,9 +52,9 @@ template <bool R_SMEM, int NR>
 isl_status plan_lean(uint32_t ef, uint32_t u_cap, uint32_t pq_m, int sms, SearchPlan* plan) {
   auto kern = leann_search_kernel<ACC_DOT, kCH, kStages, R_SMEM, 3, NR>;
   const size_t smem = search_smem_bytes<kCH, kStages>(0, (R_SMEM && NR == 0) ? ef : 0, u_cap, plan->lut_smem_floats, 0, true) +
-                      (NR > 0 ? search_smem_bytes_idc() : 0);
+                      (R_SMEM ? search_smem_bytes_idc() : 0);
   if (smem > 227 * 1024) return fail(ISL_INVALID_ARGUMENT, "search: ef needs more than 227 KB of shared memory per warp");
-  plan->novis_ok = NR > 0 && plan->lut_smem_floats != 0 && (pq_m == 16 || pq_m == 32);  // and n < kIdcMaxNodes (checked by the caller)
+  plan->novis_ok = R_SMEM && plan->lut_smem_floats != 0 && (pq_m == 16 || pq_m == 32);  // and n < kIdcMaxNodes (checked by the caller)
   ISL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   ISL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
@@ -147,12 +147,15 @@ isl_status plan_search_adc_traverse(uint32_t ef, uint32_t u_cap, uint32_t pq_m, 
   plan->lut_smem_floats = lut_floats <= kLutSmemMaxFloats ? lut_floats : 0;
   plan->aq_cap = 0;
   plan->aq_smem_entries = 0;
-  plan->nr = ef <= 64 ? 2 : (ef <= 128 ? 4 : (ef <= 192 ? 6 : (ef <= 256 ? 8 : 0)));
+  // register R: NR = 2 * ceil(ef / 64) entries per lane, up to ef = 384
+  plan->nr = ef <= 384 ? (int)(2 * ((ef + 63) / 64)) : 0;
   switch (plan->nr) {
     case 2: return plan_lean<true, 2>(ef, u_cap, pq_m, sms, plan);
     case 4: return plan_lean<true, 4>(ef, u_cap, pq_m, sms, plan);
     case 6: return plan_lean<true, 6>(ef, u_cap, pq_m, sms, plan);
     case 8: return plan_lean<true, 8>(ef, u_cap, pq_m, sms, plan);
+    case 10: return plan_lean<true, 10>(ef, u_cap, pq_m, sms, plan);
+    case 12: return plan_lean<true, 12>(ef, u_cap, pq_m, sms, plan);
   }
   return ef <= kEfSmemMax ? plan_lean<true, 0>(ef, u_cap, pq_m, sms, plan) : plan_lean<false, 0>(ef, u_cap, pq_m, sms, plan);
 }
@@ -176,6 +179,8 @@ isl_status launch_search(const SearchPlan& plan, const SearchArgs& args, cudaStr
       case 4: return launch_lean<true, 4>(plan, args, grid, st);
       case 6: return launch_lean<true, 6>(plan, args, grid, st);
       case 8: return launch_lean<true, 8>(plan, args, grid, st);
+      case 10: return launch_lean<true, 10>(plan, args, grid, st);
+      case 12: return launch_lean<true, 12>(plan, args, grid, st);
     }
     return plan.r_in_smem ? launch_lean<true, 0>(plan, args, grid, st) : launch_lean<false, 0>(plan, args, grid, st);
   }

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(ties + kTieCap);
   float* lut_smem = reinterpret_cast<float*>(bars + STAGES);
   uint2* aq_smem = reinterpret_cast<uint2*>(lut_smem + (MODE != 0 ? a.lut_smem_floats : 0));
-  uint16_t* idc = reinterpret_cast<uint16_t*>(aq_smem + (TWO ? a.aq_smem_entries : 0));  // only laid out when NR > 0
+  uint16_t* idc = reinterpret_cast<uint16_t*>(aq_smem + (TWO ? a.aq_smem_entries : 0));  // only laid out for the lean kernel with R in registers or shared memory
   // Lean ADC traversal without a visited set.  Scoring a node again can never change R: while R is not
   // full every scored node is admitted, afterwards a node that was rejected (d >= worst) or evicted
   // (key above the worst one) is rejected again because the worst distance only decreases, and a node
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
   // direct-mapped cache of admitted ids that filters most repeats before they are replayed.  Ids,
   // survivors, n_hop and n_edge are unchanged; n_adc (distinct nodes scored) is not defined in this
   // mode, which is therefore only used when no statistics are requested.
-  const bool novis = RREG && LEAN && a.novis != 0;
+  const bool novis = LEAN && R_SMEM && a.novis != 0;  // R in registers or in shared memory (the host only sets it then)
 
   const uint32_t lane = lane_id();
   const uint32_t slot = blockIdx.x;
@@ -336,6 +336,13 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
             hi = mid;
         }
         pos = lo;
+        if (novis) {  // a node that is already in R has an equal key: it sits exactly at the lower bound
+          if (pos < r_len) {
+            const uint2 e = R.ld(pos);
+            if ((e.y & ~kExpandedBit) == idnew) return;  // scored twice, admitted once
+          }
+          if (lane == 0) idc[idnew & (kIdcEntries - 1)] = (uint16_t)(idnew >> kIdcBits);
+        }
         if (full) evicted = R.ld(ef - 1);
         const int top = full ? (int)ef - 1 : (int)r_len;
         for (int t = top; t > (int)pos; t -= 32) {
