@@ -361,6 +361,11 @@ def main():
     qn = qh.numpy()
     dt_e2e = timed(lambda: index.search_batch(qn, K_TOP, ef), a.steps, max(1, a.warmup))  # isl_index_search
     e2e_qps = (world if use_dist else 1) * nq * a.steps / dt_e2e
+    lat = []  # batch latency of the synchronous host-buffer call (p50 / p99), outside the timed regions
+    for _ in range(max(a.steps, 10)):
+        t0 = time.perf_counter()
+        index.search_batch(qn, K_TOP, ef)
+        lat.append((time.perf_counter() - t0) * 1e3)
 
     peak, peak_src = measured_peak()
     traffic = None  # DRAM bytes of this launch from the committed ncu --set full capture, when it is the same workload
@@ -388,6 +393,8 @@ def main():
             "l2": "inputs larger than L2 (vector table %.2f GB vs 126 MB)" % (n * d * 4 / 1e9),
             "per_query": per_query,
         },
+        "batch_latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)), "calls": len(lat),
+                             "what": f"isl_index_search, host buffers, {nq} queries per call (this rank)"},
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": parts * nq * d * 4,
                 "d2h_bytes_per_step": parts * (nq * K_TOP * 12 + nq * 4)},
         "gpu_launches": launches,
