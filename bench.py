@@ -438,8 +438,12 @@ def main():
         xh = x.cpu().numpy()
         cq, m, o_ids = cpu_port_qps(orc, cfg, xh, g.node_offsets, g.neighbors, g.entry_point, qn, ef, threads, a.cpu_seconds)
         same = bool(np.array_equal(o_ids.astype(np.int64), index.search_batch(qn[:m], K_TOP, ef)[0].astype(np.int64)))
+        # the reference's own execution model is one thread (search_batch is a sequential map, search.rs:179-181)
+        cq1, m1, _ = cpu_port_qps(orc, cfg, xh, g.node_offsets, g.neighbors, g.entry_point, qn, ef, 1, min(a.cpu_seconds, 5.0))
         line["cpu_baseline"] = {"value": cq, "unit": "queries/s", "cores": threads, "kind": "port",
-                                "sample": f"first {m} of {nq} queries, same graph / ef, all host threads; ids equal to GPU: {same}"}
+                                "sample": f"first {m} of {nq} queries, same graph / ef, all host threads; ids equal to GPU: {same}",
+                                "single_thread": {"value": cq1, "unit": "queries/s", "sample": f"first {m1} queries, one thread "
+                                                  "(the reference's execution model, search.rs:179-181)"}}
 
         # secondary: BASELINE configs[1] names "PQ ADC traversal + exact rerank" — a mode the reference
         # specifies (docs/leann-specification.md:223-269) but does not implement; measured beside the headline.
