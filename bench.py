@@ -400,7 +400,8 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": {"bound": "hbm", "kernel": "leann_search_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "peak_source": peak_src},
+                     "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "peak_source": peak_src,
+                     "frac_of_nominal_8TBs": achieved / 8000.0},
     }
 
     # ---- N > 1: the all-islands search (every query on every shard + all-gather + merge) ---------------
