@@ -535,7 +535,31 @@ def main():
                                     "note": "bit-exact with the reference's HnswGraph, including its prune_connections quirk (hnsw.rs:419-420 with :327: "
                                             "the id being inserted is filtered out of a full neighbour list), so only the first ~m0 nodes ever "
                                             "receive incoming edges and the traversal stays among them: recall and speed are the reference's"}
-            del hg, xh_, qh_
+            # BASELINE configs[0] for the LEANN index itself: 100k x 768, ef = 64, top-10, GPU and the CPU port on the
+            # same graph and queries (1000 of them on the CPU), ids compared
+            lg = LeannIndex(cfg)
+            t0 = time.perf_counter()
+            lg.build_dev(xh_.data_ptr(), hn, d, seed=7, batch=1024)
+            torch.cuda.synchronize()
+            lbuild = time.perf_counter() - t0
+            lms = []
+            for it in range(4):
+                lg.search_batch_dev(qh_.data_ptr(), nq, d, K_TOP, 64, ids.data_ptr(), dst.data_ptr(), cnt.data_ptr(), 0)
+                if it:
+                    lms.append(lg.last_search_timing()[0])
+            lrec = recall_at_k(torch, ids[:n_gt], gth)
+            gids = ids[:1000].cpu().numpy().astype(np.int64)
+            gg = lg.graph
+            xc, qc = xh_.cpu().numpy(), qh_[:1000].cpu().numpy()
+            t0 = time.perf_counter()
+            oids, _, _ = orc.leann_search(cfg._s, xc, gg.node_offsets, gg.neighbors, gg.entry_point, qc, K_TOP, 64, threads=threads)
+            ldt = time.perf_counter() - t0
+            line["leann_config0"] = {"workload": "LeannIndex 100k x 768 uniform, m=30 m0=60 efC=128, ef=64, top-10 (BASELINE configs[0])",
+                                     "build_s": lbuild, "search_ms_per_10k": float(np.mean(lms)), "qps": nq / float(np.mean(lms)) * 1e3,
+                                     "recall_at_10": lrec, "cpu_port_qps": 1000 / ldt, "cpu_threads": threads,
+                                     "ids_equal_cpu_port": bool(np.array_equal(oids.astype(np.int64), gids)),
+                                     "note": "uniform 768-d data: recall at ef = 64 is what any graph index gives there (SURVEY F10)"}
+            del hg, lg, xh_, qh_, xc, qc
             torch.cuda.empty_cache()
 
         # secondary: the reference benches' own distribution (uniform), reported beside the headline
