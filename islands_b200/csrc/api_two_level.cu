@@ -61,7 +61,7 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
 
   if (mode == 2) {
     // Two launches: the lean ADC traversal (MODE 3: no staging ring or query vector in shared memory,
-    // result array in registers up to ef = 384) hands its ef survivors to the exact rerank (MODE 2,
+    // result array in registers up to ef = 512) hands its ef survivors to the exact rerank (MODE 2,
     // phase 2).  Each half gets the occupancy its own shared-memory footprint allows.
     const uint32_t maxdeg2 = std::max<uint32_t>(idx->max_degree, 1);
     // the vectorised hop of the lean kernel (one-byte codes, m = 16 / 32, table in shared memory) keeps its list in

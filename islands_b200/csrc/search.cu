@@ -147,8 +147,8 @@ isl_status plan_search_adc_traverse(uint32_t ef, uint32_t u_cap, uint32_t pq_m, 
   plan->lut_smem_floats = lut_floats <= kLutSmemMaxFloats ? lut_floats : 0;
   plan->aq_cap = 0;
   plan->aq_smem_entries = 0;
-  // register R: NR = 2 * ceil(ef / 64) entries per lane, up to ef = 384
-  plan->nr = ef <= 384 ? (int)(2 * ((ef + 63) / 64)) : 0;
+  // register R: NR = 2 * ceil(ef / 64) entries per lane, up to ef = 512
+  plan->nr = ef <= 512 ? (int)(2 * ((ef + 63) / 64)) : 0;
   switch (plan->nr) {
     case 2: return plan_lean<true, 2>(ef, u_cap, pq_m, sms, plan);
     case 4: return plan_lean<true, 4>(ef, u_cap, pq_m, sms, plan);
@@ -156,6 +156,8 @@ isl_status plan_search_adc_traverse(uint32_t ef, uint32_t u_cap, uint32_t pq_m, 
     case 8: return plan_lean<true, 8>(ef, u_cap, pq_m, sms, plan);
     case 10: return plan_lean<true, 10>(ef, u_cap, pq_m, sms, plan);
     case 12: return plan_lean<true, 12>(ef, u_cap, pq_m, sms, plan);
+    case 14: return plan_lean<true, 14>(ef, u_cap, pq_m, sms, plan);
+    case 16: return plan_lean<true, 16>(ef, u_cap, pq_m, sms, plan);
   }
   return ef <= kEfSmemMax ? plan_lean<true, 0>(ef, u_cap, pq_m, sms, plan) : plan_lean<false, 0>(ef, u_cap, pq_m, sms, plan);
 }
@@ -181,6 +183,8 @@ isl_status launch_search(const SearchPlan& plan, const SearchArgs& args, cudaStr
       case 8: return launch_lean<true, 8>(plan, args, grid, st);
       case 10: return launch_lean<true, 10>(plan, args, grid, st);
       case 12: return launch_lean<true, 12>(plan, args, grid, st);
+      case 14: return launch_lean<true, 14>(plan, args, grid, st);
+      case 16: return launch_lean<true, 16>(plan, args, grid, st);
     }
     return plan.r_in_smem ? launch_lean<true, 0>(plan, args, grid, st) : launch_lean<false, 0>(plan, args, grid, st);
   }

@@ -60,8 +60,8 @@ def test_adc_traversal_rerank_matches_oracle(gpu_lib, orc, m, ksub):
     idx = LeannIndex.from_csr(cfg, v, off, nbrs, levels, entry)
     idx.attach_pq(pq, codes)
     q = np.concatenate([uniform(np.random.RandomState(63), 90, 96), v[:10]])
-    # ef 16..300: result array in registers (2 / 4 / 8 / 10 entries per lane); 500: shared memory; 2500: global memory
-    for k, ef in [(10, 16), (10, 100), (25, 200), (10, 300), (10, 500), (10, 2500)]:
+    # ef 16..500: result array in registers (2 / 4 / 8 / 10 / 16 entries per lane); 600: shared memory; 2500: global memory
+    for k, ef in [(10, 16), (10, 100), (25, 200), (10, 300), (10, 500), (10, 600), (10, 2500)]:
         if ef == 2500 and m not in (32, 8):
             continue
         ids, dist, cnt, st = idx.search_adc_rerank_batch(q, k, ef, stats=True)
@@ -135,7 +135,7 @@ def test_adc_traversal_ties_with_and_without_visited_set(gpu_lib, orc, m, ksub):
     idx = LeannIndex.from_csr(cfg, v, off, nbrs, levels, entry)
     idx.attach_pq(pq, codes)
     q = np.concatenate([uniform(np.random.RandomState(72), 150, 96), v[:50]])
-    for k, ef in [(5, 8), (10, 24), (10, 64), (20, 130), (10, 256), (10, 330), (10, 450)]:  # registers up to 384, then shared memory
+    for k, ef in [(5, 8), (10, 24), (10, 64), (20, 130), (10, 256), (10, 330), (10, 450), (10, 530)]:  # registers up to 512, then shared memory
         ids, dist, cnt, st = idx.search_adc_rerank_batch(q, k, ef, stats=True)
         o_ids, o_dist, o_cnt, o_st = orc.leann_search_adc_rerank(cfg._s, v, off, nbrs, entry, cb, codes, q, k, ef,
                                                                  threads=8, stats=True)
