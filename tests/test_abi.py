@@ -125,3 +125,24 @@ def test_product_never_touches_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 for needle in ("pyoracle", "libislands_oracle", "oracle.h", "import oracle", "from oracle", "dlopen"):
                     assert needle not in text, (f, needle)
+
+
+def test_rust_sys_declarations_are_current_and_complete():
+    """bindings/rust/islands_b200_sys.rs (the `extern "C"` module of INTEGRATION.md §1) is generated from the
+    header: the committed file must be what scripts/gen_rust_sys.py produces now, and declare every symbol of
+    the ctypes table (which test_header_library_and_table_agree ties to the header and the library)."""
+    import importlib.util
+    import re
+
+    from islands_b200 import _ffi
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_rust_sys", os.path.join(root, "scripts", "gen_rust_sys.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    text, names = gen.generate()
+    with open(gen.OUT) as f:
+        assert f.read() == text, "run python scripts/gen_rust_sys.py"
+    declared = set(re.findall(r"pub fn (isl_\w+)\(", text))
+    assert declared == set(_ffi.SIGNATURES)
+    assert "pub struct IslLeannConfig" in text and "pub hub_percentile: f32" in text
