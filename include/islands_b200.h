@@ -264,7 +264,11 @@ isl_status isl_index_search_two_level(const isl_index* idx, const float* queries
 /* "PQ ADC traversal + exact rerank": the best-first search of leann.rs:899-988 runs entirely on
  * table distances (pq.rs:341-348; same admission / termination / tie rules with adc as the key),
  * then the ef surviving candidates get their exact distance (distance.rs) and are returned sorted by
- * (distance, id).  Traversal reads m code bytes per visited node instead of 4*dim. */
+ * (distance, id).  Traversal reads m code bytes per visited node instead of 4*dim.
+ * With stats_or_null == NULL (one-byte codes, m = 16 / 32, ef <= 2048, n < 2^25) the traversal keeps no
+ * visited set — a node may be scored more than once, which cannot change the result —;
+ * with statistics it keeps the exact bitset, and n_adc counts distinct nodes scored.  Ids and distances
+ * are the same either way. */
 isl_status isl_index_search_adc_rerank(const isl_index* idx, const float* queries, uint64_t nq,
                                        uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* out_ids,
                                        float* out_dist, uint32_t* out_count,
