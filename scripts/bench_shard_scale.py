@@ -1,6 +1,7 @@
 """One GPU's share of a 100M-vector index: builds and searches a 12.5M x 768 island (= 100M / 8, north_star's
 sharded target) on ONE B200 and prints a JSON line with QPS at recall@10 >= 0.95, the kernel's algorithmic
-bandwidth and the build time.  Islands are independent (island-routed queries), so the 8-GPU
+bandwidth and the build time, then (ADC=1, default) the PQ ADC traversal + exact rerank mode on the same shard.
+Islands are independent (island-routed queries), so the 8-GPU
 number is this per-GPU figure times the scaling measured by `bench.py --gpus 8` on 1M islands.
 Run under gpurun:  N=12500000 python scripts/bench_shard_scale.py
 Memory: vectors 38.4 GB in the index + the same again while the synthetic set is alive (ground truth is
@@ -15,7 +16,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
-from islands_b200 import LeannConfig, LeannIndex
+from islands_b200 import LeannConfig, LeannIndex, PQConfig, ProductQuantizer
 
 n = int(os.environ.get("N", 12_500_000))
 d, nq, k, n_gt = 768, 10_000, 10, 1000
@@ -54,6 +55,16 @@ idx = LeannIndex(LeannConfig())
 idx.build_dev(x.data_ptr(), n, d, seed=7, batch=int(os.environ.get("BATCH", 4096)))
 torch.cuda.synchronize()
 build_s = time.perf_counter() - t0
+adc = os.environ.get("ADC", "1") != "0"
+if adc:  # PQ codes for the ADC traversal + exact rerank mode, encoded chunk by chunk through the host API
+    pq_m, pq_ksub = 32, 128
+    pq = ProductQuantizer(d, PQConfig(pq_m, pq_ksub, 8, 1))
+    t0 = time.perf_counter()
+    pq.train(x[:20000].cpu().numpy())
+    codes = np.concatenate([pq.encode(x[s:min(n, s + chunk)].cpu().numpy()) for s in range(0, n, chunk)])
+    idx.attach_pq(pq, codes)
+    pq_s = time.perf_counter() - t0
+    del codes
 del x
 torch.cuda.empty_cache()
 
@@ -87,7 +98,23 @@ try:
 except Exception:
     peak = 6543.1
 km = float(np.mean(ms))
-print(json.dumps({"workload": f"{n} x {d} f32 latent32 island on one B200 (1/8 of a 100M-vector index), m=30 m0=60 efC=128 hub 2%, "
+adc_out = None
+if adc:
+    qh = q.cpu().numpy()
+
+    def adc_recall(ef_):
+        r = idx.search_adc_rerank_batch(qh, k, ef_)[0]
+        return bench.recall_at_k(torch, torch.from_numpy(r[:n_gt].astype(np.int64)).to(dev), gt)
+
+    ef_a, curve_a = bench.calibrate_ef(adc_recall, 0.95, int(os.environ.get("EF_ADC", 0)))
+    ms_a, t0 = [], time.perf_counter()
+    for _ in range(3):
+        idx.search_adc_rerank_batch(qh, k, ef_a)
+        ms_a.append(idx.last_search_timing()[0])
+    wall_a = (time.perf_counter() - t0) / 3
+    adc_out = {"pq_m": pq_m, "pq_ksub": pq_ksub, "train_encode_s": pq_s, "ef": ef_a, "recall_at_10": curve_a[ef_a], "recall_curve": curve_a,
+               "kernel_ms": float(np.mean(ms_a)), "kernel_qps": nq / float(np.mean(ms_a)) * 1e3, "e2e_qps_host_buffers": nq / wall_a}
+print(json.dumps({"adc_rerank": adc_out, "workload": f"{n} x {d} f32 latent32 island on one B200 (1/8 of a 100M-vector index), m=30 m0=60 efC=128 hub 2%, "
                               f"{nq} queries per step, top-{k}, exact traversal, cosine",
                   "build_s": build_s, "ef": ef, "recall_at_10": curve[ef], "recall_curve": curve, "qps": nq / wall, "ms_per_step": wall * 1e3,
                   "kernel_ms": km, "algorithmic_gbps": b / km / 1e6, "frac_of_measured_hbm_peak": b / km / 1e6 / peak,
