@@ -253,6 +253,12 @@ isl_status isl_pq_table_distance(const isl_pq* pq, const float* tables, const ui
 isl_status isl_pq_asymmetric_distance(const isl_pq* pq, const float* query, uint32_t dim,
                                       const uint16_t* codes, uint64_t n, float* out);
 
+/* The generator isl_pq_train draws from when config.seed is set: `StdRng::seed_from_u64(seed)` of rand 0.8.5
+ * (ChaCha12; pq.rs:190-193), restated in csrc/std_rng.h.  A scripted sequence of draws, for checking the
+ * restatement on its own: kinds[i] = 0 next_u32, 1 next_u64 (gen::<usize>()), 2 gen::<f32>() (bit pattern),
+ * 3 SliceRandom::choose index over `bound` elements.  Host code only. */
+isl_status isl_std_rng_draw(uint64_t seed, const uint8_t* kinds, uint64_t count, uint64_t bound, uint64_t* out);
+
 /* ---- two-level search (docs/leann-specification.md:223-269; no reference code) ------ */
 /* Attach PQ codes [n][m] (u16 at the ABI) for ADC-carried traversal; rerank_ratio = `a`. */
 isl_status isl_index_attach_pq(isl_index* idx, const isl_pq* pq, const uint16_t* codes);

@@ -187,6 +187,7 @@ SIGNATURES = {
     "isl_index_last_recompute": (C.c_int, [_VP, u64p, f32p, f32p, f32p]),
     "isl_index_set_hub_cache": (C.c_int, [_VP, C.c_uint64]),
     "isl_index_set_rerank_limit": (C.c_int, [_VP, C.c_uint32]),
+    "isl_std_rng_draw": (C.c_int, [C.c_uint64, C.POINTER(C.c_uint8), C.c_uint64, C.c_uint64, u64p]),
     "isl_index_hub_cache_info": (C.c_int, [_VP, u64p, u64p]),
     "isl_index_to_bytes": (C.c_int, [_VP, _VP, C.c_uint64, u64p]),
     "isl_index_from_bytes": (C.c_int, [_VP, C.c_uint64, f32p, C.c_uint32, _VPP]),

@@ -47,6 +47,8 @@ static isl_status upload_padded(const float* src, uint64_t rows, uint32_t dim, u
 }
 }  // namespace isl
 
+#include "std_rng.h"
+
 extern "C" {
 
 isl_status isl_pq_new(uint32_t dimension, const isl_pq_config* cfg, isl_pq** out) {
@@ -219,6 +221,32 @@ isl_status isl_pq_asymmetric_distance(const isl_pq* pq, const float* query, uint
   ISL_CUDA_TRY(cudaMemcpyAsync(out, dout.p, n * 4, cudaMemcpyDeviceToHost, pq->stream));
   ISL_CUDA_TRY(cudaStreamSynchronize(pq->stream));
   if (h) return fail(ISL_PQ_ERROR, "Invalid code (>= number of centroids)");  // pq.rs:290-292
+  return ISL_OK;
+}
+
+// The generator isl_pq_train draws from (std_rng.h = rand 0.8.5 StdRng::seed_from_u64), exposed so that the
+// restatement can be checked on its own: kind 0 = next_u32, 1 = next_u64, 2 = gen::<f32>() bits, 3 = choose(bound).
+isl_status isl_std_rng_draw(uint64_t seed, const uint8_t* kinds, uint64_t count, uint64_t bound, uint64_t* out) {
+  if ((!kinds || !out) && count) return fail(ISL_INVALID_ARGUMENT, "null pointer");
+  isl::StdRng rng(seed);
+  for (uint64_t i = 0; i < count; ++i) {
+    switch (kinds[i]) {
+      case 0: out[i] = rng.next_u32(); break;
+      case 1: out[i] = rng.next_u64(); break;
+      case 2: {
+        const float f = rng.next_f32();
+        uint32_t b;
+        memcpy(&b, &f, 4);
+        out[i] = b;
+        break;
+      }
+      case 3:
+        if (bound == 0) return fail(ISL_INVALID_ARGUMENT, "choose needs a non-empty range");
+        out[i] = rng.choose_index(bound);
+        break;
+      default: return fail(ISL_INVALID_ARGUMENT, "unknown draw kind");
+    }
+  }
   return ISL_OK;
 }
 

@@ -3,9 +3,11 @@
 // Same algorithm and the same f32 operation order as the reference: distance-weighted seeding
 // (weights are distances, not squared), Lloyd iterations with strict `<` assignment, centroid
 // sums accumulated in vector order and divided by the count, empty clusters reseeded with a
-// random training vector.  The reference draws from StdRng (ChaCha12); this implementation and
-// the oracle both use a splitmix64 stream instead, so codebooks match the ORACLE bit for bit
-// for a given seed but the reference only statistically.
+// random training vector.  The random numbers come from the reference's own generator, restated in
+// std_rng.h: `StdRng::seed_from_u64(seed)` (rand 0.8.5 = ChaCha12), consumed in the reference's order
+// (one generator across the subspaces; `gen::<usize>() % n`, `gen::<f32>()`, `choose`), so a seeded
+// training follows the reference's stream; the oracle restates the same generator independently and
+// codebooks match it bit for bit.
 #include <cub/cub.cuh>
 
 #include <algorithm>
@@ -13,22 +15,10 @@
 
 #include "api_common.h"
 #include "dist_pass.cuh"
+#include "std_rng.h"
 
 namespace isl {
 namespace {
-
-struct Rng {
-  uint64_t s;
-  explicit Rng(uint64_t seed) : s(seed) {}
-  uint64_t next_u64() {
-    s += 0x9E3779B97F4A7C15ull;
-    uint64_t x = s;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-    return x ^ (x >> 31);
-  }
-  float next_f32() { return (float)(next_u64() >> 40) * (1.0f / 16777216.0f); }
-};
 
 __device__ __forceinline__ float metric_fold(int32_t metric, const float* a, const float* b, uint32_t d) {
   float dot = 0.0f, na = 0.0f, nb = 0.0f, s = 0.0f;
@@ -170,7 +160,7 @@ extern "C" isl_status isl_pq_train(isl_pq* pq, const float* vectors, uint64_t n,
   const uint32_t k = (uint32_t)std::min<uint64_t>(pq->cfg.num_centroids, n);  // pq.rs:374
   const uint32_t iters = (uint32_t)pq->cfg.training_iterations;
   uint64_t seed = pq->cfg.seed >= 0 ? (uint64_t)pq->cfg.seed : ((uint64_t)std::random_device{}() << 32) ^ std::random_device{}();
-  Rng rng(seed);  // one generator across subspaces, in order (pq.rs:190-214)
+  StdRng rng(seed);  // StdRng::seed_from_u64 (pq.rs:190-193), one generator across subspaces, in order (:196-214)
 
   DevBuf<float> dv, mind, cent;
   DevBuf<uint16_t> codes, codes_sorted;
@@ -201,14 +191,14 @@ extern "C" isl_status isl_pq_train(isl_pq* pq, const float* vectors, uint64_t n,
     const uint32_t col0 = j * dsub;
     float* cj = cent.p + (size_t)j * k * ld_sub;
     // ---- seeding (pq.rs:376-415) ---------------------------------------------------------
-    const uint64_t first = rng.next_u64() % n;
+    const uint64_t first = rng.next_u64() % n;  // rng.gen::<usize>() % vectors.len() (pq.rs:380)
     copy_row_kernel<<<1, 128, 0, st>>>(dv.p, dim, col0, dsub, nullptr, first, cj, ld_sub);
     fill_kernel<<<grid_1d(n, 256), 256, 0, st>>>(mind.p, n, 3.402823466e+38f);
     count_launch(2);
     for (uint32_t c = 1; c < k; ++c) {
       update_min_dist_kernel<<<grid_1d(n, 128), 128, dsub * 4, st>>>(pq->metric, dv.p, dim, col0, dsub, n,
                                                                      cj + (size_t)(c - 1) * ld_sub, mind.p);
-      const float threshold = rng.next_f32();
+      const float threshold = rng.next_f32();  // rng.gen::<f32>() (pq.rs:404)
       weighted_pick_kernel<<<1, 32, 0, st>>>(mind.p, n, threshold, picked.p);
       copy_row_kernel<<<1, 128, 0, st>>>(dv.p, dim, col0, dsub, picked.p, 0, cj + (size_t)c * ld_sub, ld_sub);
       count_launch(3);
@@ -243,7 +233,7 @@ extern "C" isl_status isl_pq_train(isl_pq* pq, const float* vectors, uint64_t n,
       count_launch();
       for (uint32_t c = 0; c < k; ++c) {
         if (h_counts[c] == 0) {  // vectors.choose(rng) (pq.rs:452-456)
-          const uint64_t row = rng.next_u64() % n;
+          const uint64_t row = rng.choose_index(n);
           copy_row_kernel<<<1, 128, 0, st>>>(dv.p, dim, col0, dsub, nullptr, row, cj + (size_t)c * ld_sub, ld_sub);
           count_launch();
         }

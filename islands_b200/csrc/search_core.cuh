@@ -472,6 +472,9 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         cur = e.y;
         uint32_t nxt = r_len;
         if constexpr (RREG) {
+          // the cached copy of the worst entry must see the flag too: an expanded worst entry that is evicted
+          // later with a distance equal to the new worst one must not come back through the ties list
+          if (first_unexp == ef - 1) wst_ki |= 1u;
           // mark it expanded and find the next unexpanded entry (sentinel slots read as expanded);
           // rows below the popped one cannot hold it and are skipped
 #pragma unroll

@@ -322,17 +322,82 @@ inline uint64_t splitmix64(uint64_t x) {
   return x ^ (x >> 31);
 }
 
-struct Rng {  // stand-in for StdRng (ChaCha12 not restated; statistical parity only)
-  uint64_t s;
-  explicit Rng(uint64_t seed) : s(seed) {}
-  uint64_t next_u64() {
-    s += 0x9E3779B97F4A7C15ull;
-    uint64_t x = s;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-    return x ^ (x >> 31);
+// StdRng of rand 0.8.5 = ChaCha12Rng (rand_chacha 0.3.1) seeded by SeedableRng::seed_from_u64 (rand_core 0.6.4):
+// third-party crates, restated from their published algorithms (pq.rs:190-193 seeds it, :380 / :404 / :454 draw
+// from it).  Written as one continuous stream of 32-bit words — word i = ChaCha12 block i / 16, word i % 16 —
+// which is what BlockRng's 64-word buffer delivers: next_u32 = the next word, next_u64 = the next two words, low
+// first (also across a refill).  The block function is pinned by RFC 7539 and the ChaCha12 / ChaCha8
+// known answers of draft-strombergson-chacha-test-vectors (tests/test_std_rng.py).
+static void chacha_words(const uint32_t key[8], uint64_t counter, uint64_t stream, int rounds, uint32_t out[16]) {
+  const uint32_t c[4] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
+  uint32_t x[16], in[16];
+  for (int i = 0; i < 4; ++i) in[i] = c[i];
+  for (int i = 0; i < 8; ++i) in[4 + i] = key[i];
+  in[12] = (uint32_t)counter;
+  in[13] = (uint32_t)(counter >> 32);
+  in[14] = (uint32_t)stream;
+  in[15] = (uint32_t)(stream >> 32);
+  std::memcpy(x, in, sizeof(x));
+#define ORC_ROTL(v, n) (((v) << (n)) | ((v) >> (32 - (n))))
+#define ORC_QR(a, b, c_, d)                                   \
+  x[a] += x[b]; x[d] ^= x[a]; x[d] = ORC_ROTL(x[d], 16);      \
+  x[c_] += x[d]; x[b] ^= x[c_]; x[b] = ORC_ROTL(x[b], 12);    \
+  x[a] += x[b]; x[d] ^= x[a]; x[d] = ORC_ROTL(x[d], 8);       \
+  x[c_] += x[d]; x[b] ^= x[c_]; x[b] = ORC_ROTL(x[b], 7);
+  for (int r = 0; r < rounds / 2; ++r) {
+    ORC_QR(0, 4, 8, 12) ORC_QR(1, 5, 9, 13) ORC_QR(2, 6, 10, 14) ORC_QR(3, 7, 11, 15)
+    ORC_QR(0, 5, 10, 15) ORC_QR(1, 6, 11, 12) ORC_QR(2, 7, 8, 13) ORC_QR(3, 4, 9, 14)
   }
-  float next_f32() { return (float)(next_u64() >> 40) * (1.0f / 16777216.0f); }  // 24-bit, [0,1)
+#undef ORC_QR
+#undef ORC_ROTL
+  for (int i = 0; i < 16; ++i) out[i] = x[i] + in[i];
+}
+
+struct Rng {
+  uint32_t key[8];
+  uint64_t pos = 0;          // index of the next 32-bit word of the stream
+  uint64_t have = ~0ull;     // block held in `blk`
+  uint32_t blk[16];
+  explicit Rng(uint64_t seed) {  // seed_from_u64: eight PCG32 (XSH-RR) outputs, little-endian, form the 32-byte seed
+    uint64_t st = seed;
+    for (int i = 0; i < 8; ++i) {
+      st = st * 6364136223846793005ull + 11634580027462260723ull;
+      uint32_t xs = (uint32_t)(((st >> 18) ^ st) >> 27), rot = (uint32_t)(st >> 59);
+      key[i] = rot ? ((xs >> rot) | (xs << (32 - rot))) : xs;
+    }
+  }
+  uint32_t word(uint64_t i) {
+    if (i / 16 != have) {
+      have = i / 16;
+      chacha_words(key, have, 0, 12, blk);
+    }
+    return blk[i % 16];
+  }
+  uint32_t next_u32() { return word(pos++); }
+  uint64_t next_u64() {
+    uint64_t lo = word(pos), hi = word(pos + 1);
+    pos += 2;
+    return (hi << 32) | lo;
+  }
+  float next_f32() { return (float)(next_u32() >> 8) * (1.0f / 16777216.0f); }  // Standard: 24 bits, [0,1)
+  uint64_t choose(uint64_t len) {  // SliceRandom::choose -> gen_index -> gen_range(0..len) (u32 when it fits)
+    if (len <= 0xffffffffull) {
+      uint32_t n = (uint32_t)len, lz = 0;
+      while (!((n << lz) & 0x80000000u)) ++lz;
+      uint32_t zone = (n << lz) - 1u;
+      for (;;) {
+        uint64_t m = (uint64_t)next_u32() * n;
+        if ((uint32_t)m <= zone) return m >> 32;
+      }
+    }
+    uint32_t lz = 0;
+    while (!((len << lz) & 0x8000000000000000ull)) ++lz;
+    uint64_t zone = (len << lz) - 1ull;
+    for (;;) {
+      unsigned __int128 m = (unsigned __int128)next_u64() * len;
+      if ((uint64_t)m <= zone) return (uint64_t)(m >> 64);
+    }
+  }
 };
 
 // pq.rs:362-463
@@ -398,7 +463,7 @@ int32_t kmeans(const std::vector<const float*>& vecs, uint32_t dim, uint32_t k_i
         float fc = (float)counts[c];
         for (uint32_t j = 0; j < dim; ++j) dst[j] = dst[j] / fc;
       } else {
-        const float* rv = vecs[rng.next_u64() % n];  // vectors.choose(rng)
+        const float* rv = vecs[rng.choose(n)];  // vectors.choose(rng) (pq.rs:454)
         std::memcpy(dst, rv, sizeof(float) * dim);
       }
     }
@@ -858,6 +923,21 @@ void orc_merge_topk(const uint64_t* ids, const float* dist, uint32_t parts, uint
       }
     std::sort(all.begin(), all.end(), key_lt);  // search.rs:231 under the (dist,id) rule
     write_topk(all, k, out_ids + qi * k, out_dist + qi * k, out_count ? out_count + qi : nullptr);
+  }
+}
+
+// Test hooks for the generator restatement: one ChaCha block, and a scripted sequence of draws
+// (kind 0 = next_u32, 1 = next_u64, 2 = f32 bits, 3 = choose(bound)).
+void orc_chacha_block(const uint32_t* key8, uint64_t counter, uint64_t stream, int32_t rounds, uint32_t* out16) {
+  chacha_words(key8, counter, stream, rounds, out16);
+}
+void orc_std_rng_draw(uint64_t seed, const uint8_t* kinds, uint64_t count, uint64_t bound, uint64_t* out) {
+  Rng rng(seed);
+  for (uint64_t i = 0; i < count; ++i) {
+    if (kinds[i] == 0) out[i] = rng.next_u32();
+    else if (kinds[i] == 1) out[i] = rng.next_u64();
+    else if (kinds[i] == 2) { float f = rng.next_f32(); uint32_t b; std::memcpy(&b, &f, 4); out[i] = b; }
+    else out[i] = rng.choose(bound);
   }
 }
 

@@ -125,6 +125,11 @@ int32_t orc_hnsw_search(const orc_hnsw* g, const float* queries, uint64_t nq, ui
 /* search.rs:99-102 */
 float orc_to_similarity(float score);
 
+/* StdRng (rand 0.8.5) restatement, test hooks: one ChaCha block; a scripted sequence of draws
+ * (kind 0 = next_u32, 1 = next_u64, 2 = f32 bits, 3 = choose(bound)). */
+void orc_chacha_block(const uint32_t* key8, uint64_t counter, uint64_t stream, int32_t rounds, uint32_t* out16);
+void orc_std_rng_draw(uint64_t seed, const uint8_t* kinds, uint64_t count, uint64_t bound, uint64_t* out);
+
 #ifdef __cplusplus
 }
 #endif
