@@ -1,0 +1,100 @@
+"""Randomised parity sweep (run under gpurun): GPU search variants against the oracle on small random graphs with
+tie-heavy data (copied vectors, tiny codebooks), duplicate list entries and random k / ef.  Prints one line per
+mismatch and a summary; exit code 1 on any mismatch.  SEED / ROUNDS / BUDGET_S from the environment."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from islands_b200 import LeannConfig, LeannIndex, PQConfig, ProductQuantizer  # noqa: E402
+from oracle import pyoracle as orc  # noqa: E402
+
+rng = np.random.RandomState(int(os.environ.get("SEED", 1)))
+rounds, budget = int(os.environ.get("ROUNDS", 40)), float(os.environ.get("BUDGET_S", 150))
+t_start, bad, checks = time.time(), 0, 0
+
+
+def same(a, b):
+    return np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)) and np.array_equal(a[2], b[2])
+
+
+for r in range(rounds):
+    if time.time() - t_start > budget:
+        break
+    n = int(rng.choice([60, 300, 1000, 2500]))
+    d = int(rng.choice([32, 64, 96]))
+    metric = int(rng.choice([0, 0, 1, 2]))
+    m0 = int(rng.choice([8, 24, 60, 100]))
+    v = (rng.rand(n, d).astype(np.float32) * 2 - 1)
+    ncopy = int(rng.choice([0, n // 10, n // 3]))
+    if ncopy:
+        v[n - ncopy:] = v[:ncopy]                      # exact distance ties
+    if rng.rand() < 0.3:
+        v = np.round(v * 4) / 4                        # coarse grid: ties everywhere
+    cfg = LeannConfig(metric=metric, m=max(2, m0 // 2), m0=m0, ef_construction=max(m0 + 8, 32))
+    levels = orc.draw_levels(r + 5, n, cfg.ml, cfg.max_layers)
+    off, nbrs, entry, _ = orc.leann_build(cfg._s, v, levels, batch=int(rng.choice([1, 16])), threads=os.cpu_count() or 1)
+    nbrs = nbrs.copy()
+    if rng.rand() < 0.4:                               # duplicate list entries
+        for node in rng.choice(n, max(1, n // 5), replace=False):
+            s, e = int(off[node]), int(off[node + 1])
+            if e - s > 3:
+                nbrs[s + int(rng.randint(1, e - s))] = nbrs[s + int(rng.randint(0, e - s))]
+    idx = LeannIndex.from_csr(cfg, v, off, nbrs, levels, entry)
+    nq = 64
+    q = np.concatenate([(rng.rand(nq - 8, d).astype(np.float32) * 2 - 1), v[:8]])
+    m = int(rng.choice([m_ for m_ in (2, 4, 8, 16, 32) if d % m_ == 0]))
+    ksub = int(rng.choice([2, 4, 16, 64, 256]))
+    cb = orc.pq_train(1, v[:min(n, 1000)], m, ksub, 2, r)  # Euclidean quantizer, as PQConfig defaults (pq.rs:37-45)
+    codes = orc.pq_encode(1, cb, v)
+    pq = ProductQuantizer(d, PQConfig(m, ksub, 2, r))
+    pq.set_codebooks(cb)
+    idx.attach_pq(pq, codes)
+    for _ in range(4):
+        k = int(rng.choice([1, 5, 10, 40]))
+        ef = int(rng.choice([1, 7, 33, 64, 65, 130, 200, 257, 400, 513, 700]))
+        limit = int(rng.choice([0, 0, 3, 20]))
+        tag = f"round {r} n={n} d={d} metric={metric} m0={m0} copies={ncopy} pq=({m},{ksub}) k={k} ef={ef} limit={limit}"
+        # exact traversal
+        try:
+            g = idx.search_batch(q, k, ef, stats=True)
+            o = orc.leann_search(cfg._s, v, off, nbrs, entry, q, k, ef, threads=8, stats=True)
+            checks += 1
+            if not same(g, o) or any(not np.array_equal(getattr(g[3], f), o[3][f]) for f in ("n_hop", "n_edge", "n_dist")):
+                bad += 1
+                print("MISMATCH exact:", tag, flush=True)
+        except Exception as ex:  # a loud failure (the tie list limit) is not a parity error; report it
+            print("raised (exact):", tag, type(ex).__name__, str(ex)[:80], flush=True)
+        # ADC traversal + rerank, with statistics (bitset) and without (bitset-free)
+        try:
+            idx.set_rerank_limit(limit)
+            o = orc.leann_search_adc_rerank(cfg._s, v, off, nbrs, entry, cb, codes, q, k, ef, threads=8, stats=True, rerank_limit=limit)
+            g = idx.search_adc_rerank_batch(q, k, ef, stats=True)
+            checks += 1
+            if not same(g, o) or any(not np.array_equal(getattr(g[3], f), o[3][f]) for f in ("n_hop", "n_edge", "n_adc", "n_rerank")):
+                bad += 1
+                print("MISMATCH adc (statistics):", tag, flush=True)
+            g2 = idx.search_adc_rerank_batch(q, k, ef)
+            checks += 1
+            if not same(g2, o):
+                bad += 1
+                print("MISMATCH adc (no statistics):", tag, flush=True)
+        except Exception as ex:
+            print("raised (adc):", tag, type(ex).__name__, str(ex)[:80], flush=True)
+        idx.set_rerank_limit(0)
+        # two-level search
+        ratio = float(rng.choice([0.1, 0.5, 1.0]))
+        try:
+            o = orc.leann_search_two_level(cfg._s, v, off, nbrs, entry, cb, codes, q, k, ef, ratio, threads=8, stats=True)
+            g = idx.search_two_level_batch(q, k, ef, ratio, stats=True)
+            checks += 1
+            if not same(g, o):
+                bad += 1
+                print("MISMATCH two-level:", tag, "ratio", ratio, flush=True)
+        except Exception as ex:  # a loud failure (e.g. the tie list limit) is not a parity error; report it
+            print("raised:", tag, type(ex).__name__, str(ex)[:100], flush=True)
+print(f"fuzz: {checks} checks, {bad} mismatches, {time.time() - t_start:.0f}s", flush=True)
+sys.exit(1 if bad else 0)
