@@ -36,8 +36,22 @@ for r in range(rounds):
         v = np.round(v * 4) / 4                        # coarse grid: ties everywhere
     cfg = LeannConfig(metric=metric, m=max(2, m0 // 2), m0=m0, ef_construction=max(m0 + 8, 32))
     levels = orc.draw_levels(r + 5, n, cfg.ml, cfg.max_layers)
-    off, nbrs, entry, _ = orc.leann_build(cfg._s, v, levels, batch=int(rng.choice([1, 16])), threads=os.cpu_count() or 1)
+    bb = int(rng.choice([1, 16]))
+    off, nbrs, entry, _ = orc.leann_build(cfg._s, v, levels, batch=bb, threads=os.cpu_count() or 1)
     nbrs = nbrs.copy()
+    # graph construction (round model): GPU CSR against the oracle's, same levels and batch
+    try:
+        gb = LeannIndex(cfg)
+        gb.build(v, n, levels=levels, batch=bb)
+        gg = gb.graph
+        checks += 1
+        if not (np.array_equal(gg.node_offsets, off) and np.array_equal(gg.neighbors[:int(off[-1])], nbrs[:int(off[-1])])
+                and int(gg.entry_point) == int(entry)):
+            bad += 1
+            print(f"MISMATCH build: round {r} n={n} d={d} metric={metric} m0={m0} copies={ncopy} batch={bb}", flush=True)
+        del gb
+    except Exception as ex:
+        print(f"raised (build): round {r} n={n} d={d} m0={m0} copies={ncopy} batch={bb}", type(ex).__name__, str(ex)[:80], flush=True)
     if rng.rand() < 0.4:                               # duplicate list entries
         for node in rng.choice(n, max(1, n // 5), replace=False):
             s, e = int(off[node]), int(off[node + 1])
