@@ -9,7 +9,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from islands_b200 import LeannConfig, LeannIndex, PQConfig, ProductQuantizer  # noqa: E402
+from islands_b200 import HnswConfig, HnswGraph, LeannConfig, LeannIndex, PQConfig, ProductQuantizer  # noqa: E402
 from oracle import pyoracle as orc  # noqa: E402
 
 rng = np.random.RandomState(int(os.environ.get("SEED", 1)))
@@ -57,6 +57,37 @@ for r in range(rounds):
             s, e = int(off[node]), int(off[node + 1])
             if e - s > 3:
                 nbrs[s + int(rng.randint(1, e - s))] = nbrs[s + int(rng.randint(0, e - s))]
+    # HNSW (hnsw.rs): multi-layer insert (round model) and search, every layer's lists compared
+    if n <= 1000:
+        try:
+            hm = int(rng.choice([4, 8, 16]))
+            hcfg = HnswConfig(m=hm, m0=2 * hm, ef_construction=int(rng.choice([16, 40])), metric=metric, ml=float(rng.choice([0.5, 0.9])))
+            hl = orc.draw_levels(r + 9, n, hcfg.ml, hcfg.max_layers)
+            hb = int(rng.choice([1, 32]))
+            og = orc.Hnsw(hcfg._s, d)
+            og.insert_batch(v, hl, batch=hb, threads=8)
+            hg = HnswGraph(hcfg)
+            hg.insert_batch(v, hl, batch=hb)
+            ok = len(hg) == len(og) and hg.entry_point == og.entry_point() and hg.max_level == og.max_level()
+            for layer in range(int(hl.max()) + 1):
+                deg, nb = hg.export_layer(layer)
+                for i in range(n):
+                    ref = og.neighbors(i, layer)
+                    if ref is None:
+                        ok = ok and deg[i] == -1
+                    else:
+                        ok = ok and deg[i] == len(ref) and np.array_equal(nb[i, :deg[i]], ref)
+            hq = (rng.rand(32, d).astype(np.float32) * 2 - 1)
+            for hk, hef in [(1, 1), (10, 50), (20, 20)]:
+                a_ = hg.search_batch(hq, hk, hef)
+                b_ = og.search(hq, hk, hef, threads=8)
+                ok = ok and same(a_, b_)
+            checks += 1
+            if not ok:
+                bad += 1
+                print(f"MISMATCH hnsw: round {r} n={n} d={d} metric={metric} m={hm} batch={hb} copies={ncopy}", flush=True)
+        except Exception as ex:
+            print(f"raised (hnsw): round {r} n={n} d={d} metric={metric}", type(ex).__name__, str(ex)[:80], flush=True)
     idx = LeannIndex.from_csr(cfg, v, off, nbrs, levels, entry)
     nq = 64
     q = np.concatenate([(rng.rand(nq - 8, d).astype(np.float32) * 2 - 1), v[:8]])
