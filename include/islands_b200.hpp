@@ -144,6 +144,30 @@ class LeannIndex {
     g.max_level = isl_index_max_level(h_);
     return g;
   }
+  // Two-level search family (docs/leann-specification.md:223-269): PQ codes [n][m] attached to the index, then
+  // either the AQ-promotion search (rerank ratio `a`) or the traversal on table distances + exact rerank.
+  void attach_pq(const isl_pq* pq, const std::vector<uint16_t>& codes) { check(isl_index_attach_pq(h_, pq, codes.data())); }
+  void set_rerank_limit(uint32_t limit) { check(isl_index_set_rerank_limit(h_, limit)); }
+  SearchResults search_two_level(const std::vector<float>& query, uint32_t k, uint32_t ef, float rerank_ratio) const {
+    std::vector<uint64_t> ids(k);
+    std::vector<float> dist(k);
+    uint32_t count = 0;
+    check(isl_index_search_two_level(h_, query.data(), 1, (uint32_t)query.size(), k, ef, rerank_ratio, ids.data(), dist.data(),
+                                     &count, nullptr));
+    SearchResults out;
+    for (uint32_t i = 0; i < count; ++i) out.emplace_back(ids[i], dist[i]);
+    return out;
+  }
+  SearchResults search_adc_rerank(const std::vector<float>& query, uint32_t k, uint32_t ef) const {
+    std::vector<uint64_t> ids(k);
+    std::vector<float> dist(k);
+    uint32_t count = 0;
+    check(isl_index_search_adc_rerank(h_, query.data(), 1, (uint32_t)query.size(), k, ef, ids.data(), dist.data(), &count,
+                                      nullptr));
+    SearchResults out;
+    for (uint32_t i = 0; i < count; ++i) out.emplace_back(ids[i], dist[i]);
+    return out;
+  }
   isl_index* handle() const { return h_; }
 
  private:
@@ -236,6 +260,12 @@ class ProductQuantizer {
   std::vector<uint16_t> encode(const std::vector<float>& v) const {
     std::vector<uint16_t> codes(num_subquantizers());
     check(isl_pq_encode(h_, v.data(), 1, (uint32_t)v.size(), codes.data()));
+    return codes;
+  }
+  std::vector<uint16_t> encode_batch(const std::vector<float>& vectors) const {  // [n][dim] -> [n][m]
+    const uint64_t n = vectors.size() / dim_;
+    std::vector<uint16_t> codes(n * num_subquantizers());
+    check(isl_pq_encode(h_, vectors.data(), n, dim_, codes.data()));
     return codes;
   }
   std::vector<float> decode(const std::vector<uint16_t>& codes) const {

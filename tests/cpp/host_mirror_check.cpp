@@ -60,6 +60,24 @@ int main(int argc, char** argv) {
     for (size_t i = 1; i < r.size(); ++i) EXPECT(r[i - 1].second <= r[i].second);
     CsrGraph g = idx.graph();
     EXPECT(g.num_nodes == n && g.node_offsets.back() == g.neighbors.size());
+    {  // two-level family: PQ codes attached, traversal on table distances + exact rerank, AQ-promotion search
+      PQConfig pc;
+      pc.num_subquantizers = 4;
+      pc.num_centroids = 16;
+      pc.training_iterations = 3;
+      pc.seed = 1;
+      ProductQuantizer pq(d, pc);
+      pq.train(v);
+      idx.attach_pq(pq.handle(), pq.encode_batch(v));
+      auto a1 = idx.search_adc_rerank(q, 5, 64);
+      EXPECT(a1.size() == 5 && a1[0].first == 0);
+      for (size_t i = 1; i < a1.size(); ++i) EXPECT(a1[i - 1].second <= a1[i].second);
+      idx.set_rerank_limit(8);
+      EXPECT(idx.search_adc_rerank(q, 5, 64).size() == 5);
+      idx.set_rerank_limit(0);
+      auto a2 = idx.search_two_level(q, 5, 64, 0.5f);
+      EXPECT(a2.size() == 5 && a2[0].first == 0);
+    }
     HnswGraph hg;  // hnsw.rs:571-640
     EXPECT(hg.is_empty() && hg.entry_point() == ISL_NO_ENTRY);
     EXPECT(hg.insert(q) == 0 && hg.len() == 1 && hg.dimension() == d);
