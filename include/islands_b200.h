@@ -17,9 +17,13 @@
  *   - ids are u64 at the ABI (reference type); on the device they are u32 (n < 2^31)
  *
  * Host pointers are copied to / from the device inside the call.  Entry points with a
- * `_dev` suffix take device pointers on the current CUDA device and do no host copies.
- * All work is enqueued on an internal per-handle stream and the call returns after the
- * stream has been synchronised (the `_async_dev` forms return right after the launch).
+ * `_dev` suffix take device pointers on the handle's CUDA device and do no host copies.
+ * Every call runs on an internal stream of its own (searches lease one per call, so several
+ * threads can search one handle at the same time) and returns after that stream has been
+ * synchronised: outputs are complete on return.  Device INPUTS of a `_dev` call may still be
+ * being written on the caller's stream: the call first waits (on the device, cudaStreamWaitEvent)
+ * for everything enqueued so far on the caller's stream — the legacy default stream unless
+ * isl_set_caller_stream() named another one for the calling thread.
  *
  * There is NO CPU fallback: if no CUDA device is usable every compute entry point
  * returns ISL_CUDA_ERROR and isl_last_error() says why.
@@ -34,7 +38,7 @@
 extern "C" {
 #endif
 
-#define ISL_ABI_VERSION 1
+#define ISL_ABI_VERSION 2
 #define ISL_NO_ENTRY (-1)
 #define ISL_INVALID_ID UINT64_MAX
 
@@ -95,12 +99,13 @@ typedef struct isl_hnsw_config {
   uint64_t max_layers;
 } isl_hnsw_config;
 
-/* PQConfig (src/core/pq.rs:13-22); seed < 0 means None. */
+/* PQConfig (src/core/pq.rs:13-22); seed: Option<u64> = (has_seed != 0 ? Some(seed) : None). */
 typedef struct isl_pq_config {
   uint64_t num_subquantizers;
   uint64_t num_centroids;
   uint64_t training_iterations;
-  int64_t seed;
+  uint64_t seed;
+  int32_t has_seed;
 } isl_pq_config;
 
 /* Per-query traversal counters (the reference counts `embeddings_computed`, leann.rs:920,950).
@@ -135,6 +140,14 @@ typedef struct isl_index isl_index; /* LeannIndex + CsrGraph + resident vectors 
 typedef struct isl_pq isl_pq;       /* ProductQuantizer (pq.rs:116-129) */
 typedef struct isl_hnsw isl_hnsw;   /* HnswGraph (hnsw.rs:151-164) */
 typedef struct isl_encoder isl_encoder; /* CandleEmbedder's model (candle_provider.rs) for on-demand recompute */
+typedef struct isl_shard isl_shard; /* one rank's membership in a sharded index: communicator + exchange buffers */
+
+/* One entry of a per-shard result list as it travels between GPUs: 16 bytes. */
+typedef struct isl_shard_record {
+  float dist;
+  uint32_t reserved; /* 0 */
+  uint64_t id;       /* global id (local id + the shard's id_base); ISL_INVALID_ID pads short lists */
+} isl_shard_record;
 
 /* ---- library ---------------------------------------------------------------------- */
 int isl_abi_version(void);
@@ -145,6 +158,9 @@ int isl_device_count(void);
 /* Launch bookkeeping for benchmarks: kernels launched by this library since the last reset. */
 uint64_t isl_kernel_launch_count(void);
 void isl_kernel_launch_count_reset(void);
+/* Names the CUDA stream (a cudaStream_t; NULL = the legacy default stream) on which the calling thread
+ * produces the device buffers it hands to `_dev` entry points.  Thread-local. */
+isl_status isl_set_caller_stream(void* cuda_stream);
 
 /* ---- configs (leann.rs:373-461, hnsw.rs:37-85, pq.rs:24-65) ---------------------- */
 isl_status isl_leann_config_default(isl_leann_config* out);  /* paper_default(): m=30,m0=60,efC=128 */
@@ -207,6 +223,12 @@ isl_status isl_index_export_csr(const isl_index* idx, uint64_t* node_offsets, ui
 isl_status isl_index_get_neighbors(const isl_index* idx, uint64_t node_id, uint64_t* out,
                                    uint64_t cap, uint64_t* out_count);
 
+/* CsrGraph::set_neighbors (leann.rs:256-293): replace the list of node_id (graph arrays rebuilt when the
+ * length changes, as in the reference); node_id >= n is ignored as in the reference (leann.rs:258-260), a
+ * neighbour id >= n -> ISL_NODE_NOT_FOUND.
+ * Mutating (&mut self in the reference): must not run concurrently with searches on the handle. */
+isl_status isl_index_set_neighbors(isl_index* idx, uint64_t node_id, const uint64_t* neighbors, uint64_t count);
+
 /* Batched LeannIndex::search_with_params (leann.rs:868-896) over nq queries [nq][dim].
  * out_ids/out_dist are [nq][k], padded with ISL_INVALID_ID / +inf; out_count [nq];
  * stats_or_null [nq].  query_dim != index dimension -> ISL_DIM_MISMATCH. */
@@ -253,11 +275,13 @@ isl_status isl_pq_table_distance(const isl_pq* pq, const float* tables, const ui
 isl_status isl_pq_asymmetric_distance(const isl_pq* pq, const float* query, uint32_t dim,
                                       const uint16_t* codes, uint64_t n, float* out);
 
-/* The generator isl_pq_train draws from when config.seed is set: `StdRng::seed_from_u64(seed)` of rand 0.8.5
- * (ChaCha12; pq.rs:190-193), restated in csrc/std_rng.h.  A scripted sequence of draws, for checking the
- * restatement on its own: kinds[i] = 0 next_u32, 1 next_u64 (gen::<usize>()), 2 gen::<f32>() (bit pattern),
- * 3 SliceRandom::choose index over `bound` elements.  Host code only. */
+#ifdef ISL_TEST_HOOKS
+/* Test hook (not part of the product ABI; compiled into the library, declared only for the tests): the generator
+ * isl_pq_train draws from when config.seed is set — `StdRng::seed_from_u64(seed)` of rand 0.8.5 (ChaCha12;
+ * pq.rs:190-193), restated in csrc/std_rng.h.  A scripted sequence of draws: kinds[i] = 0 next_u32, 1 next_u64
+ * (gen::<usize>()), 2 gen::<f32>() (bit pattern), 3 SliceRandom::choose index over `bound` elements.  Host code only. */
 isl_status isl_std_rng_draw(uint64_t seed, const uint8_t* kinds, uint64_t count, uint64_t bound, uint64_t* out);
+#endif
 
 /* ---- two-level search (docs/leann-specification.md:223-269; no reference code) ------ */
 /* Attach PQ codes [n][m] (u16 at the ABI) for ADC-carried traversal; rerank_ratio = `a`. */
@@ -409,6 +433,42 @@ isl_status isl_merge_topk(const uint64_t* ids, const float* dist, uint32_t parts
 isl_status isl_merge_topk_dev(const uint64_t* d_ids, const float* d_dist, uint32_t parts,
                               uint64_t nq, uint32_t k, uint64_t* d_out_ids, float* d_out_dist,
                               uint32_t* d_out_count);
+
+/* ... and the merge of `parts` record lists laid out [parts][nq][k] (what follows the exchange). */
+isl_status isl_merge_packed_dev(const isl_shard_record* d_records, uint32_t parts, uint64_t nq, uint32_t k,
+                                uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_count);
+
+/* ---- sharded search (indexer/service.rs:777-801, search.rs:211-237) ------------------------------------
+ * The index is split by node range or by island, one shard per GPU / process.  Every rank calls
+ * isl_index_search_sharded with the SAME queries; each searches its shard, the per-shard top-k lists travel as
+ * isl_shard_record arrays in ONE exchange and every rank ends with the same merged top-k (by (dist, id), global
+ * ids = local id + id_base).  Search kernel, exchange and merge kernel run on one stream without a host
+ * synchronisation in between. */
+/* ncclGetUniqueId into out (128 bytes): call on one rank, hand the bytes to the others by any host channel. */
+isl_status isl_shard_unique_id(void* out, uint64_t cap);
+/* ncclCommInitRank on the current CUDA device.  Collective over the `world` ranks. */
+isl_status isl_shard_init(int rank, int world, const void* nccl_uid, isl_shard** out);
+void isl_shard_free(isl_shard* sh);
+int isl_shard_rank(const isl_shard* sh);
+int isl_shard_world(const isl_shard* sh);
+/* Exchange by peer stores instead of ncclAllGather (ranks of one node): every rank's gather buffer is mapped
+ * into the others (CUDA IPC), the search kernel stores each finished query's records straight into all of them
+ * over NVLink, and a flag handshake replaces the collective.  Collective call; max_records >= nq * k of any
+ * later search (larger searches fall back to NCCL). */
+isl_status isl_shard_enable_peer_exchange(isl_shard* sh, uint64_t max_records);
+/* Collective: every rank of the communicator must call it, with the same nq / k / queries.  id_base = first
+ * global id of this rank's shard.  An empty shard (n == 0) takes part with an empty list. */
+isl_status isl_index_search_sharded(const isl_index* idx, isl_shard* sh, uint64_t id_base, const float* queries,
+                                    uint64_t nq, uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* out_ids,
+                                    float* out_dist, uint32_t* out_count);
+isl_status isl_index_search_sharded_dev(const isl_index* idx, isl_shard* sh, uint64_t id_base, const float* d_queries,
+                                        uint64_t nq, uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
+                                        float* d_out_dist, uint32_t* d_out_count);
+/* CUDA-event durations of the three stages of the last sharded search on this rank. */
+isl_status isl_shard_last_timing(const isl_shard* sh, float* search_ms, float* exchange_ms, float* merge_ms);
+/* The halves on their own: this shard's result records [nq][k] without an exchange ... */
+isl_status isl_index_search_packed_dev(const isl_index* idx, uint64_t id_base, const float* d_queries, uint64_t nq,
+                                       uint32_t query_dim, uint32_t k, uint32_t ef, isl_shard_record* d_records);
 
 #ifdef __cplusplus
 }

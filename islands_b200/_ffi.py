@@ -55,13 +55,14 @@ class HnswConfigStruct(C.Structure):
 
 
 class PQConfigStruct(C.Structure):
-    """isl_pq_config == PQConfig (src/core/pq.rs:13-22); seed < 0 is None."""
+    """isl_pq_config == PQConfig (src/core/pq.rs:13-22); seed: Option<u64> as (seed, has_seed)."""
 
     _fields_ = [
         ("num_subquantizers", C.c_uint64),
         ("num_centroids", C.c_uint64),
         ("training_iterations", C.c_uint64),
-        ("seed", C.c_int64),
+        ("seed", C.c_uint64),
+        ("has_seed", C.c_int32),
     ]
 
 
@@ -187,7 +188,6 @@ SIGNATURES = {
     "isl_index_last_recompute": (C.c_int, [_VP, u64p, f32p, f32p, f32p]),
     "isl_index_set_hub_cache": (C.c_int, [_VP, C.c_uint64]),
     "isl_index_set_rerank_limit": (C.c_int, [_VP, C.c_uint32]),
-    "isl_std_rng_draw": (C.c_int, [C.c_uint64, C.POINTER(C.c_uint8), C.c_uint64, C.c_uint64, u64p]),
     "isl_index_hub_cache_info": (C.c_int, [_VP, u64p, u64p]),
     "isl_index_to_bytes": (C.c_int, [_VP, _VP, C.c_uint64, u64p]),
     "isl_index_from_bytes": (C.c_int, [_VP, C.c_uint64, f32p, C.c_uint32, _VPP]),
@@ -203,6 +203,24 @@ SIGNATURES = {
     "isl_index_get_vector": (C.c_int, [_VP, C.c_uint64, f32p]),
     "isl_merge_topk": (C.c_int, [u64p, f32p, C.c_uint32, C.c_uint64, C.c_uint32, u64p, f32p, u32p]),
     "isl_merge_topk_dev": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint64, C.c_uint32, _VP, _VP, _VP]),
+    "isl_set_caller_stream": (C.c_int, [_VP]),
+    "isl_index_set_neighbors": (C.c_int, [_VP, C.c_uint64, u64p, C.c_uint64]),
+    "isl_shard_unique_id": (C.c_int, [_VP, C.c_uint64]),
+    "isl_shard_init": (C.c_int, [C.c_int, C.c_int, _VP, _VPP]),
+    "isl_shard_free": (None, [_VP]),
+    "isl_shard_rank": (C.c_int, [_VP]),
+    "isl_shard_world": (C.c_int, [_VP]),
+    "isl_shard_enable_peer_exchange": (C.c_int, [_VP, C.c_uint64]),
+    "isl_index_search_sharded": (C.c_int, [_VP, _VP, C.c_uint64, f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u64p, f32p, u32p]),
+    "isl_index_search_sharded_dev": (C.c_int, [_VP, _VP, C.c_uint64, _VP, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _VP, _VP, _VP]),
+    "isl_shard_last_timing": (C.c_int, [_VP, f32p, f32p, f32p]),
+    "isl_index_search_packed_dev": (C.c_int, [_VP, C.c_uint64, _VP, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _VP]),
+    "isl_merge_packed_dev": (C.c_int, [_VP, C.c_uint32, C.c_uint64, C.c_uint32, _VP, _VP, _VP]),
+}
+
+# Test hooks: exported by the library, declared in the header only under ISL_TEST_HOOKS, not part of the product ABI.
+TEST_HOOKS = {
+    "isl_std_rng_draw": (C.c_int, [C.c_uint64, C.POINTER(C.c_uint8), C.c_uint64, C.c_uint64, u64p]),
 }
 
 _lib = None
@@ -229,6 +247,11 @@ def load(strict=True):
             continue
         fn.restype = res
         fn.argtypes = args
+    for name, (res, args) in TEST_HOOKS.items():
+        fn = getattr(lib, name, None)
+        if fn is not None:
+            fn.restype = res
+            fn.argtypes = args
     if missing and strict and not os.environ.get("ISL_DEV_ALLOW_MISSING"):
         raise ImportError(f"libislands_b200.so lacks symbols declared in islands_b200.h: {missing}")
     _lib = lib

@@ -390,8 +390,78 @@ class CsrGraph:
             self.max_level = level
         return nid
 
+    def set_neighbors(self, node_id, new_neighbors):
+        """CsrGraph::set_neighbors (leann.rs:256-293): same length overwrites in place, any other length
+        rebuilds offsets and neighbours; an unknown node is ignored."""
+        if node_id >= self.num_nodes:
+            return
+        nb = np.asarray(new_neighbors, np.uint64)
+        s, e = int(self.node_offsets[node_id]), int(self.node_offsets[node_id + 1])
+        if nb.size == e - s:
+            self.neighbors[s:e] = nb
+        else:
+            self.neighbors = np.concatenate([self.neighbors[:s], nb, self.neighbors[e:]])
+            delta = nb.size - (e - s)
+            off = self.node_offsets.astype(np.int64)
+            off[node_id + 1:] += delta
+            self.node_offsets = off.astype(np.uint64)
+        self.degree_counts[node_id] = nb.size
+
     def storage_bytes(self):
         return 8 * (self.node_offsets.size + self.neighbors.size + self.levels.size + self.degree_counts.size)
+
+
+class ShardComm:
+    """isl_shard: one rank's membership in a sharded index (NCCL communicator inside the library)."""
+
+    UNIQUE_ID_BYTES = 128
+
+    @staticmethod
+    def unique_id():
+        """ncclGetUniqueId: call on one rank, hand the 128 bytes to the others by any host channel."""
+        buf = (C.c_uint8 * ShardComm.UNIQUE_ID_BYTES)()
+        _check(_ffi.load().isl_shard_unique_id(buf, ShardComm.UNIQUE_ID_BYTES))
+        return bytes(buf)
+
+    def __init__(self, rank, world, unique_id):
+        uid = (C.c_uint8 * ShardComm.UNIQUE_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        h = C.c_void_p()
+        _check(_ffi.load().isl_shard_init(int(rank), int(world), uid, C.byref(h)))
+        self._h = h
+        self.rank, self.world = int(rank), int(world)
+
+    def enable_peer_exchange(self, max_records):
+        """Exchange by peer stores over NVLink instead of ncclAllGather (collective; ranks of one node)."""
+        _check(_ffi.load().isl_shard_enable_peer_exchange(self._h, int(max_records)))
+
+    def last_timing(self):
+        """(search_ms, exchange_ms, merge_ms) of the last sharded search on this rank (CUDA events)."""
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        _check(_ffi.load().isl_shard_last_timing(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def free(self):
+        if getattr(self, "_h", None) is not None:
+            _ffi.load().isl_shard_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def merge_packed_dev(d_records_ptr, parts, nq, k, d_ids_ptr, d_dist_ptr, d_count_ptr=None):
+    """Merge of `parts` record lists [parts][nq][k] (isl_shard_record) on the device."""
+    _check(_ffi.load().isl_merge_packed_dev(C.c_void_p(d_records_ptr), parts, nq, k, C.c_void_p(d_ids_ptr),
+                                            C.c_void_p(d_dist_ptr), C.c_void_p(d_count_ptr) if d_count_ptr else None))
+
+
+def set_caller_stream(cuda_stream_ptr):
+    """isl_set_caller_stream: the CUDA stream (raw cudaStream_t value, 0 / None = legacy default stream) on
+    which this thread produces the device buffers it hands to `_dev` entry points."""
+    _check(_ffi.load().isl_set_caller_stream(C.c_void_p(cuda_stream_ptr or 0)))
 
 
 class SearchStats:
@@ -469,6 +539,37 @@ class LeannIndex:
                                                 C.c_void_p(d_ids_ptr), C.c_void_p(d_dist_ptr),
                                                 C.c_void_p(d_count_ptr) if d_count_ptr else None,
                                                 C.c_void_p(d_stats_ptr) if d_stats_ptr else None))
+
+    def set_neighbors(self, node_id, new_neighbors):
+        """graph.set_neighbors (leann.rs:256-293) on the resident graph (device copy refreshed)."""
+        nb = np.ascontiguousarray(new_neighbors, np.uint64)
+        _check(_ffi.load().isl_index_set_neighbors(self._h, int(node_id), _ptr(nb, u64p) if nb.size else None, nb.size))
+
+    # -- sharded search (service.rs:777-801, search.rs:211-237; include/islands_b200.h "sharded search") --
+    def search_sharded(self, shard, id_base, queries, k, ef=None):
+        """Collective over the ranks of `shard` (a ShardComm): every rank passes the same queries, searches
+        its own shard and receives the same merged top-k with global ids (local id + id_base)."""
+        q = _f32(queries)
+        q = q.reshape(1, -1) if q.ndim == 1 else q
+        nq, qd = q.shape
+        ef = int(self.config.ef_search) if ef is None else int(ef)
+        ids = np.empty((nq, k), np.uint64)
+        dist = np.empty((nq, k), np.float32)
+        cnt = np.empty(nq, np.uint32)
+        _check(_ffi.load().isl_index_search_sharded(self._h, shard._h, int(id_base), _ptr(q, f32p), nq, qd, k, ef,
+                                                    _ptr(ids, u64p), _ptr(dist, f32p), _ptr(cnt, u32p)))
+        return ids, dist, cnt
+
+    def search_sharded_dev(self, shard, id_base, d_queries_ptr, nq, dim, k, ef, d_ids_ptr, d_dist_ptr, d_count_ptr=None):
+        """The same with queries and outputs on the device (raw addresses)."""
+        _check(_ffi.load().isl_index_search_sharded_dev(self._h, shard._h, int(id_base), C.c_void_p(d_queries_ptr), nq, dim,
+                                                        k, int(ef), C.c_void_p(d_ids_ptr), C.c_void_p(d_dist_ptr),
+                                                        C.c_void_p(d_count_ptr) if d_count_ptr else None))
+
+    def search_packed_dev(self, id_base, d_queries_ptr, nq, dim, k, ef, d_records_ptr):
+        """This shard's half of a sharded search: [nq][k] isl_shard_record on the device, no exchange."""
+        _check(_ffi.load().isl_index_search_packed_dev(self._h, int(id_base), C.c_void_p(d_queries_ptr), nq, dim, k,
+                                                       int(ef), C.c_void_p(d_records_ptr)))
 
     def free(self):
         if self._h is not None:
@@ -741,12 +842,13 @@ class PQConfig:
     """PQConfig (pq.rs:13-65)."""
 
     def __init__(self, num_subquantizers=8, num_centroids=256, training_iterations=25, seed=None):
-        self._s = PQConfigStruct(num_subquantizers, num_centroids, training_iterations, -1 if seed is None else seed)
+        self._s = PQConfigStruct(num_subquantizers, num_centroids, training_iterations, 0 if seed is None else int(seed),
+                                 0 if seed is None else 1)
 
     num_subquantizers = property(lambda self: self._s.num_subquantizers)
     num_centroids = property(lambda self: self._s.num_centroids)
     training_iterations = property(lambda self: self._s.training_iterations)
-    seed = property(lambda self: None if self._s.seed < 0 else self._s.seed)
+    seed = property(lambda self: self._s.seed if self._s.has_seed else None)
 
     def validate(self, dimension):
         _check(_ffi.load().isl_pq_config_validate(C.byref(self._s), dimension))

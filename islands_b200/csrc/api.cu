@@ -64,6 +64,48 @@ isl_status index_alloc_common(isl_index* idx) {
   return ISL_OK;
 }
 
+isl_status SearchScratch::init() {
+  ISL_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  ISL_CUDA_TRY(cudaEventCreate(&ev0));
+  ISL_CUDA_TRY(cudaEventCreate(&ev1));
+  ISL_CUDA_TRY(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+  ISL_TRY(ensure(counters, 4));
+  return ISL_OK;
+}
+SearchScratch::~SearchScratch() {
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  if (ev_in) cudaEventDestroy(ev_in);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+ScratchLease::ScratchLease(const isl_index* i) : idx(i) {
+  {
+    std::lock_guard<std::mutex> lock(idx->pool_mu);
+    if (!idx->pool.empty()) {
+      sc = std::move(idx->pool.back());
+      idx->pool.pop_back();
+    }
+  }
+  if (!sc) {
+    sc.reset(new SearchScratch());
+    status = sc->init();
+  }
+}
+ScratchLease::~ScratchLease() {
+  if (!sc || status != ISL_OK) return;  // a scratch that failed to initialise is dropped
+  std::lock_guard<std::mutex> lock(idx->pool_mu);
+  idx->pool.push_back(std::move(sc));
+}
+
+static thread_local cudaStream_t t_caller_stream = nullptr;  // nullptr = the legacy default stream
+cudaStream_t caller_stream() { return t_caller_stream ? t_caller_stream : cudaStreamLegacy; }
+isl_status order_after_caller(cudaStream_t st, cudaEvent_t ev) {
+  ISL_CUDA_TRY(cudaEventRecord(ev, caller_stream()));
+  ISL_CUDA_TRY(cudaStreamWaitEvent(st, ev, 0));
+  return ISL_OK;
+}
+
 // Uploads h_offsets / h_nbrs to the device (u64 offsets, u32 ids) and derives max_degree.
 isl_status index_finish_graph(isl_index* idx) {
   const uint64_t n = idx->n;
@@ -136,18 +178,19 @@ void fill_empty(uint64_t nq, uint32_t k, uint64_t* ids, float* dist, uint32_t* c
 }
 
 // Core of isl_index_search*: queries already on the device as [nq][q_ld] (q_ld % 4 == 0, zero
-// padded), outputs on the device.
-static isl_status search_device(const isl_index* idx, const float* d_queries, uint32_t q_ld,
-                                uint64_t nq, uint32_t k, uint32_t ef, uint64_t* d_ids, float* d_dist,
-                                uint32_t* d_count, isl_search_stats* d_stats) {
+// padded), outputs on the device.  shard: where the shard-exchange records go (api_shard.cu), or null.
+isl_status search_device(const isl_index* idx, SearchScratch* sc, const float* d_queries, uint32_t q_ld,
+                         uint64_t nq, uint32_t k, uint32_t ef, uint64_t* d_ids, float* d_dist,
+                         uint32_t* d_count, isl_search_stats* d_stats, const ShardOut* shard) {
   SearchPlan plan;
   const uint32_t u_cap = std::max<uint32_t>(32, round_up(idx->max_degree, 32));
   ISL_TRY(plan_search(idx->cfg.metric, idx->ld, ef, u_cap, idx->sms, &plan));
   const uint32_t vis_words = round_up((uint32_t)((idx->n + 31) / 32), 4);
   const uint32_t slots = (uint32_t)std::min<uint64_t>(plan.grid, nq);
-  ISL_TRY(ensure(idx->visited, (size_t)slots * vis_words));
-  if (!plan.r_in_smem) ISL_TRY(ensure(idx->r_global, (size_t)slots * ef));
-  ISL_CUDA_TRY(cudaMemsetAsync(idx->counters.p, 0, 4 * sizeof(unsigned int), idx->stream));
+  ISL_TRY(ensure(sc->visited, (size_t)slots * vis_words));
+  if (!plan.r_in_smem) ISL_TRY(ensure(sc->r_global, (size_t)slots * ef));
+  ISL_TRY(ensure(sc->ties_global, (size_t)slots * ef));
+  ISL_CUDA_TRY(cudaMemsetAsync(sc->counters.p, 0, 4 * sizeof(unsigned int), sc->stream));
 
   SearchArgs a{};
   a.vectors = idx->vectors.p;
@@ -165,39 +208,44 @@ static isl_status search_device(const isl_index* idx, const float* d_queries, ui
   a.metric = idx->cfg.metric;
   a.prune_ratio = idx->cfg.prune_ratio;
   a.strategy = idx->cfg.pruning_strategy;
-  a.visited = idx->visited.p;
+  a.visited = sc->visited.p;
   a.vis_words = vis_words;
-  a.r_global = idx->r_global.p;
+  a.r_global = sc->r_global.p;
+  a.ties_global = sc->ties_global.p;
   a.u_cap = u_cap;
   a.out_ids = d_ids;
   a.out_ids32 = nullptr;
   a.out_dist = d_dist;
   a.out_count = d_count;
+  if (shard) a.shard = *shard;
   a.stats = d_stats;
-  a.work_counter = idx->counters.p;
-  a.error_flag = idx->counters.p + 1;
+  a.work_counter = sc->counters.p;
+  a.error_flag = sc->counters.p + 1;
 
-  ISL_CUDA_TRY(cudaEventRecord(idx->ev0, idx->stream));
-  ISL_TRY(launch_search(plan, a, idx->stream));
-  ISL_CUDA_TRY(cudaEventRecord(idx->ev1, idx->stream));
-  idx->last_launches = 1;
+  ISL_CUDA_TRY(cudaEventRecord(sc->ev0, sc->stream));
+  ISL_TRY(launch_search(plan, a, sc->stream));
+  ISL_CUDA_TRY(cudaEventRecord(sc->ev1, sc->stream));
   return ISL_OK;
 }
 
-isl_status search_finish(const isl_index* idx) {
+// Waits for the call's stream, reads the guard flag and publishes the kernel time on the handle.
+isl_status search_finish(const isl_index* idx, SearchScratch* sc, uint64_t launches) {
   unsigned int h[4] = {0, 0, 0, 0};
-  ISL_CUDA_TRY(cudaMemcpyAsync(h, idx->counters.p, sizeof(h), cudaMemcpyDeviceToHost, idx->stream));
-  ISL_CUDA_TRY(cudaStreamSynchronize(idx->stream));
+  ISL_CUDA_TRY(cudaMemcpyAsync(h, sc->counters.p, sizeof(h), cudaMemcpyDeviceToHost, sc->stream));
+  ISL_CUDA_TRY(cudaStreamSynchronize(sc->stream));
   float ms = 0.0f;
-  if (cudaEventElapsedTime(&ms, idx->ev0, idx->ev1) == cudaSuccess) idx->last_kernel_ms = ms;
-  if (h[1])
-    return fail(ISL_INVALID_ARGUMENT,
-                "search: more than 64 unexpanded candidates tie exactly with the worst result distance");
+  if (cudaEventElapsedTime(&ms, sc->ev0, sc->ev1) == cudaSuccess) sc->kernel_ms = ms;
+  {
+    std::lock_guard<std::mutex> lock(idx->pool_mu);
+    idx->last_kernel_ms = sc->kernel_ms;
+    idx->last_launches = launches;
+  }
+  if (h[1]) return fail(ISL_CUDA_ERROR, "search: internal invariant violated (tie list overflow)");
   return ISL_OK;
 }
 
 isl_status search_checks(const isl_index* idx, const void* queries, uint64_t nq,
-                                uint32_t query_dim, uint32_t k, uint32_t* ef, bool* trivial) {
+                                uint32_t query_dim, uint32_t k, uint32_t* ef, bool* trivial, bool need_vectors) {
   *trivial = false;
   if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
   if (nq > 0 && !queries) return fail(ISL_INVALID_ARGUMENT, "queries is null");
@@ -210,12 +258,44 @@ isl_status search_checks(const isl_index* idx, const void* queries, uint64_t nq,
     return fail(ISL_DIM_MISMATCH, "dimension mismatch: expected " + std::to_string(idx->dim) +
                                       ", got " + std::to_string(query_dim));
   if (idx->entry < 0) return fail(ISL_INDEX_NOT_BUILT, "index not built");  // leann.rs:889
+  if (need_vectors && !idx->vectors.p)
+    return fail(ISL_INVALID_ARGUMENT, "the stored vectors were dropped (isl_index_drop_vectors): only "
+                                      "isl_index_search_adc_recompute works on this handle");
   if (idx->cfg.prune_ratio != 0.0f && idx->cfg.pruning_strategy == ISL_PRUNE_PROPORTIONAL)
     return fail(ISL_INVALID_CONFIG,
                 "PruningStrategy::Proportional draws from thread_rng in the reference and has no "
                 "deterministic definition; use Global or Local");
   *ef = std::max(*ef, k);  // leann.rs:890
   if (*ef > (1u << 24)) return fail(ISL_INVALID_ARGUMENT, "ef too large");
+  return ISL_OK;
+}
+
+// Device outputs of a search over an empty index / zero k: ids all ones, distances +inf, counts 0.
+isl_status fill_empty_dev(uint64_t nq, uint32_t k, uint64_t* d_ids, float* d_dist, uint32_t* d_count,
+                          isl_search_stats* d_stats) {
+  if (nq && k) {
+    if (d_ids) ISL_CUDA_TRY(cudaMemset(d_ids, 0xff, nq * k * 8));
+    if (d_dist) {
+      std::vector<float> inf(nq * k, std::numeric_limits<float>::infinity());
+      ISL_CUDA_TRY(cudaMemcpy(d_dist, inf.data(), nq * k * 4, cudaMemcpyHostToDevice));
+    }
+  }
+  if (d_count && nq) ISL_CUDA_TRY(cudaMemset(d_count, 0, nq * 4));
+  if (d_stats && nq) ISL_CUDA_TRY(cudaMemset(d_stats, 0, nq * sizeof(isl_search_stats)));
+  return ISL_OK;
+}
+
+// Queries on the device: used as they are when aligned, else padded into the call's staging buffer.
+isl_status stage_device_queries(const isl_index* idx, SearchScratch* sc, const float* d_queries, uint64_t nq,
+                                uint32_t query_dim, const float** q, uint32_t* q_ld) {
+  *q = d_queries;
+  *q_ld = query_dim;
+  if (query_dim % 4 != 0 || (reinterpret_cast<uintptr_t>(d_queries) & 15)) {
+    ISL_TRY(ensure(sc->q_stage, nq * idx->ld));
+    ISL_TRY(launch_pad_rows(d_queries, query_dim, sc->q_stage.p, idx->ld, nq, sc->stream));
+    *q = sc->q_stage.p;
+    *q_ld = idx->ld;
+  }
   return ISL_OK;
 }
 
@@ -240,6 +320,10 @@ int isl_device_count(void) {
     return 0;
   }
   return c;
+}
+isl_status isl_set_caller_stream(void* cuda_stream) {
+  t_caller_stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  return ISL_OK;
 }
 uint64_t isl_kernel_launch_count(void) { return g_launch_count.load(); }
 void isl_kernel_launch_count_reset(void) { g_launch_count.store(0); }
@@ -307,7 +391,8 @@ isl_status isl_pq_config_default(isl_pq_config* c) {
   c->num_subquantizers = 8;  // pq.rs:24-33
   c->num_centroids = 256;
   c->training_iterations = 25;
-  c->seed = -1;
+  c->seed = 0;  // None
+  c->has_seed = 0;
   return ISL_OK;
 }
 isl_status isl_pq_config_validate(const isl_pq_config* c, uint64_t dimension) {
@@ -493,6 +578,34 @@ isl_status isl_index_get_neighbors(const isl_index* idx, uint64_t node_id, uint6
   return ISL_OK;
 }
 
+// CsrGraph::set_neighbors (leann.rs:256-293).  Same-length lists are overwritten in place, any other length
+// rebuilds offsets and neighbours (the reference's "expensive but rare" branch); the device copy of the graph
+// (CSR + padded adjacency) is refreshed either way.
+isl_status isl_index_set_neighbors(isl_index* idx, uint64_t node_id, const uint64_t* neighbors, uint64_t count) {
+  if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
+  if (node_id >= idx->n) return ISL_OK;  // leann.rs:258-260: silently ignored
+  if (count && !neighbors) return fail(ISL_INVALID_ARGUMENT, "neighbors is null");
+  for (uint64_t i = 0; i < count; ++i)
+    if (neighbors[i] >= idx->n)  // the provider would fail with NodeNotFound at search time (leann.rs:146-149)
+      return fail(ISL_NODE_NOT_FOUND, "neighbor id " + std::to_string(neighbors[i]) + " out of range");
+  DeviceGuard g(idx->device);
+  std::unique_lock<std::shared_mutex> lock(idx->mu);
+  const uint64_t s = idx->h_offsets[node_id], e = idx->h_offsets[node_id + 1];
+  if (count == e - s) {
+    std::copy(neighbors, neighbors + count, idx->h_nbrs.begin() + s);
+  } else {
+    std::vector<uint64_t> nb;
+    nb.reserve(idx->h_nbrs.size() + count - (e - s));
+    nb.insert(nb.end(), idx->h_nbrs.begin(), idx->h_nbrs.begin() + s);
+    nb.insert(nb.end(), neighbors, neighbors + count);
+    nb.insert(nb.end(), idx->h_nbrs.begin() + e, idx->h_nbrs.end());
+    idx->h_nbrs.swap(nb);
+    const int64_t delta = (int64_t)count - (int64_t)(e - s);
+    for (uint64_t i = node_id + 1; i <= idx->n; ++i) idx->h_offsets[i] = (uint64_t)((int64_t)idx->h_offsets[i] + delta);
+  }
+  return index_finish_graph(idx);
+}
+
 isl_status isl_index_search(const isl_index* idx, const float* queries, uint64_t nq,
                             uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* out_ids,
                             float* out_dist, uint32_t* out_count, isl_search_stats* stats) {
@@ -504,26 +617,26 @@ isl_status isl_index_search(const isl_index* idx, const float* queries, uint64_t
   }
   if (!out_ids || !out_dist) return fail(ISL_INVALID_ARGUMENT, "output pointer is null");
   DeviceGuard g(idx->device);
-  std::lock_guard<std::mutex> lock(idx->mu);
-  ISL_TRY(ensure(idx->q_stage, nq * idx->ld));
-  ISL_TRY(ensure(idx->out_ids, nq * k));
-  ISL_TRY(ensure(idx->out_dist, nq * k));
-  ISL_TRY(ensure(idx->out_count, nq));
-  if (stats) ISL_TRY(ensure(idx->out_stats, nq));
-  if (idx->ld != idx->dim)
-    ISL_CUDA_TRY(cudaMemsetAsync(idx->q_stage.p, 0, nq * idx->ld * 4, idx->stream));
-  ISL_CUDA_TRY(cudaMemcpy2DAsync(idx->q_stage.p, (size_t)idx->ld * 4, queries, (size_t)idx->dim * 4,
-                                 (size_t)idx->dim * 4, nq, cudaMemcpyHostToDevice, idx->stream));
-  ISL_TRY(search_device(idx, idx->q_stage.p, idx->ld, nq, k, ef, idx->out_ids.p, idx->out_dist.p,
-                        idx->out_count.p, stats ? idx->out_stats.p : nullptr));
-  ISL_CUDA_TRY(cudaMemcpyAsync(out_ids, idx->out_ids.p, nq * k * 8, cudaMemcpyDeviceToHost, idx->stream));
-  ISL_CUDA_TRY(cudaMemcpyAsync(out_dist, idx->out_dist.p, nq * k * 4, cudaMemcpyDeviceToHost, idx->stream));
-  if (out_count)
-    ISL_CUDA_TRY(cudaMemcpyAsync(out_count, idx->out_count.p, nq * 4, cudaMemcpyDeviceToHost, idx->stream));
+  std::shared_lock<std::shared_mutex> lock(idx->mu);
+  ScratchLease sc(idx);
+  ISL_TRY(sc.status);
+  cudaStream_t st = sc->stream;
+  ISL_TRY(ensure(sc->q_stage, nq * idx->ld));
+  ISL_TRY(ensure(sc->out_ids, nq * k));
+  ISL_TRY(ensure(sc->out_dist, nq * k));
+  ISL_TRY(ensure(sc->out_count, nq));
+  if (stats) ISL_TRY(ensure(sc->out_stats, nq));
+  if (idx->ld != idx->dim) ISL_CUDA_TRY(cudaMemsetAsync(sc->q_stage.p, 0, nq * idx->ld * 4, st));
+  ISL_CUDA_TRY(cudaMemcpy2DAsync(sc->q_stage.p, (size_t)idx->ld * 4, queries, (size_t)idx->dim * 4,
+                                 (size_t)idx->dim * 4, nq, cudaMemcpyHostToDevice, st));
+  ISL_TRY(search_device(idx, sc.get(), sc->q_stage.p, idx->ld, nq, k, ef, sc->out_ids.p, sc->out_dist.p,
+                        sc->out_count.p, stats ? sc->out_stats.p : nullptr, nullptr));
+  ISL_CUDA_TRY(cudaMemcpyAsync(out_ids, sc->out_ids.p, nq * k * 8, cudaMemcpyDeviceToHost, st));
+  ISL_CUDA_TRY(cudaMemcpyAsync(out_dist, sc->out_dist.p, nq * k * 4, cudaMemcpyDeviceToHost, st));
+  if (out_count) ISL_CUDA_TRY(cudaMemcpyAsync(out_count, sc->out_count.p, nq * 4, cudaMemcpyDeviceToHost, st));
   if (stats)
-    ISL_CUDA_TRY(cudaMemcpyAsync(stats, idx->out_stats.p, nq * sizeof(isl_search_stats),
-                                 cudaMemcpyDeviceToHost, idx->stream));
-  return search_finish(idx);
+    ISL_CUDA_TRY(cudaMemcpyAsync(stats, sc->out_stats.p, nq * sizeof(isl_search_stats), cudaMemcpyDeviceToHost, st));
+  return search_finish(idx, sc.get(), 1);
 }
 
 isl_status isl_index_search_dev(const isl_index* idx, const float* d_queries, uint64_t nq,
@@ -533,31 +646,18 @@ isl_status isl_index_search_dev(const isl_index* idx, const float* d_queries, ui
   bool trivial;
   ISL_TRY(search_checks(idx, d_queries, nq, query_dim, k, &ef, &trivial));
   if (!d_out_ids || !d_out_dist) return fail(ISL_INVALID_ARGUMENT, "output pointer is null");
-  if (trivial) {
-    if (nq && k) {
-      // empty index: ids = INVALID (all ones), dist = +inf is written as NaN-free pattern
-      ISL_CUDA_TRY(cudaMemset(d_out_ids, 0xff, nq * k * 8));
-      std::vector<float> inf(nq * k, std::numeric_limits<float>::infinity());
-      ISL_CUDA_TRY(cudaMemcpy(d_out_dist, inf.data(), nq * k * 4, cudaMemcpyHostToDevice));
-    }
-    if (d_out_count && nq) ISL_CUDA_TRY(cudaMemset(d_out_count, 0, nq * 4));
-    if (d_stats && nq) ISL_CUDA_TRY(cudaMemset(d_stats, 0, nq * sizeof(isl_search_stats)));
-    return ISL_OK;
-  }
+  if (trivial) return fill_empty_dev(nq, k, d_out_ids, d_out_dist, d_out_count, d_stats);
   DeviceGuard g(idx->device);
-  std::lock_guard<std::mutex> lock(idx->mu);
-  const float* q = d_queries;
-  uint32_t q_ld = query_dim;
-  if (query_dim % 4 != 0 || (reinterpret_cast<uintptr_t>(d_queries) & 15)) {
-    ISL_TRY(ensure(idx->q_stage, nq * idx->ld));
-    ISL_TRY(launch_pad_rows(d_queries, query_dim, idx->q_stage.p, idx->ld, nq, idx->stream));
-    q = idx->q_stage.p;
-    q_ld = idx->ld;
-  }
-  // The caller's buffers may have been produced on another stream: order after everything
-  // already enqueued on the legacy default stream.
-  ISL_TRY(search_device(idx, q, q_ld, nq, k, ef, d_out_ids, d_out_dist, d_out_count, d_stats));
-  return search_finish(idx);
+  std::shared_lock<std::shared_mutex> lock(idx->mu);
+  ScratchLease sc(idx);
+  ISL_TRY(sc.status);
+  // the caller's buffers may still be being written on the caller's stream (isl_set_caller_stream)
+  ISL_TRY(order_after_caller(sc->stream, sc->ev_in));
+  const float* q;
+  uint32_t q_ld;
+  ISL_TRY(stage_device_queries(idx, sc.get(), d_queries, nq, query_dim, &q, &q_ld));
+  ISL_TRY(search_device(idx, sc.get(), q, q_ld, nq, k, ef, d_out_ids, d_out_dist, d_out_count, d_stats, nullptr));
+  return search_finish(idx, sc.get(), 1);
 }
 
 isl_status isl_index_search_default(const isl_index* idx, const float* queries, uint64_t nq,
@@ -570,6 +670,7 @@ isl_status isl_index_search_default(const isl_index* idx, const float* queries, 
 
 isl_status isl_index_last_search_timing(const isl_index* idx, float* kernel_ms, uint64_t* kernel_launches) {
   if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
+  std::lock_guard<std::mutex> lock(idx->pool_mu);
   if (kernel_ms) *kernel_ms = idx->last_kernel_ms;
   if (kernel_launches) *kernel_launches = idx->last_launches;
   return ISL_OK;

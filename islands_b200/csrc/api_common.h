@@ -1,7 +1,9 @@
 // api_common.h — handle definitions shared by the C-ABI translation units.
 #pragma once
 
+#include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -25,6 +27,42 @@ struct DeviceGuard {
 
 isl_status current_device(int* device, int* sms);
 inline uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
+
+// Everything one search call needs besides the resident index: its own stream, events and scratch buffers.
+// A handle keeps a pool of these (ScratchLease), so searches on one handle from several threads — legal in the
+// reference, where search takes `&self` (leann.rs:858-896) — run side by side instead of queueing on a mutex.
+struct SearchScratch {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_in = nullptr;
+  DevBuf<uint32_t> visited;
+  DevBuf<uint2> r_global;
+  DevBuf<uint2> ties_global;
+  DevBuf<unsigned int> counters;  // [0] work counter, [1] invariant guard, [2] hub-cache hits
+  DevBuf<float> q_stage;
+  DevBuf<uint64_t> out_ids;
+  DevBuf<float> out_dist;
+  DevBuf<uint32_t> out_count;
+  DevBuf<isl_search_stats> out_stats;
+  DevBuf<float> aux_f32;  // two-level: LUTs / approximate queues
+  DevBuf<uint2> aux_u2;
+  // ADC traversal -> rerank / recompute hand-over
+  DevBuf<uint32_t> rc_flags, rc_rows, rc_surv, rc_surv_cnt;
+  DevBuf<int32_t> rc_tok, rc_len;
+  DevBuf<float> rc_emb, rc_sq;
+  DevBuf<uint8_t> rc_tmp;
+  // shard exchange (api_shard.cu)
+  DevBuf<uint4> packed, gathered;
+  float kernel_ms = 0.0f;
+  isl_status init();
+  ~SearchScratch();
+};
+
+// The stream whose already-enqueued work a `_dev` entry point must wait for (isl_set_caller_stream; legacy
+// default stream unless set).  Thread-local.
+cudaStream_t caller_stream();
+// Makes `st` wait for everything enqueued so far on the caller's stream (device pointers handed to a `_dev`
+// entry point may still be being written there).
+isl_status order_after_caller(cudaStream_t st, cudaEvent_t ev);
 
 }  // namespace isl
 
@@ -87,32 +125,35 @@ struct isl_index {
   mutable uint64_t last_hub_hits = 0;
   uint32_t rerank_limit = 0;  // ADC traversal + rerank / recompute: survivors that get an exact distance (0 = all ef)
   uint32_t tok_len = 0;
-  mutable isl::DevBuf<uint32_t> rc_flags, rc_rows, rc_surv, rc_surv_cnt;
-  mutable isl::DevBuf<int32_t> rc_tok, rc_len;
-  mutable isl::DevBuf<float> rc_emb, rc_sq;
-  mutable isl::DevBuf<uint8_t> rc_tmp;
   mutable uint64_t last_recomputed = 0;
   mutable float last_encoder_ms = 0.0f, last_traverse_ms = 0.0f, last_rerank_ms = 0.0f;
-  // per-handle stream, timing and scratch (guarded by mu: searches on one handle serialise)
-  mutable std::mutex mu;
+  // Searches hold `mu` shared (they only read the handle), mutators (attach / drop / set_*) hold it exclusively.
+  mutable std::shared_mutex mu;
+  // set-up stream and scratch (construction, uploads); searches lease a SearchScratch from the pool instead
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  mutable isl::DevBuf<uint32_t> visited;      // construction only (released when the graph is finished)
+  mutable isl::DevBuf<uint2> r_global;        // construction only
+  mutable isl::DevBuf<uint2> ties_global;     // construction only
+  mutable isl::DevBuf<unsigned int> counters; // construction only
+  mutable std::mutex pool_mu;                 // guards `pool` and the last_* timing fields
+  mutable std::vector<std::unique_ptr<isl::SearchScratch>> pool;
   mutable float last_kernel_ms = 0.0f;
   mutable uint64_t last_launches = 0;
-  mutable isl::DevBuf<uint32_t> visited;
-  mutable isl::DevBuf<uint2> r_global;
-  mutable isl::DevBuf<unsigned int> counters;  // [0] work counter, [1] error flag
-  mutable isl::DevBuf<float> q_stage;
-  mutable isl::DevBuf<uint64_t> out_ids;
-  mutable isl::DevBuf<float> out_dist;
-  mutable isl::DevBuf<uint32_t> out_count;
-  mutable isl::DevBuf<isl_search_stats> out_stats;
-  mutable isl::DevBuf<float> aux_f32;   // two-level: LUTs / approximate queues
-  mutable isl::DevBuf<uint2> aux_u2;
   ~isl_index();
 };
 
 namespace isl {
+// Takes a SearchScratch out of the handle's pool (creating one when all are in use) and puts it back on scope exit.
+struct ScratchLease {
+  const isl_index* idx;
+  std::unique_ptr<SearchScratch> sc;
+  isl_status status = ISL_OK;
+  explicit ScratchLease(const isl_index* i);
+  ~ScratchLease();
+  SearchScratch* operator->() const { return sc.get(); }
+  SearchScratch* get() const { return sc.get(); }
+};
 // Shared by api_index.cu and build.cu.
 isl_status index_alloc_common(isl_index* idx);
 isl_status index_finish_graph(isl_index* idx);  // uploads CSR, computes max degree
@@ -120,8 +161,15 @@ isl_status index_make_padded_adjacency(isl_index* idx);  // device CSR -> adj_pa
 void search_args_set_graph(const isl_index* idx, SearchArgs* a);
 void fill_empty(uint64_t nq, uint32_t k, uint64_t* ids, float* dist, uint32_t* count, isl_search_stats* stats);
 isl_status search_checks(const isl_index* idx, const void* queries, uint64_t nq, uint32_t query_dim, uint32_t k,
-                         uint32_t* ef, bool* trivial);
-isl_status search_finish(const isl_index* idx);
+                         uint32_t* ef, bool* trivial, bool need_vectors = true);
+isl_status search_device(const isl_index* idx, SearchScratch* sc, const float* d_queries, uint32_t q_ld, uint64_t nq,
+                         uint32_t k, uint32_t ef, uint64_t* d_ids, float* d_dist, uint32_t* d_count,
+                         isl_search_stats* d_stats, const ShardOut* shard);
+isl_status fill_empty_dev(uint64_t nq, uint32_t k, uint64_t* d_ids, float* d_dist, uint32_t* d_count,
+                          isl_search_stats* d_stats);
+isl_status stage_device_queries(const isl_index* idx, SearchScratch* sc, const float* d_queries, uint64_t nq,
+                                uint32_t query_dim, const float** q, uint32_t* q_ld);
+isl_status search_finish(const isl_index* idx, SearchScratch* sc, uint64_t launches);
 isl_status pq_upload_codebooks(isl_pq* pq);
 template <class T>
 isl_status ensure(DevBuf<T>& b, size_t count) {

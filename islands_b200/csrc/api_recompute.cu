@@ -82,8 +82,11 @@ isl_status isl_index_set_recompute(isl_index* idx, isl_encoder* enc, const int32
                                    uint32_t seq_len) {
   if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
   DeviceGuard g(idx->device);
-  std::lock_guard<std::mutex> lock(idx->mu);
+  std::unique_lock<std::shared_mutex> lock(idx->mu);
   if (!enc) {  // detach
+    if (idx->n && !idx->vectors.p)
+      return fail(ISL_INVALID_ARGUMENT, "the stored vectors were dropped: detaching the encoder would leave the index "
+                                        "without any source of embeddings");
     idx->encoder = nullptr;
     idx->node_tokens.release();
     idx->node_lengths.release();
@@ -122,7 +125,7 @@ isl_status isl_index_set_recompute(isl_index* idx, isl_encoder* enc, const int32
 isl_status isl_index_set_hub_cache(isl_index* idx, uint64_t count) {
   if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
   DeviceGuard g(idx->device);
-  std::lock_guard<std::mutex> lock(idx->mu);
+  std::unique_lock<std::shared_mutex> lock(idx->mu);
   if (!idx->encoder) return fail(ISL_INVALID_ARGUMENT, "no recompute encoder attached (isl_index_set_recompute)");
   idx->hub_count = 0;
   idx->hub_emb.release();
@@ -176,7 +179,7 @@ isl_status isl_index_hub_cache_info(const isl_index* idx, uint64_t* cached_nodes
 isl_status isl_index_drop_vectors(isl_index* idx) {
   if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
   DeviceGuard g(idx->device);
-  std::lock_guard<std::mutex> lock(idx->mu);
+  std::unique_lock<std::shared_mutex> lock(idx->mu);
   if (!idx->encoder) return fail(ISL_INVALID_ARGUMENT, "attach a recompute encoder before dropping the stored vectors");
   idx->vectors.release();
   idx->sqnorms.release();
@@ -187,7 +190,7 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
                                           uint32_t k, uint32_t ef, uint64_t* out_ids, float* out_dist,
                                           uint32_t* out_count, isl_search_stats* stats) {
   bool trivial;
-  ISL_TRY(search_checks(idx, queries, nq, query_dim, k, &ef, &trivial));
+  ISL_TRY(search_checks(idx, queries, nq, query_dim, k, &ef, &trivial, /*need_vectors=*/false));
   if (trivial) {
     fill_empty(nq, k, out_ids, out_dist, out_count, stats);
     return ISL_OK;
@@ -197,7 +200,9 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
   if (!out_ids || !out_dist) return fail(ISL_INVALID_ARGUMENT, "output pointer is null");
   const isl_pq* pq = idx->pq;
   DeviceGuard g(idx->device);
-  std::lock_guard<std::mutex> lock(idx->mu);
+  std::shared_lock<std::shared_mutex> lock(idx->mu);
+  ScratchLease sc(idx);
+  ISL_TRY(sc.status);
   const uint32_t m = (uint32_t)pq->cfg.num_subquantizers;
   const uint32_t lut_floats = m * pq->ksub;
   const uint32_t n = (uint32_t)idx->n;
@@ -209,28 +214,29 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
   ISL_TRY(plan_search_rerank(idx->cfg.metric, idx->ld, ef, u_cap_r, idx->sms, &plan_r));
   const uint32_t vis_words = round_up((uint32_t)((idx->n + 31) / 32), 4);
   const uint32_t slots = (uint32_t)std::min<uint64_t>(std::max(plan.grid, plan_r.grid), nq);
-  ISL_TRY(ensure(idx->visited, (size_t)slots * vis_words));
-  if (!plan.r_in_smem || !plan_r.r_in_smem) ISL_TRY(ensure(idx->r_global, (size_t)slots * ef));
-  ISL_TRY(ensure(idx->aux_f32, (size_t)nq * lut_floats + 2));
-  ISL_TRY(ensure(idx->q_stage, nq * idx->ld));
-  ISL_TRY(ensure(idx->out_ids, nq * k));
-  ISL_TRY(ensure(idx->out_dist, nq * k));
-  ISL_TRY(ensure(idx->out_count, nq));
-  ISL_TRY(ensure(idx->out_stats, nq));
-  ISL_TRY(ensure(idx->rc_surv, nq * (size_t)ef));
-  ISL_TRY(ensure(idx->rc_surv_cnt, nq));
-  ISL_TRY(ensure(idx->rc_flags, (size_t)n + 1));
-  ISL_TRY(ensure(idx->rc_rows, (size_t)n + 1));
-  cudaStream_t st = idx->stream;
-  if (idx->ld != idx->dim) ISL_CUDA_TRY(cudaMemsetAsync(idx->q_stage.p, 0, nq * idx->ld * 4, st));
-  ISL_CUDA_TRY(cudaMemcpy2DAsync(idx->q_stage.p, (size_t)idx->ld * 4, queries, (size_t)idx->dim * 4, (size_t)idx->dim * 4,
+  ISL_TRY(ensure(sc->visited, (size_t)slots * vis_words));
+  if (!plan.r_in_smem || !plan_r.r_in_smem) ISL_TRY(ensure(sc->r_global, (size_t)slots * ef));
+  ISL_TRY(ensure(sc->ties_global, (size_t)slots * ef));
+  ISL_TRY(ensure(sc->aux_f32, (size_t)nq * lut_floats + 2));
+  ISL_TRY(ensure(sc->q_stage, nq * idx->ld));
+  ISL_TRY(ensure(sc->out_ids, nq * k));
+  ISL_TRY(ensure(sc->out_dist, nq * k));
+  ISL_TRY(ensure(sc->out_count, nq));
+  ISL_TRY(ensure(sc->out_stats, nq));
+  ISL_TRY(ensure(sc->rc_surv, nq * (size_t)ef));
+  ISL_TRY(ensure(sc->rc_surv_cnt, nq));
+  ISL_TRY(ensure(sc->rc_flags, (size_t)n + 1));
+  ISL_TRY(ensure(sc->rc_rows, (size_t)n + 1));
+  cudaStream_t st = sc->stream;
+  if (idx->ld != idx->dim) ISL_CUDA_TRY(cudaMemsetAsync(sc->q_stage.p, 0, nq * idx->ld * 4, st));
+  ISL_CUDA_TRY(cudaMemcpy2DAsync(sc->q_stage.p, (size_t)idx->ld * 4, queries, (size_t)idx->dim * 4, (size_t)idx->dim * 4,
                                  nq, cudaMemcpyHostToDevice, st));
-  ISL_CUDA_TRY(cudaMemsetAsync(idx->counters.p, 0, 4 * sizeof(unsigned int), st));
+  ISL_CUDA_TRY(cudaMemsetAsync(sc->counters.p, 0, 4 * sizeof(unsigned int), st));
 
   // ---- 1. ADC traversal ------------------------------------------------------------------------
-  ISL_CUDA_TRY(cudaEventRecord(idx->ev0, st));
+  ISL_CUDA_TRY(cudaEventRecord(sc->ev0, st));
   const bool fused_lut = plan.lut_smem_floats != 0;  // tables built per query inside the traversal kernel
-  if (!fused_lut) ISL_TRY(launch_pq_tables(pq->dev(), idx->q_stage.p, idx->ld, nq, idx->aux_f32.p, idx->sms, st));
+  if (!fused_lut) ISL_TRY(launch_pq_tables(pq->dev(), sc->q_stage.p, idx->ld, nq, sc->aux_f32.p, idx->sms, st));
   SearchArgs a{};
   a.vectors = nullptr;  // phase 1 never reads an embedding
   a.sqnorms = nullptr;
@@ -238,24 +244,25 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
   a.d = idx->dim;
   a.n = n;
   search_args_set_graph(idx, &a);
-  a.queries = idx->q_stage.p;
+  a.queries = sc->q_stage.p;
   a.q_ld = idx->ld;
   a.nq = (uint32_t)nq;
   a.entry = (uint32_t)idx->entry;
   a.k = k;
   a.ef = ef;
   a.metric = idx->cfg.metric;
-  a.visited = idx->visited.p;
+  a.visited = sc->visited.p;
   a.vis_words = vis_words;
-  a.r_global = idx->r_global.p;
+  a.r_global = sc->r_global.p;
+  a.ties_global = sc->ties_global.p;
   a.u_cap = u_cap_t;
-  a.out_ids = idx->out_ids.p;
-  a.out_dist = idx->out_dist.p;
-  a.out_count = idx->out_count.p;
-  a.stats = idx->out_stats.p;
-  a.work_counter = idx->counters.p;
-  a.error_flag = idx->counters.p + 1;
-  a.luts = fused_lut ? nullptr : idx->aux_f32.p;
+  a.out_ids = sc->out_ids.p;
+  a.out_dist = sc->out_dist.p;
+  a.out_count = sc->out_count.p;
+  a.stats = sc->out_stats.p;
+  a.work_counter = sc->counters.p;
+  a.error_flag = sc->counters.p + 1;
+  a.luts = fused_lut ? nullptr : sc->aux_f32.p;
   a.pq_codebooks = pq->d_codebooks.p;
   a.pq_dsub = pq->dsub;
   a.pq_ld_sub = pq->ld_sub;
@@ -266,80 +273,83 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
   a.lut_smem_floats = plan.lut_smem_floats;
   a.phase = 1;
   a.rerank_limit = idx->rerank_limit ? std::max(idx->rerank_limit, k) : 0u;
-  a.surv_ids = idx->rc_surv.p;
-  a.surv_cnt = idx->rc_surv_cnt.p;
+  a.surv_ids = sc->rc_surv.p;
+  a.surv_cnt = sc->rc_surv_cnt.p;
   ISL_TRY(launch_search(plan, a, st));
-  ISL_CUDA_TRY(cudaEventRecord(idx->ev1, st));
+  ISL_CUDA_TRY(cudaEventRecord(sc->ev1, st));
 
   // ---- 2. recompute the distinct survivors ----------------------------------------------------------
-  ISL_CUDA_TRY(cudaMemsetAsync(idx->rc_flags.p, 0, ((size_t)n + 1) * 4, st));
-  mark_survivors_kernel<<<1184, 256, 0, st>>>(idx->rc_surv.p, idx->rc_surv_cnt.p, (uint32_t)nq, ef, idx->rc_flags.p);
+  ISL_CUDA_TRY(cudaMemsetAsync(sc->rc_flags.p, 0, ((size_t)n + 1) * 4, st));
+  mark_survivors_kernel<<<1184, 256, 0, st>>>(sc->rc_surv.p, sc->rc_surv_cnt.p, (uint32_t)nq, ef, sc->rc_flags.p);
   count_launch();
   const uint32_t hubs = (uint32_t)idx->hub_count;
   if (hubs) {  // survivors with a resident embedding are not recomputed
-    ISL_CUDA_TRY(cudaMemsetAsync(idx->counters.p + 2, 0, sizeof(unsigned int), st));
-    clear_cached_flags_kernel<<<1184, 256, 0, st>>>(idx->hub_row.p, n, idx->rc_flags.p, idx->counters.p + 2);
+    ISL_CUDA_TRY(cudaMemsetAsync(sc->counters.p + 2, 0, sizeof(unsigned int), st));
+    clear_cached_flags_kernel<<<1184, 256, 0, st>>>(idx->hub_row.p, n, sc->rc_flags.p, sc->counters.p + 2);
     count_launch();
   }
   size_t scan_bytes = 0;
-  ISL_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, idx->rc_flags.p, idx->rc_rows.p, (int)(n + 1), st));
-  ISL_TRY(ensure(idx->rc_tmp, scan_bytes + 16));
-  ISL_CUDA_TRY(cub::DeviceScan::ExclusiveSum(idx->rc_tmp.p, scan_bytes, idx->rc_flags.p, idx->rc_rows.p, (int)(n + 1), st));
+  ISL_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, sc->rc_flags.p, sc->rc_rows.p, (int)(n + 1), st));
+  ISL_TRY(ensure(sc->rc_tmp, scan_bytes + 16));
+  ISL_CUDA_TRY(cub::DeviceScan::ExclusiveSum(sc->rc_tmp.p, scan_bytes, sc->rc_flags.p, sc->rc_rows.p, (int)(n + 1), st));
   count_launch(2);
   uint32_t unique = 0, hub_hits = 0;
-  ISL_CUDA_TRY(cudaMemcpyAsync(&unique, idx->rc_rows.p + n, 4, cudaMemcpyDeviceToHost, st));
-  if (hubs) ISL_CUDA_TRY(cudaMemcpyAsync(&hub_hits, idx->counters.p + 2, 4, cudaMemcpyDeviceToHost, st));
+  ISL_CUDA_TRY(cudaMemcpyAsync(&unique, sc->rc_rows.p + n, 4, cudaMemcpyDeviceToHost, st));
+  if (hubs) ISL_CUDA_TRY(cudaMemcpyAsync(&hub_hits, sc->counters.p + 2, 4, cudaMemcpyDeviceToHost, st));
   ISL_CUDA_TRY(cudaStreamSynchronize(st));
-  idx->last_hub_hits = hub_hits;
-  float ms = 0.0f;
-  if (cudaEventElapsedTime(&ms, idx->ev0, idx->ev1) == cudaSuccess) idx->last_traverse_ms = ms;
+  float traverse_ms = 0.0f, encoder_ms = 0.0f;
+  cudaEventElapsedTime(&traverse_ms, sc->ev0, sc->ev1);
   const uint32_t S = idx->tok_len;
-  ISL_TRY(ensure(idx->rc_tok, (size_t)unique * S + 1));
-  ISL_TRY(ensure(idx->rc_len, (size_t)unique + 1));
+  ISL_TRY(ensure(sc->rc_tok, (size_t)unique * S + 1));
+  ISL_TRY(ensure(sc->rc_len, (size_t)unique + 1));
   // rerank matrix: [cached hub rows | rows recomputed for this batch]
-  ISL_TRY(ensure(idx->rc_emb, ((size_t)hubs + unique) * idx->ld + 4));
-  ISL_TRY(ensure(idx->rc_sq, (size_t)hubs + unique + 1));
+  ISL_TRY(ensure(sc->rc_emb, ((size_t)hubs + unique) * idx->ld + 4));
+  ISL_TRY(ensure(sc->rc_sq, (size_t)hubs + unique + 1));
   if (hubs) {
-    ISL_CUDA_TRY(cudaMemcpyAsync(idx->rc_emb.p, idx->hub_emb.p, (size_t)hubs * idx->ld * 4, cudaMemcpyDeviceToDevice, st));
-    ISL_CUDA_TRY(cudaMemcpyAsync(idx->rc_sq.p, idx->hub_sq.p, (size_t)hubs * 4, cudaMemcpyDeviceToDevice, st));
+    ISL_CUDA_TRY(cudaMemcpyAsync(sc->rc_emb.p, idx->hub_emb.p, (size_t)hubs * idx->ld * 4, cudaMemcpyDeviceToDevice, st));
+    ISL_CUDA_TRY(cudaMemcpyAsync(sc->rc_sq.p, idx->hub_sq.p, (size_t)hubs * 4, cudaMemcpyDeviceToDevice, st));
   }
-  gather_tokens_kernel<<<1184, 256, 0, st>>>(idx->rc_flags.p, idx->rc_rows.p, n, idx->node_tokens.p, idx->node_lengths.p, S,
-                                            idx->rc_tok.p, idx->rc_len.p);
+  gather_tokens_kernel<<<1184, 256, 0, st>>>(sc->rc_flags.p, sc->rc_rows.p, n, idx->node_tokens.p, idx->node_lengths.p, S,
+                                            sc->rc_tok.p, sc->rc_len.p);
   count_launch();
   ISL_CUDA_TRY(cudaGetLastError());
   ISL_CUDA_TRY(cudaStreamSynchronize(st));
-  idx->last_encoder_ms = 0.0f;
   if (unique) {
-    ISL_TRY(isl_encoder_embed_dev(idx->encoder, idx->rc_tok.p, idx->rc_len.p, unique, S, idx->rc_emb.p + (size_t)hubs * idx->ld));
-    isl_encoder_last_timing(idx->encoder, &idx->last_encoder_ms, nullptr);
-    ISL_TRY(launch_row_sqnorms(idx->rc_emb.p + (size_t)hubs * idx->ld, unique, idx->dim, idx->ld, idx->rc_sq.p + hubs, idx->sms, st));
+    ISL_TRY(isl_encoder_embed_dev(idx->encoder, sc->rc_tok.p, sc->rc_len.p, unique, S, sc->rc_emb.p + (size_t)hubs * idx->ld));
+    isl_encoder_last_timing(idx->encoder, &encoder_ms, nullptr);
+    ISL_TRY(launch_row_sqnorms(sc->rc_emb.p + (size_t)hubs * idx->ld, unique, idx->dim, idx->ld, sc->rc_sq.p + hubs, idx->sms, st));
   }
-  idx->last_recomputed = unique;
   if (hubs) {
-    final_rows_kernel<<<1184, 256, 0, st>>>(idx->hub_row.p, hubs, n, idx->rc_rows.p);
+    final_rows_kernel<<<1184, 256, 0, st>>>(idx->hub_row.p, hubs, n, sc->rc_rows.p);
     count_launch();
   }
 
   // ---- 3. exact rerank against the recomputed rows ---------------------------------------------------
-  ISL_CUDA_TRY(cudaMemsetAsync(idx->counters.p, 0, sizeof(unsigned int), st));
-  a.vectors = idx->rc_emb.p;
-  a.sqnorms = idx->rc_sq.p;
-  a.row_of_id = idx->rc_rows.p;
+  ISL_CUDA_TRY(cudaMemsetAsync(sc->counters.p, 0, sizeof(unsigned int), st));
+  a.vectors = sc->rc_emb.p;
+  a.sqnorms = sc->rc_sq.p;
+  a.row_of_id = sc->rc_rows.p;
   a.phase = 2;
   a.u_cap = u_cap_r;
   a.lut_smem_floats = 0;
-  ISL_CUDA_TRY(cudaEventRecord(idx->ev0, st));
+  ISL_CUDA_TRY(cudaEventRecord(sc->ev0, st));
   ISL_TRY(launch_search(plan_r, a, st));
-  ISL_CUDA_TRY(cudaEventRecord(idx->ev1, st));
-  idx->last_launches = 3;
+  ISL_CUDA_TRY(cudaEventRecord(sc->ev1, st));
 
-  ISL_CUDA_TRY(cudaMemcpyAsync(out_ids, idx->out_ids.p, nq * k * 8, cudaMemcpyDeviceToHost, st));
-  ISL_CUDA_TRY(cudaMemcpyAsync(out_dist, idx->out_dist.p, nq * k * 4, cudaMemcpyDeviceToHost, st));
-  if (out_count) ISL_CUDA_TRY(cudaMemcpyAsync(out_count, idx->out_count.p, nq * 4, cudaMemcpyDeviceToHost, st));
+  ISL_CUDA_TRY(cudaMemcpyAsync(out_ids, sc->out_ids.p, nq * k * 8, cudaMemcpyDeviceToHost, st));
+  ISL_CUDA_TRY(cudaMemcpyAsync(out_dist, sc->out_dist.p, nq * k * 4, cudaMemcpyDeviceToHost, st));
+  if (out_count) ISL_CUDA_TRY(cudaMemcpyAsync(out_count, sc->out_count.p, nq * 4, cudaMemcpyDeviceToHost, st));
   if (stats)
-    ISL_CUDA_TRY(cudaMemcpyAsync(stats, idx->out_stats.p, nq * sizeof(isl_search_stats), cudaMemcpyDeviceToHost, st));
-  ISL_TRY(search_finish(idx));
-  idx->last_rerank_ms = idx->last_kernel_ms;
+    ISL_CUDA_TRY(cudaMemcpyAsync(stats, sc->out_stats.p, nq * sizeof(isl_search_stats), cudaMemcpyDeviceToHost, st));
+  ISL_TRY(search_finish(idx, sc.get(), 3));
+  {
+    std::lock_guard<std::mutex> tl(idx->pool_mu);
+    idx->last_rerank_ms = sc->kernel_ms;
+    idx->last_traverse_ms = traverse_ms;
+    idx->last_encoder_ms = encoder_ms;
+    idx->last_recomputed = unique;
+    idx->last_hub_hits = hub_hits;
+  }
   return ISL_OK;
 }
 

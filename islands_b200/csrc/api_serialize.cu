@@ -112,7 +112,7 @@ isl_status isl_pq_to_bytes(const isl_pq* pq, uint8_t* out, uint64_t cap, uint64_
   w.u64(pq->cfg.num_subquantizers);  // PQConfig (pq.rs:13-22)
   w.u64(pq->cfg.num_centroids);
   w.u64(pq->cfg.training_iterations);
-  w.opt_u64(pq->cfg.seed >= 0, (uint64_t)pq->cfg.seed);
+  w.opt_u64(pq->cfg.has_seed != 0, pq->cfg.seed);
   const uint64_t m = pq->trained ? pq->cfg.num_subquantizers : 0;  // codebooks is empty until trained (pq.rs:142)
   w.u64(m);
   for (uint64_t j = 0; j < m; ++j) {
@@ -138,7 +138,8 @@ isl_status isl_pq_from_bytes(const uint8_t* bytes, uint64_t len, isl_pq** out) {
   c.num_centroids = r.u64();
   c.training_iterations = r.u64();
   uint64_t seed = 0;
-  c.seed = r.opt_u64(&seed) ? (int64_t)seed : -1;
+  c.has_seed = r.opt_u64(&seed) ? 1 : 0;
+  c.seed = c.has_seed ? seed : 0;
   const uint64_t m = r.seq_len(16);
   std::vector<float> cb;
   uint64_t ksub = 0, dsub_cb = 0;

@@ -19,7 +19,7 @@ isl_status isl_index_attach_pq(isl_index* idx, const isl_pq* pq, const uint16_t*
                                       std::to_string(pq->dim));
   if (idx->n && !codes) return fail(ISL_INVALID_ARGUMENT, "codes is null");
   DeviceGuard g(idx->device);
-  std::lock_guard<std::mutex> lock(idx->mu);
+  std::unique_lock<std::shared_mutex> lock(idx->mu);
   const uint32_t m = (uint32_t)pq->cfg.num_subquantizers;
   const uint64_t total = idx->n * m;
   for (uint64_t i = 0; i < total; ++i)
@@ -55,7 +55,9 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
   if (!out_ids || !out_dist) return fail(ISL_INVALID_ARGUMENT, "output pointer is null");
   const isl_pq* pq = idx->pq;
   DeviceGuard g(idx->device);
-  std::lock_guard<std::mutex> lock(idx->mu);
+  std::shared_lock<std::shared_mutex> lock(idx->mu);
+  ScratchLease sc(idx);
+  ISL_TRY(sc.status);
   const uint32_t m = (uint32_t)pq->cfg.num_subquantizers;
   const uint32_t lut_floats = m * pq->ksub;
 
@@ -75,24 +77,25 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
     const uint32_t vis_words2 = round_up((uint32_t)((idx->n + 31) / 32), 4);
     const uint32_t slots_t = (uint32_t)std::min<uint64_t>(pt.grid, nq), slots_r = (uint32_t)std::min<uint64_t>(pr.grid, nq);
     const bool novis = !stats && pt.novis_ok && idx->codes8.p && idx->n < kIdcMaxNodes;
-    if (!novis) ISL_TRY(ensure(idx->visited, (size_t)slots_t * vis_words2));  // the bitset-free traversal needs no scratch
-    if (!pt.r_in_smem || !pr.r_in_smem) ISL_TRY(ensure(idx->r_global, (size_t)std::max(slots_t, slots_r) * ef));
-    ISL_TRY(ensure(idx->aux_f32, (size_t)nq * lut_floats + 2));
-    ISL_TRY(ensure(idx->q_stage, nq * idx->ld));
-    ISL_TRY(ensure(idx->out_ids, nq * k));
-    ISL_TRY(ensure(idx->out_dist, nq * k));
-    ISL_TRY(ensure(idx->out_count, nq));
-    ISL_TRY(ensure(idx->out_stats, nq));
-    ISL_TRY(ensure(idx->rc_surv, nq * (size_t)ef));
-    ISL_TRY(ensure(idx->rc_surv_cnt, nq));
-    cudaStream_t st = idx->stream;
-    if (idx->ld != idx->dim) ISL_CUDA_TRY(cudaMemsetAsync(idx->q_stage.p, 0, nq * idx->ld * 4, st));
-    ISL_CUDA_TRY(cudaMemcpy2DAsync(idx->q_stage.p, (size_t)idx->ld * 4, queries, (size_t)idx->dim * 4,
+    if (!novis) ISL_TRY(ensure(sc->visited, (size_t)slots_t * vis_words2));  // the bitset-free traversal needs no scratch
+    if (!pt.r_in_smem || !pr.r_in_smem) ISL_TRY(ensure(sc->r_global, (size_t)std::max(slots_t, slots_r) * ef));
+    ISL_TRY(ensure(sc->ties_global, (size_t)std::max(slots_t, slots_r) * ef));
+    ISL_TRY(ensure(sc->aux_f32, (size_t)nq * lut_floats + 2));
+    ISL_TRY(ensure(sc->q_stage, nq * idx->ld));
+    ISL_TRY(ensure(sc->out_ids, nq * k));
+    ISL_TRY(ensure(sc->out_dist, nq * k));
+    ISL_TRY(ensure(sc->out_count, nq));
+    ISL_TRY(ensure(sc->out_stats, nq));
+    ISL_TRY(ensure(sc->rc_surv, nq * (size_t)ef));
+    ISL_TRY(ensure(sc->rc_surv_cnt, nq));
+    cudaStream_t st = sc->stream;
+    if (idx->ld != idx->dim) ISL_CUDA_TRY(cudaMemsetAsync(sc->q_stage.p, 0, nq * idx->ld * 4, st));
+    ISL_CUDA_TRY(cudaMemcpy2DAsync(sc->q_stage.p, (size_t)idx->ld * 4, queries, (size_t)idx->dim * 4,
                                    (size_t)idx->dim * 4, nq, cudaMemcpyHostToDevice, st));
-    ISL_CUDA_TRY(cudaMemsetAsync(idx->counters.p, 0, 4 * sizeof(unsigned int), st));
-    ISL_CUDA_TRY(cudaEventRecord(idx->ev0, st));
+    ISL_CUDA_TRY(cudaMemsetAsync(sc->counters.p, 0, 4 * sizeof(unsigned int), st));
+    ISL_CUDA_TRY(cudaEventRecord(sc->ev0, st));
     const bool fused_lut = pt.lut_smem_floats != 0;  // tables built per query inside the traversal kernel
-    if (!fused_lut) ISL_TRY(launch_pq_tables(pq->dev(), idx->q_stage.p, idx->ld, nq, idx->aux_f32.p, idx->sms, st));
+    if (!fused_lut) ISL_TRY(launch_pq_tables(pq->dev(), sc->q_stage.p, idx->ld, nq, sc->aux_f32.p, idx->sms, st));
     SearchArgs a{};
     a.vectors = idx->vectors.p;
     a.sqnorms = idx->sqnorms.p;
@@ -100,26 +103,27 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
     a.d = idx->dim;
     a.n = (uint32_t)idx->n;
     search_args_set_graph(idx, &a);
-    a.queries = idx->q_stage.p;
+    a.queries = sc->q_stage.p;
     a.q_ld = idx->ld;
     a.nq = (uint32_t)nq;
     a.entry = (uint32_t)idx->entry;
     a.k = k;
     a.ef = ef;
     a.metric = idx->cfg.metric;
-    a.visited = idx->visited.p;
+    a.visited = sc->visited.p;
     a.vis_words = vis_words2;
-    a.r_global = idx->r_global.p;
+    a.r_global = sc->r_global.p;
+    a.ties_global = sc->ties_global.p;
     a.u_cap = u_cap_t;
-    a.out_ids = idx->out_ids.p;
-    a.out_dist = idx->out_dist.p;
-    a.out_count = idx->out_count.p;
-    a.stats = stats ? idx->out_stats.p : nullptr;
+    a.out_ids = sc->out_ids.p;
+    a.out_dist = sc->out_dist.p;
+    a.out_count = sc->out_count.p;
+    a.stats = stats ? sc->out_stats.p : nullptr;
     // without statistics the traversal runs without the visited bitset (same survivors; search_core.cuh)
     a.novis = novis ? 1u : 0u;
-    a.work_counter = idx->counters.p;
-    a.error_flag = idx->counters.p + 1;
-    a.luts = fused_lut ? nullptr : idx->aux_f32.p;
+    a.work_counter = sc->counters.p;
+    a.error_flag = sc->counters.p + 1;
+    a.luts = fused_lut ? nullptr : sc->aux_f32.p;
     a.pq_codebooks = pq->d_codebooks.p;
     a.pq_dsub = pq->dsub;
     a.pq_ld_sub = pq->ld_sub;
@@ -130,22 +134,21 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
     a.lut_smem_floats = pt.lut_smem_floats;
     a.phase = 1;
     a.rerank_limit = idx->rerank_limit ? std::max(idx->rerank_limit, k) : 0u;
-    a.surv_ids = idx->rc_surv.p;
-    a.surv_cnt = idx->rc_surv_cnt.p;
+    a.surv_ids = sc->rc_surv.p;
+    a.surv_cnt = sc->rc_surv_cnt.p;
     ISL_TRY(launch_search(pt, a, st));
-    ISL_CUDA_TRY(cudaMemsetAsync(idx->counters.p, 0, sizeof(unsigned int), st));  // work counter of the second launch
+    ISL_CUDA_TRY(cudaMemsetAsync(sc->counters.p, 0, sizeof(unsigned int), st));  // work counter of the second launch
     a.u_cap = u_cap_r;
     a.lut_smem_floats = 0;
     a.phase = 2;
     ISL_TRY(launch_search(pr, a, st));
-    ISL_CUDA_TRY(cudaEventRecord(idx->ev1, st));
-    idx->last_launches = 3;
-    ISL_CUDA_TRY(cudaMemcpyAsync(out_ids, idx->out_ids.p, nq * k * 8, cudaMemcpyDeviceToHost, st));
-    ISL_CUDA_TRY(cudaMemcpyAsync(out_dist, idx->out_dist.p, nq * k * 4, cudaMemcpyDeviceToHost, st));
-    if (out_count) ISL_CUDA_TRY(cudaMemcpyAsync(out_count, idx->out_count.p, nq * 4, cudaMemcpyDeviceToHost, st));
+    ISL_CUDA_TRY(cudaEventRecord(sc->ev1, st));
+    ISL_CUDA_TRY(cudaMemcpyAsync(out_ids, sc->out_ids.p, nq * k * 8, cudaMemcpyDeviceToHost, st));
+    ISL_CUDA_TRY(cudaMemcpyAsync(out_dist, sc->out_dist.p, nq * k * 4, cudaMemcpyDeviceToHost, st));
+    if (out_count) ISL_CUDA_TRY(cudaMemcpyAsync(out_count, sc->out_count.p, nq * 4, cudaMemcpyDeviceToHost, st));
     if (stats)
-      ISL_CUDA_TRY(cudaMemcpyAsync(stats, idx->out_stats.p, nq * sizeof(isl_search_stats), cudaMemcpyDeviceToHost, st));
-    return search_finish(idx);
+      ISL_CUDA_TRY(cudaMemcpyAsync(stats, sc->out_stats.p, nq * sizeof(isl_search_stats), cudaMemcpyDeviceToHost, st));
+    return search_finish(idx, sc.get(), 3);
   }
 
   // |AQ| <= max_degree / a at all times (it gains at most max_degree entries per expansion and
@@ -165,24 +168,25 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
   }
   const uint32_t vis_words = round_up((uint32_t)((idx->n + 31) / 32), 4);
   const uint32_t slots = (uint32_t)std::min<uint64_t>(plan.grid, nq);
-  ISL_TRY(ensure(idx->visited, (size_t)slots * vis_words));
-  if (!plan.r_in_smem) ISL_TRY(ensure(idx->r_global, (size_t)slots * ef));
-  if (mode == 1 && !plan.aq_smem_entries) ISL_TRY(ensure(idx->aux_u2, (size_t)slots * aq_cap));
-  ISL_TRY(ensure(idx->aux_f32, (size_t)nq * lut_floats + 2));
-  ISL_TRY(ensure(idx->q_stage, nq * idx->ld));
-  ISL_TRY(ensure(idx->out_ids, nq * k));
-  ISL_TRY(ensure(idx->out_dist, nq * k));
-  ISL_TRY(ensure(idx->out_count, nq));
-  if (stats) ISL_TRY(ensure(idx->out_stats, nq));
-  cudaStream_t st = idx->stream;
-  if (idx->ld != idx->dim) ISL_CUDA_TRY(cudaMemsetAsync(idx->q_stage.p, 0, nq * idx->ld * 4, st));
-  ISL_CUDA_TRY(cudaMemcpy2DAsync(idx->q_stage.p, (size_t)idx->ld * 4, queries, (size_t)idx->dim * 4,
+  ISL_TRY(ensure(sc->visited, (size_t)slots * vis_words));
+  if (!plan.r_in_smem) ISL_TRY(ensure(sc->r_global, (size_t)slots * ef));
+  ISL_TRY(ensure(sc->ties_global, (size_t)slots * ef));
+  if (mode == 1 && !plan.aq_smem_entries) ISL_TRY(ensure(sc->aux_u2, (size_t)slots * aq_cap));
+  ISL_TRY(ensure(sc->aux_f32, (size_t)nq * lut_floats + 2));
+  ISL_TRY(ensure(sc->q_stage, nq * idx->ld));
+  ISL_TRY(ensure(sc->out_ids, nq * k));
+  ISL_TRY(ensure(sc->out_dist, nq * k));
+  ISL_TRY(ensure(sc->out_count, nq));
+  if (stats) ISL_TRY(ensure(sc->out_stats, nq));
+  cudaStream_t st = sc->stream;
+  if (idx->ld != idx->dim) ISL_CUDA_TRY(cudaMemsetAsync(sc->q_stage.p, 0, nq * idx->ld * 4, st));
+  ISL_CUDA_TRY(cudaMemcpy2DAsync(sc->q_stage.p, (size_t)idx->ld * 4, queries, (size_t)idx->dim * 4,
                                  (size_t)idx->dim * 4, nq, cudaMemcpyHostToDevice, st));
-  ISL_CUDA_TRY(cudaMemsetAsync(idx->counters.p, 0, 4 * sizeof(unsigned int), st));
+  ISL_CUDA_TRY(cudaMemsetAsync(sc->counters.p, 0, 4 * sizeof(unsigned int), st));
 
-  ISL_CUDA_TRY(cudaEventRecord(idx->ev0, st));
+  ISL_CUDA_TRY(cudaEventRecord(sc->ev0, st));
   // K3: per-query tables LUT[j][c] = Σ (q - c)^2 (pq.rs:307-338), then the traversal.
-  ISL_TRY(launch_pq_tables(pq->dev(), idx->q_stage.p, idx->ld, nq, idx->aux_f32.p, idx->sms, st));
+  ISL_TRY(launch_pq_tables(pq->dev(), sc->q_stage.p, idx->ld, nq, sc->aux_f32.p, idx->sms, st));
 
   SearchArgs a{};
   a.vectors = idx->vectors.p;
@@ -191,7 +195,7 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
   a.d = idx->dim;
   a.n = (uint32_t)idx->n;
   search_args_set_graph(idx, &a);
-  a.queries = idx->q_stage.p;
+  a.queries = sc->q_stage.p;
   a.q_ld = idx->ld;
   a.nq = (uint32_t)nq;
   a.entry = (uint32_t)idx->entry;
@@ -200,41 +204,41 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
   a.metric = idx->cfg.metric;
   a.prune_ratio = 0.0f;  // the PQ queue replaces the frontier pruning strategies (leann.rs:351-353)
   a.strategy = 0;
-  a.visited = idx->visited.p;
+  a.visited = sc->visited.p;
   a.vis_words = vis_words;
-  a.r_global = idx->r_global.p;
+  a.r_global = sc->r_global.p;
+  a.ties_global = sc->ties_global.p;
   a.u_cap = u_cap;
-  a.out_ids = idx->out_ids.p;
-  a.out_dist = idx->out_dist.p;
-  a.out_count = idx->out_count.p;
-  a.stats = stats ? idx->out_stats.p : nullptr;
-  a.work_counter = idx->counters.p;
-  a.error_flag = idx->counters.p + 1;
-  a.luts = idx->aux_f32.p;
+  a.out_ids = sc->out_ids.p;
+  a.out_dist = sc->out_dist.p;
+  a.out_count = sc->out_count.p;
+  a.stats = stats ? sc->out_stats.p : nullptr;
+  a.work_counter = sc->counters.p;
+  a.error_flag = sc->counters.p + 1;
+  a.luts = sc->aux_f32.p;
   a.codes8 = idx->codes8.p;
   a.codes16 = idx->codes8.p ? nullptr : idx->codes16.p;
   a.pq_m = m;
   a.pq_ksub = pq->ksub;
   a.rerank_ratio = rerank_ratio;
   a.aq_cap = aq_cap;
-  a.aq_global = idx->aux_u2.p;
+  a.aq_global = sc->aux_u2.p;
   a.lut_smem_floats = plan.lut_smem_floats;
   a.aq_smem_entries = plan.aq_smem_entries;
   ISL_TRY(launch_search(plan, a, st));
-  ISL_CUDA_TRY(cudaEventRecord(idx->ev1, st));
-  idx->last_launches = 2;
+  ISL_CUDA_TRY(cudaEventRecord(sc->ev1, st));
 
-  ISL_CUDA_TRY(cudaMemcpyAsync(out_ids, idx->out_ids.p, nq * k * 8, cudaMemcpyDeviceToHost, st));
-  ISL_CUDA_TRY(cudaMemcpyAsync(out_dist, idx->out_dist.p, nq * k * 4, cudaMemcpyDeviceToHost, st));
-  if (out_count) ISL_CUDA_TRY(cudaMemcpyAsync(out_count, idx->out_count.p, nq * 4, cudaMemcpyDeviceToHost, st));
+  ISL_CUDA_TRY(cudaMemcpyAsync(out_ids, sc->out_ids.p, nq * k * 8, cudaMemcpyDeviceToHost, st));
+  ISL_CUDA_TRY(cudaMemcpyAsync(out_dist, sc->out_dist.p, nq * k * 4, cudaMemcpyDeviceToHost, st));
+  if (out_count) ISL_CUDA_TRY(cudaMemcpyAsync(out_count, sc->out_count.p, nq * 4, cudaMemcpyDeviceToHost, st));
   if (stats)
-    ISL_CUDA_TRY(cudaMemcpyAsync(stats, idx->out_stats.p, nq * sizeof(isl_search_stats), cudaMemcpyDeviceToHost, st));
-  return search_finish(idx);
+    ISL_CUDA_TRY(cudaMemcpyAsync(stats, sc->out_stats.p, nq * sizeof(isl_search_stats), cudaMemcpyDeviceToHost, st));
+  return search_finish(idx, sc.get(), 2);
 }
 
 isl_status isl_index_set_rerank_limit(isl_index* idx, uint32_t limit) {
   if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
-  std::lock_guard<std::mutex> lock(idx->mu);
+  std::unique_lock<std::shared_mutex> lock(idx->mu);
   idx->rerank_limit = limit;
   return ISL_OK;
 }

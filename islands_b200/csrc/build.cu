@@ -341,6 +341,7 @@ isl_status build_graph(isl_index* idx, const uint64_t* levels_or_null, uint64_t 
   const uint32_t slots = (uint32_t)std::min<uint64_t>(plan.grid, max_round);
   ISL_TRY(ensure(idx->visited, (size_t)slots * vis_words));
   if (!plan.r_in_smem) ISL_TRY(ensure(idx->r_global, (size_t)slots * efc));
+  ISL_TRY(ensure(idx->ties_global, (size_t)slots * efc));
 
   ISL_CUDA_TRY(cudaMemsetAsync(idx->counters.p, 0, 4 * sizeof(unsigned int), st));
   int64_t entry = ISL_NO_ENTRY;
@@ -375,6 +376,7 @@ isl_status build_graph(isl_index* idx, const uint64_t* levels_or_null, uint64_t 
       a.visited = idx->visited.p;
       a.vis_words = vis_words;
       a.r_global = idx->r_global.p;
+      a.ties_global = idx->ties_global.p;
       a.u_cap = u_cap;
       a.out_ids = nullptr;
       a.out_ids32 = cand_ids.p;
@@ -452,7 +454,11 @@ isl_status build_graph(isl_index* idx, const uint64_t* levels_or_null, uint64_t 
   idx->entry = entry;
   idx->max_level = max_level;
   ISL_TRY(index_make_padded_adjacency(idx));
-  if (hflags[1]) return fail(ISL_INVALID_ARGUMENT, "build: too many exact distance ties during construction search");
+  // construction scratch is not needed by searches (they lease their own)
+  idx->visited.release();
+  idx->r_global.release();
+  idx->ties_global.release();
+  if (hflags[1]) return fail(ISL_CUDA_ERROR, "build: internal invariant violated (tie list overflow)");
   return ISL_OK;
 }
 

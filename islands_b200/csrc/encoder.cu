@@ -653,7 +653,7 @@ template <int BN>
 isl_status launch_gemm_bn(const CUtensorMap& ma, const CUtensorMap& mb, const gemm::Params& p, int sms, cudaStream_t st) {
   auto kern = gemm::gemm_bf16_tcgen05_kernel<BN>;
   const size_t smem = gemm::smem_bytes<BN>();
-  ISL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ISL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 /* the maximum, always: never lowered under a concurrent launch */));
   const int tiles = ((p.M + gemm::BM - 1) / gemm::BM) * (p.N / BN);
   kern<<<std::min(tiles, sms), gemm::THREADS, smem, st>>>(ma, mb, p);
   count_launch();
@@ -664,7 +664,7 @@ isl_status launch_gemm_bn(const CUtensorMap& ma, const CUtensorMap& mb, const ge
 isl_status launch_gemm_pair(const CUtensorMap& ma, const CUtensorMap& mb, const gemm::Params& p, int sms, cudaStream_t st) {
   auto kern = gemm::gemm_bf16_tcgen05_pair_kernel;
   const size_t smem = gemm::pair_smem_bytes();
-  ISL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ISL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 /* the maximum, always: never lowered under a concurrent launch */));
   const int tiles = ((p.M + 2 * gemm::BM - 1) / (2 * gemm::BM)) * (p.N / gemm::PAIR_BN);
   const int clusters = std::max(1, std::min(tiles, sms / 2));
   kern<<<2 * clusters, gemm::THREADS, smem, st>>>(ma, mb, p);  // __cluster_dims__(2,1,1)
@@ -745,7 +745,7 @@ isl_status forward_device(isl_encoder* e, const int32_t* d_tokens, const int32_t
                                              T, (uint32_t)S, H, l.V, eps, e->x.p);
   count_launch();
   const size_t att_smem = ((size_t)S * kAttKStride + (size_t)S * 64 + 4 * kAttRows * 64 + 4 * (size_t)S * kAttRows) * sizeof(float);
-  ISL_CUDA_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+  ISL_CUDA_TRY(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 /* the maximum, always: never lowered under a concurrent launch */));
   for (uint32_t layer = 0; layer < l.L; ++layer) {
     const float* lp = P + l.layers + (size_t)layer * l.per_layer;
     const __nv_bfloat16* gw = e->wbf16.p + (size_t)layer * l.g_per_layer;

@@ -53,7 +53,7 @@ struct isl_hnsw {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   mutable float last_kernel_ms = 0.0f;
   mutable isl::DevBuf<uint32_t> visited, q_cur, out_count;
-  mutable isl::DevBuf<uint2> r_global;
+  mutable isl::DevBuf<uint2> r_global, ties_global;
   mutable isl::DevBuf<unsigned int> counters;
   mutable isl::DevBuf<float> q_stage, out_dist;
   mutable isl::DevBuf<uint64_t> out_ids;
@@ -329,7 +329,7 @@ isl_status grow(DevBuf<T>& b, size_t keep, size_t want, cudaStream_t st) {
 
 template <int ACC>
 isl_status launch_greedy_one(const GreedyArgs& a, uint32_t grid, size_t smem, cudaStream_t st) {
-  ISL_CUDA_TRY(cudaFuncSetAttribute(hnsw_greedy_kernel<ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ISL_CUDA_TRY(cudaFuncSetAttribute(hnsw_greedy_kernel<ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 /* the maximum, always: never lowered under a concurrent launch */));
   hnsw_greedy_kernel<ACC><<<grid, 32, smem, st>>>(a);
   count_launch();
   ISL_CUDA_TRY(cudaGetLastError());
@@ -437,7 +437,7 @@ isl_status edge_dist_one(const isl_hnsw* h, const uint32_t* owner, uint32_t rows
   if (rows == 0) return ISL_OK;
   const uint32_t u_cap = std::max<uint32_t>(32, round_up(stride, 32));
   const size_t smem = ((size_t)StageGeom<64>::STAGE_FLOATS + h->ld + u_cap) * 4 + 16;
-  ISL_CUDA_TRY(cudaFuncSetAttribute(hnsw_edge_dist_kernel<ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ISL_CUDA_TRY(cudaFuncSetAttribute(hnsw_edge_dist_kernel<ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 /* the maximum, always: never lowered under a concurrent launch */));
   hnsw_edge_dist_kernel<ACC><<<std::min<uint32_t>(rows, (uint32_t)h->sms * 16), 32, smem, st>>>(
       h->vectors.p, h->sqnorms.p, h->ld, h->dim, h->cfg.metric, owner, rows, adj, deg, stride, out, u_cap);
   count_launch();
@@ -616,6 +616,7 @@ isl_status hnsw_insert_impl(isl_hnsw* h, const float* vectors, bool on_device, u
   const uint32_t slots = (uint32_t)std::min<uint64_t>(plan.grid, max_round);
   ISL_TRY(ensure(h->visited, (size_t)slots * vis_words));
   if (!plan.r_in_smem) ISL_TRY(ensure(h->r_global, (size_t)slots * efc));
+  ISL_TRY(ensure(h->ties_global, (size_t)slots * efc));
   ISL_CUDA_TRY(cudaMemsetAsync(h->counters.p, 0, 4 * sizeof(unsigned int), st));
 
   const uint32_t sel_warps = 4;
@@ -652,6 +653,7 @@ isl_status hnsw_insert_impl(isl_hnsw* h, const float* vectors, bool on_device, u
       a.visited = h->visited.p;
       a.vis_words = vis_words;
       a.r_global = h->r_global.p;
+      a.ties_global = h->ties_global.p;
       a.u_cap = u_cap;
       a.out_ids = nullptr;
       a.out_ids32 = cand_ids.p;
@@ -692,7 +694,7 @@ isl_status hnsw_insert_impl(isl_hnsw* h, const float* vectors, bool on_device, u
   unsigned int hflags[4] = {0, 0, 0, 0};
   ISL_CUDA_TRY(cudaMemcpyAsync(hflags, h->counters.p, sizeof(hflags), cudaMemcpyDeviceToHost, st));
   ISL_CUDA_TRY(cudaStreamSynchronize(st));
-  if (hflags[1]) return fail(ISL_INVALID_ARGUMENT, "hnsw insert: too many exact distance ties during construction search");
+  if (hflags[1]) return fail(ISL_CUDA_ERROR, "hnsw insert: internal invariant violated (tie list overflow)");
   return ISL_OK;
 }
 
@@ -707,6 +709,7 @@ isl_status hnsw_search_device(const isl_hnsw* h, const float* d_queries, uint32_
   const uint32_t slots = (uint32_t)std::min<uint64_t>(plan.grid, nq);
   ISL_TRY(ensure(h->visited, (size_t)slots * vis_words));
   if (!plan.r_in_smem) ISL_TRY(ensure(h->r_global, (size_t)slots * ef));
+  ISL_TRY(ensure(h->ties_global, (size_t)slots * ef));
   ISL_TRY(ensure(h->q_cur, nq));
   ISL_CUDA_TRY(cudaMemsetAsync(h->counters.p, 0, 4 * sizeof(unsigned int), st));
   ISL_CUDA_TRY(cudaEventRecord(h->ev0, st));
@@ -731,6 +734,7 @@ isl_status hnsw_search_device(const isl_hnsw* h, const float* d_queries, uint32_
   a.visited = h->visited.p;
   a.vis_words = vis_words;
   a.r_global = h->r_global.p;
+  a.ties_global = h->ties_global.p;
   a.u_cap = u_cap;
   a.out_ids = d_ids;
   a.out_dist = d_dist;

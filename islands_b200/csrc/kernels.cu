@@ -74,7 +74,7 @@ isl_status launch_rows_fold(int32_t metric, int squared, const float* q, const f
   auto kern = rows_fold_kernel<ACC, MODE>;
   const size_t smem = (size_t)kStages * StageGeom<kCH>::STAGE_FLOATS * 4 + (size_t)ld * 4 + 32 * 4;
   if (smem > 227 * 1024) return fail(ISL_INVALID_ARGUMENT, "distance: dimension too large for shared memory");
-  ISL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ISL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 /* the maximum, always: never lowered under a concurrent launch */));
   int per_sm = 0;
   ISL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
   if (per_sm < 1) return fail(ISL_CUDA_ERROR, "distance kernel does not fit on an SM");
@@ -306,7 +306,7 @@ isl_status launch_merge_topk(const uint64_t* d_ids, const float* d_dist, uint32_
   const uint32_t warps = 4;
   const size_t smem = (size_t)warps * parts * k * 12;
   if (smem > 200 * 1024) return fail(ISL_INVALID_ARGUMENT, "merge: parts*k too large for shared memory");
-  ISL_CUDA_TRY(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ISL_CUDA_TRY(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 /* the maximum, always: never lowered under a concurrent launch */));
   const uint32_t grid = (uint32_t)((nq + warps - 1) / warps);
   merge_topk_kernel<<<grid, warps * 32, smem, st>>>(d_ids, d_dist, parts, nq, k, d_out_ids, d_out_dist,
                                                      d_out_count);

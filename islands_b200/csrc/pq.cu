@@ -191,7 +191,7 @@ isl_status launch_pq_encode(const PqDev& pq, const float* d_vectors, uint32_t ld
       std::max<uint32_t>(1, std::min<uint32_t>(pq.ksub, (96u * 1024u) / (pq.ld_sub * 4u)));
   const size_t smem = ((size_t)cb_off + (size_t)tile_c * pq.ld_sub) * 4;
   if (smem > 227 * 1024) return fail(ISL_PQ_ERROR, "pq encode: sub-vector dimension too large for shared memory");
-  ISL_CUDA_TRY(cudaFuncSetAttribute(pq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ISL_CUDA_TRY(cudaFuncSetAttribute(pq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 /* the maximum, always: never lowered under a concurrent launch */));
   const uint64_t tiles = (n + 127) / 128;
   const uint32_t gx = (uint32_t)std::min<uint64_t>(tiles, std::max<uint64_t>(1, (uint64_t)(2 * sms) / pq.m + 1));
   dim3 grid(gx, pq.m);
@@ -214,7 +214,7 @@ isl_status launch_pq_tables(const PqDev& pq, const float* d_queries, uint32_t q_
                             float* d_tables, int sms, cudaStream_t st) {
   if (nq == 0) return ISL_OK;
   const size_t smem = (size_t)kStages * StageGeom<kCH>::STAGE_FLOATS * 4 + (size_t)pq.ld_sub * 4 + 32 * 4;
-  ISL_CUDA_TRY(cudaFuncSetAttribute(pq_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ISL_CUDA_TRY(cudaFuncSetAttribute(pq_tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 /* the maximum, always: never lowered under a concurrent launch */));
   int per_sm = 0;
   ISL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pq_tables_kernel, 32, smem));
   if (per_sm < 1) return fail(ISL_CUDA_ERROR, "pq tables kernel does not fit on an SM");

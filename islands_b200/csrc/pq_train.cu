@@ -159,7 +159,7 @@ extern "C" isl_status isl_pq_train(isl_pq* pq, const float* vectors, uint64_t n,
   const uint32_t dsub = pq->dsub, ld_sub = pq->ld_sub;
   const uint32_t k = (uint32_t)std::min<uint64_t>(pq->cfg.num_centroids, n);  // pq.rs:374
   const uint32_t iters = (uint32_t)pq->cfg.training_iterations;
-  uint64_t seed = pq->cfg.seed >= 0 ? (uint64_t)pq->cfg.seed : ((uint64_t)std::random_device{}() << 32) ^ std::random_device{}();
+  uint64_t seed = pq->cfg.has_seed ? pq->cfg.seed : ((uint64_t)std::random_device{}() << 32) ^ std::random_device{}();
   StdRng rng(seed);  // StdRng::seed_from_u64 (pq.rs:190-193), one generator across subspaces, in order (:196-214)
 
   DevBuf<float> dv, mind, cent;

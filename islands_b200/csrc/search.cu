@@ -2,6 +2,7 @@
 #include "search.h"
 
 #include <algorithm>
+#include <mutex>
 
 #include "search_core.cuh"
 
@@ -21,6 +22,22 @@ constexpr int kStages = ISL_STAGES;
 constexpr uint32_t kEfSmemMax = 2048;
 constexpr uint32_t kLutSmemMaxFloats = 8192;  // 32 KB of PQ tables per query in shared memory
 constexpr uint32_t kAqSmemMaxEntries = 2048;  // 16 KB approximate queue in shared memory
+constexpr int kMaxDynSmem = 227 * 1024;
+
+// The dynamic shared-memory limit is a process-wide attribute of a kernel instantiation: it is raised ONCE to the
+// hardware maximum (call_once per instantiation and device), never to the size of one call — two threads planning
+// different searches must not lower it under each other's launches.
+template <class K>
+isl_status opt_in_smem(K kern, std::once_flag* flags, cudaError_t* results) {
+  int dev = 0;
+  ISL_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(ISL_CUDA_ERROR, "search: device ordinal out of range");
+  std::call_once(flags[dev], [&] {
+    results[dev] = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+  });
+  if (results[dev] != cudaSuccess) return cuda_fail(results[dev], "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+  return ISL_OK;
+}
 
 template <int ACC, bool R_SMEM, int TWO>
 isl_status plan_one(uint32_t ld, uint32_t ef, uint32_t u_cap, int sms, SearchPlan* plan) {
@@ -29,7 +46,9 @@ isl_status plan_one(uint32_t ld, uint32_t ef, uint32_t u_cap, int sms, SearchPla
                                                       plan->aq_smem_entries);
   if (smem > 227 * 1024)
     return fail(ISL_INVALID_ARGUMENT, "search: dimension / ef need more than 227 KB of shared memory per warp");
-  ISL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static std::once_flag once[64];
+  static cudaError_t once_result[64];
+  ISL_TRY(opt_in_smem(kern, once, once_result));
   int per_sm = 0;
   ISL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
   if (per_sm < 1) return fail(ISL_CUDA_ERROR, "search: kernel does not fit on an SM");
@@ -55,7 +74,9 @@ isl_status plan_lean(uint32_t ef, uint32_t u_cap, uint32_t pq_m, int sms, Search
                       (R_SMEM ? search_smem_bytes_idc() : 0);
   if (smem > 227 * 1024) return fail(ISL_INVALID_ARGUMENT, "search: ef needs more than 227 KB of shared memory per warp");
   plan->novis_ok = R_SMEM && plan->lut_smem_floats != 0 && (pq_m == 16 || pq_m == 32);  // and n < kIdcMaxNodes (checked by the caller)
-  ISL_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static std::once_flag once[64];
+  static cudaError_t once_result[64];
+  ISL_TRY(opt_in_smem(kern, once, once_result));
   int per_sm = 0;
   ISL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
   if (per_sm < 1) return fail(ISL_CUDA_ERROR, "search: kernel does not fit on an SM");

@@ -12,6 +12,18 @@ constexpr uint32_t kIdcBits = 9;
 constexpr uint32_t kIdcEntries = 1u << kIdcBits;
 constexpr uint32_t kIdcMaxNodes = (0xffffu << kIdcBits);  // tag 0xffff is the empty marker
 
+// Where a sharded search writes its per-query result records: 16 bytes {dist bits, 0, global id lo, hi}, laid out
+// [nq][k].  `packed` is a local buffer (NCCL exchange); `peer[0 .. n_peer)` are this rank's slots in the gather
+// buffers of all ranks of the node (its own included), mapped with CUDA IPC: the search kernel stores each
+// finished query's records straight into them over NVLink, so the exchange overlaps the search query by query.
+constexpr int kMaxPeers = 16;
+struct ShardOut {
+  uint4* packed = nullptr;
+  uint64_t id_base = 0;     // added to every local id (node-range shards: first global id of the shard)
+  uint4* peer[kMaxPeers] = {};
+  uint32_t n_peer = 0;
+};
+
 struct SearchArgs {
   // resident index
   const float* vectors;     // [n][ld] f32, rows 16B aligned, zero padded to ld
@@ -39,15 +51,17 @@ struct SearchArgs {
   uint32_t* visited;        // [slots][vis_words]
   uint32_t vis_words;
   uint2* r_global;          // [slots][ef] when R does not fit shared memory
+  uint2* ties_global;       // [slots][ef] spill area of the tie list (search_core.cuh)
   uint32_t u_cap;           // capacity of the unvisited list (>= max degree, multiple of 32)
   // outputs
   uint64_t* out_ids;        // [nq][k] (may be null)
   uint32_t* out_ids32;      // [nq][k] (may be null; build path)
   float* out_dist;          // [nq][k]
   uint32_t* out_count;      // [nq]
+  ShardOut shard;           // shard-exchange records (api_shard.cu)
   isl_search_stats* stats;  // [nq] or null
   unsigned int* work_counter;
-  unsigned int* error_flag; // set to 1 when the tie list overflows
+  unsigned int* error_flag; // internal invariant guard (never set: the tie list cannot overflow its kTieCap + ef entries)
   // two-level search: PQ ADC traversal + exact rerank (docs/leann-specification.md:223-269)
   const float* luts;        // [nq][pq_m*pq_ksub] squared-L2 tables (pq.rs:307-338); null => built per query in shared memory
   const float* pq_codebooks; // [pq_m][pq_ksub][pq_ld_sub] (only read when luts is null)

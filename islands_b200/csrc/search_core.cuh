@@ -132,6 +132,18 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
   uint32_t* vis = a.visited + (size_t)slot * a.vis_words;
   RView<R_SMEM> R{R_SMEM ? r_smem : a.r_global + (size_t)slot * a.ef};
   const uint32_t ef = a.ef;
+  // ties: the first kTieCap entries live in shared memory, the rest spill to a per-slot global array of ef
+  // entries.  Live ties all carry the current worst distance and were in R together when the first of them
+  // was evicted, so there are never more than ef - 1 of them: kTieCap + ef entries cannot overflow once the
+  // stale ones are dropped (the reference's unbounded heap, leann.rs:924-928, needs no more either).
+  uint2* ties_spill = a.ties_global + (size_t)slot * ef;
+  auto tie_ld = [&](uint32_t i) -> uint2 { return i < kTieCap ? ties[i] : __ldcg(ties_spill + (i - kTieCap)); };
+  auto tie_st = [&](uint32_t i, uint2 v) {
+    if (i < kTieCap)
+      ties[i] = v;
+    else
+      __stcg(ties_spill + (i - kTieCap), v);
+  };
   // register-resident R: entry i = row i / 32 of lane i % 32, as a pair of unsigned words whose
   // lexicographic order IS the (dist, id) order: kd = bits of the table distance (a square root: never
   // negative, so the bit patterns order like the values; every NaN is folded onto 0x7fc00000 = greatest,
@@ -183,6 +195,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     const float na = (!LEAN && a.metric == ISL_METRIC_COSINE) ? smem_sqnorm_fold(q_smem, a.d) : 0.0f;
 
     uint32_t r_len = 0, first_unexp = 0, n_ties = 0, aq_len = 0;
+    uint32_t tie_next = kTieCap;  // the tie list is compacted (stale entries dropped) when it reaches this length
     float wst_d = 0.0f;    // register R: the entry at index ef - 1 (the worst one once R is full), kept beside the rows
     uint32_t wst_kd = 0xffffffffu, wst_ki = 0xffffffffu;
     if constexpr (RREG) {
@@ -370,23 +383,24 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         // distance in R (leann.rs:924-928 uses a strict `>`).
         const float wd = RREG ? wst_d : __uint_as_float(R.ld(ef - 1).x), edist = __uint_as_float(evicted.x);
         if (!of_lt(wd, edist)) {
-          if (n_ties == kTieCap) {  // drop stale ties first
+          if (n_ties == tie_next) {  // drop stale ties first (lane 0 moves the survivors down, in order)
             uint32_t kept = 0;
             for (uint32_t i = 0; i < n_ties; ++i) {
-              const uint2 t = ties[i];
+              const uint2 t = tie_ld(i);
               if (!of_lt(wd, __uint_as_float(t.x))) {
                 __syncwarp();
-                if (lane == 0) ties[kept] = t;
+                if (lane == 0) tie_st(kept, t);
                 kept++;
               }
             }
             n_ties = kept;
+            tie_next = min(kTieCap + ef, max(kTieCap, 2 * kept));
             __syncwarp();
           }
-          if (n_ties == kTieCap) {
+          if (n_ties >= kTieCap + ef) {  // cannot happen (see above); kept as a loud guard
             if (lane == 0) atomicExch(a.error_flag, 1u);
           } else {
-            if (lane == 0) ties[n_ties] = evicted;
+            if (lane == 0) tie_st(n_ties, evicted);
             n_ties++;
             __syncwarp();
           }
@@ -503,19 +517,31 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         }
         first_unexp = nxt;
       } else {
-        // smallest live tie, if any
+        // smallest live tie, if any: lanes stride the list, then a key-ordered butterfly picks the minimum
         const float wd = RREG ? wst_d : __uint_as_float(R.ld(r_len - 1).x);
-        int best = -1;
-        for (uint32_t i = 0; i < n_ties; ++i) {
-          const uint2 t = ties[i];
+        uint32_t bpos = 0xffffffffu;
+        uint2 bt = make_uint2(0, 0);
+        for (uint32_t i = lane; i < n_ties; i += 32) {
+          const uint2 t = tie_ld(i);
           if (r_len >= ef && of_lt(wd, __uint_as_float(t.x))) continue;  // stale
-          if (best < 0 || key_lt(__uint_as_float(t.x), t.y, __uint_as_float(ties[best].x), ties[best].y))
-            best = (int)i;
+          if (bpos == 0xffffffffu || key_lt(__uint_as_float(t.x), t.y, __uint_as_float(bt.x), bt.y)) {
+            bt = t;
+            bpos = i;
+          }
         }
-        if (best < 0) break;
-        cur = ties[best].y;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          const uint32_t ox = __shfl_xor_sync(FULL, bt.x, off), oy = __shfl_xor_sync(FULL, bt.y, off);
+          const uint32_t op = __shfl_xor_sync(FULL, bpos, off);
+          if (op != 0xffffffffu && (bpos == 0xffffffffu || key_lt(__uint_as_float(ox), oy, __uint_as_float(bt.x), bt.y))) {
+            bt = make_uint2(ox, oy);
+            bpos = op;
+          }
+        }
+        if (bpos == 0xffffffffu) break;
+        cur = bt.y;
         __syncwarp();
-        if (lane == 0) ties[best] = ties[n_ties - 1];
+        if (lane == 0) tie_st(bpos, tie_ld(n_ties - 1));
         n_ties--;
         __syncwarp();
       }
@@ -776,6 +802,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       r_len = 0;
       first_unexp = 0;
       n_ties = 0;
+      tie_next = kTieCap;
       n_dist = total;
       n_rerank = total;
       score_and_admit(total);
@@ -794,7 +821,13 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       const size_t o = (size_t)qi * a.k + i;
       if (a.out_ids) a.out_ids[o] = i < cnt ? (uint64_t)id : ISL_INVALID_ID;
       if (a.out_ids32) a.out_ids32[o] = id;
-      a.out_dist[o] = dist;
+      if (a.out_dist) a.out_dist[o] = dist;
+      if (a.shard.packed || a.shard.n_peer) {  // shard exchange record: {dist bits, 0, global id lo, global id hi}
+        const uint64_t gid = i < cnt ? (uint64_t)id + a.shard.id_base : ISL_INVALID_ID;
+        const uint4 rec = make_uint4(__float_as_uint(dist), 0u, (uint32_t)gid, (uint32_t)(gid >> 32));
+        if (a.shard.packed) a.shard.packed[o] = rec;
+        for (uint32_t r = 0; r < a.shard.n_peer; ++r) a.shard.peer[r][o] = rec;  // peer stores over NVLink
+      }
     }
     if (lane == 0) {
       if (a.out_count) a.out_count[qi] = cnt;

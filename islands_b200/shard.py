@@ -1,16 +1,24 @@
 """Index sharding across the GPUs of one box: node-range shards (or one island per GPU, the
-reference's `graphs: HashMap<String, StoredIndex>` loop, src/indexer/service.rs:777-797), every
-rank searches its shard with the same queries, ONE all-gather of the per-shard (dist, id) lists
-over NCCL, then a per-query merge by (dist, id) (src/core/search.rs:211-237).
+reference's `graphs: HashMap<String, StoredIndex>` loop, src/indexer/service.rs:777-797).  Every
+rank searches its shard with the same queries, the per-shard top-k lists travel as packed 16-byte
+(dist, global id) records in ONE exchange, then a per-query merge by (dist, id)
+(src/core/search.rs:211-237).
 
-torch.distributed is plumbing here (process group, all-gather); search and merge are the CUDA
-kernels behind the C ABI.  The collective also runs on gloo/CPU tensors, which is how the host
-logic is tested without GPUs.
+The product path is entirely behind the C ABI (`isl_index_search_sharded*`, csrc/api_shard.cu):
+search kernel, NCCL all-gather (or peer stores over NVLink) and merge kernel on one stream inside
+the library.  torch.distributed is only the host channel that hands NCCL's unique id to the ranks.
+The helpers below (ranges, id mapping, record packing, the one-all-gather exchange) are the host
+logic; they also run on gloo/CPU tensors, which is how they are tested without GPUs.
 """
+import numpy as np
 import torch
 import torch.distributed as dist
 
-from .core import merge_topk_dev
+from .core import ShardComm
+
+# isl_shard_record (include/islands_b200.h): {f32 dist, u32 reserved, u64 id}
+RECORD_DTYPE = np.dtype([("dist", "<f4"), ("reserved", "<u4"), ("id", "<u8")])
+INVALID_ID = np.uint64(0xFFFFFFFFFFFFFFFF)
 
 
 def shard_range(n, rank, world):
@@ -23,37 +31,51 @@ def local_to_global(ids, base):
     return torch.where(ids >= 0, ids + base, ids)
 
 
-def gather_topk(ids, dist_, group=None):
-    """All-gather of per-shard lists: ids [nq,k] int64, dist [nq,k] f32 -> ([W,nq,k], [W,nq,k])."""
+def pack_records(ids, dist_, base=0):
+    """ids [nq,k] u64 (ISL_INVALID_ID padded), dist [nq,k] f32 -> isl_shard_record array [nq,k] with global ids."""
+    ids = np.asarray(ids, np.uint64)
+    rec = np.zeros(ids.shape, RECORD_DTYPE)
+    rec["dist"] = np.asarray(dist_, np.float32)
+    rec["id"] = np.where(ids == INVALID_ID, INVALID_ID, ids + np.uint64(base))
+    return rec
+
+
+def gather_records(rec, group=None):
+    """ONE all-gather of the packed records: [nq,k] -> [world,nq,k] (the library does the same with
+    ncclAllGather on bytes; here it runs over whatever backend the group has, gloo included)."""
     world = dist.get_world_size(group)
-    nq = ids.shape[0]
-    # the output is the concatenation along dim 0 (the form gloo and NCCL both accept)
-    g_ids = torch.empty((world * nq,) + tuple(ids.shape[1:]), dtype=ids.dtype, device=ids.device)
-    g_dst = torch.empty((world * nq,) + tuple(dist_.shape[1:]), dtype=dist_.dtype, device=dist_.device)
-    dist.all_gather_into_tensor(g_ids, ids.contiguous(), group=group)
-    dist.all_gather_into_tensor(g_dst, dist_.contiguous(), group=group)
-    return g_ids.view((world,) + tuple(ids.shape)), g_dst.view((world,) + tuple(dist_.shape))
+    mine = torch.from_numpy(rec.view(np.uint8).reshape(-1).copy())
+    out = torch.empty((world * mine.numel(),), dtype=torch.uint8)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    return out.numpy().view(RECORD_DTYPE).reshape((world,) + rec.shape)
+
+
+def make_shard_comm(group=None, device=None):
+    """Creates the library's communicator for the ranks of `group`: rank 0 draws NCCL's unique id, the host
+    channel (torch.distributed, any backend) broadcasts its 128 bytes, every rank joins."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [ShardComm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group, device=device)
+    return ShardComm(rank, world, box[0])
 
 
 class ShardedLeannIndex:
-    """One shard of a node-range-sharded LeannIndex living on this rank's GPU."""
+    """One shard of a node-range- or island-sharded LeannIndex living on this rank's GPU."""
 
-    def __init__(self, index, base, n_total, group=None):
+    def __init__(self, index, base, n_total, comm):
         self.index = index
         self.base = int(base)
         self.n_total = int(n_total)
-        self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.comm = comm
 
-    def search_batch_dev(self, q, k, ef, ids, dst, cnt, out_ids, out_dst, stats=None):
-        """q [nq,d] f32 on this GPU; ids/dst/cnt: local scratch; out_ids/out_dst [nq,k]: merged result
-        (identical on every rank).  Returns the tensor holding the final ids."""
+    def search_batch_dev(self, q, k, ef, out_ids, out_dst, out_cnt=None):
+        """q [nq,d] f32 on this GPU (the same on every rank); out_ids [nq,k] int64 / out_dst [nq,k] f32 receive
+        the merged result, identical on every rank.  One library call: search -> exchange -> merge."""
         nq, d = q.shape
-        self.index.search_batch_dev(q.data_ptr(), nq, d, k, ef, ids.data_ptr(), dst.data_ptr(), cnt.data_ptr(),
-                                    stats.data_ptr() if stats is not None else None)
-        if self.world == 1:
-            return ids, dst
-        g_ids, g_dst = gather_topk(local_to_global(ids, self.base), dst, self.group)
-        torch.cuda.current_stream().synchronize()  # the merge runs on the library's stream
-        merge_topk_dev(g_ids.data_ptr(), g_dst.data_ptr(), self.world, nq, k, out_ids.data_ptr(), out_dst.data_ptr())
+        self.index.search_sharded_dev(self.comm, self.base, q.data_ptr(), nq, d, k, ef, out_ids.data_ptr(), out_dst.data_ptr(),
+                                      out_cnt.data_ptr() if out_cnt is not None else None)
         return out_ids, out_dst
+
+    def search_batch(self, queries, k, ef):
+        """Host buffers in, host results out (numpy)."""
+        return self.index.search_sharded(self.comm, self.base, queries, k, ef)

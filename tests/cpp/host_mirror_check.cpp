@@ -66,6 +66,7 @@ int main(int argc, char** argv) {
       pc.num_centroids = 16;
       pc.training_iterations = 3;
       pc.seed = 1;
+      pc.has_seed = 1;
       ProductQuantizer pq(d, pc);
       pq.train(v);
       idx.attach_pq(pq.handle(), pq.encode_batch(v));

@@ -1,6 +1,7 @@
 """N>1 host logic on CPU (gloo, world_size 2): node-range sharding, local->global ids, the single
-all-gather exchange, and the merge semantics (checked with the oracle's merge; the product's merge
-is a CUDA kernel and is covered by the GPU tests)."""
+all-gather of packed 16-byte isl_shard_record entries (the format the library exchanges with NCCL),
+and the merge semantics (checked with the oracle's merge; the product's merge is a CUDA kernel and
+is covered by the GPU tests: tests/test_sharded_search.py)."""
 import os
 import socket
 
@@ -28,7 +29,7 @@ def _worker(rank, world, port, n, d, nq, k, ef, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from islands_b200 import LeannConfig
-    from islands_b200.shard import gather_topk, local_to_global, shard_range
+    from islands_b200.shard import gather_records, pack_records, shard_range
     from oracle import pyoracle as orc
 
     rng = np.random.RandomState(0)
@@ -40,15 +41,18 @@ def _worker(rank, world, port, n, d, nq, k, ef, out_dir):
     off, nbrs, entry, _ = orc.leann_build(cfg._s, x[lo:hi], levels, batch=8)
     # per-shard search (the oracle stands in for the GPU kernel on this CPU-only box)
     ids, dst, _ = orc.leann_search(cfg._s, x[lo:hi], off, nbrs, entry, q, k, ef)
-    t_ids = local_to_global(torch.from_numpy(ids.astype(np.int64)), lo)
-    g_ids, g_dst = gather_topk(t_ids, torch.from_numpy(dst))
-    assert g_ids.shape == (world, nq, k)
+    rec = pack_records(ids, dst, base=lo)
+    g = gather_records(rec)  # ONE all-gather of the packed records
+    assert g.shape == (world, nq, k) and g.dtype.itemsize == 16
+    g_ids, g_dst = np.ascontiguousarray(g["id"]), np.ascontiguousarray(g["dist"])
     # every rank holds the same gathered lists, laid out [parts][nq][k]
-    chk = g_ids.clone()
-    dist.broadcast(chk, src=0)
-    assert torch.equal(chk, g_ids)
-    assert torch.equal(g_ids[rank], t_ids)
-    m_ids, m_dst, m_cnt = orc.merge_topk(g_ids.numpy().astype(np.uint64), g_dst.numpy(), k)
+    chk = torch.from_numpy(g_ids.astype(np.int64))
+    ref = chk.clone()
+    dist.broadcast(ref, src=0)
+    assert torch.equal(chk, ref)
+    assert np.array_equal(g[rank], rec)
+    assert np.array_equal(g_ids[rank][ids != np.uint64(0xFFFFFFFFFFFFFFFF)], (ids + np.uint64(lo))[ids != np.uint64(0xFFFFFFFFFFFFFFFF)])
+    m_ids, m_dst, m_cnt = orc.merge_topk(g_ids, g_dst, k)
     np.save(os.path.join(out_dir, f"merged_{rank}.npy"), m_ids)
     if rank == 0:
         np.save(os.path.join(out_dir, "dist.npy"), m_dst)
