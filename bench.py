@@ -8,12 +8,15 @@ index (islands_b200 C ABI).  See DESIGN.md "measurement" for every definition us
   python bench.py --impl reference ...                     # the reference's CPU algorithm (oracle port)
   torchrun --nproc-per-node N bench.py --gpus N ...        # one island (n x d shard) per GPU, weak scaling
 
-N > 1 (DESIGN.md "multi-GPU"): every rank owns one island of `n` vectors (its own seed) — the total
-index is N*n vectors — and `value` counts queries routed to their island (the reference's
-`index_names` filter, src/indexer/service.rs:768-771): independent units, no data-path collective,
-weak scaling.  The same run also measures the all-islands search (every query on every shard, one
-NCCL all-gather of the (dist,id) lists + per-query merge, service.rs:777-801) and reports it under
-"all_islands".
+N > 1 (DESIGN.md "multi-GPU"): every rank owns one island / node-range shard of `n` vectors (its own
+seed) — the total index is N*n vectors — and `value` counts queries routed to their island (the
+reference's `index_names` filter, src/indexer/service.rs:768-771): independent units, no data-path
+collective, weak scaling.  The same run also measures the sharded search (every query on every shard,
+ONE exchange of packed (dist,id) records + per-query merge, service.rs:777-801) through the library's
+own entry point isl_index_search_sharded_dev — with ncclAllGather and with the peer-store exchange —
+and reports it under "sharded" with a search / exchange / merge breakdown.
+
+The run exits non-zero when a parity check made along the way fails (GPU ids vs the CPU port).
 """
 import argparse
 import json
@@ -55,6 +58,7 @@ def parse_args():
     ap.add_argument("--pq-ksub", type=int, default=128, help="centroids per subquantizer of the ADC secondary "
                     "(128: a 16 KB table per query in shared memory keeps twice the warps resident of 256)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline sample")
+    ap.add_argument("--build-sample", type=int, default=20000, help="nodes of the construction cpu_baseline sample (oracle build + GPU build of the same prefix, graphs compared)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)  # the timing rules ask for at least three untimed steps; the JSON line reports what was done
     a.steps = max(a.steps, 1)
@@ -202,6 +206,16 @@ def ground_truth_scores(torch, x, q, k, chunk=1024):
     return torch.cat(vs), torch.cat(is_)
 
 
+def workload_config(a, n, d, nq, parts, ef):
+    """`config` of the JSON line — the same dict in both arms (ours and --impl reference)."""
+    return {
+        "workload": f"{n} x {d} f32 {a.dataset} per GPU, LEANN graph m=30 m0=60 efC=128 hub 2% (built on the GPU in setup), "
+                    f"batched {nq} queries per GPU per step, top-10, exact traversal (leann.rs:868-988), cosine",
+        "ef": ef, "islands": parts, "island_nodes": n, "total_nodes": parts * n,
+        "l2": "inputs larger than L2 (vector table %.2f GB vs 126 MB)" % (n * d * 4 / 1e9),
+    }
+
+
 def calibrate_ef(recall_for, target, fixed=0):
     """Smallest ef with recall >= target: coarse ladder, then the last interval in steps of 8."""
     curve = {}
@@ -247,6 +261,7 @@ def main():
     from islands_b200.shard import ShardedLeannIndex
 
     lib = _ffi.load()
+    failures = []  # parity checks made along the way; any entry makes the run exit non-zero
     cfg = LeannConfig()  # paper_default: m=30, m0=60, efC=128, cosine, hub-preserving pruning 2%
     n, d, nq = a.n, a.d, a.nq
     island = rank if use_dist else 0  # one island of n vectors per GPU (weak scaling)
@@ -312,8 +327,11 @@ def main():
             "impl": "reference", "metric": metric_name, "value": qps, "unit": "queries/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{n} x {d} f32 {a.dataset}, LEANN graph m=30 m0=60 efC=128, nq={nq} (sampled {per_step}), top-10, exact traversal, cosine",
-                       "ef": ef, "recall_at_10": rec, "kind": "oracle port of src/core/leann.rs:868-988 (Rust reference cannot be built here)"},
+            "config": workload_config(a, n, d, nq, a.gpus, ef),
+            "details": {"kind": "oracle port of src/core/leann.rs:868-988 (the Rust reference cannot be built here: no cargo / rustc)",
+                        "queries_per_step": per_step, "recall_at_10": rec,
+                        "n_gpus_note": "queries are routed to their island, so the CPU's cost per query does not depend on the number of islands: "
+                                       "rank 0 searches its own island's graph with all host threads"},
             "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -387,15 +405,10 @@ def main():
         "metric": metric_name, "value": qps, "unit": "queries/s", "n_gpus": parts,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {
-            "workload": f"{n} x {d} f32 {a.dataset} per GPU, LEANN graph m=30 m0=60 efC=128 hub 2% (built on GPU in setup, {build_s:.1f}s), "
-                        f"batched {nq} queries per GPU per step, top-10, exact traversal (leann.rs:868-988), cosine",
-            "ef": ef, "recall_at_10": recall, "recall_curve": {str(k): round(v, 4) for k, v in curve.items()},
-            "islands": parts, "island_nodes": n, "total_nodes": parts * n,
-            "routing": "queries routed to their island (index_names filter, service.rs:768-771); no data-path collective" if use_dist else "single island",
-            "l2": "inputs larger than L2 (vector table %.2f GB vs 126 MB)" % (n * d * 4 / 1e9),
-            "per_query": per_query,
-        },
+        "config": workload_config(a, n, d, nq, parts, ef),
+        "details": {"recall_at_10": recall, "recall_curve": {str(k): round(v, 4) for k, v in curve.items()}, "build_s": build_s,
+                    "routing": "queries routed to their island (index_names filter, service.rs:768-771); no data-path collective" if use_dist else "single island",
+                    "per_query": per_query},
         "batch_latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)), "calls": len(lat),
                              "what": f"isl_index_search, host buffers, {nq} queries per call (this rank)"},
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": parts * nq * d * 4,
@@ -407,8 +420,10 @@ def main():
                      "frac_of_nominal_8TBs": achieved / 8000.0},
     }
 
-    # ---- N > 1: the all-islands search (every query on every shard + all-gather + merge) ---------------
+    # ---- N > 1: the sharded search (every query on every shard + ONE exchange + merge), library entry point ---------
     if use_dist:
+        from islands_b200.shard import make_shard_comm
+
         _, q_all = make_data(torch, a.dataset, 1, nq, d, dev, seed=1, qseed=43)  # the same batch on every rank
         sc, li = ground_truth_scores(torch, x, q_all[:n_gt], K_TOP)
         g_sc = torch.empty((world * n_gt, K_TOP), dtype=sc.dtype, device=dev)
@@ -418,20 +433,60 @@ def main():
         g_sc = g_sc.view(world, n_gt, K_TOP).permute(1, 0, 2).reshape(n_gt, -1)
         g_id = g_id.view(world, n_gt, K_TOP).permute(1, 0, 2).reshape(n_gt, -1)
         gt_all = g_id.gather(1, g_sc.topk(K_TOP, dim=1).indices)
-        sharded = ShardedLeannIndex(index, rank * n, world * n)
+        comm = make_shard_comm(device=dev)  # NCCL communicator inside the library; torch only carries the unique id
+        sharded = ShardedLeannIndex(index, rank * n, world * n, comm)
         m_ids = torch.empty((nq, K_TOP), dtype=torch.int64, device=dev)
         m_dst = torch.empty((nq, K_TOP), dtype=torch.float32, device=dev)
 
         def step_all(e):
-            return sharded.search_batch_dev(q_all, K_TOP, e, ids, dst, cnt, m_ids, m_dst)[0]
+            return sharded.search_batch_dev(q_all, K_TOP, e, m_ids, m_dst, cnt)[0]
 
         ef_all, curve_all = calibrate_ef(lambda e: recall_at_k(torch, step_all(e)[:n_gt], gt_all), RECALL_TARGET)
-        dt_all = timed(lambda: step_all(ef_all), a.steps, a.warmup)
-        line["all_islands"] = {
-            "qps": nq * a.steps / dt_all, "ms_per_step": dt_all / a.steps * 1e3, "ef": ef_all,
-            "recall_at_10": curve_all[ef_all], "total_nodes": world * n,
-            "merge": "one NCCL all-gather of the per-shard (dist,id) lists + per-query (dist,id) merge kernel",
-            "note": "every query searches all islands (service.rs:777-801): queries are replicated, so QPS does not grow with N; the index does"}
+        ef_all = int(all_max(ef_all))
+
+        def measure_engine():
+            for _ in range(a.warmup):
+                step_all(ef_all)
+            parts_ms = []
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(a.steps):
+                step_all(ef_all)
+                parts_ms.append(comm.last_timing())
+            barrier()
+            dt_ = all_max(time.perf_counter() - t0)
+            pm = np.asarray(parts_ms, np.float64).mean(axis=0)
+            # max over ranks of every stage (the slowest rank sets the step; a fast rank's "exchange" is mostly waiting)
+            return dt_, [all_max(pm[0]), all_max(pm[1]), all_max(pm[2])], [float(v) for v in pm]
+
+        dt_nccl, st_nccl, mine_nccl = measure_engine()
+        ids_nccl = m_ids.clone()
+        comm.enable_peer_exchange(nq * K_TOP)
+        dt_peer, st_peer, mine_peer = measure_engine()
+        same_engines = bool(torch.equal(ids_nccl, m_ids))
+        rec_all = recall_at_k(torch, m_ids[:n_gt], gt_all)
+        best = min(dt_nccl, dt_peer)
+        line["sharded"] = {
+            "what": "every query searches all shards (service.rs:777-801): isl_index_search_sharded_dev = search kernel -> ONE exchange of packed "
+                    "16-byte (dist, global id) records -> merge kernel, one stream, no host synchronisation in between",
+            "total_nodes": world * n, "shards": world, "ef": ef_all, "recall_at_10": rec_all,
+            "recall_curve": {str(k): round(v, 4) for k, v in curve_all.items()},
+            "qps": nq * a.steps / best, "ms_per_step": best / a.steps * 1e3,
+            "nccl_allgather": {"qps": nq * a.steps / dt_nccl, "ms_per_step": dt_nccl / a.steps * 1e3,
+                               "stage_ms_max_over_ranks": {"search": st_nccl[0], "exchange": st_nccl[1], "merge": st_nccl[2]},
+                               "stage_ms_rank0": {"search": mine_nccl[0], "exchange": mine_nccl[1], "merge": mine_nccl[2]}},
+            "peer_stores": {"qps": nq * a.steps / dt_peer, "ms_per_step": dt_peer / a.steps * 1e3,
+                            "stage_ms_max_over_ranks": {"search": st_peer[0], "exchange": st_peer[1], "merge": st_peer[2]},
+                            "stage_ms_rank0": {"search": mine_peer[0], "exchange": mine_peer[1], "merge": mine_peer[2]},
+                            "how": "the search kernel stores each finished query's records into every rank's gather buffer over NVLink (CUDA IPC "
+                                   "mappings); a flag handshake replaces the collective"},
+            "engines_agree": same_engines,
+            "exchange_bytes_per_rank_per_step": nq * K_TOP * 16,
+            "limiter": "the search kernel" if st_nccl[0] > 5 * (st_nccl[1] + st_nccl[2]) else "see stage_ms",
+            "note": "queries are replicated, so QPS does not grow with N; the index does (capacity scaling); exchange_ms on a rank includes waiting for the slowest rank"}
+        if not same_engines:
+            failures.append("sharded search: NCCL and peer-store exchange returned different ids")
+        comm.free()
 
     # ---- cpu_baseline + secondary workloads (single GPU run only) ------------------------------------
     if not use_dist:
@@ -444,10 +499,44 @@ def main():
         same = bool(np.array_equal(o_ids.astype(np.int64), index.search_batch(qn[:m], K_TOP, ef)[0].astype(np.int64)))
         # the reference's own execution model is one thread (search_batch is a sequential map, search.rs:179-181)
         cq1, m1, _ = cpu_port_qps(orc, cfg, xh, g.node_offsets, g.neighbors, g.entry_point, qn, ef, 1, min(a.cpu_seconds, 5.0))
+        if not same:
+            failures.append(f"headline workload: GPU ids differ from the CPU port on the first {m} queries")
         line["cpu_baseline"] = {"value": cq, "unit": "queries/s", "cores": threads, "kind": "port",
                                 "sample": f"first {m} of {nq} queries, same graph / ef, all host threads; ids equal to GPU: {same}",
                                 "single_thread": {"value": cq1, "unit": "queries/s", "sample": f"first {m1} queries, one thread "
                                                   "(the reference's execution model, search.rs:179-181)"}}
+
+        # BASELINE configs[3]: graph construction 1M x 768, efConstruction=128, hub-preserving pruning, on the GPU
+        bs = index.last_build_stats()
+        b_build = bs["n_dist"] * 4 * d + bs["n_edge"] * 4 + bs["n_hop"] * 16 + n * 4 * d + 2 * bs["edges"] * 4
+        ns = min(n, a.build_sample)
+        xs = xh[:ns]
+        lv = orc.draw_levels(7, ns, cfg.ml, cfg.max_layers)
+        t0 = time.perf_counter()
+        o_off, o_nb, o_entry, _ = orc.leann_build(cfg._s, xs, lv, batch=a.build_batch, threads=threads)
+        cpu_build_s = time.perf_counter() - t0
+        gs = LeannIndex(cfg)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        gs.build(xs, ns, levels=lv, batch=a.build_batch)
+        gpu_sample_s = time.perf_counter() - t0
+        gg = gs.graph
+        same_graph = bool(np.array_equal(gg.node_offsets, o_off) and np.array_equal(gg.neighbors, o_nb) and gg.entry_point == o_entry)
+        if not same_graph:
+            failures.append(f"construction: the GPU graph of the first {ns} nodes differs from the CPU port's")
+        gs.free()
+        line["build"] = {
+            "what": f"BASELINE configs[3]: LeannIndex::build {n} x {d}, efConstruction=128, hub-preserving pruning 2%, rounds of {a.build_batch} inserts (leann.rs:560-833)",
+            "seconds": build_s, "inserts_per_s": n / build_s, "gpu_rounds_ms": bs["rounds_ms"], "search_kernel_ms": bs["search_ms"],
+            "search_share_of_rounds": bs["search_ms"] / max(bs["rounds_ms"], 1e-9), "rounds": bs["rounds"], "edges": bs["edges"],
+            "per_insert": {"n_dist": bs["n_dist"] / n, "n_edge": bs["n_edge"] / n, "n_hop": bs["n_hop"] / n},
+            "roofline": {"bound": "hbm", "kernel": "leann_search_kernel (efConstruction searches of every round)", "algorithmic_bytes": b_build,
+                         "achieved": (b_build - 2 * bs["edges"] * 4) / max(bs["search_ms"], 1e-9) / 1e6, "peak": peak, "unit": "GB/s",
+                         "frac": (b_build - 2 * bs["edges"] * 4) / max(bs["search_ms"], 1e-9) / 1e6 / peak,
+                         "whole_build_gbps": b_build / max(bs["rounds_ms"], 1e-9) / 1e6, "peak_source": peak_src},
+            "cpu_baseline": {"value": ns / cpu_build_s, "unit": "inserts/s", "cores": threads, "kind": "port",
+                             "sample": f"oracle port of leann.rs:560-833 (same round model) on the first {ns} vectors, all host threads; "
+                                       f"GPU on the same sample: {ns / gpu_sample_s:.0f} inserts/s (host buffers), graphs bit-identical: {same_graph}"}}
 
         # secondary: BASELINE configs[1] names "PQ ADC traversal + exact rerank" — a mode the reference
         # specifies (docs/leann-specification.md:223-269) but does not implement; measured beside the headline.
@@ -464,23 +553,34 @@ def main():
 
             ef_adc, curve_adc = calibrate_ef(adc_recall, RECALL_TARGET)
             ids_bitset, dist_bitset, _, st = index.search_adc_rerank_batch(qn, K_TOP, ef_adc, stats=True)
-            ms_l, t0 = [], time.perf_counter()
-            for _ in range(3):  # timed without statistics: the traversal then runs without the visited bitset
+            for _ in range(max(3, a.warmup)):  # timed without statistics: the traversal then runs without the visited bitset
                 ids_free, dist_free, _ = index.search_adc_rerank_batch(qn, K_TOP, ef_adc)
+            ms_l = []
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(a.steps):
+                index.search_adc_rerank_batch(qn, K_TOP, ef_adc)  # isl_index_search_adc_rerank: host buffers in, host results out
+            torch.cuda.synchronize()
+            wall = (time.perf_counter() - t0) / a.steps
+            for _ in range(3):  # kernel time (CUDA events inside the library), read outside the wall-clock loop
+                index.search_adc_rerank_batch(qn, K_TOP, ef_adc)
                 ms_l.append(index.last_search_timing()[0])
             same_adc = bool(np.array_equal(ids_bitset, ids_free) and np.array_equal(dist_bitset.view(np.uint32), dist_free.view(np.uint32)))
-            wall = (time.perf_counter() - t0) / 3
+            if not same_adc:
+                failures.append("ADC traversal: bitset-free results differ from the visited-bitset results")
             ms = float(np.mean(ms_l))
             b = int(st.n_adc.sum()) * pq_m + int(st.n_edge.sum()) * 4 + int(st.n_hop.sum()) * 16 + int(st.n_rerank.sum()) * 4 * d \
                 + nq * (4 * d + 12 * K_TOP + pq_m * pq_ksub * 4)
-            line["adc_rerank"] = {"pq_m": pq_m, "pq_ksub": pq_ksub, "ef": ef_adc, "recall_at_10": curve_adc[ef_adc], "kernel_qps": nq / ms * 1e3,
-                                  "kernel_ms": ms, "e2e_qps_host_buffers": nq / wall, "algorithmic_gbps": b / ms / 1e6, "frac": b / ms / 1e6 / peak,
+            line["adc_rerank"] = {"what": "BASELINE configs[1]: 1M x 768 CSR graph, batched 10k queries, PQ ADC traversal + exact rerank, 1 B200",
+                                  "pq_m": pq_m, "pq_ksub": pq_ksub, "ef": ef_adc, "recall_at_10": curve_adc[ef_adc], "kernel_qps": nq / ms * 1e3,
+                                  "kernel_ms": ms, "e2e_qps_host_buffers": nq / wall, "e2e_steps": a.steps,
+                                  "algorithmic_gbps": b / ms / 1e6, "frac": b / ms / 1e6 / peak,
                                   "n_adc": float(st.n_adc.mean()), "n_rerank": float(st.n_rerank.mean()),
                                   "bitset_free_results_equal_bitset_results": same_adc,
-                                  "bound": "instruction latency of the per-hop chain at 12 resident warps per SM (16 KB table + 1 KB id cache per query); "
-                                           "the byte roofline is not the limiter: every access is one 32-byte sector, and with the per-query visited "
-                                           "bitset the kernel sat at the measured random-sector ceiling of HBM (profiles/r01_sector_ceiling.txt)",
-                                  "note": "parity unpinned: no reference implementation of this mode exists (leann.rs:54-56)"}
+                                  "bound": "instruction latency of the per-hop chain; the byte roofline is not the limiter: every access is one 32-byte "
+                                           "sector (profiles/r01_sector_ceiling.txt: 33-35 G random sectors/s is the HBM ceiling the bitset version sat on)",
+                                  "note": "parity unpinned: no reference implementation of this mode exists (leann.rs:54-56); oracle <-> GPU bit-exact"}
+            line["roofline"]["also"] = {"adc_rerank_kernel_qps": nq / ms * 1e3, "adc_rerank_recall_at_10": curve_adc[ef_adc], "adc_rerank_frac_of_hbm_bytes": b / ms / 1e6 / peak}
         del xh
 
         # secondary: the recompute encoder (BASELINE configs[4]: random-init 110M bf16 encoder, the only
@@ -557,6 +657,8 @@ def main():
             t0 = time.perf_counter()
             oids, _, _ = orc.leann_search(cfg._s, xc, gg.node_offsets, gg.neighbors, gg.entry_point, qc, K_TOP, 64, threads=threads)
             ldt = time.perf_counter() - t0
+            if not bool(np.array_equal(oids.astype(np.int64), gids)):
+                failures.append("leann_config0 (100k x 768 uniform): GPU ids differ from the CPU port")
             line["leann_config0"] = {"workload": "LeannIndex 100k x 768 uniform, m=30 m0=60 efC=128, ef=64, top-10 (BASELINE configs[0])",
                                      "build_s": lbuild, "search_ms_per_10k": float(np.mean(lms)), "qps": nq / float(np.mean(lms)) * 1e3,
                                      "recall_at_10": lrec, "cpu_port_qps": 1000 / ldt, "cpu_threads": threads,
@@ -584,10 +686,15 @@ def main():
             line["uniform_reference_distribution"] = {
                 "note": "U[-1,1)^768 (benches/hnsw_benchmarks.rs:9-14): distances concentrate, recall>=0.95 needs a near-exhaustive traversal for any graph index",
                 "by_ef": uni}
+    if failures:
+        line["parity_failures"] = failures
     if rank == 0:
         print(json.dumps(line))
     if use_dist:
         dist.destroy_process_group()
+    if failures:
+        print("PARITY FAILURE: " + "; ".join(failures), file=sys.stderr)
+        sys.exit(1)
 
 
 if __name__ == "__main__":

@@ -122,6 +122,19 @@ typedef struct isl_search_stats {
   uint64_t n_rerank;
 } isl_search_stats;
 
+/* What LeannIndex::build did (construction roofline): the traversal counters summed over the efConstruction
+ * searches of all inserts (same meaning as isl_search_stats), the edges of the finished graph, and CUDA-event
+ * times: search_ms = the search launches only, rounds_ms = search + selection + sort + reverse-edge kernels. */
+typedef struct isl_build_stats {
+  uint64_t n_hop;
+  uint64_t n_edge;
+  uint64_t n_dist;
+  uint64_t edges;
+  uint64_t rounds;
+  float search_ms;
+  float rounds_ms;
+} isl_build_stats;
+
 /* Shape of the recompute encoder: BERT (the reference's CandleEmbedder loads a BERT-family model,
  * src/core/embedding/candle_provider.rs:230-300).  head dimension is fixed at 64. */
 typedef struct isl_encoder_config {
@@ -207,6 +220,8 @@ isl_status isl_index_build(const isl_leann_config* cfg, uint32_t dim, uint64_t n
 isl_status isl_index_build_dev(const isl_leann_config* cfg, uint32_t dim, uint64_t n,
                                const float* d_vectors, const uint64_t* levels_or_null,
                                uint64_t seed, uint32_t batch, isl_index** out);
+/* Counters and timings of the construction behind this handle (zeros when the graph was adopted, not built). */
+isl_status isl_index_last_build_stats(const isl_index* idx, isl_build_stats* out);
 void isl_index_free(isl_index* idx);
 uint64_t isl_index_len(const isl_index* idx);            /* LeannIndex::len */
 uint32_t isl_index_dimension(const isl_index* idx);      /* LeannIndex::dimension (0 = None) */

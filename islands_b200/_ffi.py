@@ -82,6 +82,20 @@ class EncoderConfigStruct(C.Structure):
     ]
 
 
+class BuildStatsStruct(C.Structure):
+    """isl_build_stats."""
+
+    _fields_ = [
+        ("n_hop", C.c_uint64),
+        ("n_edge", C.c_uint64),
+        ("n_dist", C.c_uint64),
+        ("edges", C.c_uint64),
+        ("rounds", C.c_uint64),
+        ("search_ms", C.c_float),
+        ("rounds_ms", C.c_float),
+    ]
+
+
 class SearchStatsStruct(C.Structure):
     _fields_ = [
         ("n_hop", C.c_uint64),
@@ -204,6 +218,7 @@ SIGNATURES = {
     "isl_merge_topk": (C.c_int, [u64p, f32p, C.c_uint32, C.c_uint64, C.c_uint32, u64p, f32p, u32p]),
     "isl_merge_topk_dev": (C.c_int, [_VP, _VP, C.c_uint32, C.c_uint64, C.c_uint32, _VP, _VP, _VP]),
     "isl_set_caller_stream": (C.c_int, [_VP]),
+    "isl_index_last_build_stats": (C.c_int, [_VP, C.POINTER(BuildStatsStruct)]),
     "isl_index_set_neighbors": (C.c_int, [_VP, C.c_uint64, u64p, C.c_uint64]),
     "isl_shard_unique_id": (C.c_int, [_VP, C.c_uint64]),
     "isl_shard_init": (C.c_int, [C.c_int, C.c_int, _VP, _VPP]),

@@ -540,6 +540,12 @@ class LeannIndex:
                                                 C.c_void_p(d_count_ptr) if d_count_ptr else None,
                                                 C.c_void_p(d_stats_ptr) if d_stats_ptr else None))
 
+    def last_build_stats(self):
+        """isl_index_last_build_stats: traversal counters / edges / CUDA-event times of the construction."""
+        st = _ffi.BuildStatsStruct()
+        _check(_ffi.load().isl_index_last_build_stats(self._h, C.byref(st)))
+        return {f: getattr(st, f) for f, _ in st._fields_}
+
     def set_neighbors(self, node_id, new_neighbors):
         """graph.set_neighbors (leann.rs:256-293) on the resident graph (device copy refreshed)."""
         nb = np.ascontiguousarray(new_neighbors, np.uint64)

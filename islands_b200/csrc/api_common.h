@@ -123,6 +123,7 @@ struct isl_index {
   isl::DevBuf<float> hub_sq;          // [hub_count]
   isl::DevBuf<uint32_t> hub_row;      // [n] row in hub_emb or 0xffffffff
   mutable uint64_t last_hub_hits = 0;
+  isl_build_stats build_stats{};  // counters of the construction that produced this graph (zero for adopted graphs)
   uint32_t rerank_limit = 0;  // ADC traversal + rerank / recompute: survivors that get an exact distance (0 = all ef)
   uint32_t tok_len = 0;
   mutable uint64_t last_recomputed = 0;

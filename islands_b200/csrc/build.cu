@@ -292,6 +292,26 @@ inline uint64_t draw_level(uint64_t seed, uint64_t i, double ml, uint64_t max_la
   return std::min<uint64_t>(level, max_layers - 1);
 }
 
+// Adds the per-query traversal counters of one round to the running totals [n_hop, n_edge, n_dist].
+__global__ void accumulate_stats_kernel(const isl_search_stats* __restrict__ st, uint32_t count, unsigned long long* __restrict__ tot) {
+  unsigned long long h = 0, e = 0, d = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    h += st[i].n_hop;
+    e += st[i].n_edge;
+    d += st[i].n_dist;
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    h += __shfl_xor_sync(0xffffffffu, h, off);
+    e += __shfl_xor_sync(0xffffffffu, e, off);
+    d += __shfl_xor_sync(0xffffffffu, d, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(tot + 0, h);
+    atomicAdd(tot + 1, e);
+    atomicAdd(tot + 2, d);
+  }
+}
+
 }  // namespace
 
 // Builds the graph for idx (vectors / sqnorms already resident) and fills host + device CSR.
@@ -312,6 +332,8 @@ isl_status build_graph(isl_index* idx, const uint64_t* levels_or_null, uint64_t 
   DevBuf<float> adj_dist, cand_dist, edge_vals, edge_vals2;
   DevBuf<uint64_t> edge_keys, edge_keys2;
   DevBuf<uint8_t> sorted_flag, cub_tmp;
+  DevBuf<isl_search_stats> round_stats;   // traversal counters of the round's searches (construction roofline)
+  DevBuf<unsigned long long> stat_totals; // [n_hop, n_edge, n_dist] over the whole construction
   ISL_CUDA_TRY(adj.alloc(n * m0));
   ISL_CUDA_TRY(adj_dist.alloc(n * m0));
   ISL_CUDA_TRY(deg.alloc(n));
@@ -328,6 +350,17 @@ isl_status build_graph(isl_index* idx, const uint64_t* levels_or_null, uint64_t 
   ISL_CUDA_TRY(edge_vals2.alloc(max_round * m0));
   ISL_CUDA_TRY(heads.alloc(max_round * m0));
   ISL_CUDA_TRY(n_heads.alloc(1));
+  ISL_CUDA_TRY(round_stats.alloc(max_round));
+  ISL_CUDA_TRY(stat_totals.alloc(4));
+  ISL_CUDA_TRY(cudaMemsetAsync(stat_totals.p, 0, stat_totals.bytes(), st));
+  std::vector<cudaEvent_t> round_ev;  // start / stop of every round's search launch
+  struct EvGuard {
+    std::vector<cudaEvent_t>* v;
+    ~EvGuard() {
+      for (cudaEvent_t e : *v) cudaEventDestroy(e);
+    }
+  } ev_guard{&round_ev};
+  ISL_CUDA_TRY(cudaEventRecord(idx->ev0, st));
   size_t cub_bytes = 0;
   ISL_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, edge_keys.p, edge_keys2.p, edge_vals.p,
                                                edge_vals2.p, (int)(max_round * m0), 0, 64, st));
@@ -382,10 +415,19 @@ isl_status build_graph(isl_index* idx, const uint64_t* levels_or_null, uint64_t 
       a.out_ids32 = cand_ids.p;
       a.out_dist = cand_dist.p;
       a.out_count = cand_cnt.p;
-      a.stats = nullptr;
+      a.stats = round_stats.p;
       a.work_counter = idx->counters.p;
       a.error_flag = idx->counters.p + 1;
+      cudaEvent_t e0, e1;
+      ISL_CUDA_TRY(cudaEventCreate(&e0));
+      round_ev.push_back(e0);
+      ISL_CUDA_TRY(cudaEventCreate(&e1));
+      round_ev.push_back(e1);
+      ISL_CUDA_TRY(cudaEventRecord(e0, st));
       ISL_TRY(launch_search(plan, a, st));
+      ISL_CUDA_TRY(cudaEventRecord(e1, st));
+      accumulate_stats_kernel<<<std::min<uint32_t>((r + 255) / 256, 148), 256, 0, st>>>(round_stats.p, r, stat_totals.p);
+      count_launch();
 
       const uint32_t blocks = (r + sel_warps - 1) / sel_warps;
       select_neighbors_kernel<<<blocks, sel_warps * 32, (size_t)sel_warps * efc * 4, st>>>(
@@ -417,8 +459,21 @@ isl_status build_graph(isl_index* idx, const uint64_t* levels_or_null, uint64_t 
     s = e;
   }
   unsigned int hflags[4] = {0, 0, 0, 0};
+  unsigned long long htot[4] = {0, 0, 0, 0};
   ISL_CUDA_TRY(cudaMemcpyAsync(hflags, idx->counters.p, sizeof(hflags), cudaMemcpyDeviceToHost, st));
+  ISL_CUDA_TRY(cudaMemcpyAsync(htot, stat_totals.p, sizeof(htot), cudaMemcpyDeviceToHost, st));
+  ISL_CUDA_TRY(cudaEventRecord(idx->ev1, st));
   ISL_CUDA_TRY(cudaStreamSynchronize(st));
+  idx->build_stats = isl_build_stats{};
+  idx->build_stats.n_hop = htot[0];
+  idx->build_stats.n_edge = htot[1];
+  idx->build_stats.n_dist = htot[2];
+  idx->build_stats.rounds = round_ev.size() / 2;
+  cudaEventElapsedTime(&idx->build_stats.rounds_ms, idx->ev0, idx->ev1);
+  for (size_t i = 0; i + 1 < round_ev.size(); i += 2) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, round_ev[i], round_ev[i + 1]) == cudaSuccess) idx->build_stats.search_ms += ms;
+  }
 
   // adjacency -> CSR (leann.rs:618-627)
   DevBuf<uint64_t> deg64;
@@ -453,6 +508,7 @@ isl_status build_graph(isl_index* idx, const uint64_t* levels_or_null, uint64_t 
   idx->max_degree = maxdeg;
   idx->entry = entry;
   idx->max_level = max_level;
+  idx->build_stats.edges = num_edges;
   ISL_TRY(index_make_padded_adjacency(idx));
   // construction scratch is not needed by searches (they lease their own)
   idx->visited.release();
@@ -499,6 +555,12 @@ static isl_status build_common(const isl_leann_config* cfg, uint32_t dim, uint64
   ISL_TRY(launch_row_sqnorms(idx->vectors.p, n, dim, idx->ld, idx->sqnorms.p, idx->sms, idx->stream));
   ISL_TRY(build_graph(idx.get(), levels_or_null, seed, batch));
   *out = idx.release();
+  return ISL_OK;
+}
+
+isl_status isl_index_last_build_stats(const isl_index* idx, isl_build_stats* out) {
+  if (!idx || !out) return fail(ISL_INVALID_ARGUMENT, "null pointer");
+  *out = idx->build_stats;
   return ISL_OK;
 }
 

@@ -33,7 +33,10 @@ isl_status opt_in_smem(K kern, std::once_flag* flags, cudaError_t* results) {
   ISL_CUDA_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return fail(ISL_CUDA_ERROR, "search: device ordinal out of range");
   std::call_once(flags[dev], [&] {
-    results[dev] = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    cudaFuncAttributes fa{};
+    results[dev] = cudaFuncGetAttributes(&fa, kern);  // static shared memory (the tie-list header) counts against the 227 KB
+    if (results[dev] == cudaSuccess)
+      results[dev] = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem - (int)fa.sharedSizeBytes);
   });
   if (results[dev] != cudaSuccess) return cuda_fail(results[dev], "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
   return ISL_OK;
@@ -44,8 +47,8 @@ isl_status plan_one(uint32_t ld, uint32_t ef, uint32_t u_cap, int sms, SearchPla
   auto kern = leann_search_kernel<ACC, kCH, kStages, R_SMEM, TWO>;
   const size_t smem = search_smem_bytes<kCH, kStages>(ld, R_SMEM ? ef : 0, u_cap, plan->lut_smem_floats,
                                                       plan->aq_smem_entries);
-  if (smem > 227 * 1024)
-    return fail(ISL_INVALID_ARGUMENT, "search: dimension / ef need more than 227 KB of shared memory per warp");
+  if (smem > 226 * 1024)
+    return fail(ISL_INVALID_ARGUMENT, "search: dimension / ef need more than 226 KB of shared memory per warp");
   static std::once_flag once[64];
   static cudaError_t once_result[64];
   ISL_TRY(opt_in_smem(kern, once, once_result));
@@ -72,7 +75,7 @@ isl_status plan_lean(uint32_t ef, uint32_t u_cap, uint32_t pq_m, int sms, Search
   auto kern = leann_search_kernel<ACC_DOT, kCH, kStages, R_SMEM, 3, NR>;
   const size_t smem = search_smem_bytes<kCH, kStages>(0, (R_SMEM && NR == 0) ? ef : 0, u_cap, plan->lut_smem_floats, 0, true) +
                       (R_SMEM ? search_smem_bytes_idc() : 0);
-  if (smem > 227 * 1024) return fail(ISL_INVALID_ARGUMENT, "search: ef needs more than 227 KB of shared memory per warp");
+  if (smem > 226 * 1024) return fail(ISL_INVALID_ARGUMENT, "search: ef needs more than 226 KB of shared memory per warp");
   plan->novis_ok = R_SMEM && plan->lut_smem_floats != 0 && (pq_m == 16 || pq_m == 32);  // and n < kIdcMaxNodes (checked by the caller)
   static std::once_flag once[64];
   static cudaError_t once_result[64];

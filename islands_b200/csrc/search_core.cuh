@@ -517,31 +517,22 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         }
         first_unexp = nxt;
       } else {
-        // smallest live tie, if any: lanes stride the list, then a key-ordered butterfly picks the minimum
+        // smallest live tie, if any.  Every lane scans the whole list (broadcast loads): the result is then provably
+        // warp-uniform.  A lane-strided scan + shuffle reduction hands `cur` back through shuffles, which the compiler
+        // must treat as divergent — it then wraps every collective of the search loop in convergence barriers
+        // (BSSY/BSYNC 29 -> 370 in the SASS of the ADC traversal kernel, 63 -> 80 registers, -13 % speed).
         const float wd = RREG ? wst_d : __uint_as_float(R.ld(r_len - 1).x);
-        uint32_t bpos = 0xffffffffu;
-        uint2 bt = make_uint2(0, 0);
-        for (uint32_t i = lane; i < n_ties; i += 32) {
+        int best = -1;
+        for (uint32_t i = 0; i < n_ties; ++i) {
           const uint2 t = tie_ld(i);
           if (r_len >= ef && of_lt(wd, __uint_as_float(t.x))) continue;  // stale
-          if (bpos == 0xffffffffu || key_lt(__uint_as_float(t.x), t.y, __uint_as_float(bt.x), bt.y)) {
-            bt = t;
-            bpos = i;
-          }
+          if (best < 0 || key_lt(__uint_as_float(t.x), t.y, __uint_as_float(tie_ld(best).x), tie_ld(best).y))
+            best = (int)i;
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-          const uint32_t ox = __shfl_xor_sync(FULL, bt.x, off), oy = __shfl_xor_sync(FULL, bt.y, off);
-          const uint32_t op = __shfl_xor_sync(FULL, bpos, off);
-          if (op != 0xffffffffu && (bpos == 0xffffffffu || key_lt(__uint_as_float(ox), oy, __uint_as_float(bt.x), bt.y))) {
-            bt = make_uint2(ox, oy);
-            bpos = op;
-          }
-        }
-        if (bpos == 0xffffffffu) break;
-        cur = bt.y;
+        if (best < 0) break;
+        cur = tie_ld(best).y;
         __syncwarp();
-        if (lane == 0) tie_st(bpos, tie_ld(n_ties - 1));
+        if (lane == 0) tie_st(best, tie_ld(n_ties - 1));
         n_ties--;
         __syncwarp();
       }
