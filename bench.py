@@ -58,7 +58,7 @@ def parse_args():
     ap.add_argument("--pq-ksub", type=int, default=128, help="centroids per subquantizer of the ADC secondary "
                     "(128: a 16 KB table per query in shared memory keeps twice the warps resident of 256)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline sample")
-    ap.add_argument("--build-sample", type=int, default=20000, help="nodes of the construction cpu_baseline sample (oracle build + GPU build of the same prefix, graphs compared)")
+    ap.add_argument("--build-sample", type=int, default=10000, help="nodes of the construction cpu_baseline sample (oracle build + GPU build of the same prefix, graphs compared)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)  # the timing rules ask for at least three untimed steps; the JSON line reports what was done
     a.steps = max(a.steps, 1)

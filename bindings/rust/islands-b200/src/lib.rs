@@ -1,0 +1,779 @@
+//! Safe wrapper over `libislands_b200.so` with the signatures of panbanda/islands' `src/core`
+//! (`src/core/mod.rs:60-99`): `LeannIndex::{new, build, search, search_with_params}`, `CsrGraph`,
+//! `LeannConfig`, `EmbeddingProvider`, `ProductQuantizer`, `DistanceMetric` / `Distance`, `CoreError`.
+//! A maintainer of the reference swaps `use crate::core::leann::LeannIndex` for
+//! `use islands_b200::LeannIndex` and keeps the call sites.
+//!
+//! There is no Rust toolchain in the image this repository is developed in: this file is source for the
+//! reference's build and is not compiled by this repository's tests.  Everything below is argument marshalling;
+//! the arithmetic lives in the CUDA library, and a missing GPU surfaces as `CoreError::SearchError`, never as a
+//! CPU fallback.
+#![allow(clippy::missing_safety_doc)]
+
+use islands_b200_sys as sys;
+use std::ffi::CStr;
+use std::ptr;
+
+// ---------------------------------------------------------------------------------------------
+// error.rs:9-62
+// ---------------------------------------------------------------------------------------------
+#[derive(thiserror::Error, Debug)]
+pub enum CoreError {
+    #[error("Vector dimension mismatch: expected {expected}, got {actual}")]
+    DimensionMismatch { expected: usize, actual: usize },
+    #[error("Empty vector collection")]
+    EmptyCollection,
+    #[error("Invalid configuration: {0}")]
+    InvalidConfig(String),
+    #[error("Index not built")]
+    IndexNotBuilt,
+    #[error("Node not found: {0}")]
+    NodeNotFound(u64),
+    #[error("Serialization error: {0}")]
+    Serialization(String),
+    #[error("Deserialization error: {0}")]
+    Deserialization(String),
+    #[error("IO error: {0}")]
+    Io(#[from] std::io::Error),
+    #[error("HNSW graph error: {0}")]
+    HnswError(String),
+    #[error("Product quantization error: {0}")]
+    PQError(String),
+    /// Device failures (`ISL_CUDA_ERROR`) and ABI argument errors have no variant of their own in the reference;
+    /// they travel as `SearchError` with the library's message.
+    #[error("Search error: {0}")]
+    SearchError(String),
+    #[error("Embedding error: {0}")]
+    EmbeddingError(String),
+}
+
+pub type CoreResult<T> = Result<T, CoreError>;
+
+fn last_message() -> String {
+    unsafe {
+        let p = sys::isl_last_error();
+        if p.is_null() {
+            String::new()
+        } else {
+            CStr::from_ptr(p).to_string_lossy().into_owned()
+        }
+    }
+}
+
+/// `isl_status` -> the `CoreError` variant it mirrors, payloads included (`isl_last_error_detail`).
+fn check(status: i32) -> CoreResult<()> {
+    if status == sys::ISL_OK {
+        return Ok(());
+    }
+    let msg = last_message();
+    let (mut a, mut b) = (0u64, 0u64);
+    unsafe { sys::isl_last_error_detail(&mut a, &mut b) };
+    Err(match status {
+        sys::ISL_DIM_MISMATCH => CoreError::DimensionMismatch { expected: a as usize, actual: b as usize },
+        sys::ISL_EMPTY_COLLECTION => CoreError::EmptyCollection,
+        sys::ISL_INVALID_CONFIG => CoreError::InvalidConfig(msg),
+        sys::ISL_INDEX_NOT_BUILT => CoreError::IndexNotBuilt,
+        sys::ISL_NODE_NOT_FOUND => CoreError::NodeNotFound(a),
+        sys::ISL_PQ_ERROR => CoreError::PQError(msg),
+        sys::ISL_SERIALIZATION => CoreError::Deserialization(msg),
+        _ => CoreError::SearchError(msg),
+    })
+}
+
+// ---------------------------------------------------------------------------------------------
+// distance.rs:7-139
+// ---------------------------------------------------------------------------------------------
+#[derive(Debug, Clone, Copy, PartialEq, Eq, Default)]
+pub enum DistanceMetric {
+    #[default]
+    Cosine,
+    Euclidean,
+    DotProduct,
+    Manhattan,
+}
+
+impl DistanceMetric {
+    fn code(self) -> i32 {
+        match self {
+            DistanceMetric::Cosine => sys::ISL_METRIC_COSINE,
+            DistanceMetric::Euclidean => sys::ISL_METRIC_EUCLIDEAN,
+            DistanceMetric::DotProduct => sys::ISL_METRIC_DOT,
+            DistanceMetric::Manhattan => sys::ISL_METRIC_MANHATTAN,
+        }
+    }
+    fn from_code(c: i32) -> Self {
+        match c {
+            sys::ISL_METRIC_EUCLIDEAN => DistanceMetric::Euclidean,
+            sys::ISL_METRIC_DOT => DistanceMetric::DotProduct,
+            sys::ISL_METRIC_MANHATTAN => DistanceMetric::Manhattan,
+            _ => DistanceMetric::Cosine,
+        }
+    }
+}
+
+/// distance.rs:22-35
+pub trait Distance: Send + Sync {
+    fn calculate(&self, a: &[f32], b: &[f32]) -> CoreResult<f32>;
+    fn calculate_squared(&self, a: &[f32], b: &[f32]) -> CoreResult<f32>;
+    fn batch_calculate(&self, query: &[f32], vectors: &[&[f32]]) -> CoreResult<Vec<f32>>;
+}
+
+impl Distance for DistanceMetric {
+    fn calculate(&self, a: &[f32], b: &[f32]) -> CoreResult<f32> {
+        let mut out = 0f32;
+        check(unsafe { sys::isl_distance_calculate(self.code(), a.as_ptr(), a.len() as u64, b.as_ptr(), b.len() as u64, &mut out) })?;
+        Ok(out)
+    }
+    fn calculate_squared(&self, a: &[f32], b: &[f32]) -> CoreResult<f32> {
+        let mut out = 0f32;
+        check(unsafe {
+            sys::isl_distance_calculate_squared(self.code(), a.as_ptr(), a.len() as u64, b.as_ptr(), b.len() as u64, &mut out)
+        })?;
+        Ok(out)
+    }
+    fn batch_calculate(&self, query: &[f32], vectors: &[&[f32]]) -> CoreResult<Vec<f32>> {
+        let d = query.len();
+        let mut rows = Vec::with_capacity(vectors.len() * d);
+        for v in vectors {
+            if v.len() != d {
+                return Err(CoreError::DimensionMismatch { expected: d, actual: v.len() });
+            }
+            rows.extend_from_slice(v);
+        }
+        let mut out = vec![0f32; vectors.len()];
+        check(unsafe {
+            sys::isl_distance_batch(self.code(), query.as_ptr(), rows.as_ptr(), vectors.len() as u64, d as u32, out.as_mut_ptr())
+        })?;
+        Ok(out)
+    }
+}
+
+/// distance.rs:125-132
+pub fn normalize_vector(v: &mut [f32]) {
+    let _ = unsafe { sys::isl_normalize_rows(v.as_mut_ptr(), 1, v.len() as u32) };
+}
+
+/// distance.rs:135-139
+pub fn normalized(v: &[f32]) -> Vec<f32> {
+    let mut out = v.to_vec();
+    normalize_vector(&mut out);
+    out
+}
+
+// ---------------------------------------------------------------------------------------------
+// leann.rs:82-159 — the recompute seam
+// ---------------------------------------------------------------------------------------------
+pub trait EmbeddingProvider: Send + Sync {
+    fn compute_embedding(&self, id: u64) -> CoreResult<Vec<f32>>;
+    fn compute_embeddings_batch(&self, ids: &[u64]) -> CoreResult<Vec<Vec<f32>>> {
+        ids.iter().map(|&id| self.compute_embedding(id)).collect()
+    }
+    fn dimension(&self) -> usize;
+}
+
+pub struct InMemoryEmbeddingProvider {
+    embeddings: Vec<Vec<f32>>,
+    dimension: usize,
+}
+
+impl InMemoryEmbeddingProvider {
+    pub fn new(embeddings: Vec<Vec<f32>>) -> CoreResult<Self> {
+        if embeddings.is_empty() {
+            return Err(CoreError::EmptyCollection);
+        }
+        let dimension = embeddings[0].len();
+        Ok(Self { embeddings, dimension })
+    }
+    pub fn with_dimension(dimension: usize) -> Self {
+        Self { embeddings: Vec::new(), dimension }
+    }
+    pub fn add(&mut self, embedding: Vec<f32>) -> CoreResult<u64> {
+        if embedding.len() != self.dimension {
+            return Err(CoreError::DimensionMismatch { expected: self.dimension, actual: embedding.len() });
+        }
+        self.embeddings.push(embedding);
+        Ok((self.embeddings.len() - 1) as u64)
+    }
+}
+
+impl EmbeddingProvider for InMemoryEmbeddingProvider {
+    fn compute_embedding(&self, id: u64) -> CoreResult<Vec<f32>> {
+        self.embeddings.get(id as usize).cloned().ok_or(CoreError::NodeNotFound(id))
+    }
+    fn dimension(&self) -> usize {
+        self.dimension
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// leann.rs:168-461 — PruningStrategy, CsrGraph, LeannConfig
+// ---------------------------------------------------------------------------------------------
+#[derive(Debug, Clone, Copy, PartialEq, Eq, Default)]
+pub enum PruningStrategy {
+    #[default]
+    Global,
+    Local,
+    /// Draws from `thread_rng` in the reference (leann.rs:1043); the GPU library rejects it with `InvalidConfig`.
+    Proportional,
+}
+
+#[derive(Debug, Clone, Default)]
+pub struct CsrGraph {
+    pub node_offsets: Vec<usize>,
+    pub neighbors: Vec<u64>,
+    pub levels: Vec<usize>,
+    pub entry_point: Option<u64>,
+    pub max_level: usize,
+    pub num_nodes: usize,
+    pub degree_counts: Vec<usize>,
+}
+
+impl CsrGraph {
+    pub fn new() -> Self {
+        Self { node_offsets: vec![0], ..Default::default() }
+    }
+    pub fn get_neighbors(&self, node_id: u64) -> Option<&[u64]> {
+        let id = node_id as usize;
+        if id >= self.num_nodes {
+            return None;
+        }
+        Some(&self.neighbors[self.node_offsets[id]..self.node_offsets[id + 1]])
+    }
+    pub fn add_node(&mut self, neighbors: Vec<u64>, level: usize) -> u64 {
+        let id = self.num_nodes as u64;
+        self.num_nodes += 1;
+        self.levels.push(level);
+        self.degree_counts.push(neighbors.len());
+        self.neighbors.extend(neighbors);
+        self.node_offsets.push(self.neighbors.len());
+        if self.entry_point.is_none() || level > self.max_level {
+            self.entry_point = Some(id);
+            self.max_level = level;
+        }
+        id
+    }
+    pub fn set_neighbors(&mut self, node_id: u64, new_neighbors: Vec<u64>) {
+        let id = node_id as usize;
+        if id >= self.num_nodes {
+            return;
+        }
+        let (s, e) = (self.node_offsets[id], self.node_offsets[id + 1]);
+        if new_neighbors.len() == e - s {
+            self.neighbors[s..e].copy_from_slice(&new_neighbors);
+        } else {
+            let delta = new_neighbors.len() as isize - (e - s) as isize;
+            self.neighbors.splice(s..e, new_neighbors.iter().copied());
+            for o in self.node_offsets[id + 1..].iter_mut() {
+                *o = (*o as isize + delta) as usize;
+            }
+        }
+        self.degree_counts[id] = new_neighbors.len();
+    }
+    pub fn storage_bytes(&self) -> usize {
+        8 * (self.node_offsets.len() + self.neighbors.len() + self.levels.len() + self.degree_counts.len())
+    }
+}
+
+#[derive(Debug, Clone)]
+pub struct LeannConfig {
+    pub m: usize,
+    pub m0: usize,
+    pub ef_construction: usize,
+    pub ml: f64,
+    pub max_layers: usize,
+    pub metric: DistanceMetric,
+    pub ef_search: usize,
+    pub beam_width: usize,
+    pub prune_ratio: f32,
+    pub pruning_strategy: PruningStrategy,
+    pub high_degree_pruning: bool,
+    pub hub_percentile: f32,
+    pub is_compact: bool,
+    pub is_recompute: bool,
+}
+
+impl Default for LeannConfig {
+    fn default() -> Self {
+        Self::paper_default()
+    }
+}
+
+impl LeannConfig {
+    fn from_raw(c: &sys::IslLeannConfig) -> Self {
+        Self {
+            m: c.m as usize,
+            m0: c.m0 as usize,
+            ef_construction: c.ef_construction as usize,
+            ml: c.ml,
+            max_layers: c.max_layers as usize,
+            metric: DistanceMetric::from_code(c.metric),
+            ef_search: c.ef_search as usize,
+            beam_width: c.beam_width as usize,
+            prune_ratio: c.prune_ratio,
+            pruning_strategy: match c.pruning_strategy {
+                sys::ISL_PRUNE_LOCAL => PruningStrategy::Local,
+                sys::ISL_PRUNE_PROPORTIONAL => PruningStrategy::Proportional,
+                _ => PruningStrategy::Global,
+            },
+            high_degree_pruning: c.high_degree_pruning != 0,
+            hub_percentile: c.hub_percentile,
+            is_compact: c.is_compact != 0,
+            is_recompute: c.is_recompute != 0,
+        }
+    }
+    fn raw(&self) -> sys::IslLeannConfig {
+        sys::IslLeannConfig {
+            m: self.m as u64,
+            m0: self.m0 as u64,
+            ef_construction: self.ef_construction as u64,
+            ml: self.ml,
+            max_layers: self.max_layers as u64,
+            metric: self.metric.code(),
+            ef_search: self.ef_search as u64,
+            beam_width: self.beam_width as u64,
+            prune_ratio: self.prune_ratio,
+            pruning_strategy: match self.pruning_strategy {
+                PruningStrategy::Global => sys::ISL_PRUNE_GLOBAL,
+                PruningStrategy::Local => sys::ISL_PRUNE_LOCAL,
+                PruningStrategy::Proportional => sys::ISL_PRUNE_PROPORTIONAL,
+            },
+            high_degree_pruning: self.high_degree_pruning as i32,
+            hub_percentile: self.hub_percentile,
+            is_compact: self.is_compact as i32,
+            is_recompute: self.is_recompute as i32,
+        }
+    }
+    fn preset(f: unsafe extern "C" fn(*mut sys::IslLeannConfig) -> i32) -> Self {
+        let mut raw = std::mem::MaybeUninit::<sys::IslLeannConfig>::zeroed();
+        unsafe {
+            f(raw.as_mut_ptr());
+            Self::from_raw(&raw.assume_init())
+        }
+    }
+    /// leann.rs:386-403
+    pub fn paper_default() -> Self {
+        Self::preset(sys::isl_leann_config_default)
+    }
+    /// leann.rs:406-416
+    pub fn fast() -> Self {
+        Self::preset(sys::isl_leann_config_fast)
+    }
+    /// leann.rs:419-429
+    pub fn accurate() -> Self {
+        Self::preset(sys::isl_leann_config_accurate)
+    }
+    /// leann.rs:432-460
+    pub fn validate(&self) -> CoreResult<()> {
+        check(unsafe { sys::isl_leann_config_validate(&self.raw()) })
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// leann.rs:493-1067 — LeannIndex
+// ---------------------------------------------------------------------------------------------
+pub struct LeannIndex {
+    config: LeannConfig,
+    handle: *mut sys::IslIndex,
+}
+
+// The handle is immutable after build; searches lease per-call scratch inside the library (csrc/api.cu).
+unsafe impl Send for LeannIndex {}
+unsafe impl Sync for LeannIndex {}
+
+impl Drop for LeannIndex {
+    fn drop(&mut self) {
+        unsafe { sys::isl_index_free(self.handle) };
+    }
+}
+
+/// Levels are drawn from `thread_rng` in the reference (leann.rs:549-554); here from a seed (same formula).
+pub struct BuildOptions {
+    pub levels: Option<Vec<u64>>,
+    pub seed: u64,
+    /// 1 = the reference's sequential insertion order; > 1 = rounds of that many inserts (GPU-parallel).
+    pub batch: u32,
+}
+
+impl Default for BuildOptions {
+    fn default() -> Self {
+        Self { levels: None, seed: 0, batch: 4096 }
+    }
+}
+
+impl LeannIndex {
+    pub fn new(config: LeannConfig) -> CoreResult<Self> {
+        config.validate()?;
+        Ok(Self { config, handle: ptr::null_mut() })
+    }
+    pub fn with_defaults() -> CoreResult<Self> {
+        Self::new(LeannConfig::default())
+    }
+    pub fn len(&self) -> usize {
+        unsafe { sys::isl_index_len(self.handle) as usize }
+    }
+    pub fn is_empty(&self) -> bool {
+        self.len() == 0
+    }
+    pub fn dimension(&self) -> Option<usize> {
+        match unsafe { sys::isl_index_dimension(self.handle) } {
+            0 => None,
+            d => Some(d as usize),
+        }
+    }
+    pub fn storage_bytes(&self) -> usize {
+        if self.handle.is_null() {
+            8
+        } else {
+            unsafe { sys::isl_index_storage_bytes(self.handle) as usize }
+        }
+    }
+    pub fn is_recompute(&self) -> bool {
+        self.config.is_recompute
+    }
+    pub fn is_compact(&self) -> bool {
+        self.config.is_compact
+    }
+    pub fn config(&self) -> &LeannConfig {
+        &self.config
+    }
+
+    /// leann.rs:560-631.  The provider is drained once (`compute_embeddings_batch(0..n)`) and the embeddings become
+    /// resident in HBM; construction then runs on the GPU.
+    pub fn build<P: EmbeddingProvider>(&mut self, provider: &P, num_vectors: usize) -> CoreResult<()> {
+        self.build_with(provider, num_vectors, &BuildOptions::default())
+    }
+
+    pub fn build_with<P: EmbeddingProvider>(&mut self, provider: &P, num_vectors: usize, opt: &BuildOptions) -> CoreResult<()> {
+        if num_vectors == 0 {
+            return Ok(()); // leann.rs:565-567
+        }
+        let ids: Vec<u64> = (0..num_vectors as u64).collect();
+        let rows = provider.compute_embeddings_batch(&ids)?;
+        let dim = provider.dimension();
+        let mut flat = Vec::with_capacity(num_vectors * dim);
+        for r in &rows {
+            if r.len() != dim {
+                return Err(CoreError::DimensionMismatch { expected: dim, actual: r.len() });
+            }
+            flat.extend_from_slice(r);
+        }
+        if let Some(l) = &opt.levels {
+            if l.len() != num_vectors {
+                return Err(CoreError::InvalidConfig("levels must have one entry per vector".into()));
+            }
+        }
+        let mut h: *mut sys::IslIndex = ptr::null_mut();
+        check(unsafe {
+            sys::isl_index_build(
+                &self.config.raw(),
+                dim as u32,
+                num_vectors as u64,
+                flat.as_ptr(),
+                opt.levels.as_ref().map_or(ptr::null(), |l| l.as_ptr()),
+                opt.seed,
+                opt.batch,
+                &mut h,
+            )
+        })?;
+        unsafe { sys::isl_index_free(self.handle) };
+        self.handle = h;
+        Ok(())
+    }
+
+    /// Adopt an existing graph ("identical graphs" entry point of the parity tests).
+    pub fn from_csr<P: EmbeddingProvider>(config: LeannConfig, graph: &CsrGraph, provider: &P) -> CoreResult<Self> {
+        config.validate()?;
+        let n = graph.num_nodes;
+        let ids: Vec<u64> = (0..n as u64).collect();
+        let rows = provider.compute_embeddings_batch(&ids)?;
+        let dim = provider.dimension();
+        let flat: Vec<f32> = rows.into_iter().flatten().collect();
+        let off: Vec<u64> = graph.node_offsets.iter().map(|&x| x as u64).collect();
+        let lv: Vec<u64> = graph.levels.iter().map(|&x| x as u64).collect();
+        let mut h: *mut sys::IslIndex = ptr::null_mut();
+        check(unsafe {
+            sys::isl_index_from_csr(
+                &config.raw(),
+                dim as u32,
+                n as u64,
+                off.as_ptr(),
+                graph.neighbors.as_ptr(),
+                lv.as_ptr(),
+                graph.entry_point.map_or(-1, |e| e as i64),
+                flat.as_ptr(),
+                &mut h,
+            )
+        })?;
+        Ok(Self { config, handle: h })
+    }
+
+    /// graph: the CSR arrays in the reference's layout.
+    pub fn graph(&self) -> CoreResult<CsrGraph> {
+        let n = self.len();
+        let e = unsafe { sys::isl_index_num_edges(self.handle) } as usize;
+        let (mut off, mut nb, mut lv, mut deg) = (vec![0u64; n + 1], vec![0u64; e], vec![0u64; n], vec![0u64; n]);
+        check(unsafe { sys::isl_index_export_csr(self.handle, off.as_mut_ptr(), nb.as_mut_ptr(), lv.as_mut_ptr(), deg.as_mut_ptr()) })?;
+        let ep = unsafe { sys::isl_index_entry_point(self.handle) };
+        Ok(CsrGraph {
+            node_offsets: off.into_iter().map(|x| x as usize).collect(),
+            neighbors: nb,
+            levels: lv.into_iter().map(|x| x as usize).collect(),
+            entry_point: if ep < 0 { None } else { Some(ep as u64) },
+            max_level: unsafe { sys::isl_index_max_level(self.handle) } as usize,
+            num_nodes: n,
+            degree_counts: deg.into_iter().map(|x| x as usize).collect(),
+        })
+    }
+
+    /// leann.rs:858-865.  The provider argument is kept for signature compatibility: the embeddings it returned at
+    /// build time are resident on the device (for true on-demand recompute attach an encoder: `isl_index_set_recompute`).
+    pub fn search<P: EmbeddingProvider>(&self, query: &[f32], k: usize, provider: &P) -> CoreResult<Vec<(u64, f32)>> {
+        self.search_with_params(query, k, self.config.ef_search, provider)
+    }
+
+    /// leann.rs:868-896
+    pub fn search_with_params<P: EmbeddingProvider>(&self, query: &[f32], k: usize, ef: usize, _provider: &P) -> CoreResult<Vec<(u64, f32)>> {
+        if self.is_empty() {
+            return Ok(vec![]);
+        }
+        let (ids, dist, count) = self.search_batch(query, 1, k, ef)?;
+        Ok((0..count[0] as usize).map(|i| (ids[i], dist[i])).collect())
+    }
+
+    /// Batched form (what a GPU wants): `queries` is `[nq][dim]` row-major; returns ids / distances `[nq][k]`
+    /// (padded with `u64::MAX` / `+inf`) and the result count per query.
+    pub fn search_batch(&self, queries: &[f32], nq: usize, k: usize, ef: usize) -> CoreResult<(Vec<u64>, Vec<f32>, Vec<u32>)> {
+        let dim = if nq == 0 { 0 } else { queries.len() / nq };
+        let (mut ids, mut dist, mut count) = (vec![u64::MAX; nq * k], vec![f32::INFINITY; nq * k], vec![0u32; nq]);
+        check(unsafe {
+            sys::isl_index_search(
+                self.handle,
+                queries.as_ptr(),
+                nq as u64,
+                dim as u32,
+                k as u32,
+                ef as u32,
+                ids.as_mut_ptr(),
+                dist.as_mut_ptr(),
+                count.as_mut_ptr(),
+                ptr::null_mut(),
+            )
+        })?;
+        Ok((ids, dist, count))
+    }
+
+    /// Sharded search (service.rs:777-801): collective over the ranks of `shard`; `id_base` = first global id of
+    /// this rank's shard.  Every rank passes the same queries and receives the same merged top-k.
+    pub fn search_sharded(&self, shard: &ShardComm, id_base: u64, queries: &[f32], nq: usize, k: usize, ef: usize)
+                          -> CoreResult<(Vec<u64>, Vec<f32>, Vec<u32>)> {
+        let dim = if nq == 0 { 0 } else { queries.len() / nq };
+        let (mut ids, mut dist, mut count) = (vec![u64::MAX; nq * k], vec![f32::INFINITY; nq * k], vec![0u32; nq]);
+        check(unsafe {
+            sys::isl_index_search_sharded(self.handle, shard.handle, id_base, queries.as_ptr(), nq as u64, dim as u32, k as u32,
+                                          ef as u32, ids.as_mut_ptr(), dist.as_mut_ptr(), count.as_mut_ptr())
+        })?;
+        Ok((ids, dist, count))
+    }
+
+    /// leann.rs:1059-1061 (graph only, bincode layout)
+    pub fn to_bytes(&self) -> CoreResult<Vec<u8>> {
+        let mut len = 0u64;
+        check(unsafe { sys::isl_index_to_bytes(self.handle, ptr::null_mut(), 0, &mut len) })
+            .map_err(|e| CoreError::Serialization(e.to_string()))?;
+        let mut out = vec![0u8; len as usize];
+        check(unsafe { sys::isl_index_to_bytes(self.handle, out.as_mut_ptr(), len, &mut len) })
+            .map_err(|e| CoreError::Serialization(e.to_string()))?;
+        Ok(out)
+    }
+
+    /// leann.rs:1064-1066 + the embeddings the provider returns (the bytes hold the graph only).
+    pub fn from_bytes<P: EmbeddingProvider>(bytes: &[u8], provider: &P, num_vectors: usize) -> CoreResult<Self> {
+        let ids: Vec<u64> = (0..num_vectors as u64).collect();
+        let flat: Vec<f32> = provider.compute_embeddings_batch(&ids)?.into_iter().flatten().collect();
+        let mut h: *mut sys::IslIndex = ptr::null_mut();
+        check(unsafe { sys::isl_index_from_bytes(bytes.as_ptr(), bytes.len() as u64, flat.as_ptr(), provider.dimension() as u32, &mut h) })?;
+        let mut raw = std::mem::MaybeUninit::<sys::IslLeannConfig>::zeroed();
+        check(unsafe { sys::isl_index_get_config(h, raw.as_mut_ptr()) })?;
+        Ok(Self { config: LeannConfig::from_raw(unsafe { &raw.assume_init() }), handle: h })
+    }
+}
+
+/// One rank's membership in a sharded index (NCCL communicator inside the library).
+pub struct ShardComm {
+    handle: *mut sys::IslShard,
+}
+
+unsafe impl Send for ShardComm {}
+
+impl ShardComm {
+    /// `ncclGetUniqueId`: call on one rank, hand the 128 bytes to the others by any host channel.
+    pub fn unique_id() -> CoreResult<[u8; 128]> {
+        let mut id = [0u8; 128];
+        check(unsafe { sys::isl_shard_unique_id(id.as_mut_ptr() as *mut _, 128) })?;
+        Ok(id)
+    }
+    pub fn new(rank: i32, world: i32, unique_id: &[u8; 128]) -> CoreResult<Self> {
+        let mut h: *mut sys::IslShard = ptr::null_mut();
+        check(unsafe { sys::isl_shard_init(rank, world, unique_id.as_ptr() as *const _, &mut h) })?;
+        Ok(Self { handle: h })
+    }
+    /// Exchange by peer stores over NVLink instead of `ncclAllGather` (collective; ranks of one node).
+    pub fn enable_peer_exchange(&mut self, max_records: u64) -> CoreResult<()> {
+        check(unsafe { sys::isl_shard_enable_peer_exchange(self.handle, max_records) })
+    }
+}
+
+impl Drop for ShardComm {
+    fn drop(&mut self) {
+        unsafe { sys::isl_shard_free(self.handle) };
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pq.rs:13-359 — PQConfig, ProductQuantizer
+// ---------------------------------------------------------------------------------------------
+#[derive(Debug, Clone)]
+pub struct PQConfig {
+    pub num_subquantizers: usize,
+    pub num_centroids: usize,
+    pub training_iterations: usize,
+    pub seed: Option<u64>,
+}
+
+impl Default for PQConfig {
+    fn default() -> Self {
+        Self { num_subquantizers: 8, num_centroids: 256, training_iterations: 25, seed: None }
+    }
+}
+
+impl PQConfig {
+    fn raw(&self) -> sys::IslPqConfig {
+        sys::IslPqConfig {
+            num_subquantizers: self.num_subquantizers as u64,
+            num_centroids: self.num_centroids as u64,
+            training_iterations: self.training_iterations as u64,
+            seed: self.seed.unwrap_or(0),
+            has_seed: self.seed.is_some() as i32,
+        }
+    }
+    /// pq.rs:37-55
+    pub fn validate(&self, dimension: usize) -> CoreResult<()> {
+        check(unsafe { sys::isl_pq_config_validate(&self.raw(), dimension as u64) })
+    }
+    /// pq.rs:58-64
+    pub fn bytes_per_vector(&self) -> usize {
+        unsafe { sys::isl_pq_config_bytes_per_vector(&self.raw()) as usize }
+    }
+}
+
+pub struct ProductQuantizer {
+    handle: *mut sys::IslPq,
+    dimension: usize,
+}
+
+unsafe impl Send for ProductQuantizer {}
+unsafe impl Sync for ProductQuantizer {}
+
+impl Drop for ProductQuantizer {
+    fn drop(&mut self) {
+        unsafe { sys::isl_pq_free(self.handle) };
+    }
+}
+
+impl ProductQuantizer {
+    /// pq.rs:133-149
+    pub fn new(dimension: usize, config: PQConfig) -> CoreResult<Self> {
+        let mut h: *mut sys::IslPq = ptr::null_mut();
+        check(unsafe { sys::isl_pq_new(dimension as u32, &config.raw(), &mut h) })?;
+        Ok(Self { handle: h, dimension })
+    }
+    /// pq.rs:152-155
+    pub fn with_metric(self, metric: DistanceMetric) -> Self {
+        let _ = unsafe { sys::isl_pq_set_metric(self.handle, metric.code()) };
+        self
+    }
+    pub fn is_trained(&self) -> bool {
+        unsafe { sys::isl_pq_is_trained(self.handle) != 0 }
+    }
+    pub fn num_subquantizers(&self) -> usize {
+        unsafe { sys::isl_pq_num_subquantizers(self.handle) as usize }
+    }
+    pub fn compression_ratio(&self) -> f32 {
+        unsafe { sys::isl_pq_compression_ratio(self.handle) }
+    }
+    /// pq.rs:175-218
+    pub fn train(&mut self, vectors: &[Vec<f32>]) -> CoreResult<()> {
+        if vectors.is_empty() {
+            return Err(CoreError::EmptyCollection);
+        }
+        let mut flat = Vec::with_capacity(vectors.len() * self.dimension);
+        for v in vectors {
+            if v.len() != self.dimension {
+                return Err(CoreError::DimensionMismatch { expected: self.dimension, actual: v.len() });
+            }
+            flat.extend_from_slice(v);
+        }
+        check(unsafe { sys::isl_pq_train(self.handle, flat.as_ptr(), vectors.len() as u64, self.dimension as u32) })
+    }
+    /// pq.rs:221-244
+    pub fn encode(&self, vector: &[f32]) -> CoreResult<Vec<u16>> {
+        let mut codes = vec![0u16; self.num_subquantizers()];
+        check(unsafe { sys::isl_pq_encode(self.handle, vector.as_ptr(), 1, vector.len() as u32, codes.as_mut_ptr()) })?;
+        Ok(codes)
+    }
+    /// Batched encode: `[n][dimension]` row-major -> `[n][m]` codes.
+    pub fn encode_batch(&self, vectors: &[f32], n: usize) -> CoreResult<Vec<u16>> {
+        let mut codes = vec![0u16; n * self.num_subquantizers()];
+        check(unsafe { sys::isl_pq_encode(self.handle, vectors.as_ptr(), n as u64, self.dimension as u32, codes.as_mut_ptr()) })?;
+        Ok(codes)
+    }
+    /// pq.rs:247-271
+    pub fn decode(&self, codes: &[u16]) -> CoreResult<Vec<f32>> {
+        let mut out = vec![0f32; self.dimension];
+        check(unsafe { sys::isl_pq_decode(self.handle, codes.as_ptr(), 1, codes.len() as u64, out.as_mut_ptr()) })?;
+        Ok(out)
+    }
+    /// pq.rs:275-304
+    pub fn asymmetric_distance(&self, query: &[f32], codes: &[u16]) -> CoreResult<f32> {
+        if codes.len() != self.num_subquantizers() {
+            return Err(CoreError::PQError("Codes length mismatch".into()));
+        }
+        let mut out = 0f32;
+        check(unsafe { sys::isl_pq_asymmetric_distance(self.handle, query.as_ptr(), query.len() as u32, codes.as_ptr(), 1, &mut out) })?;
+        Ok(out)
+    }
+    /// pq.rs:307-338: tables[m][ksub]
+    pub fn build_distance_tables(&self, query: &[f32]) -> CoreResult<Vec<Vec<f32>>> {
+        let m = self.num_subquantizers();
+        let mut ksub = 0u64;
+        check(unsafe { sys::isl_pq_get_codebooks(self.handle, ptr::null_mut(), &mut ksub) })?;
+        let mut flat = vec![0f32; m * ksub as usize];
+        check(unsafe { sys::isl_pq_build_tables(self.handle, query.as_ptr(), query.len() as u32, flat.as_mut_ptr()) })?;
+        Ok(flat.chunks(ksub as usize).map(|c| c.to_vec()).collect())
+    }
+    /// pq.rs:341-348 (host arithmetic: m table lookups, left fold, sqrt — too small to ship to the device)
+    pub fn table_distance(&self, tables: &[Vec<f32>], codes: &[u16]) -> f32 {
+        let mut s = 0f32;
+        for (t, &c) in tables.iter().zip(codes) {
+            s += t[c as usize];
+        }
+        s.sqrt()
+    }
+    pub fn to_bytes(&self) -> CoreResult<Vec<u8>> {
+        let mut len = 0u64;
+        check(unsafe { sys::isl_pq_to_bytes(self.handle, ptr::null_mut(), 0, &mut len) })?;
+        let mut out = vec![0u8; len as usize];
+        check(unsafe { sys::isl_pq_to_bytes(self.handle, out.as_mut_ptr(), len, &mut len) })?;
+        Ok(out)
+    }
+    pub fn from_bytes(bytes: &[u8]) -> CoreResult<Self> {
+        let mut h: *mut sys::IslPq = ptr::null_mut();
+        check(unsafe { sys::isl_pq_from_bytes(bytes.as_ptr(), bytes.len() as u64, &mut h) })?;
+        let dimension = unsafe { sys::isl_pq_dimension(h) } as usize;
+        Ok(Self { handle: h, dimension })
+    }
+    /// Attach this quantizer's codes to an index for the "PQ ADC traversal + exact rerank" search.
+    pub fn attach_to(&self, index: &mut LeannIndex, codes: &[u16]) -> CoreResult<()> {
+        check(unsafe { sys::isl_index_attach_pq(index.handle, self.handle, codes.as_ptr()) })
+    }
+}

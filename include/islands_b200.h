@@ -166,6 +166,9 @@ typedef struct isl_shard_record {
 int isl_abi_version(void);
 /* Thread-local message of the last failing call on this thread (String payloads of CoreError). */
 const char* isl_last_error(void);
+/* Numeric payload of the last failing call on this thread: ISL_DIM_MISMATCH -> (*a, *b) = (expected, actual);
+ * ISL_NODE_NOT_FOUND -> *a = the node id; otherwise zeros.  Lets a binding rebuild the full CoreError variant. */
+void isl_last_error_detail(uint64_t* a, uint64_t* b);
 /* Number of usable CUDA devices (0 => every compute call fails with ISL_CUDA_ERROR). */
 int isl_device_count(void);
 /* Launch bookkeeping for benchmarks: kernels launched by this library since the last reset. */

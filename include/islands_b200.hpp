@@ -14,6 +14,7 @@
 // CPU fallback.
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -39,7 +40,10 @@ enum class ErrorKind {
 // CoreError (error.rs:9-62): the variant is `kind`, the String payload is what().
 class CoreError : public std::runtime_error {
  public:
-  CoreError(ErrorKind k, const std::string& msg) : std::runtime_error(msg), kind(k) {}
+  CoreError(ErrorKind k, const std::string& msg) : std::runtime_error(msg), kind(k) {
+    isl_last_error_detail(&a, &b);  // DimensionMismatch{expected = a, actual = b}, NodeNotFound(a)
+  }
+  uint64_t a = 0, b = 0;
   ErrorKind kind;
 };
 
@@ -90,6 +94,20 @@ struct CsrGraph {  // leann.rs:193-208
   std::vector<uint64_t> node_offsets{0}, neighbors, levels, degree_counts;
   int64_t entry_point = ISL_NO_ENTRY;
   uint64_t max_level = 0, num_nodes = 0;
+  // CsrGraph::set_neighbors (leann.rs:256-293): same length overwrites, any other length rebuilds the arrays
+  void set_neighbors(uint64_t node_id, const std::vector<uint64_t>& nb) {
+    if (node_id >= num_nodes) return;
+    const uint64_t s = node_offsets[node_id], e = node_offsets[node_id + 1];
+    if (nb.size() == e - s) {
+      std::copy(nb.begin(), nb.end(), neighbors.begin() + s);
+    } else {
+      const int64_t delta = (int64_t)nb.size() - (int64_t)(e - s);
+      neighbors.erase(neighbors.begin() + s, neighbors.begin() + e);
+      neighbors.insert(neighbors.begin() + s, nb.begin(), nb.end());
+      for (uint64_t i = node_id + 1; i <= num_nodes; ++i) node_offsets[i] = (uint64_t)((int64_t)node_offsets[i] + delta);
+    }
+    if (node_id < degree_counts.size()) degree_counts[node_id] = nb.size();
+  }
 };
 
 using SearchResults = std::vector<std::pair<uint64_t, float>>;  // Vec<(u64, f32)>
@@ -118,6 +136,25 @@ class LeannIndex {
   bool is_empty() const { return len() == 0; }
   uint32_t dimension() const { return isl_index_dimension(h_); }
   uint64_t storage_bytes() const { return isl_index_storage_bytes(h_); }
+  // graph.set_neighbors (leann.rs:256-293) on the resident graph
+  void set_neighbors(uint64_t node_id, const std::vector<uint64_t>& new_neighbors) {
+    check(isl_index_set_neighbors(h_, node_id, new_neighbors.data(), new_neighbors.size()));
+  }
+  isl_build_stats last_build_stats() const {
+    isl_build_stats st{};
+    check(isl_index_last_build_stats(h_, &st));
+    return st;
+  }
+  // Sharded search (service.rs:777-801): collective over the ranks of `shard`; queries [nq][dim] row-major,
+  // the same on every rank; ids / dist come back as [nq][k] (padded with ISL_INVALID_ID / +inf).
+  void search_sharded(isl_shard* shard, uint64_t id_base, const std::vector<float>& queries, uint64_t nq, uint32_t k,
+                      uint32_t ef, std::vector<uint64_t>* ids, std::vector<float>* dist, std::vector<uint32_t>* count) const {
+    ids->assign(nq * k, ISL_INVALID_ID);
+    dist->assign(nq * k, 0.0f);
+    count->assign(nq, 0);
+    check(isl_index_search_sharded(h_, shard, id_base, queries.data(), nq, nq ? (uint32_t)(queries.size() / nq) : 0, k, ef,
+                                   ids->data(), dist->data(), count->data()));
+  }
 
   // LeannIndex::search / search_with_params (leann.rs:858-896)
   SearchResults search(const std::vector<float>& query, uint32_t k) const {

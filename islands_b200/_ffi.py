@@ -120,6 +120,7 @@ _VPP = C.POINTER(C.c_void_p)
 SIGNATURES = {
     "isl_abi_version": (C.c_int, []),
     "isl_last_error": (C.c_char_p, []),
+    "isl_last_error_detail": (None, [u64p, u64p]),
     "isl_device_count": (C.c_int, []),
     "isl_kernel_launch_count": (C.c_uint64, []),
     "isl_kernel_launch_count_reset": (None, []),

@@ -11,11 +11,34 @@
 namespace isl {
 
 static thread_local std::string t_last_error;
+static thread_local uint64_t t_err_a = 0, t_err_b = 0;  // payload of the last error (isl_last_error_detail)
 std::atomic<uint64_t> g_launch_count{0};
 
 void set_last_error(const std::string& msg) { t_last_error = msg; }
+
+// The numbers a CoreError variant carries (error.rs:9-62) travel beside the message: DimensionMismatch{expected,
+// actual} and NodeNotFound(id).  Every such message of this library is written "expected X, got Y" / names the id
+// first, so the payload is taken from the text in one place instead of at fifty call sites.
+static void capture_payload(isl_status st, const std::string& msg) {
+  t_err_a = t_err_b = 0;
+  if (st != ISL_DIM_MISMATCH && st != ISL_NODE_NOT_FOUND) return;
+  uint64_t v[2] = {0, 0};
+  int found = 0;
+  for (size_t i = 0; i < msg.size() && found < 2;) {
+    if (msg[i] >= '0' && msg[i] <= '9') {
+      uint64_t x = 0;
+      while (i < msg.size() && msg[i] >= '0' && msg[i] <= '9') x = x * 10 + (uint64_t)(msg[i++] - '0');
+      v[found++] = x;
+    } else {
+      ++i;
+    }
+  }
+  t_err_a = v[0];
+  t_err_b = st == ISL_DIM_MISMATCH ? v[1] : 0;
+}
 isl_status fail(isl_status st, const std::string& msg) {
   t_last_error = msg;
+  capture_payload(st, msg);
   return st;
 }
 isl_status cuda_fail(cudaError_t e, const char* what) {
@@ -313,6 +336,10 @@ extern "C" {
 
 int isl_abi_version(void) { return ISL_ABI_VERSION; }
 const char* isl_last_error(void) { return t_last_error.c_str(); }
+void isl_last_error_detail(uint64_t* a, uint64_t* b) {
+  if (a) *a = t_err_a;
+  if (b) *b = t_err_b;
+}
 int isl_device_count(void) {
   int c = 0;
   if (cudaGetDeviceCount(&c) != cudaSuccess) {

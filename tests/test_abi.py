@@ -135,7 +135,7 @@ def test_product_never_touches_the_oracle():
 
 
 def test_rust_sys_declarations_are_current_and_complete():
-    """bindings/rust/islands_b200_sys.rs (the `extern "C"` module of INTEGRATION.md §1) is generated from the
+    """bindings/rust/islands-b200-sys/src/lib.rs (the `extern "C"` module of INTEGRATION.md §1) is generated from the
     header: the committed file must be what scripts/gen_rust_sys.py produces now, and declare every symbol of
     the ctypes table (which test_header_library_and_table_agree ties to the header and the library)."""
     import importlib.util
@@ -153,3 +153,78 @@ def test_rust_sys_declarations_are_current_and_complete():
     declared = set(re.findall(r"pub fn (isl_\w+)\(", text))
     assert declared == set(_ffi.SIGNATURES)
     assert "pub struct IslLeannConfig" in text and "pub hub_percentile: f32" in text
+
+
+def test_rust_wrapper_uses_only_declared_symbols_with_the_right_arity():
+    """bindings/rust/islands-b200/src/lib.rs (the safe wrapper with the reference's signatures) cannot be compiled
+    here (no rustc): at least every `sys::isl_*` call it makes must name a function of the generated -sys crate
+    and pass as many arguments as that declaration takes, and every `sys::ISL_*` constant must exist."""
+    sys_text = open(os.path.join(ROOT, "bindings", "rust", "islands-b200-sys", "src", "lib.rs")).read()
+    decl = {m.group(1): (0 if not m.group(2).strip() else m.group(2).count(":"))
+            for m in re.finditer(r"pub fn (isl_\w+)\(([^)]*)\)", sys_text)}
+    consts = set(re.findall(r"pub const (ISL_\w+):", sys_text))
+    structs = set(re.findall(r"pub struct (Isl\w+)", sys_text))
+    text = open(os.path.join(ROOT, "bindings", "rust", "islands-b200", "src", "lib.rs")).read()
+    text = re.sub(r"//[^\n]*", "", text)
+    calls = 0
+    for m in re.finditer(r"sys::(isl_\w+)\s*\(", text):
+        name, i, depth, args, cur = m.group(1), m.end(), 1, 0, ""
+        assert name in decl, name
+        while depth:
+            ch = text[i]
+            depth += ch in "([{"
+            depth -= ch in ")]}"
+            if ch == "," and depth == 1:
+                args += bool(cur.strip())
+                cur = ""
+            elif depth:
+                cur += ch
+            i += 1
+        args += bool(cur.strip())
+        assert args == decl[name], (name, args, decl[name])
+        calls += 1
+    assert calls >= 40
+    for c in re.findall(r"sys::(ISL_\w+)", text):
+        assert c in consts, c
+    for s_ in re.findall(r"sys::(Isl\w+)", text):
+        assert s_ in structs, s_
+    # the reference surface the wrapper promises (src/core/mod.rs:60-99)
+    for needle in ("pub fn build<P: EmbeddingProvider>(&mut self, provider: &P, num_vectors: usize) -> CoreResult<()>",
+                   "pub fn search<P: EmbeddingProvider>(&self, query: &[f32], k: usize, provider: &P) -> CoreResult<Vec<(u64, f32)>>",
+                   "pub fn search_with_params<P: EmbeddingProvider>(&self, query: &[f32], k: usize, ef: usize, _provider: &P) -> CoreResult<Vec<(u64, f32)>>",
+                   "pub fn encode(&self, vector: &[f32]) -> CoreResult<Vec<u16>>", "pub fn decode(&self, codes: &[u16]) -> CoreResult<Vec<f32>>",
+                   "pub fn set_neighbors(&mut self, node_id: u64, new_neighbors: Vec<u64>)", "DimensionMismatch { expected: usize, actual: usize }"):
+        assert needle in text, needle
+
+
+def test_error_payloads_travel_beside_the_message():
+    """CoreError::DimensionMismatch{expected, actual} (error.rs:12-18): the numbers come back through
+    isl_last_error_detail, so a binding can rebuild the full variant (no device needed for this check)."""
+    import ctypes as C
+
+    from islands_b200 import DimensionMismatch, DistanceMetric, _ffi
+
+    with pytest.raises(DimensionMismatch):
+        DistanceMetric(1).calculate([1.0, 2.0, 3.0], [1.0, 2.0])  # distance.rs:39-44, checked before any device work
+    a, b = C.c_uint64(), C.c_uint64()
+    _ffi.load().isl_last_error_detail(C.byref(a), C.byref(b))
+    assert (a.value, b.value) == (3, 2)
+
+
+def test_csr_graph_set_neighbors_host_mirror():
+    """CsrGraph::set_neighbors (leann.rs:256-293): in place for equal length, rebuild otherwise, unknown node ignored."""
+    from islands_b200 import CsrGraph
+
+    g = CsrGraph()
+    g.add_node([], 0)
+    g.add_node([0], 0)
+    g.add_node([0, 1], 1)
+    g.set_neighbors(2, [1, 0])
+    assert list(g.get_neighbors(2)) == [1, 0] and list(g.node_offsets) == [0, 0, 1, 3]
+    g.set_neighbors(0, [1, 2])
+    assert list(g.get_neighbors(0)) == [1, 2] and list(g.get_neighbors(1)) == [0] and list(g.get_neighbors(2)) == [1, 0]
+    assert list(g.node_offsets) == [0, 2, 3, 5] and list(g.degree_counts) == [2, 1, 2]
+    g.set_neighbors(1, [])
+    assert list(g.node_offsets) == [0, 2, 2, 4] and list(g.get_neighbors(2)) == [1, 0]
+    g.set_neighbors(99, [0])
+    assert g.num_nodes == 3 and g.neighbors.size == 4
