@@ -210,7 +210,7 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
   const uint32_t u_cap_t = std::max<uint32_t>(32, round_up(maxdeg + 1, 32));
   const uint32_t u_cap_r = std::max<uint32_t>(32, round_up(ef, 32));
   SearchPlan plan, plan_r;  // lean traversal (MODE 3) and rerank (MODE 2 / phase 2)
-  ISL_TRY(plan_search_adc_traverse(ef, u_cap_t, m, pq->ksub, idx->sms, &plan));
+  ISL_TRY(plan_search_adc_traverse(ef, u_cap_t, m, pq->ksub, idx->codes8.p != nullptr, idx->sms, &plan));
   ISL_TRY(plan_search_rerank(idx->cfg.metric, idx->ld, ef, u_cap_r, idx->sms, &plan_r));
   const uint32_t vis_words = round_up((uint32_t)((idx->n + 31) / 32), 4);
   const uint32_t slots = (uint32_t)std::min<uint64_t>(std::max(plan.grid, plan_r.grid), nq);

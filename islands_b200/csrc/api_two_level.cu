@@ -4,6 +4,7 @@
 // restated on the CPU in oracle/orc_leann_search_two_level.  Parity is oracle<->GPU only.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "api_common.h"
 
@@ -72,7 +73,7 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
     const uint32_t u_cap_t = vector_hop ? 32u : std::max<uint32_t>(32, round_up(maxdeg2 + 1, 32));
     const uint32_t u_cap_r = std::max<uint32_t>(32, round_up(ef, 32));
     SearchPlan pt, pr;
-    ISL_TRY(plan_search_adc_traverse(ef, u_cap_t, m, pq->ksub, idx->sms, &pt));
+    ISL_TRY(plan_search_adc_traverse(ef, u_cap_t, m, pq->ksub, idx->codes8.p != nullptr, idx->sms, &pt));
     ISL_TRY(plan_search_rerank(idx->cfg.metric, idx->ld, ef, u_cap_r, idx->sms, &pr));
     const uint32_t vis_words2 = round_up((uint32_t)((idx->n + 31) / 32), 4);
     const uint32_t slots_t = (uint32_t)std::min<uint64_t>(pt.grid, nq), slots_r = (uint32_t)std::min<uint64_t>(pr.grid, nq);
@@ -94,7 +95,7 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
                                    (size_t)idx->dim * 4, nq, cudaMemcpyHostToDevice, st));
     ISL_CUDA_TRY(cudaMemsetAsync(sc->counters.p, 0, 4 * sizeof(unsigned int), st));
     ISL_CUDA_TRY(cudaEventRecord(sc->ev0, st));
-    const bool fused_lut = pt.lut_smem_floats != 0;  // tables built per query inside the traversal kernel
+    const bool fused_lut = pt.lut_smem_floats != 0 && !getenv("ISL_DEV_SEPARATE_LUT");  // tables built per query inside the traversal kernel
     if (!fused_lut) ISL_TRY(launch_pq_tables(pq->dev(), sc->q_stage.p, idx->ld, nq, sc->aux_f32.p, idx->sms, st));
     SearchArgs a{};
     a.vectors = idx->vectors.p;

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <mutex>
 
+#include "adc_traverse.cuh"
 #include "search_core.cuh"
 
 namespace isl {
@@ -70,10 +71,10 @@ isl_status launch_one(const SearchPlan& plan, const SearchArgs& args, uint32_t g
   return ISL_OK;
 }
 
-template <bool R_SMEM, int NR>
+template <bool R_SMEM>
 isl_status plan_lean(uint32_t ef, uint32_t u_cap, uint32_t pq_m, int sms, SearchPlan* plan) {
-  auto kern = leann_search_kernel<ACC_DOT, kCH, kStages, R_SMEM, 3, NR>;
-  const size_t smem = search_smem_bytes<kCH, kStages>(0, (R_SMEM && NR == 0) ? ef : 0, u_cap, plan->lut_smem_floats, 0, true) +
+  auto kern = leann_search_kernel<ACC_DOT, kCH, kStages, R_SMEM, 3, 0>;
+  const size_t smem = search_smem_bytes<kCH, kStages>(0, R_SMEM ? ef : 0, u_cap, plan->lut_smem_floats, 0, true) +
                       (R_SMEM ? search_smem_bytes_idc() : 0);
   if (smem > 226 * 1024) return fail(ISL_INVALID_ARGUMENT, "search: ef needs more than 226 KB of shared memory per warp");
   plan->novis_ok = R_SMEM && plan->lut_smem_floats != 0 && (pq_m == 16 || pq_m == 32);  // and n < kIdcMaxNodes (checked by the caller)
@@ -90,9 +91,36 @@ isl_status plan_lean(uint32_t ef, uint32_t u_cap, uint32_t pq_m, int sms, Search
   return ISL_OK;
 }
 
-template <bool R_SMEM, int NR>
+template <bool R_SMEM>
 isl_status launch_lean(const SearchPlan& plan, const SearchArgs& args, uint32_t grid, cudaStream_t st) {
-  leann_search_kernel<ACC_DOT, kCH, kStages, R_SMEM, 3, NR><<<grid, 32, plan.smem, st>>>(args);
+  leann_search_kernel<ACC_DOT, kCH, kStages, R_SMEM, 3, 0><<<grid, 32, plan.smem, st>>>(args);
+  count_launch();
+  ISL_CUDA_TRY(cudaGetLastError());
+  return ISL_OK;
+}
+
+// The register-bag traversal (adc_traverse.cuh): one-byte codes, m = 16 / 32, table in shared memory, ef <= 32 * NR.
+template <int NR>
+isl_status plan_bag(uint32_t ef, int sms, SearchPlan* plan) {
+  auto kern = adc_traverse_kernel<NR>;
+  const size_t smem = adc_traverse_smem_bytes(plan->lut_smem_floats, ef);
+  static std::once_flag once[64];
+  static cudaError_t once_result[64];
+  ISL_TRY(opt_in_smem(kern, once, once_result));
+  int per_sm = 0;
+  ISL_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+  if (per_sm < 1) return fail(ISL_CUDA_ERROR, "search: kernel does not fit on an SM");
+  plan->novis_ok = true;  // and n < kIdcMaxNodes (checked by the caller)
+  plan->smem = smem;
+  plan->ctas_per_sm = per_sm;
+  plan->grid = (uint32_t)(per_sm * sms);
+  plan->r_in_smem = true;
+  return ISL_OK;
+}
+
+template <int NR>
+isl_status launch_bag(const SearchPlan& plan, const SearchArgs& args, uint32_t grid, cudaStream_t st) {
+  adc_traverse_kernel<NR><<<grid, 32, plan.smem, st>>>(args);
   count_launch();
   ISL_CUDA_TRY(cudaGetLastError());
   return ISL_OK;
@@ -163,7 +191,8 @@ isl_status plan_search_adc(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_
   return plan_dispatch<2>(plan->acc, ef <= kEfSmemMax, ld, ef, u_cap, sms, plan);
 }
 
-isl_status plan_search_adc_traverse(uint32_t ef, uint32_t u_cap, uint32_t pq_m, uint32_t pq_ksub, int sms, SearchPlan* plan) {
+isl_status plan_search_adc_traverse(uint32_t ef, uint32_t u_cap, uint32_t pq_m, uint32_t pq_ksub, bool one_byte_codes, int sms,
+                                    SearchPlan* plan) {
   plan->acc = ACC_DOT;
   plan->two_level = true;
   plan->mode = 3;
@@ -171,19 +200,26 @@ isl_status plan_search_adc_traverse(uint32_t ef, uint32_t u_cap, uint32_t pq_m, 
   plan->lut_smem_floats = lut_floats <= kLutSmemMaxFloats ? lut_floats : 0;
   plan->aq_cap = 0;
   plan->aq_smem_entries = 0;
-  // register R: NR = 2 * ceil(ef / 64) entries per lane, up to ef = 512
-  plan->nr = ef <= 512 ? (int)(2 * ((ef + 63) / 64)) : 0;
-  switch (plan->nr) {
-    case 2: return plan_lean<true, 2>(ef, u_cap, pq_m, sms, plan);
-    case 4: return plan_lean<true, 4>(ef, u_cap, pq_m, sms, plan);
-    case 6: return plan_lean<true, 6>(ef, u_cap, pq_m, sms, plan);
-    case 8: return plan_lean<true, 8>(ef, u_cap, pq_m, sms, plan);
-    case 10: return plan_lean<true, 10>(ef, u_cap, pq_m, sms, plan);
-    case 12: return plan_lean<true, 12>(ef, u_cap, pq_m, sms, plan);
-    case 14: return plan_lean<true, 14>(ef, u_cap, pq_m, sms, plan);
-    case 16: return plan_lean<true, 16>(ef, u_cap, pq_m, sms, plan);
+  // register bag: NR = ceil(ef / 32) entries per lane (rounded up to an instantiated size), up to ef = 512
+  plan->nr = 0;
+  if (one_byte_codes && (pq_m == 16 || pq_m == 32) && plan->lut_smem_floats && ef <= 512) {
+    const int need = (int)((ef + 31) / 32);
+    const int sizes[] = {2, 4, 6, 8, 12, 16};
+    for (int sz : sizes)
+      if (need <= sz) {
+        plan->nr = sz;
+        break;
+      }
   }
-  return ef <= kEfSmemMax ? plan_lean<true, 0>(ef, u_cap, pq_m, sms, plan) : plan_lean<false, 0>(ef, u_cap, pq_m, sms, plan);
+  switch (plan->nr) {
+    case 2: return plan_bag<2>(ef, sms, plan);
+    case 4: return plan_bag<4>(ef, sms, plan);
+    case 6: return plan_bag<6>(ef, sms, plan);
+    case 8: return plan_bag<8>(ef, sms, plan);
+    case 12: return plan_bag<12>(ef, sms, plan);
+    case 16: return plan_bag<16>(ef, sms, plan);
+  }
+  return ef <= kEfSmemMax ? plan_lean<true>(ef, u_cap, pq_m, sms, plan) : plan_lean<false>(ef, u_cap, pq_m, sms, plan);
 }
 
 isl_status plan_search_rerank(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap, int sms, SearchPlan* plan) {
@@ -201,16 +237,14 @@ isl_status launch_search(const SearchPlan& plan, const SearchArgs& args, cudaStr
   const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(plan.grid, args.nq));
   if (plan.mode == 3) {
     switch (plan.nr) {
-      case 2: return launch_lean<true, 2>(plan, args, grid, st);
-      case 4: return launch_lean<true, 4>(plan, args, grid, st);
-      case 6: return launch_lean<true, 6>(plan, args, grid, st);
-      case 8: return launch_lean<true, 8>(plan, args, grid, st);
-      case 10: return launch_lean<true, 10>(plan, args, grid, st);
-      case 12: return launch_lean<true, 12>(plan, args, grid, st);
-      case 14: return launch_lean<true, 14>(plan, args, grid, st);
-      case 16: return launch_lean<true, 16>(plan, args, grid, st);
+      case 2: return launch_bag<2>(plan, args, grid, st);
+      case 4: return launch_bag<4>(plan, args, grid, st);
+      case 6: return launch_bag<6>(plan, args, grid, st);
+      case 8: return launch_bag<8>(plan, args, grid, st);
+      case 12: return launch_bag<12>(plan, args, grid, st);
+      case 16: return launch_bag<16>(plan, args, grid, st);
     }
-    return plan.r_in_smem ? launch_lean<true, 0>(plan, args, grid, st) : launch_lean<false, 0>(plan, args, grid, st);
+    return plan.r_in_smem ? launch_lean<true>(plan, args, grid, st) : launch_lean<false>(plan, args, grid, st);
   }
   if (plan.mode == 2) return launch_dispatch<2>(plan, args, grid, st);
   return plan.mode == 1 ? launch_dispatch<1>(plan, args, grid, st) : launch_dispatch<0>(plan, args, grid, st);

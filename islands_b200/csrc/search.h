@@ -99,7 +99,7 @@ struct SearchPlan {
   int acc = 0;            // accumulation kind (dist_pass.cuh)
   bool two_level = false;
   int mode = 0;           // 0 exact, 1 two-level (AQ promotion), 2 ADC traversal + exact rerank, 3 ADC traversal only
-  int nr = 0;             // MODE 3: result array in registers, nr entries per lane (0 = shared / global memory)
+  int nr = 0;             // MODE 3: the register-bag kernel (adc_traverse.cuh), nr entries per lane (0 = search_core.cuh, shared / global memory)
   bool novis_ok = false;  // MODE 3: the launch may run without the visited bitset (SearchArgs::novis)
   uint32_t lut_smem_floats = 0;  // PQ table staged in shared memory (0 => read from global/L2)
   uint32_t aq_smem_entries = 0;  // approximate queue in shared memory (0 => global/L2)
@@ -112,7 +112,8 @@ isl_status plan_search_adc(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_
                            uint32_t pq_ksub, int sms, SearchPlan* plan);
 // The two launches of "ADC traversal + exact rerank": the lean traversal (MODE 3, survivors out) and the
 // rerank of candidate lists (MODE 2, SearchArgs::phase = 2; no PQ table in shared memory).
-isl_status plan_search_adc_traverse(uint32_t ef, uint32_t u_cap, uint32_t pq_m, uint32_t pq_ksub, int sms, SearchPlan* plan);
+isl_status plan_search_adc_traverse(uint32_t ef, uint32_t u_cap, uint32_t pq_m, uint32_t pq_ksub, bool one_byte_codes, int sms,
+                                    SearchPlan* plan);
 isl_status plan_search_rerank(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap, int sms, SearchPlan* plan);
 isl_status plan_search_two_level(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap, uint32_t pq_m,
                                  uint32_t pq_ksub, uint32_t aq_cap, int sms, SearchPlan* plan);

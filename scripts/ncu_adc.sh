@@ -1,5 +1,5 @@
 #!/bin/bash
-# --set full capture of the lean ADC traversal kernel (MODE 3, register R) at 1M x 768 (run under gpurun,
+# --set full capture of the lean ADC traversal kernel (adc_traverse.cuh, register bag) at 1M x 768 (run under gpurun,
 # one GPU; the same command must have exited 0 without ncu first).  Report lands in gpurun_out/.
 set -u
 mkdir -p gpurun_out
@@ -10,6 +10,6 @@ tail -2 gpurun_out/adc_plain.log
 # probe_adc.py calls the search twice per ef: with statistics (visited bitset) and without (bitset-free): SKIP=1 captures
 # the second, SKIP=0 the first
 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-    -k regex:'leann_search_kernel.*3, *\(?i?n?t?\)?[2468]>' -s ${SKIP:-1} -c 1 -f -o gpurun_out/${OUT:-prof_adc} \
+    -k regex:'adc_traverse_kernel' -s ${SKIP:-1} -c 1 -f -o gpurun_out/${OUT:-prof_adc} \
     env python scripts/probe_adc.py > gpurun_out/adc_ncu.log 2>&1
 echo "ncu rc=$?"; tail -3 gpurun_out/adc_ncu.log
