@@ -4,7 +4,6 @@
 // restated on the CPU in oracle/orc_leann_search_two_level.  Parity is oracle<->GPU only.
 #include <algorithm>
 #include <cmath>
-#include <cstdlib>
 
 #include "api_common.h"
 
@@ -95,7 +94,7 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
                                    (size_t)idx->dim * 4, nq, cudaMemcpyHostToDevice, st));
     ISL_CUDA_TRY(cudaMemsetAsync(sc->counters.p, 0, 4 * sizeof(unsigned int), st));
     ISL_CUDA_TRY(cudaEventRecord(sc->ev0, st));
-    const bool fused_lut = pt.lut_smem_floats != 0 && !getenv("ISL_DEV_SEPARATE_LUT");  // tables built per query inside the traversal kernel
+    const bool fused_lut = pt.lut_smem_floats != 0;  // tables built per query inside the traversal kernel
     if (!fused_lut) ISL_TRY(launch_pq_tables(pq->dev(), sc->q_stage.p, idx->ld, nq, sc->aux_f32.p, idx->sms, st));
     SearchArgs a{};
     a.vectors = idx->vectors.p;
