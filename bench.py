@@ -89,12 +89,25 @@ def make_data(torch, dataset, n, nq, d, dev, seed=42, qseed=43):
     return x.contiguous(), q.contiguous()
 
 
-def ground_truth(torch, x, q, k, chunk=1024):
-    """Exact cosine top-k by brute force (measurement infrastructure, not the hot path)."""
-    xn = torch.nn.functional.normalize(x, dim=1)
+def ground_truth_scores(torch, x, q, k, rows=1 << 20):
+    """Exact cosine top-k by brute force (measurement infrastructure, not the hot path): similarities and ids.
+    The base vectors are streamed in blocks of `rows`, so a 12.5M-node shard needs no second copy of itself."""
     qn = torch.nn.functional.normalize(q, dim=1)
-    out = [(qn[s:s + chunk] @ xn.T).topk(k, dim=1).indices for s in range(0, q.shape[0], chunk)]
-    return torch.cat(out)
+    best_v = torch.full((q.shape[0], k), -float("inf"), device=q.device)
+    best_i = torch.zeros((q.shape[0], k), dtype=torch.int64, device=q.device)
+    for s in range(0, x.shape[0], rows):
+        xb = torch.nn.functional.normalize(x[s:s + rows], dim=1)
+        t = (qn @ xb.T).topk(min(k, xb.shape[0]), dim=1)
+        v = torch.cat([best_v, t.values], dim=1)
+        i = torch.cat([best_i, t.indices + s], dim=1)
+        sel = v.topk(k, dim=1)
+        best_v, best_i = sel.values, i.gather(1, sel.indices)
+        del xb, t
+    return best_v, best_i
+
+
+def ground_truth(torch, x, q, k):
+    return ground_truth_scores(torch, x, q, k)[1]
 
 
 def recall_at_k(torch, ids, gt):
@@ -194,18 +207,6 @@ def cpu_port_qps(orc, cfg, xh, off, nbrs, entry, qh, ef, threads, seconds):
     return m / dt, m, ids
 
 
-def ground_truth_scores(torch, x, q, k, chunk=1024):
-    """Like ground_truth, also returning the cosine similarities (for the cross-island merge)."""
-    xn = torch.nn.functional.normalize(x, dim=1)
-    qn = torch.nn.functional.normalize(q, dim=1)
-    vs, is_ = [], []
-    for s in range(0, q.shape[0], chunk):
-        t = (qn[s:s + chunk] @ xn.T).topk(k, dim=1)
-        vs.append(t.values)
-        is_.append(t.indices)
-    return torch.cat(vs), torch.cat(is_)
-
-
 def workload_config(a, n, d, nq, parts, ef):
     """`config` of the JSON line — the same dict in both arms (ours and --impl reference)."""
     return {
@@ -240,6 +241,11 @@ def calibrate_ef(recall_for, target, fixed=0):
 
 def main():
     a = parse_args()
+    # stdout carries exactly one line, the JSON result: everything else a library may print there (NCCL announces its
+    # version on stdout when the first communicator is created) goes to stderr
+    sys.stdout.flush()
+    result_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -323,7 +329,7 @@ def main():
         m = min(per_step, n_gt)
         rec = recall_at_k(torch, torch.from_numpy(r_ids[:m].astype(np.int64)).to(dev), gt[:m])
         sample = f"{per_step} of {nq} queries per step, ef={ef}, graph built by the GPU library in setup (untimed)"
-        print(json.dumps({
+        print(file=result_out, flush=True, *[json.dumps({
             "impl": "reference", "metric": metric_name, "value": qps, "unit": "queries/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -335,7 +341,7 @@ def main():
             "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
-        }))
+        })])
         return
 
     # ---- counters for the roofline (one untimed pass with per-query stats) ---------------------------
@@ -689,7 +695,7 @@ def main():
     if failures:
         line["parity_failures"] = failures
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), file=result_out, flush=True)
     if use_dist:
         dist.destroy_process_group()
     if failures:
