@@ -147,7 +147,14 @@ typedef struct isl_encoder_config {
   uint32_t type_vocab_size;
   float layer_norm_eps;
   int32_t normalize; /* EmbeddingConfig::normalize: L2-normalise the pooled vector */
+  int32_t precision; /* ISL_ENCODER_BF16 (default) or ISL_ENCODER_BF16X3 */
 } isl_encoder_config;
+/* GEMM operand precision of the recompute encoder.  BF16: activations and weights rounded to bf16 (f32 accumulate).
+ * BF16X3: split precision — every operand is carried as hi + lo bf16 and each product as hi.hi + hi.lo + lo.hi on the
+ * same tensor-core kernel (3x the FLOPs), activations stay f32 between the GEMMs: embeddings agree with an f32 forward
+ * to ~1e-6, for callers that need rank-level agreement with f32 embeddings (recall within 0.002). */
+#define ISL_ENCODER_BF16 0
+#define ISL_ENCODER_BF16X3 1
 
 typedef struct isl_index isl_index; /* LeannIndex + CsrGraph + resident vectors (leann.rs:193-208, :493-500) */
 typedef struct isl_pq isl_pq;       /* ProductQuantizer (pq.rs:116-129) */

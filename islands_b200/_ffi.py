@@ -79,6 +79,7 @@ class EncoderConfigStruct(C.Structure):
         ("type_vocab_size", C.c_uint32),
         ("layer_norm_eps", C.c_float),
         ("normalize", C.c_int32),
+        ("precision", C.c_int32),
     ]
 
 

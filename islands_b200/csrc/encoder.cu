@@ -35,6 +35,9 @@ struct isl_encoder {
   // workspace for `cap_tokens` tokens
   size_t cap_tokens = 0, cap_seqs = 0;
   isl::DevBuf<__nv_bfloat16> x, y, qkv, ctx, ffn;
+  // split-precision mode (cfg.precision == 1): f32 activations, [hi | hi | lo] bf16 GEMM inputs, [hi | lo | hi] weights
+  isl::DevBuf<__nv_bfloat16> w3, a3;
+  isl::DevBuf<float> xf, yf, qkvf, ffnf;
   isl::DevBuf<int32_t> tokens, lengths;
   isl::DevBuf<float> pooled;
   float last_ms = 0.0f;
@@ -616,6 +619,244 @@ pool_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ len
   for (uint32_t c = threadIdx.x; c < H; c += blockDim.x) out[(size_t)b * H + c] /= nrm;
 }
 
+
+// ---- split-precision mode (isl_encoder_config::precision == 1) ------------------------------------------------
+// Every activation x is carried as f32 and handed to the tensor cores as hi = bf16(x), lo = bf16(x - hi); a weight w
+// likewise.  x.w ~ hi.hi + hi.lo + lo.hi (the dropped lo.lo term is 2^-16 relative), and the three products are ONE
+// GEMM over a tripled K: the activation row is laid out [hi | hi | lo], the weight row [hi | lo | hi], so the same
+// tcgen05 kernel runs unchanged (bf16 operands, f32 accumulation in TMEM, f32 output).  ~3x the FLOPs of the bf16 mode
+// for embeddings that agree with an f32 forward to ~1e-6 — the mode for callers that need rank-level agreement with
+// f32 embeddings (north_star: recall within 0.002).
+__device__ __forceinline__ void split_store(float v, __nv_bfloat16* row, uint32_t K, uint32_t c) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  row[c] = hi;
+  row[K + c] = hi;
+  row[2 * K + c] = lo;
+}
+
+// weights: [N][K] f32 -> [N][3K] bf16 = [hi | lo | hi]
+__global__ void to_split3_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t N, size_t K) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < N * K; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / K, k = i % K;
+    const float v = src[i];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16* row = dst + n * 3 * K;
+    row[k] = hi;
+    row[K + k] = lo;
+    row[2 * K + k] = hi;
+  }
+}
+
+// activations: [T][K] f32 -> [T][3K] bf16 = [hi | hi | lo]
+__global__ void split_rows_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t T, uint32_t K) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < T * K; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t t = i / K;
+    split_store(src[i], dst + t * 3 * K, K, (uint32_t)(i % K));
+  }
+}
+
+// One warp per token: embeddings + LayerNorm -> f32 row and its split copy.
+__global__ void __launch_bounds__(128)
+embed_ln_acc_kernel(const int32_t* __restrict__ tokens, const float* __restrict__ word, const float* __restrict__ pos,
+                    const float* __restrict__ type0, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                    uint32_t T, uint32_t S, uint32_t H, uint32_t V, float eps, float* __restrict__ xf,
+                    __nv_bfloat16* __restrict__ a3) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= T) return;
+  int32_t tok = tokens[w];
+  if (tok < 0 || (uint32_t)tok >= V) tok = 0;
+  const float* we = word + (size_t)tok * H;
+  const float* pe = pos + (size_t)(w % S) * H;
+  float v[kMaxPerLane];
+  float sum = 0.0f;
+  const uint32_t per = H / 32;
+  for (uint32_t i = 0; i < per; ++i) {
+    const uint32_t c = i * 32 + lane;
+    v[i] = we[c] + pe[c] + type0[c];
+    sum += v[i];
+  }
+  const float mean = warp_sum(sum) / (float)H;
+  float var = 0.0f;
+  for (uint32_t i = 0; i < per; ++i) {
+    const float d = v[i] - mean;
+    var += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(var) / (float)H + eps);
+  for (uint32_t i = 0; i < per; ++i) {
+    const uint32_t c = i * 32 + lane;
+    const float y = (v[i] - mean) * rstd * ln_w[c] + ln_b[c];
+    xf[(size_t)w * H + c] = y;
+    split_store(y, a3 + (size_t)w * 3 * H, H, c);
+  }
+}
+
+// One warp per row: x <- LayerNorm(y + x) in f32 (the residual sum is formed here), plus the split copy of the new x.
+__global__ void __launch_bounds__(128)
+ln_res_acc_kernel(const float* __restrict__ y, float* __restrict__ xf, const float* __restrict__ ln_w,
+                  const float* __restrict__ ln_b, uint32_t T, uint32_t H, float eps, __nv_bfloat16* __restrict__ a3) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= T) return;
+  float v[kMaxPerLane];
+  float sum = 0.0f;
+  const uint32_t per = H / 32;
+  for (uint32_t i = 0; i < per; ++i) {
+    const uint32_t c = i * 32 + lane;
+    v[i] = y[(size_t)w * H + c] + xf[(size_t)w * H + c];
+    sum += v[i];
+  }
+  const float mean = warp_sum(sum) / (float)H;
+  float var = 0.0f;
+  for (uint32_t i = 0; i < per; ++i) {
+    const float d = v[i] - mean;
+    var += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(var) / (float)H + eps);
+  for (uint32_t i = 0; i < per; ++i) {
+    const uint32_t c = i * 32 + lane;
+    const float o = (v[i] - mean) * rstd * ln_w[c] + ln_b[c];
+    xf[(size_t)w * H + c] = o;
+    split_store(o, a3 + (size_t)w * 3 * H, H, c);
+  }
+}
+
+// attention_kernel on f32 Q / K / V (the f32 output of the QKV GEMM); the context rows leave as split bf16.
+__global__ void __launch_bounds__(128)
+attention_acc_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ lengths, uint32_t S, uint32_t H,
+                     __nv_bfloat16* __restrict__ ctx3) {
+  extern __shared__ __align__(16) float att_smem[];
+  const uint32_t b = blockIdx.x, h = blockIdx.y;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+  const uint32_t len = min((uint32_t)max(lengths[b], 0), S);
+  float* Ks = att_smem;                           // [S][68]
+  float* Vs = Ks + (size_t)S * kAttKStride;       // [S][64]
+  float* qs = Vs + (size_t)S * 64;                // [warps][4][64]
+  float* ps = qs + warps * kAttRows * 64;         // [warps][S][4]
+  const size_t row_stride = 3 * (size_t)H;
+  const float* base = qkv + (size_t)b * S * row_stride + h * 64;
+  for (uint32_t i = threadIdx.x; i < len * 32; i += blockDim.x) {
+    const uint32_t j = i >> 5, c = (i & 31) * 2;
+    *reinterpret_cast<float2*>(Ks + j * kAttKStride + c) = *reinterpret_cast<const float2*>(base + j * row_stride + H + c);
+    *reinterpret_cast<float2*>(Vs + j * 64 + c) = *reinterpret_cast<const float2*>(base + j * row_stride + 2 * H + c);
+  }
+  __syncthreads();
+  float* q = qs + warp * kAttRows * 64;
+  float* p = ps + (size_t)warp * S * kAttRows;
+  for (uint32_t i0 = warp * kAttRows; i0 < S; i0 += warps * kAttRows) {
+    if (i0 >= len) {  // a whole group of padded rows
+      for (uint32_t r = 0; r < kAttRows && i0 + r < S; ++r) {
+        __nv_bfloat16* row = ctx3 + ((size_t)b * S + i0 + r) * 3 * H;
+        split_store(0.0f, row, H, h * 64 + lane * 2);
+        split_store(0.0f, row, H, h * 64 + lane * 2 + 1);
+      }
+      continue;
+    }
+    __syncwarp();
+#pragma unroll
+    for (uint32_t r = 0; r < kAttRows; ++r) {
+      float2 q2 = make_float2(0.0f, 0.0f);
+      if (i0 + r < S) q2 = *reinterpret_cast<const float2*>(base + (i0 + r) * row_stride + lane * 2);
+      *reinterpret_cast<float2*>(q + r * 64 + lane * 2) = make_float2(q2.x * 0.125f, q2.y * 0.125f);  // 1 / sqrt(64)
+    }
+    __syncwarp();
+    float mx[kAttRows];
+#pragma unroll
+    for (uint32_t r = 0; r < kAttRows; ++r) mx[r] = -INFINITY;
+    for (uint32_t j = lane; j < len; j += 32) {
+      float acc[kAttRows] = {0.0f, 0.0f, 0.0f, 0.0f};
+      const float4* k4 = reinterpret_cast<const float4*>(Ks + j * kAttKStride);
+#pragma unroll
+      for (uint32_t dg = 0; dg < 16; ++dg) {
+        const float4 kk = k4[dg];
+#pragma unroll
+        for (uint32_t r = 0; r < kAttRows; ++r) {
+          const float4 qq = *reinterpret_cast<const float4*>(q + r * 64 + dg * 4);
+          acc[r] = fmaf(qq.x, kk.x, acc[r]);
+          acc[r] = fmaf(qq.y, kk.y, acc[r]);
+          acc[r] = fmaf(qq.z, kk.z, acc[r]);
+          acc[r] = fmaf(qq.w, kk.w, acc[r]);
+        }
+      }
+      *reinterpret_cast<float4*>(p + j * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+#pragma unroll
+      for (uint32_t r = 0; r < kAttRows; ++r) mx[r] = fmaxf(mx[r], acc[r]);
+    }
+    float den[kAttRows];
+#pragma unroll
+    for (uint32_t r = 0; r < kAttRows; ++r) {
+      mx[r] = warp_max(mx[r]);
+      den[r] = 0.0f;
+    }
+    for (uint32_t j = lane; j < len; j += 32) {
+      float4 e = *reinterpret_cast<float4*>(p + j * 4);
+      e.x = expf(e.x - mx[0]);
+      e.y = expf(e.y - mx[1]);
+      e.z = expf(e.z - mx[2]);
+      e.w = expf(e.w - mx[3]);
+      *reinterpret_cast<float4*>(p + j * 4) = e;
+      den[0] += e.x;
+      den[1] += e.y;
+      den[2] += e.z;
+      den[3] += e.w;
+    }
+#pragma unroll
+    for (uint32_t r = 0; r < kAttRows; ++r) den[r] = warp_sum(den[r]);
+    __syncwarp();
+    float o[kAttRows][2];
+#pragma unroll
+    for (uint32_t r = 0; r < kAttRows; ++r) o[r][0] = o[r][1] = 0.0f;
+#pragma unroll 4
+    for (uint32_t j = 0; j < len; ++j) {
+      const float4 pj = *reinterpret_cast<const float4*>(p + j * 4);
+      const float2 v2 = *reinterpret_cast<const float2*>(Vs + j * 64 + lane * 2);
+      o[0][0] = fmaf(pj.x, v2.x, o[0][0]);
+      o[0][1] = fmaf(pj.x, v2.y, o[0][1]);
+      o[1][0] = fmaf(pj.y, v2.x, o[1][0]);
+      o[1][1] = fmaf(pj.y, v2.y, o[1][1]);
+      o[2][0] = fmaf(pj.z, v2.x, o[2][0]);
+      o[2][1] = fmaf(pj.z, v2.y, o[2][1]);
+      o[3][0] = fmaf(pj.w, v2.x, o[3][0]);
+      o[3][1] = fmaf(pj.w, v2.y, o[3][1]);
+    }
+#pragma unroll
+    for (uint32_t r = 0; r < kAttRows; ++r) {
+      if (i0 + r >= S) continue;
+      const bool live = i0 + r < len;
+      const float inv = live ? 1.0f / den[r] : 0.0f;
+      __nv_bfloat16* row = ctx3 + ((size_t)b * S + i0 + r) * 3 * H;
+      split_store(o[r][0] * inv, row, H, h * 64 + lane * 2);
+      split_store(o[r][1] * inv, row, H, h * 64 + lane * 2 + 1);
+    }
+  }
+}
+
+// pool_kernel on the f32 residual stream.
+__global__ void __launch_bounds__(256)
+pool_f32_kernel(const float* __restrict__ x, const int32_t* __restrict__ lengths, uint32_t S, uint32_t H, int normalize,
+                float* __restrict__ out) {
+  __shared__ float red[8];
+  const uint32_t b = blockIdx.x;
+  const uint32_t len = min((uint32_t)max(lengths[b], 0), S);
+  const float denom = fmaxf((float)len, 1e-9f);
+  float sq = 0.0f;
+  for (uint32_t c = threadIdx.x; c < H; c += blockDim.x) {
+    float s = 0.0f;
+    for (uint32_t i = 0; i < len; ++i) s += x[((size_t)b * S + i) * H + c];
+    s /= denom;
+    out[(size_t)b * H + c] = s;
+    sq += s * s;
+  }
+  if (!normalize) return;
+  sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  float tot = 0.0f;
+  for (uint32_t i = 0; i < (blockDim.x >> 5); ++i) tot += red[i];
+  const float nrm = fmaxf(sqrtf(tot), 1e-12f);
+  for (uint32_t c = threadIdx.x; c < H; c += blockDim.x) out[(size_t)b * H + c] /= nrm;
+}
+
 // ---- TMA descriptors + GEMM launch ----------------------------------------------------------
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -707,6 +948,8 @@ isl_status validate_cfg(const isl_encoder_config* c) {
     return fail(ISL_INVALID_CONFIG, "head dimension must be 64 (hidden_size == 64 * num_heads)");
   if (c->intermediate_size == 0 || c->intermediate_size % 64 != 0)
     return fail(ISL_INVALID_CONFIG, "intermediate_size must be a multiple of 64");
+  if (c->precision != ISL_ENCODER_BF16 && c->precision != ISL_ENCODER_BF16X3)
+    return fail(ISL_INVALID_CONFIG, "precision must be ISL_ENCODER_BF16 (0) or ISL_ENCODER_BF16X3 (1)");
   if (c->num_layers == 0 || c->vocab_size == 0 || c->max_position == 0 || c->type_vocab_size == 0)
     return fail(ISL_INVALID_CONFIG, "num_layers, vocab_size, max_position and type_vocab_size must be > 0");
   return ISL_OK;
@@ -715,12 +958,21 @@ isl_status validate_cfg(const isl_encoder_config* c) {
 isl_status ensure_workspace(isl_encoder* e, size_t seqs, size_t S) {
   const size_t T = seqs * S, H = e->cfg.hidden_size, I = e->cfg.intermediate_size;
   if (T > e->cap_tokens) {
-    ISL_CUDA_TRY(e->x.alloc(T * H));
-    ISL_CUDA_TRY(e->y.alloc(T * H));
-    ISL_CUDA_TRY(e->qkv.alloc(T * 3 * H));
-    ISL_CUDA_TRY(e->ctx.alloc(T * H));
-    ISL_CUDA_TRY(e->ffn.alloc(T * I));
+    if (e->cfg.precision != 1) {
+      ISL_CUDA_TRY(e->x.alloc(T * H));
+      ISL_CUDA_TRY(e->y.alloc(T * H));
+      ISL_CUDA_TRY(e->qkv.alloc(T * 3 * H));
+      ISL_CUDA_TRY(e->ctx.alloc(T * H));
+      ISL_CUDA_TRY(e->ffn.alloc(T * I));
+    }
     ISL_CUDA_TRY(e->tokens.alloc(T));
+    if (e->cfg.precision == 1) {
+      ISL_CUDA_TRY(e->xf.alloc(T * H));
+      ISL_CUDA_TRY(e->yf.alloc(T * H));
+      ISL_CUDA_TRY(e->qkvf.alloc(T * 3 * H));
+      ISL_CUDA_TRY(e->ffnf.alloc(T * I));
+      ISL_CUDA_TRY(e->a3.alloc(T * 3 * std::max(H, I)));
+    }
     e->cap_tokens = T;
   }
   if (seqs > e->cap_seqs) {
@@ -731,9 +983,51 @@ isl_status ensure_workspace(isl_encoder* e, size_t seqs, size_t S) {
   return ISL_OK;
 }
 
+// The split-precision forward: same layer recipe, f32 activations, every GEMM over a tripled K (see above).
+isl_status forward_device_split(isl_encoder* e, const int32_t* d_tokens, const int32_t* d_lengths, size_t seqs, size_t S,
+                                float* d_out) {
+  const Layout l = make_layout(e->cfg);
+  const uint32_t H = l.H, I = l.I;
+  const uint32_t T = (uint32_t)(seqs * S);
+  cudaStream_t st = e->stream;
+  const float* P = e->params.p;
+  const float eps = e->cfg.layer_norm_eps;
+  const uint32_t row_blocks = (T + 3) / 4;
+  embed_ln_acc_kernel<<<row_blocks, 128, 0, st>>>(d_tokens, P + l.word, P + l.pos, P + l.type, P + l.emb_ln_w, P + l.emb_ln_b,
+                                                 T, (uint32_t)S, H, l.V, eps, e->xf.p, e->a3.p);
+  count_launch();
+  const size_t att_smem = ((size_t)S * kAttKStride + (size_t)S * 64 + 4 * kAttRows * 64 + 4 * (size_t)S * kAttRows) * sizeof(float);
+  ISL_CUDA_TRY(cudaFuncSetAttribute(attention_acc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  for (uint32_t layer = 0; layer < l.L; ++layer) {
+    const float* lp = P + l.layers + (size_t)layer * l.per_layer;
+    const __nv_bfloat16* gw = e->w3.p + (size_t)layer * 3 * l.g_per_layer;
+    ISL_TRY(launch_gemm_bf16(e->a3.p, gw + 3 * l.g_qkv, (int)T, (int)(3 * H), (int)(3 * H), lp + l.qkv_b, nullptr, gemm::EPI_NONE,
+                             nullptr, e->qkvf.p, e->sms, st));
+    attention_acc_kernel<<<dim3((uint32_t)seqs, e->cfg.num_heads), 128, att_smem, st>>>(e->qkvf.p, d_lengths, (uint32_t)S, H, e->a3.p);
+    count_launch();
+    ISL_TRY(launch_gemm_bf16(e->a3.p, gw + 3 * l.g_ao, (int)T, (int)H, (int)(3 * H), lp + l.ao_b, nullptr, gemm::EPI_NONE, nullptr,
+                             e->yf.p, e->sms, st));
+    ln_res_acc_kernel<<<row_blocks, 128, 0, st>>>(e->yf.p, e->xf.p, lp + l.ln1_w, lp + l.ln1_b, T, H, eps, e->a3.p);
+    count_launch();
+    ISL_TRY(launch_gemm_bf16(e->a3.p, gw + 3 * l.g_f1, (int)T, (int)I, (int)(3 * H), lp + l.f1_b, nullptr, gemm::EPI_GELU, nullptr,
+                             e->ffnf.p, e->sms, st));
+    split_rows_kernel<<<1184, 256, 0, st>>>(e->ffnf.p, e->a3.p, T, I);
+    count_launch();
+    ISL_TRY(launch_gemm_bf16(e->a3.p, gw + 3 * l.g_f2, (int)T, (int)H, (int)(3 * I), lp + l.f2_b, nullptr, gemm::EPI_NONE, nullptr,
+                             e->yf.p, e->sms, st));
+    ln_res_acc_kernel<<<row_blocks, 128, 0, st>>>(e->yf.p, e->xf.p, lp + l.ln2_w, lp + l.ln2_b, T, H, eps, e->a3.p);
+    count_launch();
+  }
+  pool_f32_kernel<<<(uint32_t)seqs, 256, 0, st>>>(e->xf.p, d_lengths, (uint32_t)S, H, e->cfg.normalize, d_out);
+  count_launch();
+  ISL_CUDA_TRY(cudaGetLastError());
+  return ISL_OK;
+}
+
 // Forward of `seqs` sequences of S tokens resident on the device; d_out [seqs][H] f32.
 isl_status forward_device(isl_encoder* e, const int32_t* d_tokens, const int32_t* d_lengths, size_t seqs, size_t S,
                           float* d_out) {
+  if (e->cfg.precision == 1) return forward_device_split(e, d_tokens, d_lengths, seqs, S, d_out);
   const Layout l = make_layout(e->cfg);
   const uint32_t H = l.H, I = l.I;
   const uint32_t T = (uint32_t)(seqs * S);
@@ -845,6 +1139,15 @@ isl_status refresh_bf16(isl_encoder* e) {
       to_bf16_kernel<<<1184, 256, 0, e->stream>>>(lp + pt.src, gw + pt.dst, pt.cnt);
       count_launch();
     }
+    if (e->cfg.precision == 1) {  // [hi | lo | hi] rows for the split-precision GEMMs
+      __nv_bfloat16* g3 = e->w3.p + (size_t)layer * 3 * l.g_per_layer;
+      const struct { size_t src, dst, n, k; } p3[4] = {
+          {l.qkv_w, l.g_qkv, 3 * H, H}, {l.ao_w, l.g_ao, H, H}, {l.f1_w, l.g_f1, I, H}, {l.f2_w, l.g_f2, H, I}};
+      for (const auto& pt : p3) {
+        to_split3_weight_kernel<<<1184, 256, 0, e->stream>>>(lp + pt.src, g3 + 3 * pt.dst, pt.n, pt.k);
+        count_launch();
+      }
+    }
   }
   ISL_CUDA_TRY(cudaGetLastError());
   ISL_CUDA_TRY(cudaStreamSynchronize(e->stream));
@@ -869,6 +1172,7 @@ isl_status isl_encoder_config_default(isl_encoder_config* c) {
   c->type_vocab_size = 2;
   c->layer_norm_eps = 1e-12f;
   c->normalize = 1;  // EmbeddingConfig::normalize (candle_provider.rs:477)
+  c->precision = ISL_ENCODER_BF16;
   return ISL_OK;
 }
 
@@ -885,6 +1189,7 @@ isl_status isl_encoder_new(const isl_encoder_config* cfg, isl_encoder** out) {
   const Layout l = make_layout(e->cfg);
   ISL_CUDA_TRY(e->params.alloc(l.total));
   ISL_CUDA_TRY(e->wbf16.alloc(l.g_total));
+  if (e->cfg.precision == 1) ISL_CUDA_TRY(e->w3.alloc(3 * l.g_total));
   ISL_CUDA_TRY(cudaMemsetAsync(e->params.p, 0, e->params.bytes(), e->stream));
   ISL_CUDA_TRY(cudaStreamSynchronize(e->stream));
   e->n_gemm = l.g_total;

@@ -89,8 +89,9 @@ def test_reference_pq_behaviour(gpu_lib, orc):
 
 
 def test_train_matches_oracle_kmeans(gpu_lib, orc):
-    """Same splitmix64 stream on both sides -> identical codebooks (the reference's StdRng is not
-    reproduced: statistical parity only)."""
+    """A seeded `train` draws from the reference's own generator on both sides — `StdRng::seed_from_u64` of rand 0.8.5
+    (ChaCha12; pq.rs:190-193), restated in csrc/std_rng.h and, independently, in the oracle — so the codebooks are
+    bit-identical, not merely statistically alike (tests/test_std_rng.py pins the generator itself)."""
     from islands_b200 import PQConfig, ProductQuantizer
 
     rng = np.random.RandomState(5)

@@ -186,3 +186,36 @@ def test_recompute_with_rerank_limit(gpu_lib):
     assert np.array_equal(dist_a.view(np.uint32), dist_b.view(np.uint32))
     for f in ("n_hop", "n_edge", "n_adc", "n_rerank"):
         assert np.array_equal(getattr(st_a, f), getattr(st_b, f)), f
+
+
+def test_split_precision_recompute_meets_the_recall_bar(gpu_lib):
+    """north_star: "recall@10 must agree within 0.002 wherever bf16 recompute is used".  Same adversarial token table
+    as above (10th / 11th neighbour 3e-4 apart): with the encoder in split precision (ISL_ENCODER_BF16X3: bf16 tensor-core
+    products hi.hi + hi.lo + lo.hi, f32 activations) the recompute search agrees with the search over the fp32 oracle
+    embeddings — counters identical, recall within 0.002, distances within 2e-5."""
+    from islands_b200 import Encoder, EncoderConfig
+    from oracle.encoder_oracle import bert_embed
+
+    n, nq, S, k, ef = 3000, 2000, 16, 10, 64
+    rng = np.random.RandomState(11)
+    cfg_e = EncoderConfig(vocab_size=2000, hidden_size=128, num_layers=2, num_heads=2, intermediate_size=512, max_position=32,
+                          precision=1)
+    enc = Encoder(cfg_e).init_random(seed=3, stddev=0.08)
+    (tok, ln), (qtok, qln) = _token_table(rng, n, nq, S, 2000, 150)
+    sd = enc.state_dict()
+    vectors, queries = bert_embed(sd, cfg_e, tok, ln), bert_embed(sd, cfg_e, qtok, qln)
+    index, pq = _index_over(vectors, n)
+    ids_a, dist_a, cnt_a, st_a = index.search_adc_rerank_batch(queries, k, ef, stats=True)     # stored fp32 oracle vectors
+    index.set_recompute(enc, tok, ln)
+    ids_b, dist_b, cnt_b, st_b = index.search_adc_recompute_batch(queries, k, ef, stats=True)  # split-precision recompute
+    for f in ("n_hop", "n_edge", "n_adc", "n_rerank"):
+        assert np.array_equal(getattr(st_a, f), getattr(st_b, f)), f
+    vn = vectors / np.linalg.norm(vectors, axis=1, keepdims=True)
+    qn = queries / np.linalg.norm(queries, axis=1, keepdims=True)
+    gt = np.argsort(-(qn @ vn.T), axis=1, kind="stable")[:, :k]
+    ra, rb = _recall(ids_a, gt, k), _recall(ids_b, gt, k)
+    assert ra > 0.9
+    assert abs(ra - rb) <= 0.002, (ra, rb)
+    same = ids_a == ids_b
+    assert same.mean() > 0.99, same.mean()
+    assert np.abs(dist_a[same] - dist_b[same]).max() < 2e-5

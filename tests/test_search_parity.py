@@ -114,3 +114,41 @@ def test_search_errors(gpu_lib, orc):
     prop = LeannIndex.from_csr(LeannConfig(prune_ratio=0.5, pruning_strategy=2), v, off, nbrs, levels, entry)
     with pytest.raises(InvalidConfig):
         prop.search(v[0], 5)
+
+
+def test_search_100k_x_768_baseline_config0(gpu_lib, orc):
+    """BASELINE configs[0]: 100k random 768-d f32 vectors, M=30 (m0=60), efSearch=64, top-10 — the reference's own
+    CPU bench shape.  The graph is built on the GPU (rounds of 1024), adopted through from_csr, and searched by the GPU
+    and by the oracle: ids and distance bits equal on 1000 queries; the oracle's construction twin reproduces the
+    graph of a 6000-node prefix bit for bit (the whole 100k build is minutes of CPU: bench.py times a larger sample)."""
+    import os
+
+    from islands_b200 import LeannConfig, LeannIndex
+
+    n, d, nq, k, ef = 100_000, 768, 1000, 10, 64
+    rng = np.random.RandomState(42)
+    v = uniform(rng, n, d)
+    q = uniform(np.random.RandomState(43), nq, d)
+    cfg = LeannConfig()
+    built = LeannIndex(cfg)
+    built.build(v, n, seed=7, batch=1024)
+    g = built.graph
+    assert g.num_nodes == n and int(np.diff(g.node_offsets.astype(np.int64)).max()) <= cfg.m0
+    idx = LeannIndex.from_csr(cfg, v, g.node_offsets, g.neighbors, g.levels, g.entry_point)
+    ids, dist, cnt, st = idx.search_batch(q, k, ef, stats=True)
+    threads = os.cpu_count() or 1
+    o_ids, o_dist, o_cnt, o_st = orc.leann_search(cfg._s, v, g.node_offsets, g.neighbors, g.entry_point, q, k, ef, threads=threads, stats=True)
+    assert np.array_equal(cnt, o_cnt) and np.array_equal(ids, o_ids)
+    assert np.array_equal(dist.view(np.uint32), o_dist.view(np.uint32))
+    for f in ("n_hop", "n_edge", "n_dist"):
+        assert np.array_equal(getattr(st, f), o_st[f]), f
+    b_ids, b_dist, _ = built.search_batch(q, k, ef)  # the handle that built the graph answers the same
+    assert np.array_equal(b_ids, ids) and np.array_equal(b_dist.view(np.uint32), dist.view(np.uint32))
+    ns = 6000
+    small = LeannIndex(cfg)
+    small.build(v[:ns], ns, levels=g.levels[:ns], batch=1024)
+    off, nbrs, entry, _ = orc.leann_build(cfg._s, v[:ns], g.levels[:ns], batch=1024, threads=threads)
+    sg = small.graph
+    assert np.array_equal(sg.node_offsets, off) and np.array_equal(sg.neighbors, nbrs) and sg.entry_point == entry
+    for h in (built, idx, small):
+        h.free()
