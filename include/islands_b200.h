@@ -411,6 +411,15 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
                                           uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* out_ids,
                                           float* out_dist, uint32_t* out_count,
                                           isl_search_stats* stats_or_null);
+/* LeannIndex::search_with_params with the attached encoder as the EmbeddingProvider, exactly as the reference runs it
+ * (leann.rs:899-988): every hop asks the provider for the embeddings of its unvisited neighbours
+ * (compute_embeddings_batch, :947-950) and scores them with the exact metric; no stored vectors and no PQ are involved.
+ * The hops of all queries of the batch advance in lockstep, so one encoder pass serves the whole frontier of the batch
+ * (docs/leann-specification.md:364-394).  Results equal isl_index_search over an index that stores the encoder's
+ * outputs, bit for bit.  Cost: one encoder forward over the batch's frontier per hop. */
+isl_status isl_index_search_recompute(const isl_index* idx, const float* queries, uint64_t nq, uint32_t query_dim,
+                                      uint32_t k, uint32_t ef, uint64_t* out_ids, float* out_dist, uint32_t* out_count,
+                                      isl_search_stats* stats_or_null);
 /* "PQ ADC traversal + exact rerank" and its recompute form: give an exact distance (and, with recompute, an
  * encoder pass) only to the `limit` survivors with the best table distance instead of all ef — the
  * traversal stays wide, the expensive half shrinks (the role of the rerank ratio `a` of

@@ -201,6 +201,7 @@ SIGNATURES = {
     "isl_index_set_recompute": (C.c_int, [_VP, _VP, i32p, i32p, C.c_uint32]),
     "isl_index_drop_vectors": (C.c_int, [_VP]),
     "isl_index_search_adc_recompute": (C.c_int, [_VP, f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u64p, f32p, u32p, _SSP]),
+    "isl_index_search_recompute": (C.c_int, [_VP, f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u64p, f32p, u32p, _SSP]),
     "isl_index_last_recompute": (C.c_int, [_VP, u64p, f32p, f32p, f32p]),
     "isl_index_set_hub_cache": (C.c_int, [_VP, C.c_uint64]),
     "isl_index_set_rerank_limit": (C.c_int, [_VP, C.c_uint32]),

@@ -733,6 +733,22 @@ def _adc_recompute(self, queries, k, ef, stats=False):
     return (ids, dist, cnt, SearchStats(st)) if stats else (ids, dist, cnt)
 
 
+def _recompute_exact(self, queries, k, ef, stats=False):
+    """LeannIndex::search_with_params with the encoder as the provider, hop by hop (isl_index_search_recompute;
+    leann.rs:899-988 with compute_embeddings_batch on every hop's frontier, :947-950)."""
+    q = _f32(queries)
+    q = q.reshape(1, -1) if q.ndim == 1 else q
+    nq, qd = q.shape
+    ids = np.empty((nq, k), np.uint64)
+    dist = np.empty((nq, k), np.float32)
+    cnt = np.empty(nq, np.uint32)
+    st = np.zeros(nq, _STATS_DTYPE) if stats else None
+    _check(_ffi.load().isl_index_search_recompute(self._h, _ptr(q, f32p), nq, qd, k, int(ef), _ptr(ids, u64p),
+                                                  _ptr(dist, f32p), _ptr(cnt, u32p),
+                                                  st.ctypes.data_as(C.POINTER(SearchStatsStruct)) if stats else None))
+    return (ids, dist, cnt, SearchStats(st)) if stats else (ids, dist, cnt)
+
+
 def _last_recompute(self):
     u = C.c_uint64()
     a, b, c = C.c_float(), C.c_float(), C.c_float()
@@ -824,6 +840,7 @@ HnswGraph.from_bytes = classmethod(_hnsw_from_bytes)
 LeannIndex.set_recompute = _set_recompute
 LeannIndex.drop_vectors = _drop_vectors
 LeannIndex.search_adc_recompute_batch = _adc_recompute
+LeannIndex.search_recompute_batch = _recompute_exact
 LeannIndex.last_recompute = _last_recompute
 LeannIndex.set_hub_cache = _set_hub_cache
 

@@ -219,3 +219,37 @@ def test_split_precision_recompute_meets_the_recall_bar(gpu_lib):
     same = ids_a == ids_b
     assert same.mean() > 0.99, same.mean()
     assert np.abs(dist_a[same] - dist_b[same]).max() < 2e-5
+
+
+@pytest.mark.parametrize("metric,prune", [(0, 0.0), (1, 0.0), (0, 0.4)])
+def test_per_hop_recompute_equals_the_stored_vector_search(gpu_lib, metric, prune):
+    """The reference's own recompute semantics (leann.rs:899-988): every hop fetches the embeddings of its unvisited
+    neighbours from the provider (compute_embeddings_batch, :947-950) — here the encoder over the nodes' token rows, one
+    pass per lockstep hop of the whole batch.  An index that STORES the encoder's outputs, searched by the plain exact
+    kernel, must give the same ids, the same distance bits and the same traversal counters: the provider is the only
+    difference.  After drop_vectors the per-hop search is all that is left, and it still answers the same."""
+    from islands_b200 import Encoder, EncoderConfig, LeannConfig, LeannIndex
+
+    n, nq, S, k, ef = 2000, 96, 12, 10, 40
+    rng = np.random.RandomState(5)
+    enc = Encoder(EncoderConfig(vocab_size=1500, hidden_size=128, num_layers=2, num_heads=2, intermediate_size=256,
+                                max_position=32)).init_random(seed=9, stddev=0.08)
+    (tok, ln), (qtok, qln) = _token_table(rng, n, nq, S, 1500, 100)
+    vectors = enc.embed(tok, ln)       # what the provider returns for node i
+    queries = enc.embed(qtok, qln)
+    cfg = LeannConfig(m=10, m0=20, ef_construction=48, metric=metric, prune_ratio=prune, pruning_strategy=0)
+    index = LeannIndex(cfg)
+    index.build(vectors, n, seed=3, batch=32)
+    ids_a, dist_a, cnt_a, st_a = index.search_batch(queries, k, ef, stats=True)
+    index.set_recompute(enc, tok, ln)
+    ids_b, dist_b, cnt_b, st_b = index.search_recompute_batch(queries, k, ef, stats=True)
+    assert np.array_equal(cnt_a, cnt_b) and np.array_equal(ids_a, ids_b)
+    assert np.array_equal(dist_a.view(np.uint32), dist_b.view(np.uint32))
+    for f in ("n_hop", "n_edge", "n_dist"):
+        assert np.array_equal(getattr(st_a, f), getattr(st_b, f)), f
+    info = index.last_recompute()
+    assert info["unique_nodes"] >= int(st_b.n_dist.max()) and info["encoder_ms"] > 0
+    index.drop_vectors()
+    ids_c, dist_c, cnt_c = index.search_recompute_batch(queries[:16], k, ef)
+    assert np.array_equal(ids_c, ids_a[:16]) and np.array_equal(dist_c.view(np.uint32), dist_a[:16].view(np.uint32))
+    index.free()
