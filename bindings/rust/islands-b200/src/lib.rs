@@ -213,7 +213,8 @@ pub enum PruningStrategy {
     #[default]
     Global,
     Local,
-    /// Draws from `thread_rng` in the reference (leann.rs:1043); the GPU library rejects it with `InvalidConfig`.
+    /// Draws from `thread_rng` in the reference (leann.rs:1043); the GPU library draws from a counter stream seeded by
+    /// `LeannConfig::prune_seed` (include/islands_b200.h).
     Proportional,
 }
 
@@ -290,6 +291,8 @@ pub struct LeannConfig {
     pub hub_percentile: f32,
     pub is_compact: bool,
     pub is_recompute: bool,
+    /// Not a reference field: seed of the `PruningStrategy::Proportional` draw stream.
+    pub prune_seed: u64,
 }
 
 impl Default for LeannConfig {
@@ -319,6 +322,7 @@ impl LeannConfig {
             hub_percentile: c.hub_percentile,
             is_compact: c.is_compact != 0,
             is_recompute: c.is_recompute != 0,
+            prune_seed: c.prune_seed,
         }
     }
     fn raw(&self) -> sys::IslLeannConfig {
@@ -341,6 +345,7 @@ impl LeannConfig {
             hub_percentile: self.hub_percentile,
             is_compact: self.is_compact as i32,
             is_recompute: self.is_recompute as i32,
+            prune_seed: self.prune_seed,
         }
     }
     fn preset(f: unsafe extern "C" fn(*mut sys::IslLeannConfig) -> i32) -> Self {

@@ -68,8 +68,16 @@ typedef enum isl_metric {
 typedef enum isl_pruning_strategy {
   ISL_PRUNE_GLOBAL = 0,
   ISL_PRUNE_LOCAL = 1,
-  ISL_PRUNE_PROPORTIONAL = 2 /* thread_rng in the reference (leann.rs:1043): rejected here */
+  ISL_PRUNE_PROPORTIONAL = 2 /* the reference draws from thread_rng (leann.rs:1043); here from the seeded stream below */
 } isl_pruning_strategy;
+
+/* PruningStrategy::Proportional keeps candidate j of a hop when gen::<f32>() < prob_j * num_to_keep
+ * (leann.rs:1017-1053).  The reference draws from thread_rng, which no one can reproduce; this library (and its
+ * oracle) draws from a counter-based stream instead: draw c (0, 1, 2, ... in the order the reference's loop consumes
+ * them) of query q of a call (its row in the query matrix) with isl_leann_config::prune_seed is
+ *   mix(z) = splitmix64's finaliser (z ^= z >> 30; z *= 0xBF58476D1CE4E5B9; z ^= z >> 27; z *= 0x94D049BB133111EB; z ^= z >> 31)
+ *   h = mix(mix(prune_seed + 0x9E3779B97F4A7C15 * (q + 1)) + 0x9E3779B97F4A7C15 * (c + 1));   u = (h >> 40) * 2^-24
+ * — a uniform f32 in [0, 1) with 24 random bits, the shape of rand's gen::<f32>(). */
 
 /* LeannConfig (src/core/leann.rs:322-371), same field order. */
 typedef struct isl_leann_config {
@@ -87,6 +95,7 @@ typedef struct isl_leann_config {
   float hub_percentile;
   int32_t is_compact;
   int32_t is_recompute;
+  uint64_t prune_seed; /* not a reference field: seed of the Proportional draw stream (see isl_pruning_strategy) */
 } isl_leann_config;
 
 /* HnswConfig (src/core/hnsw.rs:15-28). */

@@ -38,6 +38,7 @@ class LeannConfigStruct(C.Structure):
         ("hub_percentile", C.c_float),
         ("is_compact", C.c_int32),
         ("is_recompute", C.c_int32),
+        ("prune_seed", C.c_uint64),
     ]
 
 

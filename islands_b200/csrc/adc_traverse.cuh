@@ -39,38 +39,35 @@ struct BagPos {
 };
 
 // argmax of (kd, id) over the occupied slots (slot i = row i / 32 of lane i % 32 is occupied iff i < r_len).
-// All lanes call; the result is warp-uniform.
+// All lanes call; the result is warp-uniform.  Fast path: exactly one entry carries the greatest kd (the rule unless
+// distances tie exactly); otherwise the id decides among the entries that share it.
 template <int NR>
 __device__ __forceinline__ void bag_argmax(const RegBag<NR>& b, uint32_t r_len, uint32_t* out_kd, uint32_t* out_ki, BagPos* pos) {
   const uint32_t lane = lane_id();
   uint32_t m = 0;
 #pragma unroll
-  for (int j = 0; j < NR; ++j) {
-    const bool occ = (uint32_t)(j * 32) + lane < r_len;
-    m = max(m, occ ? b.kd[j] : 0u);
-  }
+  for (int j = 0; j < NR; ++j) m = max(m, (uint32_t)(j * 32) + lane < r_len ? b.kd[j] : 0u);
   const uint32_t top = __reduce_max_sync(0xffffffffu, m);
-  // entries with kd == top: the greatest id wins (ids are unique, so exactly one entry remains)
-  uint32_t best_i = 0;
-  bool have = false;
+  uint32_t row = 0, sel_i = 0, cnt = 0;
 #pragma unroll
   for (int j = 0; j < NR; ++j) {
-    const bool occ = (uint32_t)(j * 32) + lane < r_len;
-    if (occ && b.kd[j] == top && (!have || (b.ki[j] >> 1) >= (best_i >> 1))) {
-      best_i = b.ki[j];
-      have = true;
+    const bool eq = b.kd[j] == top && (uint32_t)(j * 32) + lane < r_len;
+    if (eq && (cnt == 0 || (b.ki[j] >> 1) > (sel_i >> 1))) {  // within the lane: the greatest id among its matches
+      row = j;
+      sel_i = b.ki[j];
     }
+    cnt += eq ? 1u : 0u;
   }
-  const uint32_t top_id = __reduce_max_sync(0xffffffffu, have ? (best_i >> 1) : 0u);
-  const uint32_t owner = __ffs(__ballot_sync(0xffffffffu, have && (best_i >> 1) == top_id)) - 1;
-  uint32_t row = 0;
-#pragma unroll
-  for (int j = 0; j < NR; ++j)
-    if (b.kd[j] == top && (b.ki[j] >> 1) == top_id && (uint32_t)(j * 32) + lane < r_len) row = j;
+  const uint32_t bal = __ballot_sync(0xffffffffu, cnt != 0);
+  uint32_t owner = __ffs(bal) - 1;
+  if (bal & (bal - 1)) {  // several lanes hold the greatest kd: the greatest id wins (ids are unique)
+    const uint32_t top_id = __reduce_max_sync(0xffffffffu, cnt ? (sel_i >> 1) : 0u);
+    owner = __ffs(__ballot_sync(0xffffffffu, cnt != 0 && (sel_i >> 1) == top_id)) - 1;
+  }
   pos->row = __shfl_sync(0xffffffffu, row, owner);
   pos->lane = owner;
   *out_kd = top;
-  *out_ki = __shfl_sync(0xffffffffu, best_i, owner);
+  *out_ki = __shfl_sync(0xffffffffu, sel_i, owner);
 }
 
 // argmin of (kd, id) over the occupied, unexpanded slots.  Returns false when there is none.
@@ -86,21 +83,24 @@ __device__ __forceinline__ bool bag_argmin_unexpanded(const RegBag<NR>& b, uint3
   // a real entry never carries kd == 0xffffffff (NaN patterns are folded to 0x7fc00000)
   const uint32_t low = __reduce_min_sync(0xffffffffu, m);
   if (low == 0xffffffffu) return false;
-  uint32_t best_id = 0xffffffffu;
+  uint32_t row = 0, sel_id = 0xffffffffu;
 #pragma unroll
   for (int j = 0; j < NR; ++j) {
-    const bool un = (uint32_t)(j * 32) + lane < r_len && !(b.ki[j] & 1u);
-    if (un && b.kd[j] == low) best_id = min(best_id, b.ki[j] >> 1);
+    const bool eq = b.kd[j] == low && (uint32_t)(j * 32) + lane < r_len && !(b.ki[j] & 1u);
+    if (eq && (b.ki[j] >> 1) < sel_id) {  // within the lane: the smallest id among its matches
+      row = j;
+      sel_id = b.ki[j] >> 1;
+    }
   }
-  const uint32_t id = __reduce_min_sync(0xffffffffu, best_id);
-  const uint32_t owner = __ffs(__ballot_sync(0xffffffffu, best_id == id)) - 1;
-  uint32_t row = 0;
-#pragma unroll
-  for (int j = 0; j < NR; ++j)
-    if (b.kd[j] == low && (b.ki[j] >> 1) == id && (uint32_t)(j * 32) + lane < r_len) row = j;
+  const uint32_t bal = __ballot_sync(0xffffffffu, sel_id != 0xffffffffu);
+  uint32_t owner = __ffs(bal) - 1;
+  if (bal & (bal - 1)) {  // several lanes hold the smallest kd: the smallest id wins
+    const uint32_t id = __reduce_min_sync(0xffffffffu, sel_id);
+    owner = __ffs(__ballot_sync(0xffffffffu, sel_id == id)) - 1;
+  }
   pos->row = __shfl_sync(0xffffffffu, row, owner);
   pos->lane = owner;
-  *out_id = id;
+  *out_id = __shfl_sync(0xffffffffu, sel_id, owner);
   return true;
 }
 
@@ -160,6 +160,33 @@ __global__ void __launch_bounds__(32) adc_traverse_kernel(const SearchArgs a) {
             const uint32_t c = min(c0 + cc * 32 + lane, a.pq_ksub - 1);
             row[cc] = reinterpret_cast<const float4*>(a.pq_codebooks + ((size_t)j * a.pq_ksub + c) * a.pq_ld_sub);
           }
+          if (nvec <= 8) {
+            // every 16-byte piece of the four centroid rows in flight at once (up to 32 loads per lane: the bag is not
+            // live yet, so the registers are free): one L2 latency per subquantizer instead of one per piece
+            float4 y[CC][8];
+#pragma unroll
+            for (int v = 0; v < 8; ++v)
+#pragma unroll
+              for (int cc = 0; cc < CC; ++cc) y[cc][v] = (uint32_t)v < nvec ? __ldg(row[cc] + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              if ((uint32_t)v < nvec) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const uint32_t t = v * 4 + e;
+                  if (t < a.pq_dsub) {
+                    const float qe = __ldg(qs + t);
+#pragma unroll
+                    for (int cc = 0; cc < CC; ++cc) {
+                      const float ye = e == 0 ? y[cc][v].x : (e == 1 ? y[cc][v].y : (e == 2 ? y[cc][v].z : y[cc][v].w));
+                      const float diff = __fsub_rn(qe, ye);
+                      acc[cc] = __fadd_rn(acc[cc], __fmul_rn(diff, diff));
+                    }
+                  }
+                }
+              }
+            }
+          } else {
           for (uint32_t v = 0; v < nvec; ++v) {
             float4 y[CC];
 #pragma unroll
@@ -177,6 +204,7 @@ __global__ void __launch_bounds__(32) adc_traverse_kernel(const SearchArgs a) {
                 }
               }
             }
+          }
           }
 #pragma unroll
           for (int cc = 0; cc < CC; ++cc) {

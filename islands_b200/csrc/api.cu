@@ -155,6 +155,8 @@ isl_status index_make_padded_adjacency(isl_index* idx) {
   idx->lists_unique = false;
   const uint64_t n = idx->n, e = idx->h_nbrs.size();
   if (n == 0) return ISL_OK;
+  ISL_CUDA_TRY(idx->deg_counts.alloc(n));  // graph.degree_counts on the device (PruningStrategy::Proportional)
+  ISL_TRY(launch_degree_counts(idx->offsets.p, n, idx->deg_counts.p, idx->stream));
   {
     DevBuf<unsigned int> flag;
     ISL_CUDA_TRY(flag.alloc(1));
@@ -231,6 +233,8 @@ isl_status search_device(const isl_index* idx, SearchScratch* sc, const float* d
   a.metric = idx->cfg.metric;
   a.prune_ratio = idx->cfg.prune_ratio;
   a.strategy = idx->cfg.pruning_strategy;
+  a.prune_seed = idx->cfg.prune_seed;
+  a.deg_counts = idx->deg_counts.p;
   a.visited = sc->visited.p;
   a.vis_words = vis_words;
   a.r_global = sc->r_global.p;
@@ -284,10 +288,6 @@ isl_status search_checks(const isl_index* idx, const void* queries, uint64_t nq,
   if (need_vectors && !idx->vectors.p)
     return fail(ISL_INVALID_ARGUMENT, "the stored vectors were dropped (isl_index_drop_vectors): only "
                                       "isl_index_search_adc_recompute works on this handle");
-  if (idx->cfg.prune_ratio != 0.0f && idx->cfg.pruning_strategy == ISL_PRUNE_PROPORTIONAL)
-    return fail(ISL_INVALID_CONFIG,
-                "PruningStrategy::Proportional draws from thread_rng in the reference and has no "
-                "deterministic definition; use Global or Local");
   *ef = std::max(*ef, k);  // leann.rs:890
   if (*ef > (1u << 24)) return fail(ISL_INVALID_ARGUMENT, "ef too large");
   return ISL_OK;
@@ -372,6 +372,7 @@ isl_status isl_leann_config_default(isl_leann_config* c) {
   c->hub_percentile = 0.02f;
   c->is_compact = 1;
   c->is_recompute = 1;
+  c->prune_seed = 0;
   return ISL_OK;
 }
 isl_status isl_leann_config_fast(isl_leann_config* c) {

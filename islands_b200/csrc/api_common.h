@@ -106,6 +106,7 @@ struct isl_index {
   isl::DevBuf<uint32_t> nbrs;    // [E]
   // Search-time adjacency: fixed-stride rows padded with 0xffffffff (stride = max degree rounded
   // up to 32).  Used instead of the CSR arrays when it costs at most ~2x their memory.
+  isl::DevBuf<uint32_t> deg_counts;  // [n] graph.degree_counts (PruningStrategy::Proportional)
   isl::DevBuf<uint32_t> adj_pad; // [n][adj_stride]
   uint32_t adj_stride = 0;       // 0 => search walks the CSR arrays
   bool lists_unique = false;     // no neighbour list names an id twice (scanned once per graph)

@@ -21,7 +21,7 @@
 #include <algorithm>
 
 #include "api_common.h"
-#include "dist_pass.cuh"
+#include "search_core.cuh"
 
 namespace isl {
 namespace {
@@ -39,6 +39,8 @@ struct HopArgs {
   int32_t metric;
   float prune_ratio;
   int32_t strategy;
+  uint64_t prune_seed;
+  const uint32_t* deg_counts;
   // batch
   const float* queries;  // [nq][q_ld]
   uint32_t q_ld, nq, ef, k, u_cap, vis_words, tie_cap;
@@ -47,7 +49,7 @@ struct HopArgs {
   uint2* ties;         // [nq][tie_cap]
   uint32_t* vis;       // [nq][vis_words]
   uint32_t* cand;      // [nq][u_cap] this round's to_compute list
-  uint32_t* meta;      // [nq][8]: r_len, first_unexp, n_ties, cand_cnt, done, started
+  uint32_t* meta;      // [nq][8]: r_len, first_unexp, n_ties, cand_cnt, done, started, draw counter (lo, hi)
   float* q_sqnorm;     // [nq]
   isl_search_stats* stats;  // [nq]
   unsigned int* active;     // number of queries that still have a round to run
@@ -109,6 +111,7 @@ __global__ void __launch_bounds__(128) rc_expand_kernel(const HopArgs a) {
     return;
   }
   uint32_t r_len = meta[0], first_unexp = meta[1], n_ties = meta[2];
+  uint64_t draw_ctr = ((uint64_t)meta[7] << 32) | meta[6];  // Proportional pruning: draws consumed so far
   uint64_t n_hop = 0, n_edge = 0, n_dist = 0;
   uint32_t ucnt = 0, keep = 0;
   bool finished = false;
@@ -185,7 +188,9 @@ __global__ void __launch_bounds__(128) rc_expand_kernel(const HopArgs a) {
     }
     __syncwarp();
     if (ucnt == 0) continue;  // leann.rs:939-941
-    keep = prune_keep_x(a.prune_ratio, a.strategy, ucnt, r_len, a.ef);  // leann.rs:944
+    keep = (a.strategy == ISL_PRUNE_PROPORTIONAL && a.prune_ratio != 0.0f)
+               ? prune_proportional(a.prune_ratio, cand, ucnt, a.deg_counts, a.prune_seed, q, &draw_ctr)
+               : prune_keep_x(a.prune_ratio, a.strategy, ucnt, r_len, a.ef);  // leann.rs:944
     n_dist += keep;
     break;
   }
@@ -193,6 +198,8 @@ __global__ void __launch_bounds__(128) rc_expand_kernel(const HopArgs a) {
     meta[1] = first_unexp;
     meta[2] = n_ties;
     meta[3] = finished ? 0 : keep;
+    meta[6] = (uint32_t)draw_ctr;
+    meta[7] = (uint32_t)(draw_ctr >> 32);
     if (finished) {
       meta[4] = 1;
       atomicSub(a.active, 1u);
@@ -416,6 +423,8 @@ isl_status isl_index_search_recompute(const isl_index* idx, const float* queries
   a.metric = idx->cfg.metric;
   a.prune_ratio = idx->cfg.prune_ratio;
   a.strategy = idx->cfg.pruning_strategy;
+  a.prune_seed = idx->cfg.prune_seed;
+  a.deg_counts = idx->deg_counts.p;
   a.queries = sc->q_stage.p;
   a.q_ld = idx->ld;
   a.nq = (uint32_t)nq;

@@ -79,6 +79,20 @@ __host__ __device__ __forceinline__ bool key_lt64(float d1, uint64_t id1, float 
   return id1 < id2;
 }
 
+// The seeded draw stream of PruningStrategy::Proportional (include/islands_b200.h, isl_pruning_strategy).
+__host__ __device__ __forceinline__ uint64_t splitmix_mix(uint64_t z) {
+  z ^= z >> 30;
+  z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27;
+  z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return z;
+}
+__host__ __device__ __forceinline__ float prune_draw(uint64_t seed, uint64_t query, uint64_t draw) {
+  const uint64_t h = splitmix_mix(splitmix_mix(seed + 0x9E3779B97F4A7C15ull * (query + 1)) + 0x9E3779B97F4A7C15ull * (draw + 1));
+  return (float)(uint32_t)(h >> 40) * (1.0f / 16777216.0f);
+}
+
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 

@@ -290,6 +290,19 @@ isl_status launch_pad_adjacency(const uint64_t* d_offsets, const uint32_t* d_nbr
   return ISL_OK;
 }
 
+__global__ void degree_counts_kernel(const uint64_t* __restrict__ offsets, uint64_t n, uint32_t* __restrict__ deg) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    deg[i] = (uint32_t)(offsets[i + 1] - offsets[i]);
+}
+
+isl_status launch_degree_counts(const uint64_t* d_offsets, uint64_t n, uint32_t* d_deg, cudaStream_t st) {
+  if (n == 0) return ISL_OK;
+  degree_counts_kernel<<<grid_1d(n, 256), 256, 0, st>>>(d_offsets, n, d_deg);
+  count_launch();
+  ISL_CUDA_TRY(cudaGetLastError());
+  return ISL_OK;
+}
+
 isl_status launch_list_duplicates(const uint64_t* d_offsets, const uint32_t* d_nbrs, uint64_t n, unsigned int* d_flag,
                                   cudaStream_t st) {
   if (n == 0) return ISL_OK;

@@ -28,6 +28,9 @@ isl_status launch_narrow_ids(const uint64_t* d_src, uint32_t* d_dst, uint64_t co
 isl_status launch_pad_adjacency(const uint64_t* d_offsets, const uint32_t* d_nbrs, uint64_t n, uint32_t stride,
                                 uint32_t* d_out, cudaStream_t st);
 
+// d_deg[i] = offsets[i + 1] - offsets[i] (graph.degree_counts).
+isl_status launch_degree_counts(const uint64_t* d_offsets, uint64_t n, uint32_t* d_deg, cudaStream_t st);
+
 // Sets *d_flag (pre-zeroed) to 1 when some neighbour list holds an id twice.
 isl_status launch_list_duplicates(const uint64_t* d_offsets, const uint32_t* d_nbrs, uint64_t n, unsigned int* d_flag,
                                   cudaStream_t st);

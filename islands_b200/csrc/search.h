@@ -47,6 +47,8 @@ struct SearchArgs {
   int32_t metric;
   float prune_ratio;        // leann.rs:991-1056 (0 => identity)
   int32_t strategy;
+  uint64_t prune_seed;      // Proportional: seed of the draw stream
+  const uint32_t* deg_counts;  // Proportional: graph.degree_counts (out-degree per node)
   // scratch (per resident warp slot)
   uint32_t* visited;        // [slots][vis_words]
   uint32_t vis_words;

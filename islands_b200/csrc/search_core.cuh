@@ -72,6 +72,50 @@ __device__ __forceinline__ uint32_t prune_keep(float prune_ratio, int strategy, 
   return keep < n_cands ? keep : n_cands;
 }
 
+// PruningStrategy::Proportional (leann.rs:1017-1053) over list[0 .. n_cands): candidate j is kept when its draw is
+// below degree_j / total_degree * num_to_keep; the loop stops once num_to_keep are kept; nothing kept => the first
+// candidate.  The draws come from the seeded stream of common.cuh, consumed in list order (`draw_ctr` is the query's
+// running draw counter).  The kept ids are compacted to the front of `list`; returns how many.  All lanes call.
+__device__ __forceinline__ uint32_t prune_proportional(float prune_ratio, uint32_t* list, uint32_t n_cands, const uint32_t* deg_counts,
+                                                       uint64_t seed, uint32_t query, uint64_t* draw_ctr) {
+  const uint32_t lane = lane_id();
+  uint32_t num_to_keep = (uint32_t)ceilf(__fmul_rn((float)n_cands, __fsub_rn(1.0f, prune_ratio)));  // leann.rs:1001-1003
+  if (num_to_keep < 1) num_to_keep = 1;
+  unsigned long long total = 0;
+  for (uint32_t i = lane; i < n_cands; i += 32) total += __ldg(deg_counts + list[i]);
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  if (total == 0) return num_to_keep < n_cands ? num_to_keep : n_cands;  // leann.rs:1029-1031
+  const float totf = __ull2float_rn(total), keepf = (float)num_to_keep;
+  uint32_t w = 0;
+  uint64_t consumed = n_cands;
+  for (uint32_t b = 0; b < n_cands; b += 32) {
+    const uint32_t i = b + lane;
+    uint32_t id = 0;
+    bool sel = false;
+    if (i < n_cands) {
+      id = list[i];
+      const float prob = __fdiv_rn((float)__ldg(deg_counts + id), totf);
+      sel = prune_draw(seed, query, *draw_ctr + i) < __fmul_rn(prob, keepf);
+    }
+    uint32_t bal = __ballot_sync(0xffffffffu, sel);
+    const uint32_t need = num_to_keep - w;
+    bool done = false;
+    if ((uint32_t)__popc(bal) >= need) {  // the need-th kept candidate ends the reference's loop (selected.len() >= num_to_keep)
+      const uint32_t last = __fns(bal, 0, need);
+      bal &= last == 31 ? 0xffffffffu : ((1u << (last + 1)) - 1u);
+      consumed = (uint64_t)b + last + 1;
+      done = true;
+    }
+    __syncwarp();  // every lane has read its id before the compacted prefix is written (positions <= i)
+    if (bal & (1u << lane)) list[w + __popc(bal & ((1u << lane) - 1u))] = id;
+    w += __popc(bal);
+    __syncwarp();
+    if (done) break;
+  }
+  *draw_ctr += consumed;
+  return w ? w : 1u;  // nothing kept: the first candidate, still at list[0] (leann.rs:1049-1051)
+}
+
 // TWO = two-level search: unvisited neighbours are scored with the PQ table distance
 // (pq.rs:341-348) into an approximate queue AQ ordered by (adc,id); after every expansion the
 // ceil(a*|AQ|) best entries (at least one) leave AQ, get their exact distance and go through the
@@ -207,6 +251,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       wst_d = __uint_as_float(wst_kd);
     }
     uint64_t n_hop = 0, n_edge = 0, n_dist = 0, n_adc = 0, n_rerank = 0;
+    uint64_t draw_ctr = 0;  // Proportional pruning: draws consumed by this query so far
     const float* lut = nullptr;
     if (MODE != 0 && !(ADC && a.phase == 2)) {
       if (a.luts == nullptr) {
@@ -687,7 +732,9 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         continue;
       }
       if (!TWO) {
-        const uint32_t keep = prune_keep(a.prune_ratio, a.strategy, ucnt, r_len, ef);  // :944
+        const uint32_t keep = (a.strategy == ISL_PRUNE_PROPORTIONAL && a.prune_ratio != 0.0f)
+                                  ? prune_proportional(a.prune_ratio, u_list, ucnt, a.deg_counts, a.prune_seed, qi, &draw_ctr)
+                                  : prune_keep(a.prune_ratio, a.strategy, ucnt, r_len, ef);  // :944
         n_dist += keep;
         score_and_admit(keep);
         continue;

@@ -115,8 +115,54 @@ struct Visited {
   }
 };
 
-// leann.rs:991-1056.  `cands` is the unvisited list; returns how many of its prefix to keep.
-// Proportional draws from thread_rng in the reference: not reproducible, rejected by callers.
+// The seeded stand-in for thread_rng in PruningStrategy::Proportional (include/islands_b200.h, isl_pruning_strategy):
+// draw c of query q = 24 random bits of a splitmix64-mixed counter, as a uniform f32 in [0, 1).
+inline uint64_t splitmix_mix(uint64_t z) {
+  z ^= z >> 30;
+  z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27;
+  z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return z;
+}
+inline float prune_draw(uint64_t seed, uint64_t query, uint64_t draw) {
+  uint64_t h = splitmix_mix(splitmix_mix(seed + 0x9E3779B97F4A7C15ull * (query + 1)) + 0x9E3779B97F4A7C15ull * (draw + 1));
+  return (float)(uint32_t)(h >> 40) * (1.0f / 16777216.0f);
+}
+
+// leann.rs:1017-1053: Proportional.  Rewrites `cands` to the selected ids, in order.
+template <class G>
+void prune_proportional(const isl_leann_config& cfg, const G& g, std::vector<uint64_t>& cands, uint64_t query,
+                        uint64_t* draw_ctr) {
+  float fn = (float)cands.size();
+  uint64_t num_to_keep = (uint64_t)std::ceil(fn * (1.0f - cfg.prune_ratio));  // :1001-1002
+  if (num_to_keep < 1) num_to_keep = 1;                                       // :1003
+  auto degree = [&](uint64_t id) -> uint64_t {  // graph.degree_counts.get(id)
+    const uint64_t* nb;
+    uint64_t cnt;
+    g.get(id, nb, cnt);
+    return cnt;
+  };
+  uint64_t total = 0;
+  for (uint64_t id : cands) total += degree(id);                              // :1019-1028
+  if (total == 0) {                                                           // :1029-1031
+    cands.resize(std::min<uint64_t>(num_to_keep, cands.size()));
+    return;
+  }
+  std::vector<uint64_t> selected;
+  for (uint64_t id : cands) {                                                 // :1034-1048
+    float prob = (float)degree(id) / (float)total;
+    float u = prune_draw(cfg.prune_seed, query, (*draw_ctr)++);               // rand::thread_rng().gen::<f32>() in the reference
+    if (u < prob * (float)num_to_keep) {
+      selected.push_back(id);
+      if (selected.size() >= num_to_keep) break;
+    }
+  }
+  if (selected.empty()) selected.push_back(cands[0]);                         // :1049-1051
+  cands.swap(selected);
+}
+
+// leann.rs:991-1016 (Global / Local).  `cands` is the unvisited list; returns how many of its prefix to keep.
 inline uint64_t prune_keep(const isl_leann_config& cfg, uint64_t n_cands, uint64_t results_len,
                            uint64_t ef) {
   if (cfg.prune_ratio == 0.0f || n_cands == 0) return n_cands;  // leann.rs:997-999
@@ -183,8 +229,9 @@ struct AdjView {
 template <class G>
 void best_first(const isl_leann_config& cfg, bool apply_pruning, const G& g, const float* vectors,
                 uint32_t d, const float* q, uint64_t entry, uint64_t ef, Visited& visited,
-                std::vector<Key>& out, isl_search_stats* st) {
+                std::vector<Key>& out, isl_search_stats* st, uint64_t query_index = 0) {
   const int32_t metric = cfg.metric;
+  uint64_t draw_ctr = 0;
   MinHeap candidates;
   MaxHeap results;
   float entry_dist = calc(metric, q, vectors + entry * (uint64_t)d, d);  // leann.rs:911-912
@@ -206,8 +253,13 @@ void best_first(const isl_leann_config& cfg, bool apply_pruning, const G& g, con
     for (uint64_t i = 0; i < cnt; ++i)                                   // :933-937
       if (visited.insert(nb[i])) unvisited.push_back(nb[i]);
     if (unvisited.empty()) continue;                                     // :939-941
-    uint64_t keep = apply_pruning ? prune_keep(cfg, unvisited.size(), results.size(), ef)
-                                  : unvisited.size();                    // :944
+    uint64_t keep;
+    if (apply_pruning && cfg.pruning_strategy == ISL_PRUNE_PROPORTIONAL && cfg.prune_ratio != 0.0f) {
+      prune_proportional(cfg, g, unvisited, query_index, &draw_ctr);     // :1017-1053
+      keep = unvisited.size();
+    } else {
+      keep = apply_pruning ? prune_keep(cfg, unvisited.size(), results.size(), ef) : unvisited.size();  // :944
+    }
     n_dist += keep;                                                      // :950
     for (uint64_t i = 0; i < keep; ++i) {                                // :953-970
       uint64_t nbid = unvisited[i];
@@ -538,8 +590,6 @@ int32_t orc_leann_search(const isl_leann_config* cfg, const float* vectors, uint
     return ISL_OK;
   }
   if (entry < 0) return ISL_INDEX_NOT_BUILT;  // leann.rs:889
-  if (cfg->prune_ratio != 0.0f && cfg->pruning_strategy == ISL_PRUNE_PROPORTIONAL)
-    return ISL_INVALID_CONFIG;  // thread_rng (leann.rs:1043): not reproducible
   uint64_t ef = std::max<uint64_t>(ef_in, k);  // leann.rs:890
   CsrView g{offsets, nbrs, n};
   int nt = std::max(1, threads);
@@ -549,7 +599,7 @@ int32_t orc_leann_search(const isl_leann_config* cfg, const float* vectors, uint
     for (uint64_t qi = b; qi < e; ++qi) {
       vis[w].reset(n);
       best_first(*cfg, true, g, vectors, d, queries + qi * (uint64_t)d, (uint64_t)entry, ef, vis[w],
-                 res, stats ? stats + qi : nullptr);
+                 res, stats ? stats + qi : nullptr, qi);
       write_topk(res, k, out_ids + qi * k, out_dist + qi * k, out_count ? out_count + qi : nullptr);
     }
   });

@@ -59,7 +59,35 @@ for limit in [int(v) for v in os.environ.get("LIMITS", "64,32,16").split(",") if
     lim[str(limit)] = dict(recomputed=il["unique_nodes"], batch_ms=round(dtl * 1e3, 1), qps=round(nq / dtl, 1), encoder_ms=round(il["encoder_ms"], 2),
                            recall_at_10=float(np.mean([len(set(ids_l[i].tolist()) & set(gtn[i].tolist())) / k for i in range(nq)])))
 index.set_rerank_limit(0)
-print(json.dumps(dict(rerank_limit=lim, hub_cache=hub, n=n, nq=nq, S=S, ef=ef, index_encode_s=round(t_enc_all, 2), index_encode_seq_per_s=round(n / t_enc_all),
+# ef sweep of the ADC variant: recall is what the table distances let through to the encoder
+sweep = {}
+for e in [int(v) for v in os.environ.get("EFS", "256,512").split(",") if v]:
+    index.search_adc_recompute_batch(qh, k, e)
+    t0 = time.perf_counter(); ids_e, _, _ = index.search_adc_recompute_batch(qh, k, e); dte = time.perf_counter() - t0
+    ie = index.last_recompute()
+    sweep[str(e)] = dict(batch_ms=round(dte * 1e3, 1), qps=round(nq / dte, 1), recomputed=ie["unique_nodes"], encoder_ms=round(ie["encoder_ms"], 2),
+                         recall_at_10=float(np.mean([len(set(ids_e[i].tolist()) & set(gt[i].tolist())) / k for i in range(nq)])))
+# the reference's own recompute loop, hop by hop (isl_index_search_recompute): exact traversal, provider = encoder
+hop = {}
+nqx = int(os.environ.get("NQ_HOP", 64))
+for e in [int(v) for v in os.environ.get("EFS_HOP", "32,64").split(",") if v]:
+    t0 = time.perf_counter(); ids_h, dist_h, _, st_h = index.search_recompute_batch(qh[:nqx], k, e, stats=True); dth = time.perf_counter() - t0
+    ih = index.last_recompute()
+    ids_s, dist_s, _ = index.search_batch(qh[:nqx], k, e)  # stored vectors, plain exact kernel
+    hop[str(e)] = dict(queries=nqx, batch_s=round(dth, 2), qps=round(nqx / dth, 2), sequences_encoded=ih["unique_nodes"], encoder_ms=round(ih["encoder_ms"], 1),
+                       n_dist_per_query=float(st_h.n_dist.mean()), n_hop_per_query=float(st_h.n_hop.mean()),
+                       recall_at_10=float(np.mean([len(set(ids_h[i].tolist()) & set(gt[i].tolist())) / k for i in range(nqx)])),
+                       identical_to_stored_exact_search=bool(np.array_equal(ids_h, ids_s) and np.array_equal(dist_h.view(np.uint32), dist_s.view(np.uint32))))
+# the encoder in split precision (ISL_ENCODER_BF16X3): what rank-level agreement with f32 embeddings costs
+enc3 = Encoder(EncoderConfig(precision=1)).init_random(seed=46, stddev=0.02)
+nb = 2048
+out3 = torch.empty((nb, 768), device=dev)
+for _ in range(2):
+    enc3.embed_dev(tok.data_ptr(), ln.data_ptr(), nb, S, out3.data_ptr())
+ms3, _ = enc3.last_timing()
+enc.embed_dev(tok.data_ptr(), ln.data_ptr(), nb, S, emb.data_ptr()); ms1, _ = enc.last_timing()
+split = dict(batch=nb, bf16_ms=round(ms1, 2), bf16x3_ms=round(ms3, 2), max_abs_diff=float((out3 - emb[:nb]).abs().max().item()))
+print(json.dumps(dict(ef_sweep=sweep, per_hop_recompute=hop, split_precision=split, rerank_limit=lim, hub_cache=hub, n=n, nq=nq, S=S, ef=ef, index_encode_s=round(t_enc_all, 2), index_encode_seq_per_s=round(n / t_enc_all),
                       recompute_batch_ms=round(dt * 1e3, 1), qps=round(nq / dt, 1), unique_nodes=info["unique_nodes"],
                       traverse_ms=round(info["traverse_ms"], 2), encoder_ms=round(info["encoder_ms"], 2), rerank_ms=round(info["rerank_ms"], 2),
                       encoder_tflops=round(fl / ms_enc / 1e9, 1), recall_at_10=rec,

@@ -221,8 +221,8 @@ def test_split_precision_recompute_meets_the_recall_bar(gpu_lib):
     assert np.abs(dist_a[same] - dist_b[same]).max() < 2e-5
 
 
-@pytest.mark.parametrize("metric,prune", [(0, 0.0), (1, 0.0), (0, 0.4)])
-def test_per_hop_recompute_equals_the_stored_vector_search(gpu_lib, metric, prune):
+@pytest.mark.parametrize("metric,prune,strategy", [(0, 0.0, 0), (1, 0.0, 0), (0, 0.4, 0), (0, 0.5, 2)])
+def test_per_hop_recompute_equals_the_stored_vector_search(gpu_lib, metric, prune, strategy):
     """The reference's own recompute semantics (leann.rs:899-988): every hop fetches the embeddings of its unvisited
     neighbours from the provider (compute_embeddings_batch, :947-950) — here the encoder over the nodes' token rows, one
     pass per lockstep hop of the whole batch.  An index that STORES the encoder's outputs, searched by the plain exact
@@ -237,7 +237,7 @@ def test_per_hop_recompute_equals_the_stored_vector_search(gpu_lib, metric, prun
     (tok, ln), (qtok, qln) = _token_table(rng, n, nq, S, 1500, 100)
     vectors = enc.embed(tok, ln)       # what the provider returns for node i
     queries = enc.embed(qtok, qln)
-    cfg = LeannConfig(m=10, m0=20, ef_construction=48, metric=metric, prune_ratio=prune, pruning_strategy=0)
+    cfg = LeannConfig(m=10, m0=20, ef_construction=48, metric=metric, prune_ratio=prune, pruning_strategy=strategy, prune_seed=99)
     index = LeannIndex(cfg)
     index.build(vectors, n, seed=3, batch=32)
     ids_a, dist_a, cnt_a, st_a = index.search_batch(queries, k, ef, stats=True)

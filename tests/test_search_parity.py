@@ -74,6 +74,27 @@ def test_search_with_pruning(gpu_lib, orc, strategy, ratio):
     _compare(orc, cfg, v, off, nbrs, entry, levels, q, 10, 64)
 
 
+@pytest.mark.parametrize("ratio,seed", [(0.3, 0), (0.6, 12345), (0.9, 2**63 + 7)])
+def test_search_with_proportional_pruning(gpu_lib, orc, ratio, seed):
+    """leann.rs:1017-1053: keep candidate j when its draw < degree_j / total_degree * num_to_keep, stop at num_to_keep,
+    never keep nothing.  The reference draws from thread_rng; GPU and oracle draw from the same seeded counter stream
+    (include/islands_b200.h), consumed in the order of the reference's loop: ids, distances and counters bit-exact."""
+    from islands_b200 import LeannConfig
+
+    cfg0, v, levels, off, nbrs, entry = oracle_graph(orc, 2000, 32, seed=13)
+    cfg = LeannConfig(prune_ratio=ratio, pruning_strategy=2, prune_seed=seed)
+    q = uniform(np.random.RandomState(10), 150, 32)
+    _compare(orc, cfg, v, off, nbrs, entry, levels, q, 10, 64)
+    # a different seed is a different (equally valid) traversal; seed 0 of query i is not query j's stream
+    from islands_b200 import LeannIndex
+
+    a = LeannIndex.from_csr(cfg, v, off, nbrs, levels, entry).search_batch(q, 10, 64, stats=True)[3]
+    b = LeannIndex.from_csr(LeannConfig(prune_ratio=ratio, pruning_strategy=2, prune_seed=seed + 1), v, off, nbrs, levels,
+                            entry).search_batch(q, 10, 64, stats=True)[3]
+    assert not np.array_equal(a.n_dist, b.n_dist)
+    assert (a.n_dist < orc.leann_search(cfg0._s, v, off, nbrs, entry, q, 10, 64, stats=True)[3]["n_dist"]).mean() > 0.9
+
+
 def test_search_k_larger_than_n_and_ef_smaller_than_k(gpu_lib, orc):
     cfg, v, levels, off, nbrs, entry = oracle_graph(orc, 40, 16, seed=14)
     q = uniform(np.random.RandomState(11), 10, 16)
@@ -111,9 +132,8 @@ def test_search_errors(gpu_lib, orc):
     empty = LeannIndex.from_csr(cfg, np.zeros((0, 32), np.float32), [0], [], None, None)
     assert empty.search(v[0], 5) == []  # leann.rs:875-877
     assert len(empty) == 0 and empty.is_empty()
-    prop = LeannIndex.from_csr(LeannConfig(prune_ratio=0.5, pruning_strategy=2), v, off, nbrs, levels, entry)
     with pytest.raises(InvalidConfig):
-        prop.search(v[0], 5)
+        LeannConfig(prune_ratio=1.5).validate()  # leann.rs:443-447
 
 
 def test_search_100k_x_768_baseline_config0(gpu_lib, orc):
