@@ -507,6 +507,15 @@ isl_status isl_index_search_sharded(const isl_index* idx, isl_shard* sh, uint64_
 isl_status isl_index_search_sharded_dev(const isl_index* idx, isl_shard* sh, uint64_t id_base, const float* d_queries,
                                         uint64_t nq, uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
                                         float* d_out_dist, uint32_t* d_out_count);
+/* The same for the PQ searches: mode ISL_SHARD_ADC_RERANK = isl_index_search_adc_rerank on every shard,
+ * ISL_SHARD_ADC_RECOMPUTE = isl_index_search_adc_recompute (graph + codes + token rows per shard, encoder per GPU:
+ * BASELINE configs[4]); the exact-rerank launch writes the exchange records. */
+#define ISL_SHARD_EXACT 0
+#define ISL_SHARD_ADC_RERANK 1
+#define ISL_SHARD_ADC_RECOMPUTE 2
+isl_status isl_index_search_sharded_adc(const isl_index* idx, isl_shard* sh, uint64_t id_base, int32_t mode, const float* queries,
+                                        uint64_t nq, uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* out_ids,
+                                        float* out_dist, uint32_t* out_count);
 /* CUDA-event durations of the three stages of the last sharded search on this rank. */
 isl_status isl_shard_last_timing(const isl_shard* sh, float* search_ms, float* exchange_ms, float* merge_ms);
 /* The halves on their own: this shard's result records [nq][k] without an exchange ... */

@@ -232,6 +232,7 @@ SIGNATURES = {
     "isl_shard_enable_peer_exchange": (C.c_int, [_VP, C.c_uint64]),
     "isl_index_search_sharded": (C.c_int, [_VP, _VP, C.c_uint64, f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u64p, f32p, u32p]),
     "isl_index_search_sharded_dev": (C.c_int, [_VP, _VP, C.c_uint64, _VP, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _VP, _VP, _VP]),
+    "isl_index_search_sharded_adc": (C.c_int, [_VP, _VP, C.c_uint64, C.c_int32, f32p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, u64p, f32p, u32p]),
     "isl_shard_last_timing": (C.c_int, [_VP, f32p, f32p, f32p]),
     "isl_index_search_packed_dev": (C.c_int, [_VP, C.c_uint64, _VP, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _VP]),
     "isl_merge_packed_dev": (C.c_int, [_VP, C.c_uint32, C.c_uint64, C.c_uint32, _VP, _VP, _VP]),

@@ -566,6 +566,18 @@ class LeannIndex:
                                                     _ptr(ids, u64p), _ptr(dist, f32p), _ptr(cnt, u32p)))
         return ids, dist, cnt
 
+    def search_sharded_adc(self, shard, id_base, queries, k, ef, recompute=False):
+        """Sharded "PQ ADC traversal + exact rerank" (recompute=False) or its recompute form (True): collective."""
+        q = _f32(queries)
+        q = q.reshape(1, -1) if q.ndim == 1 else q
+        nq, qd = q.shape
+        ids = np.empty((nq, k), np.uint64)
+        dist = np.empty((nq, k), np.float32)
+        cnt = np.empty(nq, np.uint32)
+        _check(_ffi.load().isl_index_search_sharded_adc(self._h, shard._h, int(id_base), 2 if recompute else 1, _ptr(q, f32p), nq,
+                                                        qd, k, int(ef), _ptr(ids, u64p), _ptr(dist, f32p), _ptr(cnt, u32p)))
+        return ids, dist, cnt
+
     def search_sharded_dev(self, shard, id_base, d_queries_ptr, nq, dim, k, ef, d_ids_ptr, d_dist_ptr, d_count_ptr=None):
         """The same with queries and outputs on the device (raw addresses)."""
         _check(_ffi.load().isl_index_search_sharded_dev(self._h, shard._h, int(id_base), C.c_void_p(d_queries_ptr), nq, dim,

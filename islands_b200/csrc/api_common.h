@@ -173,6 +173,15 @@ isl_status stage_device_queries(const isl_index* idx, SearchScratch* sc, const f
                                 uint32_t query_dim, const float** q, uint32_t* q_ld);
 isl_status search_finish(const isl_index* idx, SearchScratch* sc, uint64_t launches);
 isl_status pq_upload_codebooks(isl_pq* pq);
+// PQ searches (1 two-level, 2 ADC traversal + exact rerank) and the ADC recompute search on a caller-held scratch
+// (device guard + shared lock + search_checks done by the caller); shard != null: also write the shard-exchange
+// records and leave host copies / final synchronisation to the caller (api_shard.cu).
+isl_status pq_search_on_scratch(int mode, const isl_index* idx, SearchScratch* sc, const float* queries, uint64_t nq, uint32_t k,
+                                uint32_t ef, float rerank_ratio, uint64_t* out_ids, float* out_dist, uint32_t* out_count,
+                                isl_search_stats* stats, const ShardOut* shard);
+isl_status adc_recompute_on_scratch(const isl_index* idx, SearchScratch* sc, const float* queries, uint64_t nq, uint32_t k,
+                                    uint32_t ef, uint64_t* out_ids, float* out_dist, uint32_t* out_count,
+                                    isl_search_stats* stats, const ShardOut* shard);
 template <class T>
 isl_status ensure(DevBuf<T>& b, size_t count) {
   if (b.n >= count) return ISL_OK;

@@ -186,23 +186,16 @@ isl_status isl_index_drop_vectors(isl_index* idx) {
   return ISL_OK;
 }
 
-isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* queries, uint64_t nq, uint32_t query_dim,
-                                          uint32_t k, uint32_t ef, uint64_t* out_ids, float* out_dist,
-                                          uint32_t* out_count, isl_search_stats* stats) {
-  bool trivial;
-  ISL_TRY(search_checks(idx, queries, nq, query_dim, k, &ef, &trivial, /*need_vectors=*/false));
-  if (trivial) {
-    fill_empty(nq, k, out_ids, out_dist, out_count, stats);
-    return ISL_OK;
-  }
+}  // extern "C"
+
+namespace isl {
+isl_status adc_recompute_on_scratch(const isl_index* idx, SearchScratch* sc, const float* queries, uint64_t nq, uint32_t k,
+                                    uint32_t ef, uint64_t* out_ids, float* out_dist, uint32_t* out_count,
+                                    isl_search_stats* stats, const ShardOut* shard) {
   if (!idx->pq) return fail(ISL_PQ_ERROR, "no product quantizer attached (isl_index_attach_pq)");
   if (!idx->encoder) return fail(ISL_INVALID_ARGUMENT, "no recompute encoder attached (isl_index_set_recompute)");
-  if (!out_ids || !out_dist) return fail(ISL_INVALID_ARGUMENT, "output pointer is null");
+  if (!shard && (!out_ids || !out_dist)) return fail(ISL_INVALID_ARGUMENT, "output pointer is null");
   const isl_pq* pq = idx->pq;
-  DeviceGuard g(idx->device);
-  std::shared_lock<std::shared_mutex> lock(idx->mu);
-  ScratchLease sc(idx);
-  ISL_TRY(sc.status);
   const uint32_t m = (uint32_t)pq->cfg.num_subquantizers;
   const uint32_t lut_floats = m * pq->ksub;
   const uint32_t n = (uint32_t)idx->n;
@@ -332,16 +325,25 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
   a.phase = 2;
   a.u_cap = u_cap_r;
   a.lut_smem_floats = 0;
+  if (shard) a.shard = *shard;
   ISL_CUDA_TRY(cudaEventRecord(sc->ev0, st));
   ISL_TRY(launch_search(plan_r, a, st));
   ISL_CUDA_TRY(cudaEventRecord(sc->ev1, st));
+  {
+    std::lock_guard<std::mutex> tl(idx->pool_mu);
+    idx->last_traverse_ms = traverse_ms;
+    idx->last_encoder_ms = encoder_ms;
+    idx->last_recomputed = unique;
+    idx->last_hub_hits = hub_hits;
+  }
+  if (shard) return ISL_OK;  // records written; exchange, merge and the final synchronisation follow in api_shard.cu
 
   ISL_CUDA_TRY(cudaMemcpyAsync(out_ids, sc->out_ids.p, nq * k * 8, cudaMemcpyDeviceToHost, st));
   ISL_CUDA_TRY(cudaMemcpyAsync(out_dist, sc->out_dist.p, nq * k * 4, cudaMemcpyDeviceToHost, st));
   if (out_count) ISL_CUDA_TRY(cudaMemcpyAsync(out_count, sc->out_count.p, nq * 4, cudaMemcpyDeviceToHost, st));
   if (stats)
     ISL_CUDA_TRY(cudaMemcpyAsync(stats, sc->out_stats.p, nq * sizeof(isl_search_stats), cudaMemcpyDeviceToHost, st));
-  ISL_TRY(search_finish(idx, sc.get(), 3));
+  ISL_TRY(search_finish(idx, sc, 3));
   {
     std::lock_guard<std::mutex> tl(idx->pool_mu);
     idx->last_rerank_ms = sc->kernel_ms;
@@ -351,6 +353,26 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
     idx->last_hub_hits = hub_hits;
   }
   return ISL_OK;
+}
+
+}  // namespace isl
+
+extern "C" {
+
+isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* queries, uint64_t nq, uint32_t query_dim,
+                                          uint32_t k, uint32_t ef, uint64_t* out_ids, float* out_dist,
+                                          uint32_t* out_count, isl_search_stats* stats) {
+  bool trivial;
+  ISL_TRY(search_checks(idx, queries, nq, query_dim, k, &ef, &trivial, /*need_vectors=*/false));
+  if (trivial) {
+    fill_empty(nq, k, out_ids, out_dist, out_count, stats);
+    return ISL_OK;
+  }
+  DeviceGuard g(idx->device);
+  std::shared_lock<std::shared_mutex> lock(idx->mu);
+  ScratchLease sc(idx);
+  ISL_TRY(sc.status);
+  return adc_recompute_on_scratch(idx, sc.get(), queries, nq, k, ef, out_ids, out_dist, out_count, stats, nullptr);
 }
 
 isl_status isl_index_last_recompute(const isl_index* idx, uint64_t* unique_nodes, float* traverse_ms, float* encoder_ms,

@@ -212,9 +212,11 @@ struct isl_shard {
 namespace {
 
 // search (records) -> exchange -> merge on sc->stream.  d_queries already staged ([nq][q_ld]).
-isl_status sharded_core(const isl_index* idx, isl_shard* sh, SearchScratch* sc, uint64_t id_base, const float* q,
-                        uint32_t q_ld, uint64_t nq, uint32_t k, uint32_t ef, bool trivial, uint64_t* d_out_ids,
-                        float* d_out_dist, uint32_t* d_out_count) {
+// mode: ISL_SHARD_EXACT (q = staged device queries), ISL_SHARD_ADC_RERANK / ISL_SHARD_ADC_RECOMPUTE (h_queries = the
+// caller's host queries: those pipelines stage them themselves).
+isl_status sharded_core(const isl_index* idx, isl_shard* sh, SearchScratch* sc, uint64_t id_base, int mode, const float* q,
+                        uint32_t q_ld, const float* h_queries, uint64_t nq, uint32_t k, uint32_t ef, bool trivial,
+                        uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_count) {
   NcclApi* api = nccl_api();
   cudaStream_t st = sc->stream;
   const uint64_t cnt = nq * k;
@@ -245,6 +247,10 @@ isl_status sharded_core(const isl_index* idx, isl_shard* sh, SearchScratch* sc, 
     } else {
       ISL_CUDA_TRY(cudaMemsetAsync(sc->packed.p, 0xff, cnt * 16, st));
     }
+  } else if (mode == ISL_SHARD_ADC_RERANK) {
+    ISL_TRY(pq_search_on_scratch(2, idx, sc, h_queries, nq, k, ef, 0.0f, nullptr, nullptr, nullptr, nullptr, &so));
+  } else if (mode == ISL_SHARD_ADC_RECOMPUTE) {
+    ISL_TRY(adc_recompute_on_scratch(idx, sc, h_queries, nq, k, ef, nullptr, nullptr, nullptr, nullptr, &so));
   } else {
     ISL_TRY(search_device(idx, sc, q, q_ld, nq, k, ef, nullptr, nullptr, nullptr, nullptr, &so));
   }
@@ -406,8 +412,8 @@ isl_status isl_index_search_sharded(const isl_index* idx, isl_shard* sh, uint64_
   if (ld != query_dim) ISL_CUDA_TRY(cudaMemsetAsync(sc->q_stage.p, 0, nq * ld * 4, st));
   ISL_CUDA_TRY(cudaMemcpy2DAsync(sc->q_stage.p, (size_t)ld * 4, queries, (size_t)query_dim * 4, (size_t)query_dim * 4, nq,
                                  cudaMemcpyHostToDevice, st));
-  ISL_TRY(sharded_core(idx, sh, sc.get(), id_base, sc->q_stage.p, ld, nq, k, ef, trivial, sc->out_ids.p, sc->out_dist.p,
-                       sc->out_count.p));
+  ISL_TRY(sharded_core(idx, sh, sc.get(), id_base, ISL_SHARD_EXACT, sc->q_stage.p, ld, nullptr, nq, k, ef, trivial,
+                       sc->out_ids.p, sc->out_dist.p, sc->out_count.p));
   ISL_CUDA_TRY(cudaMemcpyAsync(out_ids, sc->out_ids.p, nq * k * 8, cudaMemcpyDeviceToHost, st));
   ISL_CUDA_TRY(cudaMemcpyAsync(out_dist, sc->out_dist.p, nq * k * 4, cudaMemcpyDeviceToHost, st));
   if (out_count) ISL_CUDA_TRY(cudaMemcpyAsync(out_count, sc->out_count.p, nq * 4, cudaMemcpyDeviceToHost, st));
@@ -429,7 +435,43 @@ isl_status isl_index_search_sharded_dev(const isl_index* idx, isl_shard* sh, uin
   const float* q = d_queries;
   uint32_t q_ld = query_dim;
   if (!trivial) ISL_TRY(stage_device_queries(idx, sc.get(), d_queries, nq, query_dim, &q, &q_ld));
-  ISL_TRY(sharded_core(idx, sh, sc.get(), id_base, q, q_ld, nq, k, ef, trivial, d_out_ids, d_out_dist, d_out_count));
+  ISL_TRY(sharded_core(idx, sh, sc.get(), id_base, ISL_SHARD_EXACT, q, q_ld, nullptr, nq, k, ef, trivial, d_out_ids, d_out_dist,
+                       d_out_count));
+  return sharded_finish(idx, sh, sc.get(), trivial);
+}
+
+// The sharded form of isl_index_search_adc_rerank / isl_index_search_adc_recompute: every rank runs the ADC traversal
+// (+ encoder) + exact rerank on its shard, the rerank launch writes the exchange records, then exchange + merge.
+isl_status isl_index_search_sharded_adc(const isl_index* idx, isl_shard* sh, uint64_t id_base, int32_t mode, const float* queries,
+                                        uint64_t nq, uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* out_ids,
+                                        float* out_dist, uint32_t* out_count) {
+  if (mode != ISL_SHARD_ADC_RERANK && mode != ISL_SHARD_ADC_RECOMPUTE)
+    return fail(ISL_INVALID_ARGUMENT, "mode must be ISL_SHARD_ADC_RERANK or ISL_SHARD_ADC_RECOMPUTE");
+  if (!sh) return fail(ISL_INVALID_ARGUMENT, "shard handle is null");
+  if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
+  if (nq == 0 || k == 0) return fail(ISL_INVALID_ARGUMENT, "sharded search needs nq > 0 and k > 0 on every rank");
+  if (!queries || !out_ids || !out_dist) return fail(ISL_INVALID_ARGUMENT, "null pointer");
+  bool trivial = idx->n == 0;
+  if (!trivial) ISL_TRY(search_checks(idx, queries, nq, query_dim, k, &ef, &trivial, mode == ISL_SHARD_ADC_RERANK));
+  DeviceGuard g(sh->device);
+  std::shared_lock<std::shared_mutex> lock(idx->mu);
+  std::lock_guard<std::mutex> xl(sh->mu);
+  ScratchLease sc(idx);
+  ISL_TRY(sc.status);
+  cudaStream_t st = sc->stream;
+  ISL_TRY(ensure(sc->out_ids, nq * k));
+  ISL_TRY(ensure(sc->out_dist, nq * k));
+  ISL_TRY(ensure(sc->out_count, nq));
+  DevBuf<uint64_t> m_ids;  // the pipelines use sc->out_* for their own (unmerged) results
+  DevBuf<float> m_dist;
+  DevBuf<uint32_t> m_cnt;
+  ISL_CUDA_TRY(m_ids.alloc(nq * k));
+  ISL_CUDA_TRY(m_dist.alloc(nq * k));
+  ISL_CUDA_TRY(m_cnt.alloc(nq));
+  ISL_TRY(sharded_core(idx, sh, sc.get(), id_base, mode, nullptr, 0, queries, nq, k, ef, trivial, m_ids.p, m_dist.p, m_cnt.p));
+  ISL_CUDA_TRY(cudaMemcpyAsync(out_ids, m_ids.p, nq * k * 8, cudaMemcpyDeviceToHost, st));
+  ISL_CUDA_TRY(cudaMemcpyAsync(out_dist, m_dist.p, nq * k * 4, cudaMemcpyDeviceToHost, st));
+  if (out_count) ISL_CUDA_TRY(cudaMemcpyAsync(out_count, m_cnt.p, nq * 4, cudaMemcpyDeviceToHost, st));
   return sharded_finish(idx, sh, sc.get(), trivial);
 }
 

@@ -39,25 +39,20 @@ isl_status isl_index_attach_pq(isl_index* idx, const isl_pq* pq, const uint16_t*
   return ISL_OK;
 }
 
-static isl_status pq_search_common(int mode, const isl_index* idx, const float* queries, uint64_t nq,
-                                   uint32_t query_dim, uint32_t k, uint32_t ef, float rerank_ratio,
-                                   uint64_t* out_ids, float* out_dist, uint32_t* out_count,
-                                   isl_search_stats* stats) {
-  bool trivial;
-  ISL_TRY(search_checks(idx, queries, nq, query_dim, k, &ef, &trivial));
-  if (trivial) {
-    fill_empty(nq, k, out_ids, out_dist, out_count, stats);
-    return ISL_OK;
-  }
+}  // extern "C"
+
+namespace isl {
+// The PQ searches on a leased scratch; the caller holds the device guard and the handle's shared lock and has run
+// search_checks.  shard != null (mode 2 only): the rerank launch also writes the shard-exchange records, the host
+// copies of the results and the final synchronisation are left to the caller (api_shard.cu).
+isl_status pq_search_on_scratch(int mode, const isl_index* idx, SearchScratch* sc, const float* queries, uint64_t nq, uint32_t k,
+                                uint32_t ef, float rerank_ratio, uint64_t* out_ids, float* out_dist, uint32_t* out_count,
+                                isl_search_stats* stats, const ShardOut* shard) {
   if (!idx->pq) return fail(ISL_PQ_ERROR, "no product quantizer attached (isl_index_attach_pq)");
   if (mode == 1 && (!(rerank_ratio > 0.0f) || rerank_ratio > 1.0f))
     return fail(ISL_INVALID_ARGUMENT, "rerank_ratio must be in (0, 1]");
-  if (!out_ids || !out_dist) return fail(ISL_INVALID_ARGUMENT, "output pointer is null");
+  if (!shard && (!out_ids || !out_dist)) return fail(ISL_INVALID_ARGUMENT, "output pointer is null");
   const isl_pq* pq = idx->pq;
-  DeviceGuard g(idx->device);
-  std::shared_lock<std::shared_mutex> lock(idx->mu);
-  ScratchLease sc(idx);
-  ISL_TRY(sc.status);
   const uint32_t m = (uint32_t)pq->cfg.num_subquantizers;
   const uint32_t lut_floats = m * pq->ksub;
 
@@ -141,14 +136,16 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
     a.u_cap = u_cap_r;
     a.lut_smem_floats = 0;
     a.phase = 2;
+    if (shard) a.shard = *shard;
     ISL_TRY(launch_search(pr, a, st));
     ISL_CUDA_TRY(cudaEventRecord(sc->ev1, st));
+    if (shard) return ISL_OK;  // records written; exchange, merge and the final synchronisation follow in api_shard.cu
     ISL_CUDA_TRY(cudaMemcpyAsync(out_ids, sc->out_ids.p, nq * k * 8, cudaMemcpyDeviceToHost, st));
     ISL_CUDA_TRY(cudaMemcpyAsync(out_dist, sc->out_dist.p, nq * k * 4, cudaMemcpyDeviceToHost, st));
     if (out_count) ISL_CUDA_TRY(cudaMemcpyAsync(out_count, sc->out_count.p, nq * 4, cudaMemcpyDeviceToHost, st));
     if (stats)
       ISL_CUDA_TRY(cudaMemcpyAsync(stats, sc->out_stats.p, nq * sizeof(isl_search_stats), cudaMemcpyDeviceToHost, st));
-    return search_finish(idx, sc.get(), 3);
+    return search_finish(idx, sc, 3);
   }
 
   // |AQ| <= max_degree / a at all times (it gains at most max_degree entries per expansion and
@@ -233,7 +230,27 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
   if (out_count) ISL_CUDA_TRY(cudaMemcpyAsync(out_count, sc->out_count.p, nq * 4, cudaMemcpyDeviceToHost, st));
   if (stats)
     ISL_CUDA_TRY(cudaMemcpyAsync(stats, sc->out_stats.p, nq * sizeof(isl_search_stats), cudaMemcpyDeviceToHost, st));
-  return search_finish(idx, sc.get(), 2);
+  return search_finish(idx, sc, 2);
+}
+
+}  // namespace isl
+
+extern "C" {
+
+static isl_status pq_search_common(int mode, const isl_index* idx, const float* queries, uint64_t nq, uint32_t query_dim,
+                                   uint32_t k, uint32_t ef, float rerank_ratio, uint64_t* out_ids, float* out_dist,
+                                   uint32_t* out_count, isl_search_stats* stats) {
+  bool trivial;
+  ISL_TRY(search_checks(idx, queries, nq, query_dim, k, &ef, &trivial));
+  if (trivial) {
+    fill_empty(nq, k, out_ids, out_dist, out_count, stats);
+    return ISL_OK;
+  }
+  DeviceGuard g(idx->device);
+  std::shared_lock<std::shared_mutex> lock(idx->mu);
+  ScratchLease sc(idx);
+  ISL_TRY(sc.status);
+  return pq_search_on_scratch(mode, idx, sc.get(), queries, nq, k, ef, rerank_ratio, out_ids, out_dist, out_count, stats, nullptr);
 }
 
 isl_status isl_index_set_rerank_limit(isl_index* idx, uint32_t limit) {

@@ -57,9 +57,26 @@ def main():
         if g == rank:
             mine = (lo, hi, levels, off, nbrs, entry)
     o_ids, o_dst, o_cnt = orc.merge_topk(np.stack(ids_l), np.stack(dst_l), k)
+    # the same for "PQ ADC traversal + exact rerank": one quantizer for the whole index, per-shard codes
+    from islands_b200 import PQConfig, ProductQuantizer
+
+    pq = ProductQuantizer(d, PQConfig(16, 32, 6, 5))
+    pq.train(x[:2000])
+    books = pq.codebooks()
+    codes = pq.encode(x)
+    a_ids, a_dst = [], []
+    for g in range(world):
+        lo, hi = shard_range(n, g, world)
+        levels = orc.draw_levels(100 + g, hi - lo, cfg.ml, cfg.max_layers)
+        off, nbrs, entry, _ = orc.leann_build(cfg._s, x[lo:hi], levels, batch=16, threads=threads)
+        ids, dst, _ = orc.leann_search_adc_rerank(cfg._s, x[lo:hi], off, nbrs, entry, books, codes[lo:hi], q, k, ef, threads=threads)
+        a_ids.append(np.where(ids == INVALID, INVALID, ids + np.uint64(lo)))
+        a_dst.append(dst)
+    oa_ids, oa_dst, oa_cnt = orc.merge_topk(np.stack(a_ids), np.stack(a_dst), k)
 
     lo, hi, levels, off, nbrs, entry = mine
     idx = LeannIndex.from_csr(cfg, x[lo:hi], off, nbrs, levels, entry)
+    idx.attach_pq(pq, codes[lo:hi])
     comm = make_shard_comm()
     sharded = ShardedLeannIndex(idx, lo, n, comm)
     tq = torch.from_numpy(q).to(dev)
@@ -77,11 +94,14 @@ def main():
             ok &= bool(np.array_equal(t_ids.cpu().numpy().view(np.uint64), o_ids)
                        and np.array_equal(t_dst.cpu().numpy().view(np.uint32), o_dst.view(np.uint32))
                        and np.array_equal(t_cnt.cpu().numpy().astype(np.uint32), o_cnt))
+            ids, dst, cnt = idx.search_sharded_adc(comm, lo, q, k, ef)  # sharded ADC traversal + exact rerank
+            ok &= bool(np.array_equal(ids, oa_ids) and np.array_equal(dst.view(np.uint32), oa_dst.view(np.uint32)) and np.array_equal(cnt, oa_cnt))
+        sharded.search_batch_dev(tq, k, ef, t_ids, t_dst, t_cnt)
         timing[engine] = [round(v, 4) for v in comm.last_timing()]
     flags = [None] * world
     dist.all_gather_object(flags, ok)
     if rank == 0:
-        line = {"test": "sharded search vs oracle sub-graph searches + orc_merge_topk", "world": world, "n": n, "d": d, "nq": nq, "k": k, "ef": ef,
+        line = {"test": "sharded search (exact and ADC traversal + rerank) vs oracle sub-graph searches + orc_merge_topk", "world": world, "n": n, "d": d, "nq": nq, "k": k, "ef": ef,
                 "bit_exact_on_every_rank": all(flags), "per_rank": flags,
                 "last_call_ms_rank0 (search, exchange, merge)": timing}
         print(json.dumps(line))
