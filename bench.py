@@ -582,6 +582,10 @@ def main():
                                   "kernel_ms": ms, "e2e_qps_host_buffers": nq / wall, "e2e_steps": a.steps,
                                   "algorithmic_gbps": b / ms / 1e6, "frac": b / ms / 1e6 / peak,
                                   "n_adc": float(st.n_adc.mean()), "n_rerank": float(st.n_rerank.mean()),
+                                  # every traversal access is one 32-byte sector (a code row, an 8-sector list per hop): the rate against the
+                                  # measured ceiling of independent random sectors out of L2 (profiles/r01_sector_ceiling.txt: 210-220 G/s)
+                                  "traversal_sectors_per_s": (int(st.n_adc.sum()) * (pq_m // 32 if pq_m >= 32 else 1) + int(st.n_hop.sum()) * 8) / (ms * 1e-3),
+                                  "frac_of_l2_sector_ceiling": (int(st.n_adc.sum()) * (pq_m // 32 if pq_m >= 32 else 1) + int(st.n_hop.sum()) * 8) / (ms * 1e-3) / 215e9,
                                   "bitset_free_results_equal_bitset_results": same_adc,
                                   "bound": "instruction latency of the per-hop chain; the byte roofline is not the limiter: every access is one 32-byte "
                                            "sector (profiles/r01_sector_ceiling.txt: 33-35 G random sectors/s is the HBM ceiling the bitset version sat on)",

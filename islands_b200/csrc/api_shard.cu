@@ -167,7 +167,7 @@ struct PeerTable {
   unsigned int* flags[kMaxPeers];   // peer r's flag array [world]
 };
 
-__global__ void peer_signal_wait_kernel(PeerTable t, int rank, int world, unsigned int step) {
+__global__ void peer_signal_wait_kernel(PeerTable t, int rank, int world, unsigned int step, unsigned int* error_flag) {
   const int r = threadIdx.x;  // one thread per peer
   if (r < world) {
     __threadfence_system();
@@ -175,7 +175,13 @@ __global__ void peer_signal_wait_kernel(PeerTable t, int rank, int world, unsign
     *theirs = step;
     __threadfence_system();
     volatile unsigned int* mine = t.flags[rank] + r;
+    const long long t0 = clock64();
     while (*mine < step) {
+      // a peer that never arrives (its process died) must not hang this GPU: give up after ~10 s of SM clocks
+      if (clock64() - t0 > 20000000000ll) {
+        atomicExch(error_flag, 2u);
+        break;
+      }
     }
     __threadfence_system();
   }
@@ -240,6 +246,7 @@ isl_status sharded_core(const isl_index* idx, isl_shard* sh, SearchScratch* sc, 
   }
   ISL_CUDA_TRY(cudaEventRecord(sh->ev[0], st));
   if (trivial) {  // an empty shard contributes only padding records
+    ISL_CUDA_TRY(cudaMemsetAsync(sc->counters.p, 0, 4 * sizeof(unsigned int), st));
     if (use_peer) {
       ISL_CUDA_TRY(cudaMemsetAsync(sc->packed.p, 0xff, cnt * 16, st));
       for (int r = 0; r < sh->world; ++r)
@@ -256,7 +263,7 @@ isl_status sharded_core(const isl_index* idx, isl_shard* sh, SearchScratch* sc, 
   }
   ISL_CUDA_TRY(cudaEventRecord(sh->ev[1], st));
   if (use_peer) {
-    peer_signal_wait_kernel<<<1, 32, 0, st>>>(sh->table, sh->rank, sh->world, sh->step);
+    peer_signal_wait_kernel<<<1, 32, 0, st>>>(sh->table, sh->rank, sh->world, sh->step, sc->counters.p + 3);
     count_launch();
     ISL_CUDA_TRY(cudaGetLastError());
   } else {
@@ -274,6 +281,9 @@ isl_status sharded_finish(const isl_index* idx, isl_shard* sh, SearchScratch* sc
   } else {
     ISL_TRY(search_finish(idx, sc, 3));
   }
+  unsigned int peer_err = 0;
+  ISL_CUDA_TRY(cudaMemcpy(&peer_err, sc->counters.p + 3, sizeof(peer_err), cudaMemcpyDeviceToHost));
+  if (peer_err) return fail(ISL_CUDA_ERROR, "sharded search: a peer rank did not reach the exchange (peer-store handshake timed out)");
   cudaEventElapsedTime(&sh->search_ms, sh->ev[0], sh->ev[1]);
   cudaEventElapsedTime(&sh->exchange_ms, sh->ev[1], sh->ev[2]);
   cudaEventElapsedTime(&sh->merge_ms, sh->ev[2], sh->ev[3]);

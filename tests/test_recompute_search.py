@@ -253,3 +253,44 @@ def test_per_hop_recompute_equals_the_stored_vector_search(gpu_lib, metric, prun
     ids_c, dist_c, cnt_c = index.search_recompute_batch(queries[:16], k, ef)
     assert np.array_equal(ids_c, ids_a[:16]) and np.array_equal(dist_c.view(np.uint32), dist_a[:16].view(np.uint32))
     index.free()
+
+
+def test_split_precision_recompute_at_bert_base_shape(gpu_lib):
+    """The same bar at the shape BASELINE configs[4] names (BERT-base: 12 layers, hidden 768, 110M parameters, random
+    init N(0, 0.02)): index over the fp32 oracle's embeddings, recompute search through the split-precision encoder —
+    traversal counters identical, recall@10 within 0.002, distances within 5e-5, ids almost everywhere the same; the
+    plain bf16 encoder on the same index is reported beside it (and must stay within its documented 0.01)."""
+    from islands_b200 import Encoder, EncoderConfig, LeannConfig, LeannIndex, PQConfig, ProductQuantizer
+    from oracle.encoder_oracle import bert_embed
+
+    n, nq, S, k, ef = 1200, 400, 16, 10, 64
+    rng = np.random.RandomState(21)
+    cfg3 = EncoderConfig(precision=1)
+    enc3 = Encoder(cfg3).init_random(seed=46, stddev=0.02)
+    (tok, ln), (qtok, qln) = _token_table(rng, n, nq, S, cfg3.vocab_size, 60)
+    sd = enc3.state_dict()
+    vectors, queries = bert_embed(sd, cfg3, tok, ln), bert_embed(sd, cfg3, qtok, qln)
+    index = LeannIndex(LeannConfig(m=12, m0=24, ef_construction=64))
+    index.build(vectors, n, seed=5, batch=64)
+    pq = ProductQuantizer(768, PQConfig(32, 64, 8, 1))
+    pq.train(vectors)
+    index.attach_pq(pq, pq.encode(vectors))
+    ids_a, dist_a, cnt_a, st_a = index.search_adc_rerank_batch(queries, k, ef, stats=True)
+    vn = vectors / np.linalg.norm(vectors, axis=1, keepdims=True)
+    qn = queries / np.linalg.norm(queries, axis=1, keepdims=True)
+    gt = np.argsort(-(qn @ vn.T), axis=1, kind="stable")[:, :k]
+    ra = _recall(ids_a, gt, k)
+    index.set_recompute(enc3, tok, ln)
+    ids_b, dist_b, cnt_b, st_b = index.search_adc_recompute_batch(queries, k, ef, stats=True)
+    for f in ("n_hop", "n_edge", "n_adc", "n_rerank"):
+        assert np.array_equal(getattr(st_a, f), getattr(st_b, f)), f
+    rb = _recall(ids_b, gt, k)
+    assert abs(ra - rb) <= 0.002, (ra, rb)
+    same = ids_a == ids_b
+    assert same.mean() > 0.99, same.mean()
+    assert np.abs(dist_a[same] - dist_b[same]).max() < 5e-5
+    enc1 = Encoder(EncoderConfig()).init_random(seed=46, stddev=0.02)  # same weights, bf16 operands
+    index.set_recompute(enc1, tok, ln)
+    ids_c, _, _ = index.search_adc_recompute_batch(queries, k, ef)
+    assert abs(ra - _recall(ids_c, gt, k)) <= 0.01
+    index.free()
