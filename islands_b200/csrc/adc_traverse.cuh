@@ -27,10 +27,16 @@
 
 namespace isl {
 
+// Bag entry: kd = (bits of the table distance + 1) | expanded << 31, id = node id.  An EMPTY slot is kd = 0x80000000
+// ("expanded", distance part 0): it loses every max over the distance parts (a real entry is >= 1) and every unsigned min
+// over the raw words (an unexpanded entry is < 0x80000000), so neither reduction needs a validity test.
+constexpr uint32_t kBagExpanded = 0x80000000u;
+constexpr uint32_t kBagDistMask = 0x7fffffffu;
+
 template <int NR>
 struct RegBag {
   uint32_t kd[NR];
-  uint32_t ki[NR];
+  uint32_t id[NR];
 };
 
 // Location of an entry of the bag: row (register index) and lane.  Warp-uniform.
@@ -38,85 +44,112 @@ struct BagPos {
   uint32_t row, lane;
 };
 
-// argmax of (kd, id) over the occupied slots (slot i = row i / 32 of lane i % 32 is occupied iff i < r_len).
-// All lanes call; the result is warp-uniform.  Fast path: exactly one entry carries the greatest kd (the rule unless
-// distances tie exactly); otherwise the id decides among the entries that share it.
+// argmax of (distance, id) over the bag.  All lanes call; the result is warp-uniform.  Fast path: exactly one entry
+// carries the greatest distance (the rule unless distances tie exactly); otherwise the greatest id among them wins.
+// out_bits = bits of that distance, out_exp = its expanded flag.
 template <int NR>
-__device__ __forceinline__ void bag_argmax(const RegBag<NR>& b, uint32_t r_len, uint32_t* out_kd, uint32_t* out_ki, BagPos* pos) {
-  const uint32_t lane = lane_id();
+__device__ __forceinline__ void bag_argmax(const RegBag<NR>& b, uint32_t* out_bits, uint32_t* out_id, bool* out_exp, BagPos* pos) {
+  constexpr uint32_t FULL = 0xffffffffu;
   uint32_t m = 0;
 #pragma unroll
-  for (int j = 0; j < NR; ++j) m = max(m, (uint32_t)(j * 32) + lane < r_len ? b.kd[j] : 0u);
-  const uint32_t top = __reduce_max_sync(0xffffffffu, m);
-  uint32_t row = 0, sel_i = 0, cnt = 0;
+  for (int j = 0; j < NR; ++j) m = max(m, b.kd[j] & kBagDistMask);
+  const uint32_t top = __reduce_max_sync(FULL, m);
+  uint32_t hit = 0, sel_id = 0, sel_kd = 0;
 #pragma unroll
   for (int j = 0; j < NR; ++j) {
-    const bool eq = b.kd[j] == top && (uint32_t)(j * 32) + lane < r_len;
-    if (eq && (cnt == 0 || (b.ki[j] >> 1) > (sel_i >> 1))) {  // within the lane: the greatest id among its matches
-      row = j;
-      sel_i = b.ki[j];
+    if ((b.kd[j] & kBagDistMask) == top) {
+      hit |= 1u << j;
+      sel_id = b.id[j];
+      sel_kd = b.kd[j];
     }
-    cnt += eq ? 1u : 0u;
   }
-  const uint32_t bal = __ballot_sync(0xffffffffu, cnt != 0);
+  const uint32_t bal = __ballot_sync(FULL, hit != 0);
+  const bool multi = (bal & (bal - 1)) != 0 || __any_sync(FULL, (hit & (hit - 1)) != 0);
   uint32_t owner = __ffs(bal) - 1;
-  if (bal & (bal - 1)) {  // several lanes hold the greatest kd: the greatest id wins (ids are unique)
-    const uint32_t top_id = __reduce_max_sync(0xffffffffu, cnt ? (sel_i >> 1) : 0u);
-    owner = __ffs(__ballot_sync(0xffffffffu, cnt != 0 && (sel_i >> 1) == top_id)) - 1;
+  uint32_t row = 31 - __clz(hit);  // the lane's only match on the fast path (meaningful in the owner)
+  if (multi) {  // several entries share the greatest distance: the greatest id wins (ids are unique in the bag)
+    bool have = false;
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+      if ((b.kd[j] & kBagDistMask) == top && (!have || b.id[j] > sel_id)) {
+        have = true;
+        row = j;
+        sel_id = b.id[j];
+        sel_kd = b.kd[j];
+      }
+    }
+    const uint32_t top_id = __reduce_max_sync(FULL, have ? sel_id : 0u);
+    owner = __ffs(__ballot_sync(FULL, have && sel_id == top_id)) - 1;
   }
-  pos->row = __shfl_sync(0xffffffffu, row, owner);
+  const uint32_t packed = __shfl_sync(FULL, row | (sel_kd & kBagExpanded), owner);
+  pos->row = packed & kBagDistMask;
   pos->lane = owner;
-  *out_kd = top;
-  *out_ki = __shfl_sync(0xffffffffu, sel_i, owner);
+  *out_exp = (packed & kBagExpanded) != 0;
+  *out_bits = top - 1;
+  *out_id = __shfl_sync(FULL, sel_id, owner);
 }
 
-// argmin of (kd, id) over the occupied, unexpanded slots.  Returns false when there is none.
+// argmin of (distance, id) over the unexpanded entries.  Returns false when there is none.
 template <int NR>
-__device__ __forceinline__ bool bag_argmin_unexpanded(const RegBag<NR>& b, uint32_t r_len, uint32_t* out_id, BagPos* pos) {
-  const uint32_t lane = lane_id();
+__device__ __forceinline__ bool bag_argmin_unexpanded(const RegBag<NR>& b, uint32_t* out_id, BagPos* pos) {
+  constexpr uint32_t FULL = 0xffffffffu;
   uint32_t m = 0xffffffffu;
 #pragma unroll
-  for (int j = 0; j < NR; ++j) {
-    const bool un = (uint32_t)(j * 32) + lane < r_len && !(b.ki[j] & 1u);
-    m = min(m, un ? b.kd[j] : 0xffffffffu);
-  }
-  // a real entry never carries kd == 0xffffffff (NaN patterns are folded to 0x7fc00000)
-  const uint32_t low = __reduce_min_sync(0xffffffffu, m);
-  if (low == 0xffffffffu) return false;
-  uint32_t row = 0, sel_id = 0xffffffffu;
+  for (int j = 0; j < NR; ++j) m = min(m, b.kd[j]);
+  const uint32_t low = __reduce_min_sync(FULL, m);
+  if (low >= kBagExpanded) return false;  // every entry is expanded (or empty)
+  uint32_t hit = 0, sel_id = 0;
 #pragma unroll
   for (int j = 0; j < NR; ++j) {
-    const bool eq = b.kd[j] == low && (uint32_t)(j * 32) + lane < r_len && !(b.ki[j] & 1u);
-    if (eq && (b.ki[j] >> 1) < sel_id) {  // within the lane: the smallest id among its matches
-      row = j;
-      sel_id = b.ki[j] >> 1;
+    if (b.kd[j] == low) {
+      hit |= 1u << j;
+      sel_id = b.id[j];
     }
   }
-  const uint32_t bal = __ballot_sync(0xffffffffu, sel_id != 0xffffffffu);
+  const uint32_t bal = __ballot_sync(FULL, hit != 0);
+  const bool multi = (bal & (bal - 1)) != 0 || __any_sync(FULL, (hit & (hit - 1)) != 0);
   uint32_t owner = __ffs(bal) - 1;
-  if (bal & (bal - 1)) {  // several lanes hold the smallest kd: the smallest id wins
-    const uint32_t id = __reduce_min_sync(0xffffffffu, sel_id);
-    owner = __ffs(__ballot_sync(0xffffffffu, sel_id == id)) - 1;
+  uint32_t row = 31 - __clz(hit);
+  if (multi) {  // several unexpanded entries share the smallest distance: the smallest id wins
+    bool have = false;
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+      if (b.kd[j] == low && (!have || b.id[j] < sel_id)) {
+        have = true;
+        row = j;
+        sel_id = b.id[j];
+      }
+    }
+    const uint32_t low_id = __reduce_min_sync(FULL, have ? sel_id : 0xffffffffu);
+    owner = __ffs(__ballot_sync(FULL, have && sel_id == low_id)) - 1;
   }
-  pos->row = __shfl_sync(0xffffffffu, row, owner);
+  pos->row = __shfl_sync(FULL, row, owner);
   pos->lane = owner;
-  *out_id = __shfl_sync(0xffffffffu, sel_id, owner);
+  *out_id = __shfl_sync(FULL, sel_id, owner);
   return true;
 }
 
+// Resident CTAs per SM the kernel is compiled for: 2-byte table entries leave room for 21 queries per SM (8 KB table +
+// tie list + id cache), which needs <= 96 registers per thread; the large bags (ef up to 512) keep 128.
 template <int NR>
-__global__ void __launch_bounds__(32) adc_traverse_kernel(const SearchArgs a) {
+struct BagOccupancy {
+  static constexpr int kMinCtas = NR <= 8 ? 21 : 16;
+};
+
+template <int NR>
+__global__ void __launch_bounds__(32, BagOccupancy<NR>::kMinCtas) adc_traverse_kernel(const SearchArgs a) {
   constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: [table or, at the end of a query, the rank-sort scratch][ties][admitted-id cache]
-  float* lut_smem = reinterpret_cast<float*>(smem_raw);
-  const uint32_t table_bytes = max(a.lut_smem_floats * 4u, a.ef * 8u);  // the rank-sort scratch of a rerank limit reuses the table
+  // layout: [table (bf16 bits, 2 bytes per entry) or, at the end of a query, the rank-sort scratch][ties][admitted-id cache]
+  uint16_t* lut16 = reinterpret_cast<uint16_t*>(smem_raw);
+  const uint32_t table_bytes = max(a.lut_smem_floats * 2u, a.ef * 8u);  // the rank-sort scratch of a rerank limit reuses the table
   uint2* ties = reinterpret_cast<uint2*>(smem_raw + ((table_bytes + 15u) & ~15u));
   uint16_t* idc = reinterpret_cast<uint16_t*>(ties + kTieCap);
   const uint32_t lane = lane_id();
   const uint32_t slot = blockIdx.x;
   const uint32_t ef = a.ef;
   const bool novis = a.novis != 0;
+  const bool want_stats = a.stats != nullptr;
   uint32_t* vis = a.visited + (size_t)slot * a.vis_words;
   uint2* ties_spill = a.ties_global + (size_t)slot * ef;
   auto tie_ld = [&](uint32_t i) -> uint2 { return i < kTieCap ? ties[i] : __ldcg(ties_spill + (i - kTieCap)); };
@@ -145,10 +178,11 @@ __global__ void __launch_bounds__(32) adc_traverse_kernel(const SearchArgs a) {
     }
     if (a.luts == nullptr) {
       // build_distance_tables (pq.rs:307-338) straight into shared memory: LUT[j][c] = sum_t (q_jt - c_jct)^2, left
-      // fold, one centroid per lane, four independent fold chains in flight
+      // fold, one centroid per lane, four independent fold chains and three 16-byte pieces of each row in flight; the
+      // finished sum is rounded to bfloat16 (common.cuh: bf16_round_bits)
       const float* qv = a.queries + (size_t)qi * a.q_ld;
       const uint32_t nvec = a.pq_ld_sub >> 2;
-      constexpr int CC = 4;
+      constexpr int CC = 4, VC = 3;
       for (uint32_t j = 0; j < a.pq_m; ++j) {
         const float* qs = qv + (size_t)j * a.pq_dsub;
         for (uint32_t c0 = 0; c0 < a.pq_ksub; c0 += 32 * CC) {
@@ -160,20 +194,18 @@ __global__ void __launch_bounds__(32) adc_traverse_kernel(const SearchArgs a) {
             const uint32_t c = min(c0 + cc * 32 + lane, a.pq_ksub - 1);
             row[cc] = reinterpret_cast<const float4*>(a.pq_codebooks + ((size_t)j * a.pq_ksub + c) * a.pq_ld_sub);
           }
-          if (nvec <= 8) {
-            // every 16-byte piece of the four centroid rows in flight at once (up to 32 loads per lane: the bag is not
-            // live yet, so the registers are free): one L2 latency per subquantizer instead of one per piece
-            float4 y[CC][8];
+          for (uint32_t v0 = 0; v0 < nvec; v0 += VC) {
+            float4 y[CC][VC];
 #pragma unroll
-            for (int v = 0; v < 8; ++v)
+            for (int v = 0; v < VC; ++v)
 #pragma unroll
-              for (int cc = 0; cc < CC; ++cc) y[cc][v] = (uint32_t)v < nvec ? __ldg(row[cc] + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int cc = 0; cc < CC; ++cc) y[cc][v] = v0 + v < nvec ? __ldg(row[cc] + v0 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int v = 0; v < 8; ++v) {
-              if ((uint32_t)v < nvec) {
+            for (int v = 0; v < VC; ++v) {
+              if (v0 + v < nvec) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const uint32_t t = v * 4 + e;
+                  const uint32_t t = (v0 + v) * 4 + e;
                   if (t < a.pq_dsub) {
                     const float qe = __ldg(qs + t);
 #pragma unroll
@@ -186,89 +218,73 @@ __global__ void __launch_bounds__(32) adc_traverse_kernel(const SearchArgs a) {
                 }
               }
             }
-          } else {
-          for (uint32_t v = 0; v < nvec; ++v) {
-            float4 y[CC];
-#pragma unroll
-            for (int cc = 0; cc < CC; ++cc) y[cc] = __ldg(row[cc] + v);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint32_t t = v * 4 + e;
-              if (t < a.pq_dsub) {
-                const float qe = __ldg(qs + t);
-#pragma unroll
-                for (int cc = 0; cc < CC; ++cc) {
-                  const float ye = e == 0 ? y[cc].x : (e == 1 ? y[cc].y : (e == 2 ? y[cc].z : y[cc].w));
-                  const float diff = __fsub_rn(qe, ye);
-                  acc[cc] = __fadd_rn(acc[cc], __fmul_rn(diff, diff));
-                }
-              }
-            }
-          }
           }
 #pragma unroll
           for (int cc = 0; cc < CC; ++cc) {
             const uint32_t c = c0 + cc * 32 + lane;
-            if (c < a.pq_ksub) lut_smem[j * a.pq_ksub + c] = acc[cc];
+            if (c < a.pq_ksub) lut16[j * a.pq_ksub + c] = (uint16_t)(bf16_round_bits(__float_as_uint(acc[cc])) >> 16);
           }
         }
       }
     } else {
       const float* g = a.luts + (size_t)qi * a.pq_m * a.pq_ksub;
-      for (uint32_t i = lane; i < a.lut_smem_floats; i += 32) lut_smem[i] = __ldg(g + i);
+      for (uint32_t i = lane; i < a.lut_smem_floats; i += 32) lut16[i] = (uint16_t)(bf16_round_bits(__float_as_uint(__ldg(g + i))) >> 16);
     }
     __syncwarp();
 
     RegBag<NR> R;
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
-      R.kd[j] = 0xffffffffu;
-      R.ki[j] = 0xffffffffu;
+      R.kd[j] = kBagExpanded;
+      R.id[j] = 0xffffffffu;
     }
     uint32_t r_len = 0, n_ties = 0, tie_next = kTieCap;
-    uint32_t w_kd = 0xffffffffu, w_ki = 0xffffffffu;  // the worst entry (only meaningful once R is full) ...
-    BagPos w_pos{0, 0};                               // ... and where it sits
+    uint32_t w_bits = 0xffffffffu, w_id = 0xffffffffu;  // the worst entry (only meaningful once R is full) ...
+    bool w_exp = true;
+    BagPos w_pos{0, 0};                                 // ... and where it sits
     float w_d = 0.0f;
     uint64_t n_hop = 0, n_edge = 0, n_adc = 0;
 
     // ---- admission of one scored node (leann.rs:953-970), warp-uniform arguments ----------------------
     auto admit_one = [&](float d, uint32_t id) __attribute__((always_inline)) {
-      const uint32_t nkd = (d != d) ? 0x7fc00000u : __float_as_uint(d);
-      const uint32_t nki = id << 1;
+      const uint32_t nbits = (d != d) ? 0x7fc00000u : __float_as_uint(d);
       if (novis) {
         // no visited set: a node that is already in R was scored before and is admitted once
         bool same = false;
 #pragma unroll
-        for (int j = 0; j < NR; ++j) same = same || ((R.ki[j] ^ nki) < 2u);
+        for (int j = 0; j < NR; ++j) same = same || R.id[j] == id;
         if (__any_sync(FULL, same)) return;
         if (lane == 0) idc[id & (kIdcEntries - 1)] = (uint16_t)(id >> kIdcBits);
       }
       if (r_len < ef) {
-        const uint32_t row = r_len >> 5, ln = r_len & 31;
+        const uint32_t row = r_len >> 5;
+        const bool me = lane == (r_len & 31);
 #pragma unroll
         for (int j = 0; j < NR; ++j)
-          if ((uint32_t)j == row && lane == ln) {
-            R.kd[j] = nkd;
-            R.ki[j] = nki;
+          if ((uint32_t)j == row && me) {
+            R.kd[j] = nbits + 1u;
+            R.id[j] = id;
           }
         r_len++;
         if (r_len == ef) {
-          bag_argmax<NR>(R, r_len, &w_kd, &w_ki, &w_pos);
-          w_d = __uint_as_float(w_kd);
+          bag_argmax<NR>(R, &w_bits, &w_id, &w_exp, &w_pos);
+          w_d = __uint_as_float(w_bits);
         }
         return;
       }
       // full: the new entry takes the slot of the worst one (pop max, leann.rs:966-968)
-      const uint32_t e_kd = w_kd, e_ki = w_ki;
+      const uint32_t e_bits = w_bits, e_id = w_id;
+      const bool e_exp = w_exp;
+      const bool me = lane == w_pos.lane;
 #pragma unroll
       for (int j = 0; j < NR; ++j)
-        if ((uint32_t)j == w_pos.row && lane == w_pos.lane) {
-          R.kd[j] = nkd;
-          R.ki[j] = nki;
+        if ((uint32_t)j == w_pos.row && me) {
+          R.kd[j] = nbits + 1u;
+          R.id[j] = id;
         }
-      bag_argmax<NR>(R, r_len, &w_kd, &w_ki, &w_pos);
-      w_d = __uint_as_float(w_kd);
-      if (!(e_ki & 1u) && !of_lt(w_d, __uint_as_float(e_kd))) {
+      bag_argmax<NR>(R, &w_bits, &w_id, &w_exp, &w_pos);
+      w_d = __uint_as_float(w_bits);
+      if (!e_exp && !of_lt(w_d, __uint_as_float(e_bits))) {
         // an evicted, unexpanded node stays expandable while its distance equals the worst distance in R
         // (leann.rs:924-928 uses a strict `>`); see search_core.cuh for the capacity argument
         if (n_ties == tie_next) {
@@ -288,7 +304,7 @@ __global__ void __launch_bounds__(32) adc_traverse_kernel(const SearchArgs a) {
         if (n_ties >= kTieCap + ef) {
           if (lane == 0) atomicExch(a.error_flag, 1u);
         } else {
-          if (lane == 0) tie_st(n_ties, make_uint2(e_kd, e_ki >> 1));
+          if (lane == 0) tie_st(n_ties, make_uint2(e_bits, e_id));
           n_ties++;
           __syncwarp();
         }
@@ -305,10 +321,11 @@ __global__ void __launch_bounds__(32) adc_traverse_kernel(const SearchArgs a) {
         if (r_len < ef || dj < w_d) admit_one(dj, idj);  // raw f32 `<` (leann.rs:959)
       }
     };
+    auto lut_at = [&](uint32_t i) -> float { return __uint_as_float((uint32_t)lut16[i] << 16); };
     auto adc_of = [&](uint32_t nid) -> float {  // table_distance (pq.rs:341-348) of one node
       float sacc = 0.0f;
       const uint8_t* cd = a.codes8 + (size_t)nid * a.pq_m;
-      for (uint32_t j = 0; j < a.pq_m; ++j) sacc = __fadd_rn(sacc, lut_smem[j * a.pq_ksub + cd[j]]);
+      for (uint32_t j = 0; j < a.pq_m; ++j) sacc = __fadd_rn(sacc, lut_at(j * a.pq_ksub + cd[j]));
       return __fsqrt_rn(sacc);
     };
 
@@ -326,11 +343,12 @@ __global__ void __launch_bounds__(32) adc_traverse_kernel(const SearchArgs a) {
     for (;;) {
       uint32_t cur;
       BagPos cp;
-      if (bag_argmin_unexpanded<NR>(R, r_len, &cur, &cp)) {
+      if (bag_argmin_unexpanded<NR>(R, &cur, &cp)) {
+        const bool me = lane == cp.lane;
 #pragma unroll
         for (int j = 0; j < NR; ++j)
-          if ((uint32_t)j == cp.row && lane == cp.lane) R.ki[j] |= 1u;
-        if (r_len == ef && cp.row == w_pos.row && cp.lane == w_pos.lane) w_ki |= 1u;  // the cached copy of the worst entry sees the flag too
+          if ((uint32_t)j == cp.row && me) R.kd[j] |= kBagExpanded;
+        if (r_len == ef && cp.row == w_pos.row && cp.lane == w_pos.lane) w_exp = true;  // the cached copy of the worst entry sees the flag too
       } else {
         // smallest live tie, if any; every lane scans the whole list so that the result is provably warp-uniform
         int best = -1;
@@ -376,7 +394,7 @@ __global__ void __launch_bounds__(32) adc_traverse_kernel(const SearchArgs a) {
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           const bool valid = nid[r] != 0xffffffffu;
-          if (sentinel) n_edge += __popc(__ballot_sync(FULL, valid));
+          if (sentinel && want_stats) n_edge += __popc(__ballot_sync(FULL, valid));
           chk[r] = valid && nid[r] < a.n;
           if (!a.lists_unique && !novis) {  // first of its value in this half
             const uint32_t same = __match_any_sync(FULL, nid[r]);
@@ -408,7 +426,7 @@ __global__ void __launch_bounds__(32) adc_traverse_kernel(const SearchArgs a) {
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           float sacc = 0.0f;  // table_distance (pq.rs:341-348): left fold over the subquantizers
-          const float* lj = lut_smem;
+          const uint16_t* lj = lut16;
 #pragma unroll
           for (int v = 0; v < 2; ++v) {
             if ((uint32_t)v < nv) {
@@ -416,14 +434,14 @@ __global__ void __launch_bounds__(32) adc_traverse_kernel(const SearchArgs a) {
 #pragma unroll
               for (int k = 0; k < 16; ++k) {
                 const uint32_t code = __byte_perm(w[k >> 2], 0, 0x4440 + (k & 3));
-                sacc = __fadd_rn(sacc, lj[code]);
+                sacc = __fadd_rn(sacc, __uint_as_float((uint32_t)lj[code] << 16));
                 lj += a.pq_ksub;
               }
             }
           }
           const float adc = __fsqrt_rn(sacc);
           const bool unv = chk[r] && !(old[r] & (1u << (nid[r] & 31)));
-          n_adc += __popc(__ballot_sync(FULL, unv));
+          if (want_stats) n_adc += __popc(__ballot_sync(FULL, unv));
           admit_values(unv, adc, nid[r]);
         }
       }
@@ -440,20 +458,20 @@ __global__ void __launch_bounds__(32) adc_traverse_kernel(const SearchArgs a) {
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
         const uint32_t idx = j * 32 + lane;
-        if (idx < r_len) sk[idx] = make_uint2(R.kd[j], R.ki[j] >> 1);
+        if (idx < r_len) sk[idx] = make_uint2(R.kd[j] & kBagDistMask, R.id[j]);
       }
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
         const uint32_t idx = j * 32 + lane;
         if (idx < r_len) {
-          const uint64_t mine = ((uint64_t)R.kd[j] << 32) | (R.ki[j] >> 1);
+          const uint64_t mine = ((uint64_t)(R.kd[j] & kBagDistMask) << 32) | R.id[j];
           uint32_t rank = 0;
           for (uint32_t t = 0; t < r_len; ++t) {
             const uint2 o = sk[t];
             rank += (((uint64_t)o.x << 32) | o.y) < mine ? 1u : 0u;
           }
-          if (rank < n_surv) a.surv_ids[(size_t)qi * ef + rank] = R.ki[j] >> 1;
+          if (rank < n_surv) a.surv_ids[(size_t)qi * ef + rank] = R.id[j];
         }
       }
       __syncwarp();
@@ -461,7 +479,7 @@ __global__ void __launch_bounds__(32) adc_traverse_kernel(const SearchArgs a) {
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
         const uint32_t idx = j * 32 + lane;
-        if (idx < r_len) a.surv_ids[(size_t)qi * ef + idx] = R.ki[j] >> 1;
+        if (idx < r_len) a.surv_ids[(size_t)qi * ef + idx] = R.id[j];
       }
     }
     if (lane == 0) {
@@ -480,8 +498,8 @@ __global__ void __launch_bounds__(32) adc_traverse_kernel(const SearchArgs a) {
   }
 }
 
-__host__ __device__ constexpr size_t adc_traverse_smem_bytes(uint32_t lut_floats, uint32_t ef) {
-  const size_t table = lut_floats * 4u > ef * 8u ? lut_floats * 4u : ef * 8u;
+__host__ __device__ constexpr size_t adc_traverse_smem_bytes(uint32_t lut_entries, uint32_t ef) {
+  const size_t table = lut_entries * 2u > ef * 8u ? lut_entries * 2u : ef * 8u;
   return ((table + 15u) & ~(size_t)15u) + (size_t)kTieCap * 8 + (size_t)kIdcEntries * 2;
 }
 

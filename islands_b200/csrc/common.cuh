@@ -79,6 +79,15 @@ __host__ __device__ __forceinline__ bool key_lt64(float d1, uint64_t id1, float 
   return id1 < id2;
 }
 
+// Table entries of the ADC TRAVERSAL (isl_index_search_adc_rerank / _adc_recompute; include/islands_b200.h): every entry of
+// build_distance_tables (pq.rs:307-338) is rounded to bfloat16 (round to nearest even on the bit pattern, NaN -> quiet NaN)
+// before the traversal folds it; the per-query table is then 2 bytes per entry in shared memory, which doubles the resident
+// queries per SM.  The fold itself stays the f32 left fold + sqrt of pq.rs:341-348.  oracle.cpp restates the same rule.
+__host__ __device__ __forceinline__ uint32_t bf16_round_bits(uint32_t u) {
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc00000u;
+  return (u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u;
+}
+
 // The seeded draw stream of PruningStrategy::Proportional (include/islands_b200.h, isl_pruning_strategy).
 __host__ __device__ __forceinline__ uint64_t splitmix_mix(uint64_t z) {
   z ^= z >> 30;

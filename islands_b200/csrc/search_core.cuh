@@ -28,6 +28,9 @@
 namespace isl {
 
 constexpr uint32_t kTieCap = 64;
+
+// one entry of the ADC traversal's table: bfloat16-rounded (common.cuh)
+__device__ __forceinline__ float adc_table_entry(float x) { return __uint_as_float(bf16_round_bits(__float_as_uint(x))); }
 constexpr uint32_t kExpandedBit = 0x80000000u;
 
 // lean = the ADC-traversal-only kernel (MODE 3): no row staging ring, no query vector.
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
 #pragma unroll
             for (int cc = 0; cc < CC; ++cc) {
               const uint32_t c = c0 + cc * 32 + lane;
-              if (c < a.pq_ksub) lut_smem[j * a.pq_ksub + c] = acc[cc];
+              if (c < a.pq_ksub) lut_smem[j * a.pq_ksub + c] = ADC ? adc_table_entry(acc[cc]) : acc[cc];
             }
           }
         }
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       } else {
         const float* g = a.luts + (size_t)qi * a.pq_m * a.pq_ksub;
         if (a.lut_smem_floats) {
-          for (uint32_t i = lane; i < a.lut_smem_floats; i += 32) lut_smem[i] = __ldg(g + i);
+          for (uint32_t i = lane; i < a.lut_smem_floats; i += 32) lut_smem[i] = ADC ? adc_table_entry(__ldg(g + i)) : __ldg(g + i);
           __syncwarp();
           lut = lut_smem;
         } else {
@@ -485,12 +488,20 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     // table_distance (pq.rs:341-348) of node `nid`: left fold over the subquantizers, then sqrt
     auto adc_of = [&](uint32_t nid) -> float {
       float sacc = 0.0f;
+      // the ADC traversal folds bfloat16-rounded table entries (common.cuh; rounding is idempotent, so entries that were
+      // rounded when the table was staged pass through unchanged); the two-level search keeps the f32 table
       if (a.codes8) {
         const uint8_t* cd = a.codes8 + (size_t)nid * a.pq_m;
-        for (uint32_t j = 0; j < a.pq_m; ++j) sacc = __fadd_rn(sacc, lut[j * a.pq_ksub + cd[j]]);
+        for (uint32_t j = 0; j < a.pq_m; ++j) {
+          const float e = lut[j * a.pq_ksub + cd[j]];
+          sacc = __fadd_rn(sacc, ADC ? adc_table_entry(e) : e);
+        }
       } else {
         const uint16_t* cd = a.codes16 + (size_t)nid * a.pq_m;
-        for (uint32_t j = 0; j < a.pq_m; ++j) sacc = __fadd_rn(sacc, lut[j * a.pq_ksub + cd[j]]);
+        for (uint32_t j = 0; j < a.pq_m; ++j) {
+          const float e = lut[j * a.pq_ksub + cd[j]];
+          sacc = __fadd_rn(sacc, ADC ? adc_table_entry(e) : e);
+        }
       }
       return __fsqrt_rn(sacc);
     };

@@ -876,6 +876,21 @@ int32_t orc_leann_search_two_level(const isl_leann_config* cfg, const float* vec
   return ISL_OK;
 }
 
+// bfloat16 rounding of one table entry of the ADC traversal: round to nearest even on the bit pattern, NaN -> quiet NaN
+// (restated here independently of the product's common.cuh).
+static float bf16_round(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) {
+    u = 0x7fc00000u;
+  } else {
+    const uint32_t lsb = (u >> 16) & 1u;
+    u = (u + 0x7fffu + lsb) & 0xffff0000u;
+  }
+  std::memcpy(&x, &u, 4);
+  return x;
+}
+
 // PQ ADC traversal + exact rerank: the loop of leann.rs:899-988 with table_distance (pq.rs:341-348)
 // as the distance, then exact distances for the ef survivors and a final (dist,id) sort.
 int32_t orc_leann_search_adc_rerank(const isl_leann_config* cfg, const float* vectors, uint64_t n, uint32_t d,
@@ -910,6 +925,8 @@ int32_t orc_leann_search_adc_rerank(const isl_leann_config* cfg, const float* ve
     for (uint64_t qi = b; qi < e; ++qi) {
       const float* q = queries + qi * (uint64_t)d;
       orc_pq_build_tables(codebooks, m, ksub, dsub, q, lut.data());
+      // the traversal folds bfloat16-rounded table entries (definition: include/islands_b200.h, isl_index_search_adc_rerank)
+      for (float& t : lut) t = bf16_round(t);
       Visited& visited = vis[w];
       visited.reset(n);
       MinHeap cand;
