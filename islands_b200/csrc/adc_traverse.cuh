@@ -16,9 +16,13 @@
 // (profiles/r01_adc_traverse_novis_ncu_full.txt).  Results are bit-identical: same admission rule, same eviction
 // (the greatest (dist, id) key), same pop order (smallest (dist, id) key among the unexpanded), same tie list.
 //
-// Keys: kd = bits of the table distance (a square root: never negative, so the bit patterns order like the values;
-// NaN is folded onto 0x7fc00000, greatest, OrderedFloat's rule), ki = id << 1 | expanded; slot i (row i / 32 of lane
-// i % 32) is occupied iff i < r_len.  Reductions run on kd; the id decides only among entries that share the extreme kd.
+// Keys: the distance part of kd = bits of the table distance + 1 (a square root: never negative, so the bit patterns
+// order like the values; NaN is folded onto 0x7fc00000, greatest, OrderedFloat's rule); slot i (row i / 32 of lane
+// i % 32) is occupied iff i < r_len, empty slots are neutral for both reductions (see RegBag).  Reductions run on kd;
+// the id decides only among entries that share the extreme distance.
+// The per-query table holds bfloat16-rounded entries, 2 bytes each (common.cuh: bf16_round_bits; the definition of the
+// ADC traversal in include/islands_b200.h): 8 KB instead of 16 KB at m = 32, ksub = 128, so 21 queries are resident per
+// SM instead of 12 (profiles/r02_adc_bag_ncu.txt: issue slots 47 % -> 64 % busy).
 // (Measured and rejected: every lane keeping its NR entries sorted, so that the worst entry is the greatest column
 // top — fewer instructions per admission but a longer dependent chain: 7.85 ms against 7.16 ms at ef = 192.)
 #pragma once
@@ -27,16 +31,19 @@
 
 namespace isl {
 
-// Bag entry: kd = (bits of the table distance + 1) | expanded << 31, id = node id.  An EMPTY slot is kd = 0x80000000
-// ("expanded", distance part 0): it loses every max over the distance parts (a real entry is >= 1) and every unsigned min
-// over the raw words (an unexpanded entry is < 0x80000000), so neither reduction needs a validity test.
+// Bag entry: kd = (bits of the table distance + 1) | expanded << 31, ki = id << 1 | expanded.  An EMPTY slot is
+// kd = 0x80000000 ("expanded", distance part 0): it loses every max over the distance parts (a real entry is >= 1) and
+// every unsigned min over the raw words (an unexpanded entry is < 0x80000000), so neither reduction needs a validity
+// test.  The flag is kept twice on purpose: in kd it makes the argmin over the unexpanded entries one IMNMX per row; the
+// copy in ki travels with the id of the worst entry.  (Carrying it in a variable of its own made ptxas treat the branch
+// on it as divergent and wrap every collective of the loop in BSSY / WARPSYNC / BRA.DIV: 4656 -> 6472 SASS instructions.)
 constexpr uint32_t kBagExpanded = 0x80000000u;
 constexpr uint32_t kBagDistMask = 0x7fffffffu;
 
 template <int NR>
 struct RegBag {
   uint32_t kd[NR];
-  uint32_t id[NR];
+  uint32_t ki[NR];
 };
 
 // Location of an entry of the bag: row (register index) and lane.  Warp-uniform.
@@ -46,47 +53,44 @@ struct BagPos {
 
 // argmax of (distance, id) over the bag.  All lanes call; the result is warp-uniform.  Fast path: exactly one entry
 // carries the greatest distance (the rule unless distances tie exactly); otherwise the greatest id among them wins.
-// out_bits = bits of that distance, out_exp = its expanded flag.
+// out_bits = bits of that distance, out_ki = id << 1 | expanded of the entry.
 template <int NR>
-__device__ __forceinline__ void bag_argmax(const RegBag<NR>& b, uint32_t* out_bits, uint32_t* out_id, bool* out_exp, BagPos* pos) {
+__device__ __forceinline__ void bag_argmax(const RegBag<NR>& b, uint32_t* out_bits, uint32_t* out_ki, BagPos* pos) {
   constexpr uint32_t FULL = 0xffffffffu;
   uint32_t m = 0;
 #pragma unroll
   for (int j = 0; j < NR; ++j) m = max(m, b.kd[j] & kBagDistMask);
   const uint32_t top = __reduce_max_sync(FULL, m);
-  uint32_t hit = 0, sel_id = 0, sel_kd = 0;
+  uint32_t hit = 0, sel_ki = 0;
 #pragma unroll
   for (int j = 0; j < NR; ++j) {
     if ((b.kd[j] & kBagDistMask) == top) {
       hit |= 1u << j;
-      sel_id = b.id[j];
-      sel_kd = b.kd[j];
+      sel_ki = b.ki[j];
     }
   }
   const uint32_t bal = __ballot_sync(FULL, hit != 0);
-  const bool multi = (bal & (bal - 1)) != 0 || __any_sync(FULL, (hit & (hit - 1)) != 0);
+  const bool dup_in_lane = __any_sync(FULL, (hit & (hit - 1)) != 0);
+  const bool multi = ((bal & (bal - 1)) != 0) | dup_in_lane;
   uint32_t owner = __ffs(bal) - 1;
   uint32_t row = 31 - __clz(hit);  // the lane's only match on the fast path (meaningful in the owner)
   if (multi) {  // several entries share the greatest distance: the greatest id wins (ids are unique in the bag)
     bool have = false;
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
-      if ((b.kd[j] & kBagDistMask) == top && (!have || b.id[j] > sel_id)) {
+      if ((b.kd[j] & kBagDistMask) == top && (!have || b.ki[j] > sel_ki)) {  // ki orders like the id
         have = true;
         row = j;
-        sel_id = b.id[j];
-        sel_kd = b.kd[j];
+        sel_ki = b.ki[j];
       }
     }
-    const uint32_t top_id = __reduce_max_sync(FULL, have ? sel_id : 0u);
-    owner = __ffs(__ballot_sync(FULL, have && sel_id == top_id)) - 1;
+    const uint32_t top_ki = __reduce_max_sync(FULL, have ? sel_ki : 0u);
+    owner = __ffs(__ballot_sync(FULL, have && sel_ki == top_ki)) - 1;
   }
-  const uint32_t packed = __shfl_sync(FULL, row | (sel_kd & kBagExpanded), owner);
-  pos->row = packed & kBagDistMask;
+  pos->row = __shfl_sync(FULL, row, owner);
   pos->lane = owner;
-  *out_exp = (packed & kBagExpanded) != 0;
   *out_bits = top - 1;
-  *out_id = __shfl_sync(FULL, sel_id, owner);
+  *out_ki = __shfl_sync(FULL, sel_ki, owner);
 }
 
 // argmin of (distance, id) over the unexpanded entries.  Returns false when there is none.
@@ -98,34 +102,35 @@ __device__ __forceinline__ bool bag_argmin_unexpanded(const RegBag<NR>& b, uint3
   for (int j = 0; j < NR; ++j) m = min(m, b.kd[j]);
   const uint32_t low = __reduce_min_sync(FULL, m);
   if (low >= kBagExpanded) return false;  // every entry is expanded (or empty)
-  uint32_t hit = 0, sel_id = 0;
+  uint32_t hit = 0, sel_ki = 0;
 #pragma unroll
   for (int j = 0; j < NR; ++j) {
     if (b.kd[j] == low) {
       hit |= 1u << j;
-      sel_id = b.id[j];
+      sel_ki = b.ki[j];
     }
   }
   const uint32_t bal = __ballot_sync(FULL, hit != 0);
-  const bool multi = (bal & (bal - 1)) != 0 || __any_sync(FULL, (hit & (hit - 1)) != 0);
+  const bool dup_in_lane = __any_sync(FULL, (hit & (hit - 1)) != 0);
+  const bool multi = ((bal & (bal - 1)) != 0) | dup_in_lane;
   uint32_t owner = __ffs(bal) - 1;
   uint32_t row = 31 - __clz(hit);
   if (multi) {  // several unexpanded entries share the smallest distance: the smallest id wins
     bool have = false;
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
-      if (b.kd[j] == low && (!have || b.id[j] < sel_id)) {
+      if (b.kd[j] == low && (!have || b.ki[j] < sel_ki)) {
         have = true;
         row = j;
-        sel_id = b.id[j];
+        sel_ki = b.ki[j];
       }
     }
-    const uint32_t low_id = __reduce_min_sync(FULL, have ? sel_id : 0xffffffffu);
-    owner = __ffs(__ballot_sync(FULL, have && sel_id == low_id)) - 1;
+    const uint32_t low_ki = __reduce_min_sync(FULL, have ? sel_ki : 0xffffffffu);
+    owner = __ffs(__ballot_sync(FULL, have && sel_ki == low_ki)) - 1;
   }
   pos->row = __shfl_sync(FULL, row, owner);
   pos->lane = owner;
-  *out_id = __shfl_sync(FULL, sel_id, owner);
+  *out_id = __shfl_sync(FULL, sel_ki, owner) >> 1;  // unexpanded: the flag bit is clear
   return true;
 }
 
@@ -136,7 +141,47 @@ struct BagOccupancy {
   static constexpr int kMinCtas = NR <= 8 ? 21 : 16;
 };
 
-template <int NR>
+// table_distance (pq.rs:341-348) of one node from its code row (two 16-byte pieces): the f32 left fold over the
+// subquantizers of the bfloat16 table entries, then sqrt.  KS = 128: ksub is exactly 128, so the row offsets of the table
+// are immediates, and all four codes of a word are doubled at once (w + w: every code is < 128, no carry crosses a byte)
+// so that the extracted byte IS the byte offset of the 2-byte entry — PRMT, LDS.U16, shift, FADD per subquantizer.
+// KS = 0: any ksub <= 256.
+template <int KS>
+__device__ __forceinline__ float bag_table_distance(const uint16_t* lut16, const uint4 (&cw)[2], uint32_t nv, uint32_t ksub) {
+  float sacc = 0.0f;
+  if constexpr (KS == 128) {
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(lut16);
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      if ((uint32_t)v < nv) {
+        const uint32_t w[4] = {cw[v].x << 1, cw[v].y << 1, cw[v].z << 1, cw[v].w << 1};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const uint32_t off = __byte_perm(w[k >> 2], 0, 0x4440 + (k & 3));
+          const uint16_t e = *reinterpret_cast<const uint16_t*>(base + off + (v * 16 + k) * (KS * 2));
+          sacc = __fadd_rn(sacc, __uint_as_float((uint32_t)e << 16));
+        }
+      }
+    }
+  } else {
+    const uint16_t* lj = lut16;
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      if ((uint32_t)v < nv) {
+        const uint32_t w[4] = {cw[v].x, cw[v].y, cw[v].z, cw[v].w};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const uint32_t code = __byte_perm(w[k >> 2], 0, 0x4440 + (k & 3));
+          sacc = __fadd_rn(sacc, __uint_as_float((uint32_t)lj[code] << 16));
+          lj += ksub;
+        }
+      }
+    }
+  }
+  return __fsqrt_rn(sacc);
+}
+
+template <int NR, int KS>
 __global__ void __launch_bounds__(32, BagOccupancy<NR>::kMinCtas) adc_traverse_kernel(const SearchArgs a) {
   constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -236,11 +281,10 @@ __global__ void __launch_bounds__(32, BagOccupancy<NR>::kMinCtas) adc_traverse_k
 #pragma unroll
     for (int j = 0; j < NR; ++j) {
       R.kd[j] = kBagExpanded;
-      R.id[j] = 0xffffffffu;
+      R.ki[j] = 0xffffffffu;
     }
     uint32_t r_len = 0, n_ties = 0, tie_next = kTieCap;
-    uint32_t w_bits = 0xffffffffu, w_id = 0xffffffffu;  // the worst entry (only meaningful once R is full) ...
-    bool w_exp = true;
+    uint32_t w_bits = 0xffffffffu, w_ki = 0xffffffffu;  // the worst entry (only meaningful once R is full) ...
     BagPos w_pos{0, 0};                                 // ... and where it sits
     float w_d = 0.0f;
     uint64_t n_hop = 0, n_edge = 0, n_adc = 0;
@@ -248,11 +292,12 @@ __global__ void __launch_bounds__(32, BagOccupancy<NR>::kMinCtas) adc_traverse_k
     // ---- admission of one scored node (leann.rs:953-970), warp-uniform arguments ----------------------
     auto admit_one = [&](float d, uint32_t id) __attribute__((always_inline)) {
       const uint32_t nbits = (d != d) ? 0x7fc00000u : __float_as_uint(d);
+      const uint32_t nki = id << 1;
       if (novis) {
         // no visited set: a node that is already in R was scored before and is admitted once
         bool same = false;
 #pragma unroll
-        for (int j = 0; j < NR; ++j) same = same || R.id[j] == id;
+        for (int j = 0; j < NR; ++j) same = same || ((R.ki[j] ^ nki) < 2u);
         if (__any_sync(FULL, same)) return;
         if (lane == 0) idc[id & (kIdcEntries - 1)] = (uint16_t)(id >> kIdcBits);
       }
@@ -263,28 +308,27 @@ __global__ void __launch_bounds__(32, BagOccupancy<NR>::kMinCtas) adc_traverse_k
         for (int j = 0; j < NR; ++j)
           if ((uint32_t)j == row && me) {
             R.kd[j] = nbits + 1u;
-            R.id[j] = id;
+            R.ki[j] = nki;
           }
         r_len++;
         if (r_len == ef) {
-          bag_argmax<NR>(R, &w_bits, &w_id, &w_exp, &w_pos);
+          bag_argmax<NR>(R, &w_bits, &w_ki, &w_pos);
           w_d = __uint_as_float(w_bits);
         }
         return;
       }
       // full: the new entry takes the slot of the worst one (pop max, leann.rs:966-968)
-      const uint32_t e_bits = w_bits, e_id = w_id;
-      const bool e_exp = w_exp;
+      const uint32_t e_bits = w_bits, e_ki = w_ki;
       const bool me = lane == w_pos.lane;
 #pragma unroll
       for (int j = 0; j < NR; ++j)
         if ((uint32_t)j == w_pos.row && me) {
           R.kd[j] = nbits + 1u;
-          R.id[j] = id;
+          R.ki[j] = nki;
         }
-      bag_argmax<NR>(R, &w_bits, &w_id, &w_exp, &w_pos);
+      bag_argmax<NR>(R, &w_bits, &w_ki, &w_pos);
       w_d = __uint_as_float(w_bits);
-      if (!e_exp && !of_lt(w_d, __uint_as_float(e_bits))) {
+      if (!(e_ki & 1u) && !of_lt(w_d, __uint_as_float(e_bits))) {
         // an evicted, unexpanded node stays expandable while its distance equals the worst distance in R
         // (leann.rs:924-928 uses a strict `>`); see search_core.cuh for the capacity argument
         if (n_ties == tie_next) {
@@ -304,7 +348,7 @@ __global__ void __launch_bounds__(32, BagOccupancy<NR>::kMinCtas) adc_traverse_k
         if (n_ties >= kTieCap + ef) {
           if (lane == 0) atomicExch(a.error_flag, 1u);
         } else {
-          if (lane == 0) tie_st(n_ties, make_uint2(e_bits, e_id));
+          if (lane == 0) tie_st(n_ties, make_uint2(e_bits, e_ki >> 1));
           n_ties++;
           __syncwarp();
         }
@@ -347,8 +391,11 @@ __global__ void __launch_bounds__(32, BagOccupancy<NR>::kMinCtas) adc_traverse_k
         const bool me = lane == cp.lane;
 #pragma unroll
         for (int j = 0; j < NR; ++j)
-          if ((uint32_t)j == cp.row && me) R.kd[j] |= kBagExpanded;
-        if (r_len == ef && cp.row == w_pos.row && cp.lane == w_pos.lane) w_exp = true;  // the cached copy of the worst entry sees the flag too
+          if ((uint32_t)j == cp.row && me) {
+            R.kd[j] |= kBagExpanded;
+            R.ki[j] |= 1u;
+          }
+        if (r_len == ef && cp.row == w_pos.row && cp.lane == w_pos.lane) w_ki |= 1u;  // the cached copy of the worst entry sees the flag too
       } else {
         // smallest live tie, if any; every lane scans the whole list so that the result is provably warp-uniform
         int best = -1;
@@ -425,21 +472,7 @@ __global__ void __launch_bounds__(32, BagOccupancy<NR>::kMinCtas) adc_traverse_k
         }
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-          float sacc = 0.0f;  // table_distance (pq.rs:341-348): left fold over the subquantizers
-          const uint16_t* lj = lut16;
-#pragma unroll
-          for (int v = 0; v < 2; ++v) {
-            if ((uint32_t)v < nv) {
-              const uint32_t w[4] = {cw[r][v].x, cw[r][v].y, cw[r][v].z, cw[r][v].w};
-#pragma unroll
-              for (int k = 0; k < 16; ++k) {
-                const uint32_t code = __byte_perm(w[k >> 2], 0, 0x4440 + (k & 3));
-                sacc = __fadd_rn(sacc, __uint_as_float((uint32_t)lj[code] << 16));
-                lj += a.pq_ksub;
-              }
-            }
-          }
-          const float adc = __fsqrt_rn(sacc);
+          const float adc = bag_table_distance<KS>(lut16, cw[r], nv, a.pq_ksub);
           const bool unv = chk[r] && !(old[r] & (1u << (nid[r] & 31)));
           if (want_stats) n_adc += __popc(__ballot_sync(FULL, unv));
           admit_values(unv, adc, nid[r]);
@@ -458,20 +491,20 @@ __global__ void __launch_bounds__(32, BagOccupancy<NR>::kMinCtas) adc_traverse_k
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
         const uint32_t idx = j * 32 + lane;
-        if (idx < r_len) sk[idx] = make_uint2(R.kd[j] & kBagDistMask, R.id[j]);
+        if (idx < r_len) sk[idx] = make_uint2(R.kd[j] & kBagDistMask, R.ki[j] >> 1);
       }
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
         const uint32_t idx = j * 32 + lane;
         if (idx < r_len) {
-          const uint64_t mine = ((uint64_t)(R.kd[j] & kBagDistMask) << 32) | R.id[j];
+          const uint64_t mine = ((uint64_t)(R.kd[j] & kBagDistMask) << 32) | (R.ki[j] >> 1);
           uint32_t rank = 0;
           for (uint32_t t = 0; t < r_len; ++t) {
             const uint2 o = sk[t];
             rank += (((uint64_t)o.x << 32) | o.y) < mine ? 1u : 0u;
           }
-          if (rank < n_surv) a.surv_ids[(size_t)qi * ef + rank] = R.id[j];
+          if (rank < n_surv) a.surv_ids[(size_t)qi * ef + rank] = R.ki[j] >> 1;
         }
       }
       __syncwarp();
@@ -479,7 +512,7 @@ __global__ void __launch_bounds__(32, BagOccupancy<NR>::kMinCtas) adc_traverse_k
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
         const uint32_t idx = j * 32 + lane;
-        if (idx < r_len) a.surv_ids[(size_t)qi * ef + idx] = R.id[j];
+        if (idx < r_len) a.surv_ids[(size_t)qi * ef + idx] = R.ki[j] >> 1;
       }
     }
     if (lane == 0) {

@@ -100,9 +100,9 @@ isl_status launch_lean(const SearchPlan& plan, const SearchArgs& args, uint32_t 
 }
 
 // The register-bag traversal (adc_traverse.cuh): one-byte codes, m = 16 / 32, table in shared memory, ef <= 32 * NR.
-template <int NR>
+template <int NR, int KS>
 isl_status plan_bag(uint32_t ef, int sms, SearchPlan* plan) {
-  auto kern = adc_traverse_kernel<NR>;
+  auto kern = adc_traverse_kernel<NR, KS>;
   const size_t smem = adc_traverse_smem_bytes(plan->lut_smem_floats, ef);
   static std::once_flag once[64];
   static cudaError_t once_result[64];
@@ -118,9 +118,9 @@ isl_status plan_bag(uint32_t ef, int sms, SearchPlan* plan) {
   return ISL_OK;
 }
 
-template <int NR>
+template <int NR, int KS>
 isl_status launch_bag(const SearchPlan& plan, const SearchArgs& args, uint32_t grid, cudaStream_t st) {
-  adc_traverse_kernel<NR><<<grid, 32, plan.smem, st>>>(args);
+  adc_traverse_kernel<NR, KS><<<grid, 32, plan.smem, st>>>(args);
   count_launch();
   ISL_CUDA_TRY(cudaGetLastError());
   return ISL_OK;
@@ -211,14 +211,19 @@ isl_status plan_search_adc_traverse(uint32_t ef, uint32_t u_cap, uint32_t pq_m, 
         break;
       }
   }
+  plan->ks = pq_ksub == 128 ? 128 : 0;  // the specialised table fold of adc_traverse.cuh
+#define ISL_BAG(N) \
+  case N:          \
+    return plan->ks == 128 ? plan_bag<N, 128>(ef, sms, plan) : plan_bag<N, 0>(ef, sms, plan);
   switch (plan->nr) {
-    case 2: return plan_bag<2>(ef, sms, plan);
-    case 4: return plan_bag<4>(ef, sms, plan);
-    case 6: return plan_bag<6>(ef, sms, plan);
-    case 8: return plan_bag<8>(ef, sms, plan);
-    case 12: return plan_bag<12>(ef, sms, plan);
-    case 16: return plan_bag<16>(ef, sms, plan);
+    ISL_BAG(2)
+    ISL_BAG(4)
+    ISL_BAG(6)
+    ISL_BAG(8)
+    ISL_BAG(12)
+    ISL_BAG(16)
   }
+#undef ISL_BAG
   return ef <= kEfSmemMax ? plan_lean<true>(ef, u_cap, pq_m, sms, plan) : plan_lean<false>(ef, u_cap, pq_m, sms, plan);
 }
 
@@ -236,14 +241,18 @@ isl_status launch_search(const SearchPlan& plan, const SearchArgs& args, cudaStr
   // Never launch more warps than queries: idle slots would only clear their bitsets.
   const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(plan.grid, args.nq));
   if (plan.mode == 3) {
+#define ISL_BAG(N) \
+  case N:          \
+    return plan.ks == 128 ? launch_bag<N, 128>(plan, args, grid, st) : launch_bag<N, 0>(plan, args, grid, st);
     switch (plan.nr) {
-      case 2: return launch_bag<2>(plan, args, grid, st);
-      case 4: return launch_bag<4>(plan, args, grid, st);
-      case 6: return launch_bag<6>(plan, args, grid, st);
-      case 8: return launch_bag<8>(plan, args, grid, st);
-      case 12: return launch_bag<12>(plan, args, grid, st);
-      case 16: return launch_bag<16>(plan, args, grid, st);
+      ISL_BAG(2)
+      ISL_BAG(4)
+      ISL_BAG(6)
+      ISL_BAG(8)
+      ISL_BAG(12)
+      ISL_BAG(16)
     }
+#undef ISL_BAG
     return plan.r_in_smem ? launch_lean<true>(plan, args, grid, st) : launch_lean<false>(plan, args, grid, st);
   }
   if (plan.mode == 2) return launch_dispatch<2>(plan, args, grid, st);

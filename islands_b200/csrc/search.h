@@ -101,6 +101,7 @@ struct SearchPlan {
   int acc = 0;            // accumulation kind (dist_pass.cuh)
   bool two_level = false;
   int mode = 0;           // 0 exact, 1 two-level (AQ promotion), 2 ADC traversal + exact rerank, 3 ADC traversal only
+  int ks = 0;             // register-bag kernel: 128 = the table fold specialised for ksub == 128, 0 = any ksub
   int nr = 0;             // MODE 3: the register-bag kernel (adc_traverse.cuh), nr entries per lane (0 = search_core.cuh, shared / global memory)
   bool novis_ok = false;  // MODE 3: the launch may run without the visited bitset (SearchArgs::novis)
   uint32_t lut_smem_floats = 0;  // PQ table staged in shared memory (0 => read from global/L2)
