@@ -103,8 +103,12 @@ __device__ __forceinline__ void stream_rows_fold(RowRing<STAGES>& ring, const fl
       ring.islot = (ring.islot + 1 == STAGES) ? 0 : ring.islot + 1;
     }
   };
+  // Every slot is filled before the first wait, and a slot is refilled the moment its slice has been folded — BEFORE the
+  // group's admission runs, so the first slice of the next group is in flight while the warp replays the admissions (with
+  // a single slot nothing was in flight during on_group: one exposed DRAM latency per group, and the whole insert phase of
+  // a rerank group).
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) issue_next();
+  for (int s = 0; s < STAGES; ++s) issue_next();
   for (uint32_t g = 0; g < ngroups; ++g) {
     const uint32_t cnt = min(32u, total - (g << 5));
     const uint32_t sh = group_slice_shift<CH>(cnt);
@@ -112,7 +116,6 @@ __device__ __forceinline__ void stream_rows_fold(RowRing<STAGES>& ring, const fl
     const uint32_t nch = (d + (1u << sh) - 1) >> sh;
     float acc = 0.0f;
     for (uint32_t c = 0; c < nch; ++c) {
-      issue_next();
       mbar_wait(ring.bars + ring.cslot, (ring.phase_bits >> ring.cslot) & 1u);
       ring.phase_bits ^= 1u << ring.cslot;
       if (lane < cnt) {
@@ -148,6 +151,7 @@ __device__ __forceinline__ void stream_rows_fold(RowRing<STAGES>& ring, const fl
       }
       __syncwarp();  // every lane is done with the slot before it is refilled
       ring.cslot = (ring.cslot + 1 == STAGES) ? 0 : ring.cslot + 1;
+      issue_next();  // into the slot that was just consumed (islot follows cslot around the ring)
     }
     on_group(g << 5, cnt, acc);
   }

@@ -242,6 +242,10 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     const float na = (!LEAN && a.metric == ISL_METRIC_COSINE) ? smem_sqnorm_fold(q_smem, a.d) : 0.0f;
 
     uint32_t r_len = 0, first_unexp = 0, n_ties = 0, aq_len = 0;
+    // capacity of R for the shared / global array: ef during a traversal; k for the exact rerank of the ADC survivors,
+    // which only has to deliver the k best by (distance, id) — see the rerank below
+    uint32_t cap = ef;
+    bool rerank_topk = false;
     uint32_t tie_next = kTieCap;  // the tie list is compacted (stale entries dropped) when it reaches this length
     float wst_d = 0.0f;    // register R: the entry at index ef - 1 (the worst one once R is full), kept beside the rows
     uint32_t wst_kd = 0xffffffffu, wst_ki = 0xffffffffu;
@@ -342,7 +346,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     // by one lane (lane 31 hands over the last entry of the row below).
     auto r_insert = [&](float dnew, uint32_t idnew) __attribute__((always_inline)) {
       uint32_t pos;
-      const bool full = (r_len == ef);
+      const bool full = RREG ? (r_len == ef) : (r_len == cap);
       uint2 evicted = make_uint2(0, 0);
       if constexpr (RREG) {
         // position = number of keys below the new one: one 64-bit compare and one ballot per row.  Then
@@ -404,8 +408,8 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
           }
           if (lane == 0) idc[idnew & (kIdcEntries - 1)] = (uint16_t)(idnew >> kIdcBits);
         }
-        if (full) evicted = R.ld(ef - 1);
-        const int top = full ? (int)ef - 1 : (int)r_len;
+        if (full) evicted = R.ld(cap - 1);
+        const int top = full ? (int)cap - 1 : (int)r_len;
         for (int t = top; t > (int)pos; t -= 32) {
           const int i = t - (int)lane;
           const bool act = i > (int)pos;
@@ -426,10 +430,10 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         wst_d = __uint_as_float(wst_kd);
         if (full) evicted.y = ((evicted.y & 1u) ? kExpandedBit : 0u) | (evicted.y >> 1);
       }
-      if (full && !(evicted.y & kExpandedBit)) {
+      if (full && !rerank_topk && !(evicted.y & kExpandedBit)) {
         // An evicted, unexpanded node stays expandable while its distance equals the worst
         // distance in R (leann.rs:924-928 uses a strict `>`).
-        const float wd = RREG ? wst_d : __uint_as_float(R.ld(ef - 1).x), edist = __uint_as_float(evicted.x);
+        const float wd = RREG ? wst_d : __uint_as_float(R.ld(cap - 1).x), edist = __uint_as_float(evicted.x);
         if (!of_lt(wd, edist)) {
           if (n_ties == tie_next) {  // drop stale ties first (lane 0 moves the survivors down, in order)
             uint32_t kept = 0;
@@ -460,6 +464,27 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     // Streaming and fold: row_stream.cuh.  Admission replays the reference's per-neighbour loop
     // (leann.rs:953-970) in list order over the lanes that can still be admitted.
     auto admit_values = [&](bool ok, float dn, uint32_t cid) __attribute__((always_inline)) {
+      if constexpr (!RREG) {
+        if (rerank_topk) {
+          // exact rerank: R keeps the k best by the FULL (distance, id) key — what sorting all survivors and taking k yields
+          uint2 w = make_uint2(0, 0);
+          if (r_len > 0) w = R.ld(r_len - 1);
+          uint32_t mask = __ballot_sync(0xffffffffu, ok && (r_len < cap || key_lt(dn, cid, __uint_as_float(w.x), w.y & ~kExpandedBit)));
+          while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float dj = __shfl_sync(0xffffffffu, dn, j);
+            const uint32_t idj = __shfl_sync(0xffffffffu, cid, j);
+            bool add = r_len < cap;
+            if (!add) {
+              const uint2 e = R.ld(cap - 1);
+              add = key_lt(dj, idj, __uint_as_float(e.x), e.y & ~kExpandedBit);
+            }
+            if (add) r_insert(dj, idj);
+          }
+          return;
+        }
+      }
       float worst = 0.0f;
       if (r_len > 0) worst = RREG ? wst_d : __uint_as_float(R.ld(r_len - 1).x);
       uint32_t mask = __ballot_sync(0xffffffffu, ok && (r_len < ef || dn < worst));
@@ -854,6 +879,11 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       tie_next = kTieCap;
       n_dist = total;
       n_rerank = total;
+      // Sorting all survivors by (distance, id) and taking k == keeping a sorted array of the k best by that key: a
+      // survivor only enters R when its key is below the k-th best so far (a handful of inserts per group instead of one
+      // sorted insert into ef entries per survivor).
+      cap = a.k < ef ? a.k : ef;
+      rerank_topk = true;
       score_and_admit(total);
     }
 
