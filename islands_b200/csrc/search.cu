@@ -9,6 +9,14 @@
 
 namespace isl {
 
+// the exact traversal with R as a register bag: one translation unit per accumulation kind (search_bag.inc)
+isl_status plan_exact_bag_dot(int nr, uint32_t ld, uint32_t u_cap, int sms, SearchPlan* plan);
+isl_status plan_exact_bag_l2(int nr, uint32_t ld, uint32_t u_cap, int sms, SearchPlan* plan);
+isl_status plan_exact_bag_l1(int nr, uint32_t ld, uint32_t u_cap, int sms, SearchPlan* plan);
+isl_status launch_exact_bag_dot(const SearchPlan& plan, const SearchArgs& args, uint32_t grid, cudaStream_t st);
+isl_status launch_exact_bag_l2(const SearchPlan& plan, const SearchArgs& args, uint32_t grid, cudaStream_t st);
+isl_status launch_exact_bag_l1(const SearchPlan& plan, const SearchArgs& args, uint32_t grid, cudaStream_t st);
+
 namespace {
 #ifndef ISL_CH
 #define ISL_CH 128
@@ -21,6 +29,10 @@ constexpr int kStages = ISL_STAGES;
 // R (8 B per entry) stays in shared memory up to this many entries; above, it lives in an
 // L2-resident global buffer so that enough warps stay resident per SM.
 constexpr uint32_t kEfSmemMax = 2048;
+#ifndef ISL_BAG_EF_MAX
+#define ISL_BAG_EF_MAX 512
+#endif
+constexpr uint32_t kBagEfMax = ISL_BAG_EF_MAX;  // exact traversal: register bag up to this ef (0 disables it: dev builds)
 constexpr uint32_t kLutSmemMaxFloats = 8192;  // 32 KB of PQ tables per query in shared memory
 constexpr uint32_t kAqSmemMaxEntries = 2048;  // 16 KB approximate queue in shared memory
 constexpr int kMaxDynSmem = 227 * 1024;
@@ -164,6 +176,17 @@ isl_status plan_search(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap,
   plan->aq_smem_entries = 0;
   plan->aq_cap = 0;
   plan->mode = 0;
+  plan->nr = 0;
+  // up to ef = 512 the result set is an unsorted bag in registers (search_core.cuh), NR = 4 / 8 / 16 entries per lane
+  if (ef <= kBagEfMax) {
+    plan->nr = ef <= 128 ? 4 : (ef <= 256 ? 8 : 16);
+    switch (plan->acc) {
+      case ACC_DOT: return plan_exact_bag_dot(plan->nr, ld, u_cap, sms, plan);
+      case ACC_L2: return plan_exact_bag_l2(plan->nr, ld, u_cap, sms, plan);
+      case ACC_L1: return plan_exact_bag_l1(plan->nr, ld, u_cap, sms, plan);
+    }
+    return fail(ISL_INVALID_CONFIG, "search: unknown metric");
+  }
   return plan_dispatch<0>(plan->acc, ef <= kEfSmemMax, ld, ef, u_cap, sms, plan);
 }
 
@@ -256,6 +279,14 @@ isl_status launch_search(const SearchPlan& plan, const SearchArgs& args, cudaStr
     return plan.r_in_smem ? launch_lean<true>(plan, args, grid, st) : launch_lean<false>(plan, args, grid, st);
   }
   if (plan.mode == 2) return launch_dispatch<2>(plan, args, grid, st);
+  if (plan.mode == 0 && plan.nr > 0) {
+    switch (plan.acc) {
+      case ACC_DOT: return launch_exact_bag_dot(plan, args, grid, st);
+      case ACC_L2: return launch_exact_bag_l2(plan, args, grid, st);
+      case ACC_L1: return launch_exact_bag_l1(plan, args, grid, st);
+    }
+    return fail(ISL_INVALID_CONFIG, "search: unknown metric");
+  }
   return plan.mode == 1 ? launch_dispatch<1>(plan, args, grid, st) : launch_dispatch<0>(plan, args, grid, st);
 }
 

@@ -119,6 +119,118 @@ __device__ __forceinline__ uint32_t prune_proportional(float prune_ratio, uint32
   return w ? w : 1u;  // nothing kept: the first candidate, still at list[0] (leann.rs:1049-1051)
 }
 
+// ---- R as an unsorted bag in registers (exact traversal, ef <= 512) -------------------------------------------------
+// The reference needs three things from its two heaps (leann.rs:899-988): the worst entry of R (admission `d < worst`,
+// eviction), the closest unexpanded entry (the next candidate) and, at the end, the k best in order.  None needs R
+// sorted while the search runs: entry i lives in row i / 32 of lane i % 32 and never moves; the worst entry is an argmax
+// over the bag (per-lane max over its NR rows, redux.sync, a vote for the owner), paid once per ADMITTED node, which then
+// overwrites the evicted slot; the next candidate is an argmin over the unexpanded entries, once per hop; the results are
+// k argmin rounds at the end.  A sorted array in shared memory pays a binary search (log2 ef dependent LDS) and a shift
+// of ef/2 entries per admission: at ef = 512 that was a third of the kernel's time (0.70 of the HBM peak against 0.87 at
+// ef = 104).  Keys: kd = order-preserving image of the f32 distance (NaN folded onto the greatest word: OrderedFloat),
+// ki = id << 1 | expanded; an empty slot is kd = 0 (below every real key), ki = 0xffffffff ("expanded").
+__device__ __forceinline__ uint32_t dist_key(float d) {
+  if (d != d) return 0xffffffffu;
+  const uint32_t u = __float_as_uint(d);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_dist(uint32_t k) {
+  if (k == 0xffffffffu) return __uint_as_float(0x7fffffffu);
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+struct XBagPos {
+  uint32_t row, lane;  // warp-uniform
+};
+
+// argmax of (distance, id) over the bag; called when it holds at least one entry.  Warp-uniform result.
+template <int NR>
+__device__ __forceinline__ void xbag_argmax(const uint32_t (&kd)[NR], const uint32_t (&ki)[NR], uint32_t* out_kd, uint32_t* out_ki, XBagPos* pos) {
+  constexpr uint32_t FULL = 0xffffffffu;
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < NR; ++j) m = max(m, kd[j]);
+  const uint32_t top = __reduce_max_sync(FULL, m);
+  uint32_t hit = 0, sel_ki = 0;
+#pragma unroll
+  for (int j = 0; j < NR; ++j) {
+    if (kd[j] == top) {
+      hit |= 1u << j;
+      sel_ki = ki[j];
+    }
+  }
+  const uint32_t bal = __ballot_sync(FULL, hit != 0);
+  const bool dup_in_lane = __any_sync(FULL, (hit & (hit - 1)) != 0);
+  const bool multi = ((bal & (bal - 1)) != 0) | dup_in_lane;
+  uint32_t owner = __ffs(bal) - 1;
+  uint32_t row = 31 - __clz(hit);
+  if (multi) {  // exact distance tie: the greatest id is the worst entry (ki orders like the id)
+    bool have = false;
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+      if (kd[j] == top && (!have || ki[j] > sel_ki)) {
+        have = true;
+        row = j;
+        sel_ki = ki[j];
+      }
+    }
+    const uint32_t top_ki = __reduce_max_sync(FULL, have ? sel_ki : 0u);
+    owner = __ffs(__ballot_sync(FULL, have && sel_ki == top_ki)) - 1;
+  }
+  pos->row = __shfl_sync(FULL, row, owner);
+  pos->lane = owner;
+  *out_kd = top;
+  *out_ki = __shfl_sync(FULL, sel_ki, owner);
+}
+
+// argmin of (distance, id) over the unexpanded entries; false when there is none.  Warp-uniform result.
+template <int NR>
+__device__ __forceinline__ bool xbag_argmin_unexpanded(const uint32_t (&kd)[NR], const uint32_t (&ki)[NR], uint32_t* out_kd, uint32_t* out_id,
+                                                       XBagPos* pos) {
+  constexpr uint32_t FULL = 0xffffffffu;
+  uint32_t m = 0xffffffffu, un = 0;
+#pragma unroll
+  for (int j = 0; j < NR; ++j) {
+    if (!(ki[j] & 1u)) {
+      un |= 1u << j;
+      m = min(m, kd[j]);
+    }
+  }
+  if (!__any_sync(FULL, un != 0)) return false;
+  const uint32_t low = __reduce_min_sync(FULL, m);
+  uint32_t hit = 0, sel_ki = 0;
+#pragma unroll
+  for (int j = 0; j < NR; ++j) {
+    if (((un >> j) & 1u) && kd[j] == low) {
+      hit |= 1u << j;
+      sel_ki = ki[j];
+    }
+  }
+  const uint32_t bal = __ballot_sync(FULL, hit != 0);
+  const bool dup_in_lane = __any_sync(FULL, (hit & (hit - 1)) != 0);
+  const bool multi = ((bal & (bal - 1)) != 0) | dup_in_lane;
+  uint32_t owner = __ffs(bal) - 1;
+  uint32_t row = 31 - __clz(hit);
+  if (multi) {  // exact distance tie: the smallest id first
+    bool have = false;
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+      if (((un >> j) & 1u) && kd[j] == low && (!have || ki[j] < sel_ki)) {
+        have = true;
+        row = j;
+        sel_ki = ki[j];
+      }
+    }
+    const uint32_t low_ki = __reduce_min_sync(FULL, have ? sel_ki : 0xffffffffu);
+    owner = __ffs(__ballot_sync(FULL, have && sel_ki == low_ki)) - 1;
+  }
+  pos->row = __shfl_sync(FULL, row, owner);
+  pos->lane = owner;
+  *out_kd = low;
+  *out_id = __shfl_sync(FULL, sel_ki, owner) >> 1;
+  return true;
+}
+
 // TWO = two-level search: unvisited neighbours are scored with the PQ table distance
 // (pq.rs:341-348) into an approximate queue AQ ordered by (adc,id); after every expansion the
 // ceil(a*|AQ|) best entries (at least one) leave AQ, get their exact distance and go through the
@@ -130,16 +242,16 @@ __device__ __forceinline__ uint32_t prune_proportional(float prune_ratio, uint32
 // Traversal traffic drops from 4d bytes to m bytes per visited node.
 //
 // MODE 3 = the traversal half of MODE 2 as its own lean kernel (no staging ring, no query vector:
-// 2-3x the resident warps), survivors written out for a MODE 2 / phase 2 rerank launch.  With NR > 0
-// the result array R lives in REGISTERS, NR entries per lane (entry i = row i / 32 of lane i % 32):
-// insertion is a ballot-counted position plus one shuffle shift per row instead of a shared-memory
-// binary search and shift loop — the per-hop latency chain is what bounds the ADC traversal.
+// 2-3x the resident warps), survivors written out for a MODE 2 / phase 2 rerank launch (the register-bag
+// kernel of adc_traverse.cuh serves one-byte codes with ef <= 512; this one the rest).
+// NR > 0 (MODE 0 only): R is the unsorted register bag above, NR entries per lane, ef <= 32 * NR.
 template <int ACC, int CH, int STAGES, bool R_SMEM, int MODE, int NR = 0>
 __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
   constexpr bool TWO = MODE == 1;
   constexpr bool ADC = MODE == 2 || MODE == 3;
   constexpr bool LEAN = MODE == 3;
-  constexpr bool RREG = NR > 0;
+  constexpr bool RREG = NR > 0;  // R = unsorted bag in registers
+  static_assert(!RREG || MODE == 0, "the register bag serves the exact traversal");
   constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using G = StageGeom<CH>;
@@ -191,15 +303,9 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     else
       __stcg(ties_spill + (i - kTieCap), v);
   };
-  // register-resident R: entry i = row i / 32 of lane i % 32, as a pair of unsigned words whose
-  // lexicographic order IS the (dist, id) order: kd = bits of the table distance (a square root: never
-  // negative, so the bit patterns order like the values; every NaN is folded onto 0x7fc00000 = greatest,
-  // OrderedFloat's rule), ki = id << 1 | expanded.  Ids are unique in R, so the flag bit never decides a
-  // comparison.  Slots past r_len hold the all-ones sentinel (greatest key, "expanded").
+  // register bag (RREG): entry i = row i / 32 of lane i % 32
   uint32_t kd[RREG ? NR : 1];
   uint32_t ki[RREG ? NR : 1];
-  constexpr int WR0 = NR >= 2 ? NR - 2 : 0;  // the entry ef-1 sits in row NR-2 or NR-1 (NR = 2 * ceil(ef / 64))
-  const uint32_t wrow = (a.ef - 1) >> 5, wlane = (a.ef - 1) & 31;
 
   RowRing<STAGES> ring;
   ring.stage = stage;
@@ -247,15 +353,15 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     uint32_t cap = ef;
     bool rerank_topk = false;
     uint32_t tie_next = kTieCap;  // the tie list is compacted (stale entries dropped) when it reaches this length
-    float wst_d = 0.0f;    // register R: the entry at index ef - 1 (the worst one once R is full), kept beside the rows
+    float wst_d = 0.0f;    // register bag: the worst entry once R is full (distance, key words, position)
     uint32_t wst_kd = 0xffffffffu, wst_ki = 0xffffffffu;
+    XBagPos wst_pos{0, 0};
     if constexpr (RREG) {
 #pragma unroll
       for (int j = 0; j < NR; ++j) {
-        kd[j] = 0xffffffffu;
+        kd[j] = 0u;
         ki[j] = 0xffffffffu;
       }
-      wst_d = __uint_as_float(wst_kd);
     }
     uint64_t n_hop = 0, n_edge = 0, n_dist = 0, n_adc = 0, n_rerank = 0;
     uint64_t draw_ctr = 0;  // Proportional pruning: draws consumed by this query so far
@@ -320,76 +426,31 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
     }
 
     // ---- R access ---------------------------------------------------------------------------
-    auto r_get = [&](uint32_t i) __attribute__((always_inline)) -> uint2 {  // i is warp-uniform
-      if constexpr (!RREG) {
-        return R.ld(i);
-      } else {
-        // every row is shuffled and the wanted one selected afterwards: selecting the ROW first (by value
-        // or by a warp-uniform branch) is turned into dynamic indexing of kd[] / ki[] by the compiler and
-        // pushes them out of the register file (a stack frame in ptxas -v)
-        uint32_t sd = 0, si = 0;
-#pragma unroll
-        for (int j = 0; j < NR; ++j) {
-          const uint32_t td = __shfl_sync(FULL, kd[j], i & 31);
-          const uint32_t ti = __shfl_sync(FULL, ki[j], i & 31);
-          if ((i >> 5) == (uint32_t)j) {
-            sd = td;
-            si = ti;
-          }
-        }
-        return make_uint2(sd, ((si & 1u) ? kExpandedBit : 0u) | (si >> 1));
-      }
-    };
-    // ---- sorted insert into R ------------------------------------------------------------------
-    // shared/global R: binary search, warp shift, store.  register R: position = number of entries
-    // below the new key (one 64-bit compare + ballot per row), then every row at or above it rotates up
-    // by one lane (lane 31 hands over the last entry of the row below).
+    auto r_get = [&](uint32_t i) __attribute__((always_inline)) -> uint2 { return R.ld(i); };  // sorted array only
+    // ---- insert into R -------------------------------------------------------------------------
+    // shared/global R: sorted array — binary search, warp shift, store.  register bag: see above.
     auto r_insert = [&](float dnew, uint32_t idnew) __attribute__((always_inline)) {
       uint32_t pos;
       const bool full = RREG ? (r_len == ef) : (r_len == cap);
       uint2 evicted = make_uint2(0, 0);
       if constexpr (RREG) {
-        // position = number of keys below the new one: one 64-bit compare and one ballot per row.  Then
-        // every row at or above the position rotates up by one lane (lane 31 hands over the last entry
-        // of the row below); rows entirely below it are skipped with a warp-uniform branch.
-        const uint32_t nkd = (dnew != dnew) ? 0x7fc00000u : __float_as_uint(dnew);
-        const uint32_t nki = idnew << 1;
-        const uint64_t nkey = ((uint64_t)nkd << 32) | nki;
-        if (novis) {
-          // a node that is already in R (ids are unique there) was scored twice: admitted once.  Tested before
-          // the position is computed, so that a repeat costs one compare per row and a vote.
-          bool same = false;
+        // bag: the new entry goes into the next free slot, or takes the slot of the worst entry (pop max,
+        // leann.rs:966-968); the new worst entry is an argmax over the bag
+        const uint32_t nkd = dist_key(dnew), nki = idnew << 1;
+        if (full) evicted = make_uint2(__float_as_uint(wst_d), (wst_ki >> 1) | ((wst_ki & 1u) ? kExpandedBit : 0u));
+        const uint32_t srow = full ? wst_pos.row : (r_len >> 5);
+        const bool me = lane == (full ? wst_pos.lane : (r_len & 31));
 #pragma unroll
-          for (int j = 0; j < NR; ++j) same = same || ((ki[j] ^ nki) < 2u);
-          if (__any_sync(FULL, same)) return;
-          if (lane == 0) idc[idnew & (kIdcEntries - 1)] = (uint16_t)(idnew >> kIdcBits);
-        }
-        pos = 0;
-#pragma unroll
-        for (int j = 0; j < NR; ++j) {
-          const uint64_t key = ((uint64_t)kd[j] << 32) | ki[j];
-          pos += __popc(__ballot_sync(FULL, key < nkey));
-        }
-        if (full) evicted = make_uint2(wst_kd, wst_ki);  // the current worst entry (index ef - 1)
-        const uint32_t top = full ? ef - 1 : r_len;
-        const uint32_t src = (lane + 31) & 31;
-#pragma unroll
-        for (int j = NR - 1; j >= 0; --j) {
-          if ((uint32_t)(j * 32 + 31) >= pos && (uint32_t)(j * 32) <= top) {
-            const bool hand = j > 0 && lane == 31;
-            const uint32_t ud = __shfl_sync(FULL, hand ? kd[j > 0 ? j - 1 : 0] : kd[j], src);
-            const uint32_t ui = __shfl_sync(FULL, hand ? ki[j > 0 ? j - 1 : 0] : ki[j], src);
-            const uint32_t idx = j * 32 + lane;
-            if (idx > pos && idx <= top) {
-              kd[j] = ud;
-              ki[j] = ui;
-            }
-            if (idx == pos) {
-              kd[j] = nkd;
-              ki[j] = nki;
-            }
+        for (int j = 0; j < NR; ++j)
+          if ((uint32_t)j == srow && me) {
+            kd[j] = nkd;
+            ki[j] = nki;
           }
+        if (full || r_len + 1 == ef) {
+          xbag_argmax<NR>(kd, ki, &wst_kd, &wst_ki, &wst_pos);
+          wst_d = key_dist(wst_kd);
         }
+        pos = 0xffffffffu;  // no position in a bag: first_unexp is not used
       } else {
         uint32_t lo = 0, hi = r_len;  // first position whose key is not < new key
         while (lo < hi) {
@@ -424,12 +485,6 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       }
       if (!full) r_len++;
       if (pos <= first_unexp) first_unexp = pos;
-      if constexpr (RREG) {  // the entry at index ef - 1 (the sentinel until R is full)
-        wst_kd = __shfl_sync(FULL, wrow == (uint32_t)WR0 ? kd[WR0] : kd[NR - 1], wlane);
-        wst_ki = __shfl_sync(FULL, wrow == (uint32_t)WR0 ? ki[WR0] : ki[NR - 1], wlane);
-        wst_d = __uint_as_float(wst_kd);
-        if (full) evicted.y = ((evicted.y & 1u) ? kExpandedBit : 0u) | (evicted.y >> 1);
-      }
       if (full && !rerank_topk && !(evicted.y & kExpandedBit)) {
         // An evicted, unexpanded node stays expandable while its distance equals the worst
         // distance in R (leann.rs:924-928 uses a strict `>`).
@@ -561,43 +616,43 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
 
     // ---- main loop (leann.rs:922-972) ------------------------------------------------------
     for (; traverse;) {
-      uint32_t cur;
-      if (first_unexp < r_len) {
+      uint32_t cur = 0;
+      bool have_cur = false;
+      if constexpr (RREG) {
+        // the closest unexpanded entry of the bag; mark it expanded
+        uint32_t ckd;
+        XBagPos cp;
+        if (xbag_argmin_unexpanded<NR>(kd, ki, &ckd, &cur, &cp)) {
+          have_cur = true;
+          const bool me = lane == cp.lane;
+#pragma unroll
+          for (int j = 0; j < NR; ++j)
+            if ((uint32_t)j == cp.row && me) ki[j] |= 1u;
+          // the cached copy of the worst entry must see the flag too: an expanded worst entry that is evicted
+          // later with a distance equal to the new worst one must not come back through the ties list
+          if (r_len == ef && cp.row == wst_pos.row && cp.lane == wst_pos.lane) wst_ki |= 1u;
+        }
+      } else if (first_unexp < r_len) {
+        have_cur = true;
         const uint2 e = r_get(first_unexp);
         cur = e.y;
         uint32_t nxt = r_len;
-        if constexpr (RREG) {
-          // the cached copy of the worst entry must see the flag too: an expanded worst entry that is evicted
-          // later with a distance equal to the new worst one must not come back through the ties list
-          if (first_unexp == ef - 1) wst_ki |= 1u;
-          // mark it expanded and find the next unexpanded entry (sentinel slots read as expanded);
-          // rows below the popped one cannot hold it and are skipped
-#pragma unroll
-          for (int j = 0; j < NR; ++j) {
-            if ((uint32_t)(j * 32 + 31) >= first_unexp && nxt == r_len) {
-              const uint32_t idx = j * 32 + lane;
-              if (idx == first_unexp) ki[j] |= 1u;
-              const uint32_t bal = __ballot_sync(FULL, idx > first_unexp && !(ki[j] & 1u));
-              if (bal) nxt = j * 32 + __ffs(bal) - 1;
-            }
-          }
-        } else {
-          __syncwarp();
-          if (lane == 0) R.st(first_unexp, make_uint2(e.x, e.y | kExpandedBit));
-          __syncwarp();
-          // advance to the next unexpanded entry
-          for (uint32_t b = first_unexp + 1; b < r_len; b += 32) {
-            const uint32_t i = b + lane;
-            const bool un = i < r_len && !(R.ld(i).y & kExpandedBit);
-            const uint32_t bal = __ballot_sync(0xffffffffu, un);
-            if (bal) {
-              nxt = b + __ffs(bal) - 1;
-              break;
-            }
+        __syncwarp();
+        if (lane == 0) R.st(first_unexp, make_uint2(e.x, e.y | kExpandedBit));
+        __syncwarp();
+        // advance to the next unexpanded entry
+        for (uint32_t b = first_unexp + 1; b < r_len; b += 32) {
+          const uint32_t i = b + lane;
+          const bool un = i < r_len && !(R.ld(i).y & kExpandedBit);
+          const uint32_t bal = __ballot_sync(0xffffffffu, un);
+          if (bal) {
+            nxt = b + __ffs(bal) - 1;
+            break;
           }
         }
         first_unexp = nxt;
-      } else {
+      }
+      if (!have_cur) {
         // smallest live tie, if any.  Every lane scans the whole list (broadcast loads): the result is then provably
         // warp-uniform.  A lane-strided scan + shuffle reduction hands `cur` back through shuffles, which the compiler
         // must treat as divergent — it then wraps every collective of the search loop in convergence barriers
@@ -641,12 +696,20 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
         } else {
           deg = a.adj_stride;
           sentinel = true;
-          if (first_unexp < r_len) {  // warp-uniform: r_get shuffles
-            const uint32_t nxt = r_get(first_unexp).y & ~kExpandedBit;
-            if (lane * 32 < a.adj_stride) {
-              const uint32_t* pf = a.nbrs + (size_t)nxt * a.adj_stride + lane * 32;
-              asm volatile("prefetch.global.L2 [%0];\n" ::"l"(pf));
-            }
+          // the list of the candidate that is next as things stand goes to L2 while this one is scored
+          uint32_t nxt = 0;
+          bool have_nxt = false;
+          if constexpr (RREG) {
+            uint32_t nkd;
+            XBagPos np;
+            have_nxt = xbag_argmin_unexpanded<NR>(kd, ki, &nkd, &nxt, &np);
+          } else if (first_unexp < r_len) {
+            have_nxt = true;
+            nxt = r_get(first_unexp).y & ~kExpandedBit;
+          }
+          if (have_nxt && lane * 32 < a.adj_stride) {
+            const uint32_t* pf = a.nbrs + (size_t)nxt * a.adj_stride + lane * 32;
+            asm volatile("prefetch.global.L2 [%0];\n" ::"l"(pf));
           }
         }
       }
@@ -837,15 +900,7 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
       // traversal-only launch: hand the ef survivors (ascending adc order) to the rerank / recompute step;
       // with a rerank limit only the best of them (isl_index_set_rerank_limit)
       const uint32_t n_surv = a.rerank_limit ? min(r_len, a.rerank_limit) : r_len;
-      if constexpr (RREG) {
-#pragma unroll
-        for (int j = 0; j < NR; ++j) {
-          const uint32_t idx = j * 32 + lane;
-          if (idx < n_surv) a.surv_ids[(size_t)qi * ef + idx] = ki[j] >> 1;
-        }
-      } else {
-        for (uint32_t i = lane; i < n_surv; i += 32) a.surv_ids[(size_t)qi * ef + i] = R.ld(i).y & ~kExpandedBit;
-      }
+      for (uint32_t i = lane; i < n_surv; i += 32) a.surv_ids[(size_t)qi * ef + i] = R.ld(i).y & ~kExpandedBit;
       if (lane == 0) {
         a.surv_cnt[qi] = n_surv;
         if (a.stats) {
@@ -889,14 +944,37 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
 
     // ---- results: R is already sorted by (dist,id); take(k) (leann.rs:895) -----------------
     const uint32_t cnt = r_len < a.k ? r_len : a.k;
-    for (uint32_t i = lane; i < a.k; i += 32) {
+    if constexpr (RREG) {
+      // the k best of the bag in (distance, id) order: k argmin rounds over the entries not yet taken (every flag is
+      // cleared first; a taken entry is flagged again); lane i % 32 keeps result i until its row of 32 is complete
+#pragma unroll
+      for (int j = 0; j < NR; ++j)
+        if ((uint32_t)(j * 32) + lane < r_len) ki[j] &= ~1u;
+    }
+    for (uint32_t i0 = 0; i0 < a.k; i0 += 32) {
+      const uint32_t i = i0 + lane;
       uint32_t id = 0xffffffffu;
       float dist = __int_as_float(0x7f800000);
-      if (i < cnt) {
+      if constexpr (RREG) {
+        for (uint32_t t = i0; t < min(i0 + 32, cnt); ++t) {
+          uint32_t tkd, tid;
+          XBagPos tp;
+          xbag_argmin_unexpanded<NR>(kd, ki, &tkd, &tid, &tp);  // t < r_len: there is one
+          const bool me = lane == tp.lane;
+#pragma unroll
+          for (int j = 0; j < NR; ++j)
+            if ((uint32_t)j == tp.row && me) ki[j] |= 1u;
+          if (lane == (t & 31)) {
+            id = tid;
+            dist = key_dist(tkd);
+          }
+        }
+      } else if (i < cnt) {
         const uint2 e = R.ld(i);
         id = e.y & ~kExpandedBit;
         dist = __uint_as_float(e.x);
       }
+      if (i >= a.k) continue;
       const size_t o = (size_t)qi * a.k + i;
       if (a.out_ids) a.out_ids[o] = i < cnt ? (uint64_t)id : ISL_INVALID_ID;
       if (a.out_ids32) a.out_ids32[o] = id;
