@@ -791,7 +791,35 @@ __global__ void __launch_bounds__(32) leann_search_kernel(const SearchArgs a) {
 
       // unvisited neighbours, in list order (leann.rs:933-937)
       uint32_t ucnt = 0;
-      for (uint32_t b = 0; b < deg; b += 32) {
+      // Lists without repeated ids (a finished index, scanned once): 64 positions per pass, two per lane, so that the
+      // visited-bit atomics of both halves — DRAM read-modify-writes on big shards — are in flight together instead of
+      // one dependent round trip per 32 positions.  (With repeated ids the second half must see the bits the first
+      // half set, so that the FIRST occurrence is the one that is kept: the sequential loop below.)
+      for (uint32_t b = 0; a.lists_unique && b < deg; b += 64) {
+        uint32_t nid2[2], old2[2];
+        bool ok2[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const uint32_t i = b + r * 32 + lane;
+          nid2[r] = i < deg ? __ldg(a.nbrs + start + i) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const bool valid = nid2[r] != 0xffffffffu;  // past the degree, or the padding of a fixed-stride row
+          if (sentinel) n_edge += __popc(__ballot_sync(0xffffffffu, valid));
+          ok2[r] = valid && nid2[r] < a.n;
+          old2[r] = 0xffffffffu;
+          if (ok2[r]) old2[r] = atomicOr(vis + (nid2[r] >> 5), 1u << (nid2[r] & 31));
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const bool unv = ok2[r] && !(old2[r] & (1u << (nid2[r] & 31)));
+          const uint32_t bal = __ballot_sync(0xffffffffu, unv);
+          if (unv) u_list[ucnt + __popc(bal & ((1u << lane) - 1))] = nid2[r];
+          ucnt += __popc(bal);
+        }
+      }
+      for (uint32_t b = 0; !a.lists_unique && b < deg; b += 32) {
         const uint32_t i = b + lane;
         bool valid = i < deg;
         uint32_t nid = 0xffffffffu;
