@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--no-adc", action="store_true", help="skip the secondary PQ ADC traversal + exact rerank measurement")
     ap.add_argument("--pq-m", type=int, default=32, help="subquantizers of the ADC secondary")
     ap.add_argument("--pq-ksub", type=int, default=128, help="centroids per subquantizer of the ADC secondary "
-                    "(128: a 16 KB table per query in shared memory keeps twice the warps resident of 256)")
+                    "(128: an 8 KB bfloat16 table per query in shared memory keeps twice the warps resident of 256)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline sample")
     ap.add_argument("--build-sample", type=int, default=10000, help="nodes of the construction cpu_baseline sample (oracle build + GPU build of the same prefix, graphs compared)")
     a = ap.parse_args()
@@ -397,7 +397,7 @@ def main():
     peak, peak_src = measured_peak()
     traffic = None  # DRAM bytes of this launch from the committed ncu --set full capture, when it is the same workload
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_search_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_search_traffic.json")) as f:
             tj = json.load(f)
         if tj["workload"] == {"n": n, "d": d, "nq": nq, "dataset": a.dataset, "ef": ef, "k": K_TOP}:
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
@@ -551,7 +551,8 @@ def main():
             pq_ksub = a.pq_ksub
             pq = ProductQuantizer(d, PQConfig(pq_m, pq_ksub, 8, 1))
             pq.train(xh[:20000])
-            index.attach_pq(pq, pq.encode(xh))
+            pq_codes = pq.encode(xh)
+            index.attach_pq(pq, pq_codes)
 
             def adc_recall(e):
                 r = index.search_adc_rerank_batch(qn, K_TOP, e)[0]
@@ -574,6 +575,17 @@ def main():
             same_adc = bool(np.array_equal(ids_bitset, ids_free) and np.array_equal(dist_bitset.view(np.uint32), dist_free.view(np.uint32)))
             if not same_adc:
                 failures.append("ADC traversal: bitset-free results differ from the visited-bitset results")
+            # the oracle's twin of this mode (orc_leann_search_adc_rerank: same bfloat16 table rule, same loop) on a bounded
+            # prefix of the same queries, same graph, codebooks, codes and ef: ids and distance bits must be equal
+            m_adc = min(nq, 2000)
+            t0 = time.perf_counter()
+            o_ids_adc, o_dist_adc, _ = orc.leann_search_adc_rerank(cfg._s, xh, g.node_offsets, g.neighbors, g.entry_point, pq.codebooks(),
+                                                                   pq_codes, qn[:m_adc], K_TOP, ef_adc, threads=threads)
+            cpu_adc_qps = m_adc / (time.perf_counter() - t0)
+            same_adc_cpu = bool(np.array_equal(o_ids_adc.astype(np.int64), ids_free[:m_adc].astype(np.int64))
+                                and np.array_equal(o_dist_adc.view(np.uint32), dist_free[:m_adc].view(np.uint32)))
+            if not same_adc_cpu:
+                failures.append(f"ADC traversal + rerank: GPU results differ from the CPU port on the first {m_adc} queries")
             ms = float(np.mean(ms_l))
             b = int(st.n_adc.sum()) * pq_m + int(st.n_edge.sum()) * 4 + int(st.n_hop.sum()) * 16 + int(st.n_rerank.sum()) * 4 * d \
                 + nq * (4 * d + 12 * K_TOP + pq_m * pq_ksub * 4)
@@ -587,8 +599,11 @@ def main():
                                   "traversal_sectors_per_s": (int(st.n_adc.sum()) * (pq_m // 32 if pq_m >= 32 else 1) + int(st.n_hop.sum()) * 8) / (ms * 1e-3),
                                   "frac_of_l2_sector_ceiling": (int(st.n_adc.sum()) * (pq_m // 32 if pq_m >= 32 else 1) + int(st.n_hop.sum()) * 8) / (ms * 1e-3) / 215e9,
                                   "bitset_free_results_equal_bitset_results": same_adc,
-                                  "bound": "instruction latency of the per-hop chain; the byte roofline is not the limiter: every access is one 32-byte "
-                                           "sector (profiles/r01_sector_ceiling.txt: 33-35 G random sectors/s is the HBM ceiling the bitset version sat on)",
+                                  "cpu_baseline": {"value": cpu_adc_qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                                                   "sample": f"orc_leann_search_adc_rerank on the first {m_adc} queries, same graph / codebooks / codes / ef, "
+                                                             f"all host threads; ids and distance bits equal to GPU: {same_adc_cpu}"},
+                                  "bound": "issue slots of the per-hop chain (profiles/r02_adc_bag_ncu.txt: 60 % busy at 21 resident queries per SM); the byte "
+                                           "roofline is not the limiter: every traversal access is one 32-byte sector out of L2, only the exact rerank streams from HBM",
                                   "note": "parity unpinned: no reference implementation of this mode exists (leann.rs:54-56); oracle <-> GPU bit-exact"}
             line["roofline"]["also"] = {"adc_rerank_kernel_qps": nq / ms * 1e3, "adc_rerank_recall_at_10": curve_adc[ef_adc], "adc_rerank_frac_of_hbm_bytes": b / ms / 1e6 / peak}
         del xh

@@ -329,6 +329,14 @@ isl_status isl_index_search_two_level(const isl_index* idx, const float* queries
  * table distances (pq.rs:341-348; same admission / termination / tie rules with adc as the key),
  * then the ef surviving candidates get their exact distance (distance.rs) and are returned sorted by
  * (distance, id).  Traversal reads m code bytes per visited node instead of 4*dim.
+ * Table entries of the TRAVERSAL: every entry of build_distance_tables (pq.rs:307-338) is rounded to bfloat16
+ * (round to nearest even on the f32 bit pattern, NaN -> quiet NaN) before it is folded; table_distance is then the
+ * f32 left fold over the subquantizers of those entries and a square root (pq.rs:341-348 otherwise unchanged).  The
+ * rounding error (2^-9 relative per entry) is two orders of magnitude below the quantisation error of the codes it
+ * ranks, and the per-query table is 2 bytes per entry in shared memory — twice the resident queries per SM.  Only
+ * the traversal's ranking uses these values: isl_pq_build_tables / isl_pq_table_distance / isl_pq_asymmetric_distance and the
+ * two-level search keep the f32 tables, and every returned distance is exact.  The oracle's twin
+ * (orc_leann_search_adc_rerank) follows the same rule; like the mode itself it is defined here, not by the reference.
  * With stats_or_null == NULL (one-byte codes, m = 16 / 32, ef <= 2048, n < 2^25) the traversal keeps no
  * visited set — a node may be scored more than once, which cannot change the result —;
  * with statistics it keeps the exact bitset, and n_adc counts distinct nodes scored.  Ids and distances
