@@ -315,6 +315,9 @@ isl_status isl_pq_asymmetric_distance(const isl_pq* pq, const float* query, uint
  * pq.rs:190-193), restated in csrc/std_rng.h.  A scripted sequence of draws: kinds[i] = 0 next_u32, 1 next_u64
  * (gen::<usize>()), 2 gen::<f32>() (bit pattern), 3 SliceRandom::choose index over `bound` elements.  Host code only. */
 isl_status isl_std_rng_draw(uint64_t seed, const uint8_t* kinds, uint64_t count, uint64_t bound, uint64_t* out);
+/* Test hook: the bfloat16 rounding the ADC traversal applies to its table entries (isl_index_search_adc_rerank below;
+ * csrc/common.cuh bf16_round_bits), element by element.  Host code only. */
+isl_status isl_adc_table_round(const float* in, uint64_t count, float* out);
 #endif
 
 /* ---- two-level search (docs/leann-specification.md:223-269; no reference code) ------ */

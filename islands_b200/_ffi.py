@@ -241,6 +241,7 @@ SIGNATURES = {
 # Test hooks: exported by the library, declared in the header only under ISL_TEST_HOOKS, not part of the product ABI.
 TEST_HOOKS = {
     "isl_std_rng_draw": (C.c_int, [C.c_uint64, C.POINTER(C.c_uint8), C.c_uint64, C.c_uint64, u64p]),
+    "isl_adc_table_round": (C.c_int, [f32p, C.c_uint64, f32p]),
 }
 
 _lib = None

@@ -224,6 +224,18 @@ isl_status isl_pq_asymmetric_distance(const isl_pq* pq, const float* query, uint
   return ISL_OK;
 }
 
+// The rounding of the ADC traversal's table entries (common.cuh), exposed so that it can be checked on its own.
+isl_status isl_adc_table_round(const float* in, uint64_t count, float* out) {
+  if ((!in || !out) && count) return fail(ISL_INVALID_ARGUMENT, "null pointer");
+  for (uint64_t i = 0; i < count; ++i) {
+    uint32_t u;
+    memcpy(&u, in + i, 4);
+    u = isl::bf16_round_bits(u);
+    memcpy(out + i, &u, 4);
+  }
+  return ISL_OK;
+}
+
 // The generator isl_pq_train draws from (std_rng.h = rand 0.8.5 StdRng::seed_from_u64), exposed so that the
 // restatement can be checked on its own: kind 0 = next_u32, 1 = next_u64, 2 = gen::<f32>() bits, 3 = choose(bound).
 isl_status isl_std_rng_draw(uint64_t seed, const uint8_t* kinds, uint64_t count, uint64_t bound, uint64_t* out) {

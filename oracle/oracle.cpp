@@ -891,6 +891,10 @@ static float bf16_round(float x) {
   return x;
 }
 
+void orc_adc_table_round(const float* in, uint64_t count, float* out) {
+  for (uint64_t i = 0; i < count; ++i) out[i] = bf16_round(in[i]);
+}
+
 // PQ ADC traversal + exact rerank: the loop of leann.rs:899-988 with table_distance (pq.rs:341-348)
 // as the distance, then exact distances for the ef survivors and a final (dist,id) sort.
 int32_t orc_leann_search_adc_rerank(const isl_leann_config* cfg, const float* vectors, uint64_t n, uint32_t d,

@@ -90,6 +90,8 @@ int32_t orc_leann_search_two_level(const isl_leann_config* cfg, const float* vec
                                    float* out_dist, uint32_t* out_count,
                                    isl_search_stats* stats_or_null, int32_t threads);
 
+/* The bfloat16 rounding of the ADC traversal's table entries, element by element (so that it can be checked on its own). */
+void orc_adc_table_round(const float* in, uint64_t count, float* out);
 /* "PQ ADC traversal + exact rerank" (definition: include/islands_b200.h isl_index_search_adc_rerank). */
 int32_t orc_leann_search_adc_rerank(const isl_leann_config* cfg, const float* vectors, uint64_t n, uint32_t d,
                                     const uint64_t* offsets, const uint64_t* nbrs, int64_t entry,

@@ -71,6 +71,8 @@ def lib():
         l.orc_leann_search_adc_rerank.argtypes = [C.c_void_p, f32p, C.c_uint64, C.c_uint32, u64p, u64p, C.c_int64,
                                                   f32p, C.c_uint32, C.c_uint32, u16p, f32p, C.c_uint64, C.c_uint32,
                                                   C.c_uint32, u64p, f32p, u32p, C.c_void_p, C.c_int32, C.c_uint32]
+        l.orc_adc_table_round.restype = None
+        l.orc_adc_table_round.argtypes = [f32p, C.c_uint64, f32p]
         l.orc_merge_topk.restype = None
         l.orc_merge_topk.argtypes = [u64p, f32p, C.c_uint32, C.c_uint64, C.c_uint32, u64p, f32p, u32p]
         l.orc_to_similarity.restype = C.c_float
@@ -274,6 +276,14 @@ def leann_search_adc_rerank(cfg, vectors, offsets, nbrs, entry, codebooks, codes
     if rc != 0:
         raise RuntimeError(f"orc_leann_search_adc_rerank status {rc}")
     return (ids, dist, cnt, st) if stats else (ids, dist, cnt)
+
+
+def adc_table_round(values):
+    """bfloat16 rounding of the ADC traversal's table entries (oracle.cpp bf16_round)."""
+    v = _f32(values).reshape(-1)
+    out = np.empty_like(v)
+    lib().orc_adc_table_round(_p(v, f32p), v.size, _p(out, f32p))
+    return out
 
 
 def merge_topk(ids, dist, k):
