@@ -30,7 +30,7 @@ constexpr int kStages = ISL_STAGES;
 // L2-resident global buffer so that enough warps stay resident per SM.
 constexpr uint32_t kEfSmemMax = 2048;
 #ifndef ISL_BAG_EF_MAX
-#define ISL_BAG_EF_MAX 512
+#define ISL_BAG_EF_MAX 1024
 #endif
 constexpr uint32_t kBagEfMax = ISL_BAG_EF_MAX;  // exact traversal: register bag up to this ef (0 disables it: dev builds)
 constexpr uint32_t kLutSmemMaxFloats = 8192;  // 32 KB of PQ tables per query in shared memory
@@ -177,9 +177,9 @@ isl_status plan_search(int32_t metric, uint32_t ld, uint32_t ef, uint32_t u_cap,
   plan->aq_cap = 0;
   plan->mode = 0;
   plan->nr = 0;
-  // up to ef = 512 the result set is an unsorted bag in registers (search_core.cuh), NR = 4 / 8 / 16 entries per lane
+  // up to ef = 1024 the result set is an unsorted bag in registers (search_core.cuh), NR = 4 / 8 / 16 / 32 entries per lane
   if (ef <= kBagEfMax) {
-    plan->nr = ef <= 128 ? 4 : (ef <= 256 ? 8 : 16);
+    plan->nr = ef <= 128 ? 4 : (ef <= 256 ? 8 : (ef <= 512 ? 16 : 32));
     switch (plan->acc) {
       case ACC_DOT: return plan_exact_bag_dot(plan->nr, ld, u_cap, sms, plan);
       case ACC_L2: return plan_exact_bag_l2(plan->nr, ld, u_cap, sms, plan);

@@ -119,7 +119,7 @@ __device__ __forceinline__ uint32_t prune_proportional(float prune_ratio, uint32
   return w ? w : 1u;  // nothing kept: the first candidate, still at list[0] (leann.rs:1049-1051)
 }
 
-// ---- R as an unsorted bag in registers (exact traversal, ef <= 512) -------------------------------------------------
+// ---- R as an unsorted bag in registers (exact traversal, ef <= 1024) ------------------------------------------------
 // The reference needs three things from its two heaps (leann.rs:899-988): the worst entry of R (admission `d < worst`,
 // eviction), the closest unexpanded entry (the next candidate) and, at the end, the k best in order.  None needs R
 // sorted while the search runs: entry i lives in row i / 32 of lane i % 32 and never moves; the worst entry is an argmax

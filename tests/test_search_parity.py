@@ -55,6 +55,18 @@ def test_search_ties_duplicate_vectors(gpu_lib, orc):
         _compare(orc, cfg, v, off, nbrs, entry, levels, q, k, ef)
 
 
+@pytest.mark.parametrize("dup", [0, 600])
+def test_search_every_result_structure(gpu_lib, orc, dup):
+    """The result set is a register bag of 4 / 8 / 16 / 32 entries per lane up to ef = 1024, a sorted shared-memory array up
+    to 2048 and a sorted global array above (search_core.cuh): every size class, with ef not a multiple of 32, k up to ef
+    (k argmin rounds over the bag) and — dup — a graph whose copied vectors force exact distance ties in the argmax /
+    argmin slow paths and in the tie list."""
+    cfg, v, levels, off, nbrs, entry = oracle_graph(orc, 2500, 32, seed=21, dup=dup)
+    q = np.concatenate([v[:48], uniform(np.random.RandomState(22), 48, 32)])
+    for k, ef in [(10, 100), (100, 100), (10, 129), (200, 200), (10, 500), (10, 513), (700, 700), (10, 1024), (10, 1025), (10, 2100)]:
+        _compare(orc, cfg, v, off, nbrs, entry, levels, q, k, ef)
+
+
 def test_search_large_ef_global_results(gpu_lib, orc):
     # ef above the shared-memory bound -> result array in global memory
     cfg, v, levels, off, nbrs, entry = oracle_graph(orc, 4000, 32, seed=12)
