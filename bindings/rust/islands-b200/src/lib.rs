@@ -1,6 +1,7 @@
 //! Safe wrapper over `libislands_b200.so` with the signatures of panbanda/islands' `src/core`
 //! (`src/core/mod.rs:60-99`): `LeannIndex::{new, build, search, search_with_params}`, `CsrGraph`,
-//! `LeannConfig`, `EmbeddingProvider`, `ProductQuantizer`, `DistanceMetric` / `Distance`, `CoreError`.
+//! `LeannConfig`, `EmbeddingProvider`, `HnswGraph` / `HnswConfig` / `HnswNode`, `Searcher` / `MultiIndexSearcher` /
+//! `SearchConfig` / `SearchResult`, `ProductQuantizer`, `DistanceMetric` / `Distance`, `CoreError`, the `prelude`.
 //! A maintainer of the reference swaps `use crate::core::leann::LeannIndex` for
 //! `use islands_b200::LeannIndex` and keeps the call sites.
 //!
@@ -632,6 +633,431 @@ impl Drop for ShardComm {
     fn drop(&mut self) {
         unsafe { sys::isl_shard_free(self.handle) };
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// hnsw.rs:15-125 — HnswConfig, HnswNode
+// ---------------------------------------------------------------------------------------------
+#[derive(Debug, Clone)]
+pub struct HnswConfig {
+    pub m: usize,
+    pub m0: usize,
+    pub ef_construction: usize,
+    pub ml: f64,
+    pub metric: DistanceMetric,
+    pub max_layers: usize,
+}
+
+impl Default for HnswConfig {
+    /// hnsw.rs:37-48 (the values come from the library: `isl_hnsw_config_default`).
+    fn default() -> Self {
+        let mut raw = std::mem::MaybeUninit::<sys::IslHnswConfig>::zeroed();
+        unsafe {
+            sys::isl_hnsw_config_default(raw.as_mut_ptr());
+            Self::from_raw(&raw.assume_init())
+        }
+    }
+}
+
+impl HnswConfig {
+    fn from_raw(c: &sys::IslHnswConfig) -> Self {
+        Self {
+            m: c.m as usize,
+            m0: c.m0 as usize,
+            ef_construction: c.ef_construction as usize,
+            ml: c.ml,
+            metric: DistanceMetric::from_code(c.metric),
+            max_layers: c.max_layers as usize,
+        }
+    }
+    fn raw(&self) -> sys::IslHnswConfig {
+        sys::IslHnswConfig {
+            m: self.m as u64,
+            m0: self.m0 as u64,
+            ef_construction: self.ef_construction as u64,
+            ml: self.ml,
+            metric: self.metric.code(),
+            max_layers: self.max_layers as u64,
+        }
+    }
+    /// hnsw.rs:30-35: the reference's constructor drops its argument and returns the defaults; kept.
+    pub fn new(_config: Self) -> Self {
+        Self::default()
+    }
+    /// hnsw.rs:52-59
+    pub fn fast() -> Self {
+        Self { m: 12, m0: 24, ef_construction: 100, ..Self::default() }
+    }
+    /// hnsw.rs:62-69
+    pub fn accurate() -> Self {
+        Self { m: 32, m0: 64, ef_construction: 400, ..Self::default() }
+    }
+    /// hnsw.rs:72-85
+    pub fn validate(&self) -> CoreResult<()> {
+        check(unsafe { sys::isl_hnsw_config_validate(&self.raw()) })
+    }
+}
+
+/// hnsw.rs:88-125.  The graph lives in HBM: a node is materialised on request (`HnswGraph::get_node` returns it by
+/// value, where the reference hands out a borrow of its `HashMap` entry).
+#[derive(Debug, Clone)]
+pub struct HnswNode {
+    pub id: u64,
+    pub vector: Vec<f32>,
+    pub connections: Vec<Vec<u64>>,
+    pub level: usize,
+}
+
+impl HnswNode {
+    pub fn neighbors_at(&self, layer: usize) -> Option<&[u64]> {
+        self.connections.get(layer).map(Vec::as_slice)
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// hnsw.rs:151-515 — HnswGraph (what `IndexerService` stores per island: service.rs:622, 655-657, 781-785)
+// ---------------------------------------------------------------------------------------------
+pub struct HnswGraph {
+    config: HnswConfig,
+    handle: *mut sys::IslHnsw,
+    /// The reference draws node levels from `thread_rng` (hnsw.rs:206-211); the library applies the same formula to
+    /// draw `node id` of a counter stream with this seed.
+    level_seed: u64,
+}
+
+// Searches lease per-call scratch inside the library; inserts take `&mut self`.
+unsafe impl Send for HnswGraph {}
+unsafe impl Sync for HnswGraph {}
+
+impl Drop for HnswGraph {
+    fn drop(&mut self) {
+        unsafe { sys::isl_hnsw_free(self.handle) };
+    }
+}
+
+impl HnswGraph {
+    /// hnsw.rs:167-178
+    pub fn new(config: HnswConfig) -> CoreResult<Self> {
+        config.validate()?;
+        let mut h: *mut sys::IslHnsw = ptr::null_mut();
+        check(unsafe { sys::isl_hnsw_new(&config.raw(), &mut h) })?;
+        Ok(Self { config, handle: h, level_seed: 0 })
+    }
+    pub fn with_defaults() -> CoreResult<Self> {
+        Self::new(HnswConfig::default())
+    }
+    pub fn with_level_seed(mut self, seed: u64) -> Self {
+        self.level_seed = seed;
+        self
+    }
+    pub fn config(&self) -> &HnswConfig {
+        &self.config
+    }
+    pub fn len(&self) -> usize {
+        unsafe { sys::isl_hnsw_len(self.handle) as usize }
+    }
+    pub fn is_empty(&self) -> bool {
+        self.len() == 0
+    }
+    pub fn dimension(&self) -> Option<usize> {
+        match unsafe { sys::isl_hnsw_dimension(self.handle) } {
+            0 => None,
+            d => Some(d as usize),
+        }
+    }
+    pub fn entry_point(&self) -> Option<u64> {
+        let ep = unsafe { sys::isl_hnsw_entry_point(self.handle) };
+        if ep < 0 {
+            None
+        } else {
+            Some(ep as u64)
+        }
+    }
+    pub fn max_level(&self) -> usize {
+        unsafe { sys::isl_hnsw_max_level(self.handle) as usize }
+    }
+
+    /// hnsw.rs:201-203: vector, level and the neighbour list of every layer the node reaches, copied from the device.
+    pub fn get_node(&self, id: u64) -> Option<HnswNode> {
+        let dim = self.dimension()?;
+        let mut level = 0u64;
+        check(unsafe { sys::isl_hnsw_node_level(self.handle, id, &mut level) }).ok()?;
+        let mut vector = vec![0f32; dim];
+        check(unsafe { sys::isl_hnsw_get_vector(self.handle, id, vector.as_mut_ptr()) }).ok()?;
+        let cap = self.config.m0.max(self.config.m);
+        let mut connections = Vec::with_capacity(level as usize + 1);
+        for layer in 0..=level {
+            let mut list = vec![0u64; cap];
+            let mut count = 0u64;
+            check(unsafe { sys::isl_hnsw_get_neighbors(self.handle, id, layer, list.as_mut_ptr(), cap as u64, &mut count) }).ok()?;
+            list.truncate(count as usize);
+            connections.push(list);
+        }
+        Some(HnswNode { id, vector, connections, level: level as usize })
+    }
+
+    /// hnsw.rs:214-250: one sequential insert (`batch = 1` is the reference's loop).
+    pub fn insert(&mut self, vector: Vec<f32>) -> CoreResult<u64> {
+        self.insert_batch(&vector, 1, 1)
+    }
+
+    /// `count` inserts of `[count][dim]` row-major vectors in one call; `batch > 1` inserts rounds of that many
+    /// nodes against one graph snapshot (GPU-parallel construction).  Returns the id of the first new node.
+    pub fn insert_batch(&mut self, vectors: &[f32], count: usize, batch: u32) -> CoreResult<u64> {
+        if count == 0 {
+            return Ok(self.len() as u64);
+        }
+        let dim = vectors.len() / count;
+        let mut first = 0u64;
+        check(unsafe {
+            sys::isl_hnsw_insert_batch(self.handle, vectors.as_ptr(), count as u64, dim as u32, ptr::null(), self.level_seed, batch, &mut first)
+        })?;
+        Ok(first)
+    }
+
+    /// hnsw.rs:458-504
+    pub fn search(&self, query: &[f32], k: usize, ef: usize) -> CoreResult<Vec<(u64, f32)>> {
+        if self.is_empty() {
+            return Ok(vec![]); // hnsw.rs:459-461
+        }
+        let (ids, dist, count) = self.search_batch(query, 1, k, ef)?;
+        Ok((0..count[0] as usize).map(|i| (ids[i], dist[i])).collect())
+    }
+
+    /// Batched form: `queries` is `[nq][dim]` row-major; ids / distances `[nq][k]` (padded with `u64::MAX` / `+inf`)
+    /// and the result count per query.
+    pub fn search_batch(&self, queries: &[f32], nq: usize, k: usize, ef: usize) -> CoreResult<(Vec<u64>, Vec<f32>, Vec<u32>)> {
+        let dim = if nq == 0 { 0 } else { queries.len() / nq };
+        let (mut ids, mut dist, mut count) = (vec![u64::MAX; nq * k], vec![f32::INFINITY; nq * k], vec![0u32; nq]);
+        if nq == 0 || self.is_empty() {
+            return Ok((ids, dist, count));
+        }
+        check(unsafe {
+            sys::isl_hnsw_search(self.handle, queries.as_ptr(), nq as u64, dim as u32, k as u32, ef as u32, ids.as_mut_ptr(),
+                                 dist.as_mut_ptr(), count.as_mut_ptr())
+        })?;
+        Ok((ids, dist, count))
+    }
+
+    /// hnsw.rs:507-509 (bincode layout)
+    pub fn to_bytes(&self) -> CoreResult<Vec<u8>> {
+        let mut len = 0u64;
+        check(unsafe { sys::isl_hnsw_to_bytes(self.handle, ptr::null_mut(), 0, &mut len) })
+            .map_err(|e| CoreError::Serialization(e.to_string()))?;
+        let mut out = vec![0u8; len as usize];
+        check(unsafe { sys::isl_hnsw_to_bytes(self.handle, out.as_mut_ptr(), len, &mut len) })
+            .map_err(|e| CoreError::Serialization(e.to_string()))?;
+        Ok(out)
+    }
+
+    /// hnsw.rs:512-514
+    pub fn from_bytes(bytes: &[u8]) -> CoreResult<Self> {
+        let mut h: *mut sys::IslHnsw = ptr::null_mut();
+        check(unsafe { sys::isl_hnsw_from_bytes(bytes.as_ptr(), bytes.len() as u64, &mut h) })?;
+        let mut raw = std::mem::MaybeUninit::<sys::IslHnswConfig>::zeroed();
+        let got = check(unsafe { sys::isl_hnsw_get_config(h, raw.as_mut_ptr()) });
+        if let Err(e) = got {
+            unsafe { sys::isl_hnsw_free(h) };
+            return Err(e);
+        }
+        Ok(Self { config: HnswConfig::from_raw(unsafe { &raw.assume_init() }), handle: h, level_seed: 0 })
+    }
+}
+
+/// mod.rs:79-85 (compatibility aliases)
+pub type Index = HnswGraph;
+pub type IndexConfig = HnswConfig;
+pub type IndexBuilder = HnswConfig;
+pub type Error = CoreError;
+
+// ---------------------------------------------------------------------------------------------
+// search.rs:9-249 — SearchConfig, SearchResult, Searcher, MultiIndexSearcher
+// ---------------------------------------------------------------------------------------------
+#[derive(Debug, Clone)]
+pub struct SearchConfig {
+    pub top_k: usize,
+    pub ef: usize,
+    pub include_vectors: bool,
+    pub include_metadata: bool,
+    pub min_similarity: Option<f32>,
+}
+
+impl Default for SearchConfig {
+    fn default() -> Self {
+        Self { top_k: 10, ef: 100, include_vectors: false, include_metadata: true, min_similarity: None }
+    }
+}
+
+impl SearchConfig {
+    /// search.rs:36-42
+    pub fn fast(k: usize) -> Self {
+        Self { top_k: k, ef: k * 2, ..Self::default() }
+    }
+    /// search.rs:45-51
+    pub fn accurate(k: usize) -> Self {
+        Self { top_k: k, ef: k * 10, ..Self::default() }
+    }
+}
+
+/// search.rs:54-103
+#[derive(Debug, Clone, serde::Serialize, serde::Deserialize)]
+pub struct SearchResult {
+    pub id: u64,
+    pub score: f32,
+    pub vector: Option<Vec<f32>>,
+    pub metadata: Option<serde_json::Value>,
+    pub text: Option<String>,
+}
+
+impl SearchResult {
+    pub fn new(id: u64, score: f32) -> Self {
+        Self { id, score, vector: None, metadata: None, text: None }
+    }
+    pub fn with_vector(mut self, vector: Vec<f32>) -> Self {
+        self.vector = Some(vector);
+        self
+    }
+    pub fn with_metadata(mut self, metadata: serde_json::Value) -> Self {
+        self.metadata = Some(metadata);
+        self
+    }
+    pub fn with_text(mut self, text: impl Into<String>) -> Self {
+        self.text = Some(text.into());
+        self
+    }
+    /// 1 / (1 + distance)
+    pub fn to_similarity(&self) -> f32 {
+        1.0 / (1.0 + self.score)
+    }
+}
+
+/// Raw `(id, distance)` rows of one graph -> `SearchResult`s under `config` (vectors attached on request, then the
+/// `min_similarity` filter: search.rs:155-176).
+fn decorate(graph: &HnswGraph, config: &SearchConfig, raw: impl Iterator<Item = (u64, f32)>) -> Vec<SearchResult> {
+    raw.map(|(id, distance)| {
+        let hit = SearchResult::new(id, distance);
+        // the node is only fetched from the device when its vector was asked for
+        match config.include_vectors.then(|| graph.get_node(id)).flatten() {
+            Some(node) => hit.with_vector(node.vector),
+            None => hit,
+        }
+    })
+    .filter(|hit| config.min_similarity.map_or(true, |floor| hit.to_similarity() >= floor))
+    .collect()
+}
+
+/// search.rs:106-182
+pub struct Searcher<'a> {
+    graph: &'a HnswGraph,
+    config: SearchConfig,
+}
+
+impl<'a> Searcher<'a> {
+    pub fn new(graph: &'a HnswGraph) -> Self {
+        Self { graph, config: SearchConfig::default() }
+    }
+    pub fn with_config(graph: &'a HnswGraph, config: SearchConfig) -> Self {
+        Self { graph, config }
+    }
+    pub fn top_k(mut self, k: usize) -> Self {
+        self.config.top_k = k;
+        self
+    }
+    pub fn ef(mut self, ef: usize) -> Self {
+        self.config.ef = ef;
+        self
+    }
+    pub fn include_vectors(mut self) -> Self {
+        self.config.include_vectors = true;
+        self
+    }
+    pub fn min_similarity(mut self, threshold: f32) -> Self {
+        self.config.min_similarity = Some(threshold);
+        self
+    }
+
+    /// search.rs:150-176
+    pub fn search(&self, query: &[f32]) -> CoreResult<Vec<SearchResult>> {
+        let raw = self.graph.search(query, self.config.top_k, self.config.ef)?;
+        Ok(decorate(self.graph, &self.config, raw.into_iter()))
+    }
+
+    /// search.rs:179-181 maps `search` over the queries one by one; here the whole batch is ONE library call
+    /// (one kernel launch over all queries), with the same per-query results.
+    pub fn search_batch(&self, queries: &[Vec<f32>]) -> CoreResult<Vec<Vec<SearchResult>>> {
+        let nq = queries.len();
+        if nq == 0 || self.graph.is_empty() {
+            return Ok(vec![Vec::new(); nq]);
+        }
+        let dim = self.graph.dimension().unwrap_or(queries[0].len());
+        let mut flat = Vec::with_capacity(nq * dim);
+        for q in queries {
+            if q.len() != dim {
+                return Err(CoreError::DimensionMismatch { expected: dim, actual: q.len() });
+            }
+            flat.extend_from_slice(q);
+        }
+        let k = self.config.top_k;
+        let (ids, dist, count) = self.graph.search_batch(&flat, nq, k, self.config.ef)?;
+        Ok((0..nq)
+            .map(|q| {
+                let rows = (0..count[q] as usize).map(|i| (ids[q * k + i], dist[q * k + i]));
+                decorate(self.graph, &self.config, rows)
+            })
+            .collect())
+    }
+}
+
+/// search.rs:185-254: every island is searched and the lists are merged by score, island order breaking ties (the
+/// reference's stable sort).  `min_similarity` is not applied here, as in the reference.
+pub struct MultiIndexSearcher {
+    graphs: Vec<(String, HnswGraph)>,
+    config: SearchConfig,
+}
+
+impl Default for MultiIndexSearcher {
+    fn default() -> Self {
+        Self::new()
+    }
+}
+
+impl MultiIndexSearcher {
+    pub fn new() -> Self {
+        Self { graphs: Vec::new(), config: SearchConfig::default() }
+    }
+    pub fn add_index(&mut self, name: impl Into<String>, graph: HnswGraph) {
+        self.graphs.push((name.into(), graph));
+    }
+    pub fn with_config(mut self, config: SearchConfig) -> Self {
+        self.config = config;
+        self
+    }
+    /// search.rs:211-237
+    pub fn search(&self, query: &[f32]) -> CoreResult<Vec<(String, SearchResult)>> {
+        let unfiltered = SearchConfig { min_similarity: None, ..self.config.clone() };
+        let mut merged: Vec<(String, SearchResult)> = Vec::new();
+        for (name, graph) in &self.graphs {
+            let raw = graph.search(query, self.config.top_k, self.config.ef)?;
+            merged.extend(decorate(graph, &unfiltered, raw.into_iter()).into_iter().map(|hit| (name.clone(), hit)));
+        }
+        merged.sort_by(|a, b| a.1.score.partial_cmp(&b.1.score).unwrap_or(std::cmp::Ordering::Equal));
+        merged.truncate(self.config.top_k);
+        Ok(merged)
+    }
+    pub fn num_indexes(&self) -> usize {
+        self.graphs.len()
+    }
+    pub fn total_vectors(&self) -> usize {
+        self.graphs.iter().map(|(_, g)| g.len()).sum()
+    }
+}
+
+/// mod.rs:88-99
+pub mod prelude {
+    pub use super::{
+        CoreError, CoreResult, CsrGraph, Distance, DistanceMetric, EmbeddingProvider, HnswConfig, HnswGraph, InMemoryEmbeddingProvider,
+        LeannConfig, LeannIndex, ProductQuantizer, PruningStrategy, SearchConfig, SearchResult, Searcher,
+    };
 }
 
 // ---------------------------------------------------------------------------------------------
