@@ -9,13 +9,16 @@
 //   islands::HnswConfig / HnswGraph                       src/core/hnsw.rs:15-86, 151-531
 //   islands::EncoderConfig / Encoder                     src/core/embedding/candle_provider.rs:353-507
 //   islands::PQConfig / ProductQuantizer                    src/core/pq.rs:13-65, 116-359
-//   islands::merge_results                                  src/core/search.rs:211-237
+//   islands::SearchConfig / SearchResult / Searcher / MultiIndexSearcher   src/core/search.rs:9-249
+//   islands::ShardComm (+ LeannIndex::search_sharded)       src/indexer/service.rs:777-801
 // Link with -lislands_b200 (islands_b200/lib).  All compute runs on the GPU; nothing here has a
 // CPU fallback.
 #pragma once
 
 #include <algorithm>
+#include <array>
 #include <cstdint>
+#include <optional>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -112,6 +115,56 @@ struct CsrGraph {  // leann.rs:193-208
 
 using SearchResults = std::vector<std::pair<uint64_t, float>>;  // Vec<(u64, f32)>
 
+// Batched results: ids / dist are [nq][k] row-major (padded with ISL_INVALID_ID / +inf), count[q] <= k entries are valid.
+struct BatchResults {
+  uint32_t k = 0;
+  std::vector<uint64_t> ids;
+  std::vector<float> dist;
+  std::vector<uint32_t> count;
+  BatchResults(uint64_t nq, uint32_t k_) : k(k_), ids(nq * k_, ISL_INVALID_ID), dist(nq * k_, 0.0f), count(nq, 0) {}
+  SearchResults row(uint64_t q) const {
+    SearchResults out;
+    for (uint32_t i = 0; i < count[q]; ++i) out.emplace_back(ids[q * k + i], dist[q * k + i]);
+    return out;
+  }
+};
+
+namespace detail {
+// The two-call protocol of the *_to_bytes entry points: size query, then fill.
+template <class Handle, class Fn>
+std::vector<uint8_t> bytes_of(const Handle* h, Fn to_bytes) {
+  uint64_t len = 0;
+  check(to_bytes(h, nullptr, 0, &len));
+  std::vector<uint8_t> out(len);
+  check(to_bytes(h, out.data(), len, &len));
+  return out;
+}
+}  // namespace detail
+
+// One rank's membership in a sharded index: NCCL communicator inside the library (csrc/api_shard.cu).
+class ShardComm {
+ public:
+  using UniqueId = std::array<uint8_t, 128>;
+  // ncclGetUniqueId: call on one rank, hand the 128 bytes to the others by any host channel.
+  static UniqueId unique_id() {
+    UniqueId id{};
+    check(isl_shard_unique_id(id.data(), id.size()));
+    return id;
+  }
+  ShardComm(int rank, int world, const UniqueId& id) { check(isl_shard_init(rank, world, id.data(), &h_)); }
+  ~ShardComm() { isl_shard_free(h_); }
+  ShardComm(const ShardComm&) = delete;
+  ShardComm& operator=(const ShardComm&) = delete;
+  int rank() const { return isl_shard_rank(h_); }
+  int world() const { return isl_shard_world(h_); }
+  // Exchange by peer stores over NVLink instead of ncclAllGather (collective; ranks of one node).
+  void enable_peer_exchange(uint64_t max_records) { check(isl_shard_enable_peer_exchange(h_, max_records)); }
+  isl_shard* handle() const { return h_; }
+
+ private:
+  isl_shard* h_ = nullptr;
+};
+
 class LeannIndex {
  public:
   explicit LeannIndex(const LeannConfig& cfg = LeannConfig()) : cfg_(cfg) { cfg_.validate(); }
@@ -169,6 +222,55 @@ class LeannIndex {
     for (uint32_t i = 0; i < count; ++i) out.emplace_back(ids[i], dist[i]);
     return out;
   }
+  // Batched form (what a GPU wants): queries [nq][dim] row-major, one kernel launch over all of them.
+  BatchResults search_batch(const std::vector<float>& queries, uint64_t nq, uint32_t k, uint32_t ef) const {
+    BatchResults r(nq, k);
+    check(isl_index_search(h_, queries.data(), nq, nq ? (uint32_t)(queries.size() / nq) : 0, k, ef, r.ids.data(), r.dist.data(),
+                           r.count.data(), nullptr));
+    return r;
+  }
+  BatchResults search_sharded(const ShardComm& shard, uint64_t id_base, const std::vector<float>& queries, uint64_t nq,
+                              uint32_t k, uint32_t ef) const {
+    BatchResults r(nq, k);
+    search_sharded(shard.handle(), id_base, queries, nq, k, ef, &r.ids, &r.dist, &r.count);
+    return r;
+  }
+  // to_bytes / from_bytes (leann.rs:1059-1066): the bincode image holds the graph only, so from_bytes also takes the
+  // embeddings [n][dim] the provider returns.
+  std::vector<uint8_t> to_bytes() const { return detail::bytes_of(h_, isl_index_to_bytes); }
+  void from_bytes(const std::vector<uint8_t>& bytes, const std::vector<float>& embeddings, uint32_t dim) {
+    reset();
+    check(isl_index_from_bytes(bytes.data(), bytes.size(), embeddings.data(), dim, &h_));
+    check(isl_index_get_config(h_, &cfg_));
+  }
+  // InMemoryEmbeddingProvider::compute_embedding (leann.rs:141-150) of the resident embeddings
+  std::vector<float> get_vector(uint64_t node_id) const {
+    std::vector<float> out(dimension());
+    check(isl_index_get_vector(h_, node_id, out.data()));
+    return out;
+  }
+  // On-demand recompute (leann.rs:82-99, 947-950): `enc` over one token row per node [n][seq_len] plays the
+  // EmbeddingProvider; drop_vectors frees the resident embeddings (graph + codes + token rows remain).
+  void set_recompute(isl_encoder* enc, const std::vector<int32_t>& token_ids, const std::vector<int32_t>& lengths,
+                     uint32_t seq_len) {
+    check(isl_index_set_recompute(h_, enc, token_ids.data(), lengths.data(), seq_len));
+  }
+  void drop_vectors() { check(isl_index_drop_vectors(h_)); }
+  void set_hub_cache(uint64_t count) { check(isl_index_set_hub_cache(h_, count)); }
+  // the reference's loop: every hop's unvisited neighbours are embedded by the provider (one encoder pass per frontier)
+  BatchResults search_recompute(const std::vector<float>& queries, uint64_t nq, uint32_t k, uint32_t ef) const {
+    BatchResults r(nq, k);
+    check(isl_index_search_recompute(h_, queries.data(), nq, nq ? (uint32_t)(queries.size() / nq) : 0, k, ef, r.ids.data(),
+                                     r.dist.data(), r.count.data(), nullptr));
+    return r;
+  }
+  // the cheap variant: ADC traversal -> encoder over the distinct survivors -> exact rerank
+  BatchResults search_adc_recompute(const std::vector<float>& queries, uint64_t nq, uint32_t k, uint32_t ef) const {
+    BatchResults r(nq, k);
+    check(isl_index_search_adc_recompute(h_, queries.data(), nq, nq ? (uint32_t)(queries.size() / nq) : 0, k, ef,
+                                         r.ids.data(), r.dist.data(), r.count.data(), nullptr));
+    return r;
+  }
   CsrGraph graph() const {
     CsrGraph g;
     g.num_nodes = len();
@@ -222,9 +324,44 @@ struct HnswConfig : isl_hnsw_config {
   void validate() const { check(isl_hnsw_config_validate(this)); }
 };
 
+struct HnswNode {  // hnsw.rs:88-125, materialised from the device on request
+  uint64_t id = 0;
+  std::vector<float> vector;
+  std::vector<std::vector<uint64_t>> connections;  // [layer] -> neighbour ids, layers 0..level
+  uint64_t level = 0;
+  const std::vector<uint64_t>* neighbors_at(uint64_t layer) const {
+    return layer < connections.size() ? &connections[layer] : nullptr;
+  }
+};
+
 class HnswGraph {  // hnsw.rs:151-531
  public:
   explicit HnswGraph(const HnswConfig& cfg = HnswConfig()) { check(isl_hnsw_new(&cfg, &h_)); }
+  // HnswGraph::from_bytes (hnsw.rs:512-514)
+  explicit HnswGraph(const std::vector<uint8_t>& bytes) { check(isl_hnsw_from_bytes(bytes.data(), bytes.size(), &h_)); }
+  std::vector<uint8_t> to_bytes() const { return detail::bytes_of(h_, isl_hnsw_to_bytes); }  // hnsw.rs:507-509
+  HnswConfig config() const {
+    HnswConfig c;
+    check(isl_hnsw_get_config(h_, &c));
+    return c;
+  }
+  // get_node (hnsw.rs:201-203): nullopt for an unknown id
+  std::optional<HnswNode> get_node(uint64_t id) const {
+    HnswNode node;
+    node.id = id;
+    if (id >= len() || isl_hnsw_node_level(h_, id, &node.level) != ISL_OK) return std::nullopt;
+    node.vector.resize(dimension());
+    check(isl_hnsw_get_vector(h_, id, node.vector.data()));
+    for (uint64_t layer = 0; layer <= node.level; ++layer) node.connections.push_back(neighbors_at(id, layer));
+    return node;
+  }
+  BatchResults search_batch(const std::vector<float>& queries, uint64_t nq, uint32_t k, uint32_t ef) const {
+    BatchResults r(nq, k);
+    if (nq == 0 || is_empty()) return r;  // hnsw.rs:459-461
+    check(isl_hnsw_search(h_, queries.data(), nq, (uint32_t)(queries.size() / nq), k, ef, r.ids.data(), r.dist.data(),
+                          r.count.data()));
+    return r;
+  }
   ~HnswGraph() { isl_hnsw_free(h_); }
   HnswGraph(const HnswGraph&) = delete;
   HnswGraph& operator=(const HnswGraph&) = delete;
@@ -315,6 +452,25 @@ class ProductQuantizer {
     check(isl_pq_asymmetric_distance(h_, q.data(), (uint32_t)q.size(), codes.data(), 1, &out));
     return out;
   }
+  // build_distance_tables (pq.rs:307-338): [m][ksub] row-major; table_distance (pq.rs:341-348) for one code row
+  std::vector<float> build_distance_tables(const std::vector<float>& q) const {
+    uint64_t ksub = 0;
+    check(isl_pq_get_codebooks(h_, nullptr, &ksub));
+    std::vector<float> tables(num_subquantizers() * ksub);
+    check(isl_pq_build_tables(h_, q.data(), (uint32_t)q.size(), tables.data()));
+    return tables;
+  }
+  float table_distance(const std::vector<float>& tables, const std::vector<uint16_t>& codes) const {
+    float out = 0.0f;
+    check(isl_pq_table_distance(h_, tables.data(), codes.data(), 1, &out));
+    return out;
+  }
+  // to_bytes / from_bytes (pq.rs:351-358)
+  std::vector<uint8_t> to_bytes() const { return detail::bytes_of(h_, isl_pq_to_bytes); }
+  explicit ProductQuantizer(const std::vector<uint8_t>& bytes) : dim_(0) {
+    check(isl_pq_from_bytes(bytes.data(), bytes.size(), &h_));
+    dim_ = isl_pq_dimension(h_);
+  }
   isl_pq* handle() const { return h_; }
 
  private:
@@ -353,5 +509,99 @@ class Encoder {
 
 // ---- search.rs ----------------------------------------------------------------------------------
 inline float to_similarity(float score) { return 1.0f / (1.0f + score); }  // search.rs:99-102
+
+struct SearchConfig {  // search.rs:9-52
+  uint32_t top_k = 10, ef = 100;
+  bool include_vectors = false, include_metadata = true;
+  std::optional<float> min_similarity;
+  static SearchConfig fast(uint32_t k) {
+    SearchConfig c;
+    c.top_k = k, c.ef = k * 2;
+    return c;
+  }
+  static SearchConfig accurate(uint32_t k) {
+    SearchConfig c;
+    c.top_k = k, c.ef = k * 10;
+    return c;
+  }
+};
+
+struct SearchResult {  // search.rs:54-103 (metadata / text are the caller's: the index stores neither)
+  uint64_t id = 0;
+  float score = 0.0f;
+  std::optional<std::vector<float>> vector;
+  std::optional<std::string> text;
+  float to_similarity() const { return islands::to_similarity(score); }
+};
+
+namespace detail {
+// (id, distance) rows of one graph -> SearchResults under `cfg`: vectors on request, then the min_similarity filter
+// (search.rs:155-176).
+inline std::vector<SearchResult> decorate(const HnswGraph& g, const SearchConfig& cfg, const SearchResults& rows,
+                                          bool filter) {
+  std::vector<SearchResult> out;
+  for (const auto& [id, d] : rows) {
+    SearchResult r;
+    r.id = id, r.score = d;
+    if (filter && cfg.min_similarity && r.to_similarity() < *cfg.min_similarity) continue;
+    if (cfg.include_vectors)
+      if (auto node = g.get_node(id)) r.vector = std::move(node->vector);
+    out.push_back(std::move(r));
+  }
+  return out;
+}
+}  // namespace detail
+
+class Searcher {  // search.rs:106-182
+ public:
+  explicit Searcher(const HnswGraph& graph, SearchConfig cfg = SearchConfig()) : g_(graph), cfg_(cfg) {}
+  Searcher& top_k(uint32_t k) { return cfg_.top_k = k, *this; }
+  Searcher& ef(uint32_t ef) { return cfg_.ef = ef, *this; }
+  Searcher& include_vectors() { return cfg_.include_vectors = true, *this; }
+  Searcher& min_similarity(float t) { return cfg_.min_similarity = t, *this; }
+  std::vector<SearchResult> search(const std::vector<float>& query) const {
+    if (g_.is_empty()) return {};
+    return detail::decorate(g_, cfg_, g_.search(query, cfg_.top_k, cfg_.ef), true);
+  }
+  // search.rs:179-181 maps `search` over the queries; here the batch is one library call over [nq][dim] queries.
+  std::vector<std::vector<SearchResult>> search_batch(const std::vector<float>& queries, uint64_t nq) const {
+    std::vector<std::vector<SearchResult>> out;
+    const BatchResults r = g_.search_batch(queries, nq, cfg_.top_k, cfg_.ef);
+    for (uint64_t q = 0; q < nq; ++q) out.push_back(detail::decorate(g_, cfg_, r.row(q), true));
+    return out;
+  }
+
+ private:
+  const HnswGraph& g_;
+  SearchConfig cfg_;
+};
+
+// search.rs:185-254: every island is searched, the lists are merged by score with the island order breaking ties
+// (the reference's stable sort) and cut to top_k; min_similarity is not applied, as in the reference.
+class MultiIndexSearcher {
+ public:
+  void add_index(std::string name, const HnswGraph* graph) { graphs_.emplace_back(std::move(name), graph); }
+  MultiIndexSearcher& with_config(SearchConfig cfg) { return cfg_ = cfg, *this; }
+  std::vector<std::pair<std::string, SearchResult>> search(const std::vector<float>& query) const {
+    std::vector<std::pair<std::string, SearchResult>> all;
+    for (const auto& [name, g] : graphs_) {
+      if (g->is_empty()) continue;
+      for (auto& r : detail::decorate(*g, cfg_, g->search(query, cfg_.top_k, cfg_.ef), false)) all.emplace_back(name, std::move(r));
+    }
+    std::stable_sort(all.begin(), all.end(), [](const auto& a, const auto& b) { return a.second.score < b.second.score; });
+    if (all.size() > cfg_.top_k) all.resize(cfg_.top_k);
+    return all;
+  }
+  size_t num_indexes() const { return graphs_.size(); }
+  uint64_t total_vectors() const {
+    uint64_t n = 0;
+    for (const auto& g : graphs_) n += g.second->len();
+    return n;
+  }
+
+ private:
+  std::vector<std::pair<std::string, const HnswGraph*>> graphs_;  // not owned: handles are not copyable
+  SearchConfig cfg_;
+};
 
 }  // namespace islands

@@ -42,6 +42,22 @@ int main(int argc, char** argv) {
   HnswConfig hc;
   EXPECT(hc.m == 16 && hc.m0 == 32 && hc.ef_construction == 200 && hc.max_layers == 16);  // hnsw.rs:533-545
   EXPECT(std::fabs(to_similarity(1.0f) - 0.5f) < 1e-7f);
+  {  // search.rs:9-103 host-side types (reference tests search.rs:262-324)
+    SearchConfig sc;
+    EXPECT(sc.top_k == 10 && sc.ef == 100 && !sc.include_vectors && sc.include_metadata && !sc.min_similarity);
+    EXPECT(SearchConfig::fast(5).ef == 10 && SearchConfig::accurate(5).ef == 50 && SearchConfig::fast(5).top_k == 5);
+    SearchResult sr;
+    sr.score = 1.0f;
+    EXPECT(std::fabs(sr.to_similarity() - 0.5f) < 1e-7f && !sr.vector && !sr.text);
+    HnswNode node;
+    node.connections = {{1, 2}, {3}};
+    EXPECT(node.neighbors_at(1) && node.neighbors_at(1)->size() == 1 && node.neighbors_at(2) == nullptr);  // hnsw.rs:117-119
+    BatchResults br(2, 3);
+    br.ids[3] = 7, br.dist[3] = 0.25f, br.count[1] = 1;
+    EXPECT(br.row(0).empty() && br.row(1).size() == 1 && br.row(1)[0].first == 7 && br.ids[0] == ISL_INVALID_ID);
+    MultiIndexSearcher multi;
+    EXPECT(multi.num_indexes() == 0 && multi.total_vectors() == 0 && multi.search({1.f, 2.f}).empty());  // search.rs:416-424
+  }
   if (argc > 1 && std::strcmp(argv[1], "gpu") == 0) {
     EXPECT(std::fabs(calculate(DistanceMetric::Euclidean, {0.f, 0.f}, {3.f, 4.f}) - 5.0f) < 1e-6f);
     const uint32_t n = 300, d = 16;
