@@ -101,6 +101,10 @@ class DistanceMetric:
     def __repr__(self):
         return f"DistanceMetric.{self._names[self.value]}"
 
+    def debug_name(self):
+        """`{:?}` of the variant (distance.rs:9-19): Cosine, Euclidean, DotProduct, Manhattan."""
+        return ("Cosine", "Euclidean", "DotProduct", "Manhattan")[self.value]
+
     def calculate(self, a, b):
         a, b = _f32(a), _f32(b)
         out = C.c_float()
@@ -210,6 +214,19 @@ class HnswConfig:
         if name in HnswConfig._fields:
             return getattr(self._s, name)
         raise AttributeError(name)
+
+    @classmethod
+    def new(cls, _config=None):
+        """HnswConfig::new (hnsw.rs:30-35) drops its argument and returns the defaults; kept."""
+        return cls()
+
+    @classmethod
+    def fast(cls):
+        return cls(m=12, m0=24, ef_construction=100)  # hnsw.rs:52-59
+
+    @classmethod
+    def accurate(cls):
+        return cls(m=32, m0=64, ef_construction=400)  # hnsw.rs:62-69
 
     def validate(self):
         _check(_ffi.load().isl_hnsw_config_validate(C.byref(self._s)))
@@ -347,6 +364,21 @@ class InMemoryEmbeddingProvider:
         if e.size == 0:
             raise EmptyCollection("empty collection")
         self.embeddings = e.reshape(-1, e.shape[-1])
+
+    @classmethod
+    def with_dimension(cls, dimension):
+        """An empty provider of a fixed dimension (leann.rs:136-141), filled with `add`."""
+        self = cls.__new__(cls)
+        self.embeddings = np.zeros((0, int(dimension)), np.float32)
+        return self
+
+    def add(self, embedding):
+        """leann.rs:123-133: append one embedding, returns its id."""
+        e = _f32(embedding).reshape(-1)
+        if e.size != self.embeddings.shape[1]:
+            raise DimensionMismatch(f"dimension mismatch: expected {self.embeddings.shape[1]}, got {e.size}")
+        self.embeddings = np.concatenate([self.embeddings, e[None, :]])
+        return self.embeddings.shape[0] - 1
 
     def dimension(self):
         return self.embeddings.shape[1]

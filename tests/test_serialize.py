@@ -34,6 +34,8 @@ def test_bincode_oracle_known_answers():
 
 @pytest.mark.gpu
 def test_leann_index_bytes_match_oracle_and_round_trip(gpu_lib, orc):
+    """to_bytes / from_bytes (leann.rs:1059-1066) and the reference's own round-trip tests (leann.rs:1346-1384: the
+    restored index has the same length and answers searches), plus the bytes themselves against the bincode restatement."""
     from islands_b200 import LeannIndex, SerializationError
     from oracle import bincode_oracle as bo
 
