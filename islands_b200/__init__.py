@@ -10,7 +10,7 @@ from .core import (Encoder, EncoderConfig, gemm_bf16_dev, CoreError, CsrGraph, C
 from .registry import IslandRegistry, StoredIndex
 from .search import MultiIndexSearcher, SearchConfig, Searcher, SearchResult
 from .storage import DeserializationError, FileSystemStorage, IndexMetadata, IndexReader, IndexWriter
-from .files import (GraphFile, graph_file_from_csr, hubs_by_in_degree, read_codebook_file, read_codes_file, read_graph_file,
-                    write_codebook_file, write_codes_file, write_graph_file)
+from .files import (GraphFile, graph_file_from_csr, graph_file_from_hnsw, hubs_by_in_degree, read_codebook_file, read_codes_file,
+                    read_graph_file, write_codebook_file, write_codes_file, write_graph_file)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -213,6 +213,25 @@ def graph_file_from_csr(csr, config, dimension, hub_ids=(), source_refs=None) ->
                      [(np.asarray(csr.node_offsets), np.asarray(csr.neighbors))], np.asarray(hub_ids), source_refs)
 
 
+def layer_from_export(degrees, neighbors) -> Tuple[np.ndarray, np.ndarray]:
+    """One layer as `HnswGraph.export_layer` hands it out — `degrees [n]` (-1 where the node does not reach the layer)
+    and `neighbors [n][M]` padded rows — as the file's (`row_ptr`, `edges`): an absent node gets an empty row."""
+    deg = np.maximum(np.asarray(degrees, np.int64), 0)
+    nb = np.asarray(neighbors)
+    row_ptr = np.zeros(deg.size + 1, np.int64)
+    np.cumsum(deg, out=row_ptr[1:])
+    keep = np.arange(nb.shape[1] if nb.ndim == 2 else 0)[None, :] < deg[:, None]
+    return row_ptr, (nb[keep] if nb.size else np.zeros(0, np.uint64))
+
+
+def graph_file_from_hnsw(graph, hub_ids=(), source_refs=None) -> GraphFile:
+    """Every layer of an `HnswGraph` handle (hnsw.rs:151-164: per-node connection lists per layer) as a `GraphFile`."""
+    cfg = graph.config
+    layers = [layer_from_export(*graph.export_layer(layer)) for layer in range(int(graph.max_level) + 1)]
+    return GraphFile(len(graph), graph.entry_point, int(getattr(cfg.metric, "value", cfg.metric)), int(graph.dimension() or 0),
+                     int(cfg.m), int(cfg.ef_construction), layers, np.asarray(hub_ids), source_refs)
+
+
 def hubs_by_in_degree(row_ptr, edges, fraction: float) -> np.ndarray:
     """The `ceil(fraction · n)` nodes of highest in-degree, ties to the lower id, ascending by id — the set the
     hub-embedding cache keeps resident (docs/leann-specification.md:661-690; `isl_index_set_hub_cache`)."""

@@ -10,7 +10,8 @@ import pytest
 from conftest import oracle_graph, uniform
 from islands_b200 import CsrGraph, LeannConfig
 from islands_b200.core import SerializationError
-from islands_b200.files import (SOURCE_REF_DTYPE, GraphFile, graph_file_from_csr, hubs_by_in_degree, read_codebook_file,
+from islands_b200.files import (SOURCE_REF_DTYPE, GraphFile, graph_file_from_csr, graph_file_from_hnsw, hubs_by_in_degree,
+                                layer_from_export, read_codebook_file,
                                 read_codes_file, read_graph_file, write_codebook_file, write_codes_file, write_graph_file)
 from islands_b200.storage import DeserializationError
 
@@ -134,6 +135,38 @@ def test_graph_file_from_csr_graph(tmp_path):
     off, nb = r.to_csr()
     assert np.array_equal(off, csr.node_offsets) and np.array_equal(nb, csr.neighbors)
     assert r.hub_ids.tolist() == [0, 1]  # in-degrees 2, 2, 1: ceil(0.34 * 3) = 2 hubs, ties to the smaller id
+
+
+def test_hnsw_layers_from_export(tmp_path):
+    """`HnswGraph.export_layer` shape (degrees with -1 for absent nodes, padded neighbour rows) -> file layers, driven
+    here by a stand-in object with the handle's interface (the real handle needs a device)."""
+    pad = 0xFFFFFFFFFFFFFFFF
+    deg0, nb0 = np.array([2, 1, 2, 1]), np.array([[1, 2, pad], [0, pad, pad], [0, 3, pad], [2, pad, pad]], np.uint64)
+    deg1, nb1 = np.array([1, -1, 1, -1]), np.array([[2, pad], [pad, pad], [0, pad], [pad, pad]], np.uint64)
+    rp, ed = layer_from_export(deg1, nb1)
+    assert rp.tolist() == [0, 1, 1, 2, 2] and ed.tolist() == [2, 0]
+    assert layer_from_export(np.zeros(0, np.int64), np.zeros((0, 4), np.uint64))[0].tolist() == [0]
+
+    class Handle:  # the part of islands_b200.HnswGraph the converter uses
+        config = type("Cfg", (), dict(m=2, m0=3, ef_construction=16, metric=1))()
+        entry_point, max_level = 2, 1
+
+        def __len__(self):
+            return 4
+
+        def dimension(self):
+            return 8
+
+        def export_layer(self, layer):
+            return (deg0, nb0) if layer == 0 else (deg1, nb1)
+
+    path = tmp_path / "h.hnsw"
+    write_graph_file(path, graph_file_from_hnsw(Handle(), hub_ids=[0]))
+    r = read_graph_file(path)
+    assert (r.num_nodes, r.num_layers, r.entry_point, r.metric, r.dimension, r.m, r.ef_construction) == (4, 2, 2, 1, 8, 2, 16)
+    assert r.layers[0][0].tolist() == [0, 2, 3, 5, 6] and r.layers[0][1].tolist() == [1, 2, 0, 0, 3, 2]
+    assert r.layers[1][0].tolist() == [0, 1, 1, 2, 2] and r.layers[1][1].tolist() == [2, 0]
+    assert r.levels().tolist() == [1, 0, 1, 0] and r.hub_ids.tolist() == [0]
 
 
 def test_hubs_by_in_degree():
