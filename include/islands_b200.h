@@ -318,6 +318,10 @@ isl_status isl_std_rng_draw(uint64_t seed, const uint8_t* kinds, uint64_t count,
 /* Test hook: the bfloat16 rounding the ADC traversal applies to its table entries (isl_index_search_adc_rerank below;
  * csrc/common.cuh bf16_round_bits), element by element.  Host code only. */
 isl_status isl_adc_table_round(const float* in, uint64_t count, float* out);
+/* Test hook: throws a C++ exception inside an entry point (0 = std::bad_alloc, 1 = std::length_error, 2 = a non-std
+ * type).  Every isl_status entry point catches at the boundary: the call returns ISL_INVALID_ARGUMENT with a message,
+ * nothing unwinds into the caller. */
+isl_status isl_test_raise(int32_t kind);
 #endif
 
 /* ---- two-level search (docs/leann-specification.md:223-269; no reference code) ------ */

@@ -242,6 +242,7 @@ SIGNATURES = {
 TEST_HOOKS = {
     "isl_std_rng_draw": (C.c_int, [C.c_uint64, C.POINTER(C.c_uint8), C.c_uint64, C.c_uint64, u64p]),
     "isl_adc_table_round": (C.c_int, [f32p, C.c_uint64, f32p]),
+    "isl_test_raise": (C.c_int, [C.c_int32]),
 }
 
 _lib = None

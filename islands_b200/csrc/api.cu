@@ -5,6 +5,8 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <new>
+#include <stdexcept>
 
 #include "api_common.h"
 
@@ -40,6 +42,22 @@ isl_status fail(isl_status st, const std::string& msg) {
   t_last_error = msg;
   capture_payload(st, msg);
   return st;
+}
+// Called from a catch (...) handler at the ABI (ISL_ABI_GUARD): turns the exception in flight into a status.
+isl_status exception_status() noexcept {
+  try {
+    try {
+      throw;
+    } catch (const std::bad_alloc&) {
+      return fail(ISL_INVALID_ARGUMENT, "host memory allocation failed (std::bad_alloc)");
+    } catch (const std::exception& e) {
+      return fail(ISL_INVALID_ARGUMENT, std::string("host exception: ") + e.what());
+    } catch (...) {
+      return fail(ISL_INVALID_ARGUMENT, "host exception of unknown type");
+    }
+  } catch (...) {  // not even the message could be stored
+    return ISL_INVALID_ARGUMENT;
+  }
 }
 isl_status cuda_fail(cudaError_t e, const char* what) {
   t_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
@@ -348,15 +366,15 @@ int isl_device_count(void) {
   }
   return c;
 }
-isl_status isl_set_caller_stream(void* cuda_stream) {
+isl_status isl_set_caller_stream(void* cuda_stream) try {
   t_caller_stream = reinterpret_cast<cudaStream_t>(cuda_stream);
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 uint64_t isl_kernel_launch_count(void) { return g_launch_count.load(); }
 void isl_kernel_launch_count_reset(void) { g_launch_count.store(0); }
 
 // ---- configs ------------------------------------------------------------------------------
-isl_status isl_leann_config_default(isl_leann_config* c) {
+isl_status isl_leann_config_default(isl_leann_config* c) try {
   if (!c) return fail(ISL_INVALID_ARGUMENT, "out is null");
   c->m = 30;  // leann.rs:386-403
   c->m0 = 60;
@@ -374,8 +392,8 @@ isl_status isl_leann_config_default(isl_leann_config* c) {
   c->is_recompute = 1;
   c->prune_seed = 0;
   return ISL_OK;
-}
-isl_status isl_leann_config_fast(isl_leann_config* c) {
+} ISL_ABI_GUARD
+isl_status isl_leann_config_fast(isl_leann_config* c) try {
   ISL_TRY(isl_leann_config_default(c));  // leann.rs:406-416
   c->m = 16;
   c->m0 = 32;
@@ -384,8 +402,8 @@ isl_status isl_leann_config_fast(isl_leann_config* c) {
   c->beam_width = 1;
   c->prune_ratio = 0.3f;
   return ISL_OK;
-}
-isl_status isl_leann_config_accurate(isl_leann_config* c) {
+} ISL_ABI_GUARD
+isl_status isl_leann_config_accurate(isl_leann_config* c) try {
   ISL_TRY(isl_leann_config_default(c));  // leann.rs:419-429
   c->m = 48;
   c->m0 = 96;
@@ -394,10 +412,10 @@ isl_status isl_leann_config_accurate(isl_leann_config* c) {
   c->beam_width = 1;
   c->prune_ratio = 0.0f;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 isl_status isl_leann_config_validate(const isl_leann_config* c) { return validate_leann(c); }
 
-isl_status isl_hnsw_config_default(isl_hnsw_config* c) {
+isl_status isl_hnsw_config_default(isl_hnsw_config* c) try {
   if (!c) return fail(ISL_INVALID_ARGUMENT, "out is null");
   c->m = 16;  // hnsw.rs:37-48
   c->m0 = 32;
@@ -406,15 +424,15 @@ isl_status isl_hnsw_config_default(isl_hnsw_config* c) {
   c->metric = ISL_METRIC_COSINE;
   c->max_layers = 16;
   return ISL_OK;
-}
-isl_status isl_hnsw_config_validate(const isl_hnsw_config* c) {
+} ISL_ABI_GUARD
+isl_status isl_hnsw_config_validate(const isl_hnsw_config* c) try {
   if (!c) return fail(ISL_INVALID_ARGUMENT, "config is null");
   if (c->m == 0) return fail(ISL_INVALID_CONFIG, "M must be > 0");  // hnsw.rs:72-85
   if (c->m0 < c->m) return fail(ISL_INVALID_CONFIG, "M0 must be >= M");
   if (c->ef_construction < c->m) return fail(ISL_INVALID_CONFIG, "ef_construction must be >= M");
   return ISL_OK;
-}
-isl_status isl_pq_config_default(isl_pq_config* c) {
+} ISL_ABI_GUARD
+isl_status isl_pq_config_default(isl_pq_config* c) try {
   if (!c) return fail(ISL_INVALID_ARGUMENT, "out is null");
   c->num_subquantizers = 8;  // pq.rs:24-33
   c->num_centroids = 256;
@@ -422,8 +440,8 @@ isl_status isl_pq_config_default(isl_pq_config* c) {
   c->seed = 0;  // None
   c->has_seed = 0;
   return ISL_OK;
-}
-isl_status isl_pq_config_validate(const isl_pq_config* c, uint64_t dimension) {
+} ISL_ABI_GUARD
+isl_status isl_pq_config_validate(const isl_pq_config* c, uint64_t dimension) try {
   if (!c) return fail(ISL_INVALID_ARGUMENT, "config is null");
   if (c->num_subquantizers == 0)  // pq.rs:37-55
     return fail(ISL_INVALID_CONFIG, "num_subquantizers must be > 0");
@@ -434,7 +452,7 @@ isl_status isl_pq_config_validate(const isl_pq_config* c, uint64_t dimension) {
   if (c->num_centroids == 0 || c->num_centroids > 65536)
     return fail(ISL_INVALID_CONFIG, "num_centroids must be in range [1, 65536]");
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 uint64_t isl_pq_config_bytes_per_vector(const isl_pq_config* c) {
   if (!c) return 0;
   return c->num_centroids <= 256 ? c->num_subquantizers : c->num_subquantizers * 2;  // pq.rs:58-64
@@ -466,30 +484,30 @@ static isl_status distance_host(int32_t metric, const float* q, const float* row
 }
 
 isl_status isl_distance_calculate(int32_t metric, const float* a, uint64_t len_a, const float* b,
-                                  uint64_t len_b, float* out) {
+                                  uint64_t len_b, float* out) try {
   if (len_a != len_b)  // distance.rs:39-44
     return fail(ISL_DIM_MISMATCH, "dimension mismatch: expected " + std::to_string(len_a) + ", got " +
                                       std::to_string(len_b));
   if (!out) return fail(ISL_INVALID_ARGUMENT, "out is null");
   return distance_host(metric, a, b, 1, (uint32_t)len_a, out, false);
-}
+} ISL_ABI_GUARD
 
 isl_status isl_distance_calculate_squared(int32_t metric, const float* a, uint64_t len_a,
-                                          const float* b, uint64_t len_b, float* out) {
+                                          const float* b, uint64_t len_b, float* out) try {
   if (len_a != len_b)  // distance.rs:55-60
     return fail(ISL_DIM_MISMATCH, "dimension mismatch: expected " + std::to_string(len_a) + ", got " +
                                       std::to_string(len_b));
   if (!out) return fail(ISL_INVALID_ARGUMENT, "out is null");
   return distance_host(metric, a, b, 1, (uint32_t)len_a, out, true);
-}
+} ISL_ABI_GUARD
 
 isl_status isl_distance_batch(int32_t metric, const float* query, const float* rows, uint64_t n_rows,
-                              uint32_t dim, float* out) {
+                              uint32_t dim, float* out) try {
   return distance_host(metric, query, rows, n_rows, dim, out, false);
-}
+} ISL_ABI_GUARD
 
 isl_status isl_distance_batch_dev(int32_t metric, const float* d_query, const float* d_rows,
-                                  uint64_t n_rows, uint32_t dim, float* d_out) {
+                                  uint64_t n_rows, uint32_t dim, float* d_out) try {
   if (metric < 0 || metric > 3) return fail(ISL_INVALID_CONFIG, "unknown metric");
   if (n_rows == 0) return ISL_OK;
   if (!d_query || !d_rows || !d_out) return fail(ISL_INVALID_ARGUMENT, "null pointer");
@@ -500,9 +518,9 @@ isl_status isl_distance_batch_dev(int32_t metric, const float* d_query, const fl
   ISL_TRY(launch_distance_batch(metric, false, d_query, d_rows, n_rows, dim, dim, d_out, sms, 0));
   ISL_CUDA_TRY(cudaStreamSynchronize(0));
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
-isl_status isl_normalize_rows(float* rows, uint64_t n_rows, uint32_t dim) {
+isl_status isl_normalize_rows(float* rows, uint64_t n_rows, uint32_t dim) try {
   if (n_rows == 0 || dim == 0) return ISL_OK;
   if (!rows) return fail(ISL_INVALID_ARGUMENT, "rows is null");
   int device, sms;
@@ -517,13 +535,13 @@ isl_status isl_normalize_rows(float* rows, uint64_t n_rows, uint32_t dim) {
   ISL_CUDA_TRY(cudaMemcpy2D(rows, (size_t)dim * 4, dr.p, (size_t)ld * 4, (size_t)dim * 4, n_rows,
                             cudaMemcpyDeviceToHost));
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 // ---- LEANN index -----------------------------------------------------------------------------
 isl_status isl_index_from_csr(const isl_leann_config* cfg, uint32_t dim, uint64_t n,
                               const uint64_t* node_offsets, const uint64_t* neighbors,
                               const uint64_t* levels, int64_t entry_point, const float* vectors,
-                              isl_index** out) {
+                              isl_index** out) try {
   if (!out) return fail(ISL_INVALID_ARGUMENT, "out is null");
   *out = nullptr;
   ISL_TRY(validate_leann(cfg));  // LeannIndex::new (leann.rs:504-511)
@@ -568,7 +586,7 @@ isl_status isl_index_from_csr(const isl_leann_config* cfg, uint32_t dim, uint64_
   }
   *out = idx.release();
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 void isl_index_free(isl_index* idx) {
   if (!idx) return;
@@ -586,7 +604,7 @@ uint64_t isl_index_storage_bytes(const isl_index* idx) {
 }
 
 isl_status isl_index_export_csr(const isl_index* idx, uint64_t* node_offsets, uint64_t* neighbors,
-                                uint64_t* levels, uint64_t* degree_counts) {
+                                uint64_t* levels, uint64_t* degree_counts) try {
   if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
   if (node_offsets) std::memcpy(node_offsets, idx->h_offsets.data(), idx->h_offsets.size() * 8);
   if (neighbors && !idx->h_nbrs.empty()) std::memcpy(neighbors, idx->h_nbrs.data(), idx->h_nbrs.size() * 8);
@@ -594,22 +612,22 @@ isl_status isl_index_export_csr(const isl_index* idx, uint64_t* node_offsets, ui
   if (degree_counts)
     for (uint64_t i = 0; i < idx->n; ++i) degree_counts[i] = idx->h_offsets[i + 1] - idx->h_offsets[i];
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 isl_status isl_index_get_neighbors(const isl_index* idx, uint64_t node_id, uint64_t* out, uint64_t cap,
-                                   uint64_t* out_count) {
+                                   uint64_t* out_count) try {
   if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
   if (node_id >= idx->n) return fail(ISL_NODE_NOT_FOUND, "node " + std::to_string(node_id) + " not found");
   const uint64_t s = idx->h_offsets[node_id], e = idx->h_offsets[node_id + 1];
   if (out_count) *out_count = e - s;
   for (uint64_t i = 0; i < e - s && i < cap; ++i) out[i] = idx->h_nbrs[s + i];
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 // CsrGraph::set_neighbors (leann.rs:256-293).  Same-length lists are overwritten in place, any other length
 // rebuilds offsets and neighbours (the reference's "expensive but rare" branch); the device copy of the graph
 // (CSR + padded adjacency) is refreshed either way.
-isl_status isl_index_set_neighbors(isl_index* idx, uint64_t node_id, const uint64_t* neighbors, uint64_t count) {
+isl_status isl_index_set_neighbors(isl_index* idx, uint64_t node_id, const uint64_t* neighbors, uint64_t count) try {
   if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
   if (node_id >= idx->n) return ISL_OK;  // leann.rs:258-260: silently ignored
   if (count && !neighbors) return fail(ISL_INVALID_ARGUMENT, "neighbors is null");
@@ -632,11 +650,11 @@ isl_status isl_index_set_neighbors(isl_index* idx, uint64_t node_id, const uint6
     for (uint64_t i = node_id + 1; i <= idx->n; ++i) idx->h_offsets[i] = (uint64_t)((int64_t)idx->h_offsets[i] + delta);
   }
   return index_finish_graph(idx);
-}
+} ISL_ABI_GUARD
 
 isl_status isl_index_search(const isl_index* idx, const float* queries, uint64_t nq,
                             uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* out_ids,
-                            float* out_dist, uint32_t* out_count, isl_search_stats* stats) {
+                            float* out_dist, uint32_t* out_count, isl_search_stats* stats) try {
   bool trivial;
   ISL_TRY(search_checks(idx, queries, nq, query_dim, k, &ef, &trivial));
   if (trivial) {
@@ -665,12 +683,12 @@ isl_status isl_index_search(const isl_index* idx, const float* queries, uint64_t
   if (stats)
     ISL_CUDA_TRY(cudaMemcpyAsync(stats, sc->out_stats.p, nq * sizeof(isl_search_stats), cudaMemcpyDeviceToHost, st));
   return search_finish(idx, sc.get(), 1);
-}
+} ISL_ABI_GUARD
 
 isl_status isl_index_search_dev(const isl_index* idx, const float* d_queries, uint64_t nq,
                                 uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
                                 float* d_out_dist, uint32_t* d_out_count,
-                                isl_search_stats* d_stats) {
+                                isl_search_stats* d_stats) try {
   bool trivial;
   ISL_TRY(search_checks(idx, d_queries, nq, query_dim, k, &ef, &trivial));
   if (!d_out_ids || !d_out_dist) return fail(ISL_INVALID_ARGUMENT, "output pointer is null");
@@ -686,28 +704,28 @@ isl_status isl_index_search_dev(const isl_index* idx, const float* d_queries, ui
   ISL_TRY(stage_device_queries(idx, sc.get(), d_queries, nq, query_dim, &q, &q_ld));
   ISL_TRY(search_device(idx, sc.get(), q, q_ld, nq, k, ef, d_out_ids, d_out_dist, d_out_count, d_stats, nullptr));
   return search_finish(idx, sc.get(), 1);
-}
+} ISL_ABI_GUARD
 
 isl_status isl_index_search_default(const isl_index* idx, const float* queries, uint64_t nq,
                                     uint32_t query_dim, uint32_t k, uint64_t* out_ids,
-                                    float* out_dist, uint32_t* out_count) {
+                                    float* out_dist, uint32_t* out_count) try {
   if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
   return isl_index_search(idx, queries, nq, query_dim, k, (uint32_t)idx->cfg.ef_search, out_ids,
                           out_dist, out_count, nullptr);
-}
+} ISL_ABI_GUARD
 
-isl_status isl_index_last_search_timing(const isl_index* idx, float* kernel_ms, uint64_t* kernel_launches) {
+isl_status isl_index_last_search_timing(const isl_index* idx, float* kernel_ms, uint64_t* kernel_launches) try {
   if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
   std::lock_guard<std::mutex> lock(idx->pool_mu);
   if (kernel_ms) *kernel_ms = idx->last_kernel_ms;
   if (kernel_launches) *kernel_launches = idx->last_launches;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 // ---- merge ----------------------------------------------------------------------------------
 isl_status isl_merge_topk_dev(const uint64_t* d_ids, const float* d_dist, uint32_t parts, uint64_t nq,
                               uint32_t k, uint64_t* d_out_ids, float* d_out_dist,
-                              uint32_t* d_out_count) {
+                              uint32_t* d_out_count) try {
   if (nq == 0 || k == 0) return ISL_OK;
   if (!d_ids || !d_dist || !d_out_ids || !d_out_dist) return fail(ISL_INVALID_ARGUMENT, "null pointer");
   if (parts == 0) return fail(ISL_INVALID_ARGUMENT, "parts must be > 0");
@@ -716,10 +734,10 @@ isl_status isl_merge_topk_dev(const uint64_t* d_ids, const float* d_dist, uint32
   ISL_TRY(launch_merge_topk(d_ids, d_dist, parts, nq, k, d_out_ids, d_out_dist, d_out_count, 0));
   ISL_CUDA_TRY(cudaStreamSynchronize(0));
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 isl_status isl_merge_topk(const uint64_t* ids, const float* dist, uint32_t parts, uint64_t nq,
-                          uint32_t k, uint64_t* out_ids, float* out_dist, uint32_t* out_count) {
+                          uint32_t k, uint64_t* out_ids, float* out_dist, uint32_t* out_count) try {
   if (nq == 0 || k == 0) return ISL_OK;
   if (!ids || !dist || !out_ids || !out_dist) return fail(ISL_INVALID_ARGUMENT, "null pointer");
   if (parts == 0) return fail(ISL_INVALID_ARGUMENT, "parts must be > 0");
@@ -741,6 +759,6 @@ isl_status isl_merge_topk(const uint64_t* ids, const float* dist, uint32_t parts
   ISL_CUDA_TRY(cudaMemcpy(out_dist, dod.p, nq * k * 4, cudaMemcpyDeviceToHost));
   if (out_count) ISL_CUDA_TRY(cudaMemcpy(out_count, dc.p, nq * 4, cudaMemcpyDeviceToHost));
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 }  // extern "C"

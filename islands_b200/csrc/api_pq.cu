@@ -51,7 +51,7 @@ static isl_status upload_padded(const float* src, uint64_t rows, uint32_t dim, u
 
 extern "C" {
 
-isl_status isl_pq_new(uint32_t dimension, const isl_pq_config* cfg, isl_pq** out) {
+isl_status isl_pq_new(uint32_t dimension, const isl_pq_config* cfg, isl_pq** out) try {
   if (!out) return fail(ISL_INVALID_ARGUMENT, "out is null");
   *out = nullptr;
   ISL_TRY(isl_pq_config_validate(cfg, dimension));  // pq.rs:133-134
@@ -65,7 +65,7 @@ isl_status isl_pq_new(uint32_t dimension, const isl_pq_config* cfg, isl_pq** out
   ISL_CUDA_TRY(cudaStreamCreateWithFlags(&pq->stream, cudaStreamNonBlocking));
   *out = pq.release();
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 void isl_pq_free(isl_pq* pq) {
   if (!pq) return;
@@ -74,12 +74,12 @@ void isl_pq_free(isl_pq* pq) {
   delete pq;
 }
 
-isl_status isl_pq_set_metric(isl_pq* pq, int32_t metric) {
+isl_status isl_pq_set_metric(isl_pq* pq, int32_t metric) try {
   if (!pq) return fail(ISL_INVALID_ARGUMENT, "pq is null");
   if (metric < 0 || metric > 3) return fail(ISL_INVALID_CONFIG, "unknown metric");
   pq->metric = metric;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 int32_t isl_pq_is_trained(const isl_pq* pq) { return pq && pq->trained ? 1 : 0; }
 uint64_t isl_pq_num_subquantizers(const isl_pq* pq) { return pq ? pq->cfg.num_subquantizers : 0; }
 float isl_pq_compression_ratio(const isl_pq* pq) {
@@ -87,7 +87,7 @@ float isl_pq_compression_ratio(const isl_pq* pq) {
   return (float)(pq->dim * 4ull) / (float)isl_pq_config_bytes_per_vector(&pq->cfg);
 }
 
-isl_status isl_pq_set_codebooks(isl_pq* pq, const float* codebooks, uint64_t num_centroids) {
+isl_status isl_pq_set_codebooks(isl_pq* pq, const float* codebooks, uint64_t num_centroids) try {
   if (!pq || !codebooks) return fail(ISL_INVALID_ARGUMENT, "null pointer");
   if (num_centroids == 0 || num_centroids > 65536)
     return fail(ISL_INVALID_CONFIG, "num_centroids must be in range [1, 65536]");
@@ -99,17 +99,17 @@ isl_status isl_pq_set_codebooks(isl_pq* pq, const float* codebooks, uint64_t num
   ISL_TRY(pq_upload_codebooks(pq));
   pq->trained = true;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
-isl_status isl_pq_get_codebooks(const isl_pq* pq, float* out, uint64_t* out_num_centroids) {
+isl_status isl_pq_get_codebooks(const isl_pq* pq, float* out, uint64_t* out_num_centroids) try {
   ISL_TRY(pq_require_trained(pq));
   if (out_num_centroids) *out_num_centroids = pq->ksub;
   if (out) std::memcpy(out, pq->h_codebooks.data(), pq->h_codebooks.size() * 4);
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 isl_status isl_pq_encode(const isl_pq* pq, const float* vectors, uint64_t n, uint32_t dim,
-                         uint16_t* out_codes) {
+                         uint16_t* out_codes) try {
   ISL_TRY(pq_require_trained(pq));
   ISL_TRY(dim_check(pq, dim));  // pq.rs:225-230
   if (n == 0) return ISL_OK;
@@ -126,10 +126,10 @@ isl_status isl_pq_encode(const isl_pq* pq, const float* vectors, uint64_t n, uin
   ISL_CUDA_TRY(cudaMemcpyAsync(out_codes, dc.p, n * m * 2, cudaMemcpyDeviceToHost, pq->stream));
   ISL_CUDA_TRY(cudaStreamSynchronize(pq->stream));
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 isl_status isl_pq_decode(const isl_pq* pq, const uint16_t* codes, uint64_t n, uint64_t codes_per_vector,
-                         float* out) {
+                         float* out) try {
   ISL_TRY(pq_require_trained(pq));
   if (codes_per_vector != pq->cfg.num_subquantizers)  // pq.rs:251-257
     return fail(ISL_PQ_ERROR, "Expected " + std::to_string(pq->cfg.num_subquantizers) + " codes, got " +
@@ -154,9 +154,9 @@ isl_status isl_pq_decode(const isl_pq* pq, const uint16_t* codes, uint64_t n, ui
   ISL_CUDA_TRY(cudaStreamSynchronize(pq->stream));
   if (h) return fail(ISL_PQ_ERROR, "Invalid code (>= number of centroids)");  // pq.rs:264-266
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
-isl_status isl_pq_build_tables(const isl_pq* pq, const float* query, uint32_t dim, float* out_tables) {
+isl_status isl_pq_build_tables(const isl_pq* pq, const float* query, uint32_t dim, float* out_tables) try {
   if (!pq) return fail(ISL_INVALID_ARGUMENT, "pq is null");
   ISL_TRY(dim_check(pq, dim));  // pq.rs:308-313
   if (!query || !out_tables) return fail(ISL_INVALID_ARGUMENT, "null pointer");
@@ -172,10 +172,10 @@ isl_status isl_pq_build_tables(const isl_pq* pq, const float* query, uint32_t di
   ISL_CUDA_TRY(cudaMemcpyAsync(out_tables, dt.p, dt.bytes(), cudaMemcpyDeviceToHost, pq->stream));
   ISL_CUDA_TRY(cudaStreamSynchronize(pq->stream));
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 isl_status isl_pq_table_distance(const isl_pq* pq, const float* tables, const uint16_t* codes,
-                                 uint64_t n, float* out) {
+                                 uint64_t n, float* out) try {
   ISL_TRY(pq_require_trained(pq));
   if (n == 0) return ISL_OK;
   if (!tables || !codes || !out) return fail(ISL_INVALID_ARGUMENT, "null pointer");
@@ -193,10 +193,10 @@ isl_status isl_pq_table_distance(const isl_pq* pq, const float* tables, const ui
   ISL_CUDA_TRY(cudaMemcpyAsync(out, dout.p, n * 4, cudaMemcpyDeviceToHost, pq->stream));
   ISL_CUDA_TRY(cudaStreamSynchronize(pq->stream));
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 isl_status isl_pq_asymmetric_distance(const isl_pq* pq, const float* query, uint32_t dim,
-                                      const uint16_t* codes, uint64_t n, float* out) {
+                                      const uint16_t* codes, uint64_t n, float* out) try {
   if (!pq) return fail(ISL_INVALID_ARGUMENT, "pq is null");
   ISL_TRY(dim_check(pq, dim));  // pq.rs:276-281
   if (n == 0) return ISL_OK;
@@ -222,10 +222,10 @@ isl_status isl_pq_asymmetric_distance(const isl_pq* pq, const float* query, uint
   ISL_CUDA_TRY(cudaStreamSynchronize(pq->stream));
   if (h) return fail(ISL_PQ_ERROR, "Invalid code (>= number of centroids)");  // pq.rs:290-292
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 // The rounding of the ADC traversal's table entries (common.cuh), exposed so that it can be checked on its own.
-isl_status isl_adc_table_round(const float* in, uint64_t count, float* out) {
+isl_status isl_adc_table_round(const float* in, uint64_t count, float* out) try {
   if ((!in || !out) && count) return fail(ISL_INVALID_ARGUMENT, "null pointer");
   for (uint64_t i = 0; i < count; ++i) {
     uint32_t u;
@@ -234,11 +234,11 @@ isl_status isl_adc_table_round(const float* in, uint64_t count, float* out) {
     memcpy(out + i, &u, 4);
   }
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 // The generator isl_pq_train draws from (std_rng.h = rand 0.8.5 StdRng::seed_from_u64), exposed so that the
 // restatement can be checked on its own: kind 0 = next_u32, 1 = next_u64, 2 = gen::<f32>() bits, 3 = choose(bound).
-isl_status isl_std_rng_draw(uint64_t seed, const uint8_t* kinds, uint64_t count, uint64_t bound, uint64_t* out) {
+isl_status isl_std_rng_draw(uint64_t seed, const uint8_t* kinds, uint64_t count, uint64_t bound, uint64_t* out) try {
   if ((!kinds || !out) && count) return fail(ISL_INVALID_ARGUMENT, "null pointer");
   isl::StdRng rng(seed);
   for (uint64_t i = 0; i < count; ++i) {
@@ -260,6 +260,18 @@ isl_status isl_std_rng_draw(uint64_t seed, const uint8_t* kinds, uint64_t count,
     }
   }
   return ISL_OK;
-}
+} ISL_ABI_GUARD
+
+// Test hook: throws inside a guarded entry point, to show that nothing unwinds through the ABI (ISL_ABI_GUARD).
+// kind 0 = std::bad_alloc, 1 = std::length_error (what a vector of an absurd size throws), 2 = a non-std exception.
+isl_status isl_test_raise(int32_t kind) try {
+  if (kind == 0) throw std::bad_alloc();
+  if (kind == 1) {
+    std::vector<float> v;
+    v.resize(v.max_size() + 1);
+  }
+  if (kind == 2) throw 42;
+  return ISL_OK;
+} ISL_ABI_GUARD
 
 }  // extern "C"

@@ -79,7 +79,7 @@ using namespace isl;
 extern "C" {
 
 isl_status isl_index_set_recompute(isl_index* idx, isl_encoder* enc, const int32_t* token_ids, const int32_t* lengths,
-                                   uint32_t seq_len) {
+                                   uint32_t seq_len) try {
   if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
   DeviceGuard g(idx->device);
   std::unique_lock<std::shared_mutex> lock(idx->mu);
@@ -116,13 +116,13 @@ isl_status isl_index_set_recompute(isl_index* idx, isl_encoder* enc, const int32
   idx->hub_sq.release();
   idx->hub_row.release();
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 // Hub-embedding cache (docs/leann-specification.md:661-690): the `count` nodes with the highest in-degree
 // (ties: smaller id) keep their embedding resident — they are the rows a traversal reaches most often —
 // and the recompute search skips them.  Computed with the attached encoder, so cached and recomputed
 // rows are the same bits.  count == 0 drops the cache.
-isl_status isl_index_set_hub_cache(isl_index* idx, uint64_t count) {
+isl_status isl_index_set_hub_cache(isl_index* idx, uint64_t count) try {
   if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
   DeviceGuard g(idx->device);
   std::unique_lock<std::shared_mutex> lock(idx->mu);
@@ -166,17 +166,17 @@ isl_status isl_index_set_hub_cache(isl_index* idx, uint64_t count) {
   ISL_CUDA_TRY(cudaStreamSynchronize(st));
   idx->hub_count = count;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
-isl_status isl_index_hub_cache_info(const isl_index* idx, uint64_t* cached_nodes, uint64_t* last_hits) {
+isl_status isl_index_hub_cache_info(const isl_index* idx, uint64_t* cached_nodes, uint64_t* last_hits) try {
   if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
   if (cached_nodes) *cached_nodes = idx->hub_count;
   if (last_hits) *last_hits = idx->last_hub_hits;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 // Frees the resident f32 embeddings: afterwards only the recompute search works on this handle.
-isl_status isl_index_drop_vectors(isl_index* idx) {
+isl_status isl_index_drop_vectors(isl_index* idx) try {
   if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
   DeviceGuard g(idx->device);
   std::unique_lock<std::shared_mutex> lock(idx->mu);
@@ -184,7 +184,7 @@ isl_status isl_index_drop_vectors(isl_index* idx) {
   idx->vectors.release();
   idx->sqnorms.release();
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 }  // extern "C"
 
@@ -361,7 +361,7 @@ extern "C" {
 
 isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* queries, uint64_t nq, uint32_t query_dim,
                                           uint32_t k, uint32_t ef, uint64_t* out_ids, float* out_dist,
-                                          uint32_t* out_count, isl_search_stats* stats) {
+                                          uint32_t* out_count, isl_search_stats* stats) try {
   bool trivial;
   ISL_TRY(search_checks(idx, queries, nq, query_dim, k, &ef, &trivial, /*need_vectors=*/false));
   if (trivial) {
@@ -373,16 +373,16 @@ isl_status isl_index_search_adc_recompute(const isl_index* idx, const float* que
   ScratchLease sc(idx);
   ISL_TRY(sc.status);
   return adc_recompute_on_scratch(idx, sc.get(), queries, nq, k, ef, out_ids, out_dist, out_count, stats, nullptr);
-}
+} ISL_ABI_GUARD
 
 isl_status isl_index_last_recompute(const isl_index* idx, uint64_t* unique_nodes, float* traverse_ms, float* encoder_ms,
-                                    float* rerank_ms) {
+                                    float* rerank_ms) try {
   if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
   if (unique_nodes) *unique_nodes = idx->last_recomputed;
   if (traverse_ms) *traverse_ms = idx->last_traverse_ms;
   if (encoder_ms) *encoder_ms = idx->last_encoder_ms;
   if (rerank_ms) *rerank_ms = idx->last_rerank_ms;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 }  // extern "C"

@@ -361,7 +361,7 @@ extern "C" {
 
 isl_status isl_index_search_recompute(const isl_index* idx, const float* queries, uint64_t nq, uint32_t query_dim, uint32_t k,
                                       uint32_t ef, uint64_t* out_ids, float* out_dist, uint32_t* out_count,
-                                      isl_search_stats* stats) {
+                                      isl_search_stats* stats) try {
   bool trivial;
   ISL_TRY(search_checks(idx, queries, nq, query_dim, k, &ef, &trivial, /*need_vectors=*/false));
   if (trivial) {
@@ -506,6 +506,6 @@ isl_status isl_index_search_recompute(const isl_index* idx, const float* queries
     idx->last_launches = rounds;
   }
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 }  // extern "C"

@@ -23,7 +23,7 @@ isl_status emit(const ByteWriter& w, uint8_t* out, uint64_t cap, uint64_t* out_l
 extern "C" {
 
 // LeannIndex { config: LeannConfig, graph: CsrGraph, dimension: Option<usize> } (leann.rs:493-500)
-isl_status isl_index_to_bytes(const isl_index* idx, uint8_t* out, uint64_t cap, uint64_t* out_len) {
+isl_status isl_index_to_bytes(const isl_index* idx, uint8_t* out, uint64_t cap, uint64_t* out_len) try {
   if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
   ByteWriter w;
   const isl_leann_config& c = idx->cfg;  // LeannConfig (leann.rs:322-371), declaration order
@@ -53,10 +53,10 @@ isl_status isl_index_to_bytes(const isl_index* idx, uint8_t* out, uint64_t cap, 
   w.vec_u64(deg.data(), deg.size());
   w.opt_u64(idx->n > 0, idx->dim);  // dimension is set by build() (leann.rs:569)
   return emit(w, out, cap, out_len);
-}
+} ISL_ABI_GUARD
 
 isl_status isl_index_from_bytes(const uint8_t* bytes, uint64_t len, const float* vectors, uint32_t dim,
-                                isl_index** out) {
+                                isl_index** out) try {
   if (!out) return fail(ISL_INVALID_ARGUMENT, "out is null");
   *out = nullptr;
   if (!bytes) return fail(ISL_INVALID_ARGUMENT, "bytes is null");
@@ -102,11 +102,11 @@ isl_status isl_index_from_bytes(const uint8_t* bytes, uint64_t len, const float*
   if (st != ISL_OK) return st;
   (*out)->max_level = max_level;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 // ProductQuantizer { config, codebooks: Vec<PQCodebook{centroids: Vec<Vec<f32>>, subvector_dim}>, dimension,
 // subvector_dim, metric, trained } (pq.rs:116-129)
-isl_status isl_pq_to_bytes(const isl_pq* pq, uint8_t* out, uint64_t cap, uint64_t* out_len) {
+isl_status isl_pq_to_bytes(const isl_pq* pq, uint8_t* out, uint64_t cap, uint64_t* out_len) try {
   if (!pq) return fail(ISL_INVALID_ARGUMENT, "quantizer is null");
   ByteWriter w;
   w.u64(pq->cfg.num_subquantizers);  // PQConfig (pq.rs:13-22)
@@ -126,9 +126,9 @@ isl_status isl_pq_to_bytes(const isl_pq* pq, uint8_t* out, uint64_t cap, uint64_
   w.u32((uint32_t)pq->metric);
   w.boolean(pq->trained);
   return emit(w, out, cap, out_len);
-}
+} ISL_ABI_GUARD
 
-isl_status isl_pq_from_bytes(const uint8_t* bytes, uint64_t len, isl_pq** out) {
+isl_status isl_pq_from_bytes(const uint8_t* bytes, uint64_t len, isl_pq** out) try {
   if (!out) return fail(ISL_INVALID_ARGUMENT, "out is null");
   *out = nullptr;
   if (!bytes) return fail(ISL_INVALID_ARGUMENT, "bytes is null");
@@ -173,28 +173,28 @@ isl_status isl_pq_from_bytes(const uint8_t* bytes, uint64_t len, isl_pq** out) {
   }
   *out = guard.release();
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
-isl_status isl_index_get_config(const isl_index* idx, isl_leann_config* out) {
+isl_status isl_index_get_config(const isl_index* idx, isl_leann_config* out) try {
   if (!idx || !out) return fail(ISL_INVALID_ARGUMENT, "null pointer");
   *out = idx->cfg;
   return ISL_OK;
-}
-isl_status isl_pq_get_config(const isl_pq* pq, isl_pq_config* out) {
+} ISL_ABI_GUARD
+isl_status isl_pq_get_config(const isl_pq* pq, isl_pq_config* out) try {
   if (!pq || !out) return fail(ISL_INVALID_ARGUMENT, "null pointer");
   *out = pq->cfg;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 uint32_t isl_pq_dimension(const isl_pq* pq) { return pq ? pq->dim : 0; }
 
 // InMemoryEmbeddingProvider::compute_embedding (leann.rs:141-150) for the resident embeddings.
-isl_status isl_index_get_vector(const isl_index* idx, uint64_t node_id, float* out) {
+isl_status isl_index_get_vector(const isl_index* idx, uint64_t node_id, float* out) try {
   if (!idx || !out) return fail(ISL_INVALID_ARGUMENT, "null pointer");
   if (node_id >= idx->n) return fail(ISL_NODE_NOT_FOUND, "node " + std::to_string(node_id) + " not found");
   if (!idx->vectors.p) return fail(ISL_INVALID_ARGUMENT, "the stored vectors were dropped (recompute-only index)");
   DeviceGuard g(idx->device);
   ISL_CUDA_TRY(cudaMemcpy(out, idx->vectors.p + node_id * idx->ld, (size_t)idx->dim * 4, cudaMemcpyDeviceToHost));
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 }  // extern "C"

@@ -309,7 +309,7 @@ isl_status sharded_checks(const isl_index* idx, isl_shard* sh, const void* queri
 
 extern "C" {
 
-isl_status isl_shard_unique_id(void* out, uint64_t cap) {
+isl_status isl_shard_unique_id(void* out, uint64_t cap) try {
   if (!out || cap < sizeof(ncclUniqueId)) return fail(ISL_INVALID_ARGUMENT, "isl_shard_unique_id needs a 128-byte buffer");
   NcclApi* api = nccl_api();
   if (!api->error.empty()) return fail(ISL_CUDA_ERROR, api->error);
@@ -317,9 +317,9 @@ isl_status isl_shard_unique_id(void* out, uint64_t cap) {
   ISL_NCCL_TRY(api->GetUniqueId(&id));
   std::memcpy(out, &id, sizeof(id));
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
-isl_status isl_shard_init(int rank, int world, const void* nccl_uid, isl_shard** out) {
+isl_status isl_shard_init(int rank, int world, const void* nccl_uid, isl_shard** out) try {
   if (!out) return fail(ISL_INVALID_ARGUMENT, "out is null");
   *out = nullptr;
   if (world < 1 || rank < 0 || rank >= world) return fail(ISL_INVALID_ARGUMENT, "rank / world out of range");
@@ -338,7 +338,7 @@ isl_status isl_shard_init(int rank, int world, const void* nccl_uid, isl_shard**
   ISL_NCCL_TRY(api->CommInitRank(&sh->comm, world, id, rank));
   *out = sh.release();
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 void isl_shard_free(isl_shard* sh) {
   if (!sh) return;
@@ -351,7 +351,7 @@ int isl_shard_world(const isl_shard* sh) { return sh ? sh->world : 0; }
 // Maps every rank's gather buffer and flag array into every other rank (CUDA IPC over NVLink peer access) so
 // that the exchange becomes direct stores + a flag handshake.  Collective: every rank calls it with the same
 // max_records (= the largest nq * k a later search will use).  All ranks must be on one node.
-isl_status isl_shard_enable_peer_exchange(isl_shard* sh, uint64_t max_records) {
+isl_status isl_shard_enable_peer_exchange(isl_shard* sh, uint64_t max_records) try {
   if (!sh) return fail(ISL_INVALID_ARGUMENT, "shard handle is null");
   if (sh->world > 16) return fail(ISL_INVALID_ARGUMENT, "peer exchange supports at most 16 ranks");
   if (max_records == 0) return fail(ISL_INVALID_ARGUMENT, "max_records must be > 0");
@@ -400,11 +400,11 @@ isl_status isl_shard_enable_peer_exchange(isl_shard* sh, uint64_t max_records) {
   sh->step = 0;
   sh->peer = true;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 isl_status isl_index_search_sharded(const isl_index* idx, isl_shard* sh, uint64_t id_base, const float* queries,
                                     uint64_t nq, uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* out_ids,
-                                    float* out_dist, uint32_t* out_count) {
+                                    float* out_dist, uint32_t* out_count) try {
   bool trivial = false;
   ISL_TRY(sharded_checks(idx, sh, queries, nq, query_dim, k, &ef, &trivial));
   if (!queries || !out_ids || !out_dist) return fail(ISL_INVALID_ARGUMENT, "null pointer");
@@ -428,11 +428,11 @@ isl_status isl_index_search_sharded(const isl_index* idx, isl_shard* sh, uint64_
   ISL_CUDA_TRY(cudaMemcpyAsync(out_dist, sc->out_dist.p, nq * k * 4, cudaMemcpyDeviceToHost, st));
   if (out_count) ISL_CUDA_TRY(cudaMemcpyAsync(out_count, sc->out_count.p, nq * 4, cudaMemcpyDeviceToHost, st));
   return sharded_finish(idx, sh, sc.get(), trivial);
-}
+} ISL_ABI_GUARD
 
 isl_status isl_index_search_sharded_dev(const isl_index* idx, isl_shard* sh, uint64_t id_base, const float* d_queries,
                                         uint64_t nq, uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* d_out_ids,
-                                        float* d_out_dist, uint32_t* d_out_count) {
+                                        float* d_out_dist, uint32_t* d_out_count) try {
   bool trivial = false;
   ISL_TRY(sharded_checks(idx, sh, d_queries, nq, query_dim, k, &ef, &trivial));
   if (!d_queries || !d_out_ids || !d_out_dist) return fail(ISL_INVALID_ARGUMENT, "null pointer");
@@ -448,13 +448,13 @@ isl_status isl_index_search_sharded_dev(const isl_index* idx, isl_shard* sh, uin
   ISL_TRY(sharded_core(idx, sh, sc.get(), id_base, ISL_SHARD_EXACT, q, q_ld, nullptr, nq, k, ef, trivial, d_out_ids, d_out_dist,
                        d_out_count));
   return sharded_finish(idx, sh, sc.get(), trivial);
-}
+} ISL_ABI_GUARD
 
 // The sharded form of isl_index_search_adc_rerank / isl_index_search_adc_recompute: every rank runs the ADC traversal
 // (+ encoder) + exact rerank on its shard, the rerank launch writes the exchange records, then exchange + merge.
 isl_status isl_index_search_sharded_adc(const isl_index* idx, isl_shard* sh, uint64_t id_base, int32_t mode, const float* queries,
                                         uint64_t nq, uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* out_ids,
-                                        float* out_dist, uint32_t* out_count) {
+                                        float* out_dist, uint32_t* out_count) try {
   if (mode != ISL_SHARD_ADC_RERANK && mode != ISL_SHARD_ADC_RECOMPUTE)
     return fail(ISL_INVALID_ARGUMENT, "mode must be ISL_SHARD_ADC_RERANK or ISL_SHARD_ADC_RECOMPUTE");
   if (!sh) return fail(ISL_INVALID_ARGUMENT, "shard handle is null");
@@ -483,20 +483,20 @@ isl_status isl_index_search_sharded_adc(const isl_index* idx, isl_shard* sh, uin
   ISL_CUDA_TRY(cudaMemcpyAsync(out_dist, m_dist.p, nq * k * 4, cudaMemcpyDeviceToHost, st));
   if (out_count) ISL_CUDA_TRY(cudaMemcpyAsync(out_count, m_cnt.p, nq * 4, cudaMemcpyDeviceToHost, st));
   return sharded_finish(idx, sh, sc.get(), trivial);
-}
+} ISL_ABI_GUARD
 
-isl_status isl_shard_last_timing(const isl_shard* sh, float* search_ms, float* exchange_ms, float* merge_ms) {
+isl_status isl_shard_last_timing(const isl_shard* sh, float* search_ms, float* exchange_ms, float* merge_ms) try {
   if (!sh) return fail(ISL_INVALID_ARGUMENT, "shard handle is null");
   if (search_ms) *search_ms = sh->search_ms;
   if (exchange_ms) *exchange_ms = sh->exchange_ms;
   if (merge_ms) *merge_ms = sh->merge_ms;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 // The two halves on their own (what a rank does before and after the exchange): G shards emulated on one GPU
 // write their records into slot g of a [G][nq][k] buffer and merge them — the parity test of the sharded path.
 isl_status isl_index_search_packed_dev(const isl_index* idx, uint64_t id_base, const float* d_queries, uint64_t nq,
-                                       uint32_t query_dim, uint32_t k, uint32_t ef, isl_shard_record* d_records) {
+                                       uint32_t query_dim, uint32_t k, uint32_t ef, isl_shard_record* d_records) try {
   bool trivial;
   ISL_TRY(search_checks(idx, d_queries, nq, query_dim, k, &ef, &trivial));
   if (!d_records && nq && k) return fail(ISL_INVALID_ARGUMENT, "d_records is null");
@@ -517,10 +517,10 @@ isl_status isl_index_search_packed_dev(const isl_index* idx, uint64_t id_base, c
   so.id_base = id_base;
   ISL_TRY(search_device(idx, sc.get(), q, q_ld, nq, k, ef, nullptr, nullptr, nullptr, nullptr, &so));
   return search_finish(idx, sc.get(), 1);
-}
+} ISL_ABI_GUARD
 
 isl_status isl_merge_packed_dev(const isl_shard_record* d_records, uint32_t parts, uint64_t nq, uint32_t k,
-                                uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_count) {
+                                uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_count) try {
   if (nq == 0 || k == 0) return ISL_OK;
   if (!d_records || !d_out_ids || !d_out_dist) return fail(ISL_INVALID_ARGUMENT, "null pointer");
   if (parts == 0) return fail(ISL_INVALID_ARGUMENT, "parts must be > 0");
@@ -530,6 +530,6 @@ isl_status isl_merge_packed_dev(const isl_shard_record* d_records, uint32_t part
   ISL_TRY(launch_merge_packed(reinterpret_cast<const uint4*>(d_records), parts, nq * k, nq, k, d_out_ids, d_out_dist, d_out_count, st));
   ISL_CUDA_TRY(cudaStreamSynchronize(st));
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 }  // extern "C"

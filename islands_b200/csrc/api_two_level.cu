@@ -11,7 +11,7 @@ using namespace isl;
 
 extern "C" {
 
-isl_status isl_index_attach_pq(isl_index* idx, const isl_pq* pq, const uint16_t* codes) {
+isl_status isl_index_attach_pq(isl_index* idx, const isl_pq* pq, const uint16_t* codes) try {
   if (!idx || !pq) return fail(ISL_INVALID_ARGUMENT, "null handle");
   if (!pq->trained) return fail(ISL_PQ_ERROR, "Quantizer not trained");
   if (pq->dim != idx->dim && idx->n)
@@ -37,7 +37,7 @@ isl_status isl_index_attach_pq(isl_index* idx, const isl_pq* pq, const uint16_t*
   }
   idx->pq = pq;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 }  // extern "C"
 
@@ -253,24 +253,24 @@ static isl_status pq_search_common(int mode, const isl_index* idx, const float* 
   return pq_search_on_scratch(mode, idx, sc.get(), queries, nq, k, ef, rerank_ratio, out_ids, out_dist, out_count, stats, nullptr);
 }
 
-isl_status isl_index_set_rerank_limit(isl_index* idx, uint32_t limit) {
+isl_status isl_index_set_rerank_limit(isl_index* idx, uint32_t limit) try {
   if (!idx) return fail(ISL_INVALID_ARGUMENT, "index is null");
   std::unique_lock<std::shared_mutex> lock(idx->mu);
   idx->rerank_limit = limit;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 isl_status isl_index_search_two_level(const isl_index* idx, const float* queries, uint64_t nq,
                                       uint32_t query_dim, uint32_t k, uint32_t ef, float rerank_ratio,
                                       uint64_t* out_ids, float* out_dist, uint32_t* out_count,
-                                      isl_search_stats* stats) {
+                                      isl_search_stats* stats) try {
   return pq_search_common(1, idx, queries, nq, query_dim, k, ef, rerank_ratio, out_ids, out_dist, out_count, stats);
-}
+} ISL_ABI_GUARD
 
 isl_status isl_index_search_adc_rerank(const isl_index* idx, const float* queries, uint64_t nq,
                                        uint32_t query_dim, uint32_t k, uint32_t ef, uint64_t* out_ids,
-                                       float* out_dist, uint32_t* out_count, isl_search_stats* stats) {
+                                       float* out_dist, uint32_t* out_count, isl_search_stats* stats) try {
   return pq_search_common(2, idx, queries, nq, query_dim, k, ef, 0.0f, out_ids, out_dist, out_count, stats);
-}
+} ISL_ABI_GUARD
 
 }  // extern "C"

@@ -558,23 +558,23 @@ static isl_status build_common(const isl_leann_config* cfg, uint32_t dim, uint64
   return ISL_OK;
 }
 
-isl_status isl_index_last_build_stats(const isl_index* idx, isl_build_stats* out) {
+isl_status isl_index_last_build_stats(const isl_index* idx, isl_build_stats* out) try {
   if (!idx || !out) return fail(ISL_INVALID_ARGUMENT, "null pointer");
   *out = idx->build_stats;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 isl_status isl_index_build(const isl_leann_config* cfg, uint32_t dim, uint64_t n, const float* vectors,
-                           const uint64_t* levels_or_null, uint64_t seed, uint32_t batch, isl_index** out) {
+                           const uint64_t* levels_or_null, uint64_t seed, uint32_t batch, isl_index** out) try {
   return build_common(cfg, dim, n, vectors, false, levels_or_null, seed, batch, out);
-}
+} ISL_ABI_GUARD
 
 isl_status isl_index_build_dev(const isl_leann_config* cfg, uint32_t dim, uint64_t n, const float* d_vectors,
-                               const uint64_t* levels_or_null, uint64_t seed, uint32_t batch, isl_index** out) {
+                               const uint64_t* levels_or_null, uint64_t seed, uint32_t batch, isl_index** out) try {
   // d_vectors may have been written on another stream: order after the legacy default stream.
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceSynchronize");
   return build_common(cfg, dim, n, d_vectors, true, levels_or_null, seed, batch, out);
-}
+} ISL_ABI_GUARD
 
 }  // extern "C"

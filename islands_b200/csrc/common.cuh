@@ -29,6 +29,13 @@ extern std::atomic<uint64_t> g_launch_count;
     if (_s != ISL_OK) return _s;        \
   } while (0)
 
+// Nothing may unwind through the C ABI (the callers are Rust, ctypes, C): every `isl_status` entry point is a
+// function-try-block closed by ISL_ABI_GUARD, so a std::bad_alloc / std::length_error out of a host container (an
+// absurd size argument, an exhausted host) comes back as a status with a message instead of aborting the process.
+isl_status exception_status() noexcept;
+#define ISL_ABI_GUARD \
+  catch (...) { return ::isl::exception_status(); }
+
 inline void count_launch(uint64_t n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
 
 // RAII device buffer (cudaMalloc / cudaFree).

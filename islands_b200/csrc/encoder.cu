@@ -1161,7 +1161,7 @@ using namespace isl;
 
 extern "C" {
 
-isl_status isl_encoder_config_default(isl_encoder_config* c) {
+isl_status isl_encoder_config_default(isl_encoder_config* c) try {
   if (!c) return fail(ISL_INVALID_ARGUMENT, "out is null");
   c->vocab_size = 30522;  // BERT-base, the 110M-parameter shape of BASELINE.json configs[4]
   c->hidden_size = 768;
@@ -1174,9 +1174,9 @@ isl_status isl_encoder_config_default(isl_encoder_config* c) {
   c->normalize = 1;  // EmbeddingConfig::normalize (candle_provider.rs:477)
   c->precision = ISL_ENCODER_BF16;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
-isl_status isl_encoder_new(const isl_encoder_config* cfg, isl_encoder** out) {
+isl_status isl_encoder_new(const isl_encoder_config* cfg, isl_encoder** out) try {
   if (!out) return fail(ISL_INVALID_ARGUMENT, "out is null");
   *out = nullptr;
   ISL_TRY(validate_cfg(cfg));
@@ -1195,7 +1195,7 @@ isl_status isl_encoder_new(const isl_encoder_config* cfg, isl_encoder** out) {
   e->n_gemm = l.g_total;
   *out = e.release();
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 void isl_encoder_free(isl_encoder* e) {
   if (!e) return;
@@ -1207,7 +1207,7 @@ uint32_t isl_encoder_dimension(const isl_encoder* e) { return e ? e->cfg.hidden_
 
 uint64_t isl_encoder_num_parameters(const isl_encoder* e) { return e ? make_layout(e->cfg).total : 0; }
 
-isl_status isl_encoder_init_random(isl_encoder* e, uint64_t seed, float stddev) {
+isl_status isl_encoder_init_random(isl_encoder* e, uint64_t seed, float stddev) try {
   if (!e) return fail(ISL_INVALID_ARGUMENT, "encoder is null");
   DeviceGuard g(e->device);
   std::lock_guard<std::mutex> lock(e->mu);
@@ -1248,9 +1248,9 @@ isl_status isl_encoder_init_random(isl_encoder* e, uint64_t seed, float stddev) 
   ISL_TRY(refresh_bf16(e));
   e->n_params = l.total;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
-isl_status isl_encoder_set_parameter(isl_encoder* e, const char* name, const float* data, uint64_t count) {
+isl_status isl_encoder_set_parameter(isl_encoder* e, const char* name, const float* data, uint64_t count) try {
   if (!e || !name || !data) return fail(ISL_INVALID_ARGUMENT, "null pointer");
   DeviceGuard g(e->device);
   std::lock_guard<std::mutex> lock(e->mu);
@@ -1264,9 +1264,9 @@ isl_status isl_encoder_set_parameter(isl_encoder* e, const char* name, const flo
   ISL_TRY(refresh_bf16(e));
   e->n_params = l.total;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
-isl_status isl_encoder_get_parameter(const isl_encoder* e, const char* name, float* out, uint64_t count) {
+isl_status isl_encoder_get_parameter(const isl_encoder* e, const char* name, float* out, uint64_t count) try {
   if (!e || !name || !out) return fail(ISL_INVALID_ARGUMENT, "null pointer");
   DeviceGuard g(e->device);
   const Layout l = make_layout(e->cfg);
@@ -1276,33 +1276,33 @@ isl_status isl_encoder_get_parameter(const isl_encoder* e, const char* name, flo
     return fail(ISL_DIM_MISMATCH, "dimension mismatch: expected " + std::to_string(cnt) + ", got " + std::to_string(count));
   ISL_CUDA_TRY(cudaMemcpy(out, e->params.p + off, cnt * 4, cudaMemcpyDeviceToHost));
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 isl_status isl_encoder_embed(isl_encoder* e, const int32_t* token_ids, const int32_t* lengths, uint64_t batch,
-                             uint32_t seq_len, float* out) {
+                             uint32_t seq_len, float* out) try {
   return embed_impl(e, token_ids, lengths, false, batch, seq_len, out);
-}
+} ISL_ABI_GUARD
 
 isl_status isl_encoder_embed_dev(isl_encoder* e, const int32_t* d_token_ids, const int32_t* d_lengths, uint64_t batch,
-                                 uint32_t seq_len, float* d_out) {
+                                 uint32_t seq_len, float* d_out) try {
   if (e) {
     DeviceGuard g(e->device);
     cudaError_t err = cudaDeviceSynchronize();  // inputs may have been produced on another stream
     if (err != cudaSuccess) return cuda_fail(err, "cudaDeviceSynchronize");
   }
   return embed_impl(e, d_token_ids, d_lengths, true, batch, seq_len, d_out);
-}
+} ISL_ABI_GUARD
 
-isl_status isl_encoder_last_timing(const isl_encoder* e, float* ms, double* flops) {
+isl_status isl_encoder_last_timing(const isl_encoder* e, float* ms, double* flops) try {
   if (!e) return fail(ISL_INVALID_ARGUMENT, "encoder is null");
   if (ms) *ms = e->last_ms;
   if (flops) *flops = e->last_flops;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 isl_status isl_gemm_bf16_dev(const void* d_a_bf16, const void* d_w_bf16, uint32_t m, uint32_t n, uint32_t k,
                              const float* d_bias, const void* d_residual_bf16, int32_t gelu, void* d_out_bf16,
-                             float* d_out_f32) {
+                             float* d_out_f32) try {
   if (!d_a_bf16 || !d_w_bf16 || (!d_out_bf16 && !d_out_f32)) return fail(ISL_INVALID_ARGUMENT, "null pointer");
   int device, sms;
   ISL_TRY(current_device(&device, &sms));
@@ -1311,6 +1311,6 @@ isl_status isl_gemm_bf16_dev(const void* d_a_bf16, const void* d_w_bf16, uint32_
                            gelu ? gemm::EPI_GELU : gemm::EPI_NONE, static_cast<__nv_bfloat16*>(d_out_bf16), d_out_f32, sms, 0));
   ISL_CUDA_TRY(cudaStreamSynchronize(0));
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 }  // extern "C"

@@ -782,7 +782,7 @@ using namespace isl;
 
 extern "C" {
 
-isl_status isl_hnsw_new(const isl_hnsw_config* cfg, isl_hnsw** out) {
+isl_status isl_hnsw_new(const isl_hnsw_config* cfg, isl_hnsw** out) try {
   if (!out) return fail(ISL_INVALID_ARGUMENT, "out is null");
   *out = nullptr;
   ISL_TRY(isl_hnsw_config_validate(cfg));  // HnswGraph::new (hnsw.rs:167-178)
@@ -796,7 +796,7 @@ isl_status isl_hnsw_new(const isl_hnsw_config* cfg, isl_hnsw** out) {
   ISL_TRY(ensure(h->counters, 4));
   *out = h.release();
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 void isl_hnsw_free(isl_hnsw* h) {
   if (!h) return;
@@ -810,33 +810,33 @@ int64_t isl_hnsw_entry_point(const isl_hnsw* h) { return h ? h->entry : ISL_NO_E
 uint64_t isl_hnsw_max_level(const isl_hnsw* h) { return h ? h->max_level : 0; }
 
 isl_status isl_hnsw_insert_batch(isl_hnsw* h, const float* vectors, uint64_t count, uint32_t dim,
-                                 const uint64_t* levels_or_null, uint64_t seed, uint32_t batch, uint64_t* out_first_id) {
+                                 const uint64_t* levels_or_null, uint64_t seed, uint32_t batch, uint64_t* out_first_id) try {
   if (!h) return fail(ISL_INVALID_ARGUMENT, "graph is null");
   DeviceGuard g(h->device);
   std::lock_guard<std::mutex> lock(h->mu);
   return hnsw_insert_impl(h, vectors, false, count, dim, levels_or_null, seed, batch, out_first_id);
-}
+} ISL_ABI_GUARD
 
 isl_status isl_hnsw_insert_batch_dev(isl_hnsw* h, const float* d_vectors, uint64_t count, uint32_t dim,
                                      const uint64_t* levels_or_null, uint64_t seed, uint32_t batch,
-                                     uint64_t* out_first_id) {
+                                     uint64_t* out_first_id) try {
   if (!h) return fail(ISL_INVALID_ARGUMENT, "graph is null");
   DeviceGuard g(h->device);
   cudaError_t e = cudaDeviceSynchronize();  // d_vectors may have been written on another stream
   if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceSynchronize");
   std::lock_guard<std::mutex> lock(h->mu);
   return hnsw_insert_impl(h, d_vectors, true, count, dim, levels_or_null, seed, batch, out_first_id);
-}
+} ISL_ABI_GUARD
 
-isl_status isl_hnsw_node_level(const isl_hnsw* h, uint64_t node_id, uint64_t* out_level) {
+isl_status isl_hnsw_node_level(const isl_hnsw* h, uint64_t node_id, uint64_t* out_level) try {
   if (!h) return fail(ISL_INVALID_ARGUMENT, "graph is null");
   if (node_id >= h->n) return fail(ISL_NODE_NOT_FOUND, "node " + std::to_string(node_id) + " not found");
   if (out_level) *out_level = h->h_levels[node_id];
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 isl_status isl_hnsw_get_neighbors(const isl_hnsw* h, uint64_t node_id, uint64_t layer, uint64_t* out, uint64_t cap,
-                                  uint64_t* out_count) {
+                                  uint64_t* out_count) try {
   if (!h) return fail(ISL_INVALID_ARGUMENT, "graph is null");
   if (node_id >= h->n) return fail(ISL_NODE_NOT_FOUND, "node " + std::to_string(node_id) + " not found");
   if (layer > h->h_levels[node_id])  // neighbors_at(layer) == None (hnsw.rs:108-110)
@@ -855,9 +855,9 @@ isl_status isl_hnsw_get_neighbors(const isl_hnsw* h, uint64_t node_id, uint64_t 
   if (out_count) *out_count = d;
   for (uint64_t i = 0; i < d && i < cap && out; ++i) out[i] = ids[i];
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
-isl_status isl_hnsw_export_layer(const isl_hnsw* h, uint64_t layer, int64_t* out_degrees, uint64_t* out_neighbors) {
+isl_status isl_hnsw_export_layer(const isl_hnsw* h, uint64_t layer, int64_t* out_degrees, uint64_t* out_neighbors) try {
   if (!h) return fail(ISL_INVALID_ARGUMENT, "graph is null");
   if (h->n == 0) return ISL_OK;
   DeviceGuard g(h->device);
@@ -879,10 +879,10 @@ isl_status isl_hnsw_export_layer(const isl_hnsw* h, uint64_t layer, int64_t* out
       for (uint32_t j = 0; j < cc; ++j) out_neighbors[i * cc + j] = j < d ? adj[row * cc + j] : ISL_INVALID_ID;
   }
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 isl_status isl_hnsw_search(const isl_hnsw* h, const float* queries, uint64_t nq, uint32_t query_dim, uint32_t k,
-                           uint32_t ef, uint64_t* out_ids, float* out_dist, uint32_t* out_count) {
+                           uint32_t ef, uint64_t* out_ids, float* out_dist, uint32_t* out_count) try {
   bool trivial;
   ISL_TRY(hnsw_search_checks(h, queries, nq, query_dim, k, &ef, &trivial));
   if (trivial) {
@@ -905,10 +905,10 @@ isl_status isl_hnsw_search(const isl_hnsw* h, const float* queries, uint64_t nq,
   if (out_count)
     ISL_CUDA_TRY(cudaMemcpyAsync(out_count, h->out_count.p, nq * 4, cudaMemcpyDeviceToHost, h->stream));
   return hnsw_search_finish(h);
-}
+} ISL_ABI_GUARD
 
 isl_status isl_hnsw_search_dev(const isl_hnsw* h, const float* d_queries, uint64_t nq, uint32_t query_dim, uint32_t k,
-                               uint32_t ef, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_count) {
+                               uint32_t ef, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_count) try {
   bool trivial;
   ISL_TRY(hnsw_search_checks(h, d_queries, nq, query_dim, k, &ef, &trivial));
   if (!d_out_ids || !d_out_dist) return fail(ISL_INVALID_ARGUMENT, "output pointer is null");
@@ -933,12 +933,12 @@ isl_status isl_hnsw_search_dev(const isl_hnsw* h, const float* d_queries, uint64
   }
   ISL_TRY(hnsw_search_device(h, q, q_ld, nq, k, ef, d_out_ids, d_out_dist, d_out_count));
   return hnsw_search_finish(h);
-}
+} ISL_ABI_GUARD
 
 // HnswGraph { config, nodes: HashMap<u64, HnswNode{id, vector, connections, level}>, entry_point,
 // max_level, dimension, next_id } (hnsw.rs:151-164, :90-99) in the bincode layout of hnsw.rs:507-514.
 // The map is written in ascending id order (any order is a valid encoding of a HashMap).
-isl_status isl_hnsw_to_bytes(const isl_hnsw* h, uint8_t* out, uint64_t cap, uint64_t* out_len) {
+isl_status isl_hnsw_to_bytes(const isl_hnsw* h, uint8_t* out, uint64_t cap, uint64_t* out_len) try {
   if (!h) return fail(ISL_INVALID_ARGUMENT, "graph is null");
   DeviceGuard g(h->device);
   std::lock_guard<std::mutex> lock(h->mu);
@@ -989,9 +989,9 @@ isl_status isl_hnsw_to_bytes(const isl_hnsw* h, uint8_t* out, uint64_t cap, uint
   if (cap < w.buf.size()) return fail(ISL_INVALID_ARGUMENT, "output buffer too small: need " + std::to_string(w.buf.size()) + " bytes");
   std::memcpy(out, w.buf.data(), w.buf.size());
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
-isl_status isl_hnsw_from_bytes(const uint8_t* bytes, uint64_t len, isl_hnsw** out) {
+isl_status isl_hnsw_from_bytes(const uint8_t* bytes, uint64_t len, isl_hnsw** out) try {
   if (!out) return fail(ISL_INVALID_ARGUMENT, "out is null");
   *out = nullptr;
   if (!bytes) return fail(ISL_INVALID_ARGUMENT, "bytes is null");
@@ -1103,27 +1103,27 @@ isl_status isl_hnsw_from_bytes(const uint8_t* bytes, uint64_t len, isl_hnsw** ou
   h->max_level = max_level;
   *out = guard.release();
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 // HnswNode::vector of get_node(node_id) (hnsw.rs:93-95, :201-203).
-isl_status isl_hnsw_get_vector(const isl_hnsw* h, uint64_t node_id, float* out) {
+isl_status isl_hnsw_get_vector(const isl_hnsw* h, uint64_t node_id, float* out) try {
   if (!h || !out) return fail(ISL_INVALID_ARGUMENT, "null pointer");
   if (node_id >= h->n) return fail(ISL_NODE_NOT_FOUND, "node " + std::to_string(node_id) + " not found");
   DeviceGuard g(h->device);
   ISL_CUDA_TRY(cudaMemcpy(out, h->vectors.p + node_id * h->ld, (size_t)h->dim * 4, cudaMemcpyDeviceToHost));
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
-isl_status isl_hnsw_get_config(const isl_hnsw* h, isl_hnsw_config* out) {
+isl_status isl_hnsw_get_config(const isl_hnsw* h, isl_hnsw_config* out) try {
   if (!h || !out) return fail(ISL_INVALID_ARGUMENT, "null pointer");
   *out = h->cfg;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
-isl_status isl_hnsw_last_search_timing(const isl_hnsw* h, float* kernel_ms) {
+isl_status isl_hnsw_last_search_timing(const isl_hnsw* h, float* kernel_ms) try {
   if (!h) return fail(ISL_INVALID_ARGUMENT, "graph is null");
   if (kernel_ms) *kernel_ms = h->last_kernel_ms;
   return ISL_OK;
-}
+} ISL_ABI_GUARD
 
 }  // extern "C"

@@ -236,3 +236,35 @@ def test_csr_graph_set_neighbors_host_mirror():
     assert list(g.node_offsets) == [0, 2, 2, 4] and list(g.get_neighbors(2)) == [1, 0]
     g.set_neighbors(99, [0])
     assert g.num_nodes == 3 and g.neighbors.size == 4
+
+
+def test_nothing_unwinds_through_the_abi():
+    """Errors never abort: every `isl_status` entry point is a function-try-block closed by ISL_ABI_GUARD,
+    so a C++ exception raised below it (std::bad_alloc / std::length_error from a host container, anything else) comes
+    back as a status with a message.  Shown with the test hook that throws inside an entry point, and kept true for
+    every entry point by a scan of the sources."""
+    from islands_b200 import _ffi
+
+    lib = _ffi.load()
+    assert lib.isl_test_raise(3) == 0
+    for kind, text in ((0, b"std::bad_alloc"), (1, b"host exception: "), (2, b"unknown type")):
+        assert lib.isl_test_raise(kind) == 9  # ISL_INVALID_ARGUMENT
+        assert text in lib.isl_last_error()
+    guarded = 0
+    src = os.path.join(ROOT, "islands_b200", "csrc")
+    for name in sorted(os.listdir(src)):
+        if not name.endswith(".cu"):
+            continue
+        lines = open(os.path.join(src, name)).read().split("\n")
+        for i, line in enumerate(lines):
+            if re.match(r"^isl_status isl_\w+\(", line):
+                j = i
+                while not lines[j].rstrip().endswith("{"):
+                    j += 1
+                assert lines[j].rstrip().endswith(") try {"), (name, i + 1)
+                k = j + 1
+                while not lines[k].startswith("}"):
+                    k += 1
+                assert lines[k].startswith("} ISL_ABI_GUARD"), (name, k + 1)
+                guarded += 1
+    assert guarded >= 87
