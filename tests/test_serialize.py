@@ -117,3 +117,17 @@ def test_hnsw_bytes_match_oracle_round_trip_and_keep_inserting(gpu_lib, orc):
     assert HnswGraph.from_bytes(HnswGraph(cfg).to_bytes()).is_empty()
     with pytest.raises(SerializationError):
         HnswGraph.from_bytes(data[:-3])
+
+
+def test_from_bytes_survives_hostile_input():
+    """CPU (the parsers are host code): truncated, extended and corrupted images of all three index types — length
+    fields set to 2^64 - 1 and the like — come back as a status, never as a crash or a runaway allocation
+    (scripts/fuzz_from_bytes.py: each batch in its own process under an address-space limit; 7000 cases clean)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_from_bytes.py"), "--cases", "500", "--seed", "11"],
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "500 cases, 0 failed batches" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
