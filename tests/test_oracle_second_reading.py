@@ -1,0 +1,400 @@
+"""A second, independent reading of the reference's algorithms, against the oracle.
+
+The C++ oracle (oracle/oracle.cpp) is a restatement of the Rust; the GPU kernels are checked against it bit for bit.
+What pins the oracle itself is the handful of known answers the reference's tests hold plus *faithfulness of the
+restatement*.  This file adds a second restatement written separately from the first — plain Python over `heapq`,
+`set`, lists and scalar `numpy.float32` arithmetic, following the Rust line by line — and requires the two to agree
+bit for bit:
+
+* the search loop `leann.rs:899-988` with Global / Local frontier pruning (`:991-1016`) and the four distance folds
+  (`distance.rs:71-122`): ids, distance bits and the reference's own work counter (`embeddings_computed`, :920, :950);
+* graph construction `leann.rs:560-658, 661-749` with the hub-preserving selection `:761-833` — the part the reference's
+  tests never exercise: whole CSR arrays, entry point, top level;
+* `HnswGraph` insert / search (`hnsw.rs:214-504`) with the `prune_connections` quirk: every list of every layer;
+* `ProductQuantizer` encode / decode / tables / table and asymmetric distance (`pq.rs:86-106, 221-348`).
+
+Small cases only (pure-Python loops); tie-heavy data where the reference's order is defined.  CPU.
+"""
+import heapq
+
+import numpy as np
+import pytest
+
+from conftest import oracle_graph, uniform
+from islands_b200 import LeannConfig
+
+F = np.float32
+
+
+def _fold(terms):
+    acc = F(0.0)
+    for t in terms:  # `sum()` / `+=` over an iterator: left to right, one rounding per add
+        acc = F(acc + t)
+    return acc
+
+
+def distance(metric, a, b):
+    """distance.rs:71-122, scalar f32, every multiply and add rounded on its own."""
+    if metric == 0:  # cosine_distance
+        dot = na = nb = F(0.0)
+        for x, y in zip(a, b):
+            dot = F(dot + F(x * y))
+            na = F(na + F(x * x))
+            nb = F(nb + F(y * y))
+        norm = F(np.sqrt(F(na * nb)))
+        return F(1.0) if norm == 0 else F(F(1.0) - F(dot / norm))
+    if metric == 1:  # euclidean_distance = sqrt(euclidean_distance_squared)
+        return F(np.sqrt(_fold(F(F(x - y) * F(x - y)) for x, y in zip(a, b))))
+    if metric == 2:  # dot_product_distance
+        return F(-_fold(F(x * y) for x, y in zip(a, b)))
+    return _fold(F(abs(F(x - y))) for x, y in zip(a, b))  # manhattan_distance
+
+
+def prune(cfg, candidates, results_len, ef):
+    """apply_pruning_strategy (leann.rs:991-1016), Global and Local; the arithmetic is f32 as in the Rust."""
+    ratio = F(cfg.prune_ratio)
+    if ratio == 0 or not candidates:
+        return list(candidates)
+    if cfg.pruning_strategy == 0:  # Global
+        fill = F(F(results_len) / F(ef))
+        adjusted = int(np.ceil(F(F(len(candidates)) * F(F(1.0) - F(fill * ratio)))))
+        return candidates[:max(adjusted, 1)]
+    keep = int(np.ceil(F(F(len(candidates)) * F(F(1.0) - ratio))))  # Local
+    return candidates[:max(keep, 1)]
+
+
+def search(cfg, vectors, offsets, nbrs, entry, query, k, ef):
+    """search_with_params + search_layer_recompute (leann.rs:868-988).  The final order of exact distance ties is
+    unspecified in the reference (a distance-only stable sort over heap order); like the oracle this uses (dist, id)."""
+    ef = max(ef, k)
+    metric = cfg.metric
+    visited = {entry}
+    d0 = distance(metric, query, vectors[entry])
+    candidates = [(d0, entry)]                 # min-heap of (dist, id): Reverse<(OrderedFloat, u64)>
+    results = [(-d0, -entry)]                  # max-heap of (dist, id) through negation
+    computed = 1
+    while candidates:
+        dist, node = heapq.heappop(candidates)
+        if len(results) >= ef and dist > -results[0][0]:
+            break
+        unvisited = []
+        for nb in nbrs[int(offsets[node]):int(offsets[node + 1])]:
+            nb = int(nb)
+            if nb not in visited:              # `filter(|&n| visited.insert(n))`: marked before pruning
+                visited.add(nb)
+                unvisited.append(nb)
+        if not unvisited:
+            continue
+        to_compute = prune(cfg, unvisited, len(results), ef)
+        computed += len(to_compute)
+        for nb in to_compute:
+            nd = distance(metric, query, vectors[nb])
+            if len(results) < ef or nd < -results[0][0]:
+                heapq.heappush(candidates, (nd, nb))
+                heapq.heappush(results, (-nd, -nb))
+                if len(results) > ef:
+                    heapq.heappop(results)
+    out = sorted((-d, -i) for d, i in results)
+    return [(i, d) for d, i in out[:k]], computed
+
+
+def _compare(orc, cfg, v, off, nbrs, entry, queries, k, ef):
+    ids, dist, cnt, st = orc.leann_search(cfg._s, v, off, nbrs, entry, queries, k, ef, stats=True)
+    for qi, q in enumerate(queries):
+        mine, computed = search(cfg, v, off, nbrs, entry, q, k, ef)
+        assert cnt[qi] == len(mine)
+        assert [int(i) for i in ids[qi, :cnt[qi]]] == [i for i, _ in mine], qi
+        assert [d.view(np.uint32) for d in dist[qi, :cnt[qi]]] == [F(d).view(np.uint32) for _, d in mine], qi
+        assert int(st["n_dist"][qi]) == computed, qi  # the reference's own counter: embeddings_computed
+
+
+@pytest.mark.parametrize("metric", [0, 1, 2, 3])
+def test_search_loop_second_reading(orc, metric):
+    cfg, v, _, off, nbrs, entry = oracle_graph(orc, 400, 12, seed=21, metric=metric, m=6, m0=12, ef_construction=32)
+    q = uniform(np.random.RandomState(22 + metric), 12, 12)
+    _compare(orc, cfg, v, off, nbrs, entry, q, 10, 24)
+    _compare(orc, cfg, v, off, nbrs, entry, q[:4], 5, 3)     # ef < k is raised to k (leann.rs:890)
+    _compare(orc, cfg, v, off, nbrs, entry, q[:3], 30, 500)  # ef > n: everything reachable is scored
+
+
+@pytest.mark.parametrize("strategy,ratio", [(0, 0.3), (0, 0.9), (1, 0.5), (1, 0.8)])
+def test_frontier_pruning_second_reading(orc, strategy, ratio):
+    cfg, v, _, off, nbrs, entry = oracle_graph(orc, 400, 12, seed=21, metric=0, m=6, m0=12, ef_construction=32)
+    pruned = LeannConfig(m=6, m0=12, ef_construction=32, prune_ratio=ratio, pruning_strategy=strategy)
+    q = uniform(np.random.RandomState(5), 10, 12)
+    _compare(orc, pruned, v, off, nbrs, entry, q, 10, 32)
+
+
+def test_exact_ties_second_reading(orc):
+    """A third of the vectors are exact copies: distances tie bit for bit, pops and evictions are decided by the id."""
+    cfg, v, _, off, nbrs, entry = oracle_graph(orc, 300, 8, seed=31, metric=0, dup=100, m=6, m0=12, ef_construction=32)
+    q = np.concatenate([v[:6], uniform(np.random.RandomState(32), 6, 8)])
+    _compare(orc, cfg, v, off, nbrs, entry, q, 16, 16)
+    _compare(orc, cfg, v, off, nbrs, entry, q, 10, 40)
+
+
+def test_distance_folds_second_reading(orc):
+    rng = np.random.RandomState(41)
+    for d in (1, 3, 16, 97):
+        a, b = uniform(rng, 1, d)[0], uniform(rng, 1, d)[0]
+        for metric in range(4):
+            assert distance(metric, a, b).view(np.uint32) == F(orc.distance(metric, a, b)).view(np.uint32), (metric, d)
+    z = np.zeros(5, F)
+    assert distance(0, z, uniform(rng, 1, 5)[0]) == 1.0 == orc.distance(0, z, z)  # zero vector: cosine distance 1.0
+
+
+# ---- construction: leann.rs:560-658 (insert loop, reverse edges, prune), :661-749 (insert search), :761-833 (hub-preserving
+# selection — the part the reference's own tests never exercise) ---------------------------------------------
+
+def insert_search(cfg, emb, adjacency, query, entry, ef):
+    """search_layer_with_adjacency (leann.rs:692-749): the search loop without frontier pruning, over the temporary lists."""
+    metric = cfg.metric
+    visited = {entry}
+    d0 = distance(metric, query, emb[entry])
+    candidates, results = [(d0, entry)], [(-d0, -entry)]
+    while candidates:
+        dist, node = heapq.heappop(candidates)
+        if len(results) >= ef and dist > -results[0][0]:
+            break
+        for nb in adjacency[node]:
+            if nb in visited:
+                continue
+            visited.add(nb)
+            nd = distance(metric, query, emb[nb])
+            if len(results) < ef or nd < -results[0][0]:
+                heapq.heappush(candidates, (nd, nb))
+                heapq.heappush(results, (-nd, -nb))
+                if len(results) > ef:
+                    heapq.heappop(results)
+    return [(i, d) for d, i in sorted((-d, -i) for d, i in results)]  # ascending; exact ties by id (the oracle's rule)
+
+
+def hub_preserving_selection(cfg, candidates, adjacency, max_conn):
+    """prune_with_degree_preservation_temp (leann.rs:761-833)."""
+    if len(candidates) <= max_conn:
+        return list(candidates)
+    degrees = sorted((len(adjacency[i]) for i, _ in candidates), reverse=True)
+    hub_count = int(np.ceil(F(F(len(degrees)) * F(cfg.hub_percentile))))
+    threshold = degrees[hub_count - 1] if 0 < hub_count < len(degrees) else None  # None: usize::MAX, no hubs
+    hubs, regular = [], []
+    for i, d in candidates:
+        deg = len(adjacency[i])
+        if threshold is not None and deg >= threshold:
+            hubs.append((i, d, deg))
+        else:
+            regular.append((i, d))
+    hubs.sort(key=lambda t: -t[2])      # stable: equal degrees keep the candidates' (distance) order
+    regular.sort(key=lambda t: t[1])    # stable, by distance
+    hub_slots = max(max_conn // 4, 1)
+    selected = [(i, d) for i, d, _ in hubs[:hub_slots]]
+    for i, d in regular:
+        if len(selected) >= max_conn:
+            break
+        if all(s != i for s, _ in selected):
+            selected.append((i, d))
+    for i, d, _ in hubs[hub_slots:]:
+        if len(selected) >= max_conn:
+            break
+        if all(s != i for s, _ in selected):
+            selected.append((i, d))
+    return selected
+
+
+def build(cfg, emb, levels):
+    """LeannIndex::build (leann.rs:560-631) with the levels as an input (the reference draws them from thread_rng)."""
+    n = len(emb)
+    adjacency, entry, max_level = [], None, 0
+    for node in range(n):
+        if not adjacency:
+            neighbors = []
+        else:  # find_neighbors_for_insert_temp (leann.rs:661-689)
+            cand = insert_search(cfg, emb, adjacency, emb[node], 0 if entry is None else entry, cfg.ef_construction)
+            cand = hub_preserving_selection(cfg, cand, adjacency, cfg.m0) if cfg.high_degree_pruning else cand[:cfg.m0]
+            neighbors = [i for i, _ in cand]
+        adjacency.append(list(neighbors))
+        for nb in neighbors:
+            if node not in adjacency[nb]:
+                adjacency[nb].append(node)
+                if len(adjacency[nb]) > cfg.m0:  # prune_neighbors_temp (leann.rs:634-658): stable sort by distance, keep m0
+                    scored = [(i, distance(cfg.metric, emb[nb], emb[i])) for i in adjacency[nb]]
+                    scored.sort(key=lambda t: t[1])
+                    adjacency[nb] = [i for i, _ in scored[:cfg.m0]]
+        if entry is None or levels[node] > max_level:
+            entry, max_level = node, int(levels[node])
+    offsets = np.concatenate([[0], np.cumsum([len(a) for a in adjacency])]).astype(np.uint64)
+    return offsets, np.array([i for a in adjacency for i in a], np.uint64), entry, max_level
+
+
+@pytest.mark.parametrize("metric,hub,dup", [(0, True, 0), (1, True, 0), (0, False, 0), (3, True, 0), (0, True, 60), (2, True, 0)])
+def test_construction_second_reading(orc, metric, hub, dup):
+    """Small m0 and efC so that every branch runs many times: candidate lists longer than m0 (hub selection, with the
+    degree-saturation degeneracy of SURVEY H6), reverse-edge overflow and pruning, entry-point moves, duplicate vectors."""
+    n, d = 220, 8
+    v = uniform(np.random.RandomState(50 + metric), n, d)
+    if dup:
+        v[n - dup:] = v[:dup]
+    cfg = LeannConfig(metric=metric, m=4, m0=8, ef_construction=24, high_degree_pruning=int(hub), hub_percentile=0.1)
+    levels = orc.draw_levels(9, n, cfg.ml, cfg.max_layers)
+    assert levels.max() > 0  # the entry point moves at least once
+    off, nbrs, entry, max_level = orc.leann_build(cfg._s, v, levels)
+    m_off, m_nbrs, m_entry, m_max = build(cfg, v, levels)
+    assert np.array_equal(off, m_off) and np.array_equal(nbrs, m_nbrs)
+    assert (int(entry), int(max_level)) == (m_entry, m_max)
+    deg = np.diff(off.astype(np.int64))
+    assert deg.max() == cfg.m0 and (deg == cfg.m0).sum() > n // 4  # saturated lists: the pruning paths really ran
+
+
+# ---- HnswGraph: hnsw.rs:214-329 (insert / insert_node), :332-402 (search_layer), :405-446 (prune_connections),
+# :458-504 (search).  `Candidate` orders by distance alone (hnsw.rs:136-141), so the reference leaves exact ties to the
+# heap's internals; these cases are tie-free (random data), where the reading is unambiguous. -----------------------------
+
+class Hnsw:
+    def __init__(self, cfg):
+        self.cfg, self.nodes, self.entry, self.max_level = cfg, {}, None, 0  # nodes: id -> (vector, [list per layer])
+
+    def _dist(self, q, i):
+        return distance(self.cfg.metric, q, self.nodes[i][0])
+
+    def _greedy(self, q, current, layers):
+        cur_d = self._dist(q, current)
+        for layer in layers:
+            while True:
+                changed = False
+                conns = self.nodes[current][1]
+                if layer < len(conns):
+                    for nb in list(conns[layer]):  # the list of the node the sweep STARTED from, even after `current` moves
+                        d = self._dist(q, nb)
+                        if d < cur_d:
+                            current, cur_d, changed = nb, d, True
+                if not changed:
+                    break
+        return current
+
+    def search_layer(self, q, entry, ef, layer):
+        visited = {entry}
+        d0 = self._dist(q, entry)
+        candidates, results = [(d0, entry)], [(-d0, -entry)]
+        while candidates:
+            d, node = heapq.heappop(candidates)
+            if d > -results[0][0] and len(results) >= ef:
+                break
+            conns = self.nodes[node][1]
+            if layer < len(conns):
+                for nb in conns[layer]:
+                    if nb in visited:
+                        continue
+                    visited.add(nb)
+                    nd = self._dist(q, nb)
+                    if len(results) < ef or nd < -results[0][0]:
+                        heapq.heappush(candidates, (nd, nb))
+                        heapq.heappush(results, (-nd, -nb))
+                        if len(results) > ef:
+                            heapq.heappop(results)
+        return [(i, d) for d, i in sorted((-d, -i) for d, i in results)]
+
+    def insert(self, vector, level):
+        node = len(self.nodes)
+        conns = [[] for _ in range(level + 1)]
+        if self.entry is None:
+            self.entry, self.max_level = node, level
+            self.nodes[node] = (vector, conns)
+            return node
+        current = self._greedy(vector, self.entry, range(self.max_level, level, -1))
+        for layer in range(level, -1, -1):
+            found = self.search_layer(vector, current, self.cfg.ef_construction, layer)
+            m = self.cfg.m0 if layer == 0 else self.cfg.m
+            selected = [i for i, _ in found[:m]]
+            conns[layer] = list(selected)
+            for nb in selected:
+                nb_conns = self.nodes[nb][1]
+                if layer < len(nb_conns):
+                    nb_conns[layer].append(node)
+                    if len(nb_conns[layer]) > m:  # prune_connections: ids without a stored node are skipped, and the node
+                        scored = [(i, distance(self.cfg.metric, self.nodes[nb][0], self.nodes[i][0]))  # being inserted is
+                                  for i in nb_conns[layer] if i in self.nodes]                          # not stored yet
+                        scored.sort(key=lambda t: t[1])
+                        nb_conns[layer] = [i for i, _ in scored[:m]]
+            if selected:
+                current = selected[0]
+        if level > self.max_level:
+            self.max_level, self.entry = level, node
+        self.nodes[node] = (vector, conns)
+        return node
+
+    def search(self, q, k, ef):
+        if not self.nodes:
+            return []
+        current = self._greedy(q, self.entry, range(self.max_level, 0, -1))
+        return self.search_layer(q, current, max(ef, k), 0)[:k]
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+def test_hnsw_second_reading(orc, metric):
+    from islands_b200 import HnswConfig
+
+    n, d = 260, 8
+    v = uniform(np.random.RandomState(70 + metric), n, d)
+    cfg = HnswConfig(m=4, m0=8, ef_construction=20, metric=metric, ml=0.9)  # ml 0.9: several layers at this size
+    levels = orc.draw_levels(13, n, cfg.ml, cfg.max_layers)
+    assert levels.max() >= 2
+    theirs, mine = orc.Hnsw(cfg._s, d), Hnsw(cfg)
+    for i in range(n):
+        assert theirs.insert(v[i], int(levels[i])) == mine.insert(v[i], int(levels[i])) == i
+    assert (theirs.entry_point(), theirs.max_level()) == (mine.entry, mine.max_level)
+    for i in range(n):
+        assert theirs.node_level(i) == len(mine.nodes[i][1]) - 1
+        for layer, conns in enumerate(mine.nodes[i][1]):
+            assert theirs.neighbors(i, layer).tolist() == conns, (i, layer)
+        assert theirs.neighbors(i, len(mine.nodes[i][1])) is None
+    # the prune path ran: many layer-0 lists reached m0 (from then on a later node never enters them — the quirk)
+    assert sum(1 for i in range(n) if len(mine.nodes[i][1][0]) == cfg.m0) > n // 8
+    q = uniform(np.random.RandomState(71), 20, d)
+    ids, dist, cnt = theirs.search(q, 5, 30)
+    for qi in range(20):
+        got = mine.search(q[qi], 5, 30)
+        assert cnt[qi] == len(got) and ids[qi, :cnt[qi]].tolist() == [i for i, _ in got]
+        assert [x.view(np.uint32) for x in dist[qi, :cnt[qi]]] == [F(x).view(np.uint32) for _, x in got]
+
+
+# ---- ProductQuantizer: pq.rs:86-106 (find_nearest), :221-271 (encode / decode), :275-348 (asymmetric distance, tables,
+# table_distance) -------------------------------------------------------------------------------------------------------
+
+def find_nearest(codebook, sub, metric):
+    best, best_d = 0, F(np.finfo(np.float32).max)  # f32::MAX
+    for i, centroid in enumerate(codebook):
+        d = distance(metric, sub, centroid)
+        if d < best_d:  # strict: the first of equal centroids wins
+            best, best_d = i, d
+    return best
+
+
+def squared_sub(a, b):
+    return _fold(F(F(x - y) * F(x - y)) for x, y in zip(a, b))  # `(a - b).powi(2)` summed left to right
+
+
+@pytest.mark.parametrize("metric", [1, 0, 3])
+def test_pq_second_reading(orc, metric):
+    rng = np.random.RandomState(80 + metric)
+    m, ksub, dsub = 4, 9, 3
+    cb = uniform(rng, m * ksub, dsub).reshape(m, ksub, dsub)
+    cb[1, 5] = cb[1, 2]  # duplicate centroid: the strict `<` keeps the lower index
+    v = uniform(rng, 30, m * dsub)
+    v[7, dsub:2 * dsub] = cb[1, 2]
+    codes = orc.pq_encode(metric, cb, v)
+    mine = np.array([[find_nearest(cb[s], row[s * dsub:(s + 1) * dsub], metric) for s in range(m)] for row in v])
+    assert np.array_equal(codes, mine) and codes[7, 1] == 2
+    assert np.array_equal(orc.pq_decode(cb, codes), np.stack([np.concatenate([cb[s, c] for s, c in enumerate(row)]) for row in mine]))
+    q = uniform(rng, 1, m * dsub)[0]
+    tables = orc.pq_build_tables(cb, q)
+    my_tables = np.array([[squared_sub(q[s * dsub:(s + 1) * dsub], c) for c in cb[s]] for s in range(m)], F)
+    assert np.array_equal(tables.view(np.uint32), my_tables.view(np.uint32))
+    for row in mine[:10]:
+        total = F(0.0)
+        for s, c in enumerate(row):  # asymmetric_distance: `total_dist += sub_dist`, then sqrt
+            total = F(total + squared_sub(q[s * dsub:(s + 1) * dsub], cb[s, c]))
+        adc = F(np.sqrt(total))
+        looked_up = F(np.sqrt(_fold(my_tables[s, c] for s, c in enumerate(row))))
+        one = row.astype(np.uint16)[None, :]
+        assert orc.pq_asymmetric_distance(cb, q, one)[0].view(np.uint32) == adc.view(np.uint32)
+        assert orc.pq_table_distance(tables, one)[0].view(np.uint32) == looked_up.view(np.uint32)
+        assert adc.view(np.uint32) == looked_up.view(np.uint32)  # same terms, same order: the two routes agree bit for bit
