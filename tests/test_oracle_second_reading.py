@@ -11,7 +11,9 @@ bit for bit:
 * graph construction `leann.rs:560-658, 661-749` with the hub-preserving selection `:761-833` — the part the reference's
   tests never exercise (SURVEY H6): whole CSR arrays, entry point, top level;
 * `HnswGraph` insert / search (`hnsw.rs:214-504`) with the `prune_connections` quirk: every list of every layer;
-* `ProductQuantizer` encode / decode / tables / table and asymmetric distance (`pq.rs:86-106, 221-348`).
+* `ProductQuantizer` encode / decode / tables / table and asymmetric distance (`pq.rs:86-106, 221-348`);
+* `train` + `kmeans` (`pq.rs:175-218, 362-463`): seeding, Lloyd iterations, empty-cluster re-seeding, on the reference's
+  random stream — trained codebooks bit for bit.
 
 Small cases only (pure-Python loops); tie-heavy data where the reference's order is defined.  CPU.
 """
@@ -398,3 +400,91 @@ def test_pq_second_reading(orc, metric):
         assert orc.pq_asymmetric_distance(cb, q, one)[0].view(np.uint32) == adc.view(np.uint32)
         assert orc.pq_table_distance(tables, one)[0].view(np.uint32) == looked_up.view(np.uint32)
         assert adc.view(np.uint32) == looked_up.view(np.uint32)  # same terms, same order: the two routes agree bit for bit
+
+
+# ---- ProductQuantizer::train + kmeans: pq.rs:175-218, 362-463.  The random stream is the reference's generator (rand 0.8.5
+# StdRng, restated in the oracle and pinned by tests/test_std_rng.py); what is read a second time here is everything that
+# CONSUMES it: the distance-weighted (not squared) seeding, the cumulative-sum pick, Lloyd's iterations in f32, the
+# re-seeding of empty clusters, one generator running through all subquantizers. ---------------------------------------
+
+class ScriptedRng:
+    """Draws from `orc_std_rng_draw` — a stateless scripted interface — by replaying the growing script."""
+
+    def __init__(self, orc, seed, bound):
+        import ctypes as C
+
+        self.C, self.seed, self.bound, self.kinds = C, seed, bound, []
+        self.fn = orc.lib().orc_std_rng_draw
+        self.fn.restype = None
+        self.fn.argtypes = [C.c_uint64, C.POINTER(C.c_uint8), C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
+
+    def _next(self, kind):
+        self.kinds.append(kind)
+        kinds = np.array(self.kinds, np.uint8)
+        out = np.zeros(len(kinds), np.uint64)
+        self.fn(self.seed, kinds.ctypes.data_as(self.C.POINTER(self.C.c_uint8)), len(kinds), self.bound,
+                out.ctypes.data_as(self.C.POINTER(self.C.c_uint64)))
+        return int(out[-1])
+
+    def gen_usize(self):
+        return self._next(1)
+
+    def gen_f32(self):
+        return np.array([self._next(2)], np.uint32).view(np.float32)[0]
+
+    def choose(self):
+        return self._next(3)
+
+
+def kmeans(vectors, k, iterations, metric, rng):
+    k = min(k, len(vectors))
+    centroids = [vectors[rng.gen_usize() % len(vectors)].copy()]
+    f32_max = F(np.finfo(np.float32).max)
+    while len(centroids) < k:
+        dists = []
+        for v in vectors:
+            best = f32_max
+            for c in centroids:
+                best = min(best, distance(metric, v, c))  # fold(f32::MAX, f32::min)
+            dists.append(best)
+        total = _fold(dists)
+        if total > 0:
+            dists = [F(x / total) for x in dists]
+        threshold, cumsum, selected = rng.gen_f32(), F(0.0), 0
+        for i, x in enumerate(dists):
+            cumsum = F(cumsum + x)
+            if cumsum >= threshold:
+                selected = i
+                break
+        centroids.append(vectors[selected].copy())
+    for _ in range(iterations):
+        assign = [find_nearest(centroids, v, metric) for v in vectors]  # same strict `<` scan from f32::MAX
+        sums = [np.zeros(len(vectors[0]), F) for _ in range(k)]
+        counts = [0] * k
+        for v, c in zip(vectors, assign):
+            counts[c] += 1
+            sums[c] = (sums[c] + v).astype(F)  # elementwise f32 adds in vector order
+        for c in range(k):
+            if counts[c] > 0:
+                sums[c] = (sums[c] / F(counts[c])).astype(F)
+            else:
+                sums[c] = vectors[rng.choose()].copy()
+        centroids = sums
+    return centroids
+
+
+@pytest.mark.parametrize("metric,seed", [(1, 42), (0, 7)])
+def test_kmeans_second_reading(orc, metric, seed):
+    rng = np.random.RandomState(90 + metric)
+    m, dsub, n, ksub, iterations = 3, 2, 14, 6, 4
+    v = uniform(rng, n, m * dsub)
+    if seed == 42:  # only three distinct rows for six centroids: seeding runs out of distance mass (total == 0, the pick
+        v = v[rng.randint(0, 3, size=n)]  # falls through to row 0), duplicate centroids stay empty and are re-seeded
+    theirs = orc.pq_train(metric, v, m, ksub, iterations, seed)
+    stream = ScriptedRng(orc, seed, n)
+    mine = np.stack([np.stack(kmeans([row[s * dsub:(s + 1) * dsub] for row in v], ksub, iterations, metric, stream))
+                     for s in range(m)])
+    assert theirs.shape == mine.shape == (m, ksub, dsub)
+    assert np.array_equal(theirs.view(np.uint32), mine.view(np.uint32))
+    assert (stream.kinds.count(3) > 0) == (seed == 42)  # empty clusters: the `choose` path, taken in the degenerate case
+    assert stream.kinds.count(1) == m and stream.kinds.count(2) == m * (ksub - 1)
