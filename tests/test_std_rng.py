@@ -75,3 +75,21 @@ def test_two_restatements_agree_and_follow_the_stream_rules():
     # the seed expansion is PCG32 (XSH-RR): different seeds give unrelated streams, same seed the same stream
     assert not np.array_equal(_draw(prod, 1, np.zeros(8, np.uint8), 1), _draw(prod, 2, np.zeros(8, np.uint8), 1))
     assert np.array_equal(words[:8], _draw(prod, 7, np.zeros(8, np.uint8), 1))
+
+
+def test_std_rng_construction_known_answer_of_the_rand_crate():
+    """rand 0.8's own test of its standard generator (`rand/src/rngs/std.rs`, `test_stdrng_construction`): a StdRng built
+    `from_seed([1,0,0,0, 23,0,0,0, 200,1,0,0, 210,30,0,0, 0, ...])` returns 10719222850664546238 from `next_u64`, and a
+    second StdRng built `from_rng` of the first (its seed is the next 32 bytes of the first one's stream) returns
+    14064965282130556830.  Reproduced from the oracle's block function: this pins StdRng = ChaCha with TWELVE rounds on a
+    non-zero key, the key layout (seed bytes as little-endian words), the zero counter / stream start and `next_u64` =
+    two consecutive words, low word first — on published values, not on a restatement."""
+    seed = bytes([1, 0, 0, 0, 23, 0, 0, 0, 200, 1, 0, 0, 210, 30, 0, 0] + [0] * 16)
+    first = bytes.fromhex(_block(struct.unpack("<8I", seed), 0, 0, 12))
+    words = struct.unpack("<16I", first)
+    assert words[0] | (words[1] << 32) == 10719222850664546238
+    second = struct.unpack("<16I", bytes.fromhex(_block(words[2:10], 0, 0, 12)))  # from_rng: fill_bytes(32) = words 2..9
+    assert second[0] | (second[1] << 32) == 14064965282130556830
+    for rounds in (8, 20):  # the value is specific to twelve rounds
+        w = struct.unpack("<16I", bytes.fromhex(_block(struct.unpack("<8I", seed), 0, 0, rounds)))
+        assert w[0] | (w[1] << 32) != 10719222850664546238
