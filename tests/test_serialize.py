@@ -14,6 +14,10 @@ def test_bincode_oracle_known_answers():
     from islands_b200 import LeannConfig
     from oracle import bincode_oracle as bo
 
+    # bincode 1.x's own README example: `World(vec![Entity{x: 0.0, y: 4.0}, Entity{x: 10.0, y: 20.5}])` encodes to
+    # "8 bytes for the length of the vector, 4 bytes per float" = 24 bytes: fixed-width little-endian, no varints
+    world = bo._u64(2) + b"".join(bo._f32(x) for x in (0.0, 4.0, 10.0, 20.5))
+    assert len(world) == 8 + 4 * 4 and world[:8] == bytes([2, 0, 0, 0, 0, 0, 0, 0])
     c = LeannConfig()
     b = bo.leann_config(c)
     assert len(b) == 8 * 3 + 8 + 8 + 4 + 8 + 8 + 4 + 4 + 1 + 4 + 1 + 1 == 75
