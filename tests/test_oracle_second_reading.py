@@ -13,7 +13,9 @@ bit for bit:
 * `HnswGraph` insert / search (`hnsw.rs:214-504`) with the `prune_connections` quirk: every list of every layer;
 * `ProductQuantizer` encode / decode / tables / table and asymmetric distance (`pq.rs:86-106, 221-348`);
 * `train` + `kmeans` (`pq.rs:175-218, 362-463`): seeding, Lloyd iterations, empty-cluster re-seeding, on the reference's
-  random stream — trained codebooks bit for bit.
+  random stream — trained codebooks bit for bit;
+* "PQ ADC traversal + exact rerank" as include/islands_b200.h defines it (not a reference algorithm): checks that the
+  oracle's twin implements the written definition, bfloat16 table rule included.
 
 Small cases only (pure-Python loops); tie-heavy data where the reference's order is defined.  CPU.
 """
@@ -488,3 +490,61 @@ def test_kmeans_second_reading(orc, metric, seed):
     assert np.array_equal(theirs.view(np.uint32), mine.view(np.uint32))
     assert (stream.kinds.count(3) > 0) == (seed == 42)  # empty clusters: the `choose` path, taken in the degenerate case
     assert stream.kinds.count(1) == m and stream.kinds.count(2) == m * (ksub - 1)
+
+
+# ---- "PQ ADC traversal + exact rerank" — not a reference algorithm (leann.rs:54-56 only names it): the mode is DEFINED in
+# include/islands_b200.h.  Read a second time from that definition: the search loop above with the table distance over
+# bfloat16-rounded table entries as the key, then exact distances for the ef survivors, sorted by (distance, id).  This
+# checks that the oracle's twin implements what the header says, nothing more (parity of the mode stays unpinned). ------
+
+def bf16_round(x):
+    bits = int(F(x).view(np.uint32))
+    if (bits & 0x7FFFFFFF) > 0x7F800000:
+        return np.array([(bits | 0x00400000) & 0xFFFF0000], np.uint32).view(F)[0]  # NaN -> quiet NaN
+    bits = (bits + 0x7FFF + ((bits >> 16) & 1)) & 0xFFFF0000  # round to nearest even on the bit pattern
+    return np.array([bits], np.uint32).view(F)[0]
+
+
+def adc_rerank(cfg, vectors, offsets, nbrs, entry, cb, codes, query, k, ef):
+    m, ksub, dsub = cb.shape
+    table = [[bf16_round(squared_sub(query[s * dsub:(s + 1) * dsub], c)) for c in cb[s]] for s in range(m)]
+
+    def adc(node):  # table_distance (pq.rs:341-348) over the rounded entries
+        return F(np.sqrt(_fold(table[s][int(codes[node, s])] for s in range(m))))
+
+    ef = max(ef, k)
+    visited = {entry}
+    d0 = adc(entry)
+    candidates, results = [(d0, entry)], [(-d0, -entry)]
+    while candidates:
+        d, node = heapq.heappop(candidates)
+        if len(results) >= ef and d > -results[0][0]:
+            break
+        for nb in nbrs[int(offsets[node]):int(offsets[node + 1])]:
+            nb = int(nb)
+            if nb in visited:
+                continue
+            visited.add(nb)
+            nd = adc(nb)
+            if len(results) < ef or nd < -results[0][0]:
+                heapq.heappush(candidates, (nd, nb))
+                heapq.heappush(results, (-nd, -nb))
+                if len(results) > ef:
+                    heapq.heappop(results)
+    exact = sorted((distance(cfg.metric, query, vectors[-i]), -i) for _, i in results)
+    return [(i, d) for d, i in exact[:k]], len(visited)
+
+
+def test_adc_traversal_rerank_second_reading(orc):
+    cfg, v, _, off, nbrs, entry = oracle_graph(orc, 400, 12, seed=21, metric=0, m=6, m0=12, ef_construction=32)
+    cb = orc.pq_train(1, v, 4, 16, 5, 3)
+    codes = orc.pq_encode(1, cb, v)
+    q = uniform(np.random.RandomState(95), 10, 12)
+    ids, dist, cnt, st = orc.leann_search_adc_rerank(cfg._s, v, off, nbrs, entry, cb, codes, q, 10, 40, stats=True)
+    for qi in range(len(q)):
+        mine, scored = adc_rerank(cfg, v, off, nbrs, entry, cb, codes, q[qi], 10, 40)
+        assert cnt[qi] == len(mine) and ids[qi, :cnt[qi]].tolist() == [i for i, _ in mine], qi
+        assert [x.view(np.uint32) for x in dist[qi, :cnt[qi]]] == [F(x).view(np.uint32) for _, x in mine], qi
+        assert int(st["n_adc"][qi]) == scored and int(st["n_rerank"][qi]) == min(40, scored)
+    vals = np.array([1.0, 1.00390625, 1.005859375, 3.3895314e38, -2.5e-41, 0.1], F)
+    assert np.array_equal(orc.adc_table_round(vals).view(np.uint32), np.array([bf16_round(x) for x in vals], F).view(np.uint32))
