@@ -67,7 +67,50 @@ def prune(cfg, candidates, results_len, ef):
     return candidates[:max(keep, 1)]
 
 
-def search(cfg, vectors, offsets, nbrs, entry, query, k, ef):
+MASK64 = (1 << 64) - 1
+
+
+def _mix(z):  # splitmix64's finaliser, as written in include/islands_b200.h
+    z ^= z >> 30
+    z = (z * 0xBF58476D1CE4E5B9) & MASK64
+    z ^= z >> 27
+    z = (z * 0x94D049BB133111EB) & MASK64
+    return z ^ (z >> 31)
+
+
+class SeededDraws:
+    """The counter stream include/islands_b200.h defines for PruningStrategy::Proportional (the reference draws from
+    thread_rng, leann.rs:1043): draw c of query q = 24 bits of mix(mix(seed + G * (q + 1)) + G * (c + 1))."""
+    G = 0x9E3779B97F4A7C15
+
+    def __init__(self, seed, query_index):
+        self.base, self.c = _mix((seed + self.G * (query_index + 1)) & MASK64), 0
+
+    def next_f32(self):
+        h = _mix((self.base + self.G * (self.c + 1)) & MASK64)
+        self.c += 1
+        return F(F(h >> 40) * F(2.0 ** -24))
+
+
+def prune_proportional(cfg, candidates, degree_of, draws):
+    """apply_pruning_strategy, Proportional arm (leann.rs:1017-1053)."""
+    if F(cfg.prune_ratio) == 0 or not candidates:
+        return list(candidates)
+    keep = max(int(np.ceil(F(F(len(candidates)) * F(F(1.0) - F(cfg.prune_ratio))))), 1)
+    total = sum(degree_of(i) for i in candidates)
+    if total == 0:
+        return candidates[:keep]
+    selected = []
+    for i in candidates:
+        prob = F(F(degree_of(i)) / F(total))
+        if draws.next_f32() < F(prob * F(keep)):
+            selected.append(i)
+            if len(selected) >= keep:
+                break
+    return selected or [candidates[0]]
+
+
+def search(cfg, vectors, offsets, nbrs, entry, query, k, ef, query_index=0):
     """search_with_params + search_layer_recompute (leann.rs:868-988).  The final order of exact distance ties is
     unspecified in the reference (a distance-only stable sort over heap order); like the oracle this uses (dist, id)."""
     ef = max(ef, k)
@@ -77,6 +120,8 @@ def search(cfg, vectors, offsets, nbrs, entry, query, k, ef):
     candidates = [(d0, entry)]                 # min-heap of (dist, id): Reverse<(OrderedFloat, u64)>
     results = [(-d0, -entry)]                  # max-heap of (dist, id) through negation
     computed = 1
+    draws = SeededDraws(int(cfg.prune_seed), query_index)
+    degree_of = lambda i: int(offsets[i + 1]) - int(offsets[i])  # CsrGraph::degree_counts
     while candidates:
         dist, node = heapq.heappop(candidates)
         if len(results) >= ef and dist > -results[0][0]:
@@ -89,7 +134,10 @@ def search(cfg, vectors, offsets, nbrs, entry, query, k, ef):
                 unvisited.append(nb)
         if not unvisited:
             continue
-        to_compute = prune(cfg, unvisited, len(results), ef)
+        if cfg.pruning_strategy == 2:
+            to_compute = prune_proportional(cfg, unvisited, degree_of, draws)
+        else:
+            to_compute = prune(cfg, unvisited, len(results), ef)
         computed += len(to_compute)
         for nb in to_compute:
             nd = distance(metric, query, vectors[nb])
@@ -105,7 +153,7 @@ def search(cfg, vectors, offsets, nbrs, entry, query, k, ef):
 def _compare(orc, cfg, v, off, nbrs, entry, queries, k, ef):
     ids, dist, cnt, st = orc.leann_search(cfg._s, v, off, nbrs, entry, queries, k, ef, stats=True)
     for qi, q in enumerate(queries):
-        mine, computed = search(cfg, v, off, nbrs, entry, q, k, ef)
+        mine, computed = search(cfg, v, off, nbrs, entry, q, k, ef, query_index=qi)
         assert cnt[qi] == len(mine)
         assert [int(i) for i in ids[qi, :cnt[qi]]] == [i for i, _ in mine], qi
         assert [d.view(np.uint32) for d in dist[qi, :cnt[qi]]] == [F(d).view(np.uint32) for _, d in mine], qi
@@ -127,6 +175,17 @@ def test_frontier_pruning_second_reading(orc, strategy, ratio):
     pruned = LeannConfig(m=6, m0=12, ef_construction=32, prune_ratio=ratio, pruning_strategy=strategy)
     q = uniform(np.random.RandomState(5), 10, 12)
     _compare(orc, pruned, v, off, nbrs, entry, q, 10, 32)
+
+
+@pytest.mark.parametrize("ratio,seed", [(0.3, 0), (0.6, 12345), (0.9, 2 ** 63 + 7)])
+def test_proportional_pruning_second_reading(orc, ratio, seed):
+    """The Proportional arm with the draws of the stream the header defines (query row and draw counter as keys)."""
+    cfg, v, _, off, nbrs, entry = oracle_graph(orc, 400, 12, seed=21, metric=0, m=6, m0=12, ef_construction=32)
+    pruned = LeannConfig(m=6, m0=12, ef_construction=32, prune_ratio=ratio, pruning_strategy=2, prune_seed=seed)
+    q = uniform(np.random.RandomState(6), 10, 12)
+    _compare(orc, pruned, v, off, nbrs, entry, q, 10, 32)
+    u = [SeededDraws(seed, 3).next_f32() for _ in range(1)] + [SeededDraws(seed, 4).next_f32()]
+    assert all(0 <= x < 1 for x in u) and u[0] != u[1]  # different query rows draw different streams
 
 
 def test_exact_ties_second_reading(orc):
