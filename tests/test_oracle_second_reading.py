@@ -14,6 +14,8 @@ bit for bit:
 * `ProductQuantizer` encode / decode / tables / table and asymmetric distance (`pq.rs:86-106, 221-348`);
 * `train` + `kmeans` (`pq.rs:175-218, 362-463`): seeding, Lloyd iterations, empty-cluster re-seeding, on the reference's
   random stream — trained codebooks bit for bit;
+* the batched construction ("round model") as DESIGN.md 3.3 words it — this repository's own widening of the sequential
+  loop — for several round sizes, `batch = 1` coinciding with the sequential reading;
 * "PQ ADC traversal + exact rerank" as include/islands_b200.h defines it (not a reference algorithm): checks that the
   oracle's twin implements the written definition, bfloat16 table rule included.
 
@@ -607,3 +609,56 @@ def test_adc_traversal_rerank_second_reading(orc):
         assert int(st["n_adc"][qi]) == scored and int(st["n_rerank"][qi]) == min(40, scored)
     vals = np.array([1.0, 1.00390625, 1.005859375, 3.3895314e38, -2.5e-41, 0.1], F)
     assert np.array_equal(orc.adc_table_round(vals).view(np.uint32), np.array([bf16_round(x) for x in vals], F).view(np.uint32))
+
+
+# ---- the batched construction ("round model") — this repository's own definition of how the reference's
+# sequential loop is widened for the GPU; `batch = 1` is the reference loop itself.  Read a second time from the text:
+# rounds of min(batch, max(1, inserted / 2)) nodes; every node of a round searches the graph as it stood before the
+# round (entry point included) and selects its neighbours; the reverse edges of the round are applied per target in
+# ascending source id with the reference's rule (append, prune to the m0 closest on overflow). ---------------------------
+
+def build_rounds(cfg, emb, levels, batch):
+    n = len(emb)
+    adjacency, entry, max_level, inserted = [], None, 0, 0
+    while inserted < n:
+        size = min(batch, max(1, inserted // 2), n - inserted)
+        round_nodes = range(inserted, inserted + size)
+        frozen = [list(a) for a in adjacency]  # the graph before the round
+        chosen = {}
+        for node in round_nodes:
+            if not frozen:
+                chosen[node] = []
+                continue
+            cand = insert_search(cfg, emb, frozen, emb[node], 0 if entry is None else entry, cfg.ef_construction)
+            cand = hub_preserving_selection(cfg, cand, frozen, cfg.m0) if cfg.high_degree_pruning else cand[:cfg.m0]
+            chosen[node] = [i for i, _ in cand]
+        for node in round_nodes:
+            adjacency.append(list(chosen[node]))
+        incoming = sorted((target, node) for node in round_nodes for target in chosen[node])
+        for target, node in incoming:  # per target, ascending source id
+            if node not in adjacency[target]:
+                adjacency[target].append(node)
+                if len(adjacency[target]) > cfg.m0:
+                    scored = [(i, distance(cfg.metric, emb[target], emb[i])) for i in adjacency[target]]
+                    scored.sort(key=lambda t: t[1])
+                    adjacency[target] = [i for i, _ in scored[:cfg.m0]]
+        for node in round_nodes:
+            if entry is None or levels[node] > max_level:
+                entry, max_level = node, int(levels[node])
+        inserted += size
+    offsets = np.concatenate([[0], np.cumsum([len(a) for a in adjacency])]).astype(np.uint64)
+    return offsets, np.array([i for a in adjacency for i in a], np.uint64), entry, max_level
+
+
+@pytest.mark.parametrize("batch,hub", [(1, True), (8, True), (64, True), (16, False)])
+def test_round_model_second_reading(orc, batch, hub):
+    n, d = 200, 8
+    v = uniform(np.random.RandomState(61), n, d)
+    cfg = LeannConfig(metric=0, m=4, m0=8, ef_construction=24, high_degree_pruning=int(hub), hub_percentile=0.1)
+    levels = orc.draw_levels(9, n, cfg.ml, cfg.max_layers)
+    off, nbrs, entry, max_level = orc.leann_build(cfg._s, v, levels, batch=batch)
+    m_off, m_nbrs, m_entry, m_max = build_rounds(cfg, v, levels, batch)
+    assert np.array_equal(off, m_off) and np.array_equal(nbrs, m_nbrs) and (int(entry), int(max_level)) == (m_entry, m_max)
+    if batch == 1:  # one node per round IS the sequential loop
+        s_off, s_nbrs, s_entry, s_max = build(cfg, v, levels)
+        assert np.array_equal(off, s_off) and np.array_equal(nbrs, s_nbrs) and (s_entry, s_max) == (m_entry, m_max)
