@@ -16,6 +16,7 @@ bit for bit:
   random stream — trained codebooks bit for bit;
 * the batched construction ("round model") as DESIGN.md 3.3 words it — this repository's own widening of the sequential
   loop — for several round sizes, `batch = 1` coinciding with the sequential reading;
+* the two-level search as DESIGN.md 3.4 pins down the specification's Algorithm 2 (no reference code);
 * "PQ ADC traversal + exact rerank" as include/islands_b200.h defines it (not a reference algorithm): checks that the
   oracle's twin implements the written definition, bfloat16 table rule included.
 
@@ -662,3 +663,60 @@ def test_round_model_second_reading(orc, batch, hub):
     if batch == 1:  # one node per round IS the sequential loop
         s_off, s_nbrs, s_entry, s_max = build(cfg, v, levels)
         assert np.array_equal(off, s_off) and np.array_equal(nbrs, s_nbrs) and (s_entry, s_max) == (m_entry, m_max)
+
+
+# ---- two-level search (docs/leann-specification.md:223-269 as DESIGN.md 3.4 pins it down; no reference code): the
+# oracle's twin against a reading of that paragraph. ----------------------------------------------------------------------
+
+def two_level(cfg, vectors, offsets, nbrs, entry, cb, codes, query, k, ef, a):
+    m, ksub, dsub = cb.shape
+    table = [[squared_sub(query[s * dsub:(s + 1) * dsub], c) for c in cb[s]] for s in range(m)]  # f32 tables
+
+    def adc(node):
+        return F(np.sqrt(_fold(table[s][int(codes[node, s])] for s in range(m))))
+
+    ef = max(ef, k)
+    visited = {entry}
+    d0 = distance(cfg.metric, query, vectors[entry])
+    exact_queue, results, approx_queue = [(d0, entry)], [(-d0, -entry)], []
+    n_adc = n_rerank = 0
+    while exact_queue:
+        d, node = heapq.heappop(exact_queue)
+        if len(results) >= ef and d > -results[0][0]:
+            break
+        for nb in nbrs[int(offsets[node]):int(offsets[node + 1])]:
+            nb = int(nb)
+            if nb not in visited:
+                visited.add(nb)
+                heapq.heappush(approx_queue, (adc(nb), nb))
+                n_adc += 1
+        if not approx_queue:
+            continue
+        promote = min(max(int(np.ceil(F(F(len(approx_queue)) * F(a)))), 1), len(approx_queue))
+        for _ in range(promote):
+            _, nb = heapq.heappop(approx_queue)
+            nd = distance(cfg.metric, query, vectors[nb])
+            n_rerank += 1
+            if len(results) < ef or nd < -results[0][0]:
+                heapq.heappush(exact_queue, (nd, nb))
+                heapq.heappush(results, (-nd, -nb))
+                if len(results) > ef:
+                    heapq.heappop(results)
+    return [(i, d) for d, i in sorted((-d, -i) for d, i in results)[:k]], n_adc, n_rerank
+
+
+@pytest.mark.parametrize("a", [0.1, 0.5, 1.0])
+def test_two_level_second_reading(orc, a):
+    cfg, v, _, off, nbrs, entry = oracle_graph(orc, 400, 12, seed=21, metric=0, m=6, m0=12, ef_construction=32)
+    cb = orc.pq_train(1, v, 4, 16, 5, 3)
+    codes = orc.pq_encode(1, cb, v)
+    q = uniform(np.random.RandomState(96), 8, 12)
+    ids, dist, cnt, st = orc.leann_search_two_level(cfg._s, v, off, nbrs, entry, cb, codes, q, 10, 40, a, stats=True)
+    for qi in range(len(q)):
+        mine, n_adc, n_rerank = two_level(cfg, v, off, nbrs, entry, cb, codes, q[qi], 10, 40, a)
+        assert cnt[qi] == len(mine) and ids[qi, :cnt[qi]].tolist() == [i for i, _ in mine], qi
+        assert [x.view(np.uint32) for x in dist[qi, :cnt[qi]]] == [F(x).view(np.uint32) for _, x in mine], qi
+        assert (int(st["n_adc"][qi]), int(st["n_rerank"][qi]), int(st["n_dist"][qi])) == (n_adc, n_rerank, n_rerank + 1)
+    if a == 1.0:  # everything scored is promoted: the exact search over the same graph, node for node
+        e_ids, e_dist, _ = orc.leann_search(cfg._s, v, off, nbrs, entry, q, 10, 40)
+        assert np.array_equal(ids, e_ids) and np.array_equal(dist.view(np.uint32), e_dist.view(np.uint32))
