@@ -16,6 +16,7 @@ bit for bit:
   random stream — trained codebooks bit for bit;
 * the batched construction ("round model") as DESIGN.md 3.3 words it — this repository's own widening of the sequential
   loop — for several round sizes, `batch = 1` coinciding with the sequential reading;
+* the HNSW insert in rounds as DESIGN.md 3.5 words it;
 * the two-level search as DESIGN.md 3.4 pins down the specification's Algorithm 2 (no reference code);
 * "PQ ADC traversal + exact rerank" as include/islands_b200.h defines it (not a reference algorithm): checks that the
   oracle's twin implements the written definition, bfloat16 table rule included.
@@ -720,3 +721,66 @@ def test_two_level_second_reading(orc, a):
     if a == 1.0:  # everything scored is promoted: the exact search over the same graph, node for node
         e_ids, e_dist, _ = orc.leann_search(cfg._s, v, off, nbrs, entry, q, 10, 40)
         assert np.array_equal(ids, e_ids) and np.array_equal(dist.view(np.uint32), e_dist.view(np.uint32))
+
+
+# ---- HnswGraph in rounds: the read-only half of insert_node for all nodes of a round against the
+# pre-round graph, then the mutating half node by node in id order. ------------------------------------------------------
+
+def hnsw_insert_rounds(g, vectors, levels, batch):
+    n, inserted = len(vectors), len(g.nodes)
+    while inserted < n:
+        size = 1 if not g.nodes else min(batch, max(1, len(g.nodes) // 2), n - inserted)
+        nodes = range(inserted, inserted + size)
+        plans = {}
+        for node in nodes:  # read-only half, against the graph as it stands before the round
+            level = int(levels[node])
+            plan = [[] for _ in range(level + 1)]
+            if g.entry is not None:
+                current = g._greedy(vectors[node], g.entry, range(g.max_level, level, -1))
+                for layer in range(level, -1, -1):
+                    found = g.search_layer(vectors[node], current, g.cfg.ef_construction, layer)
+                    plan[layer] = [i for i, _ in found[:g.cfg.m0 if layer == 0 else g.cfg.m]]
+                    if plan[layer]:
+                        current = plan[layer][0]
+            plans[node] = plan
+        for node in nodes:  # mutating half, node by node
+            for layer in range(len(plans[node]) - 1, -1, -1):
+                m = g.cfg.m0 if layer == 0 else g.cfg.m
+                for target in plans[node][layer]:
+                    conns = g.nodes[target][1]
+                    if layer < len(conns):
+                        conns[layer].append(node)
+                        if len(conns[layer]) > m:
+                            scored = [(i, distance(g.cfg.metric, g.nodes[target][0], g.nodes[i][0]))
+                                      for i in conns[layer] if i in g.nodes]
+                            scored.sort(key=lambda t: t[1])
+                            conns[layer] = [i for i, _ in scored[:m]]
+            level = int(levels[node])
+            if g.entry is None:
+                g.entry, g.max_level = node, level
+            elif level > g.max_level:
+                g.max_level, g.entry = level, node
+            g.nodes[node] = (vectors[node], plans[node])
+        inserted += size
+
+
+@pytest.mark.parametrize("batch", [1, 8, 32])
+def test_hnsw_round_model_second_reading(orc, batch):
+    from islands_b200 import HnswConfig
+
+    n, d = 260, 8
+    v = uniform(np.random.RandomState(70), n, d)
+    cfg = HnswConfig(m=4, m0=8, ef_construction=20, metric=0, ml=0.9)
+    levels = orc.draw_levels(13, n, cfg.ml, cfg.max_layers)
+    theirs, mine = orc.Hnsw(cfg._s, d), Hnsw(cfg)
+    theirs.insert_batch(v, levels, batch=batch)
+    hnsw_insert_rounds(mine, v, levels, batch)
+    assert (theirs.entry_point(), theirs.max_level(), len(theirs)) == (mine.entry, mine.max_level, n)
+    for i in range(n):
+        for layer, conns in enumerate(mine.nodes[i][1]):
+            assert theirs.neighbors(i, layer).tolist() == conns, (i, layer)
+    if batch == 1:  # one node per round is the sequential insert
+        seq = Hnsw(cfg)
+        for i in range(n):
+            seq.insert(v[i], int(levels[i]))
+        assert all(seq.nodes[i][1] == mine.nodes[i][1] for i in range(n))
