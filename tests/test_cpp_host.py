@@ -26,3 +26,15 @@ def test_cpp_host_mirror_cpu(tmp_path):
 def test_cpp_host_mirror_gpu(tmp_path, gpu_lib):
     out = subprocess.run([_build(tmp_path), "gpu"], capture_output=True, text=True)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/islands_b200.h compiles as C99 with -pedantic (the form cgo / bindgen / ctypes consumers bind) and a C
+    program links against the library and gets the reference's defaults and errors back (tests/c/abi_check.c)."""
+    exe = str(tmp_path / "abi_check")
+    lib_dir = os.path.join(ROOT, "islands_b200", "lib")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "abi_check.c"), "-o", exe, "-L", lib_dir, "-lislands_b200",
+                           f"-Wl,-rpath,{lib_dir}"])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
