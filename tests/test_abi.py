@@ -268,3 +268,35 @@ def test_nothing_unwinds_through_the_abi():
                 assert lines[k].startswith("} ISL_ABI_GUARD"), (name, k + 1)
                 guarded += 1
     assert guarded >= 87
+
+
+def test_last_error_is_per_thread():
+    """`isl_last_error` / `isl_last_error_detail` are thread-local (header): concurrent failing calls on different
+    threads each read back their own message and payload (no device needed: the length check comes first)."""
+    import ctypes as C
+    import threading
+
+    from islands_b200 import _ffi
+
+    lib = _ffi.load()
+    errors = []
+
+    def worker(t):
+        a = (C.c_float * (t + 2))()
+        b = (C.c_float * 1)()
+        out = C.c_float()
+        for _ in range(300):
+            st = lib.isl_distance_calculate(1, a, t + 2, b, 1, C.byref(out))
+            x, y = C.c_uint64(), C.c_uint64()
+            lib.isl_last_error_detail(C.byref(x), C.byref(y))
+            msg = lib.isl_last_error().decode()
+            if st != 1 or (x.value, y.value) != (t + 2, 1) or f"expected {t + 2}, got 1" not in msg:
+                errors.append((t, st, x.value, y.value, msg))
+                return
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors[:3]
