@@ -33,7 +33,7 @@ def compute():
         cfg = LeannConfig(metric=metric, m=8, m0=16, ef_construction=40)
         levels = orc.draw_levels(5, n, cfg.ml, cfg.max_layers)
         off, nbrs, entry, max_level = orc.leann_build(cfg._s, v, levels)
-        out[f"m{metric}_off"], out[f"m{metric}_nbrs"] = off, nbrs
+        out[f"m{metric}_off"], out[f"m{metric}_nbrs"], out[f"m{metric}_levels"] = off, nbrs, levels
         out[f"m{metric}_entry"] = np.array([entry, max_level], np.int64)
         ids, dist, cnt, st = orc.leann_search(cfg._s, v, off, nbrs, entry, q, 10, 48, stats=True)
         out[f"m{metric}_ids"], out[f"m{metric}_dist"], out[f"m{metric}_cnt"] = ids, dist.view(np.uint32), cnt

@@ -6,6 +6,7 @@ import importlib.util
 import os
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -48,3 +49,51 @@ def test_second_reading_reproduces_the_frozen_search_results():
             assert [i for i, _ in mine] == golden[f"m{metric}_ids"][qi].tolist()
             assert [np.float32(d).view(np.uint32) for _, d in mine] == golden[f"m{metric}_dist"][qi].tolist()
             assert computed == int(golden[f"m{metric}_stats"][2, qi])
+
+
+def _inputs():
+    rng = np.random.RandomState(2024)
+    v = (rng.rand(500, 16).astype(np.float32) * 2 - 1).astype(np.float32)
+    v[450:] = v[:50]
+    q = (rng.rand(16, 16).astype(np.float32) * 2 - 1).astype(np.float32)
+    return v, q
+
+
+def _check_search_against_golden(search_fn):
+    """search_fn(cfg, vectors, offsets, neighbors, levels, entry, queries, k, ef) -> ids, dist, count, (n_hop, n_edge, n_dist)."""
+    from islands_b200 import LeannConfig
+
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "search_golden.npz"))
+    v, q = _inputs()
+    for metric in range(4):
+        cfg = LeannConfig(metric=metric, m=8, m0=16, ef_construction=40)
+        ids, dist, cnt, counters = search_fn(cfg, v, golden[f"m{metric}_off"], golden[f"m{metric}_nbrs"], golden[f"m{metric}_levels"],
+                                             int(golden[f"m{metric}_entry"][0]), q, 10, 48)
+        assert np.array_equal(cnt, golden[f"m{metric}_cnt"]), metric
+        assert np.array_equal(ids, golden[f"m{metric}_ids"]), metric
+        assert np.array_equal(np.ascontiguousarray(dist, np.float32).view(np.uint32), golden[f"m{metric}_dist"]), metric
+        assert np.array_equal(np.stack([np.asarray(c, np.uint64) for c in counters]), golden[f"m{metric}_stats"]), metric
+
+
+def test_oracle_search_against_the_frozen_results(orc):
+    def oracle(cfg, v, off, nbrs, levels, entry, q, k, ef):
+        ids, dist, cnt, st = orc.leann_search(cfg._s, v, off, nbrs, entry, q, k, ef, stats=True)
+        return ids, dist, cnt, (st["n_hop"], st["n_edge"], st["n_dist"])
+
+    _check_search_against_golden(oracle)
+
+
+
+@pytest.mark.gpu
+def test_gpu_search_against_the_frozen_results(gpu_lib):
+    """The CUDA search on the frozen graphs against the frozen results — the same comparison the oracle passes above, with
+    no oracle in the loop: ids, distance bits, counts and the three traversal counters for the four metrics."""
+    from islands_b200 import LeannIndex
+
+    def gpu(cfg, v, off, nbrs, levels, entry, q, k, ef):
+        idx = LeannIndex.from_csr(cfg, v, off, nbrs, levels, entry)
+        ids, dist, cnt, st = idx.search_batch(q, k, ef, stats=True)
+        idx.free()
+        return ids, dist, cnt, (st.n_hop, st.n_edge, st.n_dist)
+
+    _check_search_against_golden(gpu)
