@@ -24,13 +24,13 @@ def compute():
     from oracle import pyoracle as orc
 
     out = {}
-    n, d, nq = 500, 16, 16
+    n, d, nq = 500, 32, 16
     rng = np.random.RandomState(2024)
     v = uniform(rng, n, d)
     v[n - 50:] = v[:50]  # exact copies: distance ties
     q = uniform(rng, nq, d)
     for metric in range(4):
-        cfg = LeannConfig(metric=metric, m=8, m0=16, ef_construction=40)
+        cfg = LeannConfig(metric=metric)  # paper defaults: m = 30, m0 = 60, efC = 128 (leann.rs:386-403)
         levels = orc.draw_levels(5, n, cfg.ml, cfg.max_layers)
         off, nbrs, entry, max_level = orc.leann_build(cfg._s, v, levels)
         out[f"m{metric}_off"], out[f"m{metric}_nbrs"], out[f"m{metric}_levels"] = off, nbrs, levels
@@ -40,12 +40,12 @@ def compute():
         out[f"m{metric}_stats"] = np.stack([st["n_hop"], st["n_edge"], st["n_dist"]])
         if metric == 0:
             for strategy, ratio in ((0, 0.5), (1, 0.5), (2, 0.5)):
-                pc = LeannConfig(metric=0, m=8, m0=16, ef_construction=40, pruning_strategy=strategy, prune_ratio=ratio, prune_seed=77)
+                pc = LeannConfig(metric=0, pruning_strategy=strategy, prune_ratio=ratio, prune_seed=77)
                 pi, pd, _ = orc.leann_search(pc._s, v, off, nbrs, entry, q, 10, 48)
                 out[f"prune{strategy}_ids"], out[f"prune{strategy}_dist"] = pi, pd.view(np.uint32)
             r_off, r_nbrs, r_entry, _ = orc.leann_build(cfg._s, v, levels, batch=32)
             out["round32_off"], out["round32_nbrs"], out["round32_entry"] = r_off, r_nbrs, np.array([r_entry], np.int64)
-            cb = orc.pq_train(1, v, 4, 16, 6, 42)
+            cb = orc.pq_train(1, v, 4, 16, 6, 42)  # dsub = 8
             codes = orc.pq_encode(1, cb, v)
             out["pq_codebooks"], out["pq_codes"] = cb.view(np.uint32), codes
             out["pq_tables"] = orc.pq_build_tables(cb, q[0]).view(np.uint32)

@@ -22,12 +22,12 @@ def test_oracle_reproduces_its_frozen_outputs(orc):
         assert now[name].dtype == golden[name].dtype and np.array_equal(now[name], golden[name]), name
     # a few values spelled out, so that the fixture is not only compared with itself
     assert golden["m0_entry"].tolist() == [int(golden["m0_entry"][0]), int(golden["m0_entry"][1])] and golden["m0_off"][0] == 0
-    assert int(golden["m0_off"][-1]) == golden["m0_nbrs"].size and (np.diff(golden["m0_off"].astype(np.int64)) <= 16).all()
+    assert int(golden["m0_off"][-1]) == golden["m0_nbrs"].size and (np.diff(golden["m0_off"].astype(np.int64)) <= 60).all()
     for metric in range(4):
         dist = golden[f"m{metric}_dist"].view(np.float32)
         assert (golden[f"m{metric}_cnt"] == 10).all() and (np.diff(dist, axis=1) >= 0).all()
         assert (golden[f"m{metric}_ids"] < 500).all()
-    assert (golden["pq_codes"] < 16).all() and golden["pq_codebooks"].shape == (4, 16, 4)
+    assert (golden["pq_codes"] < 16).all() and golden["pq_codebooks"].shape == (4, 16, 8)
 
 
 def test_second_reading_reproduces_the_frozen_search_results():
@@ -38,11 +38,11 @@ def test_second_reading_reproduces_the_frozen_search_results():
 
     golden = np.load(os.path.join(ROOT, "tests", "golden", "search_golden.npz"))
     rng = np.random.RandomState(2024)
-    v = (rng.rand(500, 16).astype(np.float32) * 2 - 1).astype(np.float32)
+    v = (rng.rand(500, 32).astype(np.float32) * 2 - 1).astype(np.float32)
     v[450:] = v[:50]
-    q = (rng.rand(16, 16).astype(np.float32) * 2 - 1).astype(np.float32)
+    q = (rng.rand(16, 32).astype(np.float32) * 2 - 1).astype(np.float32)
     for metric in (0, 1):
-        cfg = LeannConfig(metric=metric, m=8, m0=16, ef_construction=40)
+        cfg = LeannConfig(metric=metric)
         off, nbrs, entry = golden[f"m{metric}_off"], golden[f"m{metric}_nbrs"], int(golden[f"m{metric}_entry"][0])
         for qi in range(0, 16, 3):
             mine, computed = search(cfg, v, off, nbrs, entry, q[qi], 10, 48)
@@ -53,9 +53,9 @@ def test_second_reading_reproduces_the_frozen_search_results():
 
 def _inputs():
     rng = np.random.RandomState(2024)
-    v = (rng.rand(500, 16).astype(np.float32) * 2 - 1).astype(np.float32)
+    v = (rng.rand(500, 32).astype(np.float32) * 2 - 1).astype(np.float32)
     v[450:] = v[:50]
-    q = (rng.rand(16, 16).astype(np.float32) * 2 - 1).astype(np.float32)
+    q = (rng.rand(16, 32).astype(np.float32) * 2 - 1).astype(np.float32)
     return v, q
 
 
@@ -66,7 +66,7 @@ def _check_search_against_golden(search_fn):
     golden = np.load(os.path.join(ROOT, "tests", "golden", "search_golden.npz"))
     v, q = _inputs()
     for metric in range(4):
-        cfg = LeannConfig(metric=metric, m=8, m0=16, ef_construction=40)
+        cfg = LeannConfig(metric=metric)
         ids, dist, cnt, counters = search_fn(cfg, v, golden[f"m{metric}_off"], golden[f"m{metric}_nbrs"], golden[f"m{metric}_levels"],
                                              int(golden[f"m{metric}_entry"][0]), q, 10, 48)
         assert np.array_equal(cnt, golden[f"m{metric}_cnt"]), metric
