@@ -784,3 +784,23 @@ def test_hnsw_round_model_second_reading(orc, batch):
         for i in range(n):
             seq.insert(v[i], int(levels[i]))
         assert all(seq.nodes[i][1] == mine.nodes[i][1] for i in range(n))
+
+
+def test_search_on_arbitrary_graphs_second_reading(orc):
+    """Graphs no construction would produce — repeated ids inside a list, self loops, empty lists, unreachable nodes, an
+    entry point with no edges — and coarse-grid vectors (many exact distance ties): the loop's semantics alone decide
+    (`visited.insert` keeps the first of repeated ids; ties fall to the id), for every metric and both deterministic
+    pruning strategies."""
+    rng = np.random.RandomState(123)
+    for trial in range(40):
+        n, d = int(rng.randint(1, 40)), int(rng.randint(1, 6))
+        v = rng.randint(-2, 3, size=(n, d)).astype(np.float32)  # coarse grid, zero vectors included
+        lists = [rng.randint(0, n, size=int(rng.randint(0, 9))).tolist() for _ in range(n)]
+        off = np.concatenate([[0], np.cumsum([len(x) for x in lists])]).astype(np.uint64)
+        nbrs = np.array([i for x in lists for i in x], np.uint64)
+        entry = int(rng.randint(0, n))
+        cfg = LeannConfig(metric=int(rng.randint(0, 4)), pruning_strategy=int(rng.randint(0, 2)),
+                          prune_ratio=float(rng.choice([0.0, 0.0, 0.4, 0.9])))
+        q = rng.randint(-2, 3, size=(3, d)).astype(np.float32)
+        k = int(rng.randint(1, 12))
+        _compare(orc, cfg, v, off, nbrs, entry, q, k, int(rng.randint(1, 20)))
