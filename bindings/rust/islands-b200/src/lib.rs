@@ -604,6 +604,129 @@ impl LeannIndex {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// embedding/candle_provider.rs:353-507 — the recompute encoder, and the searches that use it as the
+// EmbeddingProvider (leann.rs:82-99, 947-950)
+// ---------------------------------------------------------------------------------------------
+/// BERT shape of the recompute encoder (defaults: BERT-base, 110M parameters) and its arithmetic mode.
+#[derive(Debug, Clone, Copy, PartialEq, Eq, Default)]
+pub enum EncoderPrecision {
+    /// bf16 operands, f32 accumulation.
+    #[default]
+    Bf16,
+    /// Split precision (three bf16 products per f32 product): embeddings agree with an f32 forward to ~2e-5.
+    Bf16x3,
+}
+
+pub struct Encoder {
+    handle: *mut sys::IslEncoder,
+}
+
+unsafe impl Send for Encoder {}
+
+impl Drop for Encoder {
+    fn drop(&mut self) {
+        unsafe { sys::isl_encoder_free(self.handle) };
+    }
+}
+
+impl Encoder {
+    /// BERT-base shape; weights are set by name (`set_parameter`, Hugging Face names) or drawn (`init_random`).
+    pub fn new(precision: EncoderPrecision) -> CoreResult<Self> {
+        let mut raw = std::mem::MaybeUninit::<sys::IslEncoderConfig>::zeroed();
+        check(unsafe { sys::isl_encoder_config_default(raw.as_mut_ptr()) })?;
+        let mut cfg = unsafe { raw.assume_init() };
+        cfg.precision = match precision {
+            EncoderPrecision::Bf16 => 0,
+            EncoderPrecision::Bf16x3 => 1,
+        };
+        let mut h: *mut sys::IslEncoder = ptr::null_mut();
+        check(unsafe { sys::isl_encoder_new(&cfg, &mut h) })?;
+        Ok(Self { handle: h })
+    }
+    /// `EmbeddingProvider::dimension`
+    pub fn dimension(&self) -> usize {
+        unsafe { sys::isl_encoder_dimension(self.handle) as usize }
+    }
+    pub fn num_parameters(&self) -> u64 {
+        unsafe { sys::isl_encoder_num_parameters(self.handle) }
+    }
+    pub fn init_random(&mut self, seed: u64, stddev: f32) -> CoreResult<()> {
+        check(unsafe { sys::isl_encoder_init_random(self.handle, seed, stddev) })
+    }
+    pub fn set_parameter(&mut self, name: &str, data: &[f32]) -> CoreResult<()> {
+        let name = std::ffi::CString::new(name).map_err(|e| CoreError::EmbeddingError(e.to_string()))?;
+        check(unsafe { sys::isl_encoder_set_parameter(self.handle, name.as_ptr(), data.as_ptr(), data.len() as u64) })
+    }
+    /// The model half of `embed_texts_raw` (candle_provider.rs:404-507): `token_ids` is `[batch][seq_len]` zero padded,
+    /// `lengths[b]` the number of real tokens; returns `[batch][dimension]` pooled, L2-normalised embeddings.
+    pub fn embed(&mut self, token_ids: &[i32], lengths: &[i32], seq_len: usize) -> CoreResult<Vec<f32>> {
+        if token_ids.len() != lengths.len() * seq_len {
+            return Err(CoreError::EmbeddingError("token_ids must hold lengths.len() rows of seq_len ids".into()));
+        }
+        let mut out = vec![0f32; lengths.len() * self.dimension()];
+        check(unsafe {
+            sys::isl_encoder_embed(self.handle, token_ids.as_ptr(), lengths.as_ptr(), lengths.len() as u64, seq_len as u32, out.as_mut_ptr())
+        })
+        .map_err(|e| CoreError::EmbeddingError(e.to_string()))?;
+        Ok(out)
+    }
+}
+
+impl LeannIndex {
+    /// Attach the encoder as this index's `EmbeddingProvider`: node i is embedded from row i of `token_ids`
+    /// (`[len()][seq_len]`) whenever a recompute search needs it.  The encoder must outlive the index.
+    pub fn set_recompute(&mut self, encoder: &mut Encoder, token_ids: &[i32], lengths: &[i32], seq_len: usize) -> CoreResult<()> {
+        if lengths.len() != self.len() || token_ids.len() != lengths.len() * seq_len {
+            return Err(CoreError::EmbeddingError("one token row of seq_len ids and one length per node".into()));
+        }
+        check(unsafe { sys::isl_index_set_recompute(self.handle, encoder.handle, token_ids.as_ptr(), lengths.as_ptr(), seq_len as u32) })
+    }
+    /// LEANN's storage saving: free the resident embeddings; graph, codes and token rows remain and only the
+    /// recompute searches keep working.
+    pub fn drop_vectors(&mut self) -> CoreResult<()> {
+        check(unsafe { sys::isl_index_drop_vectors(self.handle) })
+    }
+    /// Keep the embeddings of the `count` highest in-degree nodes resident (docs/leann-specification.md:661-690).
+    pub fn set_hub_cache(&mut self, count: u64) -> CoreResult<()> {
+        check(unsafe { sys::isl_index_set_hub_cache(self.handle, count) })
+    }
+    /// Recompute / rerank only the best `limit` survivors of the ADC traversal (0 = all of them).
+    pub fn set_rerank_limit(&mut self, limit: u32) -> CoreResult<()> {
+        check(unsafe { sys::isl_index_set_rerank_limit(self.handle, limit) })
+    }
+
+    fn batched(
+        &self,
+        queries: &[f32],
+        nq: usize,
+        k: usize,
+        ef: usize,
+        call: unsafe extern "C" fn(*const sys::IslIndex, *const f32, u64, u32, u32, u32, *mut u64, *mut f32, *mut u32, *mut sys::IslSearchStats) -> i32,
+    ) -> CoreResult<(Vec<u64>, Vec<f32>, Vec<u32>)> {
+        let dim = if nq == 0 { 0 } else { queries.len() / nq };
+        let (mut ids, mut dist, mut count) = (vec![u64::MAX; nq * k], vec![f32::INFINITY; nq * k], vec![0u32; nq]);
+        check(unsafe {
+            call(self.handle, queries.as_ptr(), nq as u64, dim as u32, k as u32, ef as u32, ids.as_mut_ptr(), dist.as_mut_ptr(),
+                 count.as_mut_ptr(), ptr::null_mut())
+        })?;
+        Ok((ids, dist, count))
+    }
+    /// `search_with_params` exactly as the reference runs it with a model behind the provider (leann.rs:899-988): every
+    /// hop's unvisited neighbours are embedded by the encoder (one pass per frontier of the whole batch).
+    pub fn search_recompute_batch(&self, queries: &[f32], nq: usize, k: usize, ef: usize) -> CoreResult<(Vec<u64>, Vec<f32>, Vec<u32>)> {
+        self.batched(queries, nq, k, ef, sys::isl_index_search_recompute)
+    }
+    /// The cheap variant: ADC traversal, encoder over the batch's distinct survivors, exact rerank.
+    pub fn search_adc_recompute_batch(&self, queries: &[f32], nq: usize, k: usize, ef: usize) -> CoreResult<(Vec<u64>, Vec<f32>, Vec<u32>)> {
+        self.batched(queries, nq, k, ef, sys::isl_index_search_adc_recompute)
+    }
+    /// "PQ ADC traversal + exact rerank" over the resident embeddings (include/islands_b200.h).
+    pub fn search_adc_rerank_batch(&self, queries: &[f32], nq: usize, k: usize, ef: usize) -> CoreResult<(Vec<u64>, Vec<f32>, Vec<u32>)> {
+        self.batched(queries, nq, k, ef, sys::isl_index_search_adc_rerank)
+    }
+}
+
 /// One rank's membership in a sharded index (NCCL communicator inside the library).
 pub struct ShardComm {
     handle: *mut sys::IslShard,
