@@ -35,16 +35,6 @@ static isl_status dim_check(const isl_pq* pq, uint32_t dim) {
   return ISL_OK;
 }
 
-// Host [rows][dim] -> device [rows][ld] zero padded.
-static isl_status upload_padded(const float* src, uint64_t rows, uint32_t dim, uint32_t ld,
-                                DevBuf<float>& dst, cudaStream_t st) {
-  ISL_CUDA_TRY(dst.alloc(std::max<uint64_t>(rows * ld, 4)));
-  if (ld != dim) ISL_CUDA_TRY(cudaMemsetAsync(dst.p, 0, dst.bytes(), st));
-  if (rows)
-    ISL_CUDA_TRY(cudaMemcpy2DAsync(dst.p, (size_t)ld * 4, src, (size_t)dim * 4, (size_t)dim * 4, rows,
-                                   cudaMemcpyHostToDevice, st));
-  return ISL_OK;
-}
 }  // namespace isl
 
 #include "std_rng.h"
