@@ -380,6 +380,10 @@ impl LeannConfig {
 pub struct LeannIndex {
     config: LeannConfig,
     handle: *mut sys::IslIndex,
+    // The library keeps raw pointers to an attached quantizer / encoder: the index shares their ownership so that
+    // neither can be freed while it may still be read (fields drop after `Drop::drop` has freed the handle).
+    pq: Option<std::sync::Arc<ProductQuantizer>>,
+    encoder: Option<std::sync::Arc<Encoder>>,
 }
 
 // The handle is immutable after build; searches lease per-call scratch inside the library (csrc/api.cu).
@@ -409,7 +413,7 @@ impl Default for BuildOptions {
 impl LeannIndex {
     pub fn new(config: LeannConfig) -> CoreResult<Self> {
         config.validate()?;
-        Ok(Self { config, handle: ptr::null_mut() })
+        Ok(Self { config, handle: ptr::null_mut(), pq: None, encoder: None })
     }
     pub fn with_defaults() -> CoreResult<Self> {
         Self::new(LeannConfig::default())
@@ -483,6 +487,8 @@ impl LeannIndex {
         })?;
         unsafe { sys::isl_index_free(self.handle) };
         self.handle = h;
+        self.pq = None; // attachments belonged to the handle that was just freed
+        self.encoder = None;
         Ok(())
     }
 
@@ -510,7 +516,7 @@ impl LeannIndex {
                 &mut h,
             )
         })?;
-        Ok(Self { config, handle: h })
+        Ok(Self { config, handle: h, pq: None, encoder: None })
     }
 
     /// graph: the CSR arrays in the reference's layout.
@@ -600,7 +606,7 @@ impl LeannIndex {
         check(unsafe { sys::isl_index_from_bytes(bytes.as_ptr(), bytes.len() as u64, flat.as_ptr(), provider.dimension() as u32, &mut h) })?;
         let mut raw = std::mem::MaybeUninit::<sys::IslLeannConfig>::zeroed();
         check(unsafe { sys::isl_index_get_config(h, raw.as_mut_ptr()) })?;
-        Ok(Self { config: LeannConfig::from_raw(unsafe { &raw.assume_init() }), handle: h })
+        Ok(Self { config: LeannConfig::from_raw(unsafe { &raw.assume_init() }), handle: h, pq: None, encoder: None })
     }
 }
 
@@ -622,7 +628,9 @@ pub struct Encoder {
     handle: *mut sys::IslEncoder,
 }
 
+// The library serialises forwards on one encoder handle (a mutex inside it); weights are set through `&mut self`.
 unsafe impl Send for Encoder {}
+unsafe impl Sync for Encoder {}
 
 impl Drop for Encoder {
     fn drop(&mut self) {
@@ -660,7 +668,7 @@ impl Encoder {
     }
     /// The model half of `embed_texts_raw` (candle_provider.rs:404-507): `token_ids` is `[batch][seq_len]` zero padded,
     /// `lengths[b]` the number of real tokens; returns `[batch][dimension]` pooled, L2-normalised embeddings.
-    pub fn embed(&mut self, token_ids: &[i32], lengths: &[i32], seq_len: usize) -> CoreResult<Vec<f32>> {
+    pub fn embed(&self, token_ids: &[i32], lengths: &[i32], seq_len: usize) -> CoreResult<Vec<f32>> {
         if token_ids.len() != lengths.len() * seq_len {
             return Err(CoreError::EmbeddingError("token_ids must hold lengths.len() rows of seq_len ids".into()));
         }
@@ -674,13 +682,25 @@ impl Encoder {
 }
 
 impl LeannIndex {
+    /// Attach a trained quantizer and the codes `[len()][num_subquantizers]` of the indexed vectors: enables the
+    /// two-level search and "PQ ADC traversal + exact rerank".  The index shares ownership of the quantizer.
+    pub fn attach_pq(&mut self, pq: std::sync::Arc<ProductQuantizer>, codes: &[u16]) -> CoreResult<()> {
+        if codes.len() != self.len() * pq.num_subquantizers() {
+            return Err(CoreError::PQError("one code row per indexed vector".into()));
+        }
+        check(unsafe { sys::isl_index_attach_pq(self.handle, pq.handle, codes.as_ptr()) })?;
+        self.pq = Some(pq);
+        Ok(())
+    }
     /// Attach the encoder as this index's `EmbeddingProvider`: node i is embedded from row i of `token_ids`
-    /// (`[len()][seq_len]`) whenever a recompute search needs it.  The encoder must outlive the index.
-    pub fn set_recompute(&mut self, encoder: &mut Encoder, token_ids: &[i32], lengths: &[i32], seq_len: usize) -> CoreResult<()> {
+    /// (`[len()][seq_len]`) whenever a recompute search needs it.  The index shares ownership of the encoder.
+    pub fn set_recompute(&mut self, encoder: std::sync::Arc<Encoder>, token_ids: &[i32], lengths: &[i32], seq_len: usize) -> CoreResult<()> {
         if lengths.len() != self.len() || token_ids.len() != lengths.len() * seq_len {
             return Err(CoreError::EmbeddingError("one token row of seq_len ids and one length per node".into()));
         }
-        check(unsafe { sys::isl_index_set_recompute(self.handle, encoder.handle, token_ids.as_ptr(), lengths.as_ptr(), seq_len as u32) })
+        check(unsafe { sys::isl_index_set_recompute(self.handle, encoder.handle, token_ids.as_ptr(), lengths.as_ptr(), seq_len as u32) })?;
+        self.encoder = Some(encoder);
+        Ok(())
     }
     /// LEANN's storage saving: free the resident embeddings; graph, codes and token rows remain and only the
     /// recompute searches keep working.
@@ -1325,9 +1345,5 @@ impl ProductQuantizer {
         check(unsafe { sys::isl_pq_from_bytes(bytes.as_ptr(), bytes.len() as u64, &mut h) })?;
         let dimension = unsafe { sys::isl_pq_dimension(h) } as usize;
         Ok(Self { handle: h, dimension })
-    }
-    /// Attach this quantizer's codes to an index for the "PQ ADC traversal + exact rerank" search.
-    pub fn attach_to(&self, index: &mut LeannIndex, codes: &[u16]) -> CoreResult<()> {
-        check(unsafe { sys::isl_index_attach_pq(index.handle, self.handle, codes.as_ptr()) })
     }
 }
