@@ -1240,6 +1240,33 @@ impl PQConfig {
     }
 }
 
+/// pq.rs:66-112: the centroids of one subquantizer.
+#[derive(Debug, Clone)]
+pub struct PQCodebook {
+    pub centroids: Vec<Vec<f32>>,
+    pub subvector_dim: usize,
+}
+
+impl PQCodebook {
+    pub fn new(subvector_dim: usize) -> Self {
+        Self { centroids: Vec::new(), subvector_dim }
+    }
+    /// pq.rs:86-106, on the device: a one-subquantizer quantizer holding these centroids encodes the subvector (strict
+    /// `<` scan from `f32::MAX`: the first of equal centroids wins).
+    pub fn find_nearest(&self, subvector: &[f32], metric: &DistanceMetric) -> CoreResult<usize> {
+        if subvector.len() != self.subvector_dim {
+            return Err(CoreError::DimensionMismatch { expected: self.subvector_dim, actual: subvector.len() });
+        }
+        let config = PQConfig { num_subquantizers: 1, num_centroids: self.centroids.len(), training_iterations: 1, seed: None };
+        let mut pq = ProductQuantizer::new(self.subvector_dim, config)?.with_metric(*metric);
+        pq.set_codebooks(std::slice::from_ref(self))?;
+        Ok(pq.encode(subvector)?[0] as usize)
+    }
+    pub fn get_centroid(&self, idx: usize) -> Option<&[f32]> {
+        self.centroids.get(idx).map(Vec::as_slice)
+    }
+}
+
 pub struct ProductQuantizer {
     handle: *mut sys::IslPq,
     dimension: usize,
@@ -1288,6 +1315,40 @@ impl ProductQuantizer {
             flat.extend_from_slice(v);
         }
         check(unsafe { sys::isl_pq_train(self.handle, flat.as_ptr(), vectors.len() as u64, self.dimension as u32) })
+    }
+    /// Install codebooks trained elsewhere (one per subquantizer, equal sizes); marks the quantizer trained.
+    pub fn set_codebooks(&mut self, codebooks: &[PQCodebook]) -> CoreResult<()> {
+        let ksub = codebooks.first().map_or(0, |c| c.centroids.len());
+        let mut flat = Vec::new();
+        for cb in codebooks {
+            if cb.centroids.len() != ksub {
+                return Err(CoreError::PQError("codebooks must hold the same number of centroids".into()));
+            }
+            for centroid in &cb.centroids {
+                if centroid.len() != cb.subvector_dim {
+                    return Err(CoreError::DimensionMismatch { expected: cb.subvector_dim, actual: centroid.len() });
+                }
+                flat.extend_from_slice(centroid);
+            }
+        }
+        if codebooks.len() != self.num_subquantizers() || flat.len() != ksub * self.dimension {
+            return Err(CoreError::PQError("one codebook per subquantizer, subvector_dim = dimension / num_subquantizers".into()));
+        }
+        check(unsafe { sys::isl_pq_set_codebooks(self.handle, flat.as_ptr(), ksub as u64) })
+    }
+    /// `codebooks` (pq.rs:120-121), copied out of the library.
+    pub fn codebooks(&self) -> CoreResult<Vec<PQCodebook>> {
+        let m = self.num_subquantizers();
+        let mut ksub = 0u64;
+        check(unsafe { sys::isl_pq_get_codebooks(self.handle, ptr::null_mut(), &mut ksub) })?;
+        let dsub = if m == 0 { 0 } else { self.dimension / m };
+        let mut flat = vec![0f32; m * ksub as usize * dsub];
+        check(unsafe { sys::isl_pq_get_codebooks(self.handle, flat.as_mut_ptr(), &mut ksub) })?;
+        Ok(flat
+            .chunks((ksub as usize * dsub).max(1))
+            .take(m)
+            .map(|sub| PQCodebook { centroids: sub.chunks(dsub.max(1)).map(<[f32]>::to_vec).collect(), subvector_dim: dsub })
+            .collect())
     }
     /// pq.rs:221-244
     pub fn encode(&self, vector: &[f32]) -> CoreResult<Vec<u16>> {

@@ -3,7 +3,7 @@
 this package is the host-side mirror of the reference interface.  No CPU fallback."""
 from .core import (Encoder, EncoderConfig, gemm_bf16_dev, CoreError, CsrGraph, CudaError, DimensionMismatch, DistanceMetric, EmptyCollection,
                    HnswConfig, HnswGraph, HnswNode, IndexNotBuilt, InMemoryEmbeddingProvider, InvalidArgument, InvalidConfig,
-                   LeannConfig, LeannIndex, NodeNotFound, PQConfig, PQError, ProductQuantizer,
+                   LeannConfig, LeannIndex, NodeNotFound, PQCodebook, PQConfig, PQError, ProductQuantizer,
                    PruningStrategy, SerializationError, merge_topk, merge_topk_dev, normalize_vector, normalized,
                    random_level, to_similarity)
 

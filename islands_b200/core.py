@@ -924,6 +924,27 @@ class PQConfig:
         return int(_ffi.load().isl_pq_config_bytes_per_vector(C.byref(self._s)))
 
 
+class PQCodebook:
+    """PQCodebook (pq.rs:66-112): the centroids of one subquantizer.  `find_nearest` runs on the device through a
+    one-subquantizer quantizer holding these centroids (strict `<` scan: the first of equal centroids wins)."""
+
+    def __init__(self, subvector_dim):
+        self.centroids = []
+        self.subvector_dim = int(subvector_dim)
+
+    def find_nearest(self, subvector, metric=DistanceMetric.Euclidean):
+        v = _f32(subvector).reshape(-1)
+        if v.size != self.subvector_dim:  # pq.rs:87-92, before any arithmetic
+            raise DimensionMismatch(f"dimension mismatch: expected {self.subvector_dim}, got {v.size}")
+        cb = _f32(self.centroids).reshape(1, len(self.centroids), self.subvector_dim)
+        pq = ProductQuantizer(self.subvector_dim, PQConfig(1, len(self.centroids), 1, None)).with_metric(metric)
+        pq.set_codebooks(cb)
+        return int(pq.encode(v)[0])
+
+    def get_centroid(self, idx):
+        return _f32(self.centroids[idx]) if 0 <= idx < len(self.centroids) else None
+
+
 class ProductQuantizer:
     """ProductQuantizer (pq.rs:116-359)."""
 
@@ -973,6 +994,12 @@ class ProductQuantizer:
         out = np.empty((m, k.value, self.dimension // m), np.float32)
         _check(_ffi.load().isl_pq_get_codebooks(self._h, _ptr(out, f32p), C.byref(k)))
         return out
+
+    def codebook(self, subquantizer):
+        """`codebooks[subquantizer]` (pq.rs:120-121) as a PQCodebook."""
+        cb = PQCodebook(self.dimension // self.num_subquantizers())
+        cb.centroids = list(self.codebooks()[subquantizer])
+        return cb
 
     def encode(self, vector):
         v = _f32(vector)

@@ -253,6 +253,20 @@ def test_kmeans_basic(orc):
     assert abs(xs[0] + 1.0) < 0.11 and abs(xs[1] - 1.0) < 0.11 and np.abs(cb[0, :, 1]).max() < 0.11
 
 
+def test_codebook_host_side():
+    """PQCodebook (pq.rs:66-112): construction, `get_centroid`, and the length check of `find_nearest` (pq.rs:87-92), which
+    precedes any arithmetic; the values of pq.rs:787-809 themselves are known answers of tests/test_oracle_kat.py (oracle)
+    and tests/test_pq_parity.py (GPU)."""
+    from islands_b200 import PQCodebook
+
+    cb = PQCodebook(4)
+    assert cb.centroids == [] and cb.subvector_dim == 4
+    cb.centroids = [[1.0, 0.0, 0.0, 0.0], [0.0, 1.0, 0.0, 0.0], [0.0, 0.0, 1.0, 0.0]]
+    assert cb.get_centroid(1).tolist() == [0.0, 1.0, 0.0, 0.0] and cb.get_centroid(3) is None
+    with pytest.raises(DimensionMismatch):
+        cb.find_nearest([0.9, 0.1, 0.0])
+
+
 # ---- search.rs --------------------------------------------------------------------------------------------------------
 
 def test_multi_index_searcher_empty():
